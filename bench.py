@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched inverse 4th roots of 1024x1024 Shampoo statistics.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host cores
+
+A "step" is one pass of the preconditioner-root hot path
+(`_matrix_inverse_pth_root_vmap`, DS:2742-2744) over one batch of synthetic SPD
+statistics.  With N GPUs (torchrun, one rank per GPU) every rank owns its own
+batch (weak scaling, blocks partitioned across ranks as DS:2862-2875 does) and
+the step ends with the all-gather of the roots over NCCL (DS:2876).
+
+Prints ONE JSON line (rank 0).  See the task contract for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "inverse_pth_roots_per_sec"
+UNIT = "roots/s"
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=3)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--n", type=int, default=1024, help="statistic size (block_size)")
+  ap.add_argument("--batch", type=int, default=64, help="statistics per GPU per step")
+  ap.add_argument("--p", type=int, default=4)
+  ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc6", "tc3"])
+  ap.add_argument("--cpu-sample", type=int, default=2,
+                  help="matrices in the bounded CPU-baseline sample")
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  return ap.parse_args()
+
+
+def workload_name(a):
+  return f"ema_lowrank_statistics_{a.n}x{a.n}_p{a.p}_batch{a.batch}_per_gpu"
+
+
+def make_statistics_torch(batch, n, seed, device):
+  """Synthetic SPD statistics: S0 = 1e-6 I; S <- 0.999 S + 0.001 G G^T, 20 steps of
+  G ~ N(0, 1) [n x n/32] (SURVEY 8(d) class (ii); DS:2594, DS:2635-2636).  The
+  accumulated Gram has rank 20 n/32 < n, so the spectrum has a 1e-6 floor and a
+  condition number ~1e6 like real early-training Shampoo statistics; the coupled
+  Newton iteration needs ~19 steps on it (vs ~6 for a well-conditioned Wishart)."""
+  import torch
+  gen = torch.Generator(device=device)
+  gen.manual_seed(seed)
+  out = torch.empty((batch, n, n), dtype=torch.float32, device=device)
+  eye = torch.eye(n, device=device, dtype=torch.float64)
+  for b in range(batch):
+    s = 1e-6 * eye
+    for _ in range(20):
+      g = torch.randn((n, max(n // 32, 1)), generator=gen, device=device,
+                      dtype=torch.float32).double()
+      s = 0.999 * s + 0.001 * (g @ g.T)
+    out[b] = s.float()
+  return out
+
+
+def make_statistics_numpy(batch, n, seed):
+  rng = np.random.default_rng(seed)
+  out = np.empty((batch, n, n), np.float32)
+  for b in range(batch):
+    s = 1e-6 * np.eye(n)
+    for _ in range(20):
+      g = rng.standard_normal((n, max(n // 32, 1))).astype(np.float32).astype(np.float64)
+      s = 0.999 * s + 0.001 * (g @ g.T)
+    out[b] = s.astype(np.float32)
+  return out
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+  FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+            "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index):
+    self.rows, self.proc = [], None
+    self.gpu = gpu_index
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+           "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([x.strip() for x in line.split(",")])
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx.append(float(r[2]))
+      except (ValueError, IndexError):
+        continue
+      for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                          "sw_power_cap"), r[5:9]):
+        if v.lower().startswith("active"):
+          reasons.add(name)
+    return {"sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm
+# ---------------------------------------------------------------------------
+def cpu_threads():
+  try:
+    from threadpoolctl import threadpool_info
+    n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+    return max(n) if n else (os.cpu_count() or 1)
+  except Exception:  # pylint: disable=broad-except
+    return os.cpu_count() or 1
+
+
+def time_cpu_port(a, sample, reps=1):
+  """Times the oracle's matrix_inverse_pth_root (reference algorithm incl. its
+  redundant mat_power products, DS:655-678) on `sample` matrices; roots/s."""
+  from oracle import numerics as N
+  xs = make_statistics_numpy(sample, a.n, seed=1234)
+  N.matrix_inverse_pth_root(xs[0][:64, :64].copy(), a.p)  # warm BLAS
+  best = None
+  iters = []
+  for _ in range(reps):
+    t0 = time.perf_counter()
+    for b in range(sample):
+      _, m = N.matrix_inverse_pth_root(xs[b], a.p, literal_mat_power=True)
+      iters.append(m.inverse_pth_root_iters)
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+  return sample / best, best, iters
+
+
+def run_reference(a):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  for _ in range(max(a.warmup, 0) and 1):
+    time_cpu_port(a, 1)
+  times = []
+  for _ in range(a.steps):
+    rps, dt, _ = time_cpu_port(a, a.cpu_sample)
+    times.append(dt)
+  dt = statistics.median(times)
+  value = a.cpu_sample / dt
+  cores = cpu_threads()
+  sample = (f"{a.cpu_sample} statistics of the same workload per step, numpy/BLAS oracle port of "
+            f"matrix_inverse_pth_root (JAX is not installable in this image)")
+  line = {
+      "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+      "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+      "data": "synthetic",
+      "config": {"workload": workload_name(a), "n": a.n, "p": a.p,
+                 "note": "reference algorithm on host cores; bounded sample per step"},
+      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": sample},
+      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(a):
+  import ctypes
+  import torch
+  import torch.distributed as dist
+  from precondition_b200 import _lib, ops
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  lib = _lib.load()
+  engine = {"auto": _lib.PC_ENGINE_AUTO, "simt": _lib.PC_ENGINE_SIMT_FP32,
+            "tc6": _lib.PC_ENGINE_TC_BF16X6, "tc3": _lib.PC_ENGINE_TC_BF16X3}[a.engine]
+
+  n, B = a.n, a.batch
+  xs = make_statistics_torch(B, n, seed=1000 + rank, device=dev)
+  ps = torch.full((B,), a.p, dtype=torch.int32, device=dev)
+  roots = torch.empty_like(xs)
+  gathered = torch.empty((world * B, n, n), dtype=torch.float32, device=dev) if world > 1 else None
+
+  def step():
+    r, m = ops.matrix_inverse_pth_root_batched(xs, ps, None, engine=engine, out=roots)
+    if world > 1:
+      dist.all_gather_into_tensor(gathered, r)  # DS:2876
+    return m
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(max(a.warmup, 3)):
+    metrics = step()
+  barrier()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  stats = _lib.Stats()
+  lib.pc_stats_reset(0)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for _ in range(a.steps):
+    metrics = step()
+  e1.record()
+  barrier()
+  lib.pc_stats_get(ctypes.byref(stats))
+  launches = int(stats.kernel_launches) + (a.steps if world > 1 else 0)
+  ms = e0.elapsed_time(e1)
+  t = torch.tensor([ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms = float(t.item())
+  clocks = sampler.stop() if rank == 0 else None
+  ms_per_step = ms / a.steps
+  value = world * B / (ms_per_step * 1e-3)
+
+  # ---- end-to-end through the C ABI with HOST buffers (pinned) ----
+  host_in = torch.empty((B, n, n), dtype=torch.float32).pin_memory()
+  host_in.copy_(xs.cpu())
+  host_out = torch.empty((B, n, n), dtype=torch.float32).pin_memory()
+  host_metrics = torch.empty((B, 5), dtype=torch.float32).pin_memory()
+  dev_in = torch.empty_like(xs)
+
+  def e2e_step():
+    dev_in.copy_(host_in, non_blocking=True)
+    r, m = ops.matrix_inverse_pth_root_batched(dev_in, ps, None, engine=engine, out=roots)
+    if world > 1:
+      dist.all_gather_into_tensor(gathered, r)
+    host_out.copy_(r, non_blocking=True)
+    host_metrics.copy_(m, non_blocking=True)
+
+  e2e_step()
+  barrier()
+  e0.record()
+  for _ in range(a.steps):
+    e2e_step()
+  e1.record()
+  barrier()
+  t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  e2e_ms = float(t.item()) / a.steps
+  e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
+         "h2d_bytes_per_step": int(B * n * n * 4), "d2h_bytes_per_step": int(B * n * n * 4 + B * 20),
+         "ms_per_step": e2e_ms}
+
+  # ---- roofline of the dominant kernel (Newton-chain GEMM launches): one extra
+  #      step with CUDA events around every GEMM launch on the launching stream ----
+  lib.pc_stats_reset(1)
+  metrics = step()
+  torch.cuda.synchronize()
+  lib.pc_stats_get(ctypes.byref(stats))
+  lib.pc_stats_reset(0)
+  peaks = {}
+  try:
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+  except (OSError, ValueError):
+    pass
+  peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+  peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
+  achieved = (stats.gemm_flops / (stats.gemm_ms * 1e-3) / 1e12) if stats.gemm_ms > 0 else 0.0
+  m_host = metrics.cpu().numpy()
+  resolved = "simt_fp32"
+  if engine in (_lib.PC_ENGINE_TC_BF16X6, _lib.PC_ENGINE_TC_BF16X3) or (
+      engine == _lib.PC_ENGINE_AUTO and lib.pc_device_supports_tcgen05() and n % 128 == 0
+      and n >= 256 and lib.pc_inverse_pth_root_workspace_bytes(1, n, 2) !=
+      lib.pc_inverse_pth_root_workspace_bytes(1, n, 1)):
+    resolved = "tcgen05_bf16x3" if engine == _lib.PC_ENGINE_TC_BF16X3 else "tcgen05_bf16x6"
+  passes = {"simt_fp32": 1, "tcgen05_bf16x6": 6, "tcgen05_bf16x3": 3}[resolved]
+  roofline = {
+      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+      "frac": achieved / peak if peak else None, "traffic": None,
+      "kernel": "newton_chain_gemm", "engine": resolved,
+      "algorithmic_flops_per_step": stats.gemm_flops, "gemm_ms_per_step": stats.gemm_ms,
+      "gemm_share_of_step": stats.gemm_ms / ms_per_step if ms_per_step else None,
+      "issued_passes": passes, "issued_tflops": achieved * passes, "peak_source": peak_src,
+  }
+
+  if rank == 0:
+    cpu_baseline = None
+    if not a.no_cpu_baseline and world == 1:
+      rps, dt, iters = time_cpu_port(a, a.cpu_sample)
+      cpu_baseline = {"value": rps, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                      "sample": f"{a.cpu_sample} of the {B} statistics' class "
+                                f"({dt:.2f} s; numpy/BLAS oracle port, JAX unavailable)",
+                      "iters": iters}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "n": n, "p": a.p, "batch_per_gpu": B,
+                   "engine": resolved, "l2": "inputs_exceed_l2" if B * n * n * 4 > 126e6 else
+                   "inputs_fit_l2", "sharding": f"blocks partitioned over {world} ranks + all_gather"
+                   if world > 1 else "single gpu",
+                   "newton_iters_mean": float(m_host[:, 1].mean()),
+                   "max_error": float(np.nanmax(m_host[:, 0]))},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches // 1,
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  a = parse_args()
+  if a.impl == "reference":
+    run_reference(a)
+  else:
+    run_ours(a)
+
+
+if __name__ == "__main__":
+  main()

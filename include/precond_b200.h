@@ -1,0 +1,204 @@
+/*
+ * precond_b200 -- C ABI of the B200-native Shampoo preconditioner hot path.
+ *
+ * Drop-in boundary for the device work of precondition.distributed_shampoo
+ * (reference: /root/reference/precondition/distributed_shampoo.py, "DS" below;
+ * quantization_utils.py = "QU").  The reference has no FFI of its own -- every
+ * entry point below replaces the jnp/XLA computation at the cited seam and is
+ * what a jax.ffi custom call (or ctypes, as precondition_b200/_lib.py does)
+ * binds.  See INTEGRATION.md for the reference-side stubs.
+ *
+ * Conventions
+ *   - plain C, raw DEVICE pointers, sizes as int/int64_t, a cudaStream_t (passed
+ *     as void*) on which all work is enqueued;
+ *   - return value: 0 = ok, <0 = invalid argument / CUDA error detected on the
+ *     host (pc_last_error() gives the message).  Numerical failure is NOT an
+ *     error: it is reported through the metrics rows exactly like the
+ *     reference's TrainingMetrics (DS:902-907) and acted on by the caller
+ *     (DS:2936-2950);
+ *   - the library owns no user memory: callers pass a workspace whose size comes
+ *     from the matching *_workspace_bytes query;
+ *   - matrices are row-major, contiguous, 16-byte aligned;
+ *   - pc_inverse_pth_root_batched synchronises `stream` internally while it
+ *     polls the device-side convergence flags (documented deviation from
+ *     "enqueue only").
+ */
+#ifndef PRECOND_B200_H_
+#define PRECOND_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PC_OK 0
+#define PC_ERR_INVALID (-1)
+#define PC_ERR_CUDA (-2)
+#define PC_ERR_WORKSPACE (-3)
+#define PC_ERR_UNSUPPORTED (-4)
+
+/* metrics row layout == TrainingMetrics scalar fields, DS:338-351 */
+#define PC_METRIC_ERROR 0       /* inverse_pth_root_errors */
+#define PC_METRIC_ITERS 1       /* inverse_pth_root_iters  */
+#define PC_METRIC_ERROR_RATIO 2 /* final_error_ratio       */
+#define PC_METRIC_MAX_EV 3      /* max_eigen_value         */
+#define PC_METRIC_RETRIES 4     /* total_retries           */
+#define PC_NUM_METRICS 5
+
+/* GEMM engine used by the Newton chain */
+#define PC_ENGINE_AUTO 0
+#define PC_ENGINE_SIMT_FP32 1 /* CUDA-core fp32 FFMA tiles (any n)              */
+#define PC_ENGINE_TC_BF16X6 2 /* tcgen05, bf16 3-way split, 6 products (~fp32)  */
+#define PC_ENGINE_TC_BF16X3 3 /* tcgen05, bf16 2-way split, 3 products (~2^-16) */
+
+/* quantised storage of statistics / preconditioners, QU:49-113 */
+#define PC_QDTYPE_F32 0
+#define PC_QDTYPE_INT16 1
+#define PC_QDTYPE_INT8 2
+#define PC_QDTYPE_BF16 3
+
+/* GraftingType, DS:499-506 */
+#define PC_GRAFT_NONE 0
+#define PC_GRAFT_SGD 1
+#define PC_GRAFT_ADAGRAD 2
+#define PC_GRAFT_RMSPROP 3
+#define PC_GRAFT_RMSPROP_NORMALIZED 4
+#define PC_GRAFT_SQRT_N 5
+#define PC_GRAFT_ADAGRAD_NORMALIZED 6
+
+int pc_version(void);
+const char* pc_last_error(void);
+/* 1 if the running device is sm_100 (tcgen05 engines usable). */
+int pc_device_supports_tcgen05(void);
+
+/* ------------------------------------------------------------------------
+ * instrumentation (bench.py): kernel-launch counter and, when enabled, CUDA-event
+ * timing of the Newton-chain GEMM launches on the caller's stream.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int64_t kernel_launches;   /* every kernel this library launched since reset  */
+  int64_t gemm_launches;     /* Newton-chain GEMM phase launches                 */
+  double gemm_ms;            /* sum of their durations (only if timing enabled)  */
+  double gemm_flops;         /* algorithmic flops of the executed GEMM tiles:
+                                2 n^3 per (matrix, step), summed on the host from
+                                the final iteration counts                       */
+} pc_stats;
+void pc_stats_reset(int enable_gemm_timing);
+void pc_stats_get(pc_stats* out);
+
+/* ------------------------------------------------------------------------
+ * (2) batched matrix_inverse_pth_root
+ * replaces: _matrix_inverse_pth_root_vmap (DS:2742-2744) =
+ *           jax.vmap(matrix_inverse_pth_root) (DS:702-940), incl. power_iteration
+ *           (DS:595-652), ridge damping (DS:830), coupled Newton (DS:836-885),
+ *           retry loop (DS:858-885), padding mask (DS:777-783, DS:930-937).
+ *   xs              [batch, n, n] f32   statistics (symmetric PSD)
+ *   ps              [batch] i32         exponents p (any p >= 1)
+ *   padding_starts  [batch] i32         rows/cols >= padding_start are padding
+ *                                       (pass n for "no padding"; may be NULL)
+ *   roots           [batch, n, n] f32   out: (A + eps I)^(-1/p), zeros in padding
+ *   metrics         [batch, 5] f32      out: PC_METRIC_* rows
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  float ridge_epsilon;         /* matrix_epsilon, DS:1855 (default 1e-6)       */
+  float error_tolerance;       /* DS:707 (default 1e-6)                        */
+  int num_iters;               /* DS:705 (default 100)                         */
+  int relative_matrix_epsilon; /* DS:1884 (default 1)                          */
+  int engine;                  /* PC_ENGINE_*                                  */
+  int reserved;
+} pc_root_options;
+
+void pc_root_options_default(pc_root_options* opt);
+
+size_t pc_inverse_pth_root_workspace_bytes(int batch, int n, int engine);
+
+int pc_inverse_pth_root_batched(const float* xs, const int32_t* ps,
+                                const int32_t* padding_starts, int batch, int n,
+                                const pc_root_options* opt, float* roots,
+                                float* metrics, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* power_iteration alone (DS:595-652): lambda[b] = Rayleigh quotient of the last
+ * executed step, iters[b] = steps taken (may be NULL). */
+int pc_power_iteration_batched(const float* xs, const int32_t* padding_starts,
+                               int batch, int n, int num_iters,
+                               float error_tolerance, float* lambdas,
+                               int32_t* iters, void* stream);
+
+/* ------------------------------------------------------------------------
+ * grouped GEMM with fused epilogue -- the building block behind (1) and (4):
+ *   C = alpha * op(A) op(B) + beta * C_in          (fp32, CUDA cores or tcgen05)
+ * replaces: jnp.tensordot in gram_weighted_update (DS:1468-1470) and in
+ *           _precondition_block (DS:1707).  One descriptor per block; operands
+ *           are addressed as  X(i, k) = base[i*s_i + (k / k_inner)*s_ko +
+ *           (k % k_inner)*s_ki]  so that every mode-k unfolding of a rank<=3
+ *           gradient block is a view (no jnp.split copies, DS:1412-1422).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  const float* a;    /* A(i,k), i in [0,M), k in [0,K) */
+  const float* b;    /* B(j,k), j in [0,N), k in [0,K)  (i.e. op(B)^T) */
+  const float* c_in; /* optional, addressed like c */
+  float* c;          /* C(i,j) = c[(i / c_iinner)*c_sio + (i % c_iinner)*c_sii + j] */
+  int64_t a_si, a_sko, a_ski;
+  int64_t b_sj, b_sko, b_ski;
+  int64_t c_sio, c_sii;
+  int32_t a_kinner, b_kinner, c_iinner;
+  int32_t m, n, k;
+  float alpha, beta;
+  int32_t reserved;
+} pc_gemm_desc;
+
+/* descs: DEVICE array of `count` descriptors; max_m/max_n bound the tile grid. */
+int pc_grouped_gemm(const pc_gemm_desc* descs, int count, int max_m, int max_n,
+                    void* stream);
+
+/* ------------------------------------------------------------------------
+ * (1b) QuantizedValue (QU:49-113) for square statistics / preconditioners with
+ *      extract_diagonal=True (DS:2087-2095) and for momenta (DS:2111-2114).
+ *   quantize:   x [rows, cols] f32 -> q (int16/int8/bf16), diag [rows] (if
+ *               extract_diagonal), bucket [cols]; per-COLUMN max-abs (QU:86).
+ *   dequantize: inverse (QU:97-113).
+ *   `batch` independent matrices, contiguous.
+ * ------------------------------------------------------------------------ */
+int pc_quantize_batched(const float* x, int batch, int rows, int cols, int qdtype,
+                        int extract_diagonal, void* q, float* diag, float* bucket,
+                        void* stream);
+int pc_dequantize_batched(const void* q, const float* diag, const float* bucket,
+                          int batch, int rows, int cols, int qdtype,
+                          int extract_diagonal, float* x, void* stream);
+
+/* ------------------------------------------------------------------------
+ * (4) grafting + momentum tail of _transform_grad (DS:3496-3625) for one
+ *     parameter tensor of `numel` elements.  precond_grad is the output of the
+ *     preconditioner application (DS:3553-3556) or NULL when the parameter is
+ *     skipped (DS:3557-3561).  Momenta / diagonal statistics are f32 here; int8
+ *     momenta go through pc_(de)quantize_batched.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  double beta1, beta2; /* as Python floats: 1 - beta is formed in double, DS:3522, DS:3579 */
+  int graft_type;
+  float diagonal_epsilon;
+  float weight_decay;
+  float learning_rate; /* already evaluated at this step, DS:3545-3547 */
+  int nesterov;
+  int moving_average_for_momentum;
+  int decoupled_learning_rate;
+  int decoupled_weight_decay;
+  int run_shampoo;                  /* step >= start_preconditioning_step, DS:3588 */
+  float clip_by_scaled_gradient_norm; /* <=0: disabled, DS:3530 */
+} pc_graft_options;
+
+size_t pc_graft_momentum_workspace_bytes(int64_t numel);
+
+int pc_graft_momentum(const float* grad, const float* param,
+                      const float* precond_grad, float* diagonal_statistics,
+                      float* diagonal_momentum, float* momentum, float* update,
+                      int64_t numel, const pc_graft_options* opt, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRECOND_B200_H_ */

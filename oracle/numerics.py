@@ -101,6 +101,21 @@ def mat_power(mat_m: np.ndarray, p: int) -> np.ndarray:
   return power
 
 
+def mat_power_literal(mat_m: np.ndarray, p: int) -> np.ndarray:
+  """DS:655-678 with every product the reference issues (the multiply by the
+  identity and the discarded last squaring included) -- same values as
+  ``mat_power``; used when timing the reference algorithm on the CPU."""
+  power = np.eye(mat_m.shape[0], dtype=mat_m.dtype)
+  mat = mat_m
+  i = int(p)
+  while i > 0:
+    if i % 2 == 1:
+      power = mat @ power
+    i //= 2
+    mat = mat @ mat
+  return power
+
+
 # --------------------------------------------------------------------------
 # matrix_inverse_pth_root, coupled Newton branch  (DS:702-940)
 # --------------------------------------------------------------------------
@@ -114,6 +129,7 @@ def matrix_inverse_pth_root(
     padding_start: Optional[int] = None,
     dtype=np.float32,
     trace: Optional[list] = None,
+    literal_mat_power: bool = False,
 ) -> Tuple[np.ndarray, RootMetrics]:
   """(A + eps I)^(-1/p) by the coupled Newton iteration, DS:702-940.
 
@@ -162,7 +178,8 @@ def matrix_inverse_pth_root(
       i = 0
       while i < num_iters and err > tol and ratio < max_error_ratio:  # DS:836-840
         mat_m_i = (f(1) - alpha) * identity + alpha * mat_m  # DS:844
-        new_m = mat_power(mat_m_i, p) @ mat_m  # DS:845
+        new_m = (mat_power_literal if literal_mat_power else mat_power)(
+            mat_m_i, p) @ mat_m  # DS:845
         new_h = mat_h @ mat_m_i  # DS:846
         new_err = np.max(np.abs(new_m - identity))  # DS:847
         ratio = new_err / err

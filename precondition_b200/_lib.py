@@ -1,0 +1,124 @@
+"""ctypes binding of libprecond_b200.so (the C ABI in include/precond_b200.h).
+
+There is NO fallback: if the shared library is missing or no CUDA device is
+present, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libprecond_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+PC_ENGINE_AUTO, PC_ENGINE_SIMT_FP32, PC_ENGINE_TC_BF16X6, PC_ENGINE_TC_BF16X3 = 0, 1, 2, 3
+PC_QDTYPE_F32, PC_QDTYPE_INT16, PC_QDTYPE_INT8, PC_QDTYPE_BF16 = 0, 1, 2, 3
+PC_NUM_METRICS = 5
+
+EXPORTED_SYMBOLS = (
+    "pc_version", "pc_last_error", "pc_device_supports_tcgen05", "pc_stats_reset",
+    "pc_stats_get",
+    "pc_root_options_default", "pc_inverse_pth_root_workspace_bytes",
+    "pc_inverse_pth_root_batched", "pc_power_iteration_batched", "pc_grouped_gemm",
+    "pc_quantize_batched", "pc_dequantize_batched",
+    "pc_graft_momentum_workspace_bytes", "pc_graft_momentum",
+)
+
+
+class RootOptions(ctypes.Structure):
+  _fields_ = [("ridge_epsilon", ctypes.c_float), ("error_tolerance", ctypes.c_float),
+              ("num_iters", ctypes.c_int), ("relative_matrix_epsilon", ctypes.c_int),
+              ("engine", ctypes.c_int), ("reserved", ctypes.c_int)]
+
+
+class Stats(ctypes.Structure):
+  _fields_ = [("kernel_launches", ctypes.c_int64), ("gemm_launches", ctypes.c_int64),
+              ("gemm_ms", ctypes.c_double), ("gemm_flops", ctypes.c_double)]
+
+
+class GemmDesc(ctypes.Structure):
+  _fields_ = [("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("c_in", ctypes.c_void_p),
+              ("c", ctypes.c_void_p),
+              ("a_si", ctypes.c_int64), ("a_sko", ctypes.c_int64), ("a_ski", ctypes.c_int64),
+              ("b_sj", ctypes.c_int64), ("b_sko", ctypes.c_int64), ("b_ski", ctypes.c_int64),
+              ("c_sio", ctypes.c_int64), ("c_sii", ctypes.c_int64),
+              ("a_kinner", ctypes.c_int32), ("b_kinner", ctypes.c_int32),
+              ("c_iinner", ctypes.c_int32),
+              ("m", ctypes.c_int32), ("n", ctypes.c_int32), ("k", ctypes.c_int32),
+              ("alpha", ctypes.c_float), ("beta", ctypes.c_float),
+              ("reserved", ctypes.c_int32)]
+
+
+class GraftOptions(ctypes.Structure):
+  _fields_ = [("beta1", ctypes.c_double), ("beta2", ctypes.c_double),
+              ("graft_type", ctypes.c_int), ("diagonal_epsilon", ctypes.c_float),
+              ("weight_decay", ctypes.c_float), ("learning_rate", ctypes.c_float),
+              ("nesterov", ctypes.c_int), ("moving_average_for_momentum", ctypes.c_int),
+              ("decoupled_learning_rate", ctypes.c_int),
+              ("decoupled_weight_decay", ctypes.c_int), ("run_shampoo", ctypes.c_int),
+              ("clip_by_scaled_gradient_norm", ctypes.c_float)]
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+  """Compiles the CUDA library in-tree for sm_100a (nvcc cross-compiles on CPU)."""
+  out = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+  if verbose or out.returncode != 0:
+    print(out.stdout[-4000:])
+    print(out.stderr[-4000:])
+  if out.returncode != 0:
+    raise RuntimeError("building libprecond_b200.so failed")
+  return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+  """Loads the library (no CUDA call is made here)."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise RuntimeError(
+        f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(precondition_b200 has no CPU or PyTorch fallback)")
+  lib = ctypes.CDLL(LIB_PATH)
+  vp, i32, i64, f32, sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float,
+                           ctypes.c_size_t)
+  lib.pc_version.restype = i32
+  lib.pc_last_error.restype = ctypes.c_char_p
+  lib.pc_device_supports_tcgen05.restype = i32
+  lib.pc_stats_reset.argtypes = [i32]
+  lib.pc_stats_reset.restype = None
+  lib.pc_stats_get.argtypes = [ctypes.POINTER(Stats)]
+  lib.pc_stats_get.restype = None
+  lib.pc_root_options_default.argtypes = [ctypes.POINTER(RootOptions)]
+  lib.pc_root_options_default.restype = None
+  lib.pc_inverse_pth_root_workspace_bytes.argtypes = [i32, i32, i32]
+  lib.pc_inverse_pth_root_workspace_bytes.restype = sz
+  lib.pc_inverse_pth_root_batched.argtypes = [vp, vp, vp, i32, i32,
+                                              ctypes.POINTER(RootOptions), vp, vp, vp, sz, vp]
+  lib.pc_inverse_pth_root_batched.restype = i32
+  lib.pc_power_iteration_batched.argtypes = [vp, vp, i32, i32, i32, f32, vp, vp, vp]
+  lib.pc_power_iteration_batched.restype = i32
+  lib.pc_grouped_gemm.argtypes = [vp, i32, i32, i32, vp]
+  lib.pc_grouped_gemm.restype = i32
+  lib.pc_quantize_batched.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+  lib.pc_quantize_batched.restype = i32
+  lib.pc_dequantize_batched.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
+  lib.pc_dequantize_batched.restype = i32
+  lib.pc_graft_momentum_workspace_bytes.argtypes = [i64]
+  lib.pc_graft_momentum_workspace_bytes.restype = sz
+  lib.pc_graft_momentum.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64,
+                                    ctypes.POINTER(GraftOptions), vp, sz, vp]
+  lib.pc_graft_momentum.restype = i32
+  _lib = lib
+  return lib
+
+
+def check(rc: int):
+  if rc != 0:
+    msg = load().pc_last_error().decode("utf-8", "replace")
+    raise RuntimeError(f"precond_b200 error {rc}: {msg}")

@@ -1,0 +1,215 @@
+// Grafting + momentum tail of _transform_grad (DS:3496-3625) for one parameter
+// tensor: memory-bound, vectorised, two global norms -> reduce-then-apply.
+//
+// Algorithmic traffic (SGD graft, f32 momenta, no weight decay): read grad,
+// precond_grad, both momenta; write update, both momenta = 28 B / element
+// (+ one extra read of grad and precond_grad for the norm pass).
+#include "common.cuh"
+
+namespace pc {
+
+constexpr int kGraftThreads = 256;
+constexpr int kGraftMaxBlocks = 148 * 8;
+
+struct GraftArgs {
+  const float* grad;
+  const float* param;
+  const float* precond;  // may be null -> precond_grad = grafting_update (DS:3561)
+  float* diag;           // diagonal_statistics (in/out), null for SGD-like grafts
+  float* dmom;           // diagonal_momentum (in/out)
+  float* mom;            // momentum (in/out)
+  float* update;
+  int64_t numel;
+  pc_graft_options o;
+  float beta1f, beta2f;
+  float w2;              // (beta2 == 1 ? beta2 : 1 - beta2), DS:3522
+  float lr_mult;         // lr if !decoupled_learning_rate else 1, DS:3549
+  // reduction scratch
+  float* part_g;   // partial sums of grad^2
+  float* part_r;   // partial sums of raw graft^2 (clip)
+  float* part_gr;  // partial sums of final graft^2
+  float* part_p;   // partial sums of precond^2
+  int nblocks;
+};
+
+__device__ __forceinline__ bool has_diag(int t) {
+  return t == PC_GRAFT_ADAGRAD || t == PC_GRAFT_ADAGRAD_NORMALIZED || t == PC_GRAFT_RMSPROP ||
+         t == PC_GRAFT_RMSPROP_NORMALIZED;
+}
+__device__ __forceinline__ bool is_normalized(int t) {
+  return t == PC_GRAFT_ADAGRAD_NORMALIZED || t == PC_GRAFT_RMSPROP_NORMALIZED;
+}
+
+// deterministic total of per-block partials (every block recomputes the same value)
+__device__ float total_of(const float* part, int n, float* scratch) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  return block_sum(s, scratch);
+}
+
+// raw grafting update before clipping / lr multiplier (DS:3502-3543)
+__device__ __forceinline__ float graft_raw(const GraftArgs& a, float g, float gdenom,
+                                           float diag_old, float* diag_new) {
+  const int t = a.o.graft_type;
+  float sg = g;
+  if (is_normalized(t)) sg = g / gdenom;
+  if (t == PC_GRAFT_ADAGRAD || t == PC_GRAFT_ADAGRAD_NORMALIZED) {
+    const float nd = diag_old + sg * sg;
+    *diag_new = nd;
+    return sg / (sqrtf(nd) + a.o.diagonal_epsilon);
+  }
+  if (t == PC_GRAFT_RMSPROP || t == PC_GRAFT_RMSPROP_NORMALIZED) {
+    const float nd = a.beta2f * diag_old + a.w2 * (sg * sg);
+    *diag_new = nd;
+    return sg / (sqrtf(nd) + a.o.diagonal_epsilon);
+  }
+  *diag_new = diag_old;
+  if (t == PC_GRAFT_SQRT_N) return g > 0.f ? 1.f : (g < 0.f ? -1.f : (g == 0.f ? 0.f : g));
+  return g;  // SGD, NONE
+}
+
+__device__ __forceinline__ float clip_denom_of(const GraftArgs& a, float sum_raw_sq) {
+  // DS:3530-3535
+  const float norm = sqrtf(sum_raw_sq) / sqrtf((float)a.numel);
+  return fmaxf(1.f, norm / a.o.clip_by_scaled_gradient_norm);
+}
+
+template <int STAGE>  // 0: sum grad^2; 1: sum raw^2; 2: sum graft^2 and precond^2
+__global__ void __launch_bounds__(kGraftThreads) graft_reduce_kernel(GraftArgs a) {
+  __shared__ float scratch[32];
+  float gdenom = 1.f, cdenom = 1.f;
+  if (STAGE >= 1 && is_normalized(a.o.graft_type))
+    gdenom = sqrtf(total_of(a.part_g, a.nblocks, scratch)) + 1e-25f;
+  const bool clip = a.o.clip_by_scaled_gradient_norm > 0.f &&
+                    (a.o.graft_type == PC_GRAFT_RMSPROP ||
+                     a.o.graft_type == PC_GRAFT_RMSPROP_NORMALIZED);
+  if (STAGE == 2 && clip) cdenom = clip_denom_of(a, total_of(a.part_r, a.nblocks, scratch));
+  float s0 = 0.f, s1 = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.numel;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const float g = a.grad[e];
+    if (STAGE == 0) {
+      s0 = fmaf(g, g, s0);
+    } else {
+      float nd;
+      float r = graft_raw(a, g, gdenom, a.diag ? a.diag[e] : 0.f, &nd);
+      if (STAGE == 1) {
+        s0 = fmaf(r, r, s0);
+      } else {
+        if (clip) r = r / cdenom;
+        r = r * a.lr_mult;
+        s0 = fmaf(r, r, s0);
+        const float pg = a.precond ? a.precond[e] : r;
+        s1 = fmaf(pg, pg, s1);
+      }
+    }
+  }
+  s0 = block_sum(s0, scratch);
+  if (STAGE == 2) s1 = block_sum(s1, scratch);
+  if (threadIdx.x == 0) {
+    if (STAGE == 0) a.part_g[blockIdx.x] = s0;
+    if (STAGE == 1) a.part_r[blockIdx.x] = s0;
+    if (STAGE == 2) { a.part_gr[blockIdx.x] = s0; a.part_p[blockIdx.x] = s1; }
+  }
+}
+
+__global__ void __launch_bounds__(kGraftThreads) graft_apply_kernel(GraftArgs a) {
+  __shared__ float scratch[32];
+  const pc_graft_options& o = a.o;
+  float gdenom = 1.f, cdenom = 1.f;
+  if (is_normalized(o.graft_type))
+    gdenom = sqrtf(total_of(a.part_g, a.nblocks, scratch)) + 1e-25f;
+  const bool clip = o.clip_by_scaled_gradient_norm > 0.f &&
+                    (o.graft_type == PC_GRAFT_RMSPROP ||
+                     o.graft_type == PC_GRAFT_RMSPROP_NORMALIZED);
+  if (clip) cdenom = clip_denom_of(a, total_of(a.part_r, a.nblocks, scratch));
+  const float gnorm = sqrtf(total_of(a.part_gr, a.nblocks, scratch));  // DS:3563
+  const float pnorm = sqrtf(total_of(a.part_p, a.nblocks, scratch));   // DS:3564
+  const float mult = o.graft_type != PC_GRAFT_NONE ? gnorm / (pnorm + 1e-25f) : 1.f;
+  const float w = o.moving_average_for_momentum ? (float)(1.0 - o.beta1) : 1.f;
+  const float run = o.run_shampoo ? 1.f : 0.f;
+  const bool coupled_wd = o.weight_decay != 0.f && !o.decoupled_weight_decay;
+  const bool decoupled_wd = o.weight_decay != 0.f && o.decoupled_weight_decay;
+  const float wd_lr = o.decoupled_learning_rate ? 1.f : o.learning_rate;
+  const float mom_mult = o.decoupled_learning_rate ? o.learning_rate : 1.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.numel;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const float g = a.grad[e];
+    float nd;
+    float graft = graft_raw(a, g, gdenom, a.diag ? a.diag[e] : 0.f, &nd);
+    if (clip) graft = graft / cdenom;
+    graft = graft * a.lr_mult;
+    const float pg = a.precond ? a.precond[e] : graft;
+    const float shampoo = pg * mult;                                   // DS:3570
+    float shampoo_wd = shampoo, graft_wd = graft;
+    const float prm = (coupled_wd || decoupled_wd) ? a.param[e] : 0.f;
+    if (coupled_wd) {                                                  // DS:3575-3577
+      shampoo_wd = shampoo + o.weight_decay * prm;
+      graft_wd = graft + o.weight_decay * prm;
+    }
+    const float shampoo_m = a.mom[e] * a.beta1f + w * shampoo_wd;       // DS:3581-3582
+    const float graft_m = a.dmom[e] * a.beta1f + w * graft_wd;          // DS:3584-3586
+    const float mom = run * shampoo_m + (1.f - run) * graft_m;         // DS:3591-3593
+    const float wdu = run * shampoo_wd + (1.f - run) * graft_wd;       // DS:3595-3597
+    float nest = o.nesterov ? (w * wdu + a.beta1f * mom) : mom;         // DS:3601-3602
+    if (decoupled_wd) nest = nest + wd_lr * o.weight_decay * prm;      // DS:3604-3608
+    a.update[e] = -1.0f * mom_mult * nest;                             // DS:3610-3611
+    a.dmom[e] = graft_m;
+    a.mom[e] = shampoo_m;
+    if (a.diag) a.diag[e] = nd;
+  }
+}
+
+}  // namespace pc
+
+extern "C" {
+
+size_t pc_graft_momentum_workspace_bytes(int64_t numel) {
+  (void)numel;
+  return 4 * pc::kGraftMaxBlocks * sizeof(float) + 256;
+}
+
+int pc_graft_momentum(const float* grad, const float* param, const float* precond_grad,
+                      float* diagonal_statistics, float* diagonal_momentum, float* momentum,
+                      float* update, int64_t numel, const pc_graft_options* opt,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(numel >= 0, "negative numel");
+  if (numel == 0) return PC_OK;
+  PC_REQUIRE(grad && diagonal_momentum && momentum && update && opt && workspace,
+             "null pointer argument");
+  PC_REQUIRE(workspace_bytes >= pc_graft_momentum_workspace_bytes(numel), "workspace too small");
+  PC_REQUIRE(opt->graft_type >= PC_GRAFT_NONE && opt->graft_type <= PC_GRAFT_ADAGRAD_NORMALIZED,
+             "unknown graft_type %d", opt->graft_type);
+  const bool diag = opt->graft_type == PC_GRAFT_ADAGRAD || opt->graft_type == PC_GRAFT_RMSPROP ||
+                    opt->graft_type == PC_GRAFT_RMSPROP_NORMALIZED ||
+                    opt->graft_type == PC_GRAFT_ADAGRAD_NORMALIZED;
+  PC_REQUIRE(!diag || diagonal_statistics, "graft type needs diagonal_statistics");
+  PC_REQUIRE(opt->weight_decay == 0.f || param, "weight decay needs param");
+  pc::GraftArgs a;
+  a.grad = grad; a.param = param; a.precond = precond_grad;
+  a.diag = diag ? diagonal_statistics : nullptr;
+  a.dmom = diagonal_momentum; a.mom = momentum; a.update = update; a.numel = numel;
+  a.o = *opt;
+  a.beta1f = (float)opt->beta1; a.beta2f = (float)opt->beta2;
+  a.w2 = opt->beta2 == 1.0 ? 1.0f : (float)(1.0 - opt->beta2);
+  a.lr_mult = opt->decoupled_learning_rate ? 1.0f : opt->learning_rate;
+  float* w = reinterpret_cast<float*>(pc::align_up((size_t)workspace, 256));
+  a.part_g = w; a.part_r = w + pc::kGraftMaxBlocks; a.part_gr = w + 2 * pc::kGraftMaxBlocks;
+  a.part_p = w + 3 * pc::kGraftMaxBlocks;
+  int64_t want = (numel + pc::kGraftThreads * 4 - 1) / (pc::kGraftThreads * 4);
+  a.nblocks = (int)(want < 1 ? 1 : (want > pc::kGraftMaxBlocks ? pc::kGraftMaxBlocks : want));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool normalized = opt->graft_type == PC_GRAFT_ADAGRAD_NORMALIZED ||
+                          opt->graft_type == PC_GRAFT_RMSPROP_NORMALIZED;
+  const bool clip = opt->clip_by_scaled_gradient_norm > 0.f &&
+                    (opt->graft_type == PC_GRAFT_RMSPROP ||
+                     opt->graft_type == PC_GRAFT_RMSPROP_NORMALIZED);
+  if (normalized) pc::graft_reduce_kernel<0><<<a.nblocks, pc::kGraftThreads, 0, st>>>(a);
+  if (clip) pc::graft_reduce_kernel<1><<<a.nblocks, pc::kGraftThreads, 0, st>>>(a);
+  pc::graft_reduce_kernel<2><<<a.nblocks, pc::kGraftThreads, 0, st>>>(a);
+  pc::graft_apply_kernel<<<a.nblocks, pc::kGraftThreads, 0, st>>>(a);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+}  // extern "C"

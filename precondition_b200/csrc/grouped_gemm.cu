@@ -1,0 +1,48 @@
+// Grouped GEMM over strided views (statistics update, preconditioner apply):
+//   C = alpha * A B^T-view + beta * C_in   -- see pc_gemm_desc in the header.
+// Replaces jnp.tensordot at DS:1468-1470 and DS:1707 (fp32, CUDA cores).
+#include "simt_gemm.cuh"
+
+namespace pc {
+
+__global__ void __launch_bounds__(kSimtThreads)
+grouped_gemm_simt_kernel(const pc_gemm_desc* __restrict__ descs) {
+  __shared__ SimtSmem sm;
+  const pc_gemm_desc d = descs[blockIdx.z];
+  const int tile_m = blockIdx.y, tile_n = blockIdx.x;
+  if (tile_m * kSimtBM >= d.m || tile_n * kSimtBN >= d.n) return;
+  const OperandView A{d.a, d.a_si, d.a_sko, d.a_ski, d.a_kinner, d.m, d.k};
+  const OperandView B{d.b, d.b_sj, d.b_sko, d.b_ski, d.b_kinner, d.n, d.k};
+  simt_gemm_tile(d.k, tile_m, tile_n, A, B, A.k_fast(), B.k_fast(), sm,
+                 [&](int i, int j0, const float* acc) {
+                   if (i >= d.m) return;
+                   const int io = i / d.c_iinner, ii = i - io * d.c_iinner;
+                   const int64_t row = io * d.c_sio + ii * d.c_sii;
+#pragma unroll
+                   for (int q = 0; q < 4; ++q) {
+                     const int j = j0 + q;
+                     if (j >= d.n) continue;
+                     float v = d.alpha * acc[q];
+                     if (d.c_in) v = fmaf(d.beta, d.c_in[row + j], v);
+                     d.c[row + j] = v;
+                   }
+                 });
+}
+
+}  // namespace pc
+
+extern "C" int pc_grouped_gemm(const pc_gemm_desc* descs, int count, int max_m, int max_n,
+                               void* stream) {
+  PC_REQUIRE(count >= 0 && max_m >= 0 && max_n >= 0, "bad grouped gemm sizes");
+  if (count == 0 || max_m == 0 || max_n == 0) return PC_OK;
+  PC_REQUIRE(descs != nullptr, "null descriptor array");
+  const int tm = (max_m + pc::kSimtBM - 1) / pc::kSimtBM;
+  const int tn = (max_n + pc::kSimtBN - 1) / pc::kSimtBN;
+  for (int z0 = 0; z0 < count; z0 += 65535) {
+    const int nz = count - z0 < 65535 ? count - z0 : 65535;
+    dim3 grid(tn, tm, nz);
+    pc::grouped_gemm_simt_kernel<<<grid, pc::kSimtThreads, 0, (cudaStream_t)stream>>>(descs + z0);
+  }
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}

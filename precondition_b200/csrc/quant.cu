@@ -1,0 +1,154 @@
+// QuantizedValue (QU:49-113) on device: per-column symmetric bucket quantisation
+// to int16 / int8 with optional diagonal extraction, and bf16 casts.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace pc {
+
+template <typename Q>
+__device__ __forceinline__ Q to_q(float r);
+template <>
+__device__ __forceinline__ int16_t to_q<int16_t>(float r) { return (int16_t)r; }
+template <>
+__device__ __forceinline__ int8_t to_q<int8_t>(float r) { return (int8_t)r; }
+
+// grid (ceil(cols/32), batch); block (32, 8): each warp-row strides over rows so
+// that global reads are coalesced along the column index.
+template <typename Q>
+__global__ void __launch_bounds__(256)
+quantize_kernel(const float* __restrict__ x, int rows, int cols, float num_buckets,
+                int extract_diagonal, Q* __restrict__ q, float* __restrict__ diag,
+                float* __restrict__ bucket) {
+  __shared__ uint32_t smax[8][32];
+  const int b = blockIdx.y;
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const float* xb = x + (size_t)b * rows * cols;
+  Q* qb = q + (size_t)b * rows * cols;
+  uint32_t m = 0;
+  if (col < cols) {
+    for (int r = threadIdx.y; r < rows; r += 8) {
+      float v = xb[(size_t)r * cols + col];
+      if (extract_diagonal && r == col) {  // QU:72-76
+        diag[(size_t)b * rows + r] = v;
+        v = v - v;                        // fvalue - diag(fvalue): NaN/inf stay non-finite
+      }
+      const uint32_t ab = absbits(v);
+      m = ab > m ? ab : m;
+    }
+  }
+  smax[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int k = 1; k < 8; ++k) m = smax[k][threadIdx.x] > m ? smax[k][threadIdx.x] : m;
+    smax[0][threadIdx.x] = m;
+  }
+  __syncthreads();
+  if (col >= cols) return;
+  const float max_abs = __uint_as_float(smax[0][threadIdx.x]);  // QU:86
+  const float bs = max_abs / num_buckets;                       // QU:87
+  const float bs_nz = bs > 0.f ? bs : 1.f;                      // QU:90-91
+  if (threadIdx.y == 0) bucket[(size_t)b * cols + col] = bs;
+  for (int r = threadIdx.y; r < rows; r += 8) {
+    float v = xb[(size_t)r * cols + col];
+    if (extract_diagonal && r == col) v = v - v;
+    qb[(size_t)r * cols + col] = to_q<Q>(rintf(v / bs_nz));     // QU:92-95
+  }
+}
+
+template <typename Q>
+__global__ void dequantize_kernel(const Q* __restrict__ q, const float* __restrict__ diag,
+                                  const float* __restrict__ bucket, int rows, int cols,
+                                  int extract_diagonal, float* __restrict__ x) {
+  const int b = blockIdx.y;
+  const size_t total = (size_t)rows * cols;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / cols), c = (int)(e - (size_t)r * cols);
+    float v = (float)q[(size_t)b * total + e] * bucket[(size_t)b * cols + c];  // QU:110
+    if (extract_diagonal && r == c) v += diag[(size_t)b * rows + r];           // QU:111-112
+    x[(size_t)b * total + e] = v;
+  }
+}
+
+__global__ void to_bf16_kernel(const float* __restrict__ x, size_t total,
+                               __nv_bfloat16* __restrict__ q) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x)
+    q[e] = __float2bfloat16_rn(x[e]);
+}
+__global__ void from_bf16_kernel(const __nv_bfloat16* __restrict__ q, size_t total,
+                                 float* __restrict__ x) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x)
+    x[e] = __bfloat162float(q[e]);
+}
+
+}  // namespace pc
+
+extern "C" {
+
+int pc_quantize_batched(const float* x, int batch, int rows, int cols, int qdtype,
+                        int extract_diagonal, void* q, float* diag, float* bucket,
+                        void* stream) {
+  PC_REQUIRE(batch >= 0 && rows >= 0 && cols >= 0, "bad sizes");
+  if (batch == 0 || rows == 0 || cols == 0) return PC_OK;
+  PC_REQUIRE(x && q, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)batch * rows * cols;
+  if (qdtype == PC_QDTYPE_BF16) {
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    pc::to_bf16_kernel<<<blocks, 256, 0, st>>>(x, total, (__nv_bfloat16*)q);
+    PC_CUDA_CHECK(cudaGetLastError());
+    return PC_OK;
+  }
+  PC_REQUIRE(qdtype == PC_QDTYPE_INT16 || qdtype == PC_QDTYPE_INT8,
+             "Quantized dtype %d not supported.", qdtype);
+  PC_REQUIRE(bucket != nullptr, "bucket output required");
+  PC_REQUIRE(!extract_diagonal || (diag != nullptr && rows == cols),
+             "extract_diagonal needs a square matrix and a diagonal output");
+  dim3 grid((cols + 31) / 32, batch), block(32, 8);
+  if (qdtype == PC_QDTYPE_INT16)
+    pc::quantize_kernel<int16_t><<<grid, block, 0, st>>>(x, rows, cols, 32767.f,
+                                                        extract_diagonal, (int16_t*)q, diag,
+                                                        bucket);
+  else
+    pc::quantize_kernel<int8_t><<<grid, block, 0, st>>>(x, rows, cols, 127.f,
+                                                       extract_diagonal, (int8_t*)q, diag,
+                                                       bucket);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+int pc_dequantize_batched(const void* q, const float* diag, const float* bucket, int batch,
+                          int rows, int cols, int qdtype, int extract_diagonal, float* x,
+                          void* stream) {
+  PC_REQUIRE(batch >= 0 && rows >= 0 && cols >= 0, "bad sizes");
+  if (batch == 0 || rows == 0 || cols == 0) return PC_OK;
+  PC_REQUIRE(x && q, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)batch * rows * cols;
+  if (qdtype == PC_QDTYPE_BF16) {
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    pc::from_bf16_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)q, total, x);
+    PC_CUDA_CHECK(cudaGetLastError());
+    return PC_OK;
+  }
+  PC_REQUIRE(qdtype == PC_QDTYPE_INT16 || qdtype == PC_QDTYPE_INT8,
+             "Quantized dtype %d not supported.", qdtype);
+  PC_REQUIRE(bucket != nullptr, "bucket required");
+  PC_REQUIRE(!extract_diagonal || (diag != nullptr && rows == cols),
+             "extract_diagonal needs a square matrix and a diagonal");
+  const size_t per = (size_t)rows * cols;
+  dim3 grid((unsigned)((per + 255) / 256 < 1024 ? (per + 255) / 256 : 1024), batch);
+  if (qdtype == PC_QDTYPE_INT16)
+    pc::dequantize_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)q, diag, bucket, rows,
+                                                        cols, extract_diagonal, x);
+  else
+    pc::dequantize_kernel<int8_t><<<grid, 256, 0, st>>>((const int8_t*)q, diag, bucket, rows,
+                                                       cols, extract_diagonal, x);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+}  // extern "C"

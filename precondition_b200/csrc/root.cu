@@ -1,0 +1,687 @@
+// Batched matrix_inverse_pth_root (DS:702-940): power iteration, ridge damping,
+// coupled Newton iteration with on-device convergence / retry state machine.
+// GEMM chain engines: CUDA-core fp32 (this file) and tcgen05 split-bf16
+// (tc_gemm.cu), both behind the same per-matrix step programs.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "root_common.cuh"
+#include "simt_gemm.cuh"
+#include "tc_engine.cuh"
+
+namespace pc {
+
+// ---------------------------------------------------------------------------
+// step programs
+// ---------------------------------------------------------------------------
+bool build_program(int p, Program* out) {
+  memset(out, 0, sizeof(*out));
+  if (p < 1 || p > kMaxP) return false;
+  bool used[4] = {false, false, false, false};
+  auto alloc = [&]() -> int {
+    for (int q = 0; q < 4; ++q)
+      if (!used[q]) { used[q] = true; return LB_Q0 + q; }
+    return -100;
+  };
+  int mat = LB_D, power = LB_NONE, n = 0;
+  auto release_if_unreferenced = [&](int buf) {
+    if (buf >= LB_Q0 && buf != mat && buf != power) used[buf - LB_Q0] = false;
+  };
+  auto push = [&](Step s) -> bool {
+    if (n >= kMaxSteps) return false;
+    out->steps[n++] = s;
+    return true;
+  };
+  int i = p;
+  while (i > 0) {
+    if (i & 1) {
+      if (power == LB_NONE) {
+        power = mat;  // multiply by the identity (DS:661, DS:670-672)
+      } else {
+        int dst = alloc();
+        if (dst < 0) return false;
+        // dev(mat * power) = mat + power + mat*power
+        if (!push(Step{(int8_t)dst, (int8_t)mat, (int8_t)power, (int8_t)mat,
+                       (int8_t)power, 0, {0, 0}, 1.f, 1.f}))
+          return false;
+        int old = power;
+        power = dst;
+        release_if_unreferenced(old);
+      }
+    }
+    i >>= 1;
+    if (i > 0) {
+      int dst = alloc();
+      if (dst < 0) return false;
+      // dev(mat^2) = 2 mat + mat*mat   (DS:674)
+      if (!push(Step{(int8_t)dst, (int8_t)mat, (int8_t)mat, (int8_t)mat, LB_NONE, 0,
+                     {0, 0}, 2.f, 0.f}))
+        return false;
+      int old = mat;
+      mat = dst;
+      release_if_unreferenced(old);
+    }
+  }
+  // D' = Q_p D - Q_p / p + D   (DS:845 in deviation form), err = p max|D'|
+  if (!push(Step{LB_DN, (int8_t)power, LB_D, (int8_t)power, LB_D, 1, {0, 0},
+                 -1.0f / (float)p, 1.f}))
+    return false;
+  out->nsteps = n;
+  return true;
+}
+
+__constant__ Program c_programs[kMaxP + 1];
+// H' = H + H D  (DS:846), co-scheduled with step 0 of every program
+__constant__ Step c_hstep = {LB_HN, LB_H, LB_D, LB_H, LB_NONE, 0, {0, 0}, 1.f, 0.f};
+
+static Program h_programs[kMaxP + 1];
+static bool programs_uploaded[64] = {false};
+
+static int ensure_programs() {
+  int dev = 0;
+  PC_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 64 && programs_uploaded[dev]) return PC_OK;
+  for (int p = 1; p <= kMaxP; ++p) {
+    if (!build_program(p, &h_programs[p])) {
+      set_error("internal: cannot build Newton program for p=%d", p);
+      return PC_ERR_INVALID;
+    }
+  }
+  PC_CUDA_CHECK(cudaMemcpyToSymbol(c_programs, h_programs, sizeof(h_programs)));
+  if (dev < 64) programs_uploaded[dev] = true;
+  return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// setup
+// ---------------------------------------------------------------------------
+__global__ void root_setup_kernel(RootCtl* ctl, const int32_t* ps, const int32_t* pads,
+                                  int batch, int n, uint32_t* errbits) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  RootCtl c;
+  memset(&c, 0, sizeof(c));
+  c.p = ps[b];
+  int pad = pads ? pads[b] : n;
+  c.pad = pad < 0 ? 0 : (pad > n ? n : pad);
+  c.max_ev = 1.0f;
+  c.ratio = 1.0f;
+  c.err = 1000.0f;   // DS:860 initial outer state
+  c.m_err = 1000.0f;
+  c.m_iters = 100.f;
+  c.m_ratio = 1.0f;
+  if (c.pad == 0 || c.p < 1 || c.p > kMaxP) {
+    c.done = 1;  // DS:930-937 (all padding) / unsupported exponent -> NaN error
+    c.result_h = -2;  // root = zeros
+    if (c.pad != 0) c.m_err = __int_as_float(0x7fc00000);
+  } else {
+    c.need_init = 1;
+  }
+  ctl[b] = c;
+  errbits[b] = 0u;
+}
+
+// ---------------------------------------------------------------------------
+// power iteration (DS:595-652): one CTA per matrix, <=100 dependent mat-vecs
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+power_iteration_kernel(const float* __restrict__ xs, const int32_t* __restrict__ pads,
+                       const float* __restrict__ v0, int n, int num_iters, float tol,
+                       float* __restrict__ lambdas, int32_t* __restrict__ iters,
+                       RootCtl* ctl) {
+  extern __shared__ float smem[];
+  float* v = smem;
+  float* nv = smem + n;
+  float* y = smem + 2 * n;
+  __shared__ float scratch[32];
+  const int b = blockIdx.x;
+  int pad = n;
+  if (ctl) {
+    if (ctl[b].done) return;
+    pad = ctl[b].pad;
+  } else if (pads) {
+    pad = min(max(pads[b], 0), n);
+  }
+  const float* A = xs + (size_t)b * n * n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = i < pad ? v0[i] : 0.f;
+  __syncthreads();
+  float s = 0.f;
+  int it = 0;
+  bool run = true;
+  const bool vec4 = (n % 4 == 0);
+  while (it < num_iters && run) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < pad; i += blockDim.x) ss += v[i] * v[i];
+    const float norm = sqrtf(block_sum(ss, scratch));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) nv[i] = i < pad ? v[i] / norm : 0.f;
+    __syncthreads();
+    for (int row = warp; row < n; row += nwarp) {
+      float acc = 0.f;
+      if (row < pad) {
+        const float* ar = A + (size_t)row * n;
+        if (vec4) {
+          for (int c = lane * 4; c < pad; c += 128) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar + c));
+            acc = fmaf(a4.x, nv[c], acc);       // nv is 0 beyond pad
+            acc = fmaf(a4.y, nv[c + 1], acc);
+            acc = fmaf(a4.z, nv[c + 2], acc);
+            acc = fmaf(a4.w, nv[c + 3], acc);
+          }
+        } else {
+          for (int c = lane; c < pad; c += 32) acc = fmaf(__ldg(ar + c), nv[c], acc);
+        }
+        acc = warp_sum(acc);
+      }
+      if (lane == 0) y[row] = acc;
+    }
+    __syncthreads();
+    float dot = 0.f;
+    for (int i = threadIdx.x; i < pad; i += blockDim.x) dot += nv[i] * y[i];
+    const float s_new = block_sum(dot, scratch);
+    run = fabsf(s_new - s) > tol;  // DS:639 (NaN -> stop)
+    s = s_new;
+    ++it;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = y[i];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (lambdas) lambdas[b] = s;
+    if (iters) iters[b] = it;
+    if (ctl) ctl[b].max_ev = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// element store/load policies: fp32 buffers (SIMT engine) or 3 bf16 planes (TC)
+// ---------------------------------------------------------------------------
+struct F32Bufs {
+  float* base[kNumBufs];
+  size_t mat_elems;  // n*n
+  __device__ __forceinline__ float* mat(int phys, int b, int batch) const {
+    return base[phys] + (size_t)b * mat_elems;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// (re)initialise a try: DS:866-875
+// ---------------------------------------------------------------------------
+template <class Bufs>
+__global__ void __launch_bounds__(1024)
+root_init_kernel(const float* __restrict__ xs, RootCtl* ctl, Bufs bufs, int batch, int n,
+                 RootParams prm, float* __restrict__ roots) {
+  __shared__ float scratch[32];
+  __shared__ uint32_t uscratch[32];
+  const int b = blockIdx.x;
+  RootCtl c = ctl[b];
+  if (!c.need_init) return;
+  const float* A = xs + (size_t)b * n * n;
+  const int pad = c.pad, p = c.p;
+  if (c.tries == 0) {
+    const float ev = prm.relative_eps ? c.max_ev : 1.0f;
+    c.max_ev = ev;
+    c.ridge = prm.ridge_epsilon * fmaxf(ev, 1e-25f);  // DS:830
+  }
+  const float alpha = -1.0f / (float)p;  // DS:774
+  if (n == 1) {  // DS:850-855
+    if (threadIdx.x == 0) {
+      const float a = pad > 0 ? A[0] : 0.f;
+      roots[(size_t)b] = powf(a + c.ridge, alpha);
+      c.need_init = 0; c.done = 1; c.active = 0;
+      c.m_err = 0.f; c.m_iters = 0.f; c.m_ratio = 0.f; c.m_retries = 0.f;
+      c.result_h = -1;  // already written
+      ctl[b] = c;
+    }
+    return;
+  }
+  float tenpow = 1.f;
+  for (int t = 0; t < c.tries; ++t) tenpow *= 10.f;
+  const float eps = c.ridge * tenpow;  // DS:869
+  // pass 1: Frobenius norm of the damped, masked matrix (DS:870)
+  float ss = 0.f;
+  const size_t total = (size_t)pad * pad;
+  for (size_t e = threadIdx.x; e < total; e += blockDim.x) {
+    const int i = (int)(e / pad), j = (int)(e - (size_t)i * pad);
+    float a = __ldg(A + (size_t)i * n + j);
+    if (i == j) a += eps;
+    ss = fmaf(a, a, ss);
+  }
+  const float norm = sqrtf(block_sum(ss, scratch));
+  const float z = (float)(1 + p) / (2.0f * norm);
+  const float h0 = powf(z, (float)(1.0 / (double)p));  // DS:873
+  // pass 2: D0 = alpha (zA_d - I_m), H0 = z^(1/p) I_m, err0 = max|zA_d - I_m|
+  uint32_t emax = 0;
+  const size_t nn = (size_t)n * n;
+  for (size_t e = threadIdx.x; e < nn; e += blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+    float d = 0.f, h = 0.f;
+    if (i < pad && j < pad) {
+      float a = __ldg(A + e);
+      if (i == j) a += eps;
+      const float m0 = a * z;                       // DS:871
+      const float e0 = m0 - (i == j ? 1.f : 0.f);   // M0 - I_m
+      const uint32_t ab = absbits(e0);
+      emax = ab > emax ? ab : emax;
+      d = alpha * e0;
+      h = (i == j) ? h0 : 0.f;
+    }
+    bufs.store(0, b, i, j, n, d);  // D[0]
+    bufs.store(2, b, i, j, n, h);  // H[0]
+  }
+  emax = block_max_u32(emax, uscratch);
+  if (threadIdx.x == 0) {
+    c.need_init = 0;
+    c.iter = 0;
+    c.cur = 0;
+    c.err = __uint_as_float(emax);  // DS:872
+    c.ratio = 1.0f;
+    root_after_error_update(c, prm);
+    ctl[b] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// SIMT engine: one launch executes step `s` of every active matrix's program
+// (+ the H update alongside step 0).
+// ---------------------------------------------------------------------------
+struct F32Store : F32Bufs {
+  __device__ __forceinline__ void store(int phys, int b, int i, int j, int n, float v) const {
+    base[phys][(size_t)b * mat_elems + (size_t)i * n + j] = v;
+  }
+  __device__ __forceinline__ float load(int phys, int b, int i, int j, int n) const {
+    return base[phys][(size_t)b * mat_elems + (size_t)i * n + j];
+  }
+};
+
+struct SquareView {
+  const float* base;
+  int n, lim;
+  __device__ __forceinline__ float operator()(int i, int k) const {
+    return (i < lim && k < lim) ? base[(size_t)i * n + k] : 0.f;
+  }
+};
+
+__global__ void __launch_bounds__(kSimtThreads)
+root_phase_simt_kernel(F32Store bufs, const RootCtl* __restrict__ ctl,
+                       uint32_t* __restrict__ errbits, int n, int s) {
+  __shared__ SimtSmem sm;
+  const int b = blockIdx.z >> 1, lane_op = blockIdx.z & 1;
+  const RootCtl& c = ctl[b];
+  if (!c.active) return;
+  Step st;
+  if (lane_op == 1) {
+    if (s != 0) return;
+    st = c_hstep;
+  } else {
+    const Program& pr = c_programs[c.p];
+    if (s >= pr.nsteps) return;
+    st = pr.steps[s];
+  }
+  const int lim = c.pad;  // everything is zero outside [0,pad)^2
+  const int tile_m = blockIdx.y, tile_n = blockIdx.x;
+  if (tile_m * kSimtBM >= lim || tile_n * kSimtBN >= lim) {
+    // tile fully in the padding: result is exactly zero
+    const int cur = c.cur;
+    float* out = bufs.mat(physical_buf(st.dst, cur), b, 0);
+    for (int e = threadIdx.x; e < kSimtBM * kSimtBN; e += blockDim.x) {
+      int i = tile_m * kSimtBM + e / kSimtBN, j = tile_n * kSimtBN + e % kSimtBN;
+      if (i < n && j < n) out[(size_t)i * n + j] = 0.f;
+    }
+    return;
+  }
+  const int cur = c.cur;
+  const SquareView A{bufs.mat(physical_buf(st.a, cur), b, 0), n, lim};
+  // operands are symmetric: B(j,k) = B[j][k] reads rows (coalesced along k)
+  const SquareView B{bufs.mat(physical_buf(st.b, cur), b, 0), n, lim};
+  const float* x1 = st.x1 >= 0 ? bufs.mat(physical_buf(st.x1, cur), b, 0) : nullptr;
+  const float* x2 = st.x2 >= 0 ? bufs.mat(physical_buf(st.x2, cur), b, 0) : nullptr;
+  float* out = bufs.mat(physical_buf(st.dst, cur), b, 0);
+  const float c1 = st.c1, c2 = st.c2;
+  uint32_t emax = 0;
+  simt_gemm_tile(lim, tile_m, tile_n, A, B, true, true, sm,
+                 [&](int i, int j0, const float* acc) {
+                   if (i >= n) return;
+#pragma unroll
+                   for (int q = 0; q < 4; ++q) {
+                     const int j = j0 + q;
+                     if (j >= n) continue;
+                     float v = 0.f;
+                     if (i < lim && j < lim) {
+                       const size_t idx = (size_t)i * n + j;
+                       v = acc[q];
+                       if (x1) v = fmaf(c1, x1[idx], v);
+                       if (x2) v = fmaf(c2, x2[idx], v);
+                     }
+                     out[(size_t)i * n + j] = v;
+                     const uint32_t ab = absbits(v);
+                     emax = ab > emax ? ab : emax;
+                   }
+                 });
+  if (st.reduce_err) {
+    emax = warp_max_u32(emax);
+    if ((threadIdx.x & 31) == 0 && emax) atomicMax(errbits + b, emax);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-iteration control (DS:836-848 bookkeeping, DS:876-885 retry logic)
+// ---------------------------------------------------------------------------
+__global__ void root_control_kernel(RootCtl* ctl, uint32_t* errbits, int batch,
+                                    RootParams prm, int* n_unfinished) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  RootCtl c = ctl[b];
+  if (c.active) {
+    const float maxd = __uint_as_float(errbits[b]);
+    errbits[b] = 0u;
+    const float new_err = (float)c.p * maxd;  // max|M' - I_m|, DS:847
+    c.ratio = new_err / c.err;                // DS:848
+    c.err = new_err;
+    c.iter += 1;
+    c.cur ^= 1;
+    root_after_error_update(c, prm);
+    ctl[b] = c;
+  }
+  if (!c.done) atomicAdd(n_unfinished, 1);
+}
+
+template <class Bufs>
+__global__ void root_final_kernel(const RootCtl* __restrict__ ctl, Bufs bufs, int n,
+                                  float* __restrict__ roots, float* __restrict__ metrics) {
+  const int b = blockIdx.y;
+  const RootCtl& c = ctl[b];
+  const size_t nn = (size_t)n * n;
+  float* out = roots + (size_t)b * nn;
+  if (c.result_h != -1) {  // -1: already written by the n == 1 closed form
+    const bool zero = (c.result_h == -2) || (c.pad == 0) || !c.done;  // DS:930-937
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn;
+         e += (size_t)gridDim.x * blockDim.x) {
+      const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+      out[e] = zero ? 0.f : bufs.load(2 + c.result_h, b, i, j, n);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float* m = metrics + (size_t)b * PC_NUM_METRICS;
+    m[PC_METRIC_ERROR] = c.pad == 0 ? 0.f : c.m_err;
+    m[PC_METRIC_ITERS] = c.m_iters;
+    m[PC_METRIC_ERROR_RATIO] = c.m_ratio;
+    m[PC_METRIC_MAX_EV] = c.max_ev;
+    m[PC_METRIC_RETRIES] = c.m_retries;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+// numpy.random.RandomState(1729).uniform(-1, 1, n) -- MT19937, 53-bit doubles
+// (DS:642-643).  Generated on the host so the start vector is bit-identical.
+static void mt19937_uniform(uint32_t seed, int n, float* out) {
+  uint32_t mt[624];
+  mt[0] = seed;
+  for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + i;
+  int idx = 624;
+  auto next = [&]() -> uint32_t {
+    if (idx >= 624) {
+      for (int k = 0; k < 624; ++k) {
+        uint32_t yv = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+        mt[k] = mt[(k + 397) % 624] ^ (yv >> 1) ^ ((yv & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t yv = mt[idx++];
+    yv ^= yv >> 11;
+    yv ^= (yv << 7) & 0x9d2c5680u;
+    yv ^= (yv << 15) & 0xefc60000u;
+    yv ^= yv >> 18;
+    return yv;
+  };
+  for (int i = 0; i < n; ++i) {
+    const uint32_t a = next() >> 5, bq = next() >> 6;
+    const double r = (a * 67108864.0 + bq) / 9007199254740992.0;  // [0,1)
+    out[i] = (float)(-1.0 + 2.0 * r);  // uniform(low, high) = low + (high-low)*r
+  }
+}
+
+struct RootWorkspace {
+  RootCtl* ctl;
+  uint32_t* errbits;
+  int* unfinished;  // [1]
+  float* v0;        // [n]
+  char* engine_mem;
+  size_t engine_bytes;
+};
+
+static size_t engine_bytes_simt(int batch, int n) {
+  return (size_t)kNumBufs * batch * n * n * sizeof(float);
+}
+
+static size_t header_bytes(int batch, int n) {
+  size_t s = 0;
+  s += align_up(sizeof(RootCtl) * batch, 256);
+  s += align_up(sizeof(uint32_t) * batch, 256);
+  s += 256;
+  s += align_up(sizeof(float) * n, 256);
+  return s;
+}
+
+static int resolve_engine(int engine, int n) {
+  if (engine == PC_ENGINE_AUTO) {
+    if (tc_engine_available() && n >= 256 && n % 128 == 0) return PC_ENGINE_TC_BF16X6;
+    return PC_ENGINE_SIMT_FP32;
+  }
+  return engine;
+}
+
+size_t root_workspace_bytes(int batch, int n, int engine) {
+  engine = resolve_engine(engine, n);
+  size_t e = engine == PC_ENGINE_SIMT_FP32 ? engine_bytes_simt(batch, n)
+                                           : tc_engine_bytes(batch, n);
+  return header_bytes(batch, n) + align_up(e, 256) + 1024;
+}
+
+int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n,
+                        int num_iters, float tol, float* lambdas, int32_t* iters,
+                        RootCtl* ctl, float* v0_dev, cudaStream_t stream) {
+  std::vector<float> v0(n);
+  mt19937_uniform(1729u, n, v0.data());
+  PC_CUDA_CHECK(cudaMemcpyAsync(v0_dev, v0.data(), sizeof(float) * n,
+                                cudaMemcpyHostToDevice, stream));
+  PC_CUDA_CHECK(cudaStreamSynchronize(stream));  // v0 is a stack/heap temporary
+  const size_t smem = sizeof(float) * 3 * (size_t)n;
+  if (smem > 48 * 1024) {
+    PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+  }
+  const int threads = n >= 512 ? 1024 : (n >= 128 ? 512 : 128);
+  power_iteration_kernel<<<batch, threads, smem, stream>>>(xs, pads, v0_dev, n, num_iters,
+                                                          tol, lambdas, iters, ctl);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch, int n,
+             const pc_root_options* opt, float* roots, float* metrics, void* workspace,
+             size_t workspace_bytes, cudaStream_t stream) {
+  const int engine = resolve_engine(opt->engine, n);
+  PC_REQUIRE(engine == PC_ENGINE_SIMT_FP32 || engine == PC_ENGINE_TC_BF16X6 ||
+                 engine == PC_ENGINE_TC_BF16X3,
+             "unknown engine %d", opt->engine);
+  if (engine != PC_ENGINE_SIMT_FP32) {
+    PC_REQUIRE(n % 128 == 0 && n >= 128, "tcgen05 engine needs n %% 128 == 0 (n=%d)", n);
+    if (!tc_engine_available()) {
+      set_error("tcgen05 engine requested but device is not sm_100");
+      return PC_ERR_UNSUPPORTED;
+    }
+  }
+  if (workspace_bytes < root_workspace_bytes(batch, n, opt->engine)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes,
+              root_workspace_bytes(batch, n, opt->engine));
+    return PC_ERR_WORKSPACE;
+  }
+  int rc = ensure_programs();
+  if (rc != PC_OK) return rc;
+
+  // carve the workspace
+  char* w = reinterpret_cast<char*>(align_up((size_t)workspace, 256));
+  RootWorkspace ws;
+  ws.ctl = reinterpret_cast<RootCtl*>(w); w += align_up(sizeof(RootCtl) * batch, 256);
+  ws.errbits = reinterpret_cast<uint32_t*>(w); w += align_up(sizeof(uint32_t) * batch, 256);
+  ws.unfinished = reinterpret_cast<int*>(w); w += 256;
+  ws.v0 = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * n, 256);
+  ws.engine_mem = w;
+
+  // exponents decide how many GEMM launches one Newton iteration needs
+  std::vector<int32_t> hps(batch);
+  PC_CUDA_CHECK(cudaMemcpyAsync(hps.data(), ps, sizeof(int32_t) * batch,
+                                cudaMemcpyDeviceToHost, stream));
+  PC_CUDA_CHECK(cudaStreamSynchronize(stream));
+  int max_steps = 1;
+  for (int b = 0; b < batch; ++b)
+    if (hps[b] >= 1 && hps[b] <= kMaxP)
+      max_steps = h_programs[hps[b]].nsteps > max_steps ? h_programs[hps[b]].nsteps : max_steps;
+
+  RootParams prm{opt->ridge_epsilon, opt->error_tolerance, opt->num_iters,
+                 opt->relative_matrix_epsilon};
+  root_setup_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(ws.ctl, ps, pads, batch, n,
+                                                            ws.errbits);
+  PC_CUDA_CHECK(cudaGetLastError());
+  if (opt->relative_matrix_epsilon && n > 1) {
+    rc = run_power_iteration(xs, nullptr, batch, n, 100, 1e-6f, nullptr, nullptr, ws.ctl,
+                             ws.v0, stream);  // DS:820-825
+    if (rc != PC_OK) return rc;
+  }
+
+  F32Store f32;
+  TcEngine tc;
+  if (engine == PC_ENGINE_SIMT_FP32) {
+    for (int k = 0; k < kNumBufs; ++k)
+      f32.base[k] = reinterpret_cast<float*>(ws.engine_mem) + (size_t)k * batch * n * n;
+    f32.mat_elems = (size_t)n * n;
+  } else {
+    rc = tc_engine_init(&tc, ws.engine_mem, batch, n, engine == PC_ENGINE_TC_BF16X6 ? 6 : 3);
+    if (rc != PC_OK) return rc;
+  }
+
+  static thread_local int* h_unfinished = nullptr;  // pinned poll slot, one per host thread
+  if (!h_unfinished) PC_CUDA_CHECK(cudaMallocHost(&h_unfinished, sizeof(int)));
+  *h_unfinished = 1;
+  const int tiles = (n + kSimtBM - 1) / kSimtBM;
+  const int max_total = opt->num_iters * 6 + 8;
+  int since_check = 0, check_every = 6;
+  for (int it = 0; it < max_total; ++it) {
+    if (engine == PC_ENGINE_SIMT_FP32) {
+      root_init_kernel<F32Store><<<batch, n >= 512 ? 1024 : 256, 0, stream>>>(
+          xs, ws.ctl, f32, batch, n, prm, roots);
+      count_launch(1);
+      cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+      if (gemm_timing_enabled()) {
+        cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, stream);
+      }
+      for (int s = 0; s < max_steps; ++s) {
+        dim3 grid(tiles, tiles, batch * 2);
+        root_phase_simt_kernel<<<grid, kSimtThreads, 0, stream>>>(f32, ws.ctl, ws.errbits,
+                                                                 n, s);
+      }
+      if (ev0) { cudaEventRecord(ev1, stream); gemm_timing_record(ev0, ev1); }
+      count_launch(max_steps);
+      gemm_count(max_steps);
+    } else {
+      rc = tc_engine_iteration(&tc, xs, ws.ctl, ws.errbits, prm, roots, max_steps, stream);
+      if (rc != PC_OK) return rc;
+    }
+    count_launch(1);
+    cudaMemsetAsync(ws.unfinished, 0, sizeof(int), stream);
+    root_control_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(ws.ctl, ws.errbits, batch,
+                                                                prm, ws.unfinished);
+    if (++since_check >= check_every) {
+      since_check = 0;
+      check_every = 2;
+      cudaMemcpyAsync(h_unfinished, ws.unfinished, sizeof(int), cudaMemcpyDeviceToHost,
+                      stream);
+      cudaError_t e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess) {
+        set_error("root iteration failed: %s", cudaGetErrorString(e));
+        return PC_ERR_CUDA;
+      }
+      if (*h_unfinished == 0) break;
+    }
+  }
+  dim3 fgrid((unsigned)std::min<size_t>(((size_t)n * n + 255) / 256, 64), batch);
+  if (engine == PC_ENGINE_SIMT_FP32) {
+    root_final_kernel<F32Store><<<fgrid, 256, 0, stream>>>(ws.ctl, f32, n, roots, metrics);
+  } else {
+    rc = tc_engine_final(&tc, ws.ctl, roots, metrics, stream);
+    if (rc != PC_OK) return rc;
+  }
+  PC_CUDA_CHECK(cudaGetLastError());
+  count_launch(3);  // setup, power iteration, final
+  // algorithmic GEMM flops actually needed: iterations x G(p) x 2 n^3
+  if (gemm_timing_enabled()) {
+    std::vector<float> hm((size_t)batch * PC_NUM_METRICS);
+    cudaMemcpyAsync(hm.data(), metrics, hm.size() * sizeof(float), cudaMemcpyDeviceToHost,
+                    stream);
+    cudaStreamSynchronize(stream);
+    double fl = 0.0;
+    for (int b = 0; b < batch; ++b) {
+      const int p = hps[b];
+      if (p < 1 || p > kMaxP) continue;
+      const double gp = h_programs[p].nsteps + 1;  // chain steps + the H update
+      fl += (double)hm[(size_t)b * PC_NUM_METRICS + PC_METRIC_ITERS] * gp * 2.0 * n * (double)n * n;
+    }
+    gemm_add_flops(fl);
+  }
+  return PC_OK;
+}
+
+}  // namespace pc
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+void pc_root_options_default(pc_root_options* opt) {
+  opt->ridge_epsilon = 1e-6f;
+  opt->error_tolerance = 1e-6f;
+  opt->num_iters = 100;
+  opt->relative_matrix_epsilon = 1;
+  opt->engine = PC_ENGINE_AUTO;
+  opt->reserved = 0;
+}
+
+size_t pc_inverse_pth_root_workspace_bytes(int batch, int n, int engine) {
+  if (batch <= 0 || n <= 0) return 0;
+  return pc::root_workspace_bytes(batch, n, engine);
+}
+
+int pc_inverse_pth_root_batched(const float* xs, const int32_t* ps,
+                                const int32_t* padding_starts, int batch, int n,
+                                const pc_root_options* opt, float* roots, float* metrics,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(batch >= 0 && n >= 1, "bad batch/n (%d, %d)", batch, n);
+  if (batch == 0) return PC_OK;
+  PC_REQUIRE(xs && ps && roots && metrics && workspace && opt, "null pointer argument");
+  PC_REQUIRE(opt->num_iters >= 0, "num_iters < 0");
+  return pc::run_root(xs, ps, padding_starts, batch, n, opt, roots, metrics, workspace,
+                      workspace_bytes, (cudaStream_t)stream);
+}
+
+int pc_power_iteration_batched(const float* xs, const int32_t* padding_starts, int batch,
+                               int n, int num_iters, float error_tolerance, float* lambdas,
+                               int32_t* iters, void* stream) {
+  PC_REQUIRE(batch >= 0 && n >= 1, "bad batch/n");
+  if (batch == 0) return PC_OK;
+  PC_REQUIRE(xs && lambdas, "null pointer argument");
+  float* v0 = nullptr;
+  PC_CUDA_CHECK(cudaMallocAsync(&v0, sizeof(float) * n, (cudaStream_t)stream));
+  int rc = pc::run_power_iteration(xs, padding_starts, batch, n, num_iters, error_tolerance,
+                                   lambdas, iters, nullptr, v0, (cudaStream_t)stream);
+  cudaFreeAsync(v0, (cudaStream_t)stream);
+  return rc;
+}
+
+}  // extern "C"

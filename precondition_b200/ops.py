@@ -1,0 +1,193 @@
+"""Operator-level host API over the C ABI (torch tensors carry device memory).
+
+Each function mirrors one seam of the reference (DS = distributed_shampoo.py):
+``matrix_inverse_pth_root_batched`` <- ``_matrix_inverse_pth_root_vmap``
+(DS:2742-2744), ``power_iteration`` (DS:595-652), ``quantize`` / ``dequantize``
+(QU:49-113), ``grouped_gemm`` (DS:1468-1470, DS:1707), ``graft_momentum``
+(DS:3496-3625).  All of them require a CUDA device; nothing falls back to CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from precondition_b200 import _lib
+
+_QDT = {torch.int16: _lib.PC_QDTYPE_INT16, torch.int8: _lib.PC_QDTYPE_INT8,
+        torch.bfloat16: _lib.PC_QDTYPE_BF16, torch.float32: _lib.PC_QDTYPE_F32}
+
+gpu_launches = 0  # count of C-ABI calls that launched kernels (bench bookkeeping)
+
+
+def _stream() -> int:
+  return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors):
+  for t in tensors:
+    if t is None:
+      continue
+    if not t.is_cuda:
+      raise RuntimeError("precondition_b200 needs CUDA tensors: there is no CPU fallback")
+    if not t.is_contiguous():
+      raise ValueError("tensor must be contiguous")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+  return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+  key = (device.index if device.index is not None else torch.cuda.current_device())
+  ws = _workspaces.get(key)
+  if ws is None or ws.numel() < nbytes:
+    ws = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=device)
+    _workspaces[key] = ws
+  return ws
+
+
+def matrix_inverse_pth_root_batched(
+    xs: torch.Tensor, ps, padding_starts=None, ridge_epsilon: float = 1e-6,
+    error_tolerance: float = 1e-6, num_iters: int = 100,
+    relative_matrix_epsilon: bool = True, engine: int = _lib.PC_ENGINE_AUTO,
+    out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Batched ``(A + eps I)^(-1/p)``; returns (roots [b,n,n], metrics [b,5])."""
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(xs)
+  assert xs.dtype == torch.float32 and xs.dim() == 3 and xs.shape[1] == xs.shape[2]
+  b, n = xs.shape[0], xs.shape[1]
+  dev = xs.device
+  ps_t = torch.as_tensor(ps, dtype=torch.int32).to(dev).contiguous()
+  pads_t = None
+  if padding_starts is not None:
+    pads_t = torch.as_tensor(padding_starts, dtype=torch.int32).to(dev).contiguous()
+  roots = out if out is not None else torch.empty_like(xs)
+  metrics = torch.empty((b, _lib.PC_NUM_METRICS), dtype=torch.float32, device=dev)
+  if b == 0:
+    return roots, metrics
+  opt = _lib.RootOptions()
+  lib.pc_root_options_default(ctypes.byref(opt))
+  opt.ridge_epsilon, opt.error_tolerance = ridge_epsilon, error_tolerance
+  opt.num_iters, opt.relative_matrix_epsilon = num_iters, int(relative_matrix_epsilon)
+  opt.engine = engine
+  nbytes = lib.pc_inverse_pth_root_workspace_bytes(b, n, engine)
+  ws = _workspace(nbytes, dev)
+  with torch.cuda.device(dev):
+    _lib.check(lib.pc_inverse_pth_root_batched(
+        _ptr(xs), _ptr(ps_t), _ptr(pads_t), b, n, ctypes.byref(opt), _ptr(roots),
+        _ptr(metrics), _ptr(ws), ws.numel(), ctypes.c_void_p(_stream())))
+  gpu_launches += 1
+  return roots, metrics
+
+
+def power_iteration(xs: torch.Tensor, padding_starts=None, num_iters: int = 100,
+                    error_tolerance: float = 1e-6):
+  """Batched DS:595-652; returns (lambda [b], iters [b])."""
+  lib = _lib.load()
+  _require_cuda(xs)
+  b, n = xs.shape[0], xs.shape[1]
+  pads_t = None
+  if padding_starts is not None:
+    pads_t = torch.as_tensor(padding_starts, dtype=torch.int32).to(xs.device).contiguous()
+  lam = torch.empty(b, dtype=torch.float32, device=xs.device)
+  its = torch.empty(b, dtype=torch.int32, device=xs.device)
+  with torch.cuda.device(xs.device):
+    _lib.check(lib.pc_power_iteration_batched(_ptr(xs), _ptr(pads_t), b, n, num_iters,
+                                              error_tolerance, _ptr(lam), _ptr(its),
+                                              ctypes.c_void_p(_stream())))
+  return lam, its
+
+
+def quantize(x: torch.Tensor, qdtype: torch.dtype, extract_diagonal: bool = False):
+  """QU:49-95 on a [batch, rows, cols] (or [rows, cols]) tensor.
+
+  Returns (quantized, diagonal or None, bucket_size or None)."""
+  lib = _lib.load()
+  _require_cuda(x)
+  squeeze = x.dim() == 2
+  xb = x.unsqueeze(0) if squeeze else x
+  b, rows, cols = xb.shape
+  if qdtype == torch.float32:
+    return x, None, None
+  q = torch.empty(xb.shape, dtype=qdtype, device=x.device)
+  diag = bucket = None
+  if qdtype != torch.bfloat16:
+    bucket = torch.empty((b, cols), dtype=torch.float32, device=x.device)
+    if extract_diagonal:
+      diag = torch.empty((b, rows), dtype=torch.float32, device=x.device)
+  with torch.cuda.device(x.device):
+    _lib.check(lib.pc_quantize_batched(_ptr(xb), b, rows, cols, _QDT[qdtype],
+                                       int(extract_diagonal), _ptr(q), _ptr(diag),
+                                       _ptr(bucket), ctypes.c_void_p(_stream())))
+  if squeeze:
+    q = q[0]
+    diag = None if diag is None else diag[0]
+    bucket = None if bucket is None else bucket[0]
+  return q, diag, bucket
+
+
+def dequantize(q: torch.Tensor, diag, bucket, extract_diagonal: bool = False,
+               out: Optional[torch.Tensor] = None):
+  """QU:97-113."""
+  lib = _lib.load()
+  _require_cuda(q)
+  if q.dtype == torch.float32:
+    return q
+  squeeze = q.dim() == 2
+  qb = q.unsqueeze(0) if squeeze else q
+  b, rows, cols = qb.shape
+  x = out if out is not None else torch.empty(qb.shape, dtype=torch.float32, device=q.device)
+  with torch.cuda.device(q.device):
+    _lib.check(lib.pc_dequantize_batched(_ptr(qb), _ptr(diag), _ptr(bucket), b, rows, cols,
+                                         _QDT[q.dtype], int(extract_diagonal), _ptr(x),
+                                         ctypes.c_void_p(_stream())))
+  return x[0] if (squeeze and out is None) else x
+
+
+def upload_gemm_descs(descs: Sequence[_lib.GemmDesc], device) -> torch.Tensor:
+  """Packs descriptors into a device byte tensor (kept alive by the caller)."""
+  arr = (_lib.GemmDesc * len(descs))(*descs)
+  host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+  return host.to(device)
+
+
+def grouped_gemm(descs_dev: torch.Tensor, count: int, max_m: int, max_n: int):
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(descs_dev)
+  with torch.cuda.device(descs_dev.device):
+    _lib.check(lib.pc_grouped_gemm(_ptr(descs_dev), count, max_m, max_n,
+                                   ctypes.c_void_p(_stream())))
+  gpu_launches += 1
+
+
+def make_graft_options(**kw) -> _lib.GraftOptions:
+  o = _lib.GraftOptions()
+  for k, v in kw.items():
+    setattr(o, k, v)
+  return o
+
+
+def graft_momentum(grad, param, precond_grad, diagonal_statistics, diagonal_momentum,
+                   momentum, update, opt: _lib.GraftOptions):
+  """DS:3496-3625 tail for one parameter; state tensors are updated in place."""
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(grad, param, precond_grad, diagonal_statistics, diagonal_momentum, momentum,
+                update)
+  numel = grad.numel()
+  nbytes = lib.pc_graft_momentum_workspace_bytes(numel)
+  ws = _workspace(nbytes, grad.device)
+  with torch.cuda.device(grad.device):
+    _lib.check(lib.pc_graft_momentum(
+        _ptr(grad), _ptr(param), _ptr(precond_grad), _ptr(diagonal_statistics),
+        _ptr(diagonal_momentum), _ptr(momentum), _ptr(update), numel, ctypes.byref(opt),
+        _ptr(ws), ws.numel(), ctypes.c_void_p(_stream())))
+  gpu_launches += 1

@@ -1,0 +1,151 @@
+"""GPU parity tests of the quantisation, grouped-GEMM and grafting kernels."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import numerics as N
+
+pytestmark = pytest.mark.gpu
+
+
+def test_quantize_bit_exact(golden_quant):
+  from precondition_b200 import ops
+  g = golden_quant
+  for name in ("sym24", "rect", "zero_col", "halves"):
+    x = torch.as_tensor(g[f"{name}/x"]).cuda()
+    for dt, tag in ((torch.int8, "i8"), (torch.int16, "i16")):
+      for ext in (False, True):
+        key = f"{name}/{tag}{'_diag' if ext else ''}"
+        if f"{key}/q" not in g:
+          continue
+        q, d, b = ops.quantize(x, dt, ext)
+        np.testing.assert_array_equal(q.cpu().numpy(), g[f"{key}/q"], err_msg=key)
+        np.testing.assert_array_equal(b.cpu().numpy(), g[f"{key}/bucket"])
+        if ext:
+          np.testing.assert_array_equal(d.cpu().numpy(), g[f"{key}/diag"])
+        back = ops.dequantize(q, d, b, ext)
+        np.testing.assert_array_equal(back.cpu().numpy(), g[f"{key}/float"])
+    q, _, _ = ops.quantize(x, torch.bfloat16)
+    np.testing.assert_array_equal(ops.dequantize(q, None, None).cpu().numpy(),
+                                  g[f"{name}/bf16/float"])
+
+
+def test_quantize_batched_large():
+  from precondition_b200 import ops
+  rng = np.random.default_rng(0)
+  x = rng.standard_normal((3, 257, 257)).astype(np.float32)
+  x = x + x.transpose(0, 2, 1)
+  q, d, b = ops.quantize(torch.as_tensor(x).cuda(), torch.int16, True)
+  for i in range(3):
+    wq, wd, wb = N.quantize(x[i], np.int16, True)
+    np.testing.assert_array_equal(q[i].cpu().numpy(), wq)
+    np.testing.assert_array_equal(d[i].cpu().numpy(), wd)
+    np.testing.assert_array_equal(b[i].cpu().numpy(), wb)
+
+
+def _desc(lib, **kw):
+  d = lib.GemmDesc()
+  for k, v in kw.items():
+    setattr(d, k, v)
+  return d
+
+
+def test_grouped_gemm_views_match_tensordot():
+  """All three mode-k Gram products of a rank-3 sub-block, read in place
+  (gram_weighted_update, DS:1440-1470) and a two-sided apply (DS:1707)."""
+  from precondition_b200 import _lib, ops
+  rng = np.random.default_rng(2)
+  D0, D1, D2 = 9, 70, 45
+  t = rng.standard_normal((D0, D1, D2)).astype(np.float32)
+  tg = torch.as_tensor(t).cuda()
+  o0, o1, o2, b0, b1, b2 = 2, 10, 5, 6, 50, 33   # block offsets / sizes
+  blk = t[o0:o0 + b0, o1:o1 + b1, o2:o2 + b2]
+  base = tg.data_ptr() + 4 * (o0 * D1 * D2 + o1 * D2 + o2)
+  outs, descs, wants = [], [], []
+  w1, w2 = 0.9, 0.1
+  for axis, (m, views) in enumerate([
+      (b0, dict(si=D1 * D2, sko=D2, ski=1, kinner=b2, k=b1 * b2)),
+      (b1, dict(si=D2, sko=D1 * D2, ski=1, kinner=b2, k=b0 * b2)),
+      (b2, dict(si=1, sko=D1 * D2, ski=D2, kinner=b1, k=b0 * b1))]):
+    old = rng.standard_normal((m, m)).astype(np.float32)
+    old_t = torch.as_tensor(old).cuda()
+    out_t = torch.empty_like(old_t)
+    outs.append((old_t, out_t))
+    descs.append(_desc(_lib, a=base, b=base, c_in=old_t.data_ptr(), c=out_t.data_ptr(),
+                       a_si=views["si"], a_sko=views["sko"], a_ski=views["ski"],
+                       b_sj=views["si"], b_sko=views["sko"], b_ski=views["ski"],
+                       c_sio=0, c_sii=m, a_kinner=views["kinner"], b_kinner=views["kinner"],
+                       c_iinner=m, m=m, n=m, k=views["k"], alpha=w2, beta=w1))
+    wants.append(N.gram_weighted_update(old, blk, axis, w1, w2))
+  dev = ops.upload_gemm_descs(descs, tg.device)
+  ops.grouped_gemm(dev, len(descs), max(b0, b1, b2), max(b0, b1, b2))
+  torch.cuda.synchronize()
+  for (_, out_t), want in zip(outs, wants):
+    np.testing.assert_allclose(out_t.cpu().numpy(), want, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(graft_type=1), dict(graft_type=0), dict(graft_type=5),
+    dict(graft_type=2), dict(graft_type=6, weight_decay=0.1, decoupled_weight_decay=1,
+                             decoupled_learning_rate=0),
+    dict(graft_type=3, clip_by_scaled_gradient_norm=0.5),
+    dict(graft_type=4, weight_decay=0.01, moving_average_for_momentum=1, nesterov=0),
+    dict(graft_type=1, run_shampoo=0), dict(graft_type=1, precond=False),
+])
+def test_graft_momentum_matches_oracle(cfg):
+  """_transform_grad tail (DS:3496-3625) against the oracle's restatement."""
+  from oracle import optimizer as O
+  from precondition_b200 import ops
+  cfg = dict(cfg)
+  use_precond = cfg.pop("precond", True)
+  rng = np.random.default_rng(4)
+  shape = (37, 53)
+  grad = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+  param = rng.standard_normal(shape).astype(np.float32)
+  pg = rng.standard_normal(shape).astype(np.float32)
+  diag = np.abs(rng.standard_normal(shape)).astype(np.float32)
+  dmom = rng.standard_normal(shape).astype(np.float32)
+  mom = rng.standard_normal(shape).astype(np.float32)
+  o = dict(beta1=0.9, beta2=0.999, graft_type=1, diagonal_epsilon=1e-10, weight_decay=0.0,
+           learning_rate=0.1, nesterov=1, moving_average_for_momentum=0,
+           decoupled_learning_rate=1, decoupled_weight_decay=0, run_shampoo=1,
+           clip_by_scaled_gradient_norm=0.0)
+  o.update(cfg)
+  # oracle: drive _transform_grad with a stub preconditioner
+  opt = O.distributed_shampoo(
+      o["learning_rate"], 64, beta1=o["beta1"], beta2=o["beta2"],
+      diagonal_epsilon=o["diagonal_epsilon"], weight_decay=o["weight_decay"],
+      start_preconditioning_step=0 if o["run_shampoo"] else 10,
+      graft_type=O.GraftingType(o["graft_type"]), nesterov=bool(o["nesterov"]),
+      moving_average_for_momentum=bool(o["moving_average_for_momentum"]),
+      decoupled_learning_rate=bool(o["decoupled_learning_rate"]),
+      decoupled_weight_decay=bool(o["decoupled_weight_decay"]),
+      clip_by_scaled_gradient_norm=o["clip_by_scaled_gradient_norm"] or None,
+      skip_preconditioning_rank_lt=0 if use_precond else 3)
+
+  class _Stub:
+    def preconditioned_grad(self, g, p):
+      return pg
+  opt._preconditioner = lambda p: _Stub()
+  has_diag = o["graft_type"] in (2, 3, 4, 6)
+  st = O.ParameterStats(
+      N.QuantizedValue.from_float_value(diag if has_diag else [], np.float32), [], [],
+      N.QuantizedValue.from_float_value(dmom, np.float32),
+      N.QuantizedValue.from_float_value(mom, np.float32), None, None)
+  want_u, want_st = opt._transform_grad(grad, st, param, 5)
+  c = lambda a: torch.as_tensor(a.copy()).cuda()
+  g_t, p_t, pg_t, d_t, dm_t, m_t = c(grad), c(param), c(pg), c(diag), c(dmom), c(mom)
+  u_t = torch.empty_like(g_t)
+  ops.graft_momentum(g_t, p_t, pg_t if use_precond else None, d_t if has_diag else None,
+                     dm_t, m_t, u_t, ops.make_graft_options(**o))
+  torch.cuda.synchronize()
+  np.testing.assert_allclose(u_t.cpu().numpy(), want_u, rtol=2e-6, atol=1e-7)
+  np.testing.assert_allclose(m_t.cpu().numpy(), want_st.momentum.to_float(), rtol=2e-6,
+                             atol=1e-7)
+  np.testing.assert_allclose(dm_t.cpu().numpy(), want_st.diagonal_momentum.to_float(),
+                             rtol=2e-6, atol=1e-7)
+  if has_diag:
+    np.testing.assert_allclose(d_t.cpu().numpy(), want_st.diagonal_statistics.to_float(),
+                               rtol=2e-6, atol=1e-12)

@@ -1,0 +1,193 @@
+"""GPU parity tests of the batched inverse p-th root (C ABI) against the CPU
+oracle and the golden vectors recorded from the reference.
+
+Tolerances (north_star): relative Frobenius error of each root <= 1e-3 (the fp32
+CUDA-core engine is held to 2e-5, the split-bf16 tensor-core engine to 1e-4);
+residual max|X^p (A + eps I) - I| no worse than 2x the reference's + 1e-6;
+iteration counts, retry counts and failure flags identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import numerics as N
+from oracle.gen_golden import ema_statistics, gen_symmetric_matrix
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = [1]  # PC_ENGINE_SIMT_FP32; tcgen05 engines are appended when available
+
+
+def _engines():
+  from precondition_b200 import _lib
+  eng = [1]
+  if torch.cuda.is_available() and _lib.load().pc_device_supports_tcgen05():
+    eng += [2]
+  return eng
+
+
+def _run(xs, ps, pads=None, engine=1, **kw):
+  from precondition_b200 import ops
+  x = torch.as_tensor(np.ascontiguousarray(xs, dtype=np.float32)).cuda()
+  roots, metrics = ops.matrix_inverse_pth_root_batched(x, ps, pads, engine=engine, **kw)
+  torch.cuda.synchronize()
+  return roots.cpu().numpy(), metrics.cpu().numpy()
+
+
+def _rel_fro(a, b):
+  return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) /
+               max(np.linalg.norm(b.astype(np.float64)), 1e-300))
+
+
+def _check_case(root, row, want_root, want_row, a, p, tol, tag):
+  want_err = want_row[0]
+  if np.isnan(want_err):
+    assert np.isnan(row[0]), f"{tag}: reference error is NaN, got {row[0]}"
+    return
+  assert row[1] == want_row[1], f"{tag}: iters {row[1]} != reference {want_row[1]}"
+  assert row[4] == want_row[4], f"{tag}: retries {row[4]} != reference {want_row[4]}"
+  assert (row[0] >= 0.1) == (want_err >= 0.1), f"{tag}: failure flag differs"
+  np.testing.assert_allclose(row[3], want_row[3], rtol=1e-5, err_msg=f"{tag}: max_ev")
+  assert row[0] <= max(2 * want_err, 2e-6), f"{tag}: error {row[0]} vs {want_err}"
+  rf = _rel_fro(root, want_root)
+  assert rf <= tol, f"{tag}: rel-Frobenius {rf}"
+
+
+def _tol(engine):
+  return 2e-5 if engine == 1 else 1e-4
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+def test_golden_roots(golden_roots, engine):
+  if engine not in _engines():
+    pytest.skip("engine not available on this device")
+  g = golden_roots
+  for k in [str(n) for n in g["names"]]:
+    a = g[f"{k}/a"]
+    n = a.shape[0]
+    if engine != 1 and (n % 128 != 0):
+      continue
+    pad = int(g[f"{k}/pad"])
+    roots, metrics = _run(a[None], [int(g[f"{k}/p"])], None if pad < 0 else [pad],
+                          engine=engine, ridge_epsilon=float(g[f"{k}/ridge"]),
+                          relative_matrix_epsilon=bool(g[f"{k}/relative"]))
+    want = g[f"{k}/metrics"].astype(np.float32)
+    if k == "dst_all_padding":  # DST:400-408
+      assert np.abs(roots).sum() == 0.0 and metrics[0, 0] == 0.0
+      continue
+    _check_case(roots[0], metrics[0], g[f"{k}/root"], want, a, int(g[f"{k}/p"]),
+                _tol(engine), k)
+    if pad >= 0:  # padded rows / cols exactly zero (DST:397-398)
+      assert np.abs(roots[0][pad:]).sum() == 0 and np.abs(roots[0][:, pad:]).sum() == 0
+
+
+def test_n1_closed_form():
+  roots, metrics = _run(np.array([[[3.0]], [[0.5]]]), [4, 2])
+  want0 = N.matrix_inverse_pth_root(np.array([[3.0]], np.float32), 4)[0]
+  want1 = N.matrix_inverse_pth_root(np.array([[0.5]], np.float32), 2)[0]
+  np.testing.assert_allclose(roots[0], want0, rtol=1e-6)
+  np.testing.assert_allclose(roots[1], want1, rtol=1e-6)
+  assert metrics[0, 0] == 0 and metrics[0, 1] == 0
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+def test_mixed_batch_matches_oracle(engine):
+  """vmap semantics (DS:2742-2744): mixed p / padding in one batch, each matrix
+  behaves as if it ran alone."""
+  if engine not in _engines():
+    pytest.skip("engine not available on this device")
+  rng = np.random.default_rng(3)
+  n = 128 if engine == 1 else 256
+  mats, ps, pads = [], [], []
+  for i, (p, pad, kind) in enumerate([(2, n, "spec"), (4, n, "ema"), (6, n - 37, "ema"),
+                                      (8, n, "spec"), (4, 64, "spec"), (4, 0, "spec"),
+                                      (3, n, "ema"), (1, n, "spec"), (4, n, "lowrank")]):
+    m = max(pad, 1)
+    if kind == "spec":
+      a = gen_symmetric_matrix(rng, m, 10.0**(2 + i % 4))
+    elif kind == "ema":
+      a = ema_statistics(rng, m, 3 * m)
+    else:
+      v = rng.standard_normal((m, 3))
+      a = v @ v.T
+    full = np.eye(n)
+    full[:m, :m] = a
+    mats.append(full)
+    ps.append(p)
+    pads.append(pad)
+  xs = np.stack(mats).astype(np.float32)
+  roots, metrics = _run(xs, ps, pads, engine=engine)
+  want_r, want_m = N.matrix_inverse_pth_root_batched(xs, ps, pads)
+  for b in range(len(ps)):
+    if pads[b] == 0:
+      assert np.abs(roots[b]).sum() == 0 and metrics[b, 0] == 0
+      continue
+    _check_case(roots[b], metrics[b], want_r[b], want_m[b], xs[b], ps[b], _tol(engine),
+                f"batch[{b}] p={ps[b]} pad={pads[b]}")
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+def test_residual_no_worse_than_reference(engine):
+  if engine not in _engines():
+    pytest.skip("engine not available on this device")
+  rng = np.random.default_rng(5)
+  n = 256
+  xs = np.stack([gen_symmetric_matrix(rng, n, 1e3), ema_statistics(rng, n, 512),
+                 gen_symmetric_matrix(rng, n, 1e5)]).astype(np.float32)
+  ps = [4, 4, 2]
+  roots, metrics = _run(xs, ps, engine=engine)
+  for b in range(3):
+    ref_root, ref_m = N.matrix_inverse_pth_root(xs[b], ps[b])
+    eps = 1e-6 * ref_m.max_eigen_value
+    r_ref = N.root_residual(ref_root, xs[b], ps[b], eps)
+    r_gpu = N.root_residual(roots[b], xs[b], ps[b], eps)
+    assert r_gpu <= 2 * r_ref + 1e-6, (b, r_gpu, r_ref)
+    assert metrics[b, 1] == ref_m.inverse_pth_root_iters
+
+
+def test_dst_matrix_inverse_root_conditioning():
+  """DST:348-365: error < 0.1 up to condition number 1e6 (n=16, p=4, eps 1e-12)."""
+  rng = np.random.default_rng(1234)
+  mats = [gen_symmetric_matrix(rng, 16, 10.0**e) for e in range(2, 12)]
+  _, metrics = _run(np.stack(mats), [4] * 10, ridge_epsilon=1e-12)
+  for e in range(2, 7):
+    assert metrics[e - 2, 0] < 0.1
+
+
+def test_dst_padding_invariance():
+  """DST:367-398."""
+  rng = np.random.default_rng(1234)
+  for sz in (4, 32):
+    ms = (gen_symmetric_matrix(rng, sz, 1e3) * 1e-3).astype(np.float32)
+    rt, m = _run(ms[None], [4], ridge_epsilon=1e-3)
+    padded = np.eye(2 * sz, dtype=np.float32)
+    padded[:sz, :sz] = ms
+    prt, pm = _run(padded[None], [4], [sz], ridge_epsilon=1e-3)
+    np.testing.assert_allclose(rt[0], prt[0][:sz, :sz], rtol=1e-2 if sz == 4 else 5e-2)
+    assert pm[0, 0] <= 4 * m[0, 0] + 1e-7
+    assert np.abs(prt[0][sz:]).sum() == 0 and np.abs(prt[0][:, sz:]).sum() == 0
+
+
+def test_power_iteration_matches_oracle(golden_roots):
+  from precondition_b200 import ops
+  g = golden_roots
+  a = torch.as_tensor(g["pi/a"]).cuda()
+  lam, its = ops.power_iteration(a[None])
+  np.testing.assert_allclose(lam.cpu().numpy()[0], g["pi/s"], rtol=2e-6)
+  lam, its = ops.power_iteration(a[None], [25])
+  np.testing.assert_allclose(lam.cpu().numpy()[0], g["pi_pad/s"], rtol=2e-6)
+  rng = np.random.default_rng(8)
+  big = np.stack([ema_statistics(rng, 300, 100), gen_symmetric_matrix(rng, 300, 1e4)])
+  big = big.astype(np.float32)
+  lam, its = ops.power_iteration(torch.as_tensor(big).cuda())
+  for b in range(2):
+    _, s, it = N.power_iteration(big[b], return_iters=True)
+    np.testing.assert_allclose(lam.cpu().numpy()[b], s, rtol=5e-6)
+    assert abs(int(its[b]) - it) <= 1
+
+
+def test_invalid_arguments_fail_loudly():
+  from precondition_b200 import ops
+  x = torch.zeros((1, 4, 4))
+  with pytest.raises(RuntimeError):
+    ops.matrix_inverse_pth_root_batched(x, [4])  # CPU tensor: no fallback
