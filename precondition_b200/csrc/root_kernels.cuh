@@ -1,0 +1,135 @@
+// Kernel templates shared by the fp32 and the tcgen05 engines of the Newton
+// solver: (re)initialisation of a try and the final gather of roots / metrics.
+// `Bufs` abstracts how a logical matrix element is stored (fp32, or three bf16
+// planes whose sum is the fp32 value).
+#pragma once
+#include "root_common.cuh"
+
+namespace pc {
+
+// ---------------------------------------------------------------------------
+// element store/load policies: fp32 buffers (SIMT engine) or 3 bf16 planes (TC)
+// ---------------------------------------------------------------------------
+struct F32Bufs {
+  float* base[kNumBufs];
+  size_t mat_elems;  // n*n
+  __device__ __forceinline__ float* mat(int phys, int b, int batch) const {
+    return base[phys] + (size_t)b * mat_elems;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// (re)initialise a try: DS:866-875
+// ---------------------------------------------------------------------------
+template <class Bufs>
+__global__ void __launch_bounds__(1024)
+root_init_kernel(const float* __restrict__ xs, RootCtl* ctl, Bufs bufs, int batch, int n,
+                 RootParams prm, float* __restrict__ roots) {
+  __shared__ float scratch[32];
+  __shared__ uint32_t uscratch[32];
+  const int b = blockIdx.x;
+  RootCtl c = ctl[b];
+  if (!c.need_init) return;
+  const float* A = xs + (size_t)b * n * n;
+  const int pad = c.pad, p = c.p;
+  if (c.tries == 0) {
+    const float ev = prm.relative_eps ? c.max_ev : 1.0f;
+    c.max_ev = ev;
+    c.ridge = prm.ridge_epsilon * fmaxf(ev, 1e-25f);  // DS:830
+  }
+  const float alpha = -1.0f / (float)p;  // DS:774
+  if (n == 1) {  // DS:850-855
+    if (threadIdx.x == 0) {
+      const float a = pad > 0 ? A[0] : 0.f;
+      roots[(size_t)b] = powf(a + c.ridge, alpha);
+      c.need_init = 0; c.done = 1; c.active = 0;
+      c.m_err = 0.f; c.m_iters = 0.f; c.m_ratio = 0.f; c.m_retries = 0.f;
+      c.result_h = -1;  // already written
+      ctl[b] = c;
+    }
+    return;
+  }
+  float tenpow = 1.f;
+  for (int t = 0; t < c.tries; ++t) tenpow *= 10.f;
+  const float eps = c.ridge * tenpow;  // DS:869
+  // pass 1: Frobenius norm of the damped, masked matrix (DS:870)
+  float ss = 0.f;
+  const size_t total = (size_t)pad * pad;
+  for (size_t e = threadIdx.x; e < total; e += blockDim.x) {
+    const int i = (int)(e / pad), j = (int)(e - (size_t)i * pad);
+    float a = __ldg(A + (size_t)i * n + j);
+    if (i == j) a += eps;
+    ss = fmaf(a, a, ss);
+  }
+  const float norm = sqrtf(block_sum(ss, scratch));
+  const float z = (float)(1 + p) / (2.0f * norm);
+  const float h0 = powf(z, (float)(1.0 / (double)p));  // DS:873
+  // pass 2: D0 = alpha (zA_d - I_m), H0 = z^(1/p) I_m, err0 = max|zA_d - I_m|
+  uint32_t emax = 0;
+  const size_t nn = (size_t)n * n;
+  for (size_t e = threadIdx.x; e < nn; e += blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+    float d = 0.f, h = 0.f;
+    if (i < pad && j < pad) {
+      float a = __ldg(A + e);
+      if (i == j) a += eps;
+      const float m0 = a * z;                       // DS:871
+      const float e0 = m0 - (i == j ? 1.f : 0.f);   // M0 - I_m
+      const uint32_t ab = absbits(e0);
+      emax = ab > emax ? ab : emax;
+      d = alpha * e0;
+      h = (i == j) ? h0 : 0.f;
+    }
+    bufs.store(0, b, i, j, n, d);  // D[0]
+    bufs.store(2, b, i, j, n, h);  // H[0]
+  }
+  emax = block_max_u32(emax, uscratch);
+  if (threadIdx.x == 0) {
+    c.need_init = 0;
+    c.iter = 0;
+    c.cur = 0;
+    c.err = __uint_as_float(emax);  // DS:872
+    c.ratio = 1.0f;
+    root_after_error_update(c, prm);
+    ctl[b] = c;
+  }
+}
+
+
+struct F32Store : F32Bufs {
+  __device__ __forceinline__ void store(int phys, int b, int i, int j, int n, float v) const {
+    base[phys][(size_t)b * mat_elems + (size_t)i * n + j] = v;
+  }
+  __device__ __forceinline__ float load(int phys, int b, int i, int j, int n) const {
+    return base[phys][(size_t)b * mat_elems + (size_t)i * n + j];
+  }
+};
+
+
+template <class Bufs>
+__global__ void root_final_kernel(const RootCtl* __restrict__ ctl, Bufs bufs, int n,
+                                  float* __restrict__ roots, float* __restrict__ metrics) {
+  const int b = blockIdx.y;
+  const RootCtl& c = ctl[b];
+  const size_t nn = (size_t)n * n;
+  float* out = roots + (size_t)b * nn;
+  if (c.result_h != -1) {  // -1: already written by the n == 1 closed form
+    const bool zero = (c.result_h == -2) || (c.pad == 0) || !c.done;  // DS:930-937
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn;
+         e += (size_t)gridDim.x * blockDim.x) {
+      const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+      out[e] = zero ? 0.f : bufs.load(2 + c.result_h, b, i, j, n);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float* m = metrics + (size_t)b * PC_NUM_METRICS;
+    m[PC_METRIC_ERROR] = c.pad == 0 ? 0.f : c.m_err;
+    m[PC_METRIC_ITERS] = c.m_iters;
+    m[PC_METRIC_ERROR_RATIO] = c.m_ratio;
+    m[PC_METRIC_MAX_EV] = c.max_ev;
+    m[PC_METRIC_RETRIES] = c.m_retries;
+  }
+}
+
+
+}  // namespace pc
