@@ -304,12 +304,8 @@ def run_ours(a):
   peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
   achieved = (stats.gemm_flops / (stats.gemm_ms * 1e-3) / 1e12) if stats.gemm_ms > 0 else 0.0
   m_host = metrics.cpu().numpy()
-  resolved = "simt_fp32"
-  if engine in (_lib.PC_ENGINE_TC_BF16X6, _lib.PC_ENGINE_TC_BF16X3) or (
-      engine == _lib.PC_ENGINE_AUTO and lib.pc_device_supports_tcgen05() and n % 128 == 0
-      and n >= 256 and lib.pc_inverse_pth_root_workspace_bytes(1, n, 2) !=
-      lib.pc_inverse_pth_root_workspace_bytes(1, n, 1)):
-    resolved = "tcgen05_bf16x3" if engine == _lib.PC_ENGINE_TC_BF16X3 else "tcgen05_bf16x6"
+  resolved = {1: "simt_fp32", 2: "tcgen05_bf16x6", 3: "tcgen05_bf16x3"}[
+      lib.pc_resolve_engine(n, engine)]
   passes = {"simt_fp32": 1, "tcgen05_bf16x6": 6, "tcgen05_bf16x3": 3}[resolved]
   roofline = {
       "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -111,6 +111,8 @@ typedef struct {
 } pc_root_options;
 
 void pc_root_options_default(pc_root_options* opt);
+/* engine PC_ENGINE_AUTO resolves to for statistics of size n on the current device */
+int pc_resolve_engine(int n, int engine);
 
 size_t pc_inverse_pth_root_workspace_bytes(int batch, int n, int engine);
 
@@ -119,6 +121,12 @@ int pc_inverse_pth_root_batched(const float* xs, const int32_t* ps,
                                 const pc_root_options* opt, float* roots,
                                 float* metrics, void* workspace,
                                 size_t workspace_bytes, void* stream);
+
+/* Test hook for the tcgen05 engine: C[b] = A[b] * B[b]^T (fp32 in/out, computed as
+ * split-bf16 products, `passes` = 6 or 3), n % 128 == 0.  Workspace of at least
+ * pc_inverse_pth_root_workspace_bytes(batch, n, PC_ENGINE_TC_BF16X6) bytes. */
+int pc_debug_tc_gemm(const float* a, const float* b, float* c, int batch, int n, int passes,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* power_iteration alone (DS:595-652): lambda[b] = Rayleigh quotient of the last
  * executed step, iters[b] = steps taken (may be NULL). */

@@ -20,8 +20,9 @@ PC_NUM_METRICS = 5
 EXPORTED_SYMBOLS = (
     "pc_version", "pc_last_error", "pc_device_supports_tcgen05", "pc_stats_reset",
     "pc_stats_get",
-    "pc_root_options_default", "pc_inverse_pth_root_workspace_bytes",
-    "pc_inverse_pth_root_batched", "pc_power_iteration_batched", "pc_grouped_gemm",
+    "pc_root_options_default", "pc_resolve_engine",
+    "pc_inverse_pth_root_workspace_bytes",
+    "pc_inverse_pth_root_batched", "pc_debug_tc_gemm", "pc_power_iteration_batched", "pc_grouped_gemm",
     "pc_quantize_batched", "pc_dequantize_batched",
     "pc_graft_momentum_workspace_bytes", "pc_graft_momentum",
 )
@@ -96,11 +97,15 @@ def load() -> ctypes.CDLL:
   lib.pc_stats_get.restype = None
   lib.pc_root_options_default.argtypes = [ctypes.POINTER(RootOptions)]
   lib.pc_root_options_default.restype = None
+  lib.pc_resolve_engine.argtypes = [i32, i32]
+  lib.pc_resolve_engine.restype = i32
   lib.pc_inverse_pth_root_workspace_bytes.argtypes = [i32, i32, i32]
   lib.pc_inverse_pth_root_workspace_bytes.restype = sz
   lib.pc_inverse_pth_root_batched.argtypes = [vp, vp, vp, i32, i32,
                                               ctypes.POINTER(RootOptions), vp, vp, vp, sz, vp]
   lib.pc_inverse_pth_root_batched.restype = i32
+  lib.pc_debug_tc_gemm.argtypes = [vp, vp, vp, i32, i32, i32, vp, sz, vp]
+  lib.pc_debug_tc_gemm.restype = i32
   lib.pc_power_iteration_batched.argtypes = [vp, vp, i32, i32, i32, f32, vp, vp, vp]
   lib.pc_power_iteration_batched.restype = i32
   lib.pc_grouped_gemm.argtypes = [vp, i32, i32, i32, vp]

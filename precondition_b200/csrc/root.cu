@@ -26,7 +26,7 @@ bool build_program(int p, Program* out) {
       if (!used[q]) { used[q] = true; return LB_Q0 + q; }
     return -100;
   };
-  int mat = LB_D, power = LB_NONE, n = 0;
+  int mat = LB_MI, power = LB_NONE, n = 0;
   auto release_if_unreferenced = [&](int buf) {
     if (buf >= LB_Q0 && buf != mat && buf != power) used[buf - LB_Q0] = false;
   };
@@ -39,43 +39,35 @@ bool build_program(int p, Program* out) {
   while (i > 0) {
     if (i & 1) {
       if (power == LB_NONE) {
-        power = mat;  // multiply by the identity (DS:661, DS:670-672)
+        power = mat;  // mat @ I (DS:661, DS:670-672) is exact: alias instead
       } else {
         int dst = alloc();
         if (dst < 0) return false;
-        // dev(mat * power) = mat + power + mat*power
-        if (!push(Step{(int8_t)dst, (int8_t)mat, (int8_t)power, (int8_t)mat,
-                       (int8_t)power, 0, {0, 0}, 1.f, 1.f}))
-          return false;
+        if (!push(Step{(int8_t)dst, (int8_t)mat, (int8_t)power, 0})) return false;  // DS:671
         int old = power;
         power = dst;
         release_if_unreferenced(old);
       }
     }
     i >>= 1;
-    if (i > 0) {
+    if (i > 0) {  // the reference squares once more at i == 0 and discards it
       int dst = alloc();
       if (dst < 0) return false;
-      // dev(mat^2) = 2 mat + mat*mat   (DS:674)
-      if (!push(Step{(int8_t)dst, (int8_t)mat, (int8_t)mat, (int8_t)mat, LB_NONE, 0,
-                     {0, 0}, 2.f, 0.f}))
-        return false;
+      if (!push(Step{(int8_t)dst, (int8_t)mat, (int8_t)mat, 0})) return false;  // DS:674
       int old = mat;
       mat = dst;
       release_if_unreferenced(old);
     }
   }
-  // D' = Q_p D - Q_p / p + D   (DS:845 in deviation form), err = p max|D'|
-  if (!push(Step{LB_DN, (int8_t)power, LB_D, (int8_t)power, LB_D, 1, {0, 0},
-                 -1.0f / (float)p, 1.f}))
-    return false;
+  // M' = M_i^p M (DS:845); epilogue also emits M_i' (DS:844) and err (DS:847)
+  if (!push(Step{LB_MN, (int8_t)power, LB_M, 1})) return false;
   out->nsteps = n;
   return true;
 }
 
 __constant__ Program c_programs[kMaxP + 1];
-// H' = H + H D  (DS:846), co-scheduled with step 0 of every program
-__constant__ Step c_hstep = {LB_HN, LB_H, LB_D, LB_H, LB_NONE, 0, {0, 0}, 1.f, 0.f};
+// H' = H M_i  (DS:846), co-scheduled with step 0 of every program
+__constant__ Step c_hstep = {LB_HN, LB_H, LB_MI, 0};
 
 static Program h_programs[kMaxP + 1];
 static bool programs_uploaded[64] = {false};
@@ -229,9 +221,13 @@ root_phase_simt_kernel(F32Store bufs, const RootCtl* __restrict__ ctl,
     // tile fully in the padding: result is exactly zero
     const int cur = c.cur;
     float* out = bufs.mat(physical_buf(st.dst, cur), b, 0);
+    float* out_mi = st.emit_mi ? bufs.mat(physical_buf(LB_MIN, cur), b, 0) : nullptr;
     for (int e = threadIdx.x; e < kSimtBM * kSimtBN; e += blockDim.x) {
       int i = tile_m * kSimtBM + e / kSimtBN, j = tile_n * kSimtBN + e % kSimtBN;
-      if (i < n && j < n) out[(size_t)i * n + j] = 0.f;
+      if (i < n && j < n) {
+        out[(size_t)i * n + j] = 0.f;
+        if (out_mi) out_mi[(size_t)i * n + j] = 0.f;
+      }
     }
     return;
   }
@@ -239,10 +235,9 @@ root_phase_simt_kernel(F32Store bufs, const RootCtl* __restrict__ ctl,
   const SquareView A{bufs.mat(physical_buf(st.a, cur), b, 0), n, lim};
   // operands are symmetric: B(j,k) = B[j][k] reads rows (coalesced along k)
   const SquareView B{bufs.mat(physical_buf(st.b, cur), b, 0), n, lim};
-  const float* x1 = st.x1 >= 0 ? bufs.mat(physical_buf(st.x1, cur), b, 0) : nullptr;
-  const float* x2 = st.x2 >= 0 ? bufs.mat(physical_buf(st.x2, cur), b, 0) : nullptr;
   float* out = bufs.mat(physical_buf(st.dst, cur), b, 0);
-  const float c1 = st.c1, c2 = st.c2;
+  float* out_mi = st.emit_mi ? bufs.mat(physical_buf(LB_MIN, cur), b, 0) : nullptr;
+  const float alpha = -1.0f / (float)c.p, one_minus_alpha = 1.0f - alpha;
   uint32_t emax = 0;
   simt_gemm_tile(lim, tile_m, tile_n, A, B, true, true, sm,
                  [&](int i, int j0, const float* acc) {
@@ -251,19 +246,18 @@ root_phase_simt_kernel(F32Store bufs, const RootCtl* __restrict__ ctl,
                    for (int q = 0; q < 4; ++q) {
                      const int j = j0 + q;
                      if (j >= n) continue;
-                     float v = 0.f;
-                     if (i < lim && j < lim) {
-                       const size_t idx = (size_t)i * n + j;
-                       v = acc[q];
-                       if (x1) v = fmaf(c1, x1[idx], v);
-                       if (x2) v = fmaf(c2, x2[idx], v);
-                     }
+                     const bool in = (i < lim && j < lim);
+                     const float v = in ? acc[q] : 0.f;
                      out[(size_t)i * n + j] = v;
-                     const uint32_t ab = absbits(v);
-                     emax = ab > emax ? ab : emax;
+                     if (out_mi) {
+                       out_mi[(size_t)i * n + j] =
+                           in ? mi_from_m(v, i == j, alpha, one_minus_alpha) : 0.f;
+                       const uint32_t ab = absbits(v - ((in && i == j) ? 1.f : 0.f));
+                       emax = ab > emax ? ab : emax;
+                     }
                    }
                  });
-  if (st.reduce_err) {
+  if (st.emit_mi) {
     emax = warp_max_u32(emax);
     if ((threadIdx.x & 31) == 0 && emax) atomicMax(errbits + b, emax);
   }
@@ -278,9 +272,8 @@ __global__ void root_control_kernel(RootCtl* ctl, uint32_t* errbits, int batch,
   if (b >= batch) return;
   RootCtl c = ctl[b];
   if (c.active) {
-    const float maxd = __uint_as_float(errbits[b]);
+    const float new_err = __uint_as_float(errbits[b]);  // max|M' - I_m|, DS:847
     errbits[b] = 0u;
-    const float new_err = (float)c.p * maxd;  // max|M' - I_m|, DS:847
     c.ratio = new_err / c.err;                // DS:848
     c.err = new_err;
     c.iter += 1;
@@ -531,6 +524,8 @@ void pc_root_options_default(pc_root_options* opt) {
   opt->engine = PC_ENGINE_AUTO;
   opt->reserved = 0;
 }
+
+int pc_resolve_engine(int n, int engine) { return pc::resolve_engine(engine, n); }
 
 size_t pc_inverse_pth_root_workspace_bytes(int batch, int n, int engine) {
   if (batch <= 0 || n <= 0) return 0;

@@ -1,18 +1,22 @@
 // Shared state of the batched coupled-Newton inverse p-th root solver.
 //
-// Algorithm = matrix_inverse_pth_root of the reference (DS:702-940) in
-// "deviation form":  with I_m the masked identity, the solver carries
-//     D = (I_m - M) / p        (so that M_i = I_m + D,  DS:844)
-//     H                         (DS:846)
-// and evaluates  dev(X Y) = dev(X) + dev(Y) + dev(X) dev(Y)  for the binary
-// powering chain of mat_power (DS:655-678), finishing with
-//     D' = D - Q_p / p + Q_p D          (== (I_m - M_i^p M) / p,  DS:845)
-//     H' = H + H D                      (DS:846)
-//     err' = p * max|D'|                (== max|M' - I_m|,  DS:847)
-// Every GEMM therefore has the shape  OUT = A*B + c1*X1 + c2*X2  and all
-// operands are symmetric polynomials in the input, so "B^T" == B.
-// The number of GEMMs is the necessary count G(p), not the 6-8 the
-// reference issues.
+// Algorithm = matrix_inverse_pth_root of the reference (DS:702-940), in the
+// reference's own recurrence (I_m = identity masked by padding_start):
+//     M_i = (1 - alpha) I_m + alpha M,   alpha = -1/p           (DS:844)
+//     M'  = M_i^p M                      (mat_power, DS:655-678; DS:845)
+//     H'  = H M_i                                                 (DS:846)
+//     err = max|M' - I_m|                                         (DS:847)
+// M_i^p is evaluated with the same LSB-first binary powering and operand order
+// as mat_power, minus its no-op products (multiply by I, the discarded last
+// squaring): G(p) GEMMs per iteration instead of the 6-8 issued
+// upstream.  Every GEMM is a plain product OUT = A*B; the step that produces M'
+// also emits M_i' and reduces err in its epilogue.  All operands are symmetric
+// polynomials in the input, so the kernels read B by rows ("B^T" == B up to
+// rounding).
+//
+// A measured alternative -- iterating on D = (I_m - M)/p -- reaches lower final
+// errors but is ~10x less accurate on ill-conditioned statistics
+// (profiles/r01_precision_probe.md), so it is not used.
 #pragma once
 #include "common.cuh"
 
@@ -24,22 +28,22 @@ constexpr int kMaxSteps = 8;
 // logical buffer ids (resolved per matrix with its ping-pong bit `cur`)
 enum : int8_t {
   LB_NONE = -1,
-  LB_D = 0,   // current D
-  LB_DN = 1,  // next D
-  LB_H = 2,   // current H
-  LB_HN = 3,  // next H
-  LB_Q0 = 4,
-  LB_Q1 = 5,
-  LB_Q2 = 6,
-  LB_Q3 = 7,
-  kNumBufs = 8
+  LB_M = 0,    // current M
+  LB_MN = 1,   // next M
+  LB_MI = 2,   // current M_i
+  LB_MIN = 3,  // next M_i
+  LB_H = 4,    // current H
+  LB_HN = 5,   // next H
+  LB_Q0 = 6,
+  LB_Q1 = 7,
+  LB_Q2 = 8,
+  LB_Q3 = 9,
+  kNumBufs = 10
 };
 
 struct Step {
-  int8_t dst, a, b, x1, x2;
-  int8_t reduce_err;  // epilogue reduces max|out| into errbits (the D' step)
-  int8_t pad_[2];
-  float c1, c2;
+  int8_t dst, a, b;
+  int8_t emit_mi;  // this step produces M': also write M_i' and reduce err
 };
 
 struct Program {
@@ -55,8 +59,8 @@ struct RootCtl {
   int done;
   int iter;
   int tries;
-  int cur;        // ping-pong bit of D / H
-  int result_h;   // physical H buffer (0/1) holding the answer
+  int cur;        // ping-pong bit of M / M_i / H
+  int result_h;   // >=0: H ping-pong slot holding the answer; -1 written; -2 zeros
   float err;
   float ratio;
   float max_ev;
@@ -74,17 +78,25 @@ struct RootParams {
 
 __host__ __device__ inline int physical_buf(int logical, int cur) {
   switch (logical) {
-    case LB_D: return cur;
-    case LB_DN: return cur ^ 1;
-    case LB_H: return 2 + cur;
-    case LB_HN: return 2 + (cur ^ 1);
-    default: return logical;  // Q buffers map 1:1 (ids 4..7)
+    case LB_M: return cur;
+    case LB_MN: return cur ^ 1;
+    case LB_MI: return 2 + cur;
+    case LB_MIN: return 2 + (cur ^ 1);
+    case LB_H: return 4 + cur;
+    case LB_HN: return 4 + (cur ^ 1);
+    default: return logical;  // Q buffers map 1:1 (ids 6..9)
   }
 }
 
-// Host: builds the per-exponent step list.  Returns false if p needs more than
-// kMaxSteps GEMMs or more than 4 scratch buffers.
+// Host: builds the per-exponent step list (false if p is out of range).
 bool build_program(int p, Program* out);
+
+// M_i element from an M element, mirroring DS:844 without FMA contraction.
+__device__ __forceinline__ float mi_from_m(float m, bool diag_in_mask, float alpha,
+                                           float one_minus_alpha) {
+  const float t = __fmul_rn(alpha, m);
+  return __fadd_rn(diag_in_mask ? one_minus_alpha : 0.f, t);
+}
 
 // Device-side end-of-step bookkeeping shared by the init and control kernels;
 // mirrors the loop predicates of DS:836-840 and DS:862-885.

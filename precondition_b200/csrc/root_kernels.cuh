@@ -64,24 +64,27 @@ root_init_kernel(const float* __restrict__ xs, RootCtl* ctl, Bufs bufs, int batc
   const float norm = sqrtf(block_sum(ss, scratch));
   const float z = (float)(1 + p) / (2.0f * norm);
   const float h0 = powf(z, (float)(1.0 / (double)p));  // DS:873
-  // pass 2: D0 = alpha (zA_d - I_m), H0 = z^(1/p) I_m, err0 = max|zA_d - I_m|
+  // pass 2: M0 = z A_d, M_i0 = (1-alpha) I_m + alpha M0, H0 = z^(1/p) I_m,
+  //         err0 = max|M0 - I_m|
+  const float one_minus_alpha = 1.0f - alpha;
   uint32_t emax = 0;
   const size_t nn = (size_t)n * n;
   for (size_t e = threadIdx.x; e < nn; e += blockDim.x) {
     const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
-    float d = 0.f, h = 0.f;
+    float m0 = 0.f, mi = 0.f, h = 0.f;
     if (i < pad && j < pad) {
       float a = __ldg(A + e);
       if (i == j) a += eps;
-      const float m0 = a * z;                       // DS:871
+      m0 = a * z;                                   // DS:871
       const float e0 = m0 - (i == j ? 1.f : 0.f);   // M0 - I_m
       const uint32_t ab = absbits(e0);
       emax = ab > emax ? ab : emax;
-      d = alpha * e0;
+      mi = mi_from_m(m0, i == j, alpha, one_minus_alpha);
       h = (i == j) ? h0 : 0.f;
     }
-    bufs.store(0, b, i, j, n, d);  // D[0]
-    bufs.store(2, b, i, j, n, h);  // H[0]
+    bufs.store(0, b, i, j, n, m0);  // M[0]
+    bufs.store(2, b, i, j, n, mi);  // M_i[0]
+    bufs.store(4, b, i, j, n, h);   // H[0]
   }
   emax = block_max_u32(emax, uscratch);
   if (threadIdx.x == 0) {
@@ -118,7 +121,7 @@ __global__ void root_final_kernel(const RootCtl* __restrict__ ctl, Bufs bufs, in
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn;
          e += (size_t)gridDim.x * blockDim.x) {
       const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
-      out[e] = zero ? 0.f : bufs.load(2 + c.result_h, b, i, j, n);
+      out[e] = zero ? 0.f : bufs.load(4 + c.result_h, b, i, j, n);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {

@@ -1,20 +1,681 @@
-// tcgen05 split-bf16 GEMM engine for the Newton chain -- placeholder until the
-// tensor-core kernels land; the engine reports itself unavailable so that
-// PC_ENGINE_AUTO resolves to the CUDA-core fp32 path.
+// tcgen05 / TMEM / TMA engine for the Newton-chain GEMMs of the inverse p-th root
+// solver (sm_100a).
+//
+// Number format: every fp32 matrix X is stored as three bf16 planes X0+X1+X2 == X
+// (exact: 8+8+8 mantissa bits).  A product A*B is evaluated on the tensor cores
+// as  sum_{i+j<=2} A_i B_j  (6 bf16 MMAs, "BF16x6", dropped terms <= 2^-23 |a||b|;
+// PC_ENGINE_TC_BF16X3 keeps i+j<=1).  The tensor core accumulates in fp32 with
+// truncating adds; over K=1024 that costs ~10x in accuracy on ill-conditioned
+// statistics (profiles/r01_precision_probe.md).  Therefore only a short K-chunk
+// (kChunkKB * 64 columns) is accumulated in TMEM; the epilogue warps pull each
+// chunk with tcgen05.ld and add it to an fp32 register accumulator with
+// round-to-nearest, overlapped with the MMAs of the next chunk (2 TMEM stages).
+//
+// Kernel anatomy (one persistent CTA per SM, 256 threads):
+//   warp 0   TMA producer: 2 * kLP plane tiles (128 x 64 bf16, SWIZZLE_128B) per
+//            k-block into a kStages-deep smem ring, mbarrier complete_tx
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1
+//            .kind::f16 (M=128, N=128, K=16), tcgen05.commit frees smem slots and
+//            publishes TMEM chunks
+//   warp 2   TMEM allocator (256 columns = 2 chunk accumulators)
+//   warps 4-7  chunk accumulation + epilogue: split to 3 bf16 planes, optional
+//            M_i' emission and max|M' - I_m| reduction (DS:844-847)
+// Operands are symmetric, so both A and B tiles are K-major row blocks of the
+// same row-major planes (no transposes anywhere).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "root_kernels.cuh"
 #include "tc_engine.cuh"
 
 namespace pc {
-bool tc_engine_available() { return false; }
-size_t tc_engine_bytes(int, int) { return 0; }
-int tc_engine_init(TcEngine*, void*, int, int, int) {
-  set_error("tcgen05 engine not built");
-  return PC_ERR_UNSUPPORTED;
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_UMMA_K = 16;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;  // one plane tile: 16 KiB
+constexpr int TC_THREADS = 256;
+constexpr int TC_TMEM_COLS = 256;
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-int tc_engine_iteration(TcEngine*, const float*, RootCtl*, uint32_t*, RootParams, float*, int,
-                        cudaStream_t) {
-  return PC_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int tc_engine_final(TcEngine*, const RootCtl*, float*, float*, cudaStream_t) {
-  return PC_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued tcgen05.mma have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+//   bits [0,14) start address >> 4, [16,30) LBO >> 4 (unused for swizzled K-major),
+//   [32,46) SBO >> 4 = 1024 B between 8-row groups, [46,48) version = 1,
+//   [61,64) layout type = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kIdescBf16M128N128 =
+    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+    ((uint32_t)(TC_BM >> 4) << 24);
+
+// ---------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------
+struct TcParams {
+  uint16_t* plane[3];   // plane p: [kNumBufs][batch][n][n] bf16
+  size_t buf_stride;    // batch * n * n
+  size_t mat_stride;    // n * n
+  const RootCtl* ctl;
+  uint32_t* errbits;
+  int n, batch, tiles;  // tiles per dimension (n / 128)
+};
+
+struct TcWork {
+  int b, tm, tn, kblocks, cur, p, pad;
+  Step st;
+};
+
+__device__ __forceinline__ bool tc_get_work(const TcParams& P, const Program* progs, int s,
+                                            int w, TcWork& out) {
+  const int per_mat = 2 * P.tiles * P.tiles;
+  const int b = w / per_mat;
+  int r = w - b * per_mat;
+  const int op = r / (P.tiles * P.tiles);
+  r -= op * P.tiles * P.tiles;
+  const RootCtl& c = P.ctl[b];
+  if (!c.active) return false;
+  if (op == 1) {
+    if (s != 0) return false;
+    out.st = Step{LB_HN, LB_H, LB_MI, 0};
+  } else {
+    const Program& pr = progs[c.p];
+    if (s >= pr.nsteps) return false;
+    out.st = pr.steps[s];
+  }
+  out.b = b;
+  out.tm = r / P.tiles;
+  out.tn = r - out.tm * P.tiles;
+  out.cur = c.cur;
+  out.p = c.p;
+  out.pad = c.pad;
+  out.kblocks = (c.pad + TC_BK - 1) / TC_BK;  // columns >= pad are zero
+  return true;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+  return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+// writes 32 consecutive fp32 values of one row as three bf16 planes (64 B each)
+__device__ __forceinline__ void store_planes32(const TcParams& P, size_t elem_off,
+                                               const float (&v)[32]) {
+  uint32_t w0[16], w1[16], w2[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __nv_bfloat16 a0[2], a1[2], a2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float x = v[2 * i + h];
+      a0[h] = __float2bfloat16_rn(x);
+      const float r1 = x - __bfloat162float(a0[h]);
+      a1[h] = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(a1[h]);
+      a2[h] = __float2bfloat16_rn(r2);
+    }
+    w0[i] = pack_bf16x2(a0[0], a0[1]);
+    w1[i] = pack_bf16x2(a1[0], a1[1]);
+    w2[i] = pack_bf16x2(a2[0], a2[1]);
+  }
+  uint4* d0 = reinterpret_cast<uint4*>(P.plane[0] + elem_off);
+  uint4* d1 = reinterpret_cast<uint4*>(P.plane[1] + elem_off);
+  uint4* d2 = reinterpret_cast<uint4*>(P.plane[2] + elem_off);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    d0[q] = make_uint4(w0[4 * q], w0[4 * q + 1], w0[4 * q + 2], w0[4 * q + 3]);
+    d1[q] = make_uint4(w1[4 * q], w1[4 * q + 1], w1[4 * q + 2], w1[4 * q + 3]);
+    d2[q] = make_uint4(w2[4 * q], w2[4 * q + 1], w2[4 * q + 2], w2[4 * q + 3]);
+  }
+}
+
+template <int kLP, int kStages, int kChunkKB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_phase_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                const __grid_constant__ CUtensorMap tmap2, const TcParams P,
+                const Program* __restrict__ progs, int s, int total_work) {
+  constexpr int kStageBytes = 2 * kLP * TC_TILE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // barriers live after the operand ring
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_base + 8u * (kStages + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(
+      smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap0);
+    tma_prefetch_desc(&tmap1);
+    if (kLP > 2) tma_prefetch_desc(&tmap2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        TcWork wk;
+        if (!tc_get_work(P, progs, s, w, wk)) continue;
+        const int pa = physical_buf(wk.st.a, wk.cur), pb = physical_buf(wk.st.b, wk.cur);
+        for (int kb = 0; kb < wk.kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t dst = smem_base + stage * kStageBytes;
+          mbar_expect_tx(full_bar(stage), kStageBytes);
+          const CUtensorMap* maps[3] = {&tmap0, &tmap1, &tmap2};
+#pragma unroll
+          for (int pl = 0; pl < kLP; ++pl) {
+            tma_load_4d(dst + pl * TC_TILE_BYTES, maps[pl], full_bar(stage), kb * TC_BK,
+                        wk.tm * TC_BM, wk.b, pa);
+            tma_load_4d(dst + (kLP + pl) * TC_TILE_BYTES, maps[pl], full_bar(stage), kb * TC_BK,
+                        wk.tn * TC_BN, wk.b, pb);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int chunk = 0;  // running chunk counter -> TMEM stage / parity
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        TcWork wk;
+        if (!tc_get_work(P, progs, s, w, wk)) continue;
+        for (int kb0 = 0; kb0 < wk.kblocks; kb0 += kChunkKB, ++chunk) {
+          const int acc = chunk & 1;
+          const uint32_t acc_phase = (chunk >> 1) & 1;
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * TC_BN;
+          const int kb1 = min(kb0 + kChunkKB, wk.kblocks);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t a0 = smem_base + stage * kStageBytes;
+            const uint32_t b0 = a0 + kLP * TC_TILE_BYTES;
+            bool first = (kb == kb0);
+            // smallest terms first: plane pairs (i, j) with i + j descending
+#pragma unroll
+            for (int sum = kLP - 1; sum >= 0; --sum) {
+#pragma unroll
+              for (int i = 0; i <= sum; ++i) {
+                const int j = sum - i;
+                const uint64_t ad = make_kmajor_sw128_desc(a0 + i * TC_TILE_BYTES);
+                const uint64_t bd = make_kmajor_sw128_desc(b0 + j * TC_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                  // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in (addr >> 4)
+                  umma_bf16(tmem_d, ad + 2u * k, bd + 2u * k, kIdescBf16M128N128,
+                            (first && k == 0) ? 0u : 1u);
+                  if (k == 0) first = false;
+                }
+              }
+            }
+            umma_commit(empty_bar(stage));  // frees the smem slot when the MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(tfull_bar(acc));  // chunk accumulator complete
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============ chunk accumulation + epilogue (128 threads = 128 TMEM lanes) ============
+    const int q = warp & 3;              // TMEM lane quadrant of this warp
+    const int row_in_tile = q * 32 + lane;
+    int chunk = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      TcWork wk;
+      if (!tc_get_work(P, progs, s, w, wk)) continue;
+      float sum[TC_BN];
+#pragma unroll
+      for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
+      for (int kb0 = 0; kb0 < wk.kblocks; kb0 += kChunkKB, ++chunk) {
+        const int acc = chunk & 1;
+        const uint32_t acc_phase = (chunk >> 1) & 1;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN;
+#pragma unroll
+        for (int c = 0; c < TC_BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      // ---- epilogue: OUT = sum; optional M_i' and err (DS:844-847) ----
+      const int row = wk.tm * TC_BM + row_in_tile;
+      const int pd = physical_buf(wk.st.dst, wk.cur);
+      const size_t out_off = (size_t)pd * P.buf_stride + (size_t)wk.b * P.mat_stride +
+                             (size_t)row * P.n + (size_t)wk.tn * TC_BN;
+      const size_t mi_off = (size_t)physical_buf(LB_MIN, wk.cur) * P.buf_stride +
+                            (size_t)wk.b * P.mat_stride + (size_t)row * P.n +
+                            (size_t)wk.tn * TC_BN;
+      const float alpha = -1.0f / (float)wk.p, oma = 1.0f - alpha;
+      uint32_t emax = 0;
+#pragma unroll
+      for (int c = 0; c < TC_BN / 32; ++c) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = sum[c * 32 + i];
+        store_planes32(P, out_off + c * 32, v);
+        if (wk.st.emit_mi) {
+          const int col0 = wk.tn * TC_BN + c * 32;
+          float mi[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool dg = (col0 + i == row) && (row < wk.pad);
+            const uint32_t ab = absbits(v[i] - (dg ? 1.f : 0.f));
+            emax = ab > emax ? ab : emax;
+            mi[i] = mi_from_m(v[i], dg, alpha, oma);
+          }
+          store_planes32(P, mi_off + c * 32, mi);
+        }
+      }
+      if (wk.st.emit_mi) {
+        emax = warp_max_u32(emax);
+        if (lane == 0 && emax) atomicMax(P.errbits + wk.b, emax);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------
+// plane store/load policy for the shared init / final kernels
+// ---------------------------------------------------------------------------
+struct PlaneStore {
+  uint16_t* plane[3];
+  size_t buf_stride, mat_elems;
+  __device__ __forceinline__ void store(int phys, int b, int i, int j, int n, float v) const {
+    const size_t off = (size_t)phys * buf_stride + (size_t)b * mat_elems + (size_t)i * n + j;
+    const __nv_bfloat16 a0 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(a0);
+    const __nv_bfloat16 a1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(a1);
+    plane[0][off] = __bfloat16_as_ushort(a0);
+    plane[1][off] = __bfloat16_as_ushort(a1);
+    plane[2][off] = __bfloat16_as_ushort(__float2bfloat16_rn(r2));
+  }
+  __device__ __forceinline__ float load(int phys, int b, int i, int j, int n) const {
+    const size_t off = (size_t)phys * buf_stride + (size_t)b * mat_elems + (size_t)i * n + j;
+    const float x0 = __bfloat162float(__ushort_as_bfloat16(plane[0][off]));
+    const float x1 = __bfloat162float(__ushort_as_bfloat16(plane[1][off]));
+    const float x2 = __bfloat162float(__ushort_as_bfloat16(plane[2][off]));
+    return (x2 + x1) + x0;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+bool tc_engine_available() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return false;
+  return major == 10;
+}
+
+size_t tc_engine_bytes(int batch, int n) {
+  return (size_t)3 * kNumBufs * batch * n * n * sizeof(uint16_t) + 1024;
+}
+
+struct TcHostState {
+  CUtensorMap maps[3];
+  TcParams prm;
+  Program* progs_dev;
+};
+
+static Program* g_progs_dev[64] = {nullptr};
+
+int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
+  PC_REQUIRE(n % TC_BM == 0, "tcgen05 engine needs n %% 128 == 0");
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return PC_ERR_UNSUPPORTED;
+  }
+  e->batch = batch; e->n = n; e->passes = passes;
+  auto* hs = new TcHostState();
+  e->host_state = hs;
+  uint16_t* base = reinterpret_cast<uint16_t*>(align_up((size_t)mem, 1024));
+  const size_t buf_stride = (size_t)batch * n * n;
+  for (int pl = 0; pl < 3; ++pl) {
+    uint16_t* plane = base + (size_t)pl * kNumBufs * buf_stride;
+    hs->prm.plane[pl] = plane;
+    for (int k = 0; k < kNumBufs; ++k) e->planes[k][pl] = plane + (size_t)k * buf_stride;
+    cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)batch, (cuuint64_t)kNumBufs};
+    cuuint64_t strides[3] = {(cuuint64_t)n * 2, (cuuint64_t)n * n * 2,
+                             (cuuint64_t)buf_stride * 2};
+    cuuint32_t box[4] = {TC_BK, TC_BM, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&hs->maps[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, plane, dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed with %d", (int)r);
+      delete hs;
+      e->host_state = nullptr;
+      return PC_ERR_CUDA;
+    }
+  }
+  hs->prm.buf_stride = buf_stride;
+  hs->prm.mat_stride = (size_t)n * n;
+  hs->prm.n = n; hs->prm.batch = batch; hs->prm.tiles = n / TC_BM;
+  // device copy of the step programs (the tc kernel reads them from global memory)
+  int dev = 0;
+  PC_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 64 && !g_progs_dev[dev]) {
+    Program hp[kMaxP + 1];
+    memset(hp, 0, sizeof(hp));
+    for (int p = 1; p <= kMaxP; ++p) build_program(p, &hp[p]);
+    PC_CUDA_CHECK(cudaMalloc(&g_progs_dev[dev], sizeof(hp)));
+    PC_CUDA_CHECK(cudaMemcpy(g_progs_dev[dev], hp, sizeof(hp), cudaMemcpyHostToDevice));
+  }
+  hs->progs_dev = g_progs_dev[dev < 64 ? dev : 0];
+  return PC_OK;
+}
+
+template <int kLP, int kStages, int kChunkKB>
+static int launch_phase(TcHostState* hs, int s, int total_work, int grid, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel<kLP, kStages, kChunkKB>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  tc_phase_kernel<kLP, kStages, kChunkKB><<<grid, TC_THREADS, smem, stream>>>(
+      hs->maps[0], hs->maps[1], hs->maps[2], hs->prm, hs->progs_dev, s, total_work);
+  return PC_OK;
+}
+
+int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* errbits,
+                        RootParams prm, float* roots, int max_steps, cudaStream_t stream) {
+  auto* hs = static_cast<TcHostState*>(e->host_state);
+  hs->prm.ctl = ctl;
+  hs->prm.errbits = errbits;
+  PlaneStore ps;
+  for (int pl = 0; pl < 3; ++pl) ps.plane[pl] = hs->prm.plane[pl];
+  ps.buf_stride = hs->prm.buf_stride;
+  ps.mat_elems = hs->prm.mat_stride;
+  root_init_kernel<PlaneStore><<<e->batch, 1024, 0, stream>>>(xs, ctl, ps, e->batch, e->n, prm,
+                                                             roots);
+  count_launch(1);
+  int sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int total_work = e->batch * 2 * hs->prm.tiles * hs->prm.tiles;
+  const int grid = total_work < sms ? total_work : sms;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (gemm_timing_enabled()) {
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, stream);
+  }
+  for (int s = 0; s < max_steps; ++s) {
+    int rc = e->passes == 6 ? launch_phase<3, 2, 1>(hs, s, total_work, grid, stream)
+                            : launch_phase<2, 3, 1>(hs, s, total_work, grid, stream);
+    if (rc != PC_OK) return rc;
+  }
+  if (ev0) { cudaEventRecord(ev1, stream); gemm_timing_record(ev0, ev1); }
+  count_launch(max_steps);
+  gemm_count(max_steps);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+int tc_engine_final(TcEngine* e, const RootCtl* ctl, float* roots, float* metrics,
+                    cudaStream_t stream) {
+  auto* hs = static_cast<TcHostState*>(e->host_state);
+  PlaneStore ps;
+  for (int pl = 0; pl < 3; ++pl) ps.plane[pl] = hs->prm.plane[pl];
+  ps.buf_stride = hs->prm.buf_stride;
+  ps.mat_elems = hs->prm.mat_stride;
+  dim3 fgrid((unsigned)std::min<size_t>(((size_t)e->n * e->n + 255) / 256, 64), e->batch);
+  root_final_kernel<PlaneStore><<<fgrid, 256, 0, stream>>>(ctl, ps, e->n, roots, metrics);
+  PC_CUDA_CHECK(cudaGetLastError());
+  delete hs;
+  e->host_state = nullptr;
+  return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// debug / test hook: C = A * B^T on the tensor-core engine (one program step)
+// ---------------------------------------------------------------------------
+__global__ void tc_debug_fill_kernel(const float* a, const float* b, PlaneStore ps, int n) {
+  const int bt = blockIdx.y;
+  const size_t nn = (size_t)n * n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+    ps.store(0, bt, i, j, n, a[(size_t)bt * nn + e]);  // M   <- A
+    ps.store(2, bt, i, j, n, b[(size_t)bt * nn + e]);  // M_i <- B
+    ps.store(4, bt, i, j, n, 0.f);                     // H   <- 0
+  }
+}
+__global__ void tc_debug_read_kernel(PlaneStore ps, int phys, int n, float* c) {
+  const int bt = blockIdx.y;
+  const size_t nn = (size_t)n * n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
+    c[(size_t)bt * nn + e] = ps.load(phys, bt, i, j, n);
+  }
+}
+__global__ void tc_debug_ctl_kernel(RootCtl* ctl, int batch, int n, uint32_t* errbits) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  RootCtl c;
+  memset(&c, 0, sizeof(c));
+  c.p = 1; c.pad = n; c.active = 1;
+  ctl[b] = c;
+  errbits[b] = 0;
+}
+
+int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, int passes,
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  PC_REQUIRE(n % TC_BM == 0 && n >= TC_BM, "n must be a multiple of 128");
+  if (!tc_engine_available()) {
+    set_error("tcgen05 engine requested but device is not sm_100");
+    return PC_ERR_UNSUPPORTED;
+  }
+  const size_t need = tc_engine_bytes(batch, n) + 4096 + sizeof(RootCtl) * batch + 4 * batch;
+  if (workspace_bytes < need) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+    return PC_ERR_WORKSPACE;
+  }
+  char* w = reinterpret_cast<char*>(align_up((size_t)workspace, 256));
+  RootCtl* ctl = reinterpret_cast<RootCtl*>(w); w += align_up(sizeof(RootCtl) * batch, 256);
+  uint32_t* errbits = reinterpret_cast<uint32_t*>(w); w += align_up(4 * batch, 256);
+  TcEngine e;
+  int rc = tc_engine_init(&e, w, batch, n, passes);
+  if (rc != PC_OK) return rc;
+  auto* hs = static_cast<TcHostState*>(e.host_state);
+  // private one-step program table: p = 1 -> Q0 = M * M_i^T
+  Program hp[kMaxP + 1];
+  memset(hp, 0, sizeof(hp));
+  hp[1].nsteps = 1;
+  hp[1].steps[0] = Step{LB_Q0, LB_M, LB_MI, 0};
+  Program* dprog = nullptr;
+  PC_CUDA_CHECK(cudaMallocAsync(&dprog, sizeof(hp), stream));
+  PC_CUDA_CHECK(cudaMemcpyAsync(dprog, hp, sizeof(hp), cudaMemcpyHostToDevice, stream));
+  PC_CUDA_CHECK(cudaStreamSynchronize(stream));
+  hs->progs_dev = dprog;
+  hs->prm.ctl = ctl;
+  hs->prm.errbits = errbits;
+  PlaneStore ps;
+  for (int pl = 0; pl < 3; ++pl) ps.plane[pl] = hs->prm.plane[pl];
+  ps.buf_stride = hs->prm.buf_stride;
+  ps.mat_elems = hs->prm.mat_stride;
+  tc_debug_ctl_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(ctl, batch, n, errbits);
+  dim3 g(64, batch);
+  tc_debug_fill_kernel<<<g, 256, 0, stream>>>(a, b, ps, n);
+  const int total_work = batch * 2 * hs->prm.tiles * hs->prm.tiles;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = total_work < sms ? total_work : sms;
+  rc = passes == 6 ? launch_phase<3, 2, 1>(hs, 0, total_work, grid, stream)
+                   : launch_phase<2, 3, 1>(hs, 0, total_work, grid, stream);
+  if (rc == PC_OK) tc_debug_read_kernel<<<g, 256, 0, stream>>>(ps, LB_Q0, n, c);
+  cudaFreeAsync(dprog, stream);
+  delete hs;
+  PC_CUDA_CHECK(cudaGetLastError());
+  return rc;
+}
+
 }  // namespace pc
+
+extern "C" int pc_debug_tc_gemm(const float* a, const float* b, float* c, int batch, int n,
+                                int passes, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  PC_REQUIRE(a && b && c && workspace && batch > 0, "bad arguments");
+  PC_REQUIRE(passes == 6 || passes == 3, "passes must be 6 or 3");
+  return pc::tc_debug_gemm(a, b, c, batch, n, passes, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
+}

@@ -87,6 +87,20 @@ def matrix_inverse_pth_root_batched(
   return roots, metrics
 
 
+def debug_tc_gemm(a: torch.Tensor, b: torch.Tensor, passes: int = 6) -> torch.Tensor:
+  """Test hook: C = A @ B^T on the tcgen05 split-bf16 engine ([batch, n, n] fp32)."""
+  lib = _lib.load()
+  _require_cuda(a, b)
+  bt, n = a.shape[0], a.shape[1]
+  c = torch.empty_like(a)
+  nbytes = lib.pc_inverse_pth_root_workspace_bytes(bt, n, _lib.PC_ENGINE_TC_BF16X6) + (1 << 16)
+  ws = _workspace(nbytes, a.device)
+  with torch.cuda.device(a.device):
+    _lib.check(lib.pc_debug_tc_gemm(_ptr(a), _ptr(b), _ptr(c), bt, n, passes, _ptr(ws),
+                                    ws.numel(), ctypes.c_void_p(_stream())))
+  return c
+
+
 def power_iteration(xs: torch.Tensor, padding_starts=None, num_iters: int = 100,
                     error_tolerance: float = 1e-6):
   """Batched DS:595-652; returns (lambda [b], iters [b])."""

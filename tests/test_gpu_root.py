@@ -53,7 +53,14 @@ def _check_case(root, row, want_root, want_row, a, p, tol, tag):
   assert rf <= tol, f"{tag}: rel-Frobenius {rf}"
 
 
-def _tol(engine):
+def _tol(engine, a=None):
+  """north_star bound is 1e-3; well-conditioned inputs are held much tighter.  Two
+  correct fp32 implementations differ by ~cond * 2^-24 on ill-conditioned inputs."""
+  if a is not None:
+    w = np.linalg.eigvalsh(a.astype(np.float64))
+    cond = w[-1] / max(w[0], 1e-30) if w[-1] > 0 else np.inf
+    if cond > 3e3:
+      return 1e-3
   return 2e-5 if engine == 1 else 1e-4
 
 
@@ -75,8 +82,9 @@ def test_golden_roots(golden_roots, engine):
     if k == "dst_all_padding":  # DST:400-408
       assert np.abs(roots).sum() == 0.0 and metrics[0, 0] == 0.0
       continue
+    m = n if pad < 0 else pad
     _check_case(roots[0], metrics[0], g[f"{k}/root"], want, a, int(g[f"{k}/p"]),
-                _tol(engine), k)
+                _tol(engine, a[:m, :m]), k)
     if pad >= 0:  # padded rows / cols exactly zero (DST:397-398)
       assert np.abs(roots[0][pad:]).sum() == 0 and np.abs(roots[0][:, pad:]).sum() == 0
 
@@ -122,8 +130,8 @@ def test_mixed_batch_matches_oracle(engine):
     if pads[b] == 0:
       assert np.abs(roots[b]).sum() == 0 and metrics[b, 0] == 0
       continue
-    _check_case(roots[b], metrics[b], want_r[b], want_m[b], xs[b], ps[b], _tol(engine),
-                f"batch[{b}] p={ps[b]} pad={pads[b]}")
+    _check_case(roots[b], metrics[b], want_r[b], want_m[b], xs[b], ps[b],
+                _tol(engine, xs[b][:pads[b], :pads[b]]), f"batch[{b}] p={ps[b]} pad={pads[b]}")
 
 
 @pytest.mark.parametrize("engine", [1, 2])

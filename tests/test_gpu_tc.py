@@ -1,0 +1,43 @@
+"""GPU tests of the tcgen05 split-bf16 GEMM engine through its C-ABI test hook."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _tc_ok():
+  from precondition_b200 import _lib
+  return torch.cuda.is_available() and bool(_lib.load().pc_device_supports_tcgen05())
+
+
+@pytest.mark.parametrize("n,batch,passes,tol", [(128, 1, 6, 2e-6), (256, 3, 6, 2e-6),
+                                                (512, 2, 6, 2e-6), (256, 2, 3, 2e-4)])
+def test_tc_gemm_matches_float64(n, batch, passes, tol):
+  """C = A B^T with fp32 operands: BF16x6 must be fp32-accurate (<= 2e-6 of the
+  largest entry), BF16x3 ~2^-16."""
+  if not _tc_ok():
+    pytest.skip("needs sm_100")
+  from precondition_b200 import ops
+  rng = np.random.default_rng(n)
+  a = rng.standard_normal((batch, n, n)).astype(np.float32)
+  b = rng.standard_normal((batch, n, n)).astype(np.float32)
+  c = ops.debug_tc_gemm(torch.as_tensor(a).cuda(), torch.as_tensor(b).cuda(), passes)
+  torch.cuda.synchronize()
+  want = np.einsum("bik,bjk->bij", a.astype(np.float64), b.astype(np.float64))
+  err = np.abs(c.cpu().numpy() - want).max() / np.abs(want).max()
+  assert err <= tol, err
+
+
+def test_tc_gemm_exact_on_bf16_representable_integers():
+  """Small integers are exact in bf16 and in fp32 accumulation: bit-exact result."""
+  if not _tc_ok():
+    pytest.skip("needs sm_100")
+  from precondition_b200 import ops
+  rng = np.random.default_rng(1)
+  a = rng.integers(-4, 5, (2, 256, 256)).astype(np.float32)
+  b = rng.integers(-4, 5, (2, 256, 256)).astype(np.float32)
+  c = ops.debug_tc_gemm(torch.as_tensor(a).cuda(), torch.as_tensor(b).cuda(), 6)
+  torch.cuda.synchronize()
+  want = np.einsum("bik,bjk->bij", a, b)
+  np.testing.assert_array_equal(c.cpu().numpy(), want)
