@@ -130,16 +130,18 @@ power_iteration_kernel(const float* __restrict__ xs, const int32_t* __restrict__
   float* y = smem + 2 * n;
   __shared__ float scratch[32];
   const int b = blockIdx.x;
-  int pad = n;
+  // `pad` masks the MATRIX (solver path: DS:777-783 masks it before DS:820);
+  // `vpad` masks only the start vector (stand-alone power_iteration, DS:645-646).
+  int pad = n, vpad = n;
   if (ctl) {
     if (ctl[b].done) return;
-    pad = ctl[b].pad;
+    pad = vpad = ctl[b].pad;
   } else if (pads) {
-    pad = min(max(pads[b], 0), n);
+    vpad = min(max(pads[b], 0), n);
   }
   const float* A = xs + (size_t)b * n * n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = i < pad ? v0[i] : 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = i < vpad ? v0[i] : 0.f;
   __syncthreads();
   float s = 0.f;
   int it = 0;
@@ -216,28 +218,32 @@ root_phase_simt_kernel(F32Store bufs, const RootCtl* __restrict__ ctl,
     st = pr.steps[s];
   }
   const int lim = c.pad;  // everything is zero outside [0,pad)^2
-  const int tile_m = blockIdx.y, tile_n = blockIdx.x;
-  if (tile_m * kSimtBM >= lim || tile_n * kSimtBN >= lim) {
-    // tile fully in the padding: result is exactly zero
-    const int cur = c.cur;
-    float* out = bufs.mat(physical_buf(st.dst, cur), b, 0);
-    float* out_mi = st.emit_mi ? bufs.mat(physical_buf(LB_MIN, cur), b, 0) : nullptr;
+  // Only lower-triangular tiles (tile_m >= tile_n) are computed; the result is
+  // mirrored so that every iterate is EXACTLY symmetric.  That makes reading B by
+  // rows exact (B^T == B bitwise) -- with merely "nearly symmetric" iterates the
+  // antisymmetric rounding noise doubles per Newton step instead of being squared
+  // away -- and removes (T-1)/(2T) of the GEMM work.
+  int tile_m, tile_n;
+  tri_decode(blockIdx.x, tile_m, tile_n);
+  const int cur = c.cur;
+  float* out = bufs.mat(physical_buf(st.dst, cur), b, 0);
+  float* out_mi = st.emit_mi ? bufs.mat(physical_buf(LB_MIN, cur), b, 0) : nullptr;
+  if (tile_m * kSimtBM >= lim) {
+    // tile fully in the padding: result (and its mirror) is exactly zero
     for (int e = threadIdx.x; e < kSimtBM * kSimtBN; e += blockDim.x) {
       int i = tile_m * kSimtBM + e / kSimtBN, j = tile_n * kSimtBN + e % kSimtBN;
       if (i < n && j < n) {
         out[(size_t)i * n + j] = 0.f;
-        if (out_mi) out_mi[(size_t)i * n + j] = 0.f;
+        out[(size_t)j * n + i] = 0.f;
+        if (out_mi) { out_mi[(size_t)i * n + j] = 0.f; out_mi[(size_t)j * n + i] = 0.f; }
       }
     }
     return;
   }
-  const int cur = c.cur;
   const SquareView A{bufs.mat(physical_buf(st.a, cur), b, 0), n, lim};
-  // operands are symmetric: B(j,k) = B[j][k] reads rows (coalesced along k)
   const SquareView B{bufs.mat(physical_buf(st.b, cur), b, 0), n, lim};
-  float* out = bufs.mat(physical_buf(st.dst, cur), b, 0);
-  float* out_mi = st.emit_mi ? bufs.mat(physical_buf(LB_MIN, cur), b, 0) : nullptr;
   const float alpha = -1.0f / (float)c.p, one_minus_alpha = 1.0f - alpha;
+  const bool diag_tile = tile_m == tile_n;
   uint32_t emax = 0;
   simt_gemm_tile(lim, tile_m, tile_n, A, B, true, true, sm,
                  [&](int i, int j0, const float* acc) {
@@ -245,13 +251,15 @@ root_phase_simt_kernel(F32Store bufs, const RootCtl* __restrict__ ctl,
 #pragma unroll
                    for (int q = 0; q < 4; ++q) {
                      const int j = j0 + q;
-                     if (j >= n) continue;
+                     if (j >= n || (diag_tile && j > i)) continue;
                      const bool in = (i < lim && j < lim);
                      const float v = in ? acc[q] : 0.f;
                      out[(size_t)i * n + j] = v;
+                     if (i != j) out[(size_t)j * n + i] = v;
                      if (out_mi) {
-                       out_mi[(size_t)i * n + j] =
-                           in ? mi_from_m(v, i == j, alpha, one_minus_alpha) : 0.f;
+                       const float mi = in ? mi_from_m(v, i == j, alpha, one_minus_alpha) : 0.f;
+                       out_mi[(size_t)i * n + j] = mi;
+                       if (i != j) out_mi[(size_t)j * n + i] = mi;
                        const uint32_t ab = absbits(v - ((in && i == j) ? 1.f : 0.f));
                        emax = ab > emax ? ab : emax;
                      }
@@ -454,7 +462,7 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
         cudaEventRecord(ev0, stream);
       }
       for (int s = 0; s < max_steps; ++s) {
-        dim3 grid(tiles, tiles, batch * 2);
+        dim3 grid(tiles * (tiles + 1) / 2, 1, batch * 2);
         root_phase_simt_kernel<<<grid, kSimtThreads, 0, stream>>>(f32, ws.ctl, ws.errbits,
                                                                  n, s);
       }

@@ -88,6 +88,15 @@ __host__ __device__ inline int physical_buf(int logical, int cur) {
   }
 }
 
+// lower-triangular tile index t -> (tm, tn), tm >= tn, t = tm (tm + 1) / 2 + tn
+__host__ __device__ inline void tri_decode(int t, int& tm, int& tn) {
+  int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while (r * (r + 1) / 2 > t) --r;
+  while ((r + 1) * (r + 2) / 2 <= t) ++r;
+  tm = r;
+  tn = t - r * (r + 1) / 2;
+}
+
 // Host: builds the per-exponent step list (false if p is out of range).
 bool build_program(int p, Program* out);
 

@@ -57,7 +57,9 @@ root_init_kernel(const float* __restrict__ xs, RootCtl* ctl, Bufs bufs, int batc
   const size_t total = (size_t)pad * pad;
   for (size_t e = threadIdx.x; e < total; e += blockDim.x) {
     const int i = (int)(e / pad), j = (int)(e - (size_t)i * pad);
-    float a = __ldg(A + (size_t)i * n + j);
+    // the lower triangle is authoritative (statistics are symmetric; this makes
+    // the iterates bitwise symmetric even if the caller's matrix is not)
+    float a = __ldg(A + (size_t)max(i, j) * n + min(i, j));
     if (i == j) a += eps;
     ss = fmaf(a, a, ss);
   }
@@ -73,7 +75,7 @@ root_init_kernel(const float* __restrict__ xs, RootCtl* ctl, Bufs bufs, int batc
     const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
     float m0 = 0.f, mi = 0.f, h = 0.f;
     if (i < pad && j < pad) {
-      float a = __ldg(A + e);
+      float a = __ldg(A + (size_t)max(i, j) * n + min(i, j));
       if (i == j) a += eps;
       m0 = a * z;                                   // DS:871
       const float e0 = m0 - (i == j ? 1.f : 0.f);   // M0 - I_m

@@ -166,11 +166,12 @@ struct TcWork {
 
 __device__ __forceinline__ bool tc_get_work(const TcParams& P, const Program* progs, int s,
                                             int w, TcWork& out) {
-  const int per_mat = 2 * P.tiles * P.tiles;
+  const int ntri = P.tiles * (P.tiles + 1) / 2;  // lower-triangular tiles only
+  const int per_mat = 2 * ntri;
   const int b = w / per_mat;
   int r = w - b * per_mat;
-  const int op = r / (P.tiles * P.tiles);
-  r -= op * P.tiles * P.tiles;
+  const int op = r / ntri;
+  r -= op * ntri;
   const RootCtl& c = P.ctl[b];
   if (!c.active) return false;
   if (op == 1) {
@@ -182,8 +183,7 @@ __device__ __forceinline__ bool tc_get_work(const TcParams& P, const Program* pr
     out.st = pr.steps[s];
   }
   out.b = b;
-  out.tm = r / P.tiles;
-  out.tn = r - out.tm * P.tiles;
+  tri_decode(r, out.tm, out.tn);  // tm >= tn; the epilogue mirrors the tile
   out.cur = c.cur;
   out.p = c.p;
   out.pad = c.pad;
@@ -368,33 +368,61 @@ tc_phase_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-      // ---- epilogue: OUT = sum; optional M_i' and err (DS:844-847) ----
+      // ---- epilogue: OUT = sum (+ mirror); optional M_i' and err (DS:844-847) ----
+      // Tile (tm, tn), tm >= tn: rows of this thread go to (row, col) directly and
+      // to (col, row) as the mirror, so the stored matrix is bitwise symmetric.
       const int row = wk.tm * TC_BM + row_in_tile;
-      const int pd = physical_buf(wk.st.dst, wk.cur);
-      const size_t out_off = (size_t)pd * P.buf_stride + (size_t)wk.b * P.mat_stride +
-                             (size_t)row * P.n + (size_t)wk.tn * TC_BN;
-      const size_t mi_off = (size_t)physical_buf(LB_MIN, wk.cur) * P.buf_stride +
-                            (size_t)wk.b * P.mat_stride + (size_t)row * P.n +
-                            (size_t)wk.tn * TC_BN;
+      const bool diag_tile = wk.tm == wk.tn;
+      const size_t mat_off = (size_t)wk.b * P.mat_stride;
+      const size_t out_base = (size_t)physical_buf(wk.st.dst, wk.cur) * P.buf_stride + mat_off;
+      const size_t mi_base = (size_t)physical_buf(LB_MIN, wk.cur) * P.buf_stride + mat_off;
       const float alpha = -1.0f / (float)wk.p, oma = 1.0f - alpha;
       uint32_t emax = 0;
+      auto write_group = [&](size_t base, const float (&v)[32], int col0) {
+        if (!diag_tile) store_planes32(P, base + (size_t)row * P.n + col0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = col0 + i;
+          const bool direct = diag_tile && col <= row;
+          const bool mirror = diag_tile ? (col < row) : true;
+          const float x = v[i];
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(x);
+          const float r1 = x - __bfloat162float(h0);
+          const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+          const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+          if (direct) {
+            const size_t o = base + (size_t)row * P.n + col;
+            P.plane[0][o] = __bfloat16_as_ushort(h0);
+            P.plane[1][o] = __bfloat16_as_ushort(h1);
+            P.plane[2][o] = __bfloat16_as_ushort(h2);
+          }
+          if (mirror) {
+            const size_t o = base + (size_t)col * P.n + row;  // lanes -> consecutive rows
+            P.plane[0][o] = __bfloat16_as_ushort(h0);
+            P.plane[1][o] = __bfloat16_as_ushort(h1);
+            P.plane[2][o] = __bfloat16_as_ushort(h2);
+          }
+        }
+      };
 #pragma unroll
       for (int c = 0; c < TC_BN / 32; ++c) {
+        const int col0 = wk.tn * TC_BN + c * 32;
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = sum[c * 32 + i];
-        store_planes32(P, out_off + c * 32, v);
+        write_group(out_base, v, col0);
         if (wk.st.emit_mi) {
-          const int col0 = wk.tn * TC_BN + c * 32;
           float mi[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const bool dg = (col0 + i == row) && (row < wk.pad);
-            const uint32_t ab = absbits(v[i] - (dg ? 1.f : 0.f));
-            emax = ab > emax ? ab : emax;
+            if (!diag_tile || col0 + i <= row) {
+              const uint32_t ab = absbits(v[i] - (dg ? 1.f : 0.f));
+              emax = ab > emax ? ab : emax;
+            }
             mi[i] = mi_from_m(v[i], dg, alpha, oma);
           }
-          store_planes32(P, mi_off + c * 32, mi);
+          write_group(mi_base, mi, col0);
         }
       }
       if (wk.st.emit_mi) {
@@ -550,7 +578,7 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int total_work = e->batch * 2 * hs->prm.tiles * hs->prm.tiles;
+  const int total_work = e->batch * hs->prm.tiles * (hs->prm.tiles + 1);  // 2 ops x lower tiles
   const int grid = total_work < sms ? total_work : sms;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (gemm_timing_enabled()) {
@@ -655,7 +683,7 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
   tc_debug_ctl_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(ctl, batch, n, errbits);
   dim3 g(64, batch);
   tc_debug_fill_kernel<<<g, 256, 0, stream>>>(a, b, ps, n);
-  const int total_work = batch * 2 * hs->prm.tiles * hs->prm.tiles;
+  const int total_work = batch * hs->prm.tiles * (hs->prm.tiles + 1);
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
