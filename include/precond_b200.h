@@ -144,15 +144,16 @@ int pc_power_iteration_batched(const float* xs, const int32_t* padding_starts,
  *           (k % k_inner)*s_ki]  so that every mode-k unfolding of a rank<=3
  *           gradient block is a view (no jnp.split copies, DS:1412-1422).
  * ------------------------------------------------------------------------ */
+/*   A(i,k) = a[(i / a_iinner)*a_sio + (i % a_iinner)*a_si + (k / a_kinner)*a_sko + (k % a_kinner)*a_ski] */
 typedef struct {
   const float* a;    /* A(i,k), i in [0,M), k in [0,K) */
   const float* b;    /* B(j,k), j in [0,N), k in [0,K)  (i.e. op(B)^T) */
   const float* c_in; /* optional, addressed like c */
   float* c;          /* C(i,j) = c[(i / c_iinner)*c_sio + (i % c_iinner)*c_sii + j] */
-  int64_t a_si, a_sko, a_ski;
+  int64_t a_sio, a_si, a_sko, a_ski;
   int64_t b_sj, b_sko, b_ski;
   int64_t c_sio, c_sii;
-  int32_t a_kinner, b_kinner, c_iinner;
+  int32_t a_iinner, a_kinner, b_kinner, c_iinner;
   int32_t m, n, k;
   float alpha, beta;
   int32_t reserved;
@@ -161,6 +162,14 @@ typedef struct {
 /* descs: DEVICE array of `count` descriptors; max_m/max_n bound the tile grid. */
 int pc_grouped_gemm(const pc_gemm_desc* descs, int count, int max_m, int max_n,
                     void* stream);
+
+/* Failure fallback of DS:2936-2950 without a host round trip: for every matrix b,
+ * dst[b] <- src[b] unless metrics[b][PC_METRIC_ERROR] is NaN or >= threshold
+ * (then dst keeps the previous preconditioner).  src rows are [src_rows, src_cols]
+ * (the padded root); the top-left [rows, cols] corner is copied (DS:2950). */
+int pc_select_preconditioners(const float* src, const float* metrics, float threshold,
+                              float* dst, int batch, int src_rows, int src_cols, int rows,
+                              int cols, void* stream);
 
 /* ------------------------------------------------------------------------
  * (1b) QuantizedValue (QU:49-113) for square statistics / preconditioners with

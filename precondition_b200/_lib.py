@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "pc_stats_get",
     "pc_root_options_default", "pc_resolve_engine",
     "pc_inverse_pth_root_workspace_bytes",
-    "pc_inverse_pth_root_batched", "pc_debug_tc_gemm", "pc_power_iteration_batched", "pc_grouped_gemm",
+    "pc_inverse_pth_root_batched", "pc_debug_tc_gemm", "pc_power_iteration_batched", "pc_grouped_gemm", "pc_select_preconditioners",
     "pc_quantize_batched", "pc_dequantize_batched",
     "pc_graft_momentum_workspace_bytes", "pc_graft_momentum",
 )
@@ -42,11 +42,12 @@ class Stats(ctypes.Structure):
 class GemmDesc(ctypes.Structure):
   _fields_ = [("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("c_in", ctypes.c_void_p),
               ("c", ctypes.c_void_p),
-              ("a_si", ctypes.c_int64), ("a_sko", ctypes.c_int64), ("a_ski", ctypes.c_int64),
+              ("a_sio", ctypes.c_int64), ("a_si", ctypes.c_int64), ("a_sko", ctypes.c_int64),
+              ("a_ski", ctypes.c_int64),
               ("b_sj", ctypes.c_int64), ("b_sko", ctypes.c_int64), ("b_ski", ctypes.c_int64),
               ("c_sio", ctypes.c_int64), ("c_sii", ctypes.c_int64),
-              ("a_kinner", ctypes.c_int32), ("b_kinner", ctypes.c_int32),
-              ("c_iinner", ctypes.c_int32),
+              ("a_iinner", ctypes.c_int32), ("a_kinner", ctypes.c_int32),
+              ("b_kinner", ctypes.c_int32), ("c_iinner", ctypes.c_int32),
               ("m", ctypes.c_int32), ("n", ctypes.c_int32), ("k", ctypes.c_int32),
               ("alpha", ctypes.c_float), ("beta", ctypes.c_float),
               ("reserved", ctypes.c_int32)]
@@ -110,6 +111,8 @@ def load() -> ctypes.CDLL:
   lib.pc_power_iteration_batched.restype = i32
   lib.pc_grouped_gemm.argtypes = [vp, i32, i32, i32, vp]
   lib.pc_grouped_gemm.restype = i32
+  lib.pc_select_preconditioners.argtypes = [vp, vp, f32, vp, i32, i32, i32, i32, i32, vp]
+  lib.pc_select_preconditioners.restype = i32
   lib.pc_quantize_batched.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
   lib.pc_quantize_batched.restype = i32
   lib.pc_dequantize_batched.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]

@@ -11,8 +11,9 @@ grouped_gemm_simt_kernel(const pc_gemm_desc* __restrict__ descs) {
   const pc_gemm_desc d = descs[blockIdx.z];
   const int tile_m = blockIdx.y, tile_n = blockIdx.x;
   if (tile_m * kSimtBM >= d.m || tile_n * kSimtBN >= d.n) return;
-  const OperandView A{d.a, d.a_si, d.a_sko, d.a_ski, d.a_kinner, d.m, d.k};
-  const OperandView B{d.b, d.b_sj, d.b_sko, d.b_ski, d.b_kinner, d.n, d.k};
+  const OperandView A{d.a, d.a_sio, d.a_si, d.a_sko, d.a_ski, d.a_iinner > 0 ? d.a_iinner : d.m,
+                      d.a_kinner, d.m, d.k};
+  const OperandView B{d.b, 0, d.b_sj, d.b_sko, d.b_ski, d.n > 0 ? d.n : 1, d.b_kinner, d.n, d.k};
   simt_gemm_tile(d.k, tile_m, tile_n, A, B, A.k_fast(), B.k_fast(), sm,
                  [&](int i, int j0, const float* acc) {
                    if (i >= d.m) return;
@@ -31,6 +32,38 @@ grouped_gemm_simt_kernel(const pc_gemm_desc* __restrict__ descs) {
 
 }  // namespace pc
 
+namespace pc {
+__global__ void select_copy_kernel(const float* __restrict__ src, const float* __restrict__ metrics,
+                                   float threshold, float* __restrict__ dst, int src_cols,
+                                   size_t src_elems, int rows, int cols) {
+  const int b = blockIdx.y;
+  const float err = metrics[(size_t)b * PC_NUM_METRICS + PC_METRIC_ERROR];
+  if (isnan(err) || err >= threshold) return;  // keep the old preconditioner, DS:2936-2943
+  const size_t total = (size_t)rows * cols;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / cols), c = (int)(e - (size_t)r * cols);
+    dst[(size_t)b * total + e] = src[(size_t)b * src_elems + (size_t)r * src_cols + c];
+  }
+}
+}  // namespace pc
+
+extern "C" int pc_select_preconditioners(const float* src, const float* metrics, float threshold,
+                                         float* dst, int batch, int src_rows, int src_cols,
+                                         int rows, int cols, void* stream) {
+  PC_REQUIRE(batch >= 0 && rows >= 0 && cols >= 0 && rows <= src_rows && cols <= src_cols,
+             "bad select sizes");
+  if (batch == 0 || rows == 0 || cols == 0) return PC_OK;
+  PC_REQUIRE(src && metrics && dst, "null pointer argument");
+  const size_t total = (size_t)rows * cols;
+  dim3 grid((unsigned)((total + 255) / 256 < 256 ? (total + 255) / 256 : 256), batch);
+  pc::select_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      src, metrics, threshold, dst, src_cols, (size_t)src_rows * src_cols, rows, cols);
+  pc::count_launch(1);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
 extern "C" int pc_grouped_gemm(const pc_gemm_desc* descs, int count, int max_m, int max_n,
                                void* stream) {
   PC_REQUIRE(count >= 0 && max_m >= 0 && max_n >= 0, "bad grouped gemm sizes");
@@ -43,6 +76,7 @@ extern "C" int pc_grouped_gemm(const pc_gemm_desc* descs, int count, int max_m, 
     dim3 grid(tn, tm, nz);
     pc::grouped_gemm_simt_kernel<<<grid, pc::kSimtThreads, 0, (cudaStream_t)stream>>>(descs + z0);
   }
+  pc::count_launch((count + 65534) / 65535);
   PC_CUDA_CHECK(cudaGetLastError());
   return PC_OK;
 }

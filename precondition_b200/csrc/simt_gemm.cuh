@@ -24,13 +24,14 @@ struct SimtSmem {
 //   X(i,k) = base[i*s_i + (k / k_inner)*s_ko + (k % k_inner)*s_ki]
 struct OperandView {
   const float* base;
-  int64_t s_i, s_ko, s_ki;
-  int k_inner;
+  int64_t s_io, s_i, s_ko, s_ki;
+  int i_inner, k_inner;
   int rows, k;  // logical extents (loads outside return 0)
   __device__ __forceinline__ float operator()(int i, int kk) const {
     if (i >= rows || kk >= k) return 0.f;
-    int ko = kk / k_inner, ki = kk - ko * k_inner;
-    return __ldg(base + i * s_i + ko * s_ko + ki * s_ki);
+    const int io = i / i_inner, ii = i - io * i_inner;
+    const int ko = kk / k_inner, ki = kk - ko * k_inner;
+    return __ldg(base + io * s_io + ii * s_i + ko * s_ko + ki * s_ki);
   }
   __device__ __forceinline__ bool k_fast() const { return s_ki == 1; }
 };

@@ -1,0 +1,129 @@
+"""GPU parity of the optax-style ``distributed_shampoo`` mirror against golden
+trajectories recorded from the UNMODIFIED reference (tests/golden/optimizer.npz)
+and against the oracle on a blocked MLP-shaped problem."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import optimizer as O
+from oracle.gen_golden import OPT_CONFIGS, OPT_SHAPES, OPT_STEPS
+
+pytestmark = pytest.mark.gpu
+
+SUPPORTED = ["default", "two_devices", "quantized_int16", "sqrt_n_input",
+             "adagrad_norm_output_wd", "rmsprop_clip", "rmsprop_norm_ma", "adagrad_rank3",
+             "none_noshape", "abs_eps_beta2_1"]
+
+
+def _kw(cfg):
+  from precondition_b200 import distributed_shampoo as DS
+  kw = {k: v for k, v in cfg.items() if not k.startswith("_")}
+  if "graft_type" in kw:
+    kw["graft_type"] = DS.GraftingType(kw["graft_type"])
+  if "precondtioner_type" in kw:
+    kw["precondtioner_type"] = DS.PreconditionerType(kw["precondtioner_type"])
+  return kw
+
+
+@pytest.mark.parametrize("name", SUPPORTED)
+def test_trajectory_matches_reference_golden(golden_optimizer, name):
+  """8 steps on 4 parameters (block_size 8; ranks 1-3; p in {2,4,6}); updates must
+  follow the reference within 2e-4 of the update scale (fp32 roots of tiny,
+  ill-conditioned statistics amplify rounding differences)."""
+  from precondition_b200 import distributed_shampoo as DS
+  g = golden_optimizer
+  params = [torch.as_tensor(g[f"param/{i}"]).cuda() for i in range(len(OPT_SHAPES))]
+  opt = DS.distributed_shampoo(0.1, 8, batch_axis_name="batch", **_kw(OPT_CONFIGS[name]))
+  state = opt.init(params)
+  for t in range(OPT_STEPS):
+    grads = [torch.as_tensor(g[f"grad/{t}/{i}"]).cuda() for i in range(len(OPT_SHAPES))]
+    updates, state = opt.update(grads, state, params)
+    torch.cuda.synchronize()
+    for i, u in enumerate(updates):
+      want = g[f"{name}/update/{t}/{i}"]
+      scale = max(np.abs(want).max(), 1e-12)
+      err = np.abs(u.cpu().numpy() - want).max() / scale
+      tol = 2e-4 if name != "quantized_int16" else 2e-3
+      assert err <= tol, f"{name} step {t} param {i}: {err}"
+  assert state.count == OPT_STEPS
+  # final preconditioners and metrics
+  for i, st in enumerate(state.stats):
+    for k, pc in enumerate(st.preconditioners):
+      pc = pc.to_float() if hasattr(pc, "to_float") else pc
+      want = g[f"{name}/final_precond/{i}/{k}"]
+      err = np.abs(pc.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-12)
+      assert err <= (5e-3 if name == "quantized_int16" else 1e-3), (name, i, k, err)
+    tm = st.training_metrics
+    if tm is not None and f"{name}/final_metrics/{i}" in g and tm.shape[0]:
+      want = g[f"{name}/final_metrics/{i}"]
+      np.testing.assert_allclose(tm.cpu().numpy()[:, 1], want[:, 1], atol=1)   # iters
+      np.testing.assert_array_equal(tm.cpu().numpy()[:, 4], want[:, 4])        # retries
+
+
+@pytest.mark.parametrize("tag,expected", [("dst_small", -0.57), ("dst_larger", -0.17019942),
+                                          ("dst_small_q", -0.57),
+                                          ("dst_larger_q", -0.17019942)])
+def test_reference_end_to_end_goldens(golden_optimizer, tag, expected):
+  """DST:116-261 on the CUDA path: step-0 golden scalar, 6 finite steps."""
+  from precondition_b200 import distributed_shampoo as DS
+  g = golden_optimizer
+  base = tag.replace("_q", "")
+  params = [torch.as_tensor(g[f"{base}/param/{i}"]).cuda() for i in range(2)]
+  grads = [torch.as_tensor(g[f"{base}/grad/{i}"]).cuda() for i in range(2)]
+  opt = DS.distributed_shampoo(0.1, 32, batch_axis_name="batch",
+                               preconditioning_compute_steps=2,
+                               best_effort_memory_usage_reduction=tag.endswith("_q"))
+  state = opt.init(params)
+  for t in range(6):
+    updates, state = opt.update(grads, state, params)
+    torch.cuda.synchronize()
+    for i, u in enumerate(updates):
+      u = u.cpu().numpy()
+      assert np.all(np.isfinite(u))
+      want = g[f"{tag}/update/{t}/{i}"]
+      assert np.abs(u - want).max() <= 5e-3 * max(np.abs(want).max(), 1e-12), (tag, t, i)
+    if t == 0:
+      assert abs(float(updates[1].reshape(-1)[-1]) - expected) < 1e-4
+
+
+def test_blocked_mlp_matches_oracle():
+  """BASELINE config 2 in miniature: MLP 64->256->64, block_size 32, SGD grafting;
+  10 steps, so steps >= 5 exercise the preconditioned path."""
+  from precondition_b200 import distributed_shampoo as DS
+  rng = np.random.default_rng(0)
+  shapes = [(64, 256), (256,), (256, 64), (64,)]
+  params = [rng.standard_normal(s).astype(np.float32) * 0.1 for s in shapes]
+  oracle = O.distributed_shampoo(0.1, 32)
+  ostate = oracle.init(params)
+  opt = DS.distributed_shampoo(0.1, 32)
+  tparams = [torch.as_tensor(p).cuda() for p in params]
+  state = opt.init(tparams)
+  for t in range(10):
+    grads = [(rng.standard_normal(s) * 1e-2).astype(np.float32) for s in shapes]
+    want, ostate = oracle.update(grads, ostate, params)
+    got, state = opt.update([torch.as_tensor(x).cuda() for x in grads], state, tparams)
+    torch.cuda.synchronize()
+    for i, (u, w) in enumerate(zip(got, want)):
+      err = np.abs(u.cpu().numpy() - w).max() / max(np.abs(w).max(), 1e-12)
+      assert err <= 2e-4, (t, i, err)
+  # statistics follow the oracle to fp32 accuracy
+  for st, ost in zip(state.stats, ostate.stats):
+    for a, b in zip(st.statistics, ost.statistics):
+      np.testing.assert_allclose(a.cpu().numpy(), b, rtol=1e-4, atol=1e-9)
+
+
+def test_pytree_structure_and_errors():
+  from precondition_b200 import distributed_shampoo as DS
+  params = {"w": torch.randn(16, 8).cuda(), "b": (torch.randn(8).cuda(),)}
+  opt = DS.distributed_shampoo(0.1, 8)
+  state = opt.init(params)
+  grads = {"w": torch.randn(16, 8).cuda(), "b": (torch.randn(8).cuda(),)}
+  updates, state = opt.update(grads, state, params)
+  assert set(updates.keys()) == {"w", "b"} and isinstance(updates["b"], tuple)
+  assert updates["w"].shape == (16, 8)
+  with pytest.raises(ValueError):
+    DS.distributed_shampoo(0.1, 8, reset_preconditioner=True)
+  with pytest.raises(ValueError):
+    DS.distributed_shampoo(0.1, 8, frequent_directions=True)
+  with pytest.raises(RuntimeError):
+    DS.distributed_shampoo(0.1, 8).init([torch.zeros(4, 4)])  # CPU tensor: no fallback
