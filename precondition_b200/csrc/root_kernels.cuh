@@ -41,6 +41,10 @@ root_init_kernel(const float* __restrict__ xs, RootCtl* ctl, Bufs bufs, int batc
   if (n == 1) {  // DS:850-855
     if (threadIdx.x == 0) {
       const float a = pad > 0 ? A[0] : 0.f;
+      // power iteration on a 1x1 matrix returns the entry itself (v = +-1)
+      const float ev = prm.relative_eps ? a : 1.0f;
+      c.max_ev = ev;
+      c.ridge = prm.ridge_epsilon * fmaxf(ev, 1e-25f);
       roots[(size_t)b] = powf(a + c.ridge, alpha);
       c.need_init = 0; c.done = 1; c.active = 0;
       c.m_err = 0.f; c.m_iters = 0.f; c.m_ratio = 0.f; c.m_retries = 0.f;

@@ -675,6 +675,20 @@ class _Shampoo:
   def _roots_sharded(self, bk, world, rank):
     kw = dict(ridge_epsilon=self.matrix_epsilon,
               relative_matrix_epsilon=self.relative_matrix_epsilon, engine=self.engine)
+    if bk.size == 1 and max(self.buckets) > 1:
+      # The reference pads every statistic to the largest block (DS:2841-2843), so a
+      # 1x1 statistic goes through the coupled iteration, not the scalar closed
+      # form (DS:850-855 only triggers when max_size == 1).  Mirror that with the
+      # smallest padded problem: [[s, 0], [0, 1]], padding_start = 1.
+      padded = torch.eye(2, dtype=torch.float32, device=self.device).repeat(bk.count, 1, 1)
+      padded[:, 0, 0] = bk.stats[:, 0, 0]
+      pads = torch.ones(bk.count, dtype=torch.int32, device=self.device)
+      if world == 1:
+        r, m = ops.matrix_inverse_pth_root_batched(padded, bk.exps, pads, **kw)
+      else:
+        r, m = sharded_inverse_pth_roots(padded, bk.exps, world, rank, self.process_group,
+                                         pads=pads, **kw)
+      return r[:, :1, :1].contiguous(), m
     if world == 1:
       return ops.matrix_inverse_pth_root_batched(bk.stats, bk.exps, None, out=bk.roots_tmp, **kw)
     return sharded_inverse_pth_roots(bk.stats, bk.exps, world, rank, self.process_group, **kw)
@@ -720,7 +734,7 @@ class _Shampoo:
     return update
 
 
-def sharded_inverse_pth_roots(stats, exps, world, rank, group, root_fn=None, **kw):
+def sharded_inverse_pth_roots(stats, exps, world, rank, group, root_fn=None, pads=None, **kw):
   """Block-sharded roots + all-gather, the device boundary of DS:2841-2879.
 
   The batch is padded to a multiple of ``world`` with (I, exponent 1, padding 0)
@@ -740,7 +754,7 @@ def sharded_inverse_pth_roots(stats, exps, world, rank, group, root_fn=None, **k
   if hi > lo:
     local[:hi - lo] = stats[lo:hi]
     local_ps[:hi - lo] = exps[lo:hi]
-    local_pad[:hi - lo] = s
+    local_pad[:hi - lo] = s if pads is None else pads[lo:hi]
   roots, metrics = root_fn(local.contiguous(), local_ps, local_pad, **kw)
   all_roots = torch.empty((world * b, s, s), dtype=roots.dtype, device=roots.device)
   all_metrics = torch.empty((world * b, metrics.shape[1]), dtype=metrics.dtype,
