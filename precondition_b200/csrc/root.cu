@@ -117,30 +117,50 @@ __global__ void root_setup_kernel(RootCtl* ctl, const int32_t* ps, const int32_t
 }
 
 // ---------------------------------------------------------------------------
-// power iteration (DS:595-652): one CTA per matrix, <=100 dependent mat-vecs
+// power iteration (DS:595-652): <= 100 strictly dependent mat-vecs per matrix.
+// A cluster of `csize` CTAs owns one matrix: CTA r computes rows [r*n/csize, ...) of
+// y = A v/|v|, publishes its slice in a double-buffered global vector and a
+// cluster barrier makes it visible; every CTA then forms |y|, v.y redundantly in
+// the same order, so all CTAs take identical control decisions.  The matrix
+// (4 MiB at n = 1024) streams from L2/HBM once per iteration across csize SMs
+// instead of one.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pi_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void pi_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(1024)
 power_iteration_kernel(const float* __restrict__ xs, const int32_t* __restrict__ pads,
                        const float* __restrict__ v0, int n, int num_iters, float tol,
                        float* __restrict__ lambdas, int32_t* __restrict__ iters,
-                       RootCtl* ctl) {
+                       RootCtl* ctl, float* __restrict__ ybuf, int csize) {
   extern __shared__ float smem[];
-  float* v = smem;
-  float* nv = smem + n;
-  float* y = smem + 2 * n;
+  float* v = smem;       // current iterate (full vector)
+  float* nv = smem + n;  // normalised iterate
   __shared__ float scratch[32];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / csize;
+  const int crank = csize > 1 ? (int)pi_cluster_rank() : 0;
   // `pad` masks the MATRIX (solver path: DS:777-783 masks it before DS:820);
   // `vpad` masks only the start vector (stand-alone power_iteration, DS:645-646).
   int pad = n, vpad = n;
+  bool skip = false;
   if (ctl) {
-    if (ctl[b].done) return;
+    skip = ctl[b].done != 0;
     pad = vpad = ctl[b].pad;
   } else if (pads) {
     vpad = min(max(pads[b], 0), n);
   }
+  if (skip) return;  // uniform across the cluster
   const float* A = xs + (size_t)b * n * n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int rows_per = (n + csize - 1) / csize;
+  const int r_lo = crank * rows_per, r_hi = min(n, r_lo + rows_per);
   for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = i < vpad ? v0[i] : 0.f;
   __syncthreads();
   float s = 0.f;
@@ -149,40 +169,51 @@ power_iteration_kernel(const float* __restrict__ xs, const int32_t* __restrict__
   const bool vec4 = (n % 4 == 0);
   while (it < num_iters && run) {
     float ss = 0.f;
-    for (int i = threadIdx.x; i < pad; i += blockDim.x) ss += v[i] * v[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ss += v[i] * v[i];
     const float norm = sqrtf(block_sum(ss, scratch));
-    for (int i = threadIdx.x; i < n; i += blockDim.x) nv[i] = i < pad ? v[i] / norm : 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) nv[i] = v[i] / norm;  // DS:634
     __syncthreads();
-    for (int row = warp; row < n; row += nwarp) {
+    float* yout = ybuf + ((size_t)b * 2 + (it & 1)) * n;
+    for (int row = r_lo + warp; row < r_hi; row += nwarp) {
       float acc = 0.f;
       if (row < pad) {
         const float* ar = A + (size_t)row * n;
         if (vec4) {
           for (int c = lane * 4; c < pad; c += 128) {
             const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar + c));
-            acc = fmaf(a4.x, nv[c], acc);       // nv is 0 beyond pad
-            acc = fmaf(a4.y, nv[c + 1], acc);
-            acc = fmaf(a4.z, nv[c + 2], acc);
-            acc = fmaf(a4.w, nv[c + 3], acc);
+            const float m1 = c + 1 < pad ? a4.y : 0.f, m2 = c + 2 < pad ? a4.z : 0.f,
+                        m3 = c + 3 < pad ? a4.w : 0.f;
+            acc = fmaf(a4.x, nv[c], acc);
+            acc = fmaf(m1, nv[c + 1], acc);
+            acc = fmaf(m2, nv[c + 2], acc);
+            acc = fmaf(m3, nv[c + 3], acc);
           }
         } else {
           for (int c = lane; c < pad; c += 32) acc = fmaf(__ldg(ar + c), nv[c], acc);
         }
         acc = warp_sum(acc);
       }
-      if (lane == 0) y[row] = acc;
+      if (lane == 0) yout[row] = acc;  // DS:636
     }
-    __syncthreads();
+    if (csize > 1) {
+      pi_cluster_sync();
+    } else {
+      __threadfence_block();
+      __syncthreads();
+    }
     float dot = 0.f;
-    for (int i = threadIdx.x; i < pad; i += blockDim.x) dot += nv[i] * y[i];
-    const float s_new = block_sum(dot, scratch);
-    run = fabsf(s_new - s) > tol;  // DS:639 (NaN -> stop)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float yi = __ldcg(yout + i);
+      v[i] = yi;
+      dot += nv[i] * yi;
+    }
+    const float s_new = block_sum(dot, scratch);  // DS:637
+    run = fabsf(s_new - s) > tol;                 // DS:639 (NaN -> stop)
     s = s_new;
     ++it;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = y[i];
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && crank == 0) {
     if (lambdas) lambdas[b] = s;
     if (iters) iters[b] = it;
     if (ctl) ctl[b].max_ev = s;
@@ -329,6 +360,7 @@ struct RootWorkspace {
   uint32_t* errbits;
   int* unfinished;  // [1]
   float* v0;        // [n]
+  float* ybuf;      // [batch, 2, n] power-iteration exchange vectors
   char* engine_mem;
   size_t engine_bytes;
 };
@@ -343,6 +375,7 @@ static size_t header_bytes(int batch, int n) {
   s += align_up(sizeof(uint32_t) * batch, 256);
   s += 256;
   s += align_up(sizeof(float) * n, 256);
+  s += align_up(sizeof(float) * 2 * (size_t)batch * n, 256);
   return s;
 }
 
@@ -361,24 +394,45 @@ size_t root_workspace_bytes(int batch, int n, int engine) {
   return header_bytes(batch, n) + align_up(e, 256) + 1024;
 }
 
+static int pick_cluster_size(int batch) {
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int c = 8;
+  while (c > 1 && (long long)batch * c > sms) c >>= 1;
+  return c;
+}
+
 int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n,
                         int num_iters, float tol, float* lambdas, int32_t* iters,
-                        RootCtl* ctl, float* v0_dev, cudaStream_t stream) {
+                        RootCtl* ctl, float* v0_dev, float* ybuf, cudaStream_t stream) {
   std::vector<float> v0(n);
   mt19937_uniform(1729u, n, v0.data());
   PC_CUDA_CHECK(cudaMemcpyAsync(v0_dev, v0.data(), sizeof(float) * n,
                                 cudaMemcpyHostToDevice, stream));
-  PC_CUDA_CHECK(cudaStreamSynchronize(stream));  // v0 is a stack/heap temporary
-  const size_t smem = sizeof(float) * 3 * (size_t)n;
+  PC_CUDA_CHECK(cudaStreamSynchronize(stream));  // v0 is a heap temporary
+  const size_t smem = sizeof(float) * 2 * (size_t)n;
   if (smem > 48 * 1024) {
     PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
   }
+  int csize = n >= 256 ? pick_cluster_size(batch) : 1;
   const int threads = n >= 512 ? 1024 : (n >= 128 ? 512 : 128);
-  power_iteration_kernel<<<batch, threads, smem, stream>>>(xs, pads, v0_dev, n, num_iters,
-                                                          tol, lambdas, iters, ctl);
-  PC_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(batch * csize));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, power_iteration_kernel, xs, pads, (const float*)v0_dev,
+                                   n, num_iters, tol, lambdas, iters, ctl, ybuf, csize));
   return PC_OK;
 }
 
@@ -411,6 +465,7 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
   ws.errbits = reinterpret_cast<uint32_t*>(w); w += align_up(sizeof(uint32_t) * batch, 256);
   ws.unfinished = reinterpret_cast<int*>(w); w += 256;
   ws.v0 = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * n, 256);
+  ws.ybuf = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * 2 * (size_t)batch * n, 256);
   ws.engine_mem = w;
 
   // exponents decide how many GEMM launches one Newton iteration needs
@@ -430,7 +485,7 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
   PC_CUDA_CHECK(cudaGetLastError());
   if (opt->relative_matrix_epsilon && n > 1) {
     rc = run_power_iteration(xs, nullptr, batch, n, 100, 1e-6f, nullptr, nullptr, ws.ctl,
-                             ws.v0, stream);  // DS:820-825
+                             ws.v0, ws.ybuf, stream);  // DS:820-825
     if (rc != PC_OK) return rc;
   }
 
@@ -559,9 +614,10 @@ int pc_power_iteration_batched(const float* xs, const int32_t* padding_starts, i
   if (batch == 0) return PC_OK;
   PC_REQUIRE(xs && lambdas, "null pointer argument");
   float* v0 = nullptr;
-  PC_CUDA_CHECK(cudaMallocAsync(&v0, sizeof(float) * n, (cudaStream_t)stream));
+  PC_CUDA_CHECK(cudaMallocAsync(&v0, sizeof(float) * ((size_t)n + 2 * (size_t)batch * n),
+                                (cudaStream_t)stream));
   int rc = pc::run_power_iteration(xs, padding_starts, batch, n, num_iters, error_tolerance,
-                                   lambdas, iters, nullptr, v0, (cudaStream_t)stream);
+                                   lambdas, iters, nullptr, v0, v0 + n, (cudaStream_t)stream);
   cudaFreeAsync(v0, (cudaStream_t)stream);
   return rc;
 }

@@ -24,6 +24,7 @@
 // same row-major planes (no transposes anywhere).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "root_kernels.cuh"
 #include "tc_engine.cuh"
@@ -67,13 +68,35 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// L2 eviction-priority policies (same encodings as cute::TMA::CacheHintSm90)
+constexpr uint64_t kPolicyEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kPolicyEvictLast = 0x14F0000000000000ull;
+
+// EVICT_NORMAL by default; PC_TC_HINTS=1 switches operand loads to evict_last and result
+// stores to evict_first (measured neutral-to-worse on B200 at batch 32-64, kept as a knob)
+constexpr uint64_t kPolicyEvictNormal = 0x1000000000000000ull;
+__constant__ uint64_t g_load_policy = kPolicyEvictNormal;
+__constant__ uint64_t g_store_policy = kPolicyEvictNormal;
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "l"(g_load_policy)
       : "memory");
+}
+// results are consumed by a later launch: do not let them displace operands
+__device__ __forceinline__ void st_global_v4_stream(void* p, uint4 v) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w), "l"(g_store_policy)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_u16_stream(void* p, uint16_t v) {
+  asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"(v),
+               "l"(g_store_policy)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -157,6 +180,7 @@ struct TcParams {
   const RootCtl* ctl;
   uint32_t* errbits;
   int n, batch, tiles;  // tiles per dimension (n / 128)
+  int dbg;              // timing experiments only (PC_TC_DEBUG): 1 no mirror, 2 no stores, 4 no TMEM loads
 };
 
 struct TcWork {
@@ -226,6 +250,141 @@ __device__ __forceinline__ void store_planes32(const TcParams& P, size_t elem_of
   }
 }
 
+// Per-warp staging buffer for coalesced plane stores: 32 rows x 32 bf16 (2 KiB), 16-byte
+// chunks XOR-swizzled so that both the row writes and the 8-rows-x-64-B reads are
+// bank-conflict free.
+constexpr int TC_STAGE_BYTES_PER_WARP = 2048;
+__device__ __forceinline__ uint32_t stage_addr(uint32_t base, int r, int ch) {
+  return base + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
+}
+
+// Stores one bf16 plane of a 32 x 32 sub-block held one row per lane; hp[k] packs
+// columns 2k (low half) and 2k+1 (high half).
+//   direct: rows of the sub-block at gdirect + r * n   (8 rows x 64 B per instruction)
+//   mirror: element (r, i) also to gmirror + i * n + r  (lanes -> consecutive r, 64 B)
+// A sub-block ON the diagonal is first symmetrised through the staging buffer (lower
+// triangle authoritative) and needs no mirror.
+__device__ __forceinline__ void store_plane_block(uint32_t stage, int lane, uint32_t (&hp)[16],
+                                                  bool diag_sub, bool do_mirror,
+                                                  uint16_t* gdirect, uint16_t* gmirror, int n) {
+  auto write_row = [&]() {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(stage, lane, ch)),
+                   "r"(hp[4 * ch]), "r"(hp[4 * ch + 1]), "r"(hp[4 * ch + 2]), "r"(hp[4 * ch + 3])
+                   : "memory");
+    }
+  };
+  write_row();
+  __syncwarp();
+  if (diag_sub) {
+    // element (lane, i) for i > lane takes the value computed at (i, lane)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i > lane) {
+        const uint32_t a = stage_addr(stage, i, lane >> 3) + (lane & 7) * 2;
+        uint16_t x;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(x) : "r"(a) : "memory");
+        hp[i >> 1] = (i & 1) ? ((hp[i >> 1] & 0x0000ffffu) | ((uint32_t)x << 16))
+                             : ((hp[i >> 1] & 0xffff0000u) | (uint32_t)x);
+      }
+    }
+    __syncwarp();
+    write_row();
+    __syncwarp();
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), ch = lane & 3;
+    uint4 val;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                 : "r"(stage_addr(stage, r, ch))
+                 : "memory");
+    st_global_v4_stream(gdirect + (size_t)r * n + ch * 8, val);
+  }
+  if (do_mirror && !diag_sub) {
+    uint16_t* p = gmirror + lane;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      st_global_u16_stream(p, (uint16_t)(hp[k] & 0xffffu));
+      st_global_u16_stream(p + n, (uint16_t)(hp[k] >> 16));
+      p += 2 * (size_t)n;
+    }
+  }
+  __syncwarp();  // staging buffer is reused by the next plane
+}
+
+// fp32 row segment -> the three bf16 planes of a 32 x 32 sub-block (x is consumed).
+__device__ __forceinline__ void store_block_3planes(const TcParams& P, uint32_t stage, int lane,
+                                                    float (&x)[32], bool diag_sub, bool do_mirror,
+                                                    size_t direct_off, size_t mirror_off) {
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl) {
+    uint32_t hp[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const __nv_bfloat16 b0 = __float2bfloat16_rn(x[2 * k]);
+      const __nv_bfloat16 b1 = __float2bfloat16_rn(x[2 * k + 1]);
+      hp[k] = pack_bf16x2(b0, b1);
+      x[2 * k] -= __bfloat162float(b0);  // exact: residual feeds the next plane
+      x[2 * k + 1] -= __bfloat162float(b1);
+    }
+    store_plane_block(stage, lane, hp, diag_sub, do_mirror, P.plane[pl] + direct_off,
+                      P.plane[pl] + mirror_off, P.n);
+  }
+}
+
+// Epilogue of one 128 x 128 tile (tm, tn), tm >= tn; this thread owns one row.
+// OUT = sum, written directly and as the mirror (col, row) so that the stored matrix
+// is bitwise symmetric; optional M_i' emission and err reduction (DS:844-847).
+__device__ __forceinline__ void tc_epilogue_tile(const TcParams& P, const TcWork& wk, int tm,
+                                                 int row_in_tile, int lane, uint32_t stage,
+                                                 const float (&sum)[TC_BN]) {
+  const int q = row_in_tile >> 5;  // 32-row group of this warp inside the tile
+  const int row = tm * TC_BM + row_in_tile;
+  const int row0 = tm * TC_BM + q * 32;
+  const bool diag_tile = tm == wk.tn;
+  const size_t mat_off = (size_t)wk.b * P.mat_stride;
+  const size_t out_base = (size_t)physical_buf(wk.st.dst, wk.cur) * P.buf_stride + mat_off;
+  const size_t mi_base = (size_t)physical_buf(LB_MIN, wk.cur) * P.buf_stride + mat_off;
+  const float alpha = -1.0f / (float)wk.p, oma = 1.0f - alpha;
+  const bool mirror_on = !(P.dbg & 1);
+  uint32_t emax = 0;
+  auto write_group = [&](size_t base, float (&v)[32], int col0, bool diag_sub) {
+    if (P.dbg & 2) return;
+    store_block_3planes(P, stage, lane, v, diag_sub, mirror_on,
+                        base + (size_t)row0 * P.n + col0, base + (size_t)col0 * P.n + row0);
+  };
+#pragma unroll
+  for (int c = 0; c < TC_BN / 32; ++c) {
+    if (diag_tile && c > q) continue;  // strictly upper sub-block: written by its mirror
+    const bool diag_sub = diag_tile && c == q;
+    const int col0 = wk.tn * TC_BN + c * 32;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = sum[c * 32 + i];
+    if (wk.st.emit_mi) {
+      float mi[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool dg = (col0 + i == row) && (row < wk.pad);
+        if (!diag_sub || col0 + i <= row) {
+          const uint32_t ab = absbits(v[i] - (dg ? 1.f : 0.f));
+          emax = ab > emax ? ab : emax;
+        }
+        mi[i] = mi_from_m(v[i], dg, alpha, oma);
+      }
+      write_group(mi_base, mi, col0, diag_sub);
+    }
+    write_group(out_base, v, col0, diag_sub);
+  }
+  if (wk.st.emit_mi) {
+    emax = warp_max_u32(emax);
+    if (lane == 0 && emax) atomicMax(P.errbits + wk.b, emax);
+  }
+}
+
 template <int kLP, int kStages, int kChunkKB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_phase_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
@@ -241,6 +400,7 @@ tc_phase_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t stage_base = bar_base + 256;  // 4 warps x 2 KiB epilogue staging
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(
       smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -358,6 +518,7 @@ tc_phase_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN;
 #pragma unroll
         for (int c = 0; c < TC_BN / 32; ++c) {
+          if (P.dbg & 4) break;
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -368,71 +529,561 @@ tc_phase_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-      // ---- epilogue: OUT = sum (+ mirror); optional M_i' and err (DS:844-847) ----
-      // Tile (tm, tn), tm >= tn: rows of this thread go to (row, col) directly and
-      // to (col, row) as the mirror, so the stored matrix is bitwise symmetric.
-      const int row = wk.tm * TC_BM + row_in_tile;
-      const bool diag_tile = wk.tm == wk.tn;
-      const size_t mat_off = (size_t)wk.b * P.mat_stride;
-      const size_t out_base = (size_t)physical_buf(wk.st.dst, wk.cur) * P.buf_stride + mat_off;
-      const size_t mi_base = (size_t)physical_buf(LB_MIN, wk.cur) * P.buf_stride + mat_off;
-      const float alpha = -1.0f / (float)wk.p, oma = 1.0f - alpha;
-      uint32_t emax = 0;
-      auto write_group = [&](size_t base, const float (&v)[32], int col0) {
-        if (!diag_tile) store_planes32(P, base + (size_t)row * P.n + col0, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = col0 + i;
-          const bool direct = diag_tile && col <= row;
-          const bool mirror = diag_tile ? (col < row) : true;
-          const float x = v[i];
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(x);
-          const float r1 = x - __bfloat162float(h0);
-          const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
-          const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
-          if (direct) {
-            const size_t o = base + (size_t)row * P.n + col;
-            P.plane[0][o] = __bfloat16_as_ushort(h0);
-            P.plane[1][o] = __bfloat16_as_ushort(h1);
-            P.plane[2][o] = __bfloat16_as_ushort(h2);
-          }
-          if (mirror) {
-            const size_t o = base + (size_t)col * P.n + row;  // lanes -> consecutive rows
-            P.plane[0][o] = __bfloat16_as_ushort(h0);
-            P.plane[1][o] = __bfloat16_as_ushort(h1);
-            P.plane[2][o] = __bfloat16_as_ushort(h2);
-          }
-        }
-      };
-#pragma unroll
-      for (int c = 0; c < TC_BN / 32; ++c) {
-        const int col0 = wk.tn * TC_BN + c * 32;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = sum[c * 32 + i];
-        write_group(out_base, v, col0);
-        if (wk.st.emit_mi) {
-          float mi[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const bool dg = (col0 + i == row) && (row < wk.pad);
-            if (!diag_tile || col0 + i <= row) {
-              const uint32_t ab = absbits(v[i] - (dg ? 1.f : 0.f));
-              emax = ab > emax ? ab : emax;
-            }
-            mi[i] = mi_from_m(v[i], dg, alpha, oma);
-          }
-          write_group(mi_base, mi, col0);
-        }
-      }
-      if (wk.st.emit_mi) {
-        emax = warp_max_u32(emax);
-        if (lane == 0 && emax) atomicMax(P.errbits + wk.b, emax);
-      }
+      tc_epilogue_tile(P, wk, wk.tm, row_in_tile, lane, stage_base + q * TC_STAGE_BYTES_PER_WARP,
+                       sum);
     }
   }
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------
+// Warp-specialised 1-CTA kernel with dedicated epilogue warpgroups (512 threads):
+//   warpgroup 0  warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator
+//   warpgroup 1  chunk accumulation: pulls every K-chunk from TMEM, adds it to fp32
+//                registers (round-to-nearest) and parks the finished 128 x 128 tile
+//                in one of two TMEM "output" stages with tcgen05.st
+//   warpgroup 2  epilogue: tcgen05.ld from the output stage, 3-plane split, staged
+//                coalesced stores + mirror, M_i' / err
+// so tile i's global-memory epilogue overlaps tile i+1's MMAs.  TMEM: 2 chunk
+// accumulators + 2 output stages = 512 columns.  Registers are rebalanced with
+// setmaxnreg (40 / 200 / 136 / 136); the two epilogue warpgroups split each tile's columns.
+// ---------------------------------------------------------------------------
+constexpr int TC_WS_THREADS = 512;
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(
+          taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),
+      "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+      "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
+      "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// Same as tc_epilogue_tile but the tile is read from a TMEM output stage.
+__device__ __forceinline__ void tc_epilogue_tile_tmem(const TcParams& P, const TcWork& wk, int tm,
+                                                      int row_in_tile, int lane, uint32_t stage,
+                                                      uint32_t taddr, uint32_t oempty_bar,
+                                                      int c_begin, int c_end) {
+  const int q = row_in_tile >> 5;
+  const int row = tm * TC_BM + row_in_tile;
+  const int row0 = tm * TC_BM + q * 32;
+  const bool diag_tile = tm == wk.tn;
+  const size_t mat_off = (size_t)wk.b * P.mat_stride;
+  const size_t out_base = (size_t)physical_buf(wk.st.dst, wk.cur) * P.buf_stride + mat_off;
+  const size_t mi_base = (size_t)physical_buf(LB_MIN, wk.cur) * P.buf_stride + mat_off;
+  const float alpha = -1.0f / (float)wk.p, oma = 1.0f - alpha;
+  const bool mirror_on = !(P.dbg & 1);
+  uint32_t emax = 0;
+  auto write_group = [&](size_t base, float (&v)[32], int col0, bool diag_sub) {
+    if (P.dbg & 2) return;
+    store_block_3planes(P, stage, lane, v, diag_sub, mirror_on,
+                        base + (size_t)row0 * P.n + col0, base + (size_t)col0 * P.n + row0);
+  };
+#pragma unroll
+  for (int c = 0; c < TC_BN / 32; ++c) {
+    if (c < c_begin || c >= c_end) continue;  // the other epilogue warpgroup's columns
+    const bool skip = diag_tile && c > q;  // strictly upper sub-block: its mirror writes it
+    const bool diag_sub = diag_tile && c == q;
+    const int col0 = wk.tn * TC_BN + c * 32;
+    float g[32];
+    if (!skip) {
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(r[i]);
+    }
+    if (c == c_end - 1) {  // last TMEM read of this tile by this warp: recycle the stage
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(oempty_bar);
+    }
+    if (skip) continue;
+    if (wk.st.emit_mi) {
+      float mi[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool dg = (col0 + i == row) && (row < wk.pad);
+        if (!diag_sub || col0 + i <= row) {
+          const uint32_t ab = absbits(g[i] - (dg ? 1.f : 0.f));
+          emax = ab > emax ? ab : emax;
+        }
+        mi[i] = mi_from_m(g[i], dg, alpha, oma);
+      }
+      write_group(mi_base, mi, col0, diag_sub);
+    }
+    write_group(out_base, g, col0, diag_sub);
+  }
+  if (wk.st.emit_mi) {
+    emax = warp_max_u32(emax);
+    if (lane == 0 && emax) atomicMax(P.errbits + wk.b, emax);
+  }
+}
+
+template <int kLP, int kStages>
+__global__ void __launch_bounds__(TC_WS_THREADS, 1)
+tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
+                   const __grid_constant__ CUtensorMap tmap1,
+                   const __grid_constant__ CUtensorMap tmap2, const TcParams P,
+                   const Program* __restrict__ progs, int s, int total_work) {
+  constexpr int kStageBytes = 2 * kLP * TC_TILE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_base + 8u * (kStages + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };
+  auto ofull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 4 + i); };
+  auto oempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 6 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 8);
+  const uint32_t stage_base = bar_base + 256;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap0);
+    tma_prefetch_desc(&tmap1);
+    if (kLP > 2) tma_prefetch_desc(&tmap2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);
+      mbar_init(ofull_bar(i), 4);
+      mbar_init(oempty_bar(i), 8);  // 2 epilogue warpgroups x 4 warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        TcWork wk;
+        if (!tc_get_work(P, progs, s, w, wk)) continue;
+        const int pa = physical_buf(wk.st.a, wk.cur), pb = physical_buf(wk.st.b, wk.cur);
+        for (int kb = 0; kb < wk.kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t dst = smem_base + stage * kStageBytes;
+          mbar_expect_tx(full_bar(stage), kStageBytes);
+          const CUtensorMap* maps[3] = {&tmap0, &tmap1, &tmap2};
+#pragma unroll
+          for (int pl = 0; pl < kLP; ++pl) {
+            tma_load_4d(dst + pl * TC_TILE_BYTES, maps[pl], full_bar(stage), kb * TC_BK,
+                        wk.tm * TC_BM, wk.b, pa);
+            tma_load_4d(dst + (kLP + pl) * TC_TILE_BYTES, maps[pl], full_bar(stage), kb * TC_BK,
+                        wk.tn * TC_BN, wk.b, pb);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      int chunk = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        TcWork wk;
+        if (!tc_get_work(P, progs, s, w, wk)) continue;
+        for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+          const int acc = chunk & 1;
+          mbar_wait(tempty_bar(acc), ((chunk >> 1) & 1) ^ 1);
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * TC_BN;
+          const uint32_t a0 = smem_base + stage * kStageBytes;
+          const uint32_t b0 = a0 + kLP * TC_TILE_BYTES;
+          bool first = true;
+#pragma unroll
+          for (int sum = kLP - 1; sum >= 0; --sum) {
+#pragma unroll
+            for (int i = 0; i <= sum; ++i) {
+              const int j = sum - i;
+              const uint64_t ad = make_kmajor_sw128_desc(a0 + i * TC_TILE_BYTES);
+              const uint64_t bd = make_kmajor_sw128_desc(b0 + j * TC_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                umma_bf16(tmem_d, ad + 2u * k, bd + 2u * k, kIdescBf16M128N128,
+                          (first && k == 0) ? 0u : 1u);
+                if (k == 0) first = false;
+              }
+            }
+          }
+          umma_commit(empty_bar(stage));
+          umma_commit(tfull_bar(acc));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ============ warpgroup 1: chunk accumulation -> TMEM output stage ============
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int q = warp & 3;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    int chunk = 0, tile = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      TcWork wk;
+      if (!tc_get_work(P, progs, s, w, wk)) continue;
+      float sum[TC_BN];
+#pragma unroll
+      for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
+      for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+        const int acc = chunk & 1;
+        mbar_wait(tfull_bar(acc), (chunk >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + lane_off + acc * TC_BN;
+#pragma unroll
+        for (int c = 0; c < TC_BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      // park the finished tile in output stage o for the epilogue warpgroup
+      const int o = tile & 1;
+      mbar_wait(oempty_bar(o), ((tile >> 1) & 1) ^ 1);
+      tcgen05_fence_after();
+      const uint32_t oaddr = tmem_base + lane_off + 256 + o * TC_BN;
+#pragma unroll
+      for (int c = 0; c < TC_BN / 32; ++c) {
+        uint32_t r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(sum[c * 32 + i]);
+        tmem_st_32x32(oaddr + c * 32, r);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ofull_bar(o));
+      ++tile;
+    }
+  } else {
+    // ============ warpgroups 2, 3: epilogue (two column halves of every tile) ============
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    const int q = warp & 3;
+    const int half = (warp >> 2) - 2;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    int tile = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      TcWork wk;
+      if (!tc_get_work(P, progs, s, w, wk)) continue;
+      const int o = tile & 1;
+      mbar_wait(ofull_bar(o), (tile >> 1) & 1);
+      tcgen05_fence_after();
+      tc_epilogue_tile_tmem(P, wk, wk.tm, row_in_tile, lane,
+                            stage_base + (warp - 8) * TC_STAGE_BYTES_PER_WARP,
+                            tmem_base + lane_off + 256 + o * TC_BN, oempty_bar(o), 2 * half,
+                            2 * half + 2);
+      ++tile;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): one cluster of two CTAs owns a 256 x 128 output
+// tile.  CTA r holds A rows [r*128, r*128+128) and half of B's rows
+// [r*64, r*64+64); the leader's single thread issues tcgen05.mma.cta_group::2
+// (M = 256, N = 128) that reads both CTAs' shared memory.  Per SM this loads
+// 72 KB per k-block instead of 96 KB and leaves room for a third stage.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-pair bit of a smem address
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t"
+      "}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+// both CTAs issue; the transaction bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the MMAs retire) on the same-offset barrier of BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+constexpr uint32_t kIdescBf16M256N128 =
+    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+struct TcWork2 {
+  TcWork w;     // tm = 128-row tile index of THIS CTA
+  int valid;
+};
+
+// pair-tile index t -> (tm2, tn): all tn <= 2*tm2 + 1, i.e. t = tm2*(tm2+1) + tn
+__device__ __forceinline__ void pair_decode(int t, int& tm2, int& tn) {
+  int r = (int)((sqrtf(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while (r * (r + 1) > t) --r;
+  while ((r + 1) * (r + 2) <= t) ++r;
+  tm2 = r;
+  tn = t - r * (r + 1);
+}
+
+__device__ __forceinline__ bool tc_get_work_2cta(const TcParams& P, const Program* progs, int s,
+                                                 int w, int cta_rank, TcWork& out) {
+  const int t2 = P.tiles / 2;
+  const int npair = t2 * (t2 + 1);
+  const int per_mat = 2 * npair;
+  const int b = w / per_mat;
+  int r = w - b * per_mat;
+  const int op = r / npair;
+  r -= op * npair;
+  const RootCtl& c = P.ctl[b];
+  if (!c.active) return false;
+  if (op == 1) {
+    if (s != 0) return false;
+    out.st = Step{LB_HN, LB_H, LB_MI, 0};
+  } else {
+    const Program& pr = progs[c.p];
+    if (s >= pr.nsteps) return false;
+    out.st = pr.steps[s];
+  }
+  int tm2;
+  pair_decode(r, tm2, out.tn);
+  out.b = b;
+  out.tm = 2 * tm2 + cta_rank;
+  out.cur = c.cur;
+  out.p = c.p;
+  out.pad = c.pad;
+  out.kblocks = (c.pad + TC_BK - 1) / TC_BK;
+  return true;
+}
+
+template <int kLP, int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_phase_kernel_2cta(const __grid_constant__ CUtensorMap tmapA0,
+                     const __grid_constant__ CUtensorMap tmapA1,
+                     const __grid_constant__ CUtensorMap tmapA2,
+                     const __grid_constant__ CUtensorMap tmapB0,
+                     const __grid_constant__ CUtensorMap tmapB1,
+                     const __grid_constant__ CUtensorMap tmapB2, const TcParams P,
+                     const Program* __restrict__ progs, int s, int total_work) {
+  constexpr int kATile = TC_TILE_BYTES;      // 128 rows x 64 k
+  constexpr int kBTile = TC_TILE_BYTES / 2;  // 64 rows x 64 k (this CTA's half of B)
+  constexpr int kStageBytes = kLP * (kATile + kBTile);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };            // used in the leader
+  auto empty_bar = [&](int i) { return bar_base + 8u * (kStages + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };  // leader
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t stage_base = bar_base + 256;  // 4 warps x 2 KiB epilogue staging
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full_bar(i), 2);   // one arrive per CTA of the pair (+ tx bytes)
+      mbar_init(empty_bar(i), 1);  // tcgen05.commit multicast
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, TC_TMEM_COLS);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        TcWork wk;
+        if (!tc_get_work_2cta(P, progs, s, w, (int)cta_rank, wk)) continue;
+        const int pa = physical_buf(wk.st.a, wk.cur), pb = physical_buf(wk.st.b, wk.cur);
+        for (int kb = 0; kb < wk.kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t dst = smem_base + stage * kStageBytes;
+          if (leader) {
+            mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
+          } else {
+            mbar_arrive_remote(full_bar(stage), 0);
+          }
+          const CUtensorMap* mapsA[3] = {&tmapA0, &tmapA1, &tmapA2};
+          const CUtensorMap* mapsB[3] = {&tmapB0, &tmapB1, &tmapB2};
+#pragma unroll
+          for (int pl = 0; pl < kLP; ++pl) {
+            tma_load_4d_2sm(dst + pl * kATile, mapsA[pl], full_bar(stage), kb * TC_BK,
+                            wk.tm * TC_BM, wk.b, pa);
+            tma_load_4d_2sm(dst + kLP * kATile + pl * kBTile, mapsB[pl], full_bar(stage),
+                            kb * TC_BK, wk.tn * TC_BN + (int)cta_rank * 64, wk.b, pb);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int chunk = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        TcWork wk;
+        if (!tc_get_work_2cta(P, progs, s, w, 0, wk)) continue;
+        for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+          const int acc = chunk & 1;
+          const uint32_t acc_phase = (chunk >> 1) & 1;
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * TC_BN;
+          const uint32_t a0 = smem_base + stage * kStageBytes;
+          const uint32_t b0 = a0 + kLP * kATile;
+          bool first = true;
+#pragma unroll
+          for (int sum = kLP - 1; sum >= 0; --sum) {
+#pragma unroll
+            for (int i = 0; i <= sum; ++i) {
+              const int j = sum - i;
+              const uint64_t ad = make_kmajor_sw128_desc(a0 + i * kATile);
+              const uint64_t bd = make_kmajor_sw128_desc(b0 + j * kBTile);
+#pragma unroll
+              for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                umma_bf16_2sm(tmem_d, ad + 2u * k, bd + 2u * k, kIdescBf16M256N128,
+                              (first && k == 0) ? 0u : 1u);
+                if (k == 0) first = false;
+              }
+            }
+          }
+          umma_commit_2sm(empty_bar(stage));  // frees the slot in both CTAs
+          umma_commit_2sm(tfull_bar(acc));    // chunk accumulator ready in both CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============ chunk accumulation + epilogue (each CTA: its 128 rows) ============
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    int chunk = 0;
+    for (int w = cluster_id; w < total_work; w += num_clusters) {
+      TcWork wk;
+      if (!tc_get_work_2cta(P, progs, s, w, (int)cta_rank, wk)) continue;
+      float sum[TC_BN];
+#pragma unroll
+      for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
+      for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+        const int acc = chunk & 1;
+        const uint32_t acc_phase = (chunk >> 1) & 1;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN;
+#pragma unroll
+        for (int c = 0; c < TC_BN / 32; ++c) {
+          if (P.dbg & 4) break;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_remote(tempty_bar(acc), 0);
+        }
+      }
+      if (wk.tm >= wk.tn)  // the (2 tm2, 2 tm2 + 1) tile is upper-triangular: its mirror
+        tc_epilogue_tile(P, wk, wk.tm, row_in_tile, lane, stage_base + q * TC_STAGE_BYTES_PER_WARP,
+                       sum);  // owner writes it
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // no CTA may exit while its peer can still signal it
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, TC_TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------
@@ -494,6 +1145,9 @@ size_t tc_engine_bytes(int batch, int n) {
 
 struct TcHostState {
   CUtensorMap maps[3];
+  CUtensorMap maps_b64[3];  // box {64 k, 64 rows}: half B tiles of the CTA-pair kernel
+  bool use_2cta;
+  bool use_ws;  // warp-specialised kernel with a dedicated epilogue warpgroup
   TcParams prm;
   Program* progs_dev;
 };
@@ -524,6 +1178,11 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
     CUresult r = enc(&hs->maps[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, plane, dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint32_t box_b[4] = {TC_BK, 64, 1, 1};
+    if (r == CUDA_SUCCESS)
+      r = enc(&hs->maps_b64[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, plane, dims, strides, box_b,
+              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled failed with %d", (int)r);
       delete hs;
@@ -531,9 +1190,28 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
       return PC_ERR_CUDA;
     }
   }
+  {
+    const char* env = getenv("PC_TC_2CTA");
+    hs->use_2cta = (n % 256 == 0) && (env && env[0] == '1');  // opt-in: no gain measured yet
+    const char* ws = getenv("PC_TC_WS");
+    hs->use_ws = !(ws && ws[0] == '0');
+  }
   hs->prm.buf_stride = buf_stride;
   hs->prm.mat_stride = (size_t)n * n;
   hs->prm.n = n; hs->prm.batch = batch; hs->prm.tiles = n / TC_BM;
+  hs->prm.dbg = getenv("PC_TC_DEBUG") ? atoi(getenv("PC_TC_DEBUG")) : 0;
+  {
+    static int hints_set = -1;
+    const char* h = getenv("PC_TC_HINTS");
+    const int want = (h && h[0] == '1') ? 1 : 0;
+    if (hints_set != want) {
+      const uint64_t lp = want ? kPolicyEvictLast : kPolicyEvictNormal;
+      const uint64_t sp = want ? kPolicyEvictFirst : kPolicyEvictNormal;
+      cudaMemcpyToSymbol(g_load_policy, &lp, sizeof(lp));
+      cudaMemcpyToSymbol(g_store_policy, &sp, sizeof(sp));
+      hints_set = want;
+    }
+  }
   // device copy of the step programs (the tc kernel reads them from global memory)
   int dev = 0;
   PC_CUDA_CHECK(cudaGetDevice(&dev));
@@ -550,7 +1228,8 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
 
 template <int kLP, int kStages, int kChunkKB>
 static int launch_phase(TcHostState* hs, int s, int total_work, int grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 256;
+  constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 256 +
+                          4 * TC_STAGE_BYTES_PER_WARP;
   static bool configured = false;
   if (!configured) {
     PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel<kLP, kStages, kChunkKB>,
@@ -559,6 +1238,41 @@ static int launch_phase(TcHostState* hs, int s, int total_work, int grid, cudaSt
   }
   tc_phase_kernel<kLP, kStages, kChunkKB><<<grid, TC_THREADS, smem, stream>>>(
       hs->maps[0], hs->maps[1], hs->maps[2], hs->prm, hs->progs_dev, s, total_work);
+  return PC_OK;
+}
+
+template <int kLP, int kStages>
+static int launch_phase_ws(TcHostState* hs, int s, int total_work, int grid, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 256 +
+                          8 * TC_STAGE_BYTES_PER_WARP;
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_ws<kLP, kStages>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  tc_phase_kernel_ws<kLP, kStages><<<grid, TC_WS_THREADS, smem, stream>>>(
+      hs->maps[0], hs->maps[1], hs->maps[2], hs->prm, hs->progs_dev, s, total_work);
+  return PC_OK;
+}
+
+template <int kLP, int kStages>
+static int launch_phase_2cta(TcHostState* hs, int s, int batch, int sms, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)kStages * kLP * (TC_TILE_BYTES + TC_TILE_BYTES / 2) + 1024 + 256 +
+                          4 * TC_STAGE_BYTES_PER_WARP;
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_2cta<kLP, kStages>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int t2 = hs->prm.tiles / 2;
+  const int total_work = batch * 2 * t2 * (t2 + 1);
+  int clusters = sms / 2;
+  if (total_work < clusters) clusters = total_work;
+  tc_phase_kernel_2cta<kLP, kStages><<<2 * clusters, TC_THREADS, smem, stream>>>(
+      hs->maps[0], hs->maps[1], hs->maps[2], hs->maps_b64[0], hs->maps_b64[1], hs->maps_b64[2],
+      hs->prm, hs->progs_dev, s, total_work);
   return PC_OK;
 }
 
@@ -586,8 +1300,16 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
     cudaEventRecord(ev0, stream);
   }
   for (int s = 0; s < max_steps; ++s) {
-    int rc = e->passes == 6 ? launch_phase<3, 2, 1>(hs, s, total_work, grid, stream)
-                            : launch_phase<2, 3, 1>(hs, s, total_work, grid, stream);
+    int rc;
+    if (hs->use_2cta)
+      rc = e->passes == 6 ? launch_phase_2cta<3, 3>(hs, s, e->batch, sms, stream)
+                          : launch_phase_2cta<2, 4>(hs, s, e->batch, sms, stream);
+    else if (hs->use_ws)
+      rc = e->passes == 6 ? launch_phase_ws<3, 2>(hs, s, total_work, grid, stream)
+                          : launch_phase_ws<2, 3>(hs, s, total_work, grid, stream);
+    else
+      rc = e->passes == 6 ? launch_phase<3, 2, 1>(hs, s, total_work, grid, stream)
+                          : launch_phase<2, 3, 1>(hs, s, total_work, grid, stream);
     if (rc != PC_OK) return rc;
   }
   if (ev0) { cudaEventRecord(ev1, stream); gemm_timing_record(ev0, ev1); }
@@ -688,8 +1410,15 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = total_work < sms ? total_work : sms;
-  rc = passes == 6 ? launch_phase<3, 2, 1>(hs, 0, total_work, grid, stream)
-                   : launch_phase<2, 3, 1>(hs, 0, total_work, grid, stream);
+  if (hs->use_2cta)
+    rc = passes == 6 ? launch_phase_2cta<3, 3>(hs, 0, batch, sms, stream)
+                     : launch_phase_2cta<2, 4>(hs, 0, batch, sms, stream);
+  else if (hs->use_ws)
+    rc = passes == 6 ? launch_phase_ws<3, 2>(hs, 0, total_work, grid, stream)
+                     : launch_phase_ws<2, 3>(hs, 0, total_work, grid, stream);
+  else
+    rc = passes == 6 ? launch_phase<3, 2, 1>(hs, 0, total_work, grid, stream)
+                     : launch_phase<2, 3, 1>(hs, 0, total_work, grid, stream);
   if (rc == PC_OK) tc_debug_read_kernel<<<g, 256, 0, stream>>>(ps, LB_Q0, n, c);
   cudaFreeAsync(dprog, stream);
   delete hs;
