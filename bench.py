@@ -45,6 +45,7 @@ def parse_args():
   ap.add_argument("--cpu-sample", type=int, default=2,
                   help="matrices in the bounded CPU-baseline sample")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-step", action="store_true", help="skip the Shampoo-step measurement")
   return ap.parse_args()
 
 
@@ -303,18 +304,34 @@ def run_ours(a):
   peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
   peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
   achieved = (stats.gemm_flops / (stats.gemm_ms * 1e-3) / 1e12) if stats.gemm_ms > 0 else 0.0
+  traffic = None
+  try:  # dram bytes per launch from the committed `ncu --set full` summary of this kernel
+    tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    if tr.get("batch") == B and tr.get("n") == n:
+      traffic = tr["dram_bytes_per_launch"]
+  except (OSError, ValueError, KeyError):
+    pass
   m_host = metrics.cpu().numpy()
   resolved = {1: "simt_fp32", 2: "tcgen05_bf16x6", 3: "tcgen05_bf16x3"}[
       lib.pc_resolve_engine(n, engine)]
   passes = {"simt_fp32": 1, "tcgen05_bf16x6": 6, "tcgen05_bf16x3": 3}[resolved]
   roofline = {
       "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-      "frac": achieved / peak if peak else None, "traffic": None,
+      "frac": achieved / peak if peak else None, "traffic": traffic,
+      "launches_timed": int(stats.gemm_launches),
+      "algorithmic_flops_per_launch": stats.gemm_flops / max(int(stats.gemm_launches), 1),
       "kernel": "newton_chain_gemm", "engine": resolved,
       "algorithmic_flops_per_step": stats.gemm_flops, "gemm_ms_per_step": stats.gemm_ms,
       "gemm_share_of_step": stats.gemm_ms / ms_per_step if ms_per_step else None,
       "issued_passes": passes, "issued_tflops": achieved * passes, "peak_source": peak_src,
   }
+
+  # ---- second half of the headline metric: full Shampoo step on BASELINE config 2
+  #      (MLP 512->2048->512, block_size 128, SGD grafting, 1 GPU), through the
+  #      optax-style API; steps >= 5 so the preconditioned path is active ----
+  shampoo_step = None
+  if world == 1 and not a.no_step:
+    shampoo_step = time_shampoo_step(dev)
 
   if rank == 0:
     cpu_baseline = None
@@ -335,11 +352,41 @@ def run_ours(a):
                    "newton_iters_mean": float(m_host[:, 1].mean()),
                    "max_error": float(np.nanmax(m_host[:, 0]))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches // 1,
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "shampoo_step": shampoo_step,
     }
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()
+
+
+def time_shampoo_step(dev, steps=10, warm=6):
+  """ms per `update` of distributed_shampoo on the synthetic 2-layer MLP of BASELINE
+  config 2 (276 statistics of 128x128: 256 with p=4, 20 with p=2)."""
+  import torch
+  from precondition_b200 import distributed_shampoo as DS
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(0)
+  shapes = [(512, 2048), (2048,), (2048, 512), (512,)]
+  params = [torch.randn(s, generator=gen, device=dev) * 0.05 for s in shapes]
+  opt = DS.distributed_shampoo(0.1, 128, graft_type=DS.GraftingType.SGD)
+  state = opt.init(params)
+  grads = [[torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes]
+           for _ in range(warm + steps)]
+  for t in range(warm):
+    _, state = opt.update(grads[t], state, params)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for t in range(warm, warm + steps):
+    upd, state = opt.update(grads[t], state, params)
+  e1.record()
+  torch.cuda.synchronize()
+  tm = torch.cat([st.training_metrics for st in state.stats if st.training_metrics is not None])
+  return {"ms": e0.elapsed_time(e1) / steps, "unit": "ms/step", "steps": steps,
+          "config": "MLP 512->2048->512, block_size=128, SGD grafting, preconditioning_compute_steps=1",
+          "statistics": int(tm.shape[0]), "newton_iters_mean": float(tm[:, 1].mean()),
+          "max_root_error": float(tm[:, 0].max()),
+          "update_finite": bool(all(torch.isfinite(u).all() for u in upd))}
 
 
 def main():
