@@ -39,7 +39,8 @@ def parse_args():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--n", type=int, default=1024, help="statistic size (block_size)")
-  ap.add_argument("--batch", type=int, default=64, help="statistics per GPU per step")
+  ap.add_argument("--batch", type=int, default=74,
+                  help="statistics per GPU per step (74 = one per SM pair of a B200)")
   ap.add_argument("--p", type=int, default=4)
   ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc6", "tc3"])
   ap.add_argument("--cpu-sample", type=int, default=2,
@@ -102,7 +103,7 @@ class ClockSampler:
     try:
       self.proc = subprocess.Popen(
           ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-           "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+           "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
     except OSError:
@@ -169,6 +170,11 @@ def run_reference(a):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
+  try:  # torchrun exports OMP_NUM_THREADS=1; the reference arm may use every host core
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(limits=os.cpu_count() or 1)
+  except Exception:  # pylint: disable=broad-except
+    pass
   for _ in range(max(a.warmup, 0) and 1):
     time_cpu_port(a, 1)
   times = []

@@ -266,7 +266,15 @@ __device__ __forceinline__ uint32_t stage_addr(uint32_t base, int r, int ch) {
 // triangle authoritative) and needs no mirror.
 __device__ __forceinline__ void store_plane_block(uint32_t stage, int lane, uint32_t (&hp)[16],
                                                   bool diag_sub, bool do_mirror,
-                                                  uint16_t* gdirect, uint16_t* gmirror, int n) {
+                                                  uint16_t* gdirect, uint16_t* gmirror, int n,
+                                                  int dbg) {
+  if (dbg & 32) {  // timing experiment: keep the split live, skip staging and stores
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x ^= hp[k];
+    if (x == 0x12345678u) gdirect[0] = 1;
+    return;
+  }
   auto write_row = [&]() {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -301,9 +309,10 @@ __device__ __forceinline__ void store_plane_block(uint32_t stage, int lane, uint
                  : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                  : "r"(stage_addr(stage, r, ch))
                  : "memory");
-    st_global_v4_stream(gdirect + (size_t)r * n + ch * 8, val);
+    if (!(dbg & 16)) st_global_v4_stream(gdirect + (size_t)r * n + ch * 8, val);
+    else if (val.x == 0x12345678u) gdirect[0] = 1;
   }
-  if (do_mirror && !diag_sub) {
+  if (do_mirror && !diag_sub && !(dbg & 16)) {
     uint16_t* p = gmirror + lane;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -331,7 +340,7 @@ __device__ __forceinline__ void store_block_3planes(const TcParams& P, uint32_t 
       x[2 * k + 1] -= __bfloat162float(b1);
     }
     store_plane_block(stage, lane, hp, diag_sub, do_mirror, P.plane[pl] + direct_off,
-                      P.plane[pl] + mirror_off, P.n);
+                      P.plane[pl] + mirror_off, P.n, P.dbg);
   }
 }
 
@@ -568,11 +577,145 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+
+// ---- TMA store epilogue helpers (warp-specialised kernel) ----
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::
+                   "l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Per-thread staging addresses, computed once: row `lane` of buffer D (4 x 16-byte chunks)
+// and column `lane` of buffer T (rows 2k / 2k+1 are 128 / 64 bytes apart, the XOR swizzle
+// term only depends on k & 3).
+struct EpiAddr {
+  uint32_t d[4];  // D(lane, ch)
+  uint32_t t[4];  // T(0, lane) with the swizzle term of k & 3 == j
+};
+__device__ __forceinline__ EpiAddr make_epi_addr(uint32_t bufD, uint32_t bufT, int lane) {
+  EpiAddr e;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) e.d[ch] = stage_addr(bufD, lane, ch);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    e.t[j] = bufT + ((((uint32_t)lane >> 3) ^ (uint32_t)j) << 4) + ((uint32_t)lane & 7) * 2;
+  return e;
+}
+
+// One bf16 plane of a 32 x 32 sub-block, one row per lane (hp[k] = columns 2k, 2k+1):
+// the row-major block goes to staging buffer D, its transpose to buffer T (both in the
+// SWIZZLE_64B layout of the store tensor map), then one lane issues two bulk tensor
+// stores: D -> (row0, col0) and T -> (col0, row0).  No LDS / STG on the warp's critical
+// path; the buffers are recycled after cp.async.bulk.wait_group.read.
+__device__ __forceinline__ void store_plane_block_tma(uint32_t bufD, uint32_t bufT,
+                                                      const EpiAddr& ea, int lane,
+                                                      uint32_t (&hp)[16], bool diag_sub,
+                                                      bool do_mirror, const CUtensorMap* map,
+                                                      int row0, int col0, int b, int buf,
+                                                      int dbg) {
+  if (dbg & 32) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x ^= hp[k];
+    if (x == 0x12345678u) asm volatile("trap;");
+    return;
+  }
+  if (lane == 0 && !(dbg & 128)) tma_store_wait_read0();  // previous stores consumed the buffers
+  __syncwarp();
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ea.d[ch]), "r"(hp[4 * ch]),
+                 "r"(hp[4 * ch + 1]), "r"(hp[4 * ch + 2]), "r"(hp[4 * ch + 3])
+                 : "memory");
+  if (diag_sub) {
+    // rare path (4 of 36 tiles, 1 of 4 sub-blocks): element (lane, i), i > lane, takes the
+    // value computed at (i, lane); no mirror needed afterwards
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i > lane) {
+        const uint32_t a = stage_addr(bufD, i, lane >> 3) + (lane & 7) * 2;
+        uint16_t x;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(x) : "r"(a) : "memory");
+        hp[i >> 1] = (i & 1) ? ((hp[i >> 1] & 0x0000ffffu) | ((uint32_t)x << 16))
+                             : ((hp[i >> 1] & 0xffff0000u) | (uint32_t)x);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ea.d[ch]), "r"(hp[4 * ch]),
+                   "r"(hp[4 * ch + 1]), "r"(hp[4 * ch + 2]), "r"(hp[4 * ch + 3])
+                   : "memory");
+  } else if (do_mirror) {
+    // transpose: element (lane, i) -> T(i, lane); per row i the lanes write 64 contiguous bytes
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t a0 = ea.t[k & 3] + k * 128;  // row 2k
+      asm volatile(
+          "{\n\t"
+          ".reg .b16 lo, hi;\n\t"
+          "mov.b32 {lo, hi}, %1;\n\t"
+          "st.shared.b16 [%0], lo;\n\t"
+          "st.shared.b16 [%0 + 64], hi;\n\t"
+          "}" ::"r"(a0),
+          "r"(hp[k])
+          : "memory");
+    }
+  }
+  if (!(dbg & 64)) fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0 && !(dbg & 16)) {
+    tma_store_4d(map, bufD, col0, row0, b, buf);
+    if (do_mirror && !diag_sub) tma_store_4d(map, bufT, row0, col0, b, buf);
+    tma_store_commit();
+  }
+}
+
+// fp32 row segment (consumed) -> three bf16 planes, each staged and bulk-stored.
+__device__ __forceinline__ void store_block_3planes_tma(const TcParams& P, uint32_t stage,
+                                                        const EpiAddr& ea, int lane, float (&x)[32],
+                                                        bool diag_sub, bool do_mirror,
+                                                        const CUtensorMap* const (&smaps)[3],
+                                                        int row0, int col0, int b, int buf) {
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl) {
+    uint32_t hp[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const __nv_bfloat162 pr = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);  // one F2FP
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(&pr);
+      hp[k] = w;
+      if (pl < 2) {  // exact residuals feed the next plane
+        x[2 * k] -= __uint_as_float(w << 16);
+        x[2 * k + 1] -= __uint_as_float(w & 0xffff0000u);
+      }
+    }
+    store_plane_block_tma(stage, stage + TC_STAGE_BYTES_PER_WARP, ea, lane, hp, diag_sub,
+                          do_mirror, smaps[pl], row0, col0, b, buf, P.dbg);
+  }
+}
+
 // Same as tc_epilogue_tile but the tile is read from a TMEM output stage.
 __device__ __forceinline__ void tc_epilogue_tile_tmem(const TcParams& P, const TcWork& wk, int tm,
                                                       int row_in_tile, int lane, uint32_t stage,
                                                       uint32_t taddr, uint32_t oempty_bar,
-                                                      int c_begin, int c_end) {
+                                                      int c_begin, int c_end,
+                                                      const CUtensorMap* const (&smaps)[3]) {
   const int q = row_in_tile >> 5;
   const int row = tm * TC_BM + row_in_tile;
   const int row0 = tm * TC_BM + q * 32;
@@ -583,10 +726,11 @@ __device__ __forceinline__ void tc_epilogue_tile_tmem(const TcParams& P, const T
   const float alpha = -1.0f / (float)wk.p, oma = 1.0f - alpha;
   const bool mirror_on = !(P.dbg & 1);
   uint32_t emax = 0;
-  auto write_group = [&](size_t base, float (&v)[32], int col0, bool diag_sub) {
+  const EpiAddr ea = make_epi_addr(stage, stage + TC_STAGE_BYTES_PER_WARP, lane);
+  auto write_group = [&](int buf, float (&x)[32], int col0, bool diag_sub) {
     if (P.dbg & 2) return;
-    store_block_3planes(P, stage, lane, v, diag_sub, mirror_on,
-                        base + (size_t)row0 * P.n + col0, base + (size_t)col0 * P.n + row0);
+    store_block_3planes_tma(P, stage, ea, lane, x, diag_sub, mirror_on, smaps, row0, col0, wk.b,
+                            buf);
   };
 #pragma unroll
   for (int c = 0; c < TC_BN / 32; ++c) {
@@ -619,9 +763,9 @@ __device__ __forceinline__ void tc_epilogue_tile_tmem(const TcParams& P, const T
         }
         mi[i] = mi_from_m(g[i], dg, alpha, oma);
       }
-      write_group(mi_base, mi, col0, diag_sub);
+      write_group(physical_buf(LB_MIN, wk.cur), mi, col0, diag_sub);
     }
-    write_group(out_base, g, col0, diag_sub);
+    write_group(physical_buf(wk.st.dst, wk.cur), g, col0, diag_sub);
   }
   if (wk.st.emit_mi) {
     emax = warp_max_u32(emax);
@@ -633,7 +777,10 @@ template <int kLP, int kStages>
 __global__ void __launch_bounds__(TC_WS_THREADS, 1)
 tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
                    const __grid_constant__ CUtensorMap tmap1,
-                   const __grid_constant__ CUtensorMap tmap2, const TcParams P,
+                   const __grid_constant__ CUtensorMap tmap2,
+                   const __grid_constant__ CUtensorMap smap0,
+                   const __grid_constant__ CUtensorMap smap1,
+                   const __grid_constant__ CUtensorMap smap2, const TcParams P,
                    const Program* __restrict__ progs, int s, int total_work) {
   constexpr int kStageBytes = 2 * kLP * TC_TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -646,7 +793,7 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
   auto ofull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 4 + i); };
   auto oempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 6 + i); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 8);
-  const uint32_t stage_base = bar_base + 256;
+  const uint32_t stage_base = bar_base + 1024;  // 8 epilogue warps x (D + T) x 2 KiB, 1 KiB aligned
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -799,12 +946,14 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
       const int o = tile & 1;
       mbar_wait(ofull_bar(o), (tile >> 1) & 1);
       tcgen05_fence_after();
+      const CUtensorMap* const smaps[3] = {&smap0, &smap1, &smap2};
       tc_epilogue_tile_tmem(P, wk, wk.tm, row_in_tile, lane,
-                            stage_base + (warp - 8) * TC_STAGE_BYTES_PER_WARP,
+                            stage_base + (warp - 8) * 2 * TC_STAGE_BYTES_PER_WARP,
                             tmem_base + lane_off + 256 + o * TC_BN, oempty_bar(o), 2 * half,
-                            2 * half + 2);
+                            2 * half + 2, smaps);
       ++tile;
     }
+    if (lane == 0) tma_store_wait_all();  // all bulk stores landed before the CTA retires
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -1087,6 +1236,258 @@ tc_phase_kernel_2cta(const __grid_constant__ CUtensorMap tmapA0,
 }
 
 // ---------------------------------------------------------------------------
+// CTA-pair kernel, 256 x 256 output tile per cluster (cta_group::2, M = 256, N = 256).
+// This is the configuration that un-saturates shared memory: a 1-CTA M=128/N=128 MMA
+// reads 8 KB of operands per 64 cycles = the full 128 B/cycle smem bandwidth, so TMA
+// fills and epilogue staging starve it (measured: tensor pipe <= 69 %).  Here each CTA
+// feeds 8 KB per 128 cycles (64 B/cycle) and TMA adds 31 B/cycle.
+//   warpgroup 0   warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader), warp 2 TMEM
+//   warpgroup 1/2 chunk accumulation of columns [0,128) / [128,256) of this CTA's 128
+//                 rows in fp32 registers, then the epilogue of that 128 x 128 sub-tile
+//                 (3-plane split, swizzled staging, bulk tensor stores, mirror, M_i', err)
+// TMEM: 2 chunk accumulators x 256 columns.  setmaxnreg 40 / 232 / 232.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kIdescBf16M256N256 =
+    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ bool tc_get_work_pair256(const TcParams& P, const Program* progs, int s,
+                                                    int w, TcWork& out, int& tm2, int& tn2) {
+  const int t2 = P.tiles / 2;
+  const int ntri = t2 * (t2 + 1) / 2;
+  const int per_mat = 2 * ntri;
+  const int b = w / per_mat;
+  int r = w - b * per_mat;
+  const int op = r / ntri;
+  r -= op * ntri;
+  const RootCtl& c = P.ctl[b];
+  if (!c.active) return false;
+  if (op == 1) {
+    if (s != 0) return false;
+    out.st = Step{LB_HN, LB_H, LB_MI, 0};
+  } else {
+    const Program& pr = progs[c.p];
+    if (s >= pr.nsteps) return false;
+    out.st = pr.steps[s];
+  }
+  tri_decode(r, tm2, tn2);
+  out.b = b;
+  out.cur = c.cur;
+  out.p = c.p;
+  out.pad = c.pad;
+  out.kblocks = (c.pad + TC_BK - 1) / TC_BK;
+  return true;
+}
+
+// Epilogue of one 128 x 128 sub-tile whose fp32 values sit in this thread's registers.
+__device__ __forceinline__ void tc_epilogue_regs(const TcParams& P, const TcWork& wk, int tm, int tn,
+                                                 int row_in_tile, int lane, uint32_t stage,
+                                                 const float (&sum)[TC_BN],
+                                                 const CUtensorMap* const (&smaps)[3]) {
+  const int q = row_in_tile >> 5;
+  const int row = tm * TC_BM + row_in_tile;
+  const int row0 = tm * TC_BM + q * 32;
+  const bool diag_tile = tm == tn;
+  const float alpha = -1.0f / (float)wk.p, oma = 1.0f - alpha;
+  const bool mirror_on = !(P.dbg & 1);
+  uint32_t emax = 0;
+  const EpiAddr ea = make_epi_addr(stage, stage + TC_STAGE_BYTES_PER_WARP, lane);
+  auto write_group = [&](int buf, float (&x)[32], int col0, bool diag_sub) {
+    if (P.dbg & 2) return;
+    store_block_3planes_tma(P, stage, ea, lane, x, diag_sub, mirror_on, smaps, row0, col0, wk.b,
+                            buf);
+  };
+#pragma unroll
+  for (int c = 0; c < TC_BN / 32; ++c) {
+    if (diag_tile && c > q) continue;  // strictly upper sub-block: its mirror writes it
+    const bool diag_sub = diag_tile && c == q;
+    const int col0 = tn * TC_BN + c * 32;
+    float g[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) g[i] = sum[c * 32 + i];
+    if (wk.st.emit_mi) {
+      float mi[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool dg = (col0 + i == row) && (row < wk.pad);
+        if (!diag_sub || col0 + i <= row) {
+          const uint32_t ab = absbits(g[i] - (dg ? 1.f : 0.f));
+          emax = ab > emax ? ab : emax;
+        }
+        mi[i] = mi_from_m(g[i], dg, alpha, oma);
+      }
+      write_group(physical_buf(LB_MIN, wk.cur), mi, col0, diag_sub);
+    }
+    write_group(physical_buf(wk.st.dst, wk.cur), g, col0, diag_sub);
+  }
+  if (wk.st.emit_mi) {
+    emax = warp_max_u32(emax);
+    if (lane == 0 && emax) atomicMax(P.errbits + wk.b, emax);
+  }
+}
+
+constexpr int TC_P256_THREADS = 384;
+
+template <int kLP, int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_P256_THREADS, 1)
+tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
+                        const __grid_constant__ CUtensorMap tmap1,
+                        const __grid_constant__ CUtensorMap tmap2,
+                        const __grid_constant__ CUtensorMap smap0,
+                        const __grid_constant__ CUtensorMap smap1,
+                        const __grid_constant__ CUtensorMap smap2, const TcParams P,
+                        const Program* __restrict__ progs, int s, int total_work) {
+  constexpr int kStageBytes = 2 * kLP * TC_TILE_BYTES;  // A: 128 rows, B: this CTA's 128 rows
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };            // leader's is used
+  auto empty_bar = [&](int i) { return bar_base + 8u * (kStages + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };  // leader's
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t stage_base = bar_base + 1024;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full_bar(i), 2);
+      mbar_init(empty_bar(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 16);  // 8 accumulate warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        TcWork wk;
+        int tm2, tn2;
+        if (!tc_get_work_pair256(P, progs, s, w, wk, tm2, tn2)) continue;
+        const int pa = physical_buf(wk.st.a, wk.cur), pb = physical_buf(wk.st.b, wk.cur);
+        const int arow = tm2 * 256 + (int)cta_rank * 128, brow = tn2 * 256 + (int)cta_rank * 128;
+        for (int kb = 0; kb < wk.kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t dst = smem_base + stage * kStageBytes;
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
+          else mbar_arrive_remote(full_bar(stage), 0);
+          const CUtensorMap* maps[3] = {&tmap0, &tmap1, &tmap2};
+#pragma unroll
+          for (int pl = 0; pl < kLP; ++pl) {
+            tma_load_4d_2sm(dst + pl * TC_TILE_BYTES, maps[pl], full_bar(stage), kb * TC_BK, arow,
+                            wk.b, pa);
+            tma_load_4d_2sm(dst + (kLP + pl) * TC_TILE_BYTES, maps[pl], full_bar(stage),
+                            kb * TC_BK, brow, wk.b, pb);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0 && leader) {
+      // ===================== MMA issuer (leader CTA) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      int chunk = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        TcWork wk;
+        int tm2, tn2;
+        if (!tc_get_work_pair256(P, progs, s, w, wk, tm2, tn2)) continue;
+        for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+          const int acc = chunk & 1;
+          mbar_wait(tempty_bar(acc), ((chunk >> 1) & 1) ^ 1);
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * 256;
+          const uint32_t a0 = smem_base + stage * kStageBytes;
+          const uint32_t b0 = a0 + kLP * TC_TILE_BYTES;
+          bool first = true;
+#pragma unroll
+          for (int sum = kLP - 1; sum >= 0; --sum) {
+#pragma unroll
+            for (int i = 0; i <= sum; ++i) {
+              const int j = sum - i;
+              const uint64_t ad = make_kmajor_sw128_desc(a0 + i * TC_TILE_BYTES);
+              const uint64_t bd = make_kmajor_sw128_desc(b0 + j * TC_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                umma_bf16_2sm(tmem_d, ad + 2u * k, bd + 2u * k, kIdescBf16M256N256,
+                              (first && k == 0) ? 0u : 1u);
+                if (k == 0) first = false;
+              }
+            }
+          }
+          umma_commit_2sm(empty_bar(stage));
+          umma_commit_2sm(tfull_bar(acc));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ======= warpgroups 1, 2: accumulate columns [half*128, +128) and write that sub-tile =======
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int q = warp & 3;
+    const int half = (warp >> 2) - 1;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const CUtensorMap* const smaps[3] = {&smap0, &smap1, &smap2};
+    int chunk = 0;
+    for (int w = cluster_id; w < total_work; w += num_clusters) {
+      TcWork wk;
+      int tm2, tn2;
+      if (!tc_get_work_pair256(P, progs, s, w, wk, tm2, tn2)) continue;
+      float sum[TC_BN];
+#pragma unroll
+      for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
+      for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+        const int acc = chunk & 1;
+        mbar_wait(tfull_bar(acc), (chunk >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + lane_off + acc * 256 + half * TC_BN;
+#pragma unroll
+        for (int c = 0; c < TC_BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_remote(tempty_bar(acc), 0);
+        }
+      }
+      const int tm = 2 * tm2 + (int)cta_rank, tn = 2 * tn2 + half;
+      if (tm >= tn)  // (2 tm2, 2 tm2 + 1) of a diagonal pair-tile is upper: its mirror owns it
+        tc_epilogue_regs(P, wk, tm, tn, row_in_tile, lane,
+                         stage_base + (warp - 4) * 2 * TC_STAGE_BYTES_PER_WARP, sum, smaps);
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
 // plane store/load policy for the shared init / final kernels
 // ---------------------------------------------------------------------------
 struct PlaneStore {
@@ -1146,7 +1547,9 @@ size_t tc_engine_bytes(int batch, int n) {
 struct TcHostState {
   CUtensorMap maps[3];
   CUtensorMap maps_b64[3];  // box {64 k, 64 rows}: half B tiles of the CTA-pair kernel
+  CUtensorMap maps_st[3];   // box {32, 32}, SWIZZLE_64B: epilogue bulk stores
   bool use_2cta;
+  bool use_pair256;  // cta_group::2, 256 x 256 cluster tiles (default when n % 256 == 0)
   bool use_ws;  // warp-specialised kernel with a dedicated epilogue warpgroup
   TcParams prm;
   Program* progs_dev;
@@ -1183,6 +1586,11 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
       r = enc(&hs->maps_b64[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, plane, dims, strides, box_b,
               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint32_t box_s[4] = {32, 32, 1, 1};
+    if (r == CUDA_SUCCESS)
+      r = enc(&hs->maps_st[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, plane, dims, strides, box_s,
+              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled failed with %d", (int)r);
       delete hs;
@@ -1193,6 +1601,8 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
   {
     const char* env = getenv("PC_TC_2CTA");
     hs->use_2cta = (n % 256 == 0) && (env && env[0] == '1');  // opt-in: no gain measured yet
+    const char* p256 = getenv("PC_TC_PAIR256");
+    hs->use_pair256 = (n % 256 == 0) && !(p256 && p256[0] == '0');
     const char* ws = getenv("PC_TC_WS");
     hs->use_ws = !(ws && ws[0] == '0');
   }
@@ -1243,8 +1653,8 @@ static int launch_phase(TcHostState* hs, int s, int total_work, int grid, cudaSt
 
 template <int kLP, int kStages>
 static int launch_phase_ws(TcHostState* hs, int s, int total_work, int grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 256 +
-                          8 * TC_STAGE_BYTES_PER_WARP;
+  constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 1024 +
+                          16 * TC_STAGE_BYTES_PER_WARP;
   static bool configured = false;
   if (!configured) {
     PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_ws<kLP, kStages>,
@@ -1252,7 +1662,28 @@ static int launch_phase_ws(TcHostState* hs, int s, int total_work, int grid, cud
     configured = true;
   }
   tc_phase_kernel_ws<kLP, kStages><<<grid, TC_WS_THREADS, smem, stream>>>(
-      hs->maps[0], hs->maps[1], hs->maps[2], hs->prm, hs->progs_dev, s, total_work);
+      hs->maps[0], hs->maps[1], hs->maps[2], hs->maps_st[0], hs->maps_st[1], hs->maps_st[2],
+      hs->prm, hs->progs_dev, s, total_work);
+  return PC_OK;
+}
+
+template <int kLP, int kStages>
+static int launch_phase_pair256(TcHostState* hs, int s, int batch, int sms, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 1024 +
+                          16 * TC_STAGE_BYTES_PER_WARP;
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_pair256<kLP, kStages>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int t2 = hs->prm.tiles / 2;
+  const int total_work = batch * t2 * (t2 + 1);  // 2 ops x lower-triangular 256-tiles
+  int clusters = sms / 2;
+  if (total_work < clusters) clusters = total_work;
+  tc_phase_kernel_pair256<kLP, kStages><<<2 * clusters, TC_P256_THREADS, smem, stream>>>(
+      hs->maps[0], hs->maps[1], hs->maps[2], hs->maps_st[0], hs->maps_st[1], hs->maps_st[2],
+      hs->prm, hs->progs_dev, s, total_work);
   return PC_OK;
 }
 
@@ -1301,7 +1732,10 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
   }
   for (int s = 0; s < max_steps; ++s) {
     int rc;
-    if (hs->use_2cta)
+    if (hs->use_pair256)
+      rc = e->passes == 6 ? launch_phase_pair256<3, 2>(hs, s, e->batch, sms, stream)
+                          : launch_phase_pair256<2, 3>(hs, s, e->batch, sms, stream);
+    else if (hs->use_2cta)
       rc = e->passes == 6 ? launch_phase_2cta<3, 3>(hs, s, e->batch, sms, stream)
                           : launch_phase_2cta<2, 4>(hs, s, e->batch, sms, stream);
     else if (hs->use_ws)
@@ -1410,7 +1844,10 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = total_work < sms ? total_work : sms;
-  if (hs->use_2cta)
+  if (hs->use_pair256)
+    rc = passes == 6 ? launch_phase_pair256<3, 2>(hs, 0, batch, sms, stream)
+                     : launch_phase_pair256<2, 3>(hs, 0, batch, sms, stream);
+  else if (hs->use_2cta)
     rc = passes == 6 ? launch_phase_2cta<3, 3>(hs, 0, batch, sms, stream)
                      : launch_phase_2cta<2, 4>(hs, 0, batch, sms, stream);
   else if (hs->use_ws)
