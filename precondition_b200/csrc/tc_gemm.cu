@@ -78,13 +78,14 @@ constexpr uint64_t kPolicyEvictNormal = 0x1000000000000000ull;
 __constant__ uint64_t g_load_policy = kPolicyEvictNormal;
 __constant__ uint64_t g_store_policy = kPolicyEvictNormal;
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2, int c3) {
+// loads storage tile (tile_row, tile_col) of matrix `mat` (= buffer * batch + b): 16 KiB
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                              int tile_col, int tile_row, int mat) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
-      "l"(g_load_policy)
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(0), "r"(0), "r"(tile_col),
+      "r"(tile_row), "r"(mat), "l"(g_load_policy)
       : "memory");
 }
 // results are consumed by a later launch: do not let them displace operands
@@ -180,7 +181,6 @@ struct TcParams {
   const RootCtl* ctl;
   uint32_t* errbits;
   int n, batch, tiles;  // tiles per dimension (n / 128)
-  int dbg;              // timing experiments only (PC_TC_DEBUG): 1 no mirror, 2 no stores, 4 no TMEM loads
 };
 
 struct TcWork {
@@ -219,331 +219,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 
   return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
 }
 
-// writes 32 consecutive fp32 values of one row as three bf16 planes (64 B each)
-__device__ __forceinline__ void store_planes32(const TcParams& P, size_t elem_off,
-                                               const float (&v)[32]) {
-  uint32_t w0[16], w1[16], w2[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    __nv_bfloat16 a0[2], a1[2], a2[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float x = v[2 * i + h];
-      a0[h] = __float2bfloat16_rn(x);
-      const float r1 = x - __bfloat162float(a0[h]);
-      a1[h] = __float2bfloat16_rn(r1);
-      const float r2 = r1 - __bfloat162float(a1[h]);
-      a2[h] = __float2bfloat16_rn(r2);
-    }
-    w0[i] = pack_bf16x2(a0[0], a0[1]);
-    w1[i] = pack_bf16x2(a1[0], a1[1]);
-    w2[i] = pack_bf16x2(a2[0], a2[1]);
-  }
-  uint4* d0 = reinterpret_cast<uint4*>(P.plane[0] + elem_off);
-  uint4* d1 = reinterpret_cast<uint4*>(P.plane[1] + elem_off);
-  uint4* d2 = reinterpret_cast<uint4*>(P.plane[2] + elem_off);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    d0[q] = make_uint4(w0[4 * q], w0[4 * q + 1], w0[4 * q + 2], w0[4 * q + 3]);
-    d1[q] = make_uint4(w1[4 * q], w1[4 * q + 1], w1[4 * q + 2], w1[4 * q + 3]);
-    d2[q] = make_uint4(w2[4 * q], w2[4 * q + 1], w2[4 * q + 2], w2[4 * q + 3]);
-  }
-}
-
 // Per-warp staging buffer for coalesced plane stores: 32 rows x 32 bf16 (2 KiB), 16-byte
 // chunks XOR-swizzled so that both the row writes and the 8-rows-x-64-B reads are
 // bank-conflict free.
 constexpr int TC_STAGE_BYTES_PER_WARP = 2048;
 __device__ __forceinline__ uint32_t stage_addr(uint32_t base, int r, int ch) {
   return base + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
-}
-
-// Stores one bf16 plane of a 32 x 32 sub-block held one row per lane; hp[k] packs
-// columns 2k (low half) and 2k+1 (high half).
-//   direct: rows of the sub-block at gdirect + r * n   (8 rows x 64 B per instruction)
-//   mirror: element (r, i) also to gmirror + i * n + r  (lanes -> consecutive r, 64 B)
-// A sub-block ON the diagonal is first symmetrised through the staging buffer (lower
-// triangle authoritative) and needs no mirror.
-__device__ __forceinline__ void store_plane_block(uint32_t stage, int lane, uint32_t (&hp)[16],
-                                                  bool diag_sub, bool do_mirror,
-                                                  uint16_t* gdirect, uint16_t* gmirror, int n,
-                                                  int dbg) {
-  if (dbg & 32) {  // timing experiment: keep the split live, skip staging and stores
-    uint32_t x = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) x ^= hp[k];
-    if (x == 0x12345678u) gdirect[0] = 1;
-    return;
-  }
-  auto write_row = [&]() {
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr(stage, lane, ch)),
-                   "r"(hp[4 * ch]), "r"(hp[4 * ch + 1]), "r"(hp[4 * ch + 2]), "r"(hp[4 * ch + 3])
-                   : "memory");
-    }
-  };
-  write_row();
-  __syncwarp();
-  if (diag_sub) {
-    // element (lane, i) for i > lane takes the value computed at (i, lane)
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i > lane) {
-        const uint32_t a = stage_addr(stage, i, lane >> 3) + (lane & 7) * 2;
-        uint16_t x;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(x) : "r"(a) : "memory");
-        hp[i >> 1] = (i & 1) ? ((hp[i >> 1] & 0x0000ffffu) | ((uint32_t)x << 16))
-                             : ((hp[i >> 1] & 0xffff0000u) | (uint32_t)x);
-      }
-    }
-    __syncwarp();
-    write_row();
-    __syncwarp();
-  }
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int r = it * 8 + (lane >> 2), ch = lane & 3;
-    uint4 val;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                 : "r"(stage_addr(stage, r, ch))
-                 : "memory");
-    if (!(dbg & 16)) st_global_v4_stream(gdirect + (size_t)r * n + ch * 8, val);
-    else if (val.x == 0x12345678u) gdirect[0] = 1;
-  }
-  if (do_mirror && !diag_sub && !(dbg & 16)) {
-    uint16_t* p = gmirror + lane;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      st_global_u16_stream(p, (uint16_t)(hp[k] & 0xffffu));
-      st_global_u16_stream(p + n, (uint16_t)(hp[k] >> 16));
-      p += 2 * (size_t)n;
-    }
-  }
-  __syncwarp();  // staging buffer is reused by the next plane
-}
-
-// fp32 row segment -> the three bf16 planes of a 32 x 32 sub-block (x is consumed).
-__device__ __forceinline__ void store_block_3planes(const TcParams& P, uint32_t stage, int lane,
-                                                    float (&x)[32], bool diag_sub, bool do_mirror,
-                                                    size_t direct_off, size_t mirror_off) {
-#pragma unroll
-  for (int pl = 0; pl < 3; ++pl) {
-    uint32_t hp[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const __nv_bfloat16 b0 = __float2bfloat16_rn(x[2 * k]);
-      const __nv_bfloat16 b1 = __float2bfloat16_rn(x[2 * k + 1]);
-      hp[k] = pack_bf16x2(b0, b1);
-      x[2 * k] -= __bfloat162float(b0);  // exact: residual feeds the next plane
-      x[2 * k + 1] -= __bfloat162float(b1);
-    }
-    store_plane_block(stage, lane, hp, diag_sub, do_mirror, P.plane[pl] + direct_off,
-                      P.plane[pl] + mirror_off, P.n, P.dbg);
-  }
-}
-
-// Epilogue of one 128 x 128 tile (tm, tn), tm >= tn; this thread owns one row.
-// OUT = sum, written directly and as the mirror (col, row) so that the stored matrix
-// is bitwise symmetric; optional M_i' emission and err reduction (DS:844-847).
-__device__ __forceinline__ void tc_epilogue_tile(const TcParams& P, const TcWork& wk, int tm,
-                                                 int row_in_tile, int lane, uint32_t stage,
-                                                 const float (&sum)[TC_BN]) {
-  const int q = row_in_tile >> 5;  // 32-row group of this warp inside the tile
-  const int row = tm * TC_BM + row_in_tile;
-  const int row0 = tm * TC_BM + q * 32;
-  const bool diag_tile = tm == wk.tn;
-  const size_t mat_off = (size_t)wk.b * P.mat_stride;
-  const size_t out_base = (size_t)physical_buf(wk.st.dst, wk.cur) * P.buf_stride + mat_off;
-  const size_t mi_base = (size_t)physical_buf(LB_MIN, wk.cur) * P.buf_stride + mat_off;
-  const float alpha = -1.0f / (float)wk.p, oma = 1.0f - alpha;
-  const bool mirror_on = !(P.dbg & 1);
-  uint32_t emax = 0;
-  auto write_group = [&](size_t base, float (&v)[32], int col0, bool diag_sub) {
-    if (P.dbg & 2) return;
-    store_block_3planes(P, stage, lane, v, diag_sub, mirror_on,
-                        base + (size_t)row0 * P.n + col0, base + (size_t)col0 * P.n + row0);
-  };
-#pragma unroll
-  for (int c = 0; c < TC_BN / 32; ++c) {
-    if (diag_tile && c > q) continue;  // strictly upper sub-block: written by its mirror
-    const bool diag_sub = diag_tile && c == q;
-    const int col0 = wk.tn * TC_BN + c * 32;
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = sum[c * 32 + i];
-    if (wk.st.emit_mi) {
-      float mi[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const bool dg = (col0 + i == row) && (row < wk.pad);
-        if (!diag_sub || col0 + i <= row) {
-          const uint32_t ab = absbits(v[i] - (dg ? 1.f : 0.f));
-          emax = ab > emax ? ab : emax;
-        }
-        mi[i] = mi_from_m(v[i], dg, alpha, oma);
-      }
-      write_group(mi_base, mi, col0, diag_sub);
-    }
-    write_group(out_base, v, col0, diag_sub);
-  }
-  if (wk.st.emit_mi) {
-    emax = warp_max_u32(emax);
-    if (lane == 0 && emax) atomicMax(P.errbits + wk.b, emax);
-  }
-}
-
-template <int kLP, int kStages, int kChunkKB>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_phase_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
-                const __grid_constant__ CUtensorMap tmap2, const TcParams P,
-                const Program* __restrict__ progs, int s, int total_work) {
-  constexpr int kStageBytes = 2 * kLP * TC_TILE_BYTES;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  // barriers live after the operand ring
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
-  auto full_bar = [&](int i) { return bar_base + 8u * i; };
-  auto empty_bar = [&](int i) { return bar_base + 8u * (kStages + i); };
-  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  const uint32_t stage_base = bar_base + 256;  // 4 warps x 2 KiB epilogue staging
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(
-      smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap0);
-    tma_prefetch_desc(&tmap1);
-    if (kLP > 2) tma_prefetch_desc(&tmap2);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(full_bar(i), 1);
-      mbar_init(empty_bar(i), 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 4);  // one arrive per epilogue warp
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, TC_TMEM_COLS);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        TcWork wk;
-        if (!tc_get_work(P, progs, s, w, wk)) continue;
-        const int pa = physical_buf(wk.st.a, wk.cur), pb = physical_buf(wk.st.b, wk.cur);
-        for (int kb = 0; kb < wk.kblocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t dst = smem_base + stage * kStageBytes;
-          mbar_expect_tx(full_bar(stage), kStageBytes);
-          const CUtensorMap* maps[3] = {&tmap0, &tmap1, &tmap2};
-#pragma unroll
-          for (int pl = 0; pl < kLP; ++pl) {
-            tma_load_4d(dst + pl * TC_TILE_BYTES, maps[pl], full_bar(stage), kb * TC_BK,
-                        wk.tm * TC_BM, wk.b, pa);
-            tma_load_4d(dst + (kLP + pl) * TC_TILE_BYTES, maps[pl], full_bar(stage), kb * TC_BK,
-                        wk.tn * TC_BN, wk.b, pb);
-          }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int chunk = 0;  // running chunk counter -> TMEM stage / parity
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        TcWork wk;
-        if (!tc_get_work(P, progs, s, w, wk)) continue;
-        for (int kb0 = 0; kb0 < wk.kblocks; kb0 += kChunkKB, ++chunk) {
-          const int acc = chunk & 1;
-          const uint32_t acc_phase = (chunk >> 1) & 1;
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-          tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + acc * TC_BN;
-          const int kb1 = min(kb0 + kChunkKB, wk.kblocks);
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(full_bar(stage), phase);
-            tcgen05_fence_after();
-            const uint32_t a0 = smem_base + stage * kStageBytes;
-            const uint32_t b0 = a0 + kLP * TC_TILE_BYTES;
-            bool first = (kb == kb0);
-            // smallest terms first: plane pairs (i, j) with i + j descending
-#pragma unroll
-            for (int sum = kLP - 1; sum >= 0; --sum) {
-#pragma unroll
-              for (int i = 0; i <= sum; ++i) {
-                const int j = sum - i;
-                const uint64_t ad = make_kmajor_sw128_desc(a0 + i * TC_TILE_BYTES);
-                const uint64_t bd = make_kmajor_sw128_desc(b0 + j * TC_TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                  // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in (addr >> 4)
-                  umma_bf16(tmem_d, ad + 2u * k, bd + 2u * k, kIdescBf16M128N128,
-                            (first && k == 0) ? 0u : 1u);
-                  if (k == 0) first = false;
-                }
-              }
-            }
-            umma_commit(empty_bar(stage));  // frees the smem slot when the MMAs retire
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-          }
-          umma_commit(tfull_bar(acc));  // chunk accumulator complete
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    // ============ chunk accumulation + epilogue (128 threads = 128 TMEM lanes) ============
-    const int q = warp & 3;              // TMEM lane quadrant of this warp
-    const int row_in_tile = q * 32 + lane;
-    int chunk = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      TcWork wk;
-      if (!tc_get_work(P, progs, s, w, wk)) continue;
-      float sum[TC_BN];
-#pragma unroll
-      for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
-      for (int kb0 = 0; kb0 < wk.kblocks; kb0 += kChunkKB, ++chunk) {
-        const int acc = chunk & 1;
-        const uint32_t acc_phase = (chunk >> 1) & 1;
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN;
-#pragma unroll
-        for (int c = 0; c < TC_BN / 32; ++c) {
-          if (P.dbg & 4) break;
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-      }
-      tc_epilogue_tile(P, wk, wk.tm, row_in_tile, lane, stage_base + q * TC_STAGE_BYTES_PER_WARP,
-                       sum);
-    }
-  }
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------
@@ -579,12 +260,14 @@ __device__ __forceinline__ void tmem_st_wait() {
 
 
 // ---- TMA store epilogue helpers (warp-specialised kernel) ----
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1,
-                                             int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::
-                   "l"(reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
+// stores a 32 x 32 block whose top-left element is (row, col) of matrix `mat`
+__device__ __forceinline__ void tma_store_block(const CUtensorMap* map, uint32_t src, int col,
+                                                int row, int mat) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::
+          "l"(reinterpret_cast<uint64_t>(map)),
+      "r"(src), "r"(col & 63), "r"(row & 127), "r"(col >> 6), "r"(row >> 7), "r"(mat)
+      : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -616,6 +299,30 @@ __device__ __forceinline__ EpiAddr make_epi_addr(uint32_t bufD, uint32_t bufT, i
   return e;
 }
 
+// Diagonal 32 x 32 sub-block already staged row-major in `buf`: overwrite the strictly
+// upper triangle with the transposed lower one, in place (lower triangle authoritative).
+// Out of line and loop-rolled on purpose: it is rare and must not bloat the hot epilogue.
+__device__ __noinline__ void symmetrise_diag_block(uint32_t buf, int lane) {
+  __syncwarp();
+  uint16_t col[32];
+#pragma unroll 1
+  for (int i = 0; i < 32; ++i) {  // lane reads element (i, lane): one contiguous row per step
+    const uint32_t a = stage_addr(buf, i, lane >> 3) + (lane & 7) * 2;
+    uint16_t x;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(x) : "r"(a) : "memory");
+    col[i] = x;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int i = 0; i < 32; ++i) {  // element (lane, i), i > lane, <- value of (i, lane)
+    if (i > lane) {
+      const uint32_t a = stage_addr(buf, lane, i >> 3) + (i & 7) * 2;
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(col[i]) : "memory");
+    }
+  }
+  __syncwarp();
+}
+
 // One bf16 plane of a 32 x 32 sub-block, one row per lane (hp[k] = columns 2k, 2k+1):
 // the row-major block goes to staging buffer D, its transpose to buffer T (both in the
 // SWIZZLE_64B layout of the store tensor map), then one lane issues two bulk tensor
@@ -625,16 +332,8 @@ __device__ __forceinline__ void store_plane_block_tma(uint32_t bufD, uint32_t bu
                                                       const EpiAddr& ea, int lane,
                                                       uint32_t (&hp)[16], bool diag_sub,
                                                       bool do_mirror, const CUtensorMap* map,
-                                                      int row0, int col0, int b, int buf,
-                                                      int dbg) {
-  if (dbg & 32) {
-    uint32_t x = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) x ^= hp[k];
-    if (x == 0x12345678u) asm volatile("trap;");
-    return;
-  }
-  if (lane == 0 && !(dbg & 128)) tma_store_wait_read0();  // previous stores consumed the buffers
+                                                      int row0, int col0, int mat) {
+  if (lane == 0) tma_store_wait_read0();  // previous stores have consumed the buffers
   __syncwarp();
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch)
@@ -642,25 +341,7 @@ __device__ __forceinline__ void store_plane_block_tma(uint32_t bufD, uint32_t bu
                  "r"(hp[4 * ch + 1]), "r"(hp[4 * ch + 2]), "r"(hp[4 * ch + 3])
                  : "memory");
   if (diag_sub) {
-    // rare path (4 of 36 tiles, 1 of 4 sub-blocks): element (lane, i), i > lane, takes the
-    // value computed at (i, lane); no mirror needed afterwards
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i > lane) {
-        const uint32_t a = stage_addr(bufD, i, lane >> 3) + (lane & 7) * 2;
-        uint16_t x;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(x) : "r"(a) : "memory");
-        hp[i >> 1] = (i & 1) ? ((hp[i >> 1] & 0x0000ffffu) | ((uint32_t)x << 16))
-                             : ((hp[i >> 1] & 0xffff0000u) | (uint32_t)x);
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ea.d[ch]), "r"(hp[4 * ch]),
-                   "r"(hp[4 * ch + 1]), "r"(hp[4 * ch + 2]), "r"(hp[4 * ch + 3])
-                   : "memory");
+    symmetrise_diag_block(bufD, lane);  // rare: 1 of 4 sub-blocks of the 4-8 diagonal tiles
   } else if (do_mirror) {
     // transpose: element (lane, i) -> T(i, lane); per row i the lanes write 64 contiguous bytes
 #pragma unroll
@@ -677,11 +358,11 @@ __device__ __forceinline__ void store_plane_block_tma(uint32_t bufD, uint32_t bu
           : "memory");
     }
   }
-  if (!(dbg & 64)) fence_proxy_async_smem();
+  fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0 && !(dbg & 16)) {
-    tma_store_4d(map, bufD, col0, row0, b, buf);
-    if (do_mirror && !diag_sub) tma_store_4d(map, bufT, row0, col0, b, buf);
+  if (lane == 0) {
+    tma_store_block(map, bufD, col0, row0, mat);
+    if (do_mirror && !diag_sub) tma_store_block(map, bufT, row0, col0, mat);
     tma_store_commit();
   }
 }
@@ -691,9 +372,9 @@ __device__ __forceinline__ void store_block_3planes_tma(const TcParams& P, uint3
                                                         const EpiAddr& ea, int lane, float (&x)[32],
                                                         bool diag_sub, bool do_mirror,
                                                         const CUtensorMap* const (&smaps)[3],
-                                                        int row0, int col0, int b, int buf) {
-#pragma unroll
-  for (int pl = 0; pl < 3; ++pl) {
+                                                        int row0, int col0, int mat) {
+#pragma unroll 1
+  for (int pl = 0; pl < 3; ++pl) {  // rolled: keeps the kernel inside the instruction cache
     uint32_t hp[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -706,7 +387,7 @@ __device__ __forceinline__ void store_block_3planes_tma(const TcParams& P, uint3
       }
     }
     store_plane_block_tma(stage, stage + TC_STAGE_BYTES_PER_WARP, ea, lane, hp, diag_sub,
-                          do_mirror, smaps[pl], row0, col0, b, buf, P.dbg);
+                          do_mirror, smaps[pl], row0, col0, mat);
   }
 }
 
@@ -724,17 +405,15 @@ __device__ __forceinline__ void tc_epilogue_tile_tmem(const TcParams& P, const T
   const size_t out_base = (size_t)physical_buf(wk.st.dst, wk.cur) * P.buf_stride + mat_off;
   const size_t mi_base = (size_t)physical_buf(LB_MIN, wk.cur) * P.buf_stride + mat_off;
   const float alpha = -1.0f / (float)wk.p, oma = 1.0f - alpha;
-  const bool mirror_on = !(P.dbg & 1);
+  const bool mirror_on = true;
   uint32_t emax = 0;
   const EpiAddr ea = make_epi_addr(stage, stage + TC_STAGE_BYTES_PER_WARP, lane);
   auto write_group = [&](int buf, float (&x)[32], int col0, bool diag_sub) {
-    if (P.dbg & 2) return;
-    store_block_3planes_tma(P, stage, ea, lane, x, diag_sub, mirror_on, smaps, row0, col0, wk.b,
-                            buf);
+    store_block_3planes_tma(P, stage, ea, lane, x, diag_sub, mirror_on, smaps, row0, col0,
+                            buf * P.batch + wk.b);
   };
-#pragma unroll
-  for (int c = 0; c < TC_BN / 32; ++c) {
-    if (c < c_begin || c >= c_end) continue;  // the other epilogue warpgroup's columns
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {  // rolled: g is addressed in TMEM, not in registers
     const bool skip = diag_tile && c > q;  // strictly upper sub-block: its mirror writes it
     const bool diag_sub = diag_tile && c == q;
     const int col0 = wk.tn * TC_BN + c * 32;
@@ -752,20 +431,25 @@ __device__ __forceinline__ void tc_epilogue_tile_tmem(const TcParams& P, const T
       if (lane == 0) mbar_arrive(oempty_bar);
     }
     if (skip) continue;
-    if (wk.st.emit_mi) {
-      float mi[32];
+#pragma unroll 1
+    for (int o = wk.st.emit_mi ? 0 : 1; o < 2; ++o) {  // o = 0: M_i' (DS:844), o = 1: OUT
+      float x[32];
+      if (o == 0) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const bool dg = (col0 + i == row) && (row < wk.pad);
-        if (!diag_sub || col0 + i <= row) {
-          const uint32_t ab = absbits(g[i] - (dg ? 1.f : 0.f));
-          emax = ab > emax ? ab : emax;
+        for (int i = 0; i < 32; ++i) {
+          const bool dg = (col0 + i == row) && (row < wk.pad);
+          if (!diag_sub || col0 + i <= row) {
+            const uint32_t ab = absbits(g[i] - (dg ? 1.f : 0.f));  // DS:847
+            emax = ab > emax ? ab : emax;
+          }
+          x[i] = mi_from_m(g[i], dg, alpha, oma);
         }
-        mi[i] = mi_from_m(g[i], dg, alpha, oma);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = g[i];
       }
-      write_group(physical_buf(LB_MIN, wk.cur), mi, col0, diag_sub);
+      write_group(physical_buf(o == 0 ? (int)LB_MIN : (int)wk.st.dst, wk.cur), x, col0, diag_sub);
     }
-    write_group(physical_buf(wk.st.dst, wk.cur), g, col0, diag_sub);
   }
   if (wk.st.emit_mi) {
     emax = warp_max_u32(emax);
@@ -839,10 +523,10 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
           const CUtensorMap* maps[3] = {&tmap0, &tmap1, &tmap2};
 #pragma unroll
           for (int pl = 0; pl < kLP; ++pl) {
-            tma_load_4d(dst + pl * TC_TILE_BYTES, maps[pl], full_bar(stage), kb * TC_BK,
-                        wk.tm * TC_BM, wk.b, pa);
-            tma_load_4d(dst + (kLP + pl) * TC_TILE_BYTES, maps[pl], full_bar(stage), kb * TC_BK,
-                        wk.tn * TC_BN, wk.b, pb);
+            tma_load_tile(dst + pl * TC_TILE_BYTES, maps[pl], full_bar(stage), kb, wk.tm,
+                          pa * P.batch + wk.b);
+            tma_load_tile(dst + (kLP + pl) * TC_TILE_BYTES, maps[pl], full_bar(stage), kb, wk.tn,
+                          pb * P.batch + wk.b);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -989,13 +673,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
       : "memory");
 }
 // both CTAs issue; the transaction bytes are credited to the LEADER's barrier
-__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                                int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_tile_2sm(uint32_t dst, const CUtensorMap* map,
+                                                  uint32_t bar, int tile_col, int tile_row,
+                                                  int mat) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2),
-      "r"(c3)
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(0), "r"(0),
+      "r"(tile_col), "r"(tile_row), "r"(mat)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
@@ -1075,166 +760,6 @@ __device__ __forceinline__ bool tc_get_work_2cta(const TcParams& P, const Progra
   return true;
 }
 
-template <int kLP, int kStages>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-tc_phase_kernel_2cta(const __grid_constant__ CUtensorMap tmapA0,
-                     const __grid_constant__ CUtensorMap tmapA1,
-                     const __grid_constant__ CUtensorMap tmapA2,
-                     const __grid_constant__ CUtensorMap tmapB0,
-                     const __grid_constant__ CUtensorMap tmapB1,
-                     const __grid_constant__ CUtensorMap tmapB2, const TcParams P,
-                     const Program* __restrict__ progs, int s, int total_work) {
-  constexpr int kATile = TC_TILE_BYTES;      // 128 rows x 64 k
-  constexpr int kBTile = TC_TILE_BYTES / 2;  // 64 rows x 64 k (this CTA's half of B)
-  constexpr int kStageBytes = kLP * (kATile + kBTile);
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
-  auto full_bar = [&](int i) { return bar_base + 8u * i; };            // used in the leader
-  auto empty_bar = [&](int i) { return bar_base + 8u * (kStages + i); };
-  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };  // leader
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  const uint32_t stage_base = bar_base + 256;  // 4 warps x 2 KiB epilogue staging
-  uint32_t* tmem_slot_ptr =
-      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta_rank = cluster_ctarank();
-  const bool leader = cta_rank == 0;
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(full_bar(i), 2);   // one arrive per CTA of the pair (+ tx bytes)
-      mbar_init(empty_bar(i), 1);  // tcgen05.commit multicast
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 8);  // 4 epilogue warps x 2 CTAs
-    }
-    fence_barrier_init();
-  }
-  cluster_sync_all();
-  if (warp == 2) tmem_alloc_2sm(tmem_slot, TC_TMEM_COLS);
-  tcgen05_fence_before();
-  cluster_sync_all();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int w = cluster_id; w < total_work; w += num_clusters) {
-        TcWork wk;
-        if (!tc_get_work_2cta(P, progs, s, w, (int)cta_rank, wk)) continue;
-        const int pa = physical_buf(wk.st.a, wk.cur), pb = physical_buf(wk.st.b, wk.cur);
-        for (int kb = 0; kb < wk.kblocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t dst = smem_base + stage * kStageBytes;
-          if (leader) {
-            mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
-          } else {
-            mbar_arrive_remote(full_bar(stage), 0);
-          }
-          const CUtensorMap* mapsA[3] = {&tmapA0, &tmapA1, &tmapA2};
-          const CUtensorMap* mapsB[3] = {&tmapB0, &tmapB1, &tmapB2};
-#pragma unroll
-          for (int pl = 0; pl < kLP; ++pl) {
-            tma_load_4d_2sm(dst + pl * kATile, mapsA[pl], full_bar(stage), kb * TC_BK,
-                            wk.tm * TC_BM, wk.b, pa);
-            tma_load_4d_2sm(dst + kLP * kATile + pl * kBTile, mapsB[pl], full_bar(stage),
-                            kb * TC_BK, wk.tn * TC_BN + (int)cta_rank * 64, wk.b, pb);
-          }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int chunk = 0;
-      for (int w = cluster_id; w < total_work; w += num_clusters) {
-        TcWork wk;
-        if (!tc_get_work_2cta(P, progs, s, w, 0, wk)) continue;
-        for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
-          const int acc = chunk & 1;
-          const uint32_t acc_phase = (chunk >> 1) & 1;
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + acc * TC_BN;
-          const uint32_t a0 = smem_base + stage * kStageBytes;
-          const uint32_t b0 = a0 + kLP * kATile;
-          bool first = true;
-#pragma unroll
-          for (int sum = kLP - 1; sum >= 0; --sum) {
-#pragma unroll
-            for (int i = 0; i <= sum; ++i) {
-              const int j = sum - i;
-              const uint64_t ad = make_kmajor_sw128_desc(a0 + i * kATile);
-              const uint64_t bd = make_kmajor_sw128_desc(b0 + j * kBTile);
-#pragma unroll
-              for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                umma_bf16_2sm(tmem_d, ad + 2u * k, bd + 2u * k, kIdescBf16M256N128,
-                              (first && k == 0) ? 0u : 1u);
-                if (k == 0) first = false;
-              }
-            }
-          }
-          umma_commit_2sm(empty_bar(stage));  // frees the slot in both CTAs
-          umma_commit_2sm(tfull_bar(acc));    // chunk accumulator ready in both CTAs
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    // ============ chunk accumulation + epilogue (each CTA: its 128 rows) ============
-    const int q = warp & 3;
-    const int row_in_tile = q * 32 + lane;
-    int chunk = 0;
-    for (int w = cluster_id; w < total_work; w += num_clusters) {
-      TcWork wk;
-      if (!tc_get_work_2cta(P, progs, s, w, (int)cta_rank, wk)) continue;
-      float sum[TC_BN];
-#pragma unroll
-      for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
-      for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
-        const int acc = chunk & 1;
-        const uint32_t acc_phase = (chunk >> 1) & 1;
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN;
-#pragma unroll
-        for (int c = 0; c < TC_BN / 32; ++c) {
-          if (P.dbg & 4) break;
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (leader) mbar_arrive(tempty_bar(acc));
-          else mbar_arrive_remote(tempty_bar(acc), 0);
-        }
-      }
-      if (wk.tm >= wk.tn)  // the (2 tm2, 2 tm2 + 1) tile is upper-triangular: its mirror
-        tc_epilogue_tile(P, wk, wk.tm, row_in_tile, lane, stage_base + q * TC_STAGE_BYTES_PER_WARP,
-                       sum);  // owner writes it
-    }
-  }
-  tcgen05_fence_before();
-  cluster_sync_all();  // no CTA may exit while its peer can still signal it
-  if (warp == 2) tmem_dealloc_2sm(tmem_base, TC_TMEM_COLS);
-}
-
 // ---------------------------------------------------------------------------
 // CTA-pair kernel, 256 x 256 output tile per cluster (cta_group::2, M = 256, N = 256).
 // This is the configuration that un-saturates shared memory: a 1-CTA M=128/N=128 MMA
@@ -1288,13 +813,12 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcParams& P, const TcWork
   const int row0 = tm * TC_BM + q * 32;
   const bool diag_tile = tm == tn;
   const float alpha = -1.0f / (float)wk.p, oma = 1.0f - alpha;
-  const bool mirror_on = !(P.dbg & 1);
+  const bool mirror_on = true;
   uint32_t emax = 0;
   const EpiAddr ea = make_epi_addr(stage, stage + TC_STAGE_BYTES_PER_WARP, lane);
   auto write_group = [&](int buf, float (&x)[32], int col0, bool diag_sub) {
-    if (P.dbg & 2) return;
-    store_block_3planes_tma(P, stage, ea, lane, x, diag_sub, mirror_on, smaps, row0, col0, wk.b,
-                            buf);
+    store_block_3planes_tma(P, stage, ea, lane, x, diag_sub, mirror_on, smaps, row0, col0,
+                            buf * P.batch + wk.b);
   };
 #pragma unroll
   for (int c = 0; c < TC_BN / 32; ++c) {
@@ -1304,20 +828,25 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcParams& P, const TcWork
     float g[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) g[i] = sum[c * 32 + i];
-    if (wk.st.emit_mi) {
-      float mi[32];
+#pragma unroll 1
+    for (int o = wk.st.emit_mi ? 0 : 1; o < 2; ++o) {  // o = 0: M_i' (DS:844), o = 1: OUT
+      float x[32];
+      if (o == 0) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const bool dg = (col0 + i == row) && (row < wk.pad);
-        if (!diag_sub || col0 + i <= row) {
-          const uint32_t ab = absbits(g[i] - (dg ? 1.f : 0.f));
-          emax = ab > emax ? ab : emax;
+        for (int i = 0; i < 32; ++i) {
+          const bool dg = (col0 + i == row) && (row < wk.pad);
+          if (!diag_sub || col0 + i <= row) {
+            const uint32_t ab = absbits(g[i] - (dg ? 1.f : 0.f));  // DS:847
+            emax = ab > emax ? ab : emax;
+          }
+          x[i] = mi_from_m(g[i], dg, alpha, oma);
         }
-        mi[i] = mi_from_m(g[i], dg, alpha, oma);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = g[i];
       }
-      write_group(physical_buf(LB_MIN, wk.cur), mi, col0, diag_sub);
+      write_group(physical_buf(o == 0 ? (int)LB_MIN : (int)wk.st.dst, wk.cur), x, col0, diag_sub);
     }
-    write_group(physical_buf(wk.st.dst, wk.cur), g, col0, diag_sub);
   }
   if (wk.st.emit_mi) {
     emax = warp_max_u32(emax);
@@ -1383,7 +912,7 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
         int tm2, tn2;
         if (!tc_get_work_pair256(P, progs, s, w, wk, tm2, tn2)) continue;
         const int pa = physical_buf(wk.st.a, wk.cur), pb = physical_buf(wk.st.b, wk.cur);
-        const int arow = tm2 * 256 + (int)cta_rank * 128, brow = tn2 * 256 + (int)cta_rank * 128;
+        const int atile = 2 * tm2 + (int)cta_rank, btile = 2 * tn2 + (int)cta_rank;
         for (int kb = 0; kb < wk.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t dst = smem_base + stage * kStageBytes;
@@ -1392,10 +921,10 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
           const CUtensorMap* maps[3] = {&tmap0, &tmap1, &tmap2};
 #pragma unroll
           for (int pl = 0; pl < kLP; ++pl) {
-            tma_load_4d_2sm(dst + pl * TC_TILE_BYTES, maps[pl], full_bar(stage), kb * TC_BK, arow,
-                            wk.b, pa);
-            tma_load_4d_2sm(dst + (kLP + pl) * TC_TILE_BYTES, maps[pl], full_bar(stage),
-                            kb * TC_BK, brow, wk.b, pb);
+            tma_load_tile_2sm(dst + pl * TC_TILE_BYTES, maps[pl], full_bar(stage), kb, atile,
+                              pa * P.batch + wk.b);
+            tma_load_tile_2sm(dst + (kLP + pl) * TC_TILE_BYTES, maps[pl], full_bar(stage), kb,
+                              btile, pb * P.batch + wk.b);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -1493,8 +1022,13 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
 struct PlaneStore {
   uint16_t* plane[3];
   size_t buf_stride, mat_elems;
+  // blocked layout: 128 x 64 tiles, each contiguous
+  __device__ __forceinline__ size_t elem(int phys, int b, int i, int j, int n) const {
+    return (size_t)phys * buf_stride + (size_t)b * mat_elems +
+           ((size_t)(i >> 7) * (n >> 6) + (j >> 6)) * 8192 + (size_t)(i & 127) * 64 + (j & 63);
+  }
   __device__ __forceinline__ void store(int phys, int b, int i, int j, int n, float v) const {
-    const size_t off = (size_t)phys * buf_stride + (size_t)b * mat_elems + (size_t)i * n + j;
+    const size_t off = elem(phys, b, i, j, n);
     const __nv_bfloat16 a0 = __float2bfloat16_rn(v);
     const float r1 = v - __bfloat162float(a0);
     const __nv_bfloat16 a1 = __float2bfloat16_rn(r1);
@@ -1504,7 +1038,7 @@ struct PlaneStore {
     plane[2][off] = __bfloat16_as_ushort(__float2bfloat16_rn(r2));
   }
   __device__ __forceinline__ float load(int phys, int b, int i, int j, int n) const {
-    const size_t off = (size_t)phys * buf_stride + (size_t)b * mat_elems + (size_t)i * n + j;
+    const size_t off = elem(phys, b, i, j, n);
     const float x0 = __bfloat162float(__ushort_as_bfloat16(plane[0][off]));
     const float x1 = __bfloat162float(__ushort_as_bfloat16(plane[1][off]));
     const float x2 = __bfloat162float(__ushort_as_bfloat16(plane[2][off]));
@@ -1545,12 +1079,9 @@ size_t tc_engine_bytes(int batch, int n) {
 }
 
 struct TcHostState {
-  CUtensorMap maps[3];
-  CUtensorMap maps_b64[3];  // box {64 k, 64 rows}: half B tiles of the CTA-pair kernel
-  CUtensorMap maps_st[3];   // box {32, 32}, SWIZZLE_64B: epilogue bulk stores
-  bool use_2cta;
-  bool use_pair256;  // cta_group::2, 256 x 256 cluster tiles (default when n % 256 == 0)
-  bool use_ws;  // warp-specialised kernel with a dedicated epilogue warpgroup
+  CUtensorMap maps[3];     // operand loads: one 128 x 64 storage tile (16 KiB, contiguous)
+  CUtensorMap maps_st[3];  // epilogue bulk stores: box {32, 32}, SWIZZLE_64B
+  bool use_pair256;        // cta_group::2, 256 x 256 cluster tiles (default when n % 256 == 0)
   TcParams prm;
   Program* progs_dev;
 };
@@ -1573,22 +1104,21 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
     uint16_t* plane = base + (size_t)pl * kNumBufs * buf_stride;
     hs->prm.plane[pl] = plane;
     for (int k = 0; k < kNumBufs; ++k) e->planes[k][pl] = plane + (size_t)k * buf_stride;
-    cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)batch, (cuuint64_t)kNumBufs};
-    cuuint64_t strides[3] = {(cuuint64_t)n * 2, (cuuint64_t)n * n * 2,
-                             (cuuint64_t)buf_stride * 2};
-    cuuint32_t box[4] = {TC_BK, TC_BM, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&hs->maps[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, plane, dims, strides, box,
+    // Blocked storage: a matrix is a grid of 128 x 64 tiles, each contiguous (16 KiB),
+    // so one TMA box = one DRAM-contiguous chunk (no 2 KiB power-of-two row strides).
+    // 5-D view: [col in tile (64), row in tile (128), tile col (n/64), tile row (n/128), matrix]
+    cuuint64_t dims[5] = {64, 128, (cuuint64_t)(n / 64), (cuuint64_t)(n / 128),
+                          (cuuint64_t)batch * kNumBufs};
+    cuuint64_t strides[4] = {64 * 2, 8192 * 2, (cuuint64_t)8192 * (n / 64) * 2,
+                             (cuuint64_t)n * n * 2};
+    cuuint32_t box[5] = {64, 128, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&hs->maps[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, plane, dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    cuuint32_t box_b[4] = {TC_BK, 64, 1, 1};
+    cuuint32_t box_s[5] = {32, 32, 1, 1, 1};
     if (r == CUDA_SUCCESS)
-      r = enc(&hs->maps_b64[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, plane, dims, strides, box_b,
-              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    cuuint32_t box_s[4] = {32, 32, 1, 1};
-    if (r == CUDA_SUCCESS)
-      r = enc(&hs->maps_st[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, plane, dims, strides, box_s,
+      r = enc(&hs->maps_st[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, plane, dims, strides, box_s,
               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1599,17 +1129,12 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
     }
   }
   {
-    const char* env = getenv("PC_TC_2CTA");
-    hs->use_2cta = (n % 256 == 0) && (env && env[0] == '1');  // opt-in: no gain measured yet
     const char* p256 = getenv("PC_TC_PAIR256");
     hs->use_pair256 = (n % 256 == 0) && !(p256 && p256[0] == '0');
-    const char* ws = getenv("PC_TC_WS");
-    hs->use_ws = !(ws && ws[0] == '0');
   }
   hs->prm.buf_stride = buf_stride;
   hs->prm.mat_stride = (size_t)n * n;
   hs->prm.n = n; hs->prm.batch = batch; hs->prm.tiles = n / TC_BM;
-  hs->prm.dbg = getenv("PC_TC_DEBUG") ? atoi(getenv("PC_TC_DEBUG")) : 0;
   {
     static int hints_set = -1;
     const char* h = getenv("PC_TC_HINTS");
@@ -1633,21 +1158,6 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
     PC_CUDA_CHECK(cudaMemcpy(g_progs_dev[dev], hp, sizeof(hp), cudaMemcpyHostToDevice));
   }
   hs->progs_dev = g_progs_dev[dev < 64 ? dev : 0];
-  return PC_OK;
-}
-
-template <int kLP, int kStages, int kChunkKB>
-static int launch_phase(TcHostState* hs, int s, int total_work, int grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 256 +
-                          4 * TC_STAGE_BYTES_PER_WARP;
-  static bool configured = false;
-  if (!configured) {
-    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel<kLP, kStages, kChunkKB>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  tc_phase_kernel<kLP, kStages, kChunkKB><<<grid, TC_THREADS, smem, stream>>>(
-      hs->maps[0], hs->maps[1], hs->maps[2], hs->prm, hs->progs_dev, s, total_work);
   return PC_OK;
 }
 
@@ -1687,26 +1197,6 @@ static int launch_phase_pair256(TcHostState* hs, int s, int batch, int sms, cuda
   return PC_OK;
 }
 
-template <int kLP, int kStages>
-static int launch_phase_2cta(TcHostState* hs, int s, int batch, int sms, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)kStages * kLP * (TC_TILE_BYTES + TC_TILE_BYTES / 2) + 1024 + 256 +
-                          4 * TC_STAGE_BYTES_PER_WARP;
-  static bool configured = false;
-  if (!configured) {
-    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_2cta<kLP, kStages>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  const int t2 = hs->prm.tiles / 2;
-  const int total_work = batch * 2 * t2 * (t2 + 1);
-  int clusters = sms / 2;
-  if (total_work < clusters) clusters = total_work;
-  tc_phase_kernel_2cta<kLP, kStages><<<2 * clusters, TC_THREADS, smem, stream>>>(
-      hs->maps[0], hs->maps[1], hs->maps[2], hs->maps_b64[0], hs->maps_b64[1], hs->maps_b64[2],
-      hs->prm, hs->progs_dev, s, total_work);
-  return PC_OK;
-}
-
 int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* errbits,
                         RootParams prm, float* roots, int max_steps, cudaStream_t stream) {
   auto* hs = static_cast<TcHostState*>(e->host_state);
@@ -1735,15 +1225,9 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
     if (hs->use_pair256)
       rc = e->passes == 6 ? launch_phase_pair256<3, 2>(hs, s, e->batch, sms, stream)
                           : launch_phase_pair256<2, 3>(hs, s, e->batch, sms, stream);
-    else if (hs->use_2cta)
-      rc = e->passes == 6 ? launch_phase_2cta<3, 3>(hs, s, e->batch, sms, stream)
-                          : launch_phase_2cta<2, 4>(hs, s, e->batch, sms, stream);
-    else if (hs->use_ws)
+    else
       rc = e->passes == 6 ? launch_phase_ws<3, 2>(hs, s, total_work, grid, stream)
                           : launch_phase_ws<2, 3>(hs, s, total_work, grid, stream);
-    else
-      rc = e->passes == 6 ? launch_phase<3, 2, 1>(hs, s, total_work, grid, stream)
-                          : launch_phase<2, 3, 1>(hs, s, total_work, grid, stream);
     if (rc != PC_OK) return rc;
   }
   if (ev0) { cudaEventRecord(ev1, stream); gemm_timing_record(ev0, ev1); }
@@ -1847,15 +1331,9 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
   if (hs->use_pair256)
     rc = passes == 6 ? launch_phase_pair256<3, 2>(hs, 0, batch, sms, stream)
                      : launch_phase_pair256<2, 3>(hs, 0, batch, sms, stream);
-  else if (hs->use_2cta)
-    rc = passes == 6 ? launch_phase_2cta<3, 3>(hs, 0, batch, sms, stream)
-                     : launch_phase_2cta<2, 4>(hs, 0, batch, sms, stream);
-  else if (hs->use_ws)
+  else
     rc = passes == 6 ? launch_phase_ws<3, 2>(hs, 0, total_work, grid, stream)
                      : launch_phase_ws<2, 3>(hs, 0, total_work, grid, stream);
-  else
-    rc = passes == 6 ? launch_phase<3, 2, 1>(hs, 0, total_work, grid, stream)
-                     : launch_phase<2, 3, 1>(hs, 0, total_work, grid, stream);
   if (rc == PC_OK) tc_debug_read_kernel<<<g, 256, 0, stream>>>(ps, LB_Q0, n, c);
   cudaFreeAsync(dprog, stream);
   delete hs;
