@@ -496,7 +496,8 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
       f32.base[k] = reinterpret_cast<float*>(ws.engine_mem) + (size_t)k * batch * n * n;
     f32.mat_elems = (size_t)n * n;
   } else {
-    rc = tc_engine_init(&tc, ws.engine_mem, batch, n, engine == PC_ENGINE_TC_BF16X6 ? 6 : 3);
+    rc = tc_engine_init(&tc, ws.engine_mem, batch, n, engine == PC_ENGINE_TC_BF16X6 ? 6 : 3,
+                        stream);
     if (rc != PC_OK) return rc;
   }
 

@@ -14,7 +14,7 @@ struct TcEngine {
 
 bool tc_engine_available();
 size_t tc_engine_bytes(int batch, int n);
-int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes);
+int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, cudaStream_t stream);
 int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* errbits,
                         RootParams prm, float* roots, int max_steps, cudaStream_t stream);
 int tc_engine_final(TcEngine* e, const RootCtl* ctl, float* roots, float* metrics,

@@ -33,8 +33,6 @@ namespace pc {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_UMMA_K = 16;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;  // one plane tile: 16 KiB
-constexpr int TC_THREADS = 256;
-constexpr int TC_TMEM_COLS = 256;
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -64,6 +62,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar),
       "r"(parity)
       : "memory");
+}
+// true on exactly one lane of a converged warp; unlike `lane == 0` the compiler knows the
+// branch holds a single thread, so TMA / MMA operands go to uniform registers directly
+// instead of through a per-lane readback loop (113 instructions per TMA load before)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -181,25 +193,53 @@ struct TcParams {
   const RootCtl* ctl;
   uint32_t* errbits;
   int n, batch, tiles;  // tiles per dimension (n / 128)
+  // Group scheduling: the `sync_group` consecutive work items that read the same operand
+  // matrices start their tiles together (a counter per group, see group_sync), so every
+  // operand block is pulled from HBM once and shared through L2.  0 = no synchronisation.
+  uint32_t* sync_ctr;       // this launch's counters [2 * batch] (zero on entry)
+  uint32_t* sync_ctr_next;  // the next launch's counters: zeroed by this launch
+  int sync_group;           // items per group: per_mat, or per (matrix, op)
+  int sync_arrivals;        // arrivals that release a group (= sync_group x CTAs per item)
 };
 
 struct TcWork {
-  int b, tm, tn, kblocks, cur, p, pad;
+  int b, tm, tn, kblocks, cur, p, pad, op;
   Step st;
 };
+
+// Work items of launch `s`: step 0 runs two products per matrix (chain step 0 and the
+// H update), later steps one.
+__device__ __forceinline__ int tc_ops_per_matrix(int s) { return s == 0 ? 2 : 1; }
+
+// Start-of-tile rendezvous of the producers that work on one group (relaxed: it orders
+// nothing, it only keeps the CTAs that share operands within a tile of each other so the
+// shared blocks are still in L2).  Bounded spin: a missing partner costs time, never a hang.
+__device__ __forceinline__ void group_sync(uint32_t* ctr, uint32_t expected) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+  uint32_t v;
+  int spins = 0;
+  do {
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+  } while (v < expected && ++spins < (1 << 14));
+}
+__device__ __forceinline__ void tc_group_sync(const TcParams& P, const TcWork& wk, int ntri, int s) {
+  if (P.sync_group <= 1) return;
+  const int g = P.sync_group == ntri * tc_ops_per_matrix(s) ? wk.b : wk.b * 2 + wk.op;
+  group_sync(P.sync_ctr + g, (uint32_t)P.sync_arrivals);
+}
 
 __device__ __forceinline__ bool tc_get_work(const TcParams& P, const Program* progs, int s,
                                             int w, TcWork& out) {
   const int ntri = P.tiles * (P.tiles + 1) / 2;  // lower-triangular tiles only
-  const int per_mat = 2 * ntri;
+  const int per_mat = tc_ops_per_matrix(s) * ntri;
   const int b = w / per_mat;
   int r = w - b * per_mat;
   const int op = r / ntri;
   r -= op * ntri;
   const RootCtl& c = P.ctl[b];
   if (!c.active) return false;
+  out.op = op;
   if (op == 1) {
-    if (s != 0) return false;
     out.st = Step{LB_HN, LB_H, LB_MI, 0};
   } else {
     const Program& pr = progs[c.p];
@@ -501,6 +541,8 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 3 && blockIdx.x == 0 && P.sync_ctr_next)
+    for (int i = lane; i < 2 * P.batch; i += 32) P.sync_ctr_next[i] = 0u;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -508,14 +550,17 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
+#pragma unroll 1
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         TcWork wk;
         if (!tc_get_work(P, progs, s, w, wk)) continue;
+        tc_group_sync(P, wk, P.tiles * (P.tiles + 1) / 2, s);
         const int pa = physical_buf(wk.st.a, wk.cur), pb = physical_buf(wk.st.b, wk.cur);
+#pragma unroll 1
         for (int kb = 0; kb < wk.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t dst = smem_base + stage * kStageBytes;
@@ -531,14 +576,16 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
       // ===================== MMA issuer =====================
       int stage = 0;
       uint32_t phase = 0;
       int chunk = 0;
+#pragma unroll 1
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         TcWork wk;
         if (!tc_get_work(P, progs, s, w, wk)) continue;
+#pragma unroll 1
         for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
           const int acc = chunk & 1;
           mbar_wait(tempty_bar(acc), ((chunk >> 1) & 1) ^ 1);
@@ -575,12 +622,14 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
     const int q = warp & 3;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     int chunk = 0, tile = 0;
+#pragma unroll 1
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       TcWork wk;
       if (!tc_get_work(P, progs, s, w, wk)) continue;
       float sum[TC_BN];
 #pragma unroll
       for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
+#pragma unroll 1
       for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
         const int acc = chunk & 1;
         mbar_wait(tfull_bar(acc), (chunk >> 1) & 1);
@@ -624,6 +673,7 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     int tile = 0;
+#pragma unroll 1
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       TcWork wk;
       if (!tc_get_work(P, progs, s, w, wk)) continue;
@@ -713,53 +763,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
       : "memory");
 }
 
-constexpr uint32_t kIdescBf16M256N128 =
-    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-
-struct TcWork2 {
-  TcWork w;     // tm = 128-row tile index of THIS CTA
-  int valid;
-};
-
-// pair-tile index t -> (tm2, tn): all tn <= 2*tm2 + 1, i.e. t = tm2*(tm2+1) + tn
-__device__ __forceinline__ void pair_decode(int t, int& tm2, int& tn) {
-  int r = (int)((sqrtf(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-  while (r * (r + 1) > t) --r;
-  while ((r + 1) * (r + 2) <= t) ++r;
-  tm2 = r;
-  tn = t - r * (r + 1);
-}
-
-__device__ __forceinline__ bool tc_get_work_2cta(const TcParams& P, const Program* progs, int s,
-                                                 int w, int cta_rank, TcWork& out) {
-  const int t2 = P.tiles / 2;
-  const int npair = t2 * (t2 + 1);
-  const int per_mat = 2 * npair;
-  const int b = w / per_mat;
-  int r = w - b * per_mat;
-  const int op = r / npair;
-  r -= op * npair;
-  const RootCtl& c = P.ctl[b];
-  if (!c.active) return false;
-  if (op == 1) {
-    if (s != 0) return false;
-    out.st = Step{LB_HN, LB_H, LB_MI, 0};
-  } else {
-    const Program& pr = progs[c.p];
-    if (s >= pr.nsteps) return false;
-    out.st = pr.steps[s];
-  }
-  int tm2;
-  pair_decode(r, tm2, out.tn);
-  out.b = b;
-  out.tm = 2 * tm2 + cta_rank;
-  out.cur = c.cur;
-  out.p = c.p;
-  out.pad = c.pad;
-  out.kblocks = (c.pad + TC_BK - 1) / TC_BK;
-  return true;
-}
-
 // ---------------------------------------------------------------------------
 // CTA-pair kernel, 256 x 256 output tile per cluster (cta_group::2, M = 256, N = 256).
 // This is the configuration that un-saturates shared memory: a 1-CTA M=128/N=128 MMA
@@ -779,15 +782,15 @@ __device__ __forceinline__ bool tc_get_work_pair256(const TcParams& P, const Pro
                                                     int w, TcWork& out, int& tm2, int& tn2) {
   const int t2 = P.tiles / 2;
   const int ntri = t2 * (t2 + 1) / 2;
-  const int per_mat = 2 * ntri;
+  const int per_mat = tc_ops_per_matrix(s) * ntri;
   const int b = w / per_mat;
   int r = w - b * per_mat;
   const int op = r / ntri;
   r -= op * ntri;
   const RootCtl& c = P.ctl[b];
   if (!c.active) return false;
+  out.op = op;
   if (op == 1) {
-    if (s != 0) return false;
     out.st = Step{LB_HN, LB_H, LB_MI, 0};
   } else {
     const Program& pr = progs[c.p];
@@ -896,6 +899,8 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
   }
   cluster_sync_all();
   if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
+  if (warp == 3 && blockIdx.x == 0 && P.sync_ctr_next)
+    for (int i = lane; i < 2 * P.batch; i += 32) P.sync_ctr_next[i] = 0u;
   tcgen05_fence_before();
   cluster_sync_all();
   tcgen05_fence_after();
@@ -903,16 +908,19 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
       // ===================== TMA producer (both CTAs) =====================
       int stage = 0;
       uint32_t phase = 0;
+#pragma unroll 1
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         TcWork wk;
         int tm2, tn2;
         if (!tc_get_work_pair256(P, progs, s, w, wk, tm2, tn2)) continue;
+        tc_group_sync(P, wk, (P.tiles / 2) * (P.tiles / 2 + 1) / 2, s);
         const int pa = physical_buf(wk.st.a, wk.cur), pb = physical_buf(wk.st.b, wk.cur);
         const int atile = 2 * tm2 + (int)cta_rank, btile = 2 * tn2 + (int)cta_rank;
+#pragma unroll 1
         for (int kb = 0; kb < wk.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t dst = smem_base + stage * kStageBytes;
@@ -929,15 +937,17 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1 && lane == 0 && leader) {
+    } else if (warp == 1 && leader && elect_one()) {
       // ===================== MMA issuer (leader CTA) =====================
       int stage = 0;
       uint32_t phase = 0;
       int chunk = 0;
+#pragma unroll 1
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         TcWork wk;
         int tm2, tn2;
         if (!tc_get_work_pair256(P, progs, s, w, wk, tm2, tn2)) continue;
+#pragma unroll 1
         for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
           const int acc = chunk & 1;
           mbar_wait(tempty_bar(acc), ((chunk >> 1) & 1) ^ 1);
@@ -977,6 +987,7 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const CUtensorMap* const smaps[3] = {&smap0, &smap1, &smap2};
     int chunk = 0;
+#pragma unroll 1
     for (int w = cluster_id; w < total_work; w += num_clusters) {
       TcWork wk;
       int tm2, tn2;
@@ -984,6 +995,7 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
       float sum[TC_BN];
 #pragma unroll
       for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
+#pragma unroll 1
       for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
         const int acc = chunk & 1;
         mbar_wait(tfull_bar(acc), (chunk >> 1) & 1);
@@ -1074,8 +1086,11 @@ bool tc_engine_available() {
   return major == 10;
 }
 
+static size_t tc_plane_bytes(int batch, int n) {
+  return (size_t)3 * kNumBufs * batch * n * n * sizeof(uint16_t);
+}
 size_t tc_engine_bytes(int batch, int n) {
-  return (size_t)3 * kNumBufs * batch * n * n * sizeof(uint16_t) + 1024;
+  return tc_plane_bytes(batch, n) + 1024 + 4 * (size_t)batch * sizeof(uint32_t) + 256;
 }
 
 struct TcHostState {
@@ -1084,11 +1099,43 @@ struct TcHostState {
   bool use_pair256;        // cta_group::2, 256 x 256 cluster tiles (default when n % 256 == 0)
   TcParams prm;
   Program* progs_dev;
+  uint32_t* sync_mem;  // 2 x [2 * batch] group counters, used alternately by successive launches
+  unsigned launch_seq;
+  bool group_sync;     // PC_TC_SYNC=1 enables the rendezvous (off by default)
+  int sms;
 };
+
+// Grid and synchronisation group of one launch.  `units` = CTAs (ws kernel) or clusters
+// (pair kernel) the device can hold, `ntri` = work items per (matrix, product), `cpi` =
+// producer threads per item.  A group must fit in one round (group <= units) and rounds
+// must not split groups (grid % group == 0), otherwise a CTA would wait on itself.
+static void plan_launch(TcHostState* hs, int s, int ntri, int units, int cpi, int* grid_units,
+                        int* total_work) {
+  const int per_mat = (s == 0 ? 2 : 1) * ntri;
+  *total_work = hs->prm.batch * per_mat;
+  int group = 0, best = 0;
+  if (hs->group_sync) {
+    for (int cand : {per_mat, ntri}) {
+      if (cand <= 1 || cand > units) continue;
+      const int g = (units / cand) * cand;
+      if (g > best) { best = g; group = cand; }
+    }
+  }
+  uint32_t* cur = hs->sync_mem + (size_t)(hs->launch_seq & 1) * 2 * hs->prm.batch;
+  uint32_t* nxt = hs->sync_mem + (size_t)((hs->launch_seq + 1) & 1) * 2 * hs->prm.batch;
+  ++hs->launch_seq;
+  hs->prm.sync_ctr = cur;
+  hs->prm.sync_ctr_next = nxt;
+  hs->prm.sync_group = group;
+  hs->prm.sync_arrivals = group * cpi;
+  int g = group ? best : units;
+  if (!group && *total_work < g) g = *total_work;
+  *grid_units = g;
+}
 
 static Program* g_progs_dev[64] = {nullptr};
 
-int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
+int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, cudaStream_t stream) {
   PC_REQUIRE(n % TC_BM == 0, "tcgen05 engine needs n %% 128 == 0");
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
@@ -1132,6 +1179,18 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
     const char* p256 = getenv("PC_TC_PAIR256");
     hs->use_pair256 = (n % 256 == 0) && !(p256 && p256[0] == '0');
   }
+  {
+    const char* gs = getenv("PC_TC_SYNC");
+    hs->group_sync = gs && gs[0] == '1';  // measured: DRAM reads -60 %, but slower
+    hs->sync_mem = reinterpret_cast<uint32_t*>(
+        align_up((size_t)(reinterpret_cast<char*>(base) + tc_plane_bytes(batch, n)), 256));
+    hs->launch_seq = 0;
+    PC_CUDA_CHECK(cudaMemsetAsync(hs->sync_mem, 0, 4 * (size_t)batch * sizeof(uint32_t), stream));
+    int dev = 0;
+    hs->sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&hs->sms, cudaDevAttrMultiProcessorCount, dev);
+  }
   hs->prm.buf_stride = buf_stride;
   hs->prm.mat_stride = (size_t)n * n;
   hs->prm.n = n; hs->prm.batch = batch; hs->prm.tiles = n / TC_BM;
@@ -1162,7 +1221,7 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes) {
 }
 
 template <int kLP, int kStages>
-static int launch_phase_ws(TcHostState* hs, int s, int total_work, int grid, cudaStream_t stream) {
+static int launch_phase_ws(TcHostState* hs, int s, cudaStream_t stream) {
   constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 1024 +
                           16 * TC_STAGE_BYTES_PER_WARP;
   static bool configured = false;
@@ -1171,6 +1230,8 @@ static int launch_phase_ws(TcHostState* hs, int s, int total_work, int grid, cud
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  int grid, total_work;
+  plan_launch(hs, s, hs->prm.tiles * (hs->prm.tiles + 1) / 2, hs->sms, 1, &grid, &total_work);
   tc_phase_kernel_ws<kLP, kStages><<<grid, TC_WS_THREADS, smem, stream>>>(
       hs->maps[0], hs->maps[1], hs->maps[2], hs->maps_st[0], hs->maps_st[1], hs->maps_st[2],
       hs->prm, hs->progs_dev, s, total_work);
@@ -1178,7 +1239,7 @@ static int launch_phase_ws(TcHostState* hs, int s, int total_work, int grid, cud
 }
 
 template <int kLP, int kStages>
-static int launch_phase_pair256(TcHostState* hs, int s, int batch, int sms, cudaStream_t stream) {
+static int launch_phase_pair256(TcHostState* hs, int s, cudaStream_t stream) {
   constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 1024 +
                           16 * TC_STAGE_BYTES_PER_WARP;
   static bool configured = false;
@@ -1188,9 +1249,8 @@ static int launch_phase_pair256(TcHostState* hs, int s, int batch, int sms, cuda
     configured = true;
   }
   const int t2 = hs->prm.tiles / 2;
-  const int total_work = batch * t2 * (t2 + 1);  // 2 ops x lower-triangular 256-tiles
-  int clusters = sms / 2;
-  if (total_work < clusters) clusters = total_work;
+  int clusters, total_work;
+  plan_launch(hs, s, t2 * (t2 + 1) / 2, hs->sms / 2, 2, &clusters, &total_work);
   tc_phase_kernel_pair256<kLP, kStages><<<2 * clusters, TC_P256_THREADS, smem, stream>>>(
       hs->maps[0], hs->maps[1], hs->maps[2], hs->maps_st[0], hs->maps_st[1], hs->maps_st[2],
       hs->prm, hs->progs_dev, s, total_work);
@@ -1209,12 +1269,6 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
   root_init_kernel<PlaneStore><<<e->batch, 1024, 0, stream>>>(xs, ctl, ps, e->batch, e->n, prm,
                                                              roots);
   count_launch(1);
-  int sms = 148;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int total_work = e->batch * hs->prm.tiles * (hs->prm.tiles + 1);  // 2 ops x lower tiles
-  const int grid = total_work < sms ? total_work : sms;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (gemm_timing_enabled()) {
     cudaEventCreate(&ev0); cudaEventCreate(&ev1);
@@ -1223,11 +1277,11 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
   for (int s = 0; s < max_steps; ++s) {
     int rc;
     if (hs->use_pair256)
-      rc = e->passes == 6 ? launch_phase_pair256<3, 2>(hs, s, e->batch, sms, stream)
-                          : launch_phase_pair256<2, 3>(hs, s, e->batch, sms, stream);
+      rc = e->passes == 6 ? launch_phase_pair256<3, 2>(hs, s, stream)
+                          : launch_phase_pair256<2, 3>(hs, s, stream);
     else
-      rc = e->passes == 6 ? launch_phase_ws<3, 2>(hs, s, total_work, grid, stream)
-                          : launch_phase_ws<2, 3>(hs, s, total_work, grid, stream);
+      rc = e->passes == 6 ? launch_phase_ws<3, 2>(hs, s, stream)
+                          : launch_phase_ws<2, 3>(hs, s, stream);
     if (rc != PC_OK) return rc;
   }
   if (ev0) { cudaEventRecord(ev1, stream); gemm_timing_record(ev0, ev1); }
@@ -1301,7 +1355,7 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
   RootCtl* ctl = reinterpret_cast<RootCtl*>(w); w += align_up(sizeof(RootCtl) * batch, 256);
   uint32_t* errbits = reinterpret_cast<uint32_t*>(w); w += align_up(4 * batch, 256);
   TcEngine e;
-  int rc = tc_engine_init(&e, w, batch, n, passes);
+  int rc = tc_engine_init(&e, w, batch, n, passes, stream);
   if (rc != PC_OK) return rc;
   auto* hs = static_cast<TcHostState*>(e.host_state);
   // private one-step program table: p = 1 -> Q0 = M * M_i^T
@@ -1323,17 +1377,12 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
   tc_debug_ctl_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(ctl, batch, n, errbits);
   dim3 g(64, batch);
   tc_debug_fill_kernel<<<g, 256, 0, stream>>>(a, b, ps, n);
-  const int total_work = batch * hs->prm.tiles * (hs->prm.tiles + 1);
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = total_work < sms ? total_work : sms;
   if (hs->use_pair256)
-    rc = passes == 6 ? launch_phase_pair256<3, 2>(hs, 0, batch, sms, stream)
-                     : launch_phase_pair256<2, 3>(hs, 0, batch, sms, stream);
+    rc = passes == 6 ? launch_phase_pair256<3, 2>(hs, 0, stream)
+                     : launch_phase_pair256<2, 3>(hs, 0, stream);
   else
-    rc = passes == 6 ? launch_phase_ws<3, 2>(hs, 0, total_work, grid, stream)
-                     : launch_phase_ws<2, 3>(hs, 0, total_work, grid, stream);
+    rc = passes == 6 ? launch_phase_ws<3, 2>(hs, 0, stream)
+                     : launch_phase_ws<2, 3>(hs, 0, stream);
   if (rc == PC_OK) tc_debug_read_kernel<<<g, 256, 0, stream>>>(ps, LB_Q0, n, c);
   cudaFreeAsync(dprog, stream);
   delete hs;
