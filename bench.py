@@ -42,7 +42,7 @@ def parse_args():
   ap.add_argument("--batch", type=int, default=74,
                   help="statistics per GPU per step (74 = one per SM pair of a B200)")
   ap.add_argument("--p", type=int, default=4)
-  ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc6", "tc3"])
+  ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc6", "tc3", "fp16x3"])
   ap.add_argument("--cpu-sample", type=int, default=2,
                   help="matrices in the bounded CPU-baseline sample")
   ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -220,7 +220,8 @@ def run_ours(a):
     dist.init_process_group("nccl", device_id=dev)
   lib = _lib.load()
   engine = {"auto": _lib.PC_ENGINE_AUTO, "simt": _lib.PC_ENGINE_SIMT_FP32,
-            "tc6": _lib.PC_ENGINE_TC_BF16X6, "tc3": _lib.PC_ENGINE_TC_BF16X3}[a.engine]
+            "tc6": _lib.PC_ENGINE_TC_BF16X6, "tc3": _lib.PC_ENGINE_TC_BF16X3,
+            "fp16x3": _lib.PC_ENGINE_TC_FP16X3}[a.engine]
 
   n, B = a.n, a.batch
   xs = make_statistics_torch(B, n, seed=1000 + rank, device=dev)
@@ -318,9 +319,9 @@ def run_ours(a):
   except (OSError, ValueError, KeyError):
     pass
   m_host = metrics.cpu().numpy()
-  resolved = {1: "simt_fp32", 2: "tcgen05_bf16x6", 3: "tcgen05_bf16x3"}[
+  resolved = {1: "simt_fp32", 2: "tcgen05_bf16x6", 3: "tcgen05_bf16x3", 4: "tcgen05_fp16x3"}[
       lib.pc_resolve_engine(n, engine)]
-  passes = {"simt_fp32": 1, "tcgen05_bf16x6": 6, "tcgen05_bf16x3": 3}[resolved]
+  passes = {"simt_fp32": 1, "tcgen05_bf16x6": 6, "tcgen05_bf16x3": 3, "tcgen05_fp16x3": 3}[resolved]
   roofline = {
       "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
       "frac": achieved / peak if peak else None, "traffic": traffic,

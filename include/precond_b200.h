@@ -52,6 +52,8 @@ extern "C" {
 #define PC_ENGINE_SIMT_FP32 1 /* CUDA-core fp32 FFMA tiles (any n)              */
 #define PC_ENGINE_TC_BF16X6 2 /* tcgen05, bf16 3-way split, 6 products (~fp32)  */
 #define PC_ENGINE_TC_BF16X3 3 /* tcgen05, bf16 2-way split, 3 products (~2^-16) */
+#define PC_ENGINE_TC_FP16X3 4 /* tcgen05, fp16 + 2^11-scaled fp16 residual, 3 products
+                                 (22-bit operands, like 3xTF32 at the f16 MMA rate)  */
 
 /* quantised storage of statistics / preconditioners, QU:49-113 */
 #define PC_QDTYPE_F32 0
@@ -123,7 +125,7 @@ int pc_inverse_pth_root_batched(const float* xs, const int32_t* ps,
                                 size_t workspace_bytes, void* stream);
 
 /* Test hook for the tcgen05 engine: C[b] = A[b] * B[b]^T (fp32 in/out, computed as
- * split-bf16 products, `passes` = 6 or 3), n % 128 == 0.  Workspace of at least
+ * split-bf16 products, `passes` = 6 or 3, or scaled-fp16 products, `passes` = -3), n % 128 == 0.  Workspace of at least
  * pc_inverse_pth_root_workspace_bytes(batch, n, PC_ENGINE_TC_BF16X6) bytes. */
 int pc_debug_tc_gemm(const float* a, const float* b, float* c, int batch, int n, int passes,
                      void* workspace, size_t workspace_bytes, void* stream);

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libprecond_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 PC_ENGINE_AUTO, PC_ENGINE_SIMT_FP32, PC_ENGINE_TC_BF16X6, PC_ENGINE_TC_BF16X3 = 0, 1, 2, 3
+PC_ENGINE_TC_FP16X3 = 4
 PC_QDTYPE_F32, PC_QDTYPE_INT16, PC_QDTYPE_INT8, PC_QDTYPE_BF16 = 0, 1, 2, 3
 PC_NUM_METRICS = 5
 

@@ -381,7 +381,7 @@ static size_t header_bytes(int batch, int n) {
 
 static int resolve_engine(int engine, int n) {
   if (engine == PC_ENGINE_AUTO) {
-    if (tc_engine_available() && n >= 256 && n % 128 == 0) return PC_ENGINE_TC_BF16X6;
+    if (tc_engine_available() && n >= 256 && n % 128 == 0) return PC_ENGINE_TC_FP16X3;
     return PC_ENGINE_SIMT_FP32;
   }
   return engine;
@@ -390,7 +390,7 @@ static int resolve_engine(int engine, int n) {
 size_t root_workspace_bytes(int batch, int n, int engine) {
   engine = resolve_engine(engine, n);
   size_t e = engine == PC_ENGINE_SIMT_FP32 ? engine_bytes_simt(batch, n)
-                                           : tc_engine_bytes(batch, n);
+                                           : tc_engine_bytes(batch, n, engine == PC_ENGINE_TC_FP16X3 ? 2 : 3);
   return header_bytes(batch, n) + align_up(e, 256) + 1024;
 }
 
@@ -441,7 +441,7 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
              size_t workspace_bytes, cudaStream_t stream) {
   const int engine = resolve_engine(opt->engine, n);
   PC_REQUIRE(engine == PC_ENGINE_SIMT_FP32 || engine == PC_ENGINE_TC_BF16X6 ||
-                 engine == PC_ENGINE_TC_BF16X3,
+                 engine == PC_ENGINE_TC_BF16X3 || engine == PC_ENGINE_TC_FP16X3,
              "unknown engine %d", opt->engine);
   if (engine != PC_ENGINE_SIMT_FP32) {
     PC_REQUIRE(n % 128 == 0 && n >= 128, "tcgen05 engine needs n %% 128 == 0 (n=%d)", n);
@@ -497,7 +497,7 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
     f32.mat_elems = (size_t)n * n;
   } else {
     rc = tc_engine_init(&tc, ws.engine_mem, batch, n, engine == PC_ENGINE_TC_BF16X6 ? 6 : 3,
-                        stream);
+                        engine == PC_ENGINE_TC_FP16X3 ? 1 : 0, stream);
     if (rc != PC_OK) return rc;
   }
 

@@ -65,6 +65,7 @@ struct RootCtl {
   float ratio;
   float max_ev;
   float ridge;    // ridge_epsilon * max(max_ev, 1e-25), DS:830
+  float hmul;     // stored H = H / hmul (1 unless the engine keeps H in a scaled format)
   // final metrics (DS:902-907)
   float m_err, m_iters, m_ratio, m_retries;
 };

@@ -70,6 +70,8 @@ root_init_kernel(const float* __restrict__ xs, RootCtl* ctl, Bufs bufs, int batc
   const float norm = sqrtf(block_sum(ss, scratch));
   const float z = (float)(1 + p) / (2.0f * norm);
   const float h0 = powf(z, (float)(1.0 / (double)p));  // DS:873
+  float hmul = 1.0f;
+  const float hdiag = bufs.h_init_scale(h0, powf(fmaxf(z * eps, 1e-37f), alpha), &hmul);
   // pass 2: M0 = z A_d, M_i0 = (1-alpha) I_m + alpha M0, H0 = z^(1/p) I_m,
   //         err0 = max|M0 - I_m|
   const float one_minus_alpha = 1.0f - alpha;
@@ -86,7 +88,7 @@ root_init_kernel(const float* __restrict__ xs, RootCtl* ctl, Bufs bufs, int batc
       const uint32_t ab = absbits(e0);
       emax = ab > emax ? ab : emax;
       mi = mi_from_m(m0, i == j, alpha, one_minus_alpha);
-      h = (i == j) ? h0 : 0.f;
+      h = (i == j) ? hdiag : 0.f;
     }
     bufs.store(0, b, i, j, n, m0);  // M[0]
     bufs.store(2, b, i, j, n, mi);  // M_i[0]
@@ -99,6 +101,7 @@ root_init_kernel(const float* __restrict__ xs, RootCtl* ctl, Bufs bufs, int batc
     c.cur = 0;
     c.err = __uint_as_float(emax);  // DS:872
     c.ratio = 1.0f;
+    c.hmul = hmul;
     root_after_error_update(c, prm);
     ctl[b] = c;
   }
@@ -106,6 +109,10 @@ root_init_kernel(const float* __restrict__ xs, RootCtl* ctl, Bufs bufs, int batc
 
 
 struct F32Store : F32Bufs {
+  __device__ __forceinline__ float h_init_scale(float h0, float, float* hmul) const {
+    *hmul = 1.0f;
+    return h0;
+  }
   __device__ __forceinline__ void store(int phys, int b, int i, int j, int n, float v) const {
     base[phys][(size_t)b * mat_elems + (size_t)i * n + j] = v;
   }
@@ -127,7 +134,7 @@ __global__ void root_final_kernel(const RootCtl* __restrict__ ctl, Bufs bufs, in
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn;
          e += (size_t)gridDim.x * blockDim.x) {
       const int i = (int)(e / n), j = (int)(e - (size_t)i * n);
-      out[e] = zero ? 0.f : bufs.load(4 + c.result_h, b, i, j, n);
+      out[e] = zero ? 0.f : bufs.load(4 + c.result_h, b, i, j, n) * c.hmul;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {

@@ -6,6 +6,7 @@ namespace pc {
 
 struct TcEngine {
   int batch, n, passes;  // passes: 6 (3 planes, ~fp32) or 3 (2 planes)
+  int fmt;               // 0: bf16 planes, 1: fp16 + 2^11-scaled fp16 residual (3 passes)
   // 8 logical matrices x 3 bf16 planes, each [batch, n, n]
   uint16_t* planes[kNumBufs][3];
   void* tmaps;  // device copy of the CUtensorMap table (one per buffer x plane)
@@ -13,8 +14,9 @@ struct TcEngine {
 };
 
 bool tc_engine_available();
-size_t tc_engine_bytes(int batch, int n);
-int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, cudaStream_t stream);
+size_t tc_engine_bytes(int batch, int n, int planes);
+int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt,
+                   cudaStream_t stream);
 int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* errbits,
                         RootParams prm, float* roots, int max_steps, cudaStream_t stream);
 int tc_engine_final(TcEngine* e, const RootCtl* ctl, float* roots, float* metrics,

@@ -24,6 +24,7 @@
 // same row-major planes (no transposes anywhere).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "root_kernels.cuh"
@@ -33,6 +34,17 @@ namespace pc {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_UMMA_K = 16;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;  // one plane tile: 16 KiB
+
+// Plane formats.
+//   TC_FMT_BF16   X = X0 + X1 + X2, bf16 planes (8+8+8 mantissa bits, exact), 6 (or 3) MMAs
+//   TC_FMT_FP16S  X ~ X0 + 2^-11 X1, fp16 planes (11+11 mantissa bits, |error| <= 2^-23 |X|):
+//                 the residual plane is stored scaled by 2^11 so that it lives in fp16's
+//                 normal range.  A*B = A0 B0 + 2^-11 (A0 B1 + A1 B0) takes THREE MMAs: the
+//                 cross terms are accumulated first and the leading term is issued with the
+//                 instruction's scale-input-d = 11 (D = A0 B0 + D * 2^-11).  Same 11-bit
+//                 operand mantissa as 3xTF32, at the f16 MMA rate (2x TF32) and 4 B / element.
+constexpr int TC_FMT_BF16 = 0, TC_FMT_FP16S = 1;
+constexpr float TC_FP16_SCALE = 2048.0f;
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -142,6 +154,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] = A * B + D * 2^-11 (scale-input-d; needs the explicit disable-output-lane vector)
+__device__ __forceinline__ void umma_f16_scaled_d(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                  uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p, 11;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
 // arrives on the mbarrier once all previously issued tcgen05.mma have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -182,6 +206,9 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 constexpr uint32_t kIdescBf16M128N128 =
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
     ((uint32_t)(TC_BM >> 4) << 24);
+// a = b = F16 (format 0)
+constexpr uint32_t kIdescF16M128N128 =
+    (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
 // ---------------------------------------------------------------------------
 // kernel
@@ -407,23 +434,38 @@ __device__ __forceinline__ void store_plane_block_tma(uint32_t bufD, uint32_t bu
   }
 }
 
-// fp32 row segment (consumed) -> three bf16 planes, each staged and bulk-stored.
+// fp32 row segment (consumed) -> planes (3 x bf16, or fp16 + 2^11-scaled fp16 residual), each
+// staged and bulk-stored.
+template <int kFmt>
 __device__ __forceinline__ void store_block_3planes_tma(const TcParams& P, uint32_t stage,
                                                         const EpiAddr& ea, int lane, float (&x)[32],
                                                         bool diag_sub, bool do_mirror,
                                                         const CUtensorMap* const (&smaps)[3],
                                                         int row0, int col0, int mat) {
+  constexpr int kPlanes = kFmt == TC_FMT_FP16S ? 2 : 3;
 #pragma unroll 1
-  for (int pl = 0; pl < 3; ++pl) {  // rolled: keeps the kernel inside the instruction cache
+  for (int pl = 0; pl < kPlanes; ++pl) {  // rolled: keeps the kernel inside the instruction cache
     uint32_t hp[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const __nv_bfloat162 pr = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);  // one F2FP
-      const uint32_t w = *reinterpret_cast<const uint32_t*>(&pr);
-      hp[k] = w;
-      if (pl < 2) {  // exact residuals feed the next plane
-        x[2 * k] -= __uint_as_float(w << 16);
-        x[2 * k + 1] -= __uint_as_float(w & 0xffff0000u);
+      if (kFmt == TC_FMT_FP16S) {
+        uint32_t w;  // one F2FP; saturates instead of overflowing to inf, NaN stays NaN
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(x[2 * k + 1]), "f"(x[2 * k]));
+        hp[k] = w;
+        if (pl == 0) {  // exact residual, scaled into fp16's normal range
+          const __half2 h2 = *reinterpret_cast<const __half2*>(&w);
+          const float2 f2 = __half22float2(h2);
+          x[2 * k] = (x[2 * k] - f2.x) * TC_FP16_SCALE;
+          x[2 * k + 1] = (x[2 * k + 1] - f2.y) * TC_FP16_SCALE;
+        }
+      } else {
+        const __nv_bfloat162 pr = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);  // one F2FP
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(&pr);
+        hp[k] = w;
+        if (pl < 2) {  // exact residuals feed the next plane
+          x[2 * k] -= __uint_as_float(w << 16);
+          x[2 * k + 1] -= __uint_as_float(w & 0xffff0000u);
+        }
       }
     }
     store_plane_block_tma(stage, stage + TC_STAGE_BYTES_PER_WARP, ea, lane, hp, diag_sub,
@@ -432,6 +474,7 @@ __device__ __forceinline__ void store_block_3planes_tma(const TcParams& P, uint3
 }
 
 // Same as tc_epilogue_tile but the tile is read from a TMEM output stage.
+template <int kFmt>
 __device__ __forceinline__ void tc_epilogue_tile_tmem(const TcParams& P, const TcWork& wk, int tm,
                                                       int row_in_tile, int lane, uint32_t stage,
                                                       uint32_t taddr, uint32_t oempty_bar,
@@ -449,7 +492,7 @@ __device__ __forceinline__ void tc_epilogue_tile_tmem(const TcParams& P, const T
   uint32_t emax = 0;
   const EpiAddr ea = make_epi_addr(stage, stage + TC_STAGE_BYTES_PER_WARP, lane);
   auto write_group = [&](int buf, float (&x)[32], int col0, bool diag_sub) {
-    store_block_3planes_tma(P, stage, ea, lane, x, diag_sub, mirror_on, smaps, row0, col0,
+    store_block_3planes_tma<kFmt>(P, stage, ea, lane, x, diag_sub, mirror_on, smaps, row0, col0,
                             buf * P.batch + wk.b);
   };
 #pragma unroll 1
@@ -497,7 +540,7 @@ __device__ __forceinline__ void tc_epilogue_tile_tmem(const TcParams& P, const T
   }
 }
 
-template <int kLP, int kStages>
+template <int kLP, int kStages, int kFmt>
 __global__ void __launch_bounds__(TC_WS_THREADS, 1)
 tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
                    const __grid_constant__ CUtensorMap tmap1,
@@ -594,6 +637,21 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
           const uint32_t tmem_d = tmem_base + acc * TC_BN;
           const uint32_t a0 = smem_base + stage * kStageBytes;
           const uint32_t b0 = a0 + kLP * TC_TILE_BYTES;
+          if (kFmt == TC_FMT_FP16S) {
+            // D = A0 B1 + A1 B0 (both x 2^11), then D = A0 B0 + D * 2^-11
+            const uint64_t a0d = make_kmajor_sw128_desc(a0), a1d = make_kmajor_sw128_desc(a0 + TC_TILE_BYTES);
+            const uint64_t b0d = make_kmajor_sw128_desc(b0), b1d = make_kmajor_sw128_desc(b0 + TC_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+              umma_bf16(tmem_d, a0d + 2u * k, b1d + 2u * k, kIdescF16M128N128, k == 0 ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+              umma_bf16(tmem_d, a1d + 2u * k, b0d + 2u * k, kIdescF16M128N128, 1u);
+            umma_f16_scaled_d(tmem_d, a0d, b0d, kIdescF16M128N128);
+#pragma unroll
+            for (int k = 1; k < TC_BK / TC_UMMA_K; ++k)
+              umma_bf16(tmem_d, a0d + 2u * k, b0d + 2u * k, kIdescF16M128N128, 1u);
+          } else {
           bool first = true;
 #pragma unroll
           for (int sum = kLP - 1; sum >= 0; --sum) {
@@ -609,6 +667,7 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
                 if (k == 0) first = false;
               }
             }
+          }
           }
           umma_commit(empty_bar(stage));
           umma_commit(tfull_bar(acc));
@@ -681,7 +740,7 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
       mbar_wait(ofull_bar(o), (tile >> 1) & 1);
       tcgen05_fence_after();
       const CUtensorMap* const smaps[3] = {&smap0, &smap1, &smap2};
-      tc_epilogue_tile_tmem(P, wk, wk.tm, row_in_tile, lane,
+      tc_epilogue_tile_tmem<kFmt>(P, wk, wk.tm, row_in_tile, lane,
                             stage_base + (warp - 8) * 2 * TC_STAGE_BYTES_PER_WARP,
                             tmem_base + lane_off + 256 + o * TC_BN, oempty_bar(o), 2 * half,
                             2 * half + 2, smaps);
@@ -754,6 +813,19 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16_scaled_d_2sm(uint32_t tmem_d, uint64_t adesc,
+                                                      uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, "
+      "p, 11;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u),
+      "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
 // arrive (once the MMAs retire) on the same-offset barrier of BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
   asm volatile(
@@ -777,6 +849,8 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
 // ---------------------------------------------------------------------------
 constexpr uint32_t kIdescBf16M256N256 =
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t kIdescF16M256N256 =
+    (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ bool tc_get_work_pair256(const TcParams& P, const Program* progs, int s,
                                                     int w, TcWork& out, int& tm2, int& tn2) {
@@ -807,6 +881,7 @@ __device__ __forceinline__ bool tc_get_work_pair256(const TcParams& P, const Pro
 }
 
 // Epilogue of one 128 x 128 sub-tile whose fp32 values sit in this thread's registers.
+template <int kFmt>
 __device__ __forceinline__ void tc_epilogue_regs(const TcParams& P, const TcWork& wk, int tm, int tn,
                                                  int row_in_tile, int lane, uint32_t stage,
                                                  const float (&sum)[TC_BN],
@@ -820,7 +895,7 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcParams& P, const TcWork
   uint32_t emax = 0;
   const EpiAddr ea = make_epi_addr(stage, stage + TC_STAGE_BYTES_PER_WARP, lane);
   auto write_group = [&](int buf, float (&x)[32], int col0, bool diag_sub) {
-    store_block_3planes_tma(P, stage, ea, lane, x, diag_sub, mirror_on, smaps, row0, col0,
+    store_block_3planes_tma<kFmt>(P, stage, ea, lane, x, diag_sub, mirror_on, smaps, row0, col0,
                             buf * P.batch + wk.b);
   };
 #pragma unroll
@@ -859,7 +934,7 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcParams& P, const TcWork
 
 constexpr int TC_P256_THREADS = 384;
 
-template <int kLP, int kStages>
+template <int kLP, int kStages, int kFmt>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_P256_THREADS, 1)
 tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
                         const __grid_constant__ CUtensorMap tmap1,
@@ -956,6 +1031,20 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
           const uint32_t tmem_d = tmem_base + acc * 256;
           const uint32_t a0 = smem_base + stage * kStageBytes;
           const uint32_t b0 = a0 + kLP * TC_TILE_BYTES;
+          if (kFmt == TC_FMT_FP16S) {
+            const uint64_t a0d = make_kmajor_sw128_desc(a0), a1d = make_kmajor_sw128_desc(a0 + TC_TILE_BYTES);
+            const uint64_t b0d = make_kmajor_sw128_desc(b0), b1d = make_kmajor_sw128_desc(b0 + TC_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+              umma_bf16_2sm(tmem_d, a0d + 2u * k, b1d + 2u * k, kIdescF16M256N256, k == 0 ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+              umma_bf16_2sm(tmem_d, a1d + 2u * k, b0d + 2u * k, kIdescF16M256N256, 1u);
+            umma_f16_scaled_d_2sm(tmem_d, a0d, b0d, kIdescF16M256N256);
+#pragma unroll
+            for (int k = 1; k < TC_BK / TC_UMMA_K; ++k)
+              umma_bf16_2sm(tmem_d, a0d + 2u * k, b0d + 2u * k, kIdescF16M256N256, 1u);
+          } else {
           bool first = true;
 #pragma unroll
           for (int sum = kLP - 1; sum >= 0; --sum) {
@@ -971,6 +1060,7 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
                 if (k == 0) first = false;
               }
             }
+          }
           }
           umma_commit_2sm(empty_bar(stage));
           umma_commit_2sm(tfull_bar(acc));
@@ -1018,7 +1108,7 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
       }
       const int tm = 2 * tm2 + (int)cta_rank, tn = 2 * tn2 + half;
       if (tm >= tn)  // (2 tm2, 2 tm2 + 1) of a diagonal pair-tile is upper: its mirror owns it
-        tc_epilogue_regs(P, wk, tm, tn, row_in_tile, lane,
+        tc_epilogue_regs<kFmt>(P, wk, tm, tn, row_in_tile, lane,
                          stage_base + (warp - 4) * 2 * TC_STAGE_BYTES_PER_WARP, sum, smaps);
     }
     if (lane == 0) tma_store_wait_all();
@@ -1034,6 +1124,21 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
 struct PlaneStore {
   uint16_t* plane[3];
   size_t buf_stride, mat_elems;
+  int fmt;  // TC_FMT_*
+  // H is kept as H / hmul with hmul = z^(1/p) / s, s a power of two <= 1 chosen so that
+  // every entry stays inside fp16's range: (z eps)^(-1/p) bounds the largest eigenvalue
+  // of H / z^(1/p) (eps = the damping of this try, a lower bound of lambda_min).
+  __device__ __forceinline__ float h_init_scale(float h0, float bound, float* hmul) const {
+    if (fmt != TC_FMT_FP16S) { *hmul = 1.0f; return h0; }
+    float s = 1.0f;
+    if (bound > 8192.0f) {
+      int e = 0;
+      frexpf(bound / 8192.0f, &e);  // bound / 8192 in [2^(e-1), 2^e)
+      s = ldexpf(1.0f, -(e < 100 ? e : 100));
+    }
+    *hmul = h0 / s;
+    return s;
+  }
   // blocked layout: 128 x 64 tiles, each contiguous
   __device__ __forceinline__ size_t elem(int phys, int b, int i, int j, int n) const {
     return (size_t)phys * buf_stride + (size_t)b * mat_elems +
@@ -1041,6 +1146,14 @@ struct PlaneStore {
   }
   __device__ __forceinline__ void store(int phys, int b, int i, int j, int n, float v) const {
     const size_t off = elem(phys, b, i, j, n);
+    if (fmt == TC_FMT_FP16S) {
+      const float c = fabsf(v) > 65504.0f ? copysignf(65504.0f, v) : v;  // NaN stays NaN
+      const __half h0 = __float2half_rn(c);
+      const float r1 = (c - __half2float(h0)) * TC_FP16_SCALE;
+      plane[0][off] = __half_as_ushort(h0);
+      plane[1][off] = __half_as_ushort(__float2half_rn(r1));
+      return;
+    }
     const __nv_bfloat16 a0 = __float2bfloat16_rn(v);
     const float r1 = v - __bfloat162float(a0);
     const __nv_bfloat16 a1 = __float2bfloat16_rn(r1);
@@ -1051,6 +1164,11 @@ struct PlaneStore {
   }
   __device__ __forceinline__ float load(int phys, int b, int i, int j, int n) const {
     const size_t off = elem(phys, b, i, j, n);
+    if (fmt == TC_FMT_FP16S) {
+      const float x0 = __half2float(__ushort_as_half(plane[0][off]));
+      const float x1 = __half2float(__ushort_as_half(plane[1][off]));
+      return fmaf(x1, 1.0f / TC_FP16_SCALE, x0);
+    }
     const float x0 = __bfloat162float(__ushort_as_bfloat16(plane[0][off]));
     const float x1 = __bfloat162float(__ushort_as_bfloat16(plane[1][off]));
     const float x2 = __bfloat162float(__ushort_as_bfloat16(plane[2][off]));
@@ -1086,17 +1204,18 @@ bool tc_engine_available() {
   return major == 10;
 }
 
-static size_t tc_plane_bytes(int batch, int n) {
-  return (size_t)3 * kNumBufs * batch * n * n * sizeof(uint16_t);
+static size_t tc_plane_bytes(int batch, int n, int planes) {
+  return (size_t)planes * kNumBufs * batch * n * n * sizeof(uint16_t);
 }
-size_t tc_engine_bytes(int batch, int n) {
-  return tc_plane_bytes(batch, n) + 1024 + 4 * (size_t)batch * sizeof(uint32_t) + 256;
+size_t tc_engine_bytes(int batch, int n, int planes) {
+  return tc_plane_bytes(batch, n, planes) + 1024 + 4 * (size_t)batch * sizeof(uint32_t) + 256;
 }
 
 struct TcHostState {
   CUtensorMap maps[3];     // operand loads: one 128 x 64 storage tile (16 KiB, contiguous)
   CUtensorMap maps_st[3];  // epilogue bulk stores: box {32, 32}, SWIZZLE_64B
   bool use_pair256;        // cta_group::2, 256 x 256 cluster tiles (default when n % 256 == 0)
+  int fmt, planes;         // TC_FMT_*, stored planes per matrix
   TcParams prm;
   Program* progs_dev;
   uint32_t* sync_mem;  // 2 x [2 * batch] group counters, used alternately by successive launches
@@ -1135,19 +1254,23 @@ static void plan_launch(TcHostState* hs, int s, int ntri, int units, int cpi, in
 
 static Program* g_progs_dev[64] = {nullptr};
 
-int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, cudaStream_t stream) {
+int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt,
+                   cudaStream_t stream) {
   PC_REQUIRE(n % TC_BM == 0, "tcgen05 engine needs n %% 128 == 0");
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return PC_ERR_UNSUPPORTED;
   }
-  e->batch = batch; e->n = n; e->passes = passes;
+  e->batch = batch; e->n = n; e->passes = passes; e->fmt = fmt;
   auto* hs = new TcHostState();
   e->host_state = hs;
+  hs->fmt = fmt;
+  hs->planes = fmt == TC_FMT_FP16S ? 2 : 3;
+  for (int pl = 0; pl < 3; ++pl) hs->prm.plane[pl] = nullptr;
   uint16_t* base = reinterpret_cast<uint16_t*>(align_up((size_t)mem, 1024));
   const size_t buf_stride = (size_t)batch * n * n;
-  for (int pl = 0; pl < 3; ++pl) {
+  for (int pl = 0; pl < hs->planes; ++pl) {
     uint16_t* plane = base + (size_t)pl * kNumBufs * buf_stride;
     hs->prm.plane[pl] = plane;
     for (int k = 0; k < kNumBufs; ++k) e->planes[k][pl] = plane + (size_t)k * buf_stride;
@@ -1160,12 +1283,14 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, cudaStr
                              (cuuint64_t)n * n * 2};
     cuuint32_t box[5] = {64, 128, 1, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(&hs->maps[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, plane, dims, strides, box,
+    const CUtensorMapDataType dt =
+        fmt == TC_FMT_FP16S ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = enc(&hs->maps[pl], dt, 5, plane, dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     cuuint32_t box_s[5] = {32, 32, 1, 1, 1};
     if (r == CUDA_SUCCESS)
-      r = enc(&hs->maps_st[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, plane, dims, strides, box_s,
+      r = enc(&hs->maps_st[pl], dt, 5, plane, dims, strides, box_s,
               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1175,6 +1300,10 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, cudaStr
       return PC_ERR_CUDA;
     }
   }
+  for (int pl = hs->planes; pl < 3; ++pl) {  // unused slots: valid descriptors, never dereferenced
+    hs->maps[pl] = hs->maps[0];
+    hs->maps_st[pl] = hs->maps_st[0];
+  }
   {
     const char* p256 = getenv("PC_TC_PAIR256");
     hs->use_pair256 = (n % 256 == 0) && !(p256 && p256[0] == '0');
@@ -1183,7 +1312,8 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, cudaStr
     const char* gs = getenv("PC_TC_SYNC");
     hs->group_sync = gs && gs[0] == '1';  // measured: DRAM reads -60 %, but slower
     hs->sync_mem = reinterpret_cast<uint32_t*>(
-        align_up((size_t)(reinterpret_cast<char*>(base) + tc_plane_bytes(batch, n)), 256));
+        align_up((size_t)(reinterpret_cast<char*>(base) + tc_plane_bytes(batch, n, hs->planes)),
+                 256));
     hs->launch_seq = 0;
     PC_CUDA_CHECK(cudaMemsetAsync(hs->sync_mem, 0, 4 * (size_t)batch * sizeof(uint32_t), stream));
     int dev = 0;
@@ -1220,41 +1350,52 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, cudaStr
   return PC_OK;
 }
 
-template <int kLP, int kStages>
+template <int kLP, int kStages, int kFmt>
 static int launch_phase_ws(TcHostState* hs, int s, cudaStream_t stream) {
   constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 1024 +
                           16 * TC_STAGE_BYTES_PER_WARP;
   static bool configured = false;
   if (!configured) {
-    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_ws<kLP, kStages>,
+    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_ws<kLP, kStages, kFmt>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int grid, total_work;
   plan_launch(hs, s, hs->prm.tiles * (hs->prm.tiles + 1) / 2, hs->sms, 1, &grid, &total_work);
-  tc_phase_kernel_ws<kLP, kStages><<<grid, TC_WS_THREADS, smem, stream>>>(
+  tc_phase_kernel_ws<kLP, kStages, kFmt><<<grid, TC_WS_THREADS, smem, stream>>>(
       hs->maps[0], hs->maps[1], hs->maps[2], hs->maps_st[0], hs->maps_st[1], hs->maps_st[2],
       hs->prm, hs->progs_dev, s, total_work);
   return PC_OK;
 }
 
-template <int kLP, int kStages>
+template <int kLP, int kStages, int kFmt>
 static int launch_phase_pair256(TcHostState* hs, int s, cudaStream_t stream) {
   constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 1024 +
                           16 * TC_STAGE_BYTES_PER_WARP;
   static bool configured = false;
   if (!configured) {
-    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_pair256<kLP, kStages>,
+    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_pair256<kLP, kStages, kFmt>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int t2 = hs->prm.tiles / 2;
   int clusters, total_work;
   plan_launch(hs, s, t2 * (t2 + 1) / 2, hs->sms / 2, 2, &clusters, &total_work);
-  tc_phase_kernel_pair256<kLP, kStages><<<2 * clusters, TC_P256_THREADS, smem, stream>>>(
+  tc_phase_kernel_pair256<kLP, kStages, kFmt><<<2 * clusters, TC_P256_THREADS, smem, stream>>>(
       hs->maps[0], hs->maps[1], hs->maps[2], hs->maps_st[0], hs->maps_st[1], hs->maps_st[2],
       hs->prm, hs->progs_dev, s, total_work);
   return PC_OK;
+}
+
+static int launch_phase(TcHostState* hs, int passes, int s, cudaStream_t stream) {
+  if (hs->fmt == TC_FMT_FP16S)
+    return hs->use_pair256 ? launch_phase_pair256<2, 3, TC_FMT_FP16S>(hs, s, stream)
+                           : launch_phase_ws<2, 3, TC_FMT_FP16S>(hs, s, stream);
+  if (hs->use_pair256)
+    return passes == 6 ? launch_phase_pair256<3, 2, TC_FMT_BF16>(hs, s, stream)
+                       : launch_phase_pair256<2, 3, TC_FMT_BF16>(hs, s, stream);
+  return passes == 6 ? launch_phase_ws<3, 2, TC_FMT_BF16>(hs, s, stream)
+                     : launch_phase_ws<2, 3, TC_FMT_BF16>(hs, s, stream);
 }
 
 int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* errbits,
@@ -1264,6 +1405,7 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
   hs->prm.errbits = errbits;
   PlaneStore ps;
   for (int pl = 0; pl < 3; ++pl) ps.plane[pl] = hs->prm.plane[pl];
+  ps.fmt = hs->fmt;
   ps.buf_stride = hs->prm.buf_stride;
   ps.mat_elems = hs->prm.mat_stride;
   root_init_kernel<PlaneStore><<<e->batch, 1024, 0, stream>>>(xs, ctl, ps, e->batch, e->n, prm,
@@ -1276,12 +1418,7 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
   }
   for (int s = 0; s < max_steps; ++s) {
     int rc;
-    if (hs->use_pair256)
-      rc = e->passes == 6 ? launch_phase_pair256<3, 2>(hs, s, stream)
-                          : launch_phase_pair256<2, 3>(hs, s, stream);
-    else
-      rc = e->passes == 6 ? launch_phase_ws<3, 2>(hs, s, stream)
-                          : launch_phase_ws<2, 3>(hs, s, stream);
+    rc = launch_phase(hs, e->passes, s, stream);
     if (rc != PC_OK) return rc;
   }
   if (ev0) { cudaEventRecord(ev1, stream); gemm_timing_record(ev0, ev1); }
@@ -1296,6 +1433,7 @@ int tc_engine_final(TcEngine* e, const RootCtl* ctl, float* roots, float* metric
   auto* hs = static_cast<TcHostState*>(e->host_state);
   PlaneStore ps;
   for (int pl = 0; pl < 3; ++pl) ps.plane[pl] = hs->prm.plane[pl];
+  ps.fmt = hs->fmt;
   ps.buf_stride = hs->prm.buf_stride;
   ps.mat_elems = hs->prm.mat_stride;
   dim3 fgrid((unsigned)std::min<size_t>(((size_t)e->n * e->n + 255) / 256, 64), e->batch);
@@ -1346,7 +1484,9 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
     set_error("tcgen05 engine requested but device is not sm_100");
     return PC_ERR_UNSUPPORTED;
   }
-  const size_t need = tc_engine_bytes(batch, n) + 4096 + sizeof(RootCtl) * batch + 4 * batch;
+  const int fmt = passes < 0 ? TC_FMT_FP16S : TC_FMT_BF16;
+  const size_t need = tc_engine_bytes(batch, n, fmt == TC_FMT_FP16S ? 2 : 3) + 4096 +
+                      sizeof(RootCtl) * batch + 4 * batch;
   if (workspace_bytes < need) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, need);
     return PC_ERR_WORKSPACE;
@@ -1355,7 +1495,7 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
   RootCtl* ctl = reinterpret_cast<RootCtl*>(w); w += align_up(sizeof(RootCtl) * batch, 256);
   uint32_t* errbits = reinterpret_cast<uint32_t*>(w); w += align_up(4 * batch, 256);
   TcEngine e;
-  int rc = tc_engine_init(&e, w, batch, n, passes, stream);
+  int rc = tc_engine_init(&e, w, batch, n, passes < 0 ? 3 : passes, fmt, stream);
   if (rc != PC_OK) return rc;
   auto* hs = static_cast<TcHostState*>(e.host_state);
   // private one-step program table: p = 1 -> Q0 = M * M_i^T
@@ -1372,17 +1512,13 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
   hs->prm.errbits = errbits;
   PlaneStore ps;
   for (int pl = 0; pl < 3; ++pl) ps.plane[pl] = hs->prm.plane[pl];
+  ps.fmt = hs->fmt;
   ps.buf_stride = hs->prm.buf_stride;
   ps.mat_elems = hs->prm.mat_stride;
   tc_debug_ctl_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(ctl, batch, n, errbits);
   dim3 g(64, batch);
   tc_debug_fill_kernel<<<g, 256, 0, stream>>>(a, b, ps, n);
-  if (hs->use_pair256)
-    rc = passes == 6 ? launch_phase_pair256<3, 2>(hs, 0, stream)
-                     : launch_phase_pair256<2, 3>(hs, 0, stream);
-  else
-    rc = passes == 6 ? launch_phase_ws<3, 2>(hs, 0, stream)
-                     : launch_phase_ws<2, 3>(hs, 0, stream);
+  rc = launch_phase(hs, passes < 0 ? 3 : passes, 0, stream);
   if (rc == PC_OK) tc_debug_read_kernel<<<g, 256, 0, stream>>>(ps, LB_Q0, n, c);
   cudaFreeAsync(dprog, stream);
   delete hs;
@@ -1396,7 +1532,8 @@ extern "C" int pc_debug_tc_gemm(const float* a, const float* b, float* c, int ba
                                 int passes, void* workspace, size_t workspace_bytes,
                                 void* stream) {
   PC_REQUIRE(a && b && c && workspace && batch > 0, "bad arguments");
-  PC_REQUIRE(passes == 6 || passes == 3, "passes must be 6 or 3");
+  PC_REQUIRE(passes == 6 || passes == 3 || passes == -3,
+             "passes must be 6, 3 (bf16 planes) or -3 (scaled fp16 planes)");
   return pc::tc_debug_gemm(a, b, c, batch, n, passes, workspace, workspace_bytes,
                            (cudaStream_t)stream);
 }

@@ -63,6 +63,11 @@ if __name__ == "__main__":
   gemm_case(256, 3, 6, "random")
   gemm_case(256, 2, 3, "random")
   gemm_case(1024, 2, 6, "random")
+  for kind in ("identity", "rowid", "random"):
+    gemm_case(128, 1, -3, kind)
+  gemm_case(256, 3, -3, "random")
+  gemm_case(1024, 2, -3, "random")
   for n in (128, 256, 1024):
     root_case(n, 4, 2)
+    root_case(n, 4, 4)
   root_case(256, 4, 1)

@@ -22,7 +22,7 @@ def _engines():
   from precondition_b200 import _lib
   eng = [1]
   if torch.cuda.is_available() and _lib.load().pc_device_supports_tcgen05():
-    eng += [2]
+    eng += [2, 4]  # PC_ENGINE_TC_BF16X6, PC_ENGINE_TC_FP16X3
   return eng
 
 
@@ -98,7 +98,7 @@ def _check_case(root, row, a, p, pad, engine, tag, ridge=1e-6, relative=True):
     assert rf <= 3 * (ours + ref) + 1e-4, f"{tag}: rel-Frobenius {rf}"
 
 
-@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("engine", [1, 2, 4])
 def test_golden_roots(golden_roots, engine):
   if engine not in _engines():
     pytest.skip("engine not available on this device")
@@ -130,7 +130,7 @@ def test_n1_closed_form():
   assert metrics[0, 0] == 0 and metrics[0, 1] == 0
 
 
-@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("engine", [1, 2, 4])
 def test_mixed_batch_matches_oracle(engine):
   """vmap semantics (DS:2742-2744): mixed p / padding in one batch, each matrix
   behaves as if it ran alone."""
@@ -166,7 +166,7 @@ def test_mixed_batch_matches_oracle(engine):
                 f"batch[{b}] p={ps[b]} pad={pads[b]}")
 
 
-@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("engine", [1, 2, 4])
 def test_residual_no_worse_than_reference(engine):
   if engine not in _engines():
     pytest.skip("engine not available on this device")

@@ -12,12 +12,13 @@ def _tc_ok():
 
 
 @pytest.mark.parametrize("n,batch,passes,tol", [(128, 1, 6, 2e-6), (256, 3, 6, 2e-6),
-                                                (512, 2, 6, 2e-6), (256, 2, 3, 2e-4)])
+                                                (512, 2, 6, 2e-6), (256, 2, 3, 2e-4),
+                                                (256, 3, -3, 4e-6), (1024, 1, -3, 4e-6)])
 def test_tc_gemm_matches_float64(n, batch, passes, tol):
   """lower(C) = lower(A B^T) with fp32 operands, mirrored into the upper triangle
   (the engine only ever multiplies commuting symmetric matrices and keeps its
   outputs bitwise symmetric): BF16x6 must be fp32-accurate (<= 2e-6 of the
-  largest entry), BF16x3 ~2^-16."""
+  largest entry), BF16x3 ~2^-16, scaled FP16x3 (passes = -3) ~2^-21."""
   if not _tc_ok():
     pytest.skip("needs sm_100")
   from precondition_b200 import ops
