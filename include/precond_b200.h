@@ -174,6 +174,42 @@ int pc_select_preconditioners(const float* src, const float* metrics, float thre
                               int cols, void* stream);
 
 /* ------------------------------------------------------------------------
+ * (3) Sketchy / frequent-directions sketch update
+ * replaces: _fd_update_root (DS:1123-1290) as vmapped by new_mi_pth_root
+ *           (DS:2706-2738), incl. _fd_low_rank_unpack / _fd_low_rank_pack (DS:555-592).
+ *   new_grad  input_is_gram = 0: [batch, d, m] f32, any factor F with F F^T = x x^T -- the
+ *             reference's zero-padded QR factor from frequent_directions_update
+ *             (DS:1473-1505) has m = d; the gradient block unfolding itself works too.
+ *             input_is_gram = 1: [batch, d, d] f32, x x^T itself (m ignored).
+ *   prev      [batch, d, rank+2] f32  previous packed sketch (DS:563-568)
+ *   ps        [batch] i32             exponents
+ *   padding_starts [batch] i32        may be NULL (= d)
+ *   out       [batch, d, rank+2] f32  new packed sketch
+ *   metrics   [batch, 5] f32          may be NULL; error 0 like DS:1263-1264
+ * The left singular vectors / values of [sqrt(beta2) U sqrt(lambda+eps) | G] (DS:1180-1193)
+ * are computed as eigenpairs of the d x d covariance: exactly (cyclic Jacobi on all of it)
+ * for d <= full_eigh_max_dim, else by block subspace iteration warm-started from the
+ * previous sketch with a (rank+1+oversample)^2 Rayleigh-Ritz eigenproblem.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  float ridge_epsilon;         /* matrix_epsilon                                  */
+  float error_tolerance;       /* floor of the relative damping, DS:1159 (1e-6)   */
+  int relative_matrix_epsilon; /* DS:1155-1158                                    */
+  float decay;                 /* beta2, DS:1180, DS:1201                         */
+  int input_is_gram;
+  int subspace_iters;          /* block iterations of the large-d path (8)        */
+  int oversample;              /* extra basis vectors of the large-d path (32)    */
+  int full_eigh_max_dim;       /* <= 512: d up to here is solved exactly (512)    */
+} pc_fd_options;
+
+void pc_fd_options_default(pc_fd_options* opt);
+size_t pc_fd_update_workspace_bytes(int batch, int d, int m, int rank, const pc_fd_options* opt);
+int pc_fd_update_batched(const float* new_grad, const float* prev, const int32_t* ps,
+                         const int32_t* padding_starts, int batch, int d, int m, int rank,
+                         const pc_fd_options* opt, float* out, float* metrics, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * (1b) QuantizedValue (QU:49-113) for square statistics / preconditioners with
  *      extract_diagonal=True (DS:2087-2095) and for momenta (DS:2111-2114).
  *   quantize:   x [rows, cols] f32 -> q (int16/int8/bf16), diag [rows] (if

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "pc_inverse_pth_root_batched", "pc_debug_tc_gemm", "pc_power_iteration_batched", "pc_grouped_gemm", "pc_select_preconditioners",
     "pc_quantize_batched", "pc_dequantize_batched",
     "pc_graft_momentum_workspace_bytes", "pc_graft_momentum",
+    "pc_fd_options_default", "pc_fd_update_workspace_bytes", "pc_fd_update_batched",
 )
 
 
@@ -33,6 +34,13 @@ class RootOptions(ctypes.Structure):
   _fields_ = [("ridge_epsilon", ctypes.c_float), ("error_tolerance", ctypes.c_float),
               ("num_iters", ctypes.c_int), ("relative_matrix_epsilon", ctypes.c_int),
               ("engine", ctypes.c_int), ("reserved", ctypes.c_int)]
+
+
+class FdOptions(ctypes.Structure):
+  _fields_ = [("ridge_epsilon", ctypes.c_float), ("error_tolerance", ctypes.c_float),
+              ("relative_matrix_epsilon", ctypes.c_int), ("decay", ctypes.c_float),
+              ("input_is_gram", ctypes.c_int), ("subspace_iters", ctypes.c_int),
+              ("oversample", ctypes.c_int), ("full_eigh_max_dim", ctypes.c_int)]
 
 
 class Stats(ctypes.Structure):
@@ -123,6 +131,13 @@ def load() -> ctypes.CDLL:
   lib.pc_graft_momentum.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64,
                                     ctypes.POINTER(GraftOptions), vp, sz, vp]
   lib.pc_graft_momentum.restype = i32
+  lib.pc_fd_options_default.argtypes = [ctypes.POINTER(FdOptions)]
+  lib.pc_fd_options_default.restype = None
+  lib.pc_fd_update_workspace_bytes.argtypes = [i32, i32, i32, i32, ctypes.POINTER(FdOptions)]
+  lib.pc_fd_update_workspace_bytes.restype = sz
+  lib.pc_fd_update_batched.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32,
+                                       ctypes.POINTER(FdOptions), vp, vp, vp, sz, vp]
+  lib.pc_fd_update_batched.restype = i32
   _lib = lib
   return lib
 

@@ -1,0 +1,653 @@
+// Sketchy / frequent-directions sketch update on the GPU  (reference: _fd_update_root,
+// DS:1123-1290; pack / unpack DS:555-592; caller new_mi_pth_root DS:2706-2738).
+//
+// The reference stacks  [sqrt(beta2) U sqrt(lambda + eps) | G]  (d x (r + d)) and takes a
+// LAPACK SVD.  Only the left singular vectors u_i and s_i^2 are used, and those are the
+// eigenpairs of the d x d covariance
+//        C = beta2 * U diag(lambda + eps) U^T + G G^T,
+// so the B200 path is GEMM-shaped:
+//   1. fd_prepare_kernel   unpack the previous sketch, damping, masks      (DS:1150-1174)
+//   2. batched GEMMs       C = Bs Bs^T + F F^T   (or + the Gram itself)
+//   3. top-(r+1) eigenpairs of C
+//        d <= full_eigh_max_dim : cyclic one-sided Jacobi on all of C (exact "small eigh")
+//        otherwise              : block subspace iteration warm-started from the previous
+//                                 sketch, Rayleigh-Ritz on a k x k matrix (k = r+1+oversample)
+//                                 solved by the same Jacobi kernel
+//   4. fd_finalize_kernel  deflation by s_r^2, tail accumulation, inversion, safety
+//                          masks and packing                             (DS:1195-1262)
+// Vectors are kept as ROWS ("transposed" layout) so Jacobi rotations and GEMM operands
+// are contiguous.  All GEMMs run on the fp32 CUDA-core tile of simt_gemm.cuh.
+#include <math.h>
+
+#include <algorithm>
+
+#include "simt_gemm.cuh"
+
+namespace pc {
+
+// ---------------------------------------------------------------------------
+// batched strided GEMM, descriptor by value:
+//   C[z](i,j) = rs[z][i] * alpha * sum_k A[z](i,k) B[z](j,k) + beta * Cin[z](i,j)
+// ---------------------------------------------------------------------------
+struct FdGemm {
+  const float* a; const float* b; const float* cin; float* c;
+  const float* row_scale;  // optional [batch, m]
+  int64_t a_bs, b_bs, c_bs, rs_bs;
+  int64_t a_si, a_sk, b_sj, b_sk, c_si;
+  int m, n, k;
+  float alpha, beta;
+};
+
+__global__ void __launch_bounds__(kSimtThreads) fd_gemm_kernel(const FdGemm g) {
+  __shared__ SimtSmem sm;
+  const int z = blockIdx.z;
+  const int tile_m = blockIdx.y, tile_n = blockIdx.x;
+  const OperandView A{g.a + z * g.a_bs, 0, g.a_si, 0, g.a_sk, g.m > 0 ? g.m : 1,
+                      g.k > 0 ? g.k : 1, g.m, g.k};
+  const OperandView B{g.b + z * g.b_bs, 0, g.b_sj, 0, g.b_sk, g.n > 0 ? g.n : 1,
+                      g.k > 0 ? g.k : 1, g.n, g.k};
+  const float* cin = g.cin ? g.cin + z * g.c_bs : nullptr;
+  float* c = g.c + z * g.c_bs;
+  const float* rs = g.row_scale ? g.row_scale + z * g.rs_bs : nullptr;
+  simt_gemm_tile(g.k, tile_m, tile_n, A, B, A.k_fast(), B.k_fast(), sm,
+                 [&](int i, int j0, const float* acc) {
+                   if (i >= g.m) return;
+                   const float sc = rs ? rs[i] * g.alpha : g.alpha;
+#pragma unroll
+                   for (int q = 0; q < 4; ++q) {
+                     const int j = j0 + q;
+                     if (j >= g.n) continue;
+                     float v = sc * acc[q];
+                     if (cin) v = fmaf(g.beta, cin[(int64_t)i * g.c_si + j], v);
+                     c[(int64_t)i * g.c_si + j] = v;
+                   }
+                 });
+}
+
+static void fd_gemm(const FdGemm& g, int batch, cudaStream_t stream) {
+  if (g.m <= 0 || g.n <= 0 || batch <= 0) return;
+  dim3 grid((g.n + kSimtBN - 1) / kSimtBN, (g.m + kSimtBM - 1) / kSimtBM, batch);
+  fd_gemm_kernel<<<grid, kSimtThreads, 0, stream>>>(g);
+  count_launch(1);
+}
+
+// ---------------------------------------------------------------------------
+// per-matrix scalars handed from prepare to finalize
+// ---------------------------------------------------------------------------
+struct FdScalars {
+  float tail_decayed;  // tail * decay, DS:1201
+  float ridge;
+  int pad;
+  int p;
+};
+
+__device__ __forceinline__ float fd_hash_uniform(uint32_t b, uint32_t j, uint32_t i) {
+  uint32_t x = b * 0x9E3779B1u ^ (j + 0x7F4A7C15u) * 0x85EBCA77u ^ (i + 0x165667B1u) * 0xC2B2AE3Du;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return (float)(x >> 8) * (1.0f / 8388608.0f) - 1.0f;
+}
+
+// prev [d, r+2] -> Bs [d, r] = sqrt(decay) * (U masked) * sqrt((lambda + ridge) masked)
+// (DS:1155-1171, DS:1180-1192); optionally the start basis of the subspace iteration
+// Yt [k, d]: rows < r = previous eigenvectors (random if that slot was empty), rows >= r
+// pseudo-random, all masked to the unpadded rows.
+__global__ void __launch_bounds__(256)
+fd_prepare_kernel(const float* __restrict__ prev, const int32_t* __restrict__ ps,
+                  const int32_t* __restrict__ pads, int d, int r, float ridge_epsilon,
+                  float error_tolerance, int relative_eps, float decay, float* __restrict__ bs,
+                  FdScalars* __restrict__ scal, float* __restrict__ yt, int k) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x;
+  const int pd = r + 2;
+  const float* P = prev + (size_t)b * d * pd;
+  const int pad = pads ? min(max(pads[b], 0), d) : d;
+  const float max_ev = relative_eps ? P[(size_t)(d - r) * pd + r + 1] : 1.0f;   // DS:1155-1158
+  const float ridge = ridge_epsilon * fmaxf(max_ev, error_tolerance);           // DS:1159
+  if (threadIdx.x == 0) {
+    FdScalars s;
+    s.tail_decayed = P[(size_t)1 * pd + r + 1] * decay;  // DS:1201
+    s.ridge = ridge;
+    s.pad = pad;
+    s.p = ps[b];
+    scal[b] = s;
+  }
+  const float sdecay = sqrtf(decay);
+  float* B = bs + (size_t)b * d * r;
+  for (size_t e = threadIdx.x; e < (size_t)d * r; e += blockDim.x) {
+    const int i = (int)(e / r), j = (int)(e - (size_t)i * r);
+    const bool on = i < pad && j < pad;                                  // DS:1167-1168
+    const float ev = (P[(size_t)(d - r + j) * pd + r + 1] + ridge) * (j < pad ? 1.f : 0.f);
+    const float w = (on ? P[(size_t)i * pd + j] : 0.f) * sqrtf(ev);      // DS:1171
+    B[e] = sdecay * w;
+  }
+  if (!yt) return;
+  float* Y = yt + (size_t)b * k * d;
+  for (int j = 0; j < k; ++j) {
+    bool use_prev = false;
+    if (j < r) {  // block-uniform decision: is the previous eigenvector slot populated?
+      float ss = 0.f;
+      for (int i = threadIdx.x; i < pad; i += blockDim.x) {
+        const float v = P[(size_t)i * pd + j];
+        ss = fmaf(v, v, ss);
+      }
+      use_prev = block_sum(ss, scratch) > 0.25f;
+    }
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+      float v = 0.f;
+      if (i < pad) v = use_prev ? P[(size_t)i * pd + j] : fd_hash_uniform(b, j, i);
+      Y[(size_t)j * d + i] = v;
+    }
+  }
+}
+
+// masked copy of the new-gradient input (DS:1172-1174): factor [d, m] -> Fm (columns are
+// masked as well when the factor is square, as in the reference), or Gram [d, d] -> C.
+__global__ void fd_mask_kernel(const float* __restrict__ src, const FdScalars* __restrict__ scal,
+                               int rows, int cols, int mask_cols, float* __restrict__ dst) {
+  const int b = blockIdx.y;
+  const int pad = scal[b].pad;
+  const size_t total = (size_t)rows * cols;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / cols), j = (int)(e - (size_t)i * cols);
+    const bool on = i < pad && (!mask_cols || j < pad);
+    dst[(size_t)b * total + e] = on ? src[(size_t)b * total + e] : 0.f;
+  }
+}
+
+// each row of X [rows, len] scaled to unit 2-norm (zero rows stay zero)
+__global__ void __launch_bounds__(256)
+fd_row_normalize_kernel(float* __restrict__ x, int rows, int len) {
+  __shared__ float scratch[32];
+  float* row = x + ((size_t)blockIdx.y * rows + blockIdx.x) * len;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) ss = fmaf(row[i], row[i], ss);
+  const float nrm = sqrtf(block_sum(ss, scratch));
+  const float inv = nrm > 0.f ? 1.0f / nrm : 0.f;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) row[i] *= inv;
+}
+
+// ---------------------------------------------------------------------------
+// Symmetric eigensolver: cyclic one-sided Jacobi (Hestenes) on the ROWS of A [n, n]
+// (symmetric, destroyed) with the rotations accumulated in Vt [n, n] (rows = eigenvectors).
+// Round-robin ordering: n/2 disjoint pairs per round, one warp per pair; a thread-block
+// cluster shares one matrix (rows live in L2, ld/st.cg) and a cluster barrier separates
+// rounds.  theta_i = <A_i, Vt_i> (Rayleigh quotient; A_i = theta_i v_i at convergence).
+// ---------------------------------------------------------------------------
+constexpr int kJacThreads = 512;
+constexpr int kJacMaxN = 512;
+constexpr int kJacMaxSweeps = 15;
+
+__device__ __forceinline__ void jac_cluster_sync(int csize) {
+  if (csize > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kJacThreads)
+fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, float tol,
+                 unsigned* __restrict__ rot_count, float* __restrict__ theta_all, int csize) {
+  const int b = blockIdx.x / csize;
+  int crank = 0;
+  if (csize > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  float* A = a_all + (size_t)b * n * n;
+  float* V = vt_all + (size_t)b * n * n;
+  unsigned* cnt = rot_count + (size_t)b * kJacMaxSweeps;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarp = (kJacThreads / 32) * csize, gw = crank * (kJacThreads / 32) + warp;
+  // Vt <- I
+  for (size_t e = (size_t)crank * kJacThreads + threadIdx.x; e < (size_t)n * n;
+       e += (size_t)csize * kJacThreads)
+    __stcg(V + e, (e / n == e % n) ? 1.f : 0.f);
+  jac_cluster_sync(csize);
+  const int m2 = (n + 1) & ~1;  // players (one phantom if n is odd)
+  const int rounds = m2 - 1, npairs = m2 / 2;
+  constexpr int Q = kJacMaxN / 32;
+  for (int sweep = 0; sweep < kJacMaxSweeps; ++sweep) {
+    unsigned rotated = 0;
+    for (int t = 0; t < rounds; ++t) {
+      for (int p = gw; p < npairs; p += nwarp) {
+        int i, j;  // circle method: player m2-1 is fixed, the others rotate
+        if (p == 0) { i = t; j = m2 - 1; }
+        else { i = (t + p) % rounds; j = (t - p + rounds) % rounds; }
+        if (i > j) { const int tmp = i; i = j; j = tmp; }
+        if (j >= n) continue;  // phantom
+        float ai[Q], aj[Q];
+        float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const int c = lane + 32 * q;
+          ai[q] = c < n ? __ldcg(A + (size_t)i * n + c) : 0.f;
+          aj[q] = c < n ? __ldcg(A + (size_t)j * n + c) : 0.f;
+          al = fmaf(ai[q], ai[q], al);
+          be = fmaf(aj[q], aj[q], be);
+          ga = fmaf(ai[q], aj[q], ga);
+        }
+        al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+        const float lim = tol * sqrtf(al) * sqrtf(be);
+        if (!(fabsf(ga) > lim) || lim == 0.f) continue;  // warp-uniform
+        ++rotated;
+        const float zeta = (be - al) / (2.0f * ga);
+        const float tt = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+        const float cs = rsqrtf(1.0f + tt * tt), sn = cs * tt;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const int c = lane + 32 * q;
+          if (c < n) {
+            __stcg(A + (size_t)i * n + c, cs * ai[q] - sn * aj[q]);
+            __stcg(A + (size_t)j * n + c, sn * ai[q] + cs * aj[q]);
+            const float vi = __ldcg(V + (size_t)i * n + c), vj = __ldcg(V + (size_t)j * n + c);
+            __stcg(V + (size_t)i * n + c, cs * vi - sn * vj);
+            __stcg(V + (size_t)j * n + c, sn * vi + cs * vj);
+          }
+        }
+      }
+      jac_cluster_sync(csize);
+    }
+    if (lane == 0 && rotated) atomicAdd(cnt + sweep, rotated);
+    __threadfence();
+    jac_cluster_sync(csize);
+    if (__ldcg(cnt + sweep) == 0u) break;  // uniform across the cluster
+  }
+  float* theta = theta_all + (size_t)b * n;
+  for (int i = gw; i < n; i += nwarp) {
+    float dot = 0.f;
+    for (int c = lane; c < n; c += 32)
+      dot = fmaf(__ldcg(A + (size_t)i * n + c), __ldcg(V + (size_t)i * n + c), dot);
+    dot = warp_sum(dot);
+    if (lane == 0) theta[i] = dot;
+  }
+}
+
+// order[rank] = index of the rank-th largest theta (ties by index); sorted[rank] = theta
+__global__ void __launch_bounds__(512)
+fd_sort_kernel(const float* __restrict__ theta_all, int n, int* __restrict__ order_all,
+               float* __restrict__ sorted_all) {
+  const int b = blockIdx.x;
+  const float* th = theta_all + (size_t)b * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float raw = th[i];
+    const float x = raw != raw ? INFINITY : raw;  // NaN sorts first so that it is seen
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float yr = th[j];
+      const float y = yr != yr ? INFINITY : yr;
+      rank += (y > x || (y == x && j < i)) ? 1 : 0;
+    }
+    order_all[(size_t)b * n + rank] = i;
+    sorted_all[(size_t)b * n + rank] = raw;
+  }
+}
+
+// 1/sqrt(theta) row scales for the Gram-based orthonormalisation (directions whose Gram
+// eigenvalue is numerically zero are dropped)
+__global__ void fd_orth_scale_kernel(const float* __restrict__ theta_all, int n,
+                                     float* __restrict__ scale_all) {
+  __shared__ float smax;
+  const int b = blockIdx.x;
+  const float* th = theta_all + (size_t)b * n;
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int i = 0; i < n; ++i) m = fmaxf(m, th[i]);
+    smax = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = th[i];
+    scale_all[(size_t)b * n + i] = (x > 1e-5f * smax && x > 0.f) ? rsqrtf(x) : 0.f;
+  }
+}
+
+// dst[b][t][:] = src[b][order[b][t]][:] for t < count
+__global__ void fd_gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ order,
+                                      int n_rows, int len, int count, float* __restrict__ dst) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  const float* s = src + ((size_t)b * n_rows + order[(size_t)b * n_rows + t]) * len;
+  float* o = dst + ((size_t)b * count + t) * len;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) o[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------
+// deflation, tail, inversion, safety masks and packing: DS:1195-1262, DS:572-592
+//   vt      [batch, nv, d]  candidate eigenvectors as rows, sorted by eigenvalue (>= r rows)
+//   theta   [batch, ld_theta] eigenvalues s_i^2, descending (>= r + 1 entries)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fd_finalize_kernel(const float* __restrict__ vt_all, int nv, const float* __restrict__ theta_all,
+                   int ld_theta, const FdScalars* __restrict__ scal, int d, int r,
+                   float* __restrict__ out_all, float* __restrict__ metrics) {
+  extern __shared__ float sh[];
+  float* deflated = sh;        // [r]
+  float* inverted = sh + r;    // [r]
+  float* keep = sh + 2 * r;    // [r] 1 = direction kept
+  float* scale = sh + 3 * r;   // [r] 1 / norm
+  __shared__ int has_zero_flag;
+  const int b = blockIdx.x;
+  const FdScalars s = scal[b];
+  const float* vt = vt_all + (size_t)b * nv * d;
+  const float* theta = theta_all + (size_t)b * ld_theta;
+  float* out = out_all + (size_t)b * d * (r + 2);
+  const int pd = r + 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (threadIdx.x == 0) has_zero_flag = 0;
+  __syncthreads();
+  const float alpha = -1.0f / (float)s.p;
+  const float cutoff = sqrtf(fmaxf(theta[r], 0.f));  // s[rank], DS:1195
+  const float rho = cutoff * cutoff;
+  float new_tail = s.tail_decayed + rho;             // DS:1202
+  const float new_const = new_tail <= 0.f ? 0.f : powf(new_tail, alpha);  // DS:1205
+  new_tail = new_tail <= 0.f ? 0.f : new_tail;
+  // one warp per direction: deflation, norm / padding safety (DS:1199-1246)
+  for (int j = warp; j < r; j += nwarp) {
+    const float top = sqrtf(fmaxf(theta[j], 0.f));
+    float defl = (top - cutoff) * (top + cutoff);    // DS:1199
+    defl = defl <= 0.f ? 0.f : defl;                 // DS:1209
+    float ss = 0.f, padmass = 0.f;
+    const float on = defl > 0.f ? 1.f : 0.f;         // DS:1210
+    for (int i = lane; i < d; i += 32) {
+      const float v = vt[(size_t)j * d + i] * on;
+      ss = fmaf(v, v, ss);
+    }
+    const float nrm = sqrtf(warp_sum(ss));
+    const bool safe = 0.99f <= nrm && nrm <= 1.01f;  // DS:1214-1216
+    const float inv = safe ? 1.0f / nrm : 1.0f;
+    for (int i = lane; i < d; i += 32)
+      if (i >= s.pad)  // DS:1224-1226: L1 mass of the (normalised) vector on padding rows
+        padmass += fabsf(vt[(size_t)j * d + i] * on * (safe ? inv : 0.f));
+    padmass = warp_sum(padmass);
+    const bool haspad = padmass > 0.01f;
+    const float kp = (safe && !haspad) ? on : 0.f;
+    defl = defl * (safe ? 1.f : 0.f) * (haspad ? 0.f : 1.f);
+    float up = (top * top + s.tail_decayed) * (defl > 0.f ? 1.f : 0.f);  // DS:1247-1248
+    up = up <= 0.f ? 0.f : up;
+    const float invd = up <= 0.f ? 0.f : powf(up, alpha);
+    if (lane == 0) {
+      deflated[j] = defl;
+      inverted[j] = invd;
+      keep[j] = kp;
+      scale[j] = inv;
+      if (defl <= 0.f) has_zero_flag = 1;  // DS:1251
+    }
+  }
+  __syncthreads();
+  const bool has_zeros = has_zero_flag != 0 || new_tail <= 0.f;
+  const bool zero_all = s.pad == 0;  // DS:1265-1268
+  for (size_t e = threadIdx.x; e < (size_t)d * pd; e += blockDim.x) {
+    const int i = (int)(e / pd), j = (int)(e - (size_t)i * pd);
+    float v = 0.f;
+    if (!zero_all) {
+      if (j < r) {
+        v = vt[(size_t)j * d + i] * keep[j] * scale[j];
+        if (v == 0.f) v = 0.f;  // -0 -> +0 like the reference's masked product
+      } else if (j == r) {      // column -2: inverted eigenvalues, has_zeros in the last row
+        if (i < r) v = inverted[i];
+        if (i == d - 1) v = has_zeros ? 1.f : 0.f;
+      } else {                  // column -1: const, tail, deflated eigenvalues (DS:585-591)
+        if (i == 0) v = new_const;
+        if (i == 1) v = new_tail;
+        if (i >= d - r) v = deflated[i - (d - r)];
+      }
+    }
+    out[e] = v;
+  }
+  if (threadIdx.x == 0 && metrics) {
+    float* m = metrics + (size_t)b * PC_NUM_METRICS;  // DS:1263-1264: error 0, rest default
+    m[0] = 0.f; m[1] = 0.f; m[2] = 0.f; m[3] = 0.f; m[4] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------
+struct FdPlan {
+  bool subspace;
+  int k;  // Jacobi size: d (full) or r + 1 + oversample
+};
+
+static FdPlan fd_plan(int d, int rank, const pc_fd_options* opt) {
+  FdPlan p;
+  p.subspace = d > opt->full_eigh_max_dim;
+  p.k = d;
+  if (p.subspace) {
+    int k = rank + 1 + std::max(opt->oversample, 0);
+    k = std::min(k, std::min(d, kJacMaxN));
+    p.k = k;
+  }
+  return p;
+}
+
+struct FdWorkspace {
+  FdScalars* scal; unsigned* rot; float* bs; float* fm; float* cmat; float* vt; float* theta;
+  float* sorted; int* order; float* rscale; float* yt; float* qt; float* pt; float* small;
+  float* zsel; float* vtop;
+};
+
+static size_t fd_carve(FdWorkspace* w, char* base, int batch, int d, int m, int rank,
+                       const FdPlan& pl, bool gram) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const size_t B = (size_t)batch;
+  const int k = pl.k;
+  const int rot_slots = 64;  // Jacobi calls per update (each uses kJacMaxSweeps counters)
+  w->scal = (FdScalars*)take(B * sizeof(FdScalars));
+  w->rot = (unsigned*)take(B * kJacMaxSweeps * rot_slots * sizeof(unsigned));
+  w->bs = (float*)take(B * d * rank * 4);
+  w->fm = gram ? nullptr : (float*)take(B * d * m * 4);
+  w->cmat = (float*)take(B * d * d * 4);
+  w->vt = (float*)take(B * k * k * 4);
+  w->theta = (float*)take(B * k * 4);
+  w->sorted = (float*)take(B * k * 4);
+  w->order = (int*)take(B * k * 4);
+  w->rscale = (float*)take(B * k * 4);
+  if (pl.subspace) {
+    w->yt = (float*)take(B * k * d * 4);
+    w->qt = (float*)take(B * k * d * 4);
+    w->pt = (float*)take(B * k * d * 4);
+    w->small = (float*)take(B * k * k * 4);
+    w->zsel = (float*)take(B * (rank + 1) * k * 4);
+    w->vtop = (float*)take(B * (rank + 1) * d * 4);
+  } else {
+    w->yt = w->qt = w->pt = w->small = w->zsel = nullptr;
+    w->vtop = (float*)take(B * (rank + 1) * d * 4);
+  }
+  return off + 256;
+}
+
+static int fd_jacobi(float* a, float* vt, int n, int batch, unsigned* rot, float* theta,
+                     cudaStream_t stream) {
+  int csize = 1;
+  while (csize < 8 && (kJacThreads / 32) * csize < (n + 1) / 2) csize <<= 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(batch * csize));
+  cfg.blockDim = dim3(kJacThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fd_jacobi_kernel, a, vt, n, 3e-6f, rot, theta, csize));
+  count_launch(1);
+  return PC_OK;
+}
+
+int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
+                  const int32_t* pads, int batch, int d, int m, int rank,
+                  const pc_fd_options* opt, float* out, float* metrics, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream) {
+  const bool gram = opt->input_is_gram != 0;
+  const FdPlan pl = fd_plan(d, rank, opt);
+  FdWorkspace w;
+  const size_t need = fd_carve(&w, nullptr, batch, d, m, rank, pl, gram);
+  if (workspace_bytes < need) {
+    set_error("fd workspace too small: %zu < %zu", workspace_bytes, need);
+    return PC_ERR_WORKSPACE;
+  }
+  fd_carve(&w, reinterpret_cast<char*>(align_up((size_t)workspace, 256)), batch, d, m, rank, pl,
+           gram);
+  const int k = pl.k;
+  PC_CUDA_CHECK(cudaMemsetAsync(w.rot, 0, (size_t)batch * kJacMaxSweeps * 64 * sizeof(unsigned),
+                                stream));
+  int jac_calls = 0;
+  auto jacobi = [&](float* a, float* vt, int n) -> int {
+    unsigned* rot = w.rot + (size_t)(jac_calls++ % 64) * batch * kJacMaxSweeps;
+    return fd_jacobi(a, vt, n, batch, rot, w.theta, stream);
+  };
+
+  fd_prepare_kernel<<<batch, 256, 0, stream>>>(prev, ps, pads, d, rank, opt->ridge_epsilon,
+                                              opt->error_tolerance, opt->relative_matrix_epsilon,
+                                              opt->decay, w.bs, w.scal, pl.subspace ? w.yt : nullptr,
+                                              k);
+  count_launch(1);
+  const unsigned mgrid = (unsigned)std::min<size_t>(((size_t)d * std::max(d, m) + 255) / 256, 1024);
+  // ---- covariance C = Bs Bs^T + (masked) F F^T ----
+  FdGemm g{};
+  g.alpha = 1.f;
+  if (gram) {
+    fd_mask_kernel<<<dim3(mgrid, batch), 256, 0, stream>>>(new_grad, w.scal, d, d, 1, w.cmat);
+    count_launch(1);
+  } else {
+    fd_mask_kernel<<<dim3(mgrid, batch), 256, 0, stream>>>(new_grad, w.scal, d, m, m == d ? 1 : 0,
+                                                          w.fm);
+    count_launch(1);
+    g.a = g.b = w.fm; g.cin = nullptr; g.c = w.cmat;
+    g.a_bs = g.b_bs = (int64_t)d * m; g.c_bs = (int64_t)d * d;
+    g.a_si = g.b_sj = m; g.a_sk = g.b_sk = 1; g.c_si = d;
+    g.m = g.n = d; g.k = m; g.beta = 0.f;
+    fd_gemm(g, batch, stream);
+  }
+  g = FdGemm{};
+  g.alpha = 1.f; g.beta = 1.f;
+  g.a = g.b = w.bs; g.cin = w.cmat; g.c = w.cmat;
+  g.a_bs = g.b_bs = (int64_t)d * rank; g.c_bs = (int64_t)d * d;
+  g.a_si = g.b_sj = rank; g.a_sk = g.b_sk = 1; g.c_si = d;
+  g.m = g.n = d; g.k = rank;
+  fd_gemm(g, batch, stream);
+
+  const float* vt_final = nullptr;
+  int nv = 0;
+  if (!pl.subspace) {
+    // ---- exact: all eigenpairs of C ----
+    int rc = jacobi(w.cmat, w.vt, d);
+    if (rc != PC_OK) return rc;
+    fd_sort_kernel<<<batch, 512, 0, stream>>>(w.theta, d, w.order, w.sorted);
+    fd_gather_rows_kernel<<<dim3(rank + 1, batch), 256, 0, stream>>>(w.vt, w.order, d, d, rank + 1,
+                                                                    w.vtop);
+    count_launch(2);
+    vt_final = w.vtop;
+    nv = rank + 1;
+  } else {
+    // ---- block subspace iteration with Rayleigh-Ritz ----
+    const int iters = std::max(opt->subspace_iters, 1);
+    auto gemm_small_from_rows = [&](const float* x, const float* y, float* dst) {
+      FdGemm q{};  // dst [k,k] = X Y^T over the long dimension d
+      q.alpha = 1.f; q.a = x; q.b = y; q.c = dst;
+      q.a_bs = q.b_bs = (int64_t)k * d; q.c_bs = (int64_t)k * k;
+      q.a_si = q.b_sj = d; q.a_sk = q.b_sk = 1; q.c_si = k;
+      q.m = q.n = k; q.k = d;
+      fd_gemm(q, batch, stream);
+    };
+    auto rotate_rows = [&](const float* coef, int rows, int64_t coef_bs, const float* rs,
+                           const float* x, float* dst, int64_t dst_bs) {
+      FdGemm q{};  // dst [rows, d] = diag(rs) coef [rows, k] X [k, d]
+      q.alpha = 1.f; q.a = coef; q.b = x; q.c = dst; q.row_scale = rs;
+      q.a_bs = coef_bs; q.b_bs = (int64_t)k * d; q.c_bs = dst_bs; q.rs_bs = k;
+      q.a_si = k; q.a_sk = 1; q.b_sj = 1; q.b_sk = d; q.c_si = d;
+      q.m = rows; q.n = d; q.k = k;
+      fd_gemm(q, batch, stream);
+    };
+    for (int it = 0; it < iters; ++it) {
+      // orthonormalise the rows of Yt: unit rows, Gram, eigh, Qt = S^-1/2 W^T Yt
+      fd_row_normalize_kernel<<<dim3(k, batch), 256, 0, stream>>>(w.yt, k, d);
+      count_launch(1);
+      gemm_small_from_rows(w.yt, w.yt, w.small);
+      int rc = jacobi(w.small, w.vt, k);
+      if (rc != PC_OK) return rc;
+      fd_orth_scale_kernel<<<batch, 256, 0, stream>>>(w.theta, k, w.rscale);
+      count_launch(1);
+      rotate_rows(w.vt, k, (int64_t)k * k, w.rscale, w.yt, w.qt, (int64_t)k * d);
+      // Pt = Qt C   (rows of Pt = C q_i)
+      FdGemm q{};
+      q.alpha = 1.f; q.a = w.qt; q.b = w.cmat; q.c = w.pt;
+      q.a_bs = (int64_t)k * d; q.b_bs = (int64_t)d * d; q.c_bs = (int64_t)k * d;
+      q.a_si = d; q.a_sk = 1; q.b_sj = d; q.b_sk = 1; q.c_si = d;
+      q.m = k; q.n = d; q.k = d;
+      fd_gemm(q, batch, stream);
+      // Rayleigh-Ritz: T = Qt Pt^T, eigh -> Zt (rows = Ritz coefficient vectors)
+      gemm_small_from_rows(w.qt, w.pt, w.small);
+      rc = jacobi(w.small, w.vt, k);
+      if (rc != PC_OK) return rc;
+      if (it + 1 < iters)  // next block: Yt = Zt Pt = (C Q Z)^T
+        rotate_rows(w.vt, k, (int64_t)k * k, nullptr, w.pt, w.yt, (int64_t)k * d);
+    }
+    fd_sort_kernel<<<batch, 512, 0, stream>>>(w.theta, k, w.order, w.sorted);
+    fd_gather_rows_kernel<<<dim3(rank + 1, batch), 256, 0, stream>>>(w.vt, w.order, k, k, rank + 1,
+                                                                    w.zsel);
+    count_launch(2);
+    rotate_rows(w.zsel, rank + 1, (int64_t)(rank + 1) * k, nullptr, w.qt, w.vtop,
+                (int64_t)(rank + 1) * d);
+    vt_final = w.vtop;
+    nv = rank + 1;
+  }
+  fd_finalize_kernel<<<batch, 256, sizeof(float) * 4 * rank, stream>>>(
+      vt_final, nv, w.sorted, k, w.scal, d, rank, out, metrics);
+  count_launch(1);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+}  // namespace pc
+
+extern "C" {
+
+void pc_fd_options_default(pc_fd_options* opt) {
+  opt->ridge_epsilon = 1e-6f;
+  opt->error_tolerance = 1e-6f;
+  opt->relative_matrix_epsilon = 1;
+  opt->decay = 1.0f;
+  opt->input_is_gram = 0;
+  opt->subspace_iters = 8;
+  opt->oversample = 32;
+  opt->full_eigh_max_dim = 512;
+}
+
+size_t pc_fd_update_workspace_bytes(int batch, int d, int m, int rank, const pc_fd_options* opt) {
+  if (batch <= 0 || d <= 0 || rank <= 0 || !opt) return 0;
+  pc::FdWorkspace w;
+  return pc::fd_carve(&w, nullptr, batch, d, opt->input_is_gram ? d : m, rank,
+                      pc::fd_plan(d, rank, opt), opt->input_is_gram != 0) + 512;
+}
+
+int pc_fd_update_batched(const float* new_grad, const float* prev, const int32_t* ps,
+                         const int32_t* padding_starts, int batch, int d, int m, int rank,
+                         const pc_fd_options* opt, float* out, float* metrics, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(batch >= 0 && d > 0 && rank > 0, "bad fd sizes");
+  if (batch == 0) return PC_OK;
+  PC_REQUIRE(new_grad && prev && ps && opt && out && workspace, "null pointer argument");
+  PC_REQUIRE(rank + 2 < d, "frequent directions needs rank + 2 < d (DS:535-537), got rank=%d d=%d",
+             rank, d);
+  if (opt->input_is_gram) m = d;
+  PC_REQUIRE(m > 0, "factor needs at least one column");
+  PC_REQUIRE(opt->subspace_iters <= 30, "subspace_iters must be <= 30");
+  PC_REQUIRE(opt->full_eigh_max_dim <= pc::kJacMaxN, "full_eigh_max_dim must be <= %d",
+             pc::kJacMaxN);
+  if (d > opt->full_eigh_max_dim)
+    PC_REQUIRE(rank + 1 <= pc::kJacMaxN, "rank + 1 must be <= %d for the subspace path",
+               pc::kJacMaxN);
+  return pc::run_fd_update(new_grad, prev, ps, padding_starts, batch, d, m, rank, opt, out, metrics,
+                           workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -5,6 +5,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "root_common.cuh"
@@ -406,11 +408,23 @@ static int pick_cluster_size(int batch) {
 int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n,
                         int num_iters, float tol, float* lambdas, int32_t* iters,
                         RootCtl* ctl, float* v0_dev, float* ybuf, cudaStream_t stream) {
-  std::vector<float> v0(n);
-  mt19937_uniform(1729u, n, v0.data());
-  PC_CUDA_CHECK(cudaMemcpyAsync(v0_dev, v0.data(), sizeof(float) * n,
-                                cudaMemcpyHostToDevice, stream));
-  PC_CUDA_CHECK(cudaStreamSynchronize(stream));  // v0 is a heap temporary
+  // the start vector lives in pinned memory that is never freed, so the upload needs
+  // no host synchronisation (one buffer per size, built once)
+  static std::mutex v0_mu;
+  static std::map<int, float*> v0_cache;
+  float* v0 = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(v0_mu);
+    auto it = v0_cache.find(n);
+    if (it == v0_cache.end()) {
+      PC_CUDA_CHECK(cudaMallocHost(&v0, sizeof(float) * n));
+      mt19937_uniform(1729u, n, v0);
+      v0_cache[n] = v0;
+    } else {
+      v0 = it->second;
+    }
+  }
+  PC_CUDA_CHECK(cudaMemcpyAsync(v0_dev, v0, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
   const size_t smem = sizeof(float) * 2 * (size_t)n;
   if (smem > 48 * 1024) {
     PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_kernel,
@@ -468,15 +482,33 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
   ws.ybuf = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * 2 * (size_t)batch * n, 256);
   ws.engine_mem = w;
 
-  // exponents decide how many GEMM launches one Newton iteration needs
-  std::vector<int32_t> hps(batch);
-  PC_CUDA_CHECK(cudaMemcpyAsync(hps.data(), ps, sizeof(int32_t) * batch,
-                                cudaMemcpyDeviceToHost, stream));
-  PC_CUDA_CHECK(cudaStreamSynchronize(stream));
-  int max_steps = 1;
-  for (int b = 0; b < batch; ++b)
-    if (hps[b] >= 1 && hps[b] <= kMaxP)
-      max_steps = h_programs[hps[b]].nsteps > max_steps ? h_programs[hps[b]].nsteps : max_steps;
+  // Per-host-thread pinned scratch: exponents (decide how many GEMM launches one Newton
+  // iteration needs) and a ring of poll slots for the device-side "unfinished" counter.
+  constexpr int kPollRing = 4, kPollLag = 2;
+  struct HostScratch {
+    int32_t* ps = nullptr;
+    int ps_cap = 0;
+    int* poll = nullptr;
+    cudaEvent_t ev[kPollRing] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ps_ev = nullptr;
+  };
+  static thread_local HostScratch hsx;
+  if (!hsx.poll) {
+    PC_CUDA_CHECK(cudaMallocHost(&hsx.poll, sizeof(int) * kPollRing));
+    for (int i = 0; i < kPollRing; ++i)
+      PC_CUDA_CHECK(cudaEventCreateWithFlags(&hsx.ev[i], cudaEventDisableTiming));
+    PC_CUDA_CHECK(cudaEventCreateWithFlags(&hsx.ps_ev, cudaEventDisableTiming));
+  }
+  if (hsx.ps_cap < batch) {
+    if (hsx.ps) cudaFreeHost(hsx.ps);
+    PC_CUDA_CHECK(cudaMallocHost(&hsx.ps, sizeof(int32_t) * batch));
+    hsx.ps_cap = batch;
+  }
+  int32_t* hps = hsx.ps;
+  // the copy is queued BEFORE the power iteration and waited for after it has been
+  // launched, so the host round trip hides behind that kernel
+  PC_CUDA_CHECK(cudaMemcpyAsync(hps, ps, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, stream));
+  PC_CUDA_CHECK(cudaEventRecord(hsx.ps_ev, stream));
 
   RootParams prm{opt->ridge_epsilon, opt->error_tolerance, opt->num_iters,
                  opt->relative_matrix_epsilon};
@@ -488,6 +520,11 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
                              ws.v0, ws.ybuf, stream);  // DS:820-825
     if (rc != PC_OK) return rc;
   }
+  PC_CUDA_CHECK(cudaEventSynchronize(hsx.ps_ev));
+  int max_steps = 1;
+  for (int b = 0; b < batch; ++b)
+    if (hps[b] >= 1 && hps[b] <= kMaxP)
+      max_steps = h_programs[hps[b]].nsteps > max_steps ? h_programs[hps[b]].nsteps : max_steps;
 
   F32Store f32;
   TcEngine tc;
@@ -501,13 +538,22 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
     if (rc != PC_OK) return rc;
   }
 
-  static thread_local int* h_unfinished = nullptr;  // pinned poll slot, one per host thread
-  if (!h_unfinished) PC_CUDA_CHECK(cudaMallocHost(&h_unfinished, sizeof(int)));
-  *h_unfinished = 1;
+  // Convergence is polled kPollLag iterations behind the launches: the host never waits
+  // for the iteration it has just enqueued, so the device queue stays non-empty.  The
+  // (at most kPollLag) surplus iterations find no active matrix and return at once.
   const int tiles = (n + kSimtBM - 1) / kSimtBM;
   const int max_total = opt->num_iters * 6 + 8;
-  int since_check = 0, check_every = 6;
-  for (int it = 0; it < max_total; ++it) {
+  for (int it = 0; it < max_total + kPollLag; ++it) {
+    if (it >= kPollLag) {
+      const int slot = (it - kPollLag) % kPollRing;
+      cudaError_t e = cudaEventSynchronize(hsx.ev[slot]);
+      if (e != cudaSuccess) {
+        set_error("root iteration failed: %s", cudaGetErrorString(e));
+        return PC_ERR_CUDA;
+      }
+      if (hsx.poll[slot] == 0) break;
+    }
+    if (it >= max_total) continue;
     if (engine == PC_ENGINE_SIMT_FP32) {
       root_init_kernel<F32Store><<<batch, n >= 512 ? 1024 : 256, 0, stream>>>(
           xs, ws.ctl, f32, batch, n, prm, roots);
@@ -533,18 +579,9 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
     cudaMemsetAsync(ws.unfinished, 0, sizeof(int), stream);
     root_control_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(ws.ctl, ws.errbits, batch,
                                                                 prm, ws.unfinished);
-    if (++since_check >= check_every) {
-      since_check = 0;
-      check_every = 2;
-      cudaMemcpyAsync(h_unfinished, ws.unfinished, sizeof(int), cudaMemcpyDeviceToHost,
-                      stream);
-      cudaError_t e = cudaStreamSynchronize(stream);
-      if (e != cudaSuccess) {
-        set_error("root iteration failed: %s", cudaGetErrorString(e));
-        return PC_ERR_CUDA;
-      }
-      if (*h_unfinished == 0) break;
-    }
+    const int slot = it % kPollRing;
+    cudaMemcpyAsync(hsx.poll + slot, ws.unfinished, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    cudaEventRecord(hsx.ev[slot], stream);
   }
   dim3 fgrid((unsigned)std::min<size_t>(((size_t)n * n + 255) / 256, 64), batch);
   if (engine == PC_ENGINE_SIMT_FP32) {

@@ -87,6 +87,55 @@ def matrix_inverse_pth_root_batched(
   return roots, metrics
 
 
+def fd_update_root_batched(
+    new_grad: torch.Tensor, prev: torch.Tensor, ps, rank: int, padding_starts=None,
+    ridge_epsilon: float = 1e-6, error_tolerance: float = 1e-6,
+    relative_matrix_epsilon: bool = True, decay: float = 1.0, input_is_gram: bool = False,
+    subspace_iters: Optional[int] = None, oversample: Optional[int] = None,
+    full_eigh_max_dim: Optional[int] = None,
+    out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Batched Sketchy / frequent-directions step, ``_fd_update_root`` (DS:1123-1290).
+
+  new_grad [b, d, m]: a factor F with F F^T = x x^T (the reference's QR factor has m = d),
+  or with ``input_is_gram`` the covariance x x^T [b, d, d].  prev / result: packed sketches
+  [b, d, rank + 2].  Returns (packed, metrics [b, 5])."""
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(new_grad, prev)
+  assert new_grad.dtype == torch.float32 and new_grad.dim() == 3
+  assert prev.dtype == torch.float32 and prev.dim() == 3 and prev.shape[2] == rank + 2
+  b, d, m = new_grad.shape
+  assert prev.shape[0] == b and prev.shape[1] == d
+  dev = new_grad.device
+  ps_t = torch.as_tensor(ps, dtype=torch.int32).to(dev).contiguous()
+  pads_t = None
+  if padding_starts is not None:
+    pads_t = torch.as_tensor(padding_starts, dtype=torch.int32).to(dev).contiguous()
+  res = out if out is not None else torch.empty_like(prev)
+  metrics = torch.empty((b, _lib.PC_NUM_METRICS), dtype=torch.float32, device=dev)
+  if b == 0:
+    return res, metrics
+  opt = _lib.FdOptions()
+  lib.pc_fd_options_default(ctypes.byref(opt))
+  opt.ridge_epsilon, opt.error_tolerance = ridge_epsilon, error_tolerance
+  opt.relative_matrix_epsilon, opt.decay = int(relative_matrix_epsilon), decay
+  opt.input_is_gram = int(input_is_gram)
+  if subspace_iters is not None:
+    opt.subspace_iters = subspace_iters
+  if oversample is not None:
+    opt.oversample = oversample
+  if full_eigh_max_dim is not None:
+    opt.full_eigh_max_dim = full_eigh_max_dim
+  nbytes = lib.pc_fd_update_workspace_bytes(b, d, m, rank, ctypes.byref(opt))
+  ws = _workspace(nbytes, dev)
+  with torch.cuda.device(dev):
+    _lib.check(lib.pc_fd_update_batched(
+        _ptr(new_grad), _ptr(prev), _ptr(ps_t), _ptr(pads_t), b, d, m, rank, ctypes.byref(opt),
+        _ptr(res), _ptr(metrics), _ptr(ws), ws.numel(), ctypes.c_void_p(_stream())))
+  gpu_launches += 1
+  return res, metrics
+
+
 def debug_tc_gemm(a: torch.Tensor, b: torch.Tensor, passes: int = 6) -> torch.Tensor:
   """Test hook: C = A @ B^T on the tcgen05 split-bf16 engine ([batch, n, n] fp32)."""
   lib = _lib.load()
