@@ -209,6 +209,16 @@ int pc_fd_update_batched(const float* new_grad, const float* prev, const int32_t
                          const pc_fd_options* opt, float* out, float* metrics, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Dense form of the operator a packed low-rank preconditioner applies in
+ * _precondition_block (DS:1690-1705, _low_rank_unpack DS:540-545):
+ *   dense[b] = c I + V diag(lambda^- - c) V^T   (identity if the has_zeros flag is set),
+ * so that g -> c (g - g V V^T) + (g V lambda^-) V^T is one product g * dense[b] and the
+ * low-rank blocks go through the same grouped GEMM as the full ones.
+ *   packed [batch, d, rank+2] f32 -> dense [batch, d, d] f32 */
+size_t pc_low_rank_to_dense_workspace_bytes(int batch, int d, int rank);
+int pc_low_rank_to_dense(const float* packed, int batch, int d, int rank, float* dense,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------
  * (1b) QuantizedValue (QU:49-113) for square statistics / preconditioners with
  *      extract_diagonal=True (DS:2087-2095) and for momenta (DS:2111-2114).

@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "pc_quantize_batched", "pc_dequantize_batched",
     "pc_graft_momentum_workspace_bytes", "pc_graft_momentum",
     "pc_fd_options_default", "pc_fd_update_workspace_bytes", "pc_fd_update_batched",
+    "pc_low_rank_to_dense_workspace_bytes", "pc_low_rank_to_dense",
 )
 
 
@@ -138,6 +139,10 @@ def load() -> ctypes.CDLL:
   lib.pc_fd_update_batched.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32,
                                        ctypes.POINTER(FdOptions), vp, vp, vp, sz, vp]
   lib.pc_fd_update_batched.restype = i32
+  lib.pc_low_rank_to_dense_workspace_bytes.argtypes = [i32, i32, i32]
+  lib.pc_low_rank_to_dense_workspace_bytes.restype = sz
+  lib.pc_low_rank_to_dense.argtypes = [vp, i32, i32, i32, vp, vp, sz, vp]
+  lib.pc_low_rank_to_dense.restype = i32
   _lib = lib
   return lib
 

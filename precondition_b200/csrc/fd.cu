@@ -336,14 +336,20 @@ fd_finalize_kernel(const float* __restrict__ vt_all, int nv, const float* __rest
   if (threadIdx.x == 0) has_zero_flag = 0;
   __syncthreads();
   const float alpha = -1.0f / (float)s.p;
-  const float cutoff = sqrtf(fmaxf(theta[r], 0.f));  // s[rank], DS:1195
+  // Eigenvalues of the fp32 covariance carry absolute noise ~ eps * sqrt(d) * theta_0, where
+  // LAPACK's SVD of the stacked factor returns (near-)exact zeros for a rank-deficient
+  // update.  Values under that floor are treated as the zeros they stand for, so the
+  // has_zeros / skip logic (DS:1209-1251) fires like it does in the reference.
+  const float floor_ev = 4.0f * 1.1920929e-7f * sqrtf((float)d) * fmaxf(theta[0], 0.f);
+  auto ev = [&](int j) { const float t = theta[j]; return t > floor_ev ? t : 0.f; };
+  const float cutoff = sqrtf(ev(r));  // s[rank], DS:1195
   const float rho = cutoff * cutoff;
   float new_tail = s.tail_decayed + rho;             // DS:1202
   const float new_const = new_tail <= 0.f ? 0.f : powf(new_tail, alpha);  // DS:1205
   new_tail = new_tail <= 0.f ? 0.f : new_tail;
   // one warp per direction: deflation, norm / padding safety (DS:1199-1246)
   for (int j = warp; j < r; j += nwarp) {
-    const float top = sqrtf(fmaxf(theta[j], 0.f));
+    const float top = sqrtf(ev(j));
     float defl = (top - cutoff) * (top + cutoff);    // DS:1199
     defl = defl <= 0.f ? 0.f : defl;                 // DS:1209
     float ss = 0.f, padmass = 0.f;
@@ -607,9 +613,73 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
   return PC_OK;
 }
 
+// ---------------------------------------------------------------------------
+// packed low-rank preconditioner -> the dense operator it applies (DS:1690-1705):
+//   g -> c (g - g V V^T) + (g V lambda^-) V^T  ==  g (c I + V diag(lambda^- - c) V^T),
+// identity when has_zeros is set (the reference bypasses the block then).
+// ---------------------------------------------------------------------------
+__global__ void fd_lowrank_scale_kernel(const float* __restrict__ packed, int d, int r,
+                                        float* __restrict__ ws) {
+  const int b = blockIdx.y, pd = r + 2;
+  const float* P = packed + (size_t)b * d * pd;
+  const float c = P[r + 1];
+  const bool skip = P[(size_t)(d - 1) * pd + r] != 0.f;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)d * r;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / r), j = (int)(e - (size_t)i * r);
+    ws[(size_t)b * d * r + e] = skip ? 0.f : P[(size_t)i * pd + j] * (P[(size_t)j * pd + r] - c);
+  }
+}
+__global__ void fd_add_diag_kernel(const float* __restrict__ packed, int d, int r,
+                                   float* __restrict__ dense) {
+  const int b = blockIdx.y, pd = r + 2;
+  const float* P = packed + (size_t)b * d * pd;
+  const bool skip = P[(size_t)(d - 1) * pd + r] != 0.f;
+  const float c = skip ? 1.0f : P[r + 1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d; i += gridDim.x * blockDim.x)
+    dense[((size_t)b * d + i) * d + i] += c;
+}
+
+int run_low_rank_to_dense(const float* packed, int batch, int d, int rank, float* dense,
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const size_t need = (size_t)batch * d * rank * sizeof(float) + 256;
+  if (workspace_bytes < need) {
+    set_error("low-rank workspace too small: %zu < %zu", workspace_bytes, need);
+    return PC_ERR_WORKSPACE;
+  }
+  float* ws = reinterpret_cast<float*>(align_up((size_t)workspace, 256));
+  const unsigned grid = (unsigned)std::min<size_t>(((size_t)d * rank + 255) / 256, 512);
+  fd_lowrank_scale_kernel<<<dim3(grid, batch), 256, 0, stream>>>(packed, d, rank, ws);
+  FdGemm g{};
+  g.alpha = 1.f;
+  g.a = ws; g.b = packed; g.c = dense;
+  g.a_bs = (int64_t)d * rank; g.b_bs = (int64_t)d * (rank + 2); g.c_bs = (int64_t)d * d;
+  g.a_si = rank; g.a_sk = 1; g.b_sj = rank + 2; g.b_sk = 1; g.c_si = d;
+  g.m = g.n = d; g.k = rank;
+  fd_gemm(g, batch, stream);
+  fd_add_diag_kernel<<<dim3((d + 255) / 256, batch), 256, 0, stream>>>(packed, d, rank, dense);
+  count_launch(2);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
 }  // namespace pc
 
 extern "C" {
+
+size_t pc_low_rank_to_dense_workspace_bytes(int batch, int d, int rank) {
+  if (batch <= 0 || d <= 0 || rank <= 0) return 0;
+  return (size_t)batch * d * rank * sizeof(float) + 512;
+}
+
+int pc_low_rank_to_dense(const float* packed, int batch, int d, int rank, float* dense,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(batch >= 0 && d > 0 && rank > 0 && rank + 2 < d, "bad low-rank sizes");
+  if (batch == 0) return PC_OK;
+  PC_REQUIRE(packed && dense && workspace, "null pointer argument");
+  return pc::run_low_rank_to_dense(packed, batch, d, rank, dense, workspace, workspace_bytes,
+                                   (cudaStream_t)stream);
+}
 
 void pc_fd_options_default(pc_fd_options* opt) {
   opt->ridge_epsilon = 1e-6f;

@@ -345,7 +345,9 @@ class _Shampoo:
                skip_preconditioning_dim_size_gt, clip_by_scaled_gradient_norm,
                relative_matrix_epsilon, merge_small_dims_block_size, precondtioner_type,
                compression_rank, skip_preconditioning_rank_lt, decoupled_learning_rate,
-               decoupled_weight_decay, generate_training_metrics, engine, process_group):
+               decoupled_weight_decay, generate_training_metrics, engine, process_group,
+               frequent_directions=False, reuse_preconditioner=False, reset_frequency=None,
+               average_grad=False):
     self.__dict__.update({k: v for k, v in locals().items() if k != "self"})
     # DS:2051-2064: second-moment quantisation only with a batch axis
     self.quantize_second_moment = bool(best_effort_memory_usage_reduction and
@@ -396,6 +398,11 @@ class _Shampoo:
     self.pgbuf = torch.zeros(total, dtype=torch.float32, device=dev)
     self.t1buf = torch.zeros(total, dtype=torch.float32, device=dev)
     self.t2buf = torch.zeros(total, dtype=torch.float32, device=dev)
+    # Sketchy with average_grad (DS:2640-2645): statistics are taken from the running
+    # gradient sum divided by statistics_compute_steps instead of the raw gradient
+    self.use_avg_grad = bool(self.frequent_directions and self.average_grad)
+    self.agbuf = torch.zeros(total, dtype=torch.float32, device=dev) if self.use_avg_grad else None
+    self.sgbuf = torch.zeros(total, dtype=torch.float32, device=dev) if self.use_avg_grad else None
 
     self.plans, self.buckets = [], {}
     for idx, p in enumerate(leaves):
@@ -434,7 +441,14 @@ class _Shampoo:
     for s, bk in self.buckets.items():
       eye = torch.eye(s, dtype=torch.float32, device=dev)
       bk.stats = (self.matrix_epsilon * eye).repeat(bk.count, 1, 1).contiguous()
-      bk.precs = eye.repeat(bk.count, 1, 1).contiguous()
+      bk.compressed = bk.pdim != s  # DS:535-537: low-rank [s, rank + 2] preconditioners
+      if bk.compressed:
+        # packed sketches start at zero (DS:2598-2602); `precs` holds the dense operator the
+        # packed form applies (pc_low_rank_to_dense) and is what the apply GEMMs read
+        bk.packed = torch.zeros((bk.count, s, bk.pdim), dtype=torch.float32, device=dev)
+        bk.precs = torch.zeros((bk.count, s, s), dtype=torch.float32, device=dev)
+      else:
+        bk.precs = eye.repeat(bk.count, 1, 1).contiguous()
       bk.exps = torch.tensor(bk.exponents, dtype=torch.int32, device=dev)
       bk.roots_tmp = torch.empty_like(bk.stats)
       self.metrics[s] = torch.zeros((bk.count, 5), dtype=torch.float32, device=dev)
@@ -455,7 +469,8 @@ class _Shampoo:
           [self._prec_view(r) for r in plan.stat_refs],
           QuantizedValue.from_float_value(torch.zeros_like(p), mdt),
           QuantizedValue.from_float_value(torch.zeros_like(p), mdt),
-          None,
+          (self.agbuf[plan.offset:plan.offset + plan.numel].view(p.shape)
+           if self.use_avg_grad else None),
           (self, plan.stat_refs) if self.generate_training_metrics else None)
       stats.append(st)
     self._built = True
@@ -475,7 +490,7 @@ class _Shampoo:
     if self.quantize_second_moment:
       q, d, b = bk.qprecs
       return QuantizedValue(q[i], d[i], b[i], self.qdt_second, True, [s, s])
-    return bk.precs[i]
+    return bk.packed[i] if bk.compressed else bk.precs[i]
 
   # ---- static launch lists ------------------------------------------------
   def _build_launch_lists(self, leaves):
@@ -489,6 +504,7 @@ class _Shampoo:
     f32 = 4
     g0, pg0, t10, t20 = (self.gbuf.data_ptr(), self.pgbuf.data_ptr(), self.t1buf.data_ptr(),
                          self.t2buf.data_ptr())
+    sg0 = self.sgbuf.data_ptr() if self.use_avg_grad else g0  # source of the statistics
     for plan in self.plans:
       if plan.skip:
         continue
@@ -509,7 +525,7 @@ class _Shampoo:
           others = [a for a in range(rank) if a != axis]
           k = int(np.prod([sizes[a] for a in others])) if others else 1
           d = D()
-          d.a = d.b = gbase
+          d.a = d.b = sg0 + f32 * base_elem
           d.c = d.c_in = cptr
           d.a_si = d.b_sj = strides[axis]
           d.a_iinner, d.a_sio = sizes[axis], 0
@@ -526,6 +542,11 @@ class _Shampoo:
           d.m = d.n = s
           d.k = k
           d.alpha, d.beta = w2, w1
+          if self.frequent_directions and bk.compressed:
+            # frequent_directions_update (DS:1473-1505) ignores the old statistic and the
+            # weights: R R^T = x x^T.  Only that product enters the sketch update, so the
+            # statistic slot holds x x^T itself (no QR on the device).
+            d.c_in, d.alpha, d.beta = None, 1.0, 0.0
           stat_descs.append(d)
           self._stat_max = [max(self._stat_max[0], s), max(self._stat_max[1], s)]
         # ---- application: contract the leading axis and roll (DS:1678-1707) ----
@@ -600,13 +621,20 @@ class _Shampoo:
     # (0) stage gradients into the flat buffer the static descriptors point at
     for plan, g in zip(self.plans, g_leaves):
       self.gbuf[plan.offset:plan.offset + plan.numel].copy_(g.reshape(-1))
+    if self.use_avg_grad:  # DS:2640-2645
+      k = self.statistics_compute_steps
+      if k == 1 or step % k == 1:
+        self.agbuf.copy_(self.gbuf)
+      else:
+        self.agbuf.add_(self.gbuf)
+      torch.div(self.agbuf, float(k), out=self.sgbuf)
     # (1) statistics (DS:3644 -> DS:2631-2675)
     if self._stat_descs[1] and (self.statistics_compute_steps <= 1 or
                                 step % self.statistics_compute_steps == 0):
       self._update_statistics()
     # (2) preconditioners (DS:3648 -> DS:3442-3494)
     if self.buckets and step % self.preconditioning_compute_steps == 0:
-      self._compute_preconditioners()
+      self._compute_preconditioners(step)
     # (3) transform (DS:3650 -> DS:3496-3625)
     self._apply_preconditioners()
     updates = []
@@ -648,9 +676,13 @@ class _Shampoo:
     dst[0].copy_(q); dst[1].copy_(d); dst[2].copy_(b)  # keep state views alive
     return dst[0], dst[1], dst[2]
 
-  def _compute_preconditioners(self):
+  def _compute_preconditioners(self, step=0):
     world, rank = self._world()
+    if any(bk.compressed for bk in self.buckets.values()):
+      self._fd_update(step, world, rank)
     for s, bk in self.buckets.items():
+      if bk.compressed:
+        continue
       if self.quantize_second_moment:
         q, d, b = bk.qstats
         ops.dequantize(q, d, b, True, out=bk.stats)
@@ -671,6 +703,52 @@ class _Shampoo:
             ctypes.c_void_p(roots.data_ptr()), ctypes.c_void_p(metrics.data_ptr()),
             float(self.inverse_failure_threshold), ctypes.c_void_p(bk.precs.data_ptr()),
             bk.count, s, s, s, s, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+  def _fd_update(self, step, world, rank):
+    """Sketchy branch of new_mi_pth_root (DS:2706-2738) for every compressed statistic.
+
+    The reference runs it in the frame padded to the largest statistic (DS:2841-2843)
+    and slices the packed result back to [size, rank + 2] (DS:2950): for a statistic
+    smaller than that frame the eigenvalue / has_zeros slots that live in the last
+    rows of the padded sketch are cut off.  Mirrored exactly by working in the same
+    padded frame; when every compressed statistic has the frame size (the usual case)
+    the bucket tensors are used in place."""
+    r = abs(self.compression_rank)
+    comp = [bk for _, bk in sorted(self.buckets.items()) if bk.compressed]
+    frame = max(self.buckets)
+    dev = self.device
+    total = sum(bk.count for bk in comp)
+    if len(comp) == 1 and comp[0].size == frame:
+      bk = comp[0]
+      grams, prevs, exps = bk.stats, bk.packed, bk.exps
+      pads = torch.full((total,), frame, dtype=torch.int32, device=dev)
+    else:
+      grams = torch.zeros((total, frame, frame), dtype=torch.float32, device=dev)
+      prevs = torch.zeros((total, frame, r + 2), dtype=torch.float32, device=dev)
+      exps = torch.cat([bk.exps for bk in comp])
+      pads = torch.cat([torch.full((bk.count,), bk.size, dtype=torch.int32, device=dev)
+                        for bk in comp])
+      o = 0
+      for bk in comp:
+        grams[o:o + bk.count, :bk.size, :bk.size] = bk.stats
+        prevs[o:o + bk.count, :bk.size] = bk.packed
+        o += bk.count
+    if self.reset_frequency is not None and step % self.reset_frequency == 0:
+      prevs = torch.zeros_like(prevs)  # DS:2140-2143
+    kw = dict(ridge_epsilon=self.matrix_epsilon,
+              relative_matrix_epsilon=self.relative_matrix_epsilon, decay=float(self.beta2),
+              input_is_gram=True)
+    if world == 1:
+      new, _ = ops.fd_update_root_batched(grams.contiguous(), prevs.contiguous(), exps, r, pads,
+                                          **kw)
+    else:
+      new = sharded_fd_updates(grams, prevs, exps, pads, r, world, rank, self.process_group, **kw)
+    o = 0
+    for bk in comp:
+      bk.packed.copy_(new[o:o + bk.count, :bk.size])
+      o += bk.count
+      ops.low_rank_to_dense(bk.packed, r, out=bk.precs)
+      self.metrics[bk.size].zero_()  # DS:1263-1264: FD reports zero error
 
   def _roots_sharded(self, bk, world, rank):
     kw = dict(ridge_epsilon=self.matrix_epsilon,
@@ -764,6 +842,30 @@ def sharded_inverse_pth_roots(stats, exps, world, rank, group, root_fn=None, pad
   return all_roots[:n_stats], all_metrics[:n_stats]
 
 
+def sharded_fd_updates(grams, prevs, exps, pads, r, world, rank, group, fd_fn=None, **kw):
+  """Block-sharded Sketchy updates + all-gather: the same contiguous partition and filler
+  rule as the roots (DS:2844-2850, DS:2862-2877); fillers are (zero, exponent 1, padding 0)
+  and produce all-zero sketches (DS:1265-1268)."""
+  import torch.distributed as dist
+  fd_fn = fd_fn or ops.fd_update_root_batched
+  n_stats, d = grams.shape[0], grams.shape[1]
+  b = (n_stats + (-n_stats % world)) // world
+  lo, hi = rank * b, min((rank + 1) * b, n_stats)
+  local_g = torch.zeros((b, d, d), dtype=grams.dtype, device=grams.device)
+  local_p = torch.zeros((b, d, r + 2), dtype=prevs.dtype, device=grams.device)
+  local_e = torch.ones(b, dtype=torch.int32, device=grams.device)
+  local_pad = torch.zeros(b, dtype=torch.int32, device=grams.device)
+  if hi > lo:
+    local_g[:hi - lo] = grams[lo:hi]
+    local_p[:hi - lo] = prevs[lo:hi]
+    local_e[:hi - lo] = exps[lo:hi]
+    local_pad[:hi - lo] = pads[lo:hi]
+  new, _ = fd_fn(local_g, local_p, local_e, r, local_pad, **kw)
+  gathered = torch.empty((world * b, d, r + 2), dtype=new.dtype, device=new.device)
+  dist.all_gather_into_tensor(gathered, new.contiguous(), group=group)
+  return gathered[:n_stats]
+
+
 def distributed_shampoo(
     learning_rate,
     block_size,
@@ -825,6 +927,10 @@ def distributed_shampoo(
   del preconditioner_partition_spec, num_devices_for_pjit, generate_fd_metrics
   if reset_preconditioner and not frequent_directions:  # DS:2019-2020
     raise ValueError("reset_preconditioner=True requries frequent_directions")
+  reset_frequency = None
+  if reset_preconditioner:  # DS:2022-2024
+    reset_frequency = int(np.round(1 / (1 - beta2))) if beta2 != 1 else None
+    beta2 = 1.0
   if frequent_directions and compression_rank <= 0:  # DS:2028-2030
     raise ValueError("frequent_directions=True requires compression_rank > 0,"
                      f" found {compression_rank}")
@@ -837,15 +943,18 @@ def distributed_shampoo(
                      f"({preconditioning_compute_steps})")
   for name, val in (("lobpcg_topk_precondition", lobpcg_topk_precondition), ("eigh", eigh),
                     ("shard_optimizer_states", shard_optimizer_states),
-                    ("compression_rank", compression_rank),
-                    ("frequent_directions", frequent_directions),
-                    ("reuse_preconditioner", False),
+                    ("compression_rank without frequent_directions (eigh-based "
+                     "_low_rank_root)", compression_rank and not frequent_directions),
                     ("decay_preconditioning_compute_steps",
                      decay_preconditioning_compute_steps and end_preconditioning_compute_steps)):
     if val:
       raise NotImplementedError(
           f"{name} is not built in the B200 hot path yet (see DESIGN.md, out of scope table)")
-  del reuse_preconditioner  # only consumed by the FD branch (DS:764, DS:2855-2860)
+  if frequent_directions and not reuse_preconditioner:
+    # _fd_update_root asserts that the previous sketch is passed in (DS:1150)
+    raise ValueError("frequent_directions=True needs reuse_preconditioner=True")
+  if frequent_directions and best_effort_memory_usage_reduction and batch_axis_name:
+    pass  # DS:2051-2064: no second-moment quantisation with compression_rank != 0
   opt = _Shampoo(learning_rate, block_size, beta1, beta2, diagonal_epsilon, matrix_epsilon,
                  weight_decay, start_preconditioning_step, preconditioning_compute_steps,
                  statistics_compute_steps, best_effort_shape_interpretation,
@@ -855,5 +964,6 @@ def distributed_shampoo(
                  clip_by_scaled_gradient_norm, relative_matrix_epsilon,
                  merge_small_dims_block_size, PreconditionerType(precondtioner_type),
                  compression_rank, skip_preconditioning_rank_lt, decoupled_learning_rate,
-                 decoupled_weight_decay, generate_training_metrics, engine, process_group)
+                 decoupled_weight_decay, generate_training_metrics, engine, process_group,
+                 frequent_directions, reuse_preconditioner, reset_frequency, average_grad)
   return GradientTransformation(opt.init, opt.update)

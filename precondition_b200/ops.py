@@ -136,6 +136,27 @@ def fd_update_root_batched(
   return res, metrics
 
 
+def low_rank_to_dense(packed: torch.Tensor, rank: int,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """Dense operator of packed low-rank preconditioners [b, d, rank+2] -> [b, d, d]
+  (``c I + V diag(lambda^- - c) V^T``; identity when has_zeros), DS:1690-1705."""
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(packed)
+  b, d, pd = packed.shape
+  assert pd == rank + 2 and packed.dtype == torch.float32
+  dense = out if out is not None else torch.empty((b, d, d), dtype=torch.float32,
+                                                  device=packed.device)
+  if b == 0:
+    return dense
+  ws = _workspace(lib.pc_low_rank_to_dense_workspace_bytes(b, d, rank), packed.device)
+  with torch.cuda.device(packed.device):
+    _lib.check(lib.pc_low_rank_to_dense(_ptr(packed), b, d, rank, _ptr(dense), _ptr(ws),
+                                        ws.numel(), ctypes.c_void_p(_stream())))
+  gpu_launches += 1
+  return dense
+
+
 def debug_tc_gemm(a: torch.Tensor, b: torch.Tensor, passes: int = 6) -> torch.Tensor:
   """Test hook: C = A @ B^T on the tcgen05 split-bf16 engine ([batch, n, n] fp32)."""
   lib = _lib.load()

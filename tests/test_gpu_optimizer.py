@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 
 SUPPORTED = ["default", "two_devices", "quantized_int16", "sqrt_n_input",
              "adagrad_norm_output_wd", "rmsprop_clip", "rmsprop_norm_ma", "adagrad_rank3",
-             "abs_eps_beta2_1"]  # "none_noshape" needs rank-4 blocks (not built yet)
+             "abs_eps_beta2_1",  # "none_noshape" needs rank-4 blocks (not built yet)
+             "fd", "fd_avg_reset", "fd_every2"]  # Sketchy / frequent directions
 
 
 def _kw(cfg):
@@ -23,6 +24,15 @@ def _kw(cfg):
   if "precondtioner_type" in kw:
     kw["precondtioner_type"] = DS.PreconditionerType(kw["precondtioner_type"])
   return kw
+
+
+def _sketch_operator(packed, r):
+  from oracle import numerics as N
+  vecs, inv, const, skip = N.low_rank_unpack(packed.astype(np.float64), r)
+  d = packed.shape[0]
+  if skip:
+    return np.eye(d)
+  return const * (np.eye(d) - vecs @ vecs.T) + (vecs * inv) @ vecs.T
 
 
 @pytest.mark.parametrize("name", SUPPORTED)
@@ -46,6 +56,15 @@ def test_trajectory_matches_reference_golden(golden_optimizer, name):
       scale = max(np.abs(want).max(), 1e-12)
       err = np.abs(u.cpu().numpy() - want).max() / scale
       tol = 2e-4 if name != "quantized_int16" else 1.2e-2
+      if name.startswith("fd") and t >= 5:
+        # These parameters merge to vectors, so their first sketch updates are rank
+        # deficient: the reference's third singular value is LAPACK rounding noise (exactly
+        # 0 or ~1e-9, case by case) and decides has_zeros / const = noise^(-2/p) there.
+        # That noise sits in the Shampoo momentum once preconditioning starts, so only
+        # finiteness is comparable here; the sketches themselves are compared below and
+        # full-rank trajectories in test_sketchy_full_rank_blocks_match_oracle.
+        assert np.all(np.isfinite(u.cpu().numpy())), f"{name} step {t} param {i}"
+        continue
       assert err <= tol, f"{name} step {t} param {i}: {err}"
   assert state.count == OPT_STEPS
   # final preconditioners and metrics
@@ -53,6 +72,16 @@ def test_trajectory_matches_reference_golden(golden_optimizer, name):
     for k, pc in enumerate(st.preconditioners):
       pc = pc.to_float() if hasattr(pc, "to_float") else pc
       want = g[f"{name}/final_precond/{i}/{k}"]
+      if want.shape[0] != want.shape[1]:
+        # packed sketch: eigenvectors are defined up to sign -> compare the operator the
+        # sketch applies (DS:1690-1705) and the scalar slots
+        r = want.shape[1] - 2
+        got = pc.cpu().numpy()
+        np.testing.assert_allclose(got[:, r:], want[:, r:], rtol=2e-3,
+                                   atol=2e-3 * max(np.abs(want[:, r:]).max(), 1e-12))
+        og, ow = _sketch_operator(got, r), _sketch_operator(want, r)
+        assert np.abs(og - ow).max() <= 2e-3 * max(np.abs(ow).max(), 1e-12), (name, i, k)
+        continue
       err = np.abs(pc.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-12)
       assert err <= (5e-3 if name == "quantized_int16" else 1e-3), (name, i, k, err)
     tm = st.training_metrics
@@ -115,6 +144,40 @@ def test_blocked_mlp_matches_oracle():
       np.testing.assert_allclose(a.cpu().numpy(), b, rtol=1e-4, atol=1e-9)
 
 
+@pytest.mark.parametrize("extra", [{}, {"average_grad": True, "statistics_compute_steps": 2,
+                                        "preconditioning_compute_steps": 2},
+                                   {"reset_preconditioner": True, "beta2": 0.75}])
+def test_sketchy_full_rank_blocks_match_oracle(extra):
+  """Sketchy branch end to end (frequent_directions, compression_rank, reuse_preconditioner;
+  DS:2706-2738, DS:1690-1705) on 2-D parameters whose 8 x 8 blocks have full-rank
+  gradients, so every singular value the update uses is well above rounding noise."""
+  from precondition_b200 import distributed_shampoo as DS
+  rng = np.random.default_rng(3)
+  shapes = [(16, 16), (8, 24)]
+  params = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+  kw = dict(compression_rank=2, frequent_directions=True, reuse_preconditioner=True,
+            merge_small_dims_block_size=8, start_preconditioning_step=2, **extra)
+  oracle = O.distributed_shampoo(0.1, 8, **kw)
+  ostate = oracle.init(params)
+  opt = DS.distributed_shampoo(0.1, 8, **kw)
+  tparams = [torch.as_tensor(p).cuda() for p in params]
+  state = opt.init(tparams)
+  for t in range(8):
+    grads = [(rng.standard_normal(s) * 0.1).astype(np.float32) for s in shapes]
+    want, ostate = oracle.update(grads, ostate, params)
+    got, state = opt.update([torch.as_tensor(x).cuda() for x in grads], state, tparams)
+    torch.cuda.synchronize()
+    for i, (u, w) in enumerate(zip(got, want)):
+      err = np.abs(u.cpu().numpy() - w).max() / max(np.abs(w).max(), 1e-12)
+      assert err <= 5e-4, (extra, t, i, err)
+  for st, ost in zip(state.stats, ostate.stats):
+    for pa, pb in zip(st.preconditioners, ost.preconditioners):
+      og, ow = _sketch_operator(pa.cpu().numpy(), 2), _sketch_operator(pb, 2)
+      assert np.abs(og - ow).max() <= 1e-3 * np.abs(ow).max()
+    for a, b in zip(st.statistics, ost.statistics):  # x x^T here, its QR factor upstream
+      np.testing.assert_allclose(a.cpu().numpy(), b @ b.T, rtol=1e-4, atol=1e-8)
+
+
 def test_pytree_structure_and_errors():
   from precondition_b200 import distributed_shampoo as DS
   params = {"w": torch.randn(16, 8).cuda(), "b": (torch.randn(8).cuda(),)}
@@ -128,5 +191,9 @@ def test_pytree_structure_and_errors():
     DS.distributed_shampoo(0.1, 8, reset_preconditioner=True)
   with pytest.raises(ValueError):
     DS.distributed_shampoo(0.1, 8, frequent_directions=True)
+  with pytest.raises(ValueError):  # the sketch update needs the previous sketch (DS:1150)
+    DS.distributed_shampoo(0.1, 8, frequent_directions=True, compression_rank=2)
+  with pytest.raises(NotImplementedError):  # eigh-based _low_rank_root: SURVEY 8(f)
+    DS.distributed_shampoo(0.1, 8, compression_rank=3)
   with pytest.raises(RuntimeError):
     DS.distributed_shampoo(0.1, 8).init([torch.zeros(4, 4)])  # CPU tensor: no fallback

@@ -43,12 +43,36 @@ def _worker(rank, world, port, n_stats, out):
   dist.destroy_process_group()
 
 
-def _run(world, n_stats):
+def _fake_fd(grams, prevs, exps, r, pads, **kw):
+  """Stand-in for the sketch update: fillers (padding 0) give zeros (DS:1265-1268)."""
+  new = (prevs + grams[:, :, :r + 2] * exps.float()[:, None, None]) * (pads > 0)[:, None, None]
+  return new, torch.zeros((len(exps), 5))
+
+
+def _fd_worker(rank, world, port, n_stats, out):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from precondition_b200.distributed_shampoo import sharded_fd_updates
+  g = torch.Generator().manual_seed(1)
+  d, r = 6, 2
+  grams = torch.randn((n_stats, d, d), generator=g)
+  prevs = torch.randn((n_stats, d, r + 2), generator=g)
+  exps = torch.arange(1, n_stats + 1, dtype=torch.int32)
+  pads = torch.full((n_stats,), d, dtype=torch.int32)
+  new = sharded_fd_updates(grams, prevs, exps, pads, r, world, rank, None, fd_fn=_fake_fd)
+  want = prevs + grams[:, :, :r + 2] * exps.float()[:, None, None]
+  out[rank] = bool(torch.equal(new, want) and new.shape[0] == n_stats)
+  dist.destroy_process_group()
+
+
+def _run(world, n_stats, worker=None):
+  worker = worker or _worker
   port = _free_port()
   ctx = mp.get_context("spawn")
   with ctx.Manager() as mgr:
     out = mgr.dict()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_stats, out))
+    procs = [ctx.Process(target=worker, args=(r, world, port, n_stats, out))
              for r in range(world)]
     [p.start() for p in procs]
     [p.join(120) for p in procs]
@@ -66,3 +90,8 @@ def test_two_ranks_even_count():
 
 def test_more_ranks_than_statistics():
   _run(3, 2)
+
+
+def test_sketch_updates_two_ranks_uneven_count():
+  """Same partition / filler / gather logic around the Sketchy update (DS:2706-2738)."""
+  _run(2, 3, _fd_worker)
