@@ -295,6 +295,154 @@ __device__ __forceinline__ uint32_t stage_addr(uint32_t base, int r, int ch) {
 }
 
 // ---------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): one cluster of two CTAs owns a 256 x 128 output
+// tile.  CTA r holds A rows [r*128, r*128+128) and half of B's rows
+// [r*64, r*64+64); the leader's single thread issues tcgen05.mma.cta_group::2
+// (M = 256, N = 128) that reads both CTAs' shared memory.  Per SM this loads
+// 72 KB per k-block instead of 96 KB and leaves room for a third stage.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-pair bit of a smem address
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t"
+      "}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+// both CTAs issue; the transaction bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_tile_2sm(uint32_t dst, const CUtensorMap* map,
+                                                  uint32_t bar, int tile_col, int tile_row,
+                                                  int mat) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(0), "r"(0),
+      "r"(tile_col), "r"(tile_row), "r"(mat)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_scaled_d_2sm(uint32_t tmem_d, uint64_t adesc,
+                                                      uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, "
+      "p, 11;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u),
+      "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// arrive (once the MMAs retire) on the same-offset barrier of BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+constexpr uint32_t kIdescBf16M256N256 =
+    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t kIdescF16M256N256 =
+    (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+
+// ---------------------------------------------------------------------------
+// MMA issue helpers shared by the 1-CTA and the CTA-pair kernels.  One "k-block" is a
+// 64-column slab: kLP plane tiles of A at a0 and of B at b0 (K-major, SWIZZLE_128B).
+// ---------------------------------------------------------------------------
+template <bool k2sm>
+__device__ __forceinline__ void umma_any(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc,
+                                         uint32_t acc) {
+  if (k2sm) umma_bf16_2sm(d, a, b, idesc, acc);
+  else umma_bf16(d, a, b, idesc, acc);
+}
+// scaled fp16 planes, cross terms of one k-block: D (+)= A0 B1 + A1 B0   (both x 2^11)
+template <bool k2sm>
+__device__ __forceinline__ void issue_fp16_cross(uint32_t d, uint32_t a0, uint32_t b0,
+                                                 uint32_t idesc, bool first) {
+  const uint64_t a0d = make_kmajor_sw128_desc(a0), a1d = make_kmajor_sw128_desc(a0 + TC_TILE_BYTES);
+  const uint64_t b0d = make_kmajor_sw128_desc(b0), b1d = make_kmajor_sw128_desc(b0 + TC_TILE_BYTES);
+#pragma unroll
+  for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+    umma_any<k2sm>(d, a0d + 2u * k, b1d + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+  for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+    umma_any<k2sm>(d, a1d + 2u * k, b0d + 2u * k, idesc, 1u);
+}
+// leading term of one k-block: D += A0 B0; with `rescale` the first MMA applies
+// scale-input-d = 11, i.e. D = A0 B0 + D * 2^-11 (all cross terms of the chunk are in D)
+template <bool k2sm>
+__device__ __forceinline__ void issue_fp16_main(uint32_t d, uint32_t a0, uint32_t b0,
+                                                uint32_t idesc, bool rescale) {
+  const uint64_t a0d = make_kmajor_sw128_desc(a0), b0d = make_kmajor_sw128_desc(b0);
+  if (rescale) {
+    if (k2sm) umma_f16_scaled_d_2sm(d, a0d, b0d, idesc);
+    else umma_f16_scaled_d(d, a0d, b0d, idesc);
+  } else {
+    umma_any<k2sm>(d, a0d, b0d, idesc, 1u);
+  }
+#pragma unroll
+  for (int k = 1; k < TC_BK / TC_UMMA_K; ++k)
+    umma_any<k2sm>(d, a0d + 2u * k, b0d + 2u * k, idesc, 1u);
+}
+// bf16 planes, all products i + j <= kLP - 1 of one k-block, smallest terms first
+template <int kLP, bool k2sm>
+__device__ __forceinline__ void issue_bf16_block(uint32_t d, uint32_t a0, uint32_t b0,
+                                                 uint32_t idesc, bool first_in) {
+  bool first = first_in;
+#pragma unroll
+  for (int sum = kLP - 1; sum >= 0; --sum) {
+#pragma unroll
+    for (int i = 0; i <= sum; ++i) {
+      const int j = sum - i;
+      const uint64_t ad = make_kmajor_sw128_desc(a0 + i * TC_TILE_BYTES);
+      const uint64_t bd = make_kmajor_sw128_desc(b0 + j * TC_TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+        umma_any<k2sm>(d, ad + 2u * k, bd + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+        if (k == 0) first = false;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Warp-specialised 1-CTA kernel with dedicated epilogue warpgroups (512 threads):
 //   warpgroup 0  warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator
 //   warpgroup 1  chunk accumulation: pulls every K-chunk from TMEM, adds it to fp32
@@ -540,7 +688,7 @@ __device__ __forceinline__ void tc_epilogue_tile_tmem(const TcParams& P, const T
   }
 }
 
-template <int kLP, int kStages, int kFmt>
+template <int kLP, int kStages, int kFmt, int kChunkKB>
 __global__ void __launch_bounds__(TC_WS_THREADS, 1)
 tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
                    const __grid_constant__ CUtensorMap tmap1,
@@ -629,49 +777,43 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
         TcWork wk;
         if (!tc_get_work(P, progs, s, w, wk)) continue;
 #pragma unroll 1
-        for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+        for (int kb = 0; kb < wk.kblocks; kb += kChunkKB, ++chunk) {
+          const int nkb = min(kChunkKB, wk.kblocks - kb);
           const int acc = chunk & 1;
           mbar_wait(tempty_bar(acc), ((chunk >> 1) & 1) ^ 1);
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
           const uint32_t tmem_d = tmem_base + acc * TC_BN;
-          const uint32_t a0 = smem_base + stage * kStageBytes;
-          const uint32_t b0 = a0 + kLP * TC_TILE_BYTES;
+          constexpr uint32_t idesc = kFmt == TC_FMT_FP16S ? kIdescF16M128N128 : kIdescBf16M128N128;
+          int st[kChunkKB];
+          // phase 1 (per k-block, as its operands land): cross terms / all bf16 products
+#pragma unroll
+          for (int j = 0; j < kChunkKB; ++j) {
+            if (j < nkb) {
+              st[j] = stage;
+              mbar_wait(full_bar(stage), phase);
+              tcgen05_fence_after();
+              const uint32_t a0 = smem_base + stage * kStageBytes;
+              const uint32_t b0 = a0 + kLP * TC_TILE_BYTES;
+              if (kFmt == TC_FMT_FP16S) {
+                issue_fp16_cross<false>(tmem_d, a0, b0, idesc, j == 0);
+              } else {
+                issue_bf16_block<kLP, false>(tmem_d, a0, b0, idesc, j == 0);
+                umma_commit(empty_bar(stage));
+              }
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          // phase 2 (scaled fp16 only): D = A0 B0 + D * 2^-11, then the other leading terms
           if (kFmt == TC_FMT_FP16S) {
-            // D = A0 B1 + A1 B0 (both x 2^11), then D = A0 B0 + D * 2^-11
-            const uint64_t a0d = make_kmajor_sw128_desc(a0), a1d = make_kmajor_sw128_desc(a0 + TC_TILE_BYTES);
-            const uint64_t b0d = make_kmajor_sw128_desc(b0), b1d = make_kmajor_sw128_desc(b0 + TC_TILE_BYTES);
 #pragma unroll
-            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
-              umma_bf16(tmem_d, a0d + 2u * k, b1d + 2u * k, kIdescF16M128N128, k == 0 ? 0u : 1u);
-#pragma unroll
-            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
-              umma_bf16(tmem_d, a1d + 2u * k, b0d + 2u * k, kIdescF16M128N128, 1u);
-            umma_f16_scaled_d(tmem_d, a0d, b0d, kIdescF16M128N128);
-#pragma unroll
-            for (int k = 1; k < TC_BK / TC_UMMA_K; ++k)
-              umma_bf16(tmem_d, a0d + 2u * k, b0d + 2u * k, kIdescF16M128N128, 1u);
-          } else {
-          bool first = true;
-#pragma unroll
-          for (int sum = kLP - 1; sum >= 0; --sum) {
-#pragma unroll
-            for (int i = 0; i <= sum; ++i) {
-              const int j = sum - i;
-              const uint64_t ad = make_kmajor_sw128_desc(a0 + i * TC_TILE_BYTES);
-              const uint64_t bd = make_kmajor_sw128_desc(b0 + j * TC_TILE_BYTES);
-#pragma unroll
-              for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                umma_bf16(tmem_d, ad + 2u * k, bd + 2u * k, kIdescBf16M128N128,
-                          (first && k == 0) ? 0u : 1u);
-                if (k == 0) first = false;
+            for (int j = 0; j < kChunkKB; ++j) {
+              if (j < nkb) {
+                const uint32_t a0 = smem_base + st[j] * kStageBytes;
+                issue_fp16_main<false>(tmem_d, a0, a0 + kLP * TC_TILE_BYTES, idesc, j == 0);
+                umma_commit(empty_bar(st[j]));
               }
             }
           }
-          }
-          umma_commit(empty_bar(stage));
           umma_commit(tfull_bar(acc));
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -689,7 +831,7 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
 #pragma unroll
       for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
 #pragma unroll 1
-      for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+      for (int kb = 0; kb < wk.kblocks; kb += kChunkKB, ++chunk) {
         const int acc = chunk & 1;
         mbar_wait(tfull_bar(acc), (chunk >> 1) & 1);
         tcgen05_fence_after();
@@ -754,88 +896,6 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
 }
 
 // ---------------------------------------------------------------------------
-// CTA-pair kernel (cta_group::2): one cluster of two CTAs owns a 256 x 128 output
-// tile.  CTA r holds A rows [r*128, r*128+128) and half of B's rows
-// [r*64, r*64+64); the leader's single thread issues tcgen05.mma.cta_group::2
-// (M = 256, N = 128) that reads both CTAs' shared memory.  Per SM this loads
-// 72 KB per k-block instead of 96 KB and leaves room for a third stage.
-// ---------------------------------------------------------------------------
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-pair bit of a smem address
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
-  asm volatile(
-      "{\n\t"
-      ".reg .b32 remAddr32;\n\t"
-      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t"
-      "}" ::"r"(bar),
-      "r"(cta)
-      : "memory");
-}
-// both CTAs issue; the transaction bytes are credited to the LEADER's barrier
-__device__ __forceinline__ void tma_load_tile_2sm(uint32_t dst, const CUtensorMap* map,
-                                                  uint32_t bar, int tile_col, int tile_row,
-                                                  int mat) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(0), "r"(0),
-      "r"(tile_col), "r"(tile_row), "r"(mat)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
-               "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                              uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_scaled_d_2sm(uint32_t tmem_d, uint64_t adesc,
-                                                      uint64_t bdesc, uint32_t idesc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, "
-      "p, 11;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u),
-      "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
-// arrive (once the MMAs retire) on the same-offset barrier of BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
-      "[%0], %1;" ::"r"(bar),
-      "h"((uint16_t)3)
-      : "memory");
-}
-
-// ---------------------------------------------------------------------------
 // CTA-pair kernel, 256 x 256 output tile per cluster (cta_group::2, M = 256, N = 256).
 // This is the configuration that un-saturates shared memory: a 1-CTA M=128/N=128 MMA
 // reads 8 KB of operands per 64 cycles = the full 128 B/cycle smem bandwidth, so TMA
@@ -847,11 +907,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
 //                 (3-plane split, swizzled staging, bulk tensor stores, mirror, M_i', err)
 // TMEM: 2 chunk accumulators x 256 columns.  setmaxnreg 40 / 232 / 232.
 // ---------------------------------------------------------------------------
-constexpr uint32_t kIdescBf16M256N256 =
-    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-constexpr uint32_t kIdescF16M256N256 =
-    (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-
 __device__ __forceinline__ bool tc_get_work_pair256(const TcParams& P, const Program* progs, int s,
                                                     int w, TcWork& out, int& tm2, int& tn2) {
   const int t2 = P.tiles / 2;
@@ -934,7 +989,7 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcParams& P, const TcWork
 
 constexpr int TC_P256_THREADS = 384;
 
-template <int kLP, int kStages, int kFmt>
+template <int kLP, int kStages, int kFmt, int kChunkKB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_P256_THREADS, 1)
 tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
                         const __grid_constant__ CUtensorMap tmap1,
@@ -1023,48 +1078,41 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
         int tm2, tn2;
         if (!tc_get_work_pair256(P, progs, s, w, wk, tm2, tn2)) continue;
 #pragma unroll 1
-        for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+        for (int kb = 0; kb < wk.kblocks; kb += kChunkKB, ++chunk) {
+          const int nkb = min(kChunkKB, wk.kblocks - kb);
           const int acc = chunk & 1;
           mbar_wait(tempty_bar(acc), ((chunk >> 1) & 1) ^ 1);
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
           const uint32_t tmem_d = tmem_base + acc * 256;
-          const uint32_t a0 = smem_base + stage * kStageBytes;
-          const uint32_t b0 = a0 + kLP * TC_TILE_BYTES;
+          constexpr uint32_t idesc = kFmt == TC_FMT_FP16S ? kIdescF16M256N256 : kIdescBf16M256N256;
+          int st[kChunkKB];
+#pragma unroll
+          for (int j = 0; j < kChunkKB; ++j) {
+            if (j < nkb) {
+              st[j] = stage;
+              mbar_wait(full_bar(stage), phase);
+              tcgen05_fence_after();
+              const uint32_t a0 = smem_base + stage * kStageBytes;
+              const uint32_t b0 = a0 + kLP * TC_TILE_BYTES;
+              if (kFmt == TC_FMT_FP16S) {
+                issue_fp16_cross<true>(tmem_d, a0, b0, idesc, j == 0);
+              } else {
+                issue_bf16_block<kLP, true>(tmem_d, a0, b0, idesc, j == 0);
+                umma_commit_2sm(empty_bar(stage));
+              }
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
           if (kFmt == TC_FMT_FP16S) {
-            const uint64_t a0d = make_kmajor_sw128_desc(a0), a1d = make_kmajor_sw128_desc(a0 + TC_TILE_BYTES);
-            const uint64_t b0d = make_kmajor_sw128_desc(b0), b1d = make_kmajor_sw128_desc(b0 + TC_TILE_BYTES);
 #pragma unroll
-            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
-              umma_bf16_2sm(tmem_d, a0d + 2u * k, b1d + 2u * k, kIdescF16M256N256, k == 0 ? 0u : 1u);
-#pragma unroll
-            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
-              umma_bf16_2sm(tmem_d, a1d + 2u * k, b0d + 2u * k, kIdescF16M256N256, 1u);
-            umma_f16_scaled_d_2sm(tmem_d, a0d, b0d, kIdescF16M256N256);
-#pragma unroll
-            for (int k = 1; k < TC_BK / TC_UMMA_K; ++k)
-              umma_bf16_2sm(tmem_d, a0d + 2u * k, b0d + 2u * k, kIdescF16M256N256, 1u);
-          } else {
-          bool first = true;
-#pragma unroll
-          for (int sum = kLP - 1; sum >= 0; --sum) {
-#pragma unroll
-            for (int i = 0; i <= sum; ++i) {
-              const int j = sum - i;
-              const uint64_t ad = make_kmajor_sw128_desc(a0 + i * TC_TILE_BYTES);
-              const uint64_t bd = make_kmajor_sw128_desc(b0 + j * TC_TILE_BYTES);
-#pragma unroll
-              for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                umma_bf16_2sm(tmem_d, ad + 2u * k, bd + 2u * k, kIdescBf16M256N256,
-                              (first && k == 0) ? 0u : 1u);
-                if (k == 0) first = false;
+            for (int j = 0; j < kChunkKB; ++j) {
+              if (j < nkb) {
+                const uint32_t a0 = smem_base + st[j] * kStageBytes;
+                issue_fp16_main<true>(tmem_d, a0, a0 + kLP * TC_TILE_BYTES, idesc, j == 0);
+                umma_commit_2sm(empty_bar(st[j]));
               }
             }
           }
-          }
-          umma_commit_2sm(empty_bar(stage));
           umma_commit_2sm(tfull_bar(acc));
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -1086,7 +1134,7 @@ tc_phase_kernel_pair256(const __grid_constant__ CUtensorMap tmap0,
 #pragma unroll
       for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
 #pragma unroll 1
-      for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+      for (int kb = 0; kb < wk.kblocks; kb += kChunkKB, ++chunk) {
         const int acc = chunk & 1;
         mbar_wait(tfull_bar(acc), (chunk >> 1) & 1);
         tcgen05_fence_after();
@@ -1214,8 +1262,9 @@ size_t tc_engine_bytes(int batch, int n, int planes) {
 struct TcHostState {
   CUtensorMap maps[3];     // operand loads: one 128 x 64 storage tile (16 KiB, contiguous)
   CUtensorMap maps_st[3];  // epilogue bulk stores: box {32, 32}, SWIZZLE_64B
-  bool use_pair256;        // cta_group::2, 256 x 256 cluster tiles (default when n % 256 == 0)
+  bool use_pair256;        // cta_group::2, 256 x 256 cluster tiles (PC_TC_PAIR256=1)
   int fmt, planes;         // TC_FMT_*, stored planes per matrix
+  int chunk_kb;            // 64-column k-blocks accumulated in TMEM before the fp32 register add
   TcParams prm;
   Program* progs_dev;
   uint32_t* sync_mem;  // 2 x [2 * batch] group counters, used alternately by successive launches
@@ -1306,7 +1355,14 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt
   }
   {
     const char* p256 = getenv("PC_TC_PAIR256");
-    hs->use_pair256 = (n % 256 == 0) && !(p256 && p256[0] == '0');
+    // measured on B200 (batch 74, n = 1024): the 1-CTA kernel is 3-7 % faster for both
+    // plane formats (36 of 64 tiles instead of 40 of 64, hidden epilogue), so the CTA-pair
+    // kernel is opt-in: PC_TC_PAIR256=1
+    hs->use_pair256 = (n % 256 == 0) && (p256 && p256[0] == '1');
+    const char* ck = getenv("PC_TC_CHUNK");
+    // measured on B200: 128-column chunks are not faster (the TMEM pull is not the limiter)
+    // and cost accuracy, so 64 stays the default; PC_TC_CHUNK=2 selects 128
+    hs->chunk_kb = (fmt == TC_FMT_FP16S && ck && ck[0] == '2') ? 2 : 1;
   }
   {
     const char* gs = getenv("PC_TC_SYNC");
@@ -1350,52 +1406,58 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt
   return PC_OK;
 }
 
-template <int kLP, int kStages, int kFmt>
+template <int kLP, int kStages, int kFmt, int kChunkKB>
 static int launch_phase_ws(TcHostState* hs, int s, cudaStream_t stream) {
   constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 1024 +
                           16 * TC_STAGE_BYTES_PER_WARP;
   static bool configured = false;
   if (!configured) {
-    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_ws<kLP, kStages, kFmt>,
+    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_ws<kLP, kStages, kFmt, kChunkKB>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int grid, total_work;
   plan_launch(hs, s, hs->prm.tiles * (hs->prm.tiles + 1) / 2, hs->sms, 1, &grid, &total_work);
-  tc_phase_kernel_ws<kLP, kStages, kFmt><<<grid, TC_WS_THREADS, smem, stream>>>(
+  tc_phase_kernel_ws<kLP, kStages, kFmt, kChunkKB><<<grid, TC_WS_THREADS, smem, stream>>>(
       hs->maps[0], hs->maps[1], hs->maps[2], hs->maps_st[0], hs->maps_st[1], hs->maps_st[2],
       hs->prm, hs->progs_dev, s, total_work);
   return PC_OK;
 }
 
-template <int kLP, int kStages, int kFmt>
+template <int kLP, int kStages, int kFmt, int kChunkKB>
 static int launch_phase_pair256(TcHostState* hs, int s, cudaStream_t stream) {
   constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 1024 +
                           16 * TC_STAGE_BYTES_PER_WARP;
   static bool configured = false;
   if (!configured) {
-    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_pair256<kLP, kStages, kFmt>,
+    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_pair256<kLP, kStages, kFmt, kChunkKB>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int t2 = hs->prm.tiles / 2;
   int clusters, total_work;
   plan_launch(hs, s, t2 * (t2 + 1) / 2, hs->sms / 2, 2, &clusters, &total_work);
-  tc_phase_kernel_pair256<kLP, kStages, kFmt><<<2 * clusters, TC_P256_THREADS, smem, stream>>>(
+  tc_phase_kernel_pair256<kLP, kStages, kFmt, kChunkKB><<<2 * clusters, TC_P256_THREADS, smem, stream>>>(
       hs->maps[0], hs->maps[1], hs->maps[2], hs->maps_st[0], hs->maps_st[1], hs->maps_st[2],
       hs->prm, hs->progs_dev, s, total_work);
   return PC_OK;
 }
 
 static int launch_phase(TcHostState* hs, int passes, int s, cudaStream_t stream) {
-  if (hs->fmt == TC_FMT_FP16S)
-    return hs->use_pair256 ? launch_phase_pair256<2, 3, TC_FMT_FP16S>(hs, s, stream)
-                           : launch_phase_ws<2, 3, TC_FMT_FP16S>(hs, s, stream);
+  if (hs->fmt == TC_FMT_FP16S) {
+    // K-chunk of 128 columns (24 MMAs per TMEM accumulation, like bf16x6 at 64): the
+    // chunk pull from TMEM (64 B/clk) then stays shorter than the chunk's MMAs
+    if (hs->chunk_kb == 2)
+      return hs->use_pair256 ? launch_phase_pair256<2, 3, TC_FMT_FP16S, 2>(hs, s, stream)
+                             : launch_phase_ws<2, 3, TC_FMT_FP16S, 2>(hs, s, stream);
+    return hs->use_pair256 ? launch_phase_pair256<2, 3, TC_FMT_FP16S, 1>(hs, s, stream)
+                           : launch_phase_ws<2, 3, TC_FMT_FP16S, 1>(hs, s, stream);
+  }
   if (hs->use_pair256)
-    return passes == 6 ? launch_phase_pair256<3, 2, TC_FMT_BF16>(hs, s, stream)
-                       : launch_phase_pair256<2, 3, TC_FMT_BF16>(hs, s, stream);
-  return passes == 6 ? launch_phase_ws<3, 2, TC_FMT_BF16>(hs, s, stream)
-                     : launch_phase_ws<2, 3, TC_FMT_BF16>(hs, s, stream);
+    return passes == 6 ? launch_phase_pair256<3, 2, TC_FMT_BF16, 1>(hs, s, stream)
+                       : launch_phase_pair256<2, 3, TC_FMT_BF16, 1>(hs, s, stream);
+  return passes == 6 ? launch_phase_ws<3, 2, TC_FMT_BF16, 1>(hs, s, stream)
+                     : launch_phase_ws<2, 3, TC_FMT_BF16, 1>(hs, s, stream);
 }
 
 int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* errbits,
