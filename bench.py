@@ -336,9 +336,10 @@ def run_ours(a):
   # ---- second half of the headline metric: full Shampoo step on BASELINE config 2
   #      (MLP 512->2048->512, block_size 128, SGD grafting, 1 GPU), through the
   #      optax-style API; steps >= 5 so the preconditioned path is active ----
-  shampoo_step = None
+  shampoo_step, sketchy = None, None
   if world == 1 and not a.no_step:
     shampoo_step = time_shampoo_step(dev)
+    sketchy = time_sketchy_update(dev)
 
   if rank == 0:
     cpu_baseline = None
@@ -360,6 +361,7 @@ def run_ours(a):
                    "max_error": float(np.nanmax(m_host[:, 0]))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches // 1,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "shampoo_step": shampoo_step,
+        "sketchy_update": sketchy,
     }
     print(json.dumps(line), flush=True)
   if world > 1:
@@ -394,6 +396,36 @@ def time_shampoo_step(dev, steps=10, warm=6):
           "statistics": int(tm.shape[0]), "newton_iters_mean": float(tm[:, 1].mean()),
           "max_root_error": float(tm[:, 0].max()),
           "update_finite": bool(all(torch.isfinite(u).all() for u in upd))}
+
+
+def time_sketchy_update(dev, d=4096, rank=256, batch=2, steps=2):
+  """ms per batched Sketchy / frequent-directions sketch update at BASELINE config 5's
+  per-GPU share (16 statistics of 4096 x 4096, rank 256, over 8 GPUs = 2 per GPU)."""
+  import torch
+  from precondition_b200 import ops
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(5)
+  u = torch.linalg.qr(torch.randn(d, d, generator=gen, device=dev))[0]
+  spec = torch.cat([torch.logspace(0, -1.5, rank + 64, device=dev),
+                    torch.full((d - rank - 64,), 0.01, device=dev)])
+  xs = torch.stack([(u * spec) @ torch.randn(d, d, generator=gen, device=dev) / d**0.5
+                    for _ in range(batch)]).contiguous()
+  sketch = torch.zeros((batch, d, rank + 2), device=dev)
+  ps = [4] * batch
+  for _ in range(2):  # warm the sketch up
+    sketch, _ = ops.fd_update_root_batched(xs, sketch, ps, rank, decay=0.999)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(steps):
+    sketch, _ = ops.fd_update_root_batched(xs, sketch, ps, rank, decay=0.999)
+  e1.record()
+  torch.cuda.synchronize()
+  v = sketch[0, :, :rank]
+  orth = float((v.T @ v - torch.eye(rank, device=dev)).abs().max())
+  return {"ms": e0.elapsed_time(e1) / steps, "unit": "ms/update", "d": d, "rank": rank,
+          "batch": batch, "config": "frequent_directions sketch update, 4096x4096 blocks, rank 256",
+          "eigvec_orthogonality_error": orth, "has_zeros": float(sketch[0, -1, -2])}
 
 
 def main():

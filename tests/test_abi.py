@@ -33,6 +33,14 @@ def test_workspace_queries_are_host_only():
   big = lib.pc_inverse_pth_root_workspace_bytes(8, 128, 1)
   assert 0 < small < big
   assert lib.pc_graft_momentum_workspace_bytes(1000) > 0
+  import ctypes
+  opt = _lib.FdOptions()
+  lib.pc_fd_options_default(ctypes.byref(opt))
+  assert opt.subspace_iters > 0 and opt.full_eigh_max_dim == 512
+  exact = lib.pc_fd_update_workspace_bytes(2, 256, 256, 16, ctypes.byref(opt))
+  sub = lib.pc_fd_update_workspace_bytes(2, 1024, 1024, 16, ctypes.byref(opt))
+  assert 0 < exact < sub
+  assert lib.pc_low_rank_to_dense_workspace_bytes(2, 256, 16) > 0
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -42,9 +50,10 @@ def test_struct_layouts_match_header(tmp_path):
   src = tmp_path / "sz.c"
   src.write_text(
       '#include <stdio.h>\n#include <stddef.h>\n#include "precond_b200.h"\n'
-      'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(pc_root_options),'
+      'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pc_root_options),'
       'sizeof(pc_gemm_desc), sizeof(pc_graft_options), offsetof(pc_gemm_desc, m),'
-      'offsetof(pc_gemm_desc, alpha), offsetof(pc_graft_options, run_shampoo));return 0;}\n')
+      'offsetof(pc_gemm_desc, alpha), offsetof(pc_graft_options, run_shampoo),'
+      'sizeof(pc_fd_options), offsetof(pc_fd_options, full_eigh_max_dim));return 0;}\n')
   exe = tmp_path / "sz"
   subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
                  check=True)
@@ -52,5 +61,6 @@ def test_struct_layouts_match_header(tmp_path):
                                         check=True).stdout.split()]
   want = [ctypes.sizeof(_lib.RootOptions), ctypes.sizeof(_lib.GemmDesc),
           ctypes.sizeof(_lib.GraftOptions), _lib.GemmDesc.m.offset,
-          _lib.GemmDesc.alpha.offset, _lib.GraftOptions.run_shampoo.offset]
+          _lib.GemmDesc.alpha.offset, _lib.GraftOptions.run_shampoo.offset,
+          ctypes.sizeof(_lib.FdOptions), _lib.FdOptions.full_eigh_max_dim.offset]
   assert got == want
