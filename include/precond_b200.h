@@ -165,6 +165,17 @@ typedef struct {
 int pc_grouped_gemm(const pc_gemm_desc* descs, int count, int max_m, int max_n,
                     void* stream);
 
+/* tcgen05 path of the grouped GEMM for descriptors whose m and n are multiples of 128 (k is
+ * arbitrary; c / c_in 16-byte aligned with c_sii, c_sio multiples of 4): every operand view is
+ * packed once into scaled-fp16 plane tiles (22 mantissa bits, per-operand power-of-two scale)
+ * and the products run as three kind::f16 MMAs per k-step with fp32 accumulation.  A descriptor
+ * with identical A and B views (the Gram update of DS:1468-1470) is computed as a symmetric
+ * rank-k update: lower tiles only, mirrored, so the result is bitwise symmetric.
+ * descs_host: HOST array (the host plans the tile list); synchronises `stream` once per call. */
+size_t pc_grouped_gemm_tc_workspace_bytes(const pc_gemm_desc* descs_host, int count);
+int pc_grouped_gemm_tc(const pc_gemm_desc* descs_host, int count, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Failure fallback of DS:2936-2950 without a host round trip: for every matrix b,
  * dst[b] <- src[b] unless metrics[b][PC_METRIC_ERROR] is NaN or >= threshold
  * (then dst keeps the previous preconditioner).  src rows are [src_rows, src_cols]

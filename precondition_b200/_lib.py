@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     "pc_graft_momentum_workspace_bytes", "pc_graft_momentum",
     "pc_fd_options_default", "pc_fd_update_workspace_bytes", "pc_fd_update_batched",
     "pc_low_rank_to_dense_workspace_bytes", "pc_low_rank_to_dense",
+    "pc_grouped_gemm_tc_workspace_bytes", "pc_grouped_gemm_tc",
 )
 
 
@@ -143,6 +144,10 @@ def load() -> ctypes.CDLL:
   lib.pc_low_rank_to_dense_workspace_bytes.restype = sz
   lib.pc_low_rank_to_dense.argtypes = [vp, i32, i32, i32, vp, vp, sz, vp]
   lib.pc_low_rank_to_dense.restype = i32
+  lib.pc_grouped_gemm_tc_workspace_bytes.argtypes = [vp, i32]
+  lib.pc_grouped_gemm_tc_workspace_bytes.restype = sz
+  lib.pc_grouped_gemm_tc.argtypes = [vp, i32, vp, sz, vp]
+  lib.pc_grouped_gemm_tc.restype = i32
   _lib = lib
   return lib
 

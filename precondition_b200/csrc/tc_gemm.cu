@@ -27,6 +27,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "root_kernels.cuh"
 #include "tc_engine.cuh"
 
@@ -1588,6 +1590,469 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
   return rc;
 }
 
+
+// ===========================================================================
+// tcgen05 grouped GEMM on fp32 operands:  C = alpha * A B^T-view + beta * C_in
+// (the statistics update L <- b2 L + (1-b2) G G^T, DS:1440-1470, and the preconditioner
+// application, DS:1676-1708, for blocks whose output sizes are multiples of 128).
+//   1. tc_pack_max_kernel / tc_pack_kernel: every operand view (strided, possibly
+//      transposed -- the same two-level addressing as pc_gemm_desc) is converted ONCE into
+//      scaled-fp16 plane tiles (128 x 64, contiguous): X ~ (X0 + 2^-11 X1) / s with a
+//      per-operand power-of-two s that brings max|X| to ~2^10, so gradients of any
+//      magnitude keep 22 mantissa bits (fp16 alone would flush 1e-6 gradients).
+//   2. tc_ggemm_kernel: the Newton engine's pipeline (TMA producer, single-thread
+//      tcgen05.mma issuer with the scale-input-d three-pass scheme, 64-column K-chunks
+//      summed in fp32 registers, TMEM output stages) with an fp32 epilogue:
+//      C = alpha / (sA sB) * acc + beta * C_in.  Symmetric products (A == B: the Gram
+//      update) compute lower tiles only and write the mirror from the same registers.
+// ===========================================================================
+struct TcGgItem {
+  const float* a; const float* b; const float* c_in; float* c;
+  int64_t a_sio, a_si, a_sko, a_ski, b_sj, b_sko, b_ski, c_sio, c_sii;
+  int a_iinner, a_kinner, b_kinner, c_iinner;
+  int m, n, k, kblocks;
+  int a_tile0, b_tile0;  // first packed tile of each operand (b_tile0 == a_tile0 if symmetric)
+  int symmetric;
+  float alpha, beta;
+};
+struct TcGgWork { int z, tm, tn, pad; };
+struct TcGgOperand {  // one packed operand: view + where its tiles go
+  const float* base;
+  int64_t s_io, s_i, s_ko, s_ki;
+  int i_inner, k_inner, rows, k, kblocks, tile0, scale_slot, pad;
+};
+
+__device__ __forceinline__ float tc_gg_view(const TcGgOperand& o, int i, int kk) {
+  if (i >= o.rows || kk >= o.k) return 0.f;
+  const int io = i / o.i_inner, ii = i - io * o.i_inner;
+  const int ko = kk / o.k_inner, ki = kk - ko * o.k_inner;
+  return __ldg(o.base + io * o.s_io + ii * o.s_i + ko * o.s_ko + ki * o.s_ki);
+}
+
+// max |x| per operand (bit pattern of a non-negative float orders like the float)
+__global__ void __launch_bounds__(256)
+tc_pack_max_kernel(const TcGgOperand* __restrict__ ops, uint32_t* __restrict__ maxbits) {
+  const TcGgOperand o = ops[blockIdx.y];
+  const int tiles = (o.rows / 128) * o.kblocks;
+  uint32_t mx = 0;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int tr = t / o.kblocks, kb = t - tr * o.kblocks;
+    const bool kfast = o.s_ki == 1;
+    for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
+      const int r = kfast ? e >> 6 : e & 127, c = kfast ? e & 63 : e >> 7;
+      const uint32_t ab = absbits(tc_gg_view(o, tr * 128 + r, kb * 64 + c));
+      mx = ab > mx ? ab : mx;
+    }
+  }
+  mx = warp_max_u32(mx);
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(maxbits + o.scale_slot, mx);
+}
+
+__device__ __forceinline__ float tc_gg_scale(uint32_t maxbits) {
+  const float mx = __uint_as_float(maxbits);
+  if (!(mx > 0.f) || !(mx < 3.0e38f)) return 1.0f;  // zero, inf or NaN operand: leave as is
+  int e = 0;
+  frexpf(mx, &e);  // mx in [2^(e-1), 2^e)
+  int sh = 10 - e;
+  sh = sh > 120 ? 120 : (sh < -120 ? -120 : sh);
+  return ldexpf(1.0f, sh);
+}
+
+__global__ void __launch_bounds__(256)
+tc_pack_kernel(const TcGgOperand* __restrict__ ops, const uint32_t* __restrict__ maxbits,
+               uint16_t* __restrict__ plane0, uint16_t* __restrict__ plane1) {
+  __shared__ float tile[64][129];
+  const TcGgOperand o = ops[blockIdx.y];
+  const int tiles = (o.rows / 128) * o.kblocks;
+  const float sc = tc_gg_scale(maxbits[o.scale_slot]);
+  const bool kfast = o.s_ki == 1;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int tr = t / o.kblocks, kb = t - tr * o.kblocks;
+    __syncthreads();
+    for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {  // coalesced along the fast axis
+      const int r = kfast ? e >> 6 : e & 127, c = kfast ? e & 63 : e >> 7;
+      tile[c][r] = tc_gg_view(o, tr * 128 + r, kb * 64 + c) * sc;
+    }
+    __syncthreads();
+    const size_t base = (size_t)(o.tile0 + t) * 8192;
+    for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
+      const int r = e >> 6, c = e & 63;
+      const float v = tile[c][r];
+      const float cl = fabsf(v) > 65504.0f ? copysignf(65504.0f, v) : v;
+      const __half h0 = __float2half_rn(cl);
+      const float r1 = (cl - __half2float(h0)) * TC_FP16_SCALE;
+      plane0[base + e] = __half_as_ushort(h0);
+      plane1[base + e] = __half_as_ushort(__float2half_rn(r1));
+    }
+  }
+}
+
+// loads packed tile `t` (16 KiB) of a plane: 3-D map [64, 128, tiles]
+__device__ __forceinline__ void tma_load_packed_tile(uint32_t dst, const CUtensorMap* map,
+                                                     uint32_t bar, int t) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(0), "r"(0), "r"(t)
+      : "memory");
+}
+
+constexpr int TC_GG_THREADS = 512;
+constexpr int TC_GG_STAGES = 3;
+
+__global__ void __launch_bounds__(TC_GG_THREADS, 1)
+tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                const TcGgItem* __restrict__ items, const TcGgWork* __restrict__ work,
+                const uint32_t* __restrict__ maxbits, int total_work) {
+  constexpr int kStageBytes = 4 * TC_TILE_BYTES;  // A0 A1 B0 B1
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + TC_GG_STAGES * kStageBytes;
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_base + 8u * (TC_GG_STAGES + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * TC_GG_STAGES + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * TC_GG_STAGES + 2 + i); };
+  auto ofull_bar = [&](int i) { return bar_base + 8u * (2 * TC_GG_STAGES + 4 + i); };
+  auto oempty_bar = [&](int i) { return bar_base + 8u * (2 * TC_GG_STAGES + 6 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_GG_STAGES + 8);
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map0);
+    tma_prefetch_desc(&map1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < TC_GG_STAGES; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);
+      mbar_init(ofull_bar(i), 4);
+      mbar_init(oempty_bar(i), 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && elect_one()) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+#pragma unroll 1
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const TcGgWork wk = work[w];
+        const TcGgItem& it = items[wk.z];
+        const int kblocks = it.kblocks;
+        const int at = it.a_tile0 + wk.tm * kblocks, bt = it.b_tile0 + wk.tn * kblocks;
+#pragma unroll 1
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t dst = smem_base + stage * kStageBytes;
+          mbar_expect_tx(full_bar(stage), kStageBytes);
+          tma_load_packed_tile(dst, &map0, full_bar(stage), at + kb);
+          tma_load_packed_tile(dst + TC_TILE_BYTES, &map1, full_bar(stage), at + kb);
+          tma_load_packed_tile(dst + 2 * TC_TILE_BYTES, &map0, full_bar(stage), bt + kb);
+          tma_load_packed_tile(dst + 3 * TC_TILE_BYTES, &map1, full_bar(stage), bt + kb);
+          if (++stage == TC_GG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && elect_one()) {
+      // ===================== MMA issuer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      int chunk = 0;
+#pragma unroll 1
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int kblocks = items[work[w].z].kblocks;
+#pragma unroll 1
+        for (int kb = 0; kb < kblocks; ++kb, ++chunk) {
+          const int acc = chunk & 1;
+          mbar_wait(tempty_bar(acc), ((chunk >> 1) & 1) ^ 1);
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * TC_BN;
+          const uint32_t a0 = smem_base + stage * kStageBytes;
+          const uint32_t b0 = a0 + 2 * TC_TILE_BYTES;
+          issue_fp16_cross<false>(tmem_d, a0, b0, kIdescF16M128N128, true);
+          issue_fp16_main<false>(tmem_d, a0, b0, kIdescF16M128N128, true);
+          umma_commit(empty_bar(stage));
+          umma_commit(tfull_bar(acc));
+          if (++stage == TC_GG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ============ warpgroup 1: chunk accumulation -> TMEM output stage ============
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int q = warp & 3;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    int chunk = 0, tile = 0;
+#pragma unroll 1
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int kblocks = items[work[w].z].kblocks;
+      float sum[TC_BN];
+#pragma unroll
+      for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
+#pragma unroll 1
+      for (int kb = 0; kb < kblocks; ++kb, ++chunk) {
+        const int acc = chunk & 1;
+        mbar_wait(tfull_bar(acc), (chunk >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + lane_off + acc * TC_BN;
+#pragma unroll
+        for (int c = 0; c < TC_BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      const int o = tile & 1;
+      mbar_wait(oempty_bar(o), ((tile >> 1) & 1) ^ 1);
+      tcgen05_fence_after();
+      const uint32_t oaddr = tmem_base + lane_off + 256 + o * TC_BN;
+#pragma unroll
+      for (int c = 0; c < TC_BN / 32; ++c) {
+        uint32_t r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(sum[c * 32 + i]);
+        tmem_st_32x32(oaddr + c * 32, r);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ofull_bar(o));
+      ++tile;
+    }
+  } else {
+    // ============ warpgroups 2, 3: fp32 epilogue (two column halves of every tile) ============
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    const int q = warp & 3;
+    const int half = (warp >> 2) - 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    int tile = 0;
+#pragma unroll 1
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const TcGgWork wk = work[w];
+      const TcGgItem it = items[wk.z];
+      const int o = tile & 1;
+      mbar_wait(ofull_bar(o), (tile >> 1) & 1);
+      tcgen05_fence_after();
+      const float sa = tc_gg_scale(maxbits[2 * wk.z]), sb = tc_gg_scale(maxbits[2 * wk.z + 1]);
+      const float alpha = it.alpha / (sa * (it.symmetric ? sa : sb));
+      const int row = wk.tm * TC_BM + q * 32 + lane;
+      const int io = row / it.c_iinner, ii = row - io * it.c_iinner;
+      const int64_t rowoff = io * it.c_sio + ii * it.c_sii;
+      const bool diag_tile = it.symmetric && wk.tm == wk.tn;
+#pragma unroll 1
+      for (int c = 2 * half; c < 2 * half + 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + lane_off + 256 + o * TC_BN + c * 32, r);
+        tmem_ld_wait();
+        if (c == 2 * half + 1) {  // last TMEM read of this tile by this warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(oempty_bar(o));
+        }
+        const int col0 = wk.tn * TC_BN + c * 32;
+        if (diag_tile && c > q) continue;  // strictly upper sub-block: written by its mirror
+        float x[32];
+        const float* cin = it.c_in ? it.c_in + rowoff + col0 : nullptr;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cin) old = *reinterpret_cast<const float4*>(cin + i);
+          x[i] = fmaf(it.beta, old.x, alpha * __uint_as_float(r[i]));
+          x[i + 1] = fmaf(it.beta, old.y, alpha * __uint_as_float(r[i + 1]));
+          x[i + 2] = fmaf(it.beta, old.z, alpha * __uint_as_float(r[i + 2]));
+          x[i + 3] = fmaf(it.beta, old.w, alpha * __uint_as_float(r[i + 3]));
+        }
+        const bool diag_sub = diag_tile && c == q;
+        float* crow = it.c + rowoff + col0;
+        if (!diag_sub) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(crow + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+        } else {  // lower triangle of the diagonal sub-block only (its mirror fills the rest)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i <= lane) crow[i] = x[i];
+        }
+        if (it.symmetric) {
+          // mirror: element (row, col0 + i) -> (col0 + i, row); lanes write consecutive floats
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int mr = col0 + i;
+            if (diag_sub && i >= lane) continue;  // strictly lower elements only
+            const int mio = mr / it.c_iinner, mii = mr - mio * it.c_iinner;
+            it.c[mio * it.c_sio + mii * it.c_sii + row] = x[i];
+          }
+        }
+      }
+      ++tile;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host ----
+static bool tc_gg_supported(const pc_gemm_desc& d) {
+  return d.m > 0 && d.n > 0 && d.k > 0 && d.m % 128 == 0 && d.n % 128 == 0 &&
+         (reinterpret_cast<uintptr_t>(d.c) % 16 == 0) && d.c_sii % 4 == 0 && d.c_sio % 4 == 0 &&
+         (!d.c_in || (reinterpret_cast<uintptr_t>(d.c_in) % 16 == 0));
+}
+static bool tc_gg_symmetric(const pc_gemm_desc& d) {
+  return d.a == d.b && d.m == d.n && d.a_sio == 0 && d.a_iinner >= d.m && d.a_si == d.b_sj &&
+         d.a_sko == d.b_sko && d.a_ski == d.b_ski && d.a_kinner == d.b_kinner;
+}
+
+struct TcGgPlan {
+  std::vector<TcGgItem> items;
+  std::vector<TcGgOperand> ops;
+  std::vector<TcGgWork> work;
+  int total_tiles = 0;
+};
+
+static void tc_gg_plan(const pc_gemm_desc* descs, int count, TcGgPlan* pl) {
+  for (int z = 0; z < count; ++z) {
+    const pc_gemm_desc& d = descs[z];
+    TcGgItem it{};
+    it.a = d.a; it.b = d.b; it.c_in = d.c_in; it.c = d.c;
+    it.c_sio = d.c_sio; it.c_sii = d.c_sii; it.c_iinner = d.c_iinner > 0 ? d.c_iinner : d.m;
+    it.m = d.m; it.n = d.n; it.k = d.k; it.kblocks = (d.k + TC_BK - 1) / TC_BK;
+    it.alpha = d.alpha; it.beta = d.beta;
+    it.symmetric = tc_gg_symmetric(d) ? 1 : 0;
+    TcGgOperand oa{};
+    oa.base = d.a; oa.s_io = d.a_sio; oa.s_i = d.a_si; oa.s_ko = d.a_sko; oa.s_ki = d.a_ski;
+    oa.i_inner = d.a_iinner > 0 ? d.a_iinner : d.m; oa.k_inner = d.a_kinner > 0 ? d.a_kinner : d.k;
+    oa.rows = d.m; oa.k = d.k; oa.kblocks = it.kblocks; oa.tile0 = pl->total_tiles;
+    oa.scale_slot = 2 * z;
+    it.a_tile0 = oa.tile0;
+    pl->total_tiles += (d.m / 128) * it.kblocks;
+    pl->ops.push_back(oa);
+    if (it.symmetric) {
+      it.b_tile0 = it.a_tile0;
+    } else {
+      TcGgOperand ob{};
+      ob.base = d.b; ob.s_io = 0; ob.s_i = d.b_sj; ob.s_ko = d.b_sko; ob.s_ki = d.b_ski;
+      ob.i_inner = d.n; ob.k_inner = d.b_kinner > 0 ? d.b_kinner : d.k;
+      ob.rows = d.n; ob.k = d.k; ob.kblocks = it.kblocks; ob.tile0 = pl->total_tiles;
+      ob.scale_slot = 2 * z + 1;
+      it.b_tile0 = ob.tile0;
+      pl->total_tiles += (d.n / 128) * it.kblocks;
+      pl->ops.push_back(ob);
+    }
+    pl->items.push_back(it);
+    for (int tm = 0; tm < d.m / 128; ++tm)
+      for (int tn = 0; tn < d.n / 128; ++tn)
+        if (!it.symmetric || tn <= tm) pl->work.push_back(TcGgWork{z, tm, tn, 0});
+  }
+}
+
+static size_t tc_gg_bytes(const TcGgPlan& pl) {
+  size_t s = 0;
+  s += align_up(pl.items.size() * sizeof(TcGgItem), 256);
+  s += align_up(pl.ops.size() * sizeof(TcGgOperand), 256);
+  s += align_up(pl.work.size() * sizeof(TcGgWork), 256);
+  s += align_up(2 * pl.items.size() * sizeof(uint32_t), 256);
+  s += 1024 + 2 * align_up((size_t)pl.total_tiles * TC_TILE_BYTES, 1024);
+  return s + 1024;
+}
+
+size_t tc_grouped_gemm_workspace_bytes(const pc_gemm_desc* descs, int count) {
+  TcGgPlan pl;
+  tc_gg_plan(descs, count, &pl);
+  return tc_gg_bytes(pl);
+}
+
+int tc_grouped_gemm(const pc_gemm_desc* descs, int count, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream) {
+  for (int z = 0; z < count; ++z)
+    PC_REQUIRE(tc_gg_supported(descs[z]),
+               "descriptor %d is not eligible for the tcgen05 grouped GEMM (m, n %% 128, alignment)", z);
+  if (!tc_engine_available()) {
+    set_error("tcgen05 grouped GEMM requested but device is not sm_100");
+    return PC_ERR_UNSUPPORTED;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return PC_ERR_UNSUPPORTED;
+  }
+  TcGgPlan pl;
+  tc_gg_plan(descs, count, &pl);
+  if (workspace_bytes < tc_gg_bytes(pl)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, tc_gg_bytes(pl));
+    return PC_ERR_WORKSPACE;
+  }
+  char* w = reinterpret_cast<char*>(align_up((size_t)workspace, 256));
+  TcGgItem* d_items = reinterpret_cast<TcGgItem*>(w); w += align_up(pl.items.size() * sizeof(TcGgItem), 256);
+  TcGgOperand* d_ops = reinterpret_cast<TcGgOperand*>(w); w += align_up(pl.ops.size() * sizeof(TcGgOperand), 256);
+  TcGgWork* d_work = reinterpret_cast<TcGgWork*>(w); w += align_up(pl.work.size() * sizeof(TcGgWork), 256);
+  uint32_t* d_max = reinterpret_cast<uint32_t*>(w); w += align_up(2 * pl.items.size() * sizeof(uint32_t), 256);
+  uint16_t* plane0 = reinterpret_cast<uint16_t*>(align_up((size_t)w, 1024));
+  uint16_t* plane1 = plane0 + align_up((size_t)pl.total_tiles * TC_TILE_BYTES, 1024) / 2;
+  // the plan lives in heap vectors: synchronous copies (pageable memory) keep them valid
+  PC_CUDA_CHECK(cudaMemcpyAsync(d_items, pl.items.data(), pl.items.size() * sizeof(TcGgItem),
+                                cudaMemcpyHostToDevice, stream));
+  PC_CUDA_CHECK(cudaMemcpyAsync(d_ops, pl.ops.data(), pl.ops.size() * sizeof(TcGgOperand),
+                                cudaMemcpyHostToDevice, stream));
+  PC_CUDA_CHECK(cudaMemcpyAsync(d_work, pl.work.data(), pl.work.size() * sizeof(TcGgWork),
+                                cudaMemcpyHostToDevice, stream));
+  PC_CUDA_CHECK(cudaMemsetAsync(d_max, 0, 2 * pl.items.size() * sizeof(uint32_t), stream));
+  PC_CUDA_CHECK(cudaStreamSynchronize(stream));
+  CUtensorMap maps[2];
+  for (int plx = 0; plx < 2; ++plx) {
+    cuuint64_t dims[3] = {64, 128, (cuuint64_t)pl.total_tiles};
+    cuuint64_t strides[2] = {64 * 2, 8192 * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&maps[plx], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, plx ? plane1 : plane0, dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed with %d", (int)r);
+      return PC_ERR_CUDA;
+    }
+  }
+  const int nops = (int)pl.ops.size();
+  tc_pack_max_kernel<<<dim3(32, nops), 256, 0, stream>>>(d_ops, d_max);
+  tc_pack_kernel<<<dim3(64, nops), 256, 0, stream>>>(d_ops, d_max, plane0, plane1);
+  constexpr size_t smem = (size_t)TC_GG_STAGES * 4 * TC_TILE_BYTES + 1024 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_ggemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    configured = true;
+  }
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int total_work = (int)pl.work.size();
+  const int grid = total_work < sms ? total_work : sms;
+  tc_ggemm_kernel<<<grid, TC_GG_THREADS, smem, stream>>>(maps[0], maps[1], d_items, d_work, d_max,
+                                                        total_work);
+  count_launch(3);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
 }  // namespace pc
 
 extern "C" int pc_debug_tc_gemm(const float* a, const float* b, float* c, int batch, int n,
@@ -1598,4 +2063,17 @@ extern "C" int pc_debug_tc_gemm(const float* a, const float* b, float* c, int ba
              "passes must be 6, 3 (bf16 planes) or -3 (scaled fp16 planes)");
   return pc::tc_debug_gemm(a, b, c, batch, n, passes, workspace, workspace_bytes,
                            (cudaStream_t)stream);
+}
+
+extern "C" size_t pc_grouped_gemm_tc_workspace_bytes(const pc_gemm_desc* descs_host, int count) {
+  if (!descs_host || count <= 0) return 0;
+  return pc::tc_grouped_gemm_workspace_bytes(descs_host, count);
+}
+
+extern "C" int pc_grouped_gemm_tc(const pc_gemm_desc* descs_host, int count, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(count >= 0, "bad count");
+  if (count == 0) return PC_OK;
+  PC_REQUIRE(descs_host && workspace, "null pointer argument");
+  return pc::tc_grouped_gemm(descs_host, count, workspace, workspace_bytes, (cudaStream_t)stream);
 }

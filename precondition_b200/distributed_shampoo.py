@@ -600,10 +600,27 @@ class _Shampoo:
                                 max(self._apply_max[j][1], d0)]
           cur_ptr, cur_sizes, cur_strides = d.c, new_sizes, new_strides
         tmp_off += bnumel
-    self._stat_descs = (ops.upload_gemm_descs(stat_descs, self.device), len(stat_descs)) \
-        if stat_descs else (None, 0)
-    self._apply_descs = [(ops.upload_gemm_descs(lst, self.device), len(lst)) if lst else (None, 0)
-                         for lst in apply_descs]
+    # Blocks whose GEMM output sizes are multiples of 128 go to the tcgen05 grouped GEMM
+    # (scaled-fp16 three-pass products, symmetric rank-k for the Gram update); the rest
+    # stay on the fp32 CUDA-core tile.
+    use_tc = (self.engine != _lib.PC_ENGINE_SIMT_FP32 and
+              bool(_lib.load().pc_device_supports_tcgen05()))
+
+    def split(descs):
+      tc = [d for d in descs if use_tc and ops.tc_gemm_eligible(d)]
+      simt = [d for d in descs if not (use_tc and ops.tc_gemm_eligible(d))]
+      mx = [max([d.m for d in simt], default=1), max([d.n for d in simt], default=1)]
+      return (ops.TcGemmList(tc, self.device) if tc else None,
+              (ops.upload_gemm_descs(simt, self.device), len(simt)) if simt else (None, 0), mx)
+
+    self._stat_count = len(stat_descs)
+    self._stat_tc, self._stat_descs, self._stat_max = split(stat_descs)
+    self._apply_tc, self._apply_descs, self._apply_max = [], [], []
+    for lst in apply_descs:
+      tc, simt, mx = split(lst)
+      self._apply_tc.append(tc)
+      self._apply_descs.append(simt)
+      self._apply_max.append(mx)
 
   def _identity(self, n):
     cache = self.__dict__.setdefault("_eyes", {})
@@ -629,7 +646,7 @@ class _Shampoo:
         self.agbuf.add_(self.gbuf)
       torch.div(self.agbuf, float(k), out=self.sgbuf)
     # (1) statistics (DS:3644 -> DS:2631-2675)
-    if self._stat_descs[1] and (self.statistics_compute_steps <= 1 or
+    if self._stat_count and (self.statistics_compute_steps <= 1 or
                                 step % self.statistics_compute_steps == 0):
       self._update_statistics()
     # (2) preconditioners (DS:3648 -> DS:3442-3494)
@@ -666,7 +683,10 @@ class _Shampoo:
         q, d, b = bk.qstats
         ops.dequantize(q, d, b, True, out=bk.stats)
     dev, count = self._stat_descs
-    ops.grouped_gemm(dev, count, self._stat_max[0], self._stat_max[1])
+    if count:
+      ops.grouped_gemm(dev, count, self._stat_max[0], self._stat_max[1])
+    if self._stat_tc is not None:
+      self._stat_tc.run()
     if self.quantize_second_moment:  # from_float (DS:2654)
       for bk in self.buckets.values():
         bk.qstats[0], bk.qstats[1], bk.qstats[2] = self._requant(bk.stats, bk.qstats)
@@ -779,6 +799,8 @@ class _Shampoo:
     for j, (dev, count) in enumerate(self._apply_descs):
       if count:
         ops.grouped_gemm(dev, count, self._apply_max[j][0], self._apply_max[j][1])
+      if self._apply_tc[j] is not None:
+        self._apply_tc[j].run()
 
   def _transform_grad(self, plan, grad, st, param, step, lr):
     gflat = self.gbuf[plan.offset:plan.offset + plan.numel]

@@ -252,6 +252,39 @@ def grouped_gemm(descs_dev: torch.Tensor, count: int, max_m: int, max_n: int):
   gpu_launches += 1
 
 
+def tc_gemm_eligible(d: _lib.GemmDesc) -> bool:
+  """Descriptor can run on the tcgen05 grouped GEMM (include/precond_b200.h)."""
+  return (d.m > 0 and d.n > 0 and d.k > 0 and d.m % 128 == 0 and d.n % 128 == 0 and
+          (d.c or 0) % 16 == 0 and d.c_sii % 4 == 0 and d.c_sio % 4 == 0 and
+          (d.c_in or 0) % 16 == 0)
+
+
+class TcGemmList:
+  """Host-side descriptor array for ``pc_grouped_gemm_tc`` (kept alive by the caller)."""
+
+  def __init__(self, descs: Sequence[_lib.GemmDesc], device):
+    self.count = len(descs)
+    self.arr = (_lib.GemmDesc * max(self.count, 1))(*descs)
+    self.device = device
+    lib = _lib.load()
+    self.nbytes = lib.pc_grouped_gemm_tc_workspace_bytes(
+        ctypes.cast(self.arr, ctypes.c_void_p), self.count) if self.count else 0
+    self.ws = None
+
+  def run(self):
+    global gpu_launches
+    if not self.count:
+      return
+    lib = _lib.load()
+    if self.ws is None:  # private workspace: the packed planes must not alias other scratch
+      self.ws = torch.empty(self.nbytes + 4096, dtype=torch.uint8, device=self.device)
+    with torch.cuda.device(self.device):
+      _lib.check(lib.pc_grouped_gemm_tc(ctypes.cast(self.arr, ctypes.c_void_p), self.count,
+                                        _ptr(self.ws), self.ws.numel(),
+                                        ctypes.c_void_p(_stream())))
+    gpu_launches += 1
+
+
 def make_graft_options(**kw) -> _lib.GraftOptions:
   o = _lib.GraftOptions()
   for k, v in kw.items():

@@ -149,3 +149,75 @@ def test_graft_momentum_matches_oracle(cfg):
   if has_diag:
     np.testing.assert_allclose(d_t.cpu().numpy(), want_st.diagonal_statistics.to_float(),
                                rtol=2e-6, atol=1e-12)
+
+
+def _tc_ok():
+  from precondition_b200 import _lib
+  return torch.cuda.is_available() and bool(_lib.load().pc_device_supports_tcgen05())
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-6, 3e4])
+def test_tc_grouped_gemm_gram_update_and_apply(scale):
+  """tcgen05 grouped GEMM (pc_grouped_gemm_tc) against float64: the Gram update
+  S <- w1 S + w2 G G^T / G^T G on both unfoldings of a [256, 384] block (strided and
+  transposed views, k not a multiple of 64 via a [256, 200] block) and the application
+  G P with a non-symmetric product.  Operands carry 22 mantissa bits with a per-operand
+  power-of-two scale, so tiny (1e-6) and large (3e4) gradients are equally accurate."""
+  if not _tc_ok():
+    pytest.skip("needs sm_100")
+  from precondition_b200 import _lib, ops
+  rng = np.random.default_rng(17)
+  f32 = 4
+  g = torch.as_tensor((rng.standard_normal((256, 384)) * scale).astype(np.float32)).cuda()
+  g2 = torch.as_tensor((rng.standard_normal((256, 200)) * scale).astype(np.float32)).cuda()
+  sl = torch.as_tensor(np.cov(rng.standard_normal((256, 300))).astype(np.float32)).cuda().contiguous()
+  sr = torch.as_tensor(np.cov(rng.standard_normal((384, 500))).astype(np.float32)).cuda().contiguous()
+  s2 = torch.zeros((256, 256), dtype=torch.float32).cuda()
+  p = torch.as_tensor(rng.standard_normal((384, 384)).astype(np.float32)).cuda()
+  out = torch.zeros((256, 384), dtype=torch.float32).cuda()
+  sl0, sr0 = sl.cpu().numpy().astype(np.float64), sr.cpu().numpy().astype(np.float64)
+  w1, w2 = 0.9, 0.1
+  D = _lib.GemmDesc
+  descs = []
+  d = D()  # L = w1 L + w2 G G^T (rows of G, k-fast)
+  d.a = d.b = g.data_ptr(); d.c = d.c_in = sl.data_ptr()
+  d.a_si = d.b_sj = 384; d.a_iinner, d.a_sio = 256, 0
+  d.a_kinner = d.b_kinner = 384; d.a_sko = d.b_sko = 0; d.a_ski = d.b_ski = 1
+  d.c_iinner, d.c_sio, d.c_sii = 256, 0, 256
+  d.m = d.n = 256; d.k = 384; d.alpha, d.beta = w2, w1
+  descs.append(d)
+  d = D()  # R = w1 R + w2 G^T G (columns of G: transposed view)
+  d.a = d.b = g.data_ptr(); d.c = d.c_in = sr.data_ptr()
+  d.a_si = d.b_sj = 1; d.a_iinner, d.a_sio = 384, 0
+  d.a_kinner = d.b_kinner = 256; d.a_sko = d.b_sko = 0; d.a_ski = d.b_ski = 384
+  d.c_iinner, d.c_sio, d.c_sii = 384, 0, 384
+  d.m = d.n = 384; d.k = 256; d.alpha, d.beta = w2, w1
+  descs.append(d)
+  d = D()  # k = 200 (zero-padded to 256 inside), no c_in
+  d.a = d.b = g2.data_ptr(); d.c = s2.data_ptr(); d.c_in = None
+  d.a_si = d.b_sj = 200; d.a_iinner, d.a_sio = 256, 0
+  d.a_kinner = d.b_kinner = 200; d.a_sko = d.b_sko = 0; d.a_ski = d.b_ski = 1
+  d.c_iinner, d.c_sio, d.c_sii = 256, 0, 256
+  d.m = d.n = 256; d.k = 200; d.alpha, d.beta = 1.0, 0.0
+  descs.append(d)
+  d = D()  # out = G P : A(i,k) = G[i,k], B(j,k) = P[k,j]
+  d.a = g.data_ptr(); d.b = p.data_ptr(); d.c = out.data_ptr(); d.c_in = None
+  d.a_si = 384; d.a_iinner, d.a_sio = 256, 0; d.a_kinner, d.a_sko, d.a_ski = 384, 0, 1
+  d.b_sj, d.b_kinner, d.b_sko, d.b_ski = 1, 384, 0, 384
+  d.c_iinner, d.c_sio, d.c_sii = 256, 0, 384
+  d.m, d.n, d.k = 256, 384, 384; d.alpha, d.beta = 1.0, 0.0
+  descs.append(d)
+  assert all(ops.tc_gemm_eligible(x) for x in descs)
+  lst = ops.TcGemmList(descs, g.device)
+  lst.run()
+  torch.cuda.synchronize()
+  g64, g264, p64 = (x.cpu().numpy().astype(np.float64) for x in (g, g2, p))
+  want = [w1 * sl0 + w2 * g64 @ g64.T, w1 * sr0 + w2 * g64.T @ g64, g264 @ g264.T, g64 @ p64]
+  for got, w, sym in zip((sl, sr, s2, out), want, (True, True, True, False)):
+    got = got.cpu().numpy()
+    # the symmetric path treats the lower triangle as authoritative
+    ref = np.tril(w) + np.tril(w, -1).T if sym else w
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err <= 2e-6, err
+    if sym:
+      np.testing.assert_array_equal(got, got.T)
