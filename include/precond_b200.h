@@ -171,10 +171,13 @@ int pc_grouped_gemm(const pc_gemm_desc* descs, int count, int max_m, int max_n,
  * and the products run as three kind::f16 MMAs per k-step with fp32 accumulation.  A descriptor
  * with identical A and B views (the Gram update of DS:1468-1470) is computed as a symmetric
  * rank-k update: lower tiles only, mirrored, so the result is bitwise symmetric.
- * descs_host: HOST array (the host plans the tile list); synchronises `stream` once per call. */
+ * descs_host: HOST array (the host plans the tile list and uploads it into `workspace`, which
+ * costs one synchronisation of `stream`).  reuse_plan != 0: the caller guarantees that
+ * `workspace` still holds the plan of the previous call with identical descriptors (a
+ * training loop's static launch list) -- nothing is uploaded and the call only enqueues. */
 size_t pc_grouped_gemm_tc_workspace_bytes(const pc_gemm_desc* descs_host, int count);
 int pc_grouped_gemm_tc(const pc_gemm_desc* descs_host, int count, void* workspace,
-                       size_t workspace_bytes, void* stream);
+                       size_t workspace_bytes, int reuse_plan, void* stream);
 
 /* Failure fallback of DS:2936-2950 without a host round trip: for every matrix b,
  * dst[b] <- src[b] unless metrics[b][PC_METRIC_ERROR] is NaN or >= threshold

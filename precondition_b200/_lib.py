@@ -146,7 +146,7 @@ def load() -> ctypes.CDLL:
   lib.pc_low_rank_to_dense.restype = i32
   lib.pc_grouped_gemm_tc_workspace_bytes.argtypes = [vp, i32]
   lib.pc_grouped_gemm_tc_workspace_bytes.restype = sz
-  lib.pc_grouped_gemm_tc.argtypes = [vp, i32, vp, sz, vp]
+  lib.pc_grouped_gemm_tc.argtypes = [vp, i32, vp, sz, i32, vp]
   lib.pc_grouped_gemm_tc.restype = i32
   _lib = lib
   return lib

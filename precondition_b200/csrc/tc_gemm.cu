@@ -27,6 +27,7 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "root_kernels.cuh"
@@ -1595,15 +1596,16 @@ int tc_debug_gemm(const float* a, const float* b, float* c, int batch, int n, in
 // tcgen05 grouped GEMM on fp32 operands:  C = alpha * A B^T-view + beta * C_in
 // (the statistics update L <- b2 L + (1-b2) G G^T, DS:1440-1470, and the preconditioner
 // application, DS:1676-1708, for blocks whose output sizes are multiples of 128).
-//   1. tc_pack_max_kernel / tc_pack_kernel: every operand view (strided, possibly
-//      transposed -- the same two-level addressing as pc_gemm_desc) is converted ONCE into
-//      scaled-fp16 plane tiles (128 x 64, contiguous): X ~ (X0 + 2^-11 X1) / s with a
-//      per-operand power-of-two s that brings max|X| to ~2^10, so gradients of any
+//   1. tc_pack_kernel: every operand view (strided, possibly transposed -- the same
+//      two-level addressing as pc_gemm_desc) is converted ONCE into scaled-fp16 plane tiles
+//      (128 x 64, contiguous): X ~ (X0 + 2^-11 X1) / s with a per-TILE power-of-two s that
+//      brings the tile's max|X| to ~2^10 (block floating point), so gradients of any
 //      magnitude keep 22 mantissa bits (fp16 alone would flush 1e-6 gradients).
 //   2. tc_ggemm_kernel: the Newton engine's pipeline (TMA producer, single-thread
 //      tcgen05.mma issuer with the scale-input-d three-pass scheme, 64-column K-chunks
 //      summed in fp32 registers, TMEM output stages) with an fp32 epilogue:
-//      C = alpha / (sA sB) * acc + beta * C_in.  Symmetric products (A == B: the Gram
+//      every K-chunk is multiplied by 1 / (sA sB) of its two tiles as it is added, then
+//      C = alpha * acc + beta * C_in.  Symmetric products (A == B: the Gram
 //      update) compute lower tiles only and write the mirror from the same registers.
 // ===========================================================================
 struct TcGgItem {
@@ -1619,7 +1621,7 @@ struct TcGgWork { int z, tm, tn, pad; };
 struct TcGgOperand {  // one packed operand: view + where its tiles go
   const float* base;
   int64_t s_io, s_i, s_ko, s_ki;
-  int i_inner, k_inner, rows, k, kblocks, tile0, scale_slot, pad;
+  int i_inner, k_inner, rows, k, kblocks, tile0;
 };
 
 __device__ __forceinline__ float tc_gg_view(const TcGgOperand& o, int i, int kk) {
@@ -1629,28 +1631,11 @@ __device__ __forceinline__ float tc_gg_view(const TcGgOperand& o, int i, int kk)
   return __ldg(o.base + io * o.s_io + ii * o.s_i + ko * o.s_ko + ki * o.s_ki);
 }
 
-// max |x| per operand (bit pattern of a non-negative float orders like the float)
-__global__ void __launch_bounds__(256)
-tc_pack_max_kernel(const TcGgOperand* __restrict__ ops, uint32_t* __restrict__ maxbits) {
-  const TcGgOperand o = ops[blockIdx.y];
-  const int tiles = (o.rows / 128) * o.kblocks;
-  uint32_t mx = 0;
-  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const int tr = t / o.kblocks, kb = t - tr * o.kblocks;
-    const bool kfast = o.s_ki == 1;
-    for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
-      const int r = kfast ? e >> 6 : e & 127, c = kfast ? e & 63 : e >> 7;
-      const uint32_t ab = absbits(tc_gg_view(o, tr * 128 + r, kb * 64 + c));
-      mx = ab > mx ? ab : mx;
-    }
-  }
-  mx = warp_max_u32(mx);
-  if ((threadIdx.x & 31) == 0 && mx) atomicMax(maxbits + o.scale_slot, mx);
-}
-
+// Power-of-two scale that brings max|x| of a tile to [2^9, 2^10): fp16 then holds the tile's
+// largest entries with full precision and the 2^11-scaled residual stays in range.
 __device__ __forceinline__ float tc_gg_scale(uint32_t maxbits) {
   const float mx = __uint_as_float(maxbits);
-  if (!(mx > 0.f) || !(mx < 3.0e38f)) return 1.0f;  // zero, inf or NaN operand: leave as is
+  if (!(mx > 0.f) || !(mx < 3.0e38f)) return 1.0f;  // zero, inf or NaN tile: leave as is
   int e = 0;
   frexpf(mx, &e);  // mx in [2^(e-1), 2^e)
   int sh = 10 - e;
@@ -1658,31 +1643,46 @@ __device__ __forceinline__ float tc_gg_scale(uint32_t maxbits) {
   return ldexpf(1.0f, sh);
 }
 
+// One CTA per 128 x 64 tile of an operand view: stage the tile in shared memory, reduce its
+// max |x|, then write the two fp16 planes scaled by the TILE's power of two (block floating
+// point; the GEMM multiplies each K-chunk by 1 / (sA sB) when it adds it in fp32).
 __global__ void __launch_bounds__(256)
-tc_pack_kernel(const TcGgOperand* __restrict__ ops, const uint32_t* __restrict__ maxbits,
+tc_pack_kernel(const TcGgOperand* __restrict__ ops, float* __restrict__ inv_scale,
                uint16_t* __restrict__ plane0, uint16_t* __restrict__ plane1) {
   __shared__ float tile[64][129];
+  __shared__ uint32_t red[32];
   const TcGgOperand o = ops[blockIdx.y];
   const int tiles = (o.rows / 128) * o.kblocks;
-  const float sc = tc_gg_scale(maxbits[o.scale_slot]);
   const bool kfast = o.s_ki == 1;
+  const bool simple = o.i_inner >= o.rows && o.k_inner >= o.k;  // one-level addressing
   for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int tr = t / o.kblocks, kb = t - tr * o.kblocks;
+    uint32_t mx = 0;
     __syncthreads();
     for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {  // coalesced along the fast axis
       const int r = kfast ? e >> 6 : e & 127, c = kfast ? e & 63 : e >> 7;
-      tile[c][r] = tc_gg_view(o, tr * 128 + r, kb * 64 + c) * sc;
+      const int i = tr * 128 + r, kk = kb * 64 + c;
+      float v;
+      if (simple) v = kk < o.k ? __ldg(o.base + (int64_t)i * o.s_i + (int64_t)kk * o.s_ki) : 0.f;
+      else v = tc_gg_view(o, i, kk);
+      tile[c][r] = v;
+      const uint32_t ab = absbits(v);
+      mx = ab > mx ? ab : mx;
     }
-    __syncthreads();
+    mx = block_max_u32(mx, red);  // (contains the barrier that publishes the tile)
+    const float sc = tc_gg_scale(mx);
+    if (threadIdx.x == 0) inv_scale[o.tile0 + t] = 1.0f / sc;
     const size_t base = (size_t)(o.tile0 + t) * 8192;
-    for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
-      const int r = e >> 6, c = e & 63;
-      const float v = tile[c][r];
-      const float cl = fabsf(v) > 65504.0f ? copysignf(65504.0f, v) : v;
-      const __half h0 = __float2half_rn(cl);
-      const float r1 = (cl - __half2float(h0)) * TC_FP16_SCALE;
-      plane0[base + e] = __half_as_ushort(h0);
-      plane1[base + e] = __half_as_ushort(__float2half_rn(r1));
+    for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {  // two columns per thread
+      const int r = e >> 5, c = (e & 31) * 2;
+      const float v0 = tile[c][r] * sc, v1 = tile[c + 1][r] * sc;
+      uint32_t w0, w1;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w0) : "f"(v1), "f"(v0));
+      const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w1)
+          : "f"((v1 - f2.y) * TC_FP16_SCALE), "f"((v0 - f2.x) * TC_FP16_SCALE));
+      reinterpret_cast<uint32_t*>(plane0 + base)[e] = w0;
+      reinterpret_cast<uint32_t*>(plane1 + base)[e] = w1;
     }
   }
 }
@@ -1703,7 +1703,7 @@ constexpr int TC_GG_STAGES = 3;
 __global__ void __launch_bounds__(TC_GG_THREADS, 1)
 tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                 const TcGgItem* __restrict__ items, const TcGgWork* __restrict__ work,
-                const uint32_t* __restrict__ maxbits, int total_work) {
+                const float* __restrict__ inv_scale, int total_work) {
   constexpr int kStageBytes = 4 * TC_TILE_BYTES;  // A0 A1 B0 B1
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1799,12 +1799,17 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     int chunk = 0, tile = 0;
 #pragma unroll 1
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const int kblocks = items[work[w].z].kblocks;
+      const TcGgWork wk = work[w];
+      const TcGgItem& it = items[wk.z];
+      const int kblocks = it.kblocks;
+      const float* sa = inv_scale + it.a_tile0 + wk.tm * kblocks;
+      const float* sb = inv_scale + it.b_tile0 + wk.tn * kblocks;
       float sum[TC_BN];
 #pragma unroll
       for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
 #pragma unroll 1
       for (int kb = 0; kb < kblocks; ++kb, ++chunk) {
+        const float f = __ldg(sa + kb) * __ldg(sb + kb);  // 1 / (sA sB) of this K-chunk's tiles
         const int acc = chunk & 1;
         mbar_wait(tfull_bar(acc), (chunk >> 1) & 1);
         tcgen05_fence_after();
@@ -1815,7 +1820,8 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i)
+            sum[c * 32 + i] = fmaf(__uint_as_float(r[i]), f, sum[c * 32 + i]);
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -1852,8 +1858,7 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       const int o = tile & 1;
       mbar_wait(ofull_bar(o), (tile >> 1) & 1);
       tcgen05_fence_after();
-      const float sa = tc_gg_scale(maxbits[2 * wk.z]), sb = tc_gg_scale(maxbits[2 * wk.z + 1]);
-      const float alpha = it.alpha / (sa * (it.symmetric ? sa : sb));
+      const float alpha = it.alpha;
       const int row = wk.tm * TC_BM + q * 32 + lane;
       const int io = row / it.c_iinner, ii = row - io * it.c_iinner;
       const int64_t rowoff = io * it.c_sio + ii * it.c_sii;
@@ -1942,7 +1947,6 @@ static void tc_gg_plan(const pc_gemm_desc* descs, int count, TcGgPlan* pl) {
     oa.base = d.a; oa.s_io = d.a_sio; oa.s_i = d.a_si; oa.s_ko = d.a_sko; oa.s_ki = d.a_ski;
     oa.i_inner = d.a_iinner > 0 ? d.a_iinner : d.m; oa.k_inner = d.a_kinner > 0 ? d.a_kinner : d.k;
     oa.rows = d.m; oa.k = d.k; oa.kblocks = it.kblocks; oa.tile0 = pl->total_tiles;
-    oa.scale_slot = 2 * z;
     it.a_tile0 = oa.tile0;
     pl->total_tiles += (d.m / 128) * it.kblocks;
     pl->ops.push_back(oa);
@@ -1953,7 +1957,6 @@ static void tc_gg_plan(const pc_gemm_desc* descs, int count, TcGgPlan* pl) {
       ob.base = d.b; ob.s_io = 0; ob.s_i = d.b_sj; ob.s_ko = d.b_sko; ob.s_ki = d.b_ski;
       ob.i_inner = d.n; ob.k_inner = d.b_kinner > 0 ? d.b_kinner : d.k;
       ob.rows = d.n; ob.k = d.k; ob.kblocks = it.kblocks; ob.tile0 = pl->total_tiles;
-      ob.scale_slot = 2 * z + 1;
       it.b_tile0 = ob.tile0;
       pl->total_tiles += (d.n / 128) * it.kblocks;
       pl->ops.push_back(ob);
@@ -1970,7 +1973,7 @@ static size_t tc_gg_bytes(const TcGgPlan& pl) {
   s += align_up(pl.items.size() * sizeof(TcGgItem), 256);
   s += align_up(pl.ops.size() * sizeof(TcGgOperand), 256);
   s += align_up(pl.work.size() * sizeof(TcGgWork), 256);
-  s += align_up(2 * pl.items.size() * sizeof(uint32_t), 256);
+  s += align_up((size_t)pl.total_tiles * sizeof(float), 256);
   s += 1024 + 2 * align_up((size_t)pl.total_tiles * TC_TILE_BYTES, 1024);
   return s + 1024;
 }
@@ -1982,7 +1985,7 @@ size_t tc_grouped_gemm_workspace_bytes(const pc_gemm_desc* descs, int count) {
 }
 
 int tc_grouped_gemm(const pc_gemm_desc* descs, int count, void* workspace, size_t workspace_bytes,
-                    cudaStream_t stream) {
+                    int reuse_plan, cudaStream_t stream) {
   for (int z = 0; z < count; ++z)
     PC_REQUIRE(tc_gg_supported(descs[z]),
                "descriptor %d is not eligible for the tcgen05 grouped GEMM (m, n %% 128, alignment)", z);
@@ -2005,18 +2008,19 @@ int tc_grouped_gemm(const pc_gemm_desc* descs, int count, void* workspace, size_
   TcGgItem* d_items = reinterpret_cast<TcGgItem*>(w); w += align_up(pl.items.size() * sizeof(TcGgItem), 256);
   TcGgOperand* d_ops = reinterpret_cast<TcGgOperand*>(w); w += align_up(pl.ops.size() * sizeof(TcGgOperand), 256);
   TcGgWork* d_work = reinterpret_cast<TcGgWork*>(w); w += align_up(pl.work.size() * sizeof(TcGgWork), 256);
-  uint32_t* d_max = reinterpret_cast<uint32_t*>(w); w += align_up(2 * pl.items.size() * sizeof(uint32_t), 256);
+  float* d_inv = reinterpret_cast<float*>(w); w += align_up((size_t)pl.total_tiles * sizeof(float), 256);
   uint16_t* plane0 = reinterpret_cast<uint16_t*>(align_up((size_t)w, 1024));
   uint16_t* plane1 = plane0 + align_up((size_t)pl.total_tiles * TC_TILE_BYTES, 1024) / 2;
-  // the plan lives in heap vectors: synchronous copies (pageable memory) keep them valid
-  PC_CUDA_CHECK(cudaMemcpyAsync(d_items, pl.items.data(), pl.items.size() * sizeof(TcGgItem),
-                                cudaMemcpyHostToDevice, stream));
-  PC_CUDA_CHECK(cudaMemcpyAsync(d_ops, pl.ops.data(), pl.ops.size() * sizeof(TcGgOperand),
-                                cudaMemcpyHostToDevice, stream));
-  PC_CUDA_CHECK(cudaMemcpyAsync(d_work, pl.work.data(), pl.work.size() * sizeof(TcGgWork),
-                                cudaMemcpyHostToDevice, stream));
-  PC_CUDA_CHECK(cudaMemsetAsync(d_max, 0, 2 * pl.items.size() * sizeof(uint32_t), stream));
-  PC_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (!reuse_plan) {
+    // the plan lives in heap vectors: wait for the copies before they go out of scope
+    PC_CUDA_CHECK(cudaMemcpyAsync(d_items, pl.items.data(), pl.items.size() * sizeof(TcGgItem),
+                                  cudaMemcpyHostToDevice, stream));
+    PC_CUDA_CHECK(cudaMemcpyAsync(d_ops, pl.ops.data(), pl.ops.size() * sizeof(TcGgOperand),
+                                  cudaMemcpyHostToDevice, stream));
+    PC_CUDA_CHECK(cudaMemcpyAsync(d_work, pl.work.data(), pl.work.size() * sizeof(TcGgWork),
+                                  cudaMemcpyHostToDevice, stream));
+    PC_CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
   CUtensorMap maps[2];
   for (int plx = 0; plx < 2; ++plx) {
     cuuint64_t dims[3] = {64, 128, (cuuint64_t)pl.total_tiles};
@@ -2032,8 +2036,11 @@ int tc_grouped_gemm(const pc_gemm_desc* descs, int count, void* workspace, size_
     }
   }
   const int nops = (int)pl.ops.size();
-  tc_pack_max_kernel<<<dim3(32, nops), 256, 0, stream>>>(d_ops, d_max);
-  tc_pack_kernel<<<dim3(64, nops), 256, 0, stream>>>(d_ops, d_max, plane0, plane1);
+  int max_tiles = 1;
+  for (const TcGgOperand& o : pl.ops)
+    max_tiles = std::max(max_tiles, (o.rows / 128) * o.kblocks);
+  tc_pack_kernel<<<dim3((unsigned)std::min(max_tiles, 1024), nops), 256, 0, stream>>>(
+      d_ops, d_inv, plane0, plane1);
   constexpr size_t smem = (size_t)TC_GG_STAGES * 4 * TC_TILE_BYTES + 1024 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -2046,9 +2053,9 @@ int tc_grouped_gemm(const pc_gemm_desc* descs, int count, void* workspace, size_
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int total_work = (int)pl.work.size();
   const int grid = total_work < sms ? total_work : sms;
-  tc_ggemm_kernel<<<grid, TC_GG_THREADS, smem, stream>>>(maps[0], maps[1], d_items, d_work, d_max,
+  tc_ggemm_kernel<<<grid, TC_GG_THREADS, smem, stream>>>(maps[0], maps[1], d_items, d_work, d_inv,
                                                         total_work);
-  count_launch(3);
+  count_launch(2);
   PC_CUDA_CHECK(cudaGetLastError());
   return PC_OK;
 }
@@ -2071,9 +2078,10 @@ extern "C" size_t pc_grouped_gemm_tc_workspace_bytes(const pc_gemm_desc* descs_h
 }
 
 extern "C" int pc_grouped_gemm_tc(const pc_gemm_desc* descs_host, int count, void* workspace,
-                                  size_t workspace_bytes, void* stream) {
+                                  size_t workspace_bytes, int reuse_plan, void* stream) {
   PC_REQUIRE(count >= 0, "bad count");
   if (count == 0) return PC_OK;
   PC_REQUIRE(descs_host && workspace, "null pointer argument");
-  return pc::tc_grouped_gemm(descs_host, count, workspace, workspace_bytes, (cudaStream_t)stream);
+  return pc::tc_grouped_gemm(descs_host, count, workspace, workspace_bytes, reuse_plan,
+                             (cudaStream_t)stream);
 }

@@ -276,11 +276,12 @@ class TcGemmList:
     if not self.count:
       return
     lib = _lib.load()
-    if self.ws is None:  # private workspace: the packed planes must not alias other scratch
+    reuse = self.ws is not None  # private workspace: the uploaded plan stays valid
+    if self.ws is None:
       self.ws = torch.empty(self.nbytes + 4096, dtype=torch.uint8, device=self.device)
     with torch.cuda.device(self.device):
       _lib.check(lib.pc_grouped_gemm_tc(ctypes.cast(self.arr, ctypes.c_void_p), self.count,
-                                        _ptr(self.ws), self.ws.numel(),
+                                        _ptr(self.ws), self.ws.numel(), int(reuse),
                                         ctypes.c_void_p(_stream())))
     gpu_launches += 1
 

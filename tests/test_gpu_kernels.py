@@ -221,3 +221,12 @@ def test_tc_grouped_gemm_gram_update_and_apply(scale):
     assert err <= 2e-6, err
     if sym:
       np.testing.assert_array_equal(got, got.T)
+  # second and third call of a static list re-use the plan uploaded by the first one
+  lst2 = ops.TcGemmList(descs[2:], g.device)
+  for _ in range(3):
+    s2.zero_(); out.zero_()
+    lst2.run()
+  torch.cuda.synchronize()
+  for got, w, sym in zip((s2, out), want[2:], (True, False)):
+    ref = np.tril(w) + np.tril(w, -1).T if sym else w
+    assert np.abs(got.cpu().numpy() - ref).max() / np.abs(ref).max() <= 2e-6
