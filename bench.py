@@ -273,19 +273,51 @@ def run_ours(a):
   host_metrics = torch.empty((B, 5), dtype=torch.float32).pin_memory()
   dev_in = torch.empty_like(xs)
 
-  def e2e_step():
-    dev_in.copy_(host_in, non_blocking=True)
-    r, m = ops.matrix_inverse_pth_root_batched(dev_in, ps, None, engine=engine, out=roots)
-    if world > 1:
-      dist.all_gather_into_tensor(gathered, r)
-    host_out.copy_(r, non_blocking=True)
-    host_metrics.copy_(m, non_blocking=True)
+  # A double-buffered serving loop over the public API: the upload of step i+1 and the
+  # download of step i-1 run on their own streams beside the solve of step i.  Every step's
+  # H2D and D2H copies happen inside the timed region.
+  cur = torch.cuda.current_stream(dev)
+  s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+  dev_ins = [dev_in, torch.empty_like(xs)]
+  dev_outs = [roots, torch.empty_like(xs)]
+  ev_in = [torch.cuda.Event() for _ in range(2)]      # upload of slot landed
+  ev_solved = [torch.cuda.Event() for _ in range(2)]  # solve that read/wrote slot finished
+  ev_out = [torch.cuda.Event() for _ in range(2)]     # download of slot finished
 
-  e2e_step()
+  def upload(i):
+    k = i % 2
+    with torch.cuda.stream(s_h2d):
+      s_h2d.wait_event(ev_solved[k])  # the previous user of this input slot is done
+      dev_ins[k].copy_(host_in, non_blocking=True)
+      ev_in[k].record(s_h2d)
+
+  def e2e_loop(steps):
+    s_h2d.wait_stream(cur)
+    s_d2h.wait_stream(cur)
+    upload(0)
+    for i in range(steps):
+      k = i % 2
+      if i + 1 < steps:
+        upload(i + 1)
+      cur.wait_event(ev_in[k])
+      cur.wait_event(ev_out[k])  # the previous download of this output slot is done
+      r, m = ops.matrix_inverse_pth_root_batched(dev_ins[k], ps, None, engine=engine,
+                                                 out=dev_outs[k])
+      if world > 1:
+        dist.all_gather_into_tensor(gathered, r)
+      ev_solved[k].record(cur)
+      with torch.cuda.stream(s_d2h):
+        s_d2h.wait_event(ev_solved[k])
+        host_out.copy_(r, non_blocking=True)
+        host_metrics.copy_(m, non_blocking=True)
+        ev_out[k].record(s_d2h)
+    cur.wait_stream(s_h2d)
+    cur.wait_stream(s_d2h)
+
+  e2e_loop(2)
   barrier()
   e0.record()
-  for _ in range(a.steps):
-    e2e_step()
+  e2e_loop(a.steps)
   e1.record()
   barrier()
   t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -294,7 +326,9 @@ def run_ours(a):
   e2e_ms = float(t.item()) / a.steps
   e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
          "h2d_bytes_per_step": int(B * n * n * 4), "d2h_bytes_per_step": int(B * n * n * 4 + B * 20),
-         "ms_per_step": e2e_ms}
+         "ms_per_step": e2e_ms,
+         "pipelining": "double-buffered: H2D of step i+1 and D2H of step i-1 overlap the solve of "
+                       "step i (separate copy streams); all copies inside the timed region"}
 
   # ---- roofline of the dominant kernel (Newton-chain GEMM launches): one extra
   #      step with CUDA events around every GEMM launch on the launching stream ----
