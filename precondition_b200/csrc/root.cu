@@ -377,7 +377,7 @@ static size_t header_bytes(int batch, int n) {
   s += align_up(sizeof(uint32_t) * batch, 256);
   s += 256;
   s += align_up(sizeof(float) * n, 256);
-  s += align_up(sizeof(float) * 2 * (size_t)batch * n, 256);
+  s += align_up(sizeof(float) * 2 * (size_t)batch * (n < 4 ? 4 : n), 256);
   return s;
 }
 
@@ -481,7 +481,7 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
   ws.errbits = reinterpret_cast<uint32_t*>(w); w += align_up(sizeof(uint32_t) * batch, 256);
   ws.unfinished = reinterpret_cast<int*>(w); w += 256;
   ws.v0 = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * n, 256);
-  ws.ybuf = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * 2 * (size_t)batch * n, 256);
+  ws.ybuf = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * 2 * (size_t)batch * (n < 4 ? 4 : n), 256);
   ws.engine_mem = w;
 
   // Per-host-thread pinned scratch: exponents (decide how many GEMM launches one Newton
@@ -557,6 +557,13 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
     }
     if (it >= max_total) continue;
     if (engine == PC_ENGINE_SIMT_FP32) {
+      if (it == 0 && n >= 256) {  // first initialisation: whole-GPU strip kernels
+        const int strips = (n + 31) / 32;
+        root_norm_strip_kernel<<<dim3(strips, batch), 256, 0, stream>>>(xs, ws.ctl, n, strips, prm,
+                                                                       ws.ybuf, batch);
+        root_init_strip_kernel<F32Store><<<dim3(strips, batch), 1024, 0, stream>>>(
+            xs, ws.ctl, f32, batch, n, strips, prm, ws.ybuf);
+      }
       root_init_kernel<F32Store><<<batch, n >= 512 ? 1024 : 256, 0, stream>>>(
           xs, ws.ctl, f32, batch, n, prm, roots);
       count_launch(1);
@@ -574,7 +581,8 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
       count_launch(max_steps);
       gemm_count(max_steps);
     } else {
-      rc = tc_engine_iteration(&tc, xs, ws.ctl, ws.errbits, prm, roots, max_steps, stream);
+      rc = tc_engine_iteration(&tc, xs, ws.ctl, ws.errbits, prm, roots, max_steps,
+                               it == 0 ? ws.ybuf : nullptr, stream);
       if (rc != PC_OK) return rc;
     }
     count_launch(1);

@@ -17,8 +17,11 @@ bool tc_engine_available();
 size_t tc_engine_bytes(int batch, int n, int planes);
 int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt,
                    cudaStream_t stream);
+// first_init_scratch != nullptr: first iteration of a call -- initialise with the whole-GPU
+// strip kernels (scratch of batch * (n / 32 + 2) floats)
 int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* errbits,
-                        RootParams prm, float* roots, int max_steps, cudaStream_t stream);
+                        RootParams prm, float* roots, int max_steps, float* first_init_scratch,
+                        cudaStream_t stream);
 int tc_engine_final(TcEngine* e, const RootCtl* ctl, float* roots, float* metrics,
                     cudaStream_t stream);
 

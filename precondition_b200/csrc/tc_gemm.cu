@@ -1464,7 +1464,8 @@ static int launch_phase(TcHostState* hs, int passes, int s, cudaStream_t stream)
 }
 
 int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* errbits,
-                        RootParams prm, float* roots, int max_steps, cudaStream_t stream) {
+                        RootParams prm, float* roots, int max_steps, float* first_init_scratch,
+                        cudaStream_t stream) {
   auto* hs = static_cast<TcHostState*>(e->host_state);
   hs->prm.ctl = ctl;
   hs->prm.errbits = errbits;
@@ -1473,6 +1474,14 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
   ps.fmt = hs->fmt;
   ps.buf_stride = hs->prm.buf_stride;
   ps.mat_elems = hs->prm.mat_stride;
+  if (first_init_scratch && e->n >= 256) {
+    const int strips = (e->n + 31) / 32;
+    root_norm_strip_kernel<<<dim3(strips, e->batch), 256, 0, stream>>>(
+        xs, ctl, e->n, strips, prm, first_init_scratch, e->batch);
+    root_init_strip_kernel<PlaneStore><<<dim3(strips, e->batch), 1024, 0, stream>>>(
+        xs, ctl, ps, e->batch, e->n, strips, prm, first_init_scratch);
+    count_launch(2);
+  }
   root_init_kernel<PlaneStore><<<e->batch, 1024, 0, stream>>>(xs, ctl, ps, e->batch, e->n, prm,
                                                              roots);
   count_launch(1);
