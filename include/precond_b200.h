@@ -223,6 +223,19 @@ int pc_fd_update_batched(const float* new_grad, const float* prev, const int32_t
                          const pc_fd_options* opt, float* out, float* metrics, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* eigh-based low-rank root for compression_rank != 0 without frequent_directions:
+ * replaces _low_rank_root (DS:1033-1120) as vmapped by new_mi_pth_root (DS:2706-2738).
+ *   xs [batch, d, d] f32 (lower triangle authoritative), ps [batch] i32, padding_starts [batch]
+ *   i32 or NULL, compression_rank: > 0 keeps the largest eigenvalues, < 0 the smallest
+ *   out [batch, d, |rank|+2] packed (eigvecs, inverted eigenvalues, const; DS:548-552),
+ *   metrics [batch, 5]: error = max |U^T reg U - diag(e)| (DS:1076-1081).  d <= 512. */
+size_t pc_low_rank_root_workspace_bytes(int batch, int d);
+int pc_low_rank_root_batched(const float* xs, const int32_t* ps, const int32_t* padding_starts,
+                             int batch, int d, int compression_rank, float ridge_epsilon,
+                             float error_tolerance, int relative_matrix_epsilon, float* out,
+                             float* metrics, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 /* Dense form of the operator a packed low-rank preconditioner applies in
  * _precondition_block (DS:1690-1705, _low_rank_unpack DS:540-545):
  *   dense[b] = c I + V diag(lambda^- - c) V^T   (identity if the has_zeros flag is set),

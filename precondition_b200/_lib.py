@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "pc_fd_options_default", "pc_fd_update_workspace_bytes", "pc_fd_update_batched",
     "pc_low_rank_to_dense_workspace_bytes", "pc_low_rank_to_dense",
     "pc_grouped_gemm_tc_workspace_bytes", "pc_grouped_gemm_tc",
+    "pc_low_rank_root_workspace_bytes", "pc_low_rank_root_batched",
 )
 
 
@@ -148,6 +149,11 @@ def load() -> ctypes.CDLL:
   lib.pc_grouped_gemm_tc_workspace_bytes.restype = sz
   lib.pc_grouped_gemm_tc.argtypes = [vp, i32, vp, sz, i32, vp]
   lib.pc_grouped_gemm_tc.restype = i32
+  lib.pc_low_rank_root_workspace_bytes.argtypes = [i32, i32]
+  lib.pc_low_rank_root_workspace_bytes.restype = sz
+  lib.pc_low_rank_root_batched.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, i32, vp, vp, vp,
+                                           sz, vp]
+  lib.pc_low_rank_root_batched.restype = i32
   _lib = lib
   return lib
 

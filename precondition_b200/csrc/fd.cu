@@ -663,6 +663,189 @@ int run_low_rank_to_dense(const float* packed, int batch, int d, int rank, float
   return PC_OK;
 }
 
+
+// ===========================================================================
+// eigh-based low-rank root (compression_rank != 0 without frequent_directions):
+// _low_rank_root, DS:1033-1120.  reg = masked A + ridge I_m; all eigenpairs by the cluster
+// Jacobi kernel (d <= 512); keep the |rank| largest (rank > 0) or smallest (rank < 0)
+// eigenvalues inverted to the power -1/p, average the rest into `const`, pack (DS:548-552).
+// The reported error is max |U^T reg U - diag(e)| like DS:1076-1081.
+// ===========================================================================
+int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n, int num_iters,
+                        float tol, float* lambdas, int32_t* iters, struct RootCtl* ctl,
+                        float* v0_dev, float* ybuf, cudaStream_t stream);  // root.cu
+
+// reg (two copies) <- masked A; lambda-independent part of DS:1052-1060
+__global__ void lr_mask_kernel(const float* __restrict__ xs, const int32_t* __restrict__ pads,
+                               int d, float* __restrict__ a_masked) {
+  const int b = blockIdx.y;
+  const int pad = pads ? min(max(pads[b], 0), d) : d;
+  const size_t nn = (size_t)d * d;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / d), j = (int)(e - (size_t)i * d);
+    // lower triangle authoritative, like the Newton solver
+    const float v = xs[(size_t)b * nn + (size_t)max(i, j) * d + min(i, j)];
+    a_masked[(size_t)b * nn + e] = (i < pad && j < pad) ? v : 0.f;
+  }
+}
+// reg = a + ridge I_m (in place), copy kept for the error check; ridge per matrix (DS:1069)
+__global__ void lr_damp_kernel(float* __restrict__ a, float* __restrict__ copy,
+                               const float* __restrict__ lambdas, const int32_t* __restrict__ pads,
+                               int d, float ridge_epsilon, float error_tolerance, int relative,
+                               float* __restrict__ ridge_out) {
+  const int b = blockIdx.y;
+  const int pad = pads ? min(max(pads[b], 0), d) : d;
+  const float max_ev = relative ? lambdas[b] : 1.0f;
+  const float ridge = ridge_epsilon * fmaxf(max_ev, error_tolerance);
+  if (blockIdx.x == 0 && threadIdx.x == 0) ridge_out[b] = ridge;
+  const size_t nn = (size_t)d * d;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / d), j = (int)(e - (size_t)i * d);
+    float v = a[(size_t)b * nn + e];
+    if (i == j && i < pad) v += ridge;
+    a[(size_t)b * nn + e] = v;
+    copy[(size_t)b * nn + e] = v;
+  }
+}
+// err[b] = max over rows i and real eigen-columns j (sorted rank < pad) of
+// |recovered[i][j] - delta_ij e_j|   (DS:1076-1081)
+__global__ void __launch_bounds__(256)
+lr_error_kernel(const float* __restrict__ recovered, const float* __restrict__ sorted,
+                const int32_t* __restrict__ pads, int d, uint32_t* __restrict__ errbits) {
+  const int b = blockIdx.y;
+  const int pad = pads ? min(max(pads[b], 0), d) : d;
+  uint32_t mx = 0;
+  const size_t nn = (size_t)d * d;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / d), j = (int)(e - (size_t)i * d);
+    if (j >= pad) continue;
+    const float v = recovered[(size_t)b * nn + e] - (i == j ? sorted[(size_t)b * d + j] : 0.f);
+    const uint32_t ab = absbits(v);
+    mx = ab > mx ? ab : mx;
+  }
+  mx = warp_max_u32(mx);
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(errbits + b, mx);
+}
+// selection, inversion, averaging and packing: DS:1083-1112, DS:548-552
+__global__ void __launch_bounds__(256)
+lr_pack_kernel(const float* __restrict__ vs, const float* __restrict__ sorted,
+               const float* __restrict__ ridge_all, const int32_t* __restrict__ ps,
+               const int32_t* __restrict__ pads, const uint32_t* __restrict__ errbits, int d,
+               int rank_signed, float* __restrict__ out_all, float* __restrict__ metrics) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const int k = rank_signed < 0 ? -rank_signed : rank_signed, pd = k + 2;
+  const int pad = pads ? min(max(pads[b], 0), d) : d;
+  const float ridge = ridge_all[b];
+  const float alpha = -1.0f / (float)ps[b];
+  const float* e = sorted + (size_t)b * d;            // descending
+  const float* V = vs + (size_t)b * d * d;             // rows = eigenvectors, descending order
+  float* out = out_all + (size_t)b * d * pd;
+  auto inv_e = [&](int idx) {  // idx in descending order; padded eigenvalues (idx >= pad) are 0
+    return idx < pad ? powf(fmaxf(e[idx], ridge), alpha) : 0.f;
+  };
+  // kept slot t <-> descending index: rank > 0: t; rank < 0: pad - 1 - t (ascending real ones)
+  auto kept_idx = [&](int t) { return rank_signed > 0 ? t : pad - 1 - t; };
+  float part = 0.f;  // sum of inv_e over everything that is not kept (DS:1101-1106)
+  for (int idx = threadIdx.x; idx < pad; idx += blockDim.x) {
+    const bool kept = rank_signed > 0 ? idx < k : idx >= pad - k;
+    if (!kept) part += inv_e(idx);
+  }
+  const float total = block_sum(part, red);
+  const int n_avg = pad - k;
+  const float cst = total / (n_avg > 0 ? (float)n_avg : 1.0f);
+  const bool zero_all = pad == 0;  // DS:1115-1118
+  for (size_t x = threadIdx.x; x < (size_t)d * pd; x += blockDim.x) {
+    const int i = (int)(x / pd), j = (int)(x - (size_t)i * pd);
+    float v = 0.f;
+    if (!zero_all) {
+      if (j < k) {
+        const int idx = kept_idx(j);
+        v = (idx >= 0 && idx < d) ? V[(size_t)idx * d + i] : 0.f;
+      } else if (j == k) {
+        if (i < k) { const int idx = kept_idx(i); v = (idx >= 0 && idx < d) ? inv_e(idx) : 0.f; }
+      } else if (i == 0) {
+        v = cst;
+      }
+    }
+    out[x] = v;
+  }
+  if (threadIdx.x == 0 && metrics) {
+    float* m = metrics + (size_t)b * PC_NUM_METRICS;
+    m[0] = zero_all ? 0.f : __uint_as_float(errbits[b]);
+    m[1] = 0.f; m[2] = 0.f; m[3] = 0.f; m[4] = 0.f;
+  }
+}
+
+size_t low_rank_root_bytes(int batch, int d) {
+  const size_t B = (size_t)batch, nn = (size_t)d * d * 4;
+  return 6 * align_up(B * nn, 256) + 4 * align_up(B * d * 4, 256) + align_up(B * kJacMaxSweeps * 4, 256) +
+         align_up((size_t)d * 4, 256) + align_up(2 * B * d * 4, 256) + 2048;
+}
+
+int run_low_rank_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch, int d,
+                      int rank_signed, float ridge_epsilon, float error_tolerance, int relative,
+                      float* out, float* metrics, void* workspace, size_t workspace_bytes,
+                      cudaStream_t stream) {
+  if (workspace_bytes < low_rank_root_bytes(batch, d)) {
+    set_error("low-rank root workspace too small: %zu < %zu", workspace_bytes,
+              low_rank_root_bytes(batch, d));
+    return PC_ERR_WORKSPACE;
+  }
+  const size_t B = (size_t)batch, nn = (size_t)d * d;
+  char* w = reinterpret_cast<char*>(align_up((size_t)workspace, 256));
+  auto take = [&](size_t bytes) { char* p = w; w += align_up(bytes, 256); return p; };
+  float* reg = (float*)take(B * nn * 4);       // destroyed by the Jacobi solve
+  float* reg_copy = (float*)take(B * nn * 4);
+  float* vt = (float*)take(B * nn * 4);
+  float* vs = (float*)take(B * nn * 4);        // eigenvectors as rows, sorted descending
+  float* t1 = (float*)take(B * nn * 4);
+  float* rec = (float*)take(B * nn * 4);
+  float* theta = (float*)take(B * d * 4);
+  float* sorted = (float*)take(B * d * 4);
+  int* order = (int*)take(B * d * 4);
+  float* lambdas = (float*)take(B * d * 4);    // [batch] lambdas, [batch] ridge, [batch] err bits
+  unsigned* rot = (unsigned*)take(B * kJacMaxSweeps * 4);
+  float* v0 = (float*)take((size_t)d * 4);
+  float* ybuf = (float*)take(2 * B * d * 4);
+  float* ridge = lambdas + batch;
+  uint32_t* errbits = reinterpret_cast<uint32_t*>(lambdas + 2 * (size_t)batch);
+  PC_REQUIRE(d >= 3, "low-rank root needs d >= 3");
+  const unsigned g = (unsigned)std::min<size_t>((nn + 255) / 256, 512);
+  PC_CUDA_CHECK(cudaMemsetAsync(rot, 0, B * kJacMaxSweeps * 4, stream));
+  PC_CUDA_CHECK(cudaMemsetAsync(lambdas, 0, B * d * 4, stream));
+  lr_mask_kernel<<<dim3(g, batch), 256, 0, stream>>>(xs, pads, d, reg);
+  if (relative) {
+    int rc = run_power_iteration(reg, pads, batch, d, 100, error_tolerance, lambdas, nullptr,
+                                 nullptr, v0, ybuf, stream);  // DS:1061-1067
+    if (rc != PC_OK) return rc;
+  }
+  lr_damp_kernel<<<dim3(g, batch), 256, 0, stream>>>(reg, reg_copy, lambdas, pads, d,
+                                                    ridge_epsilon, error_tolerance, relative, ridge);
+  int rc = fd_jacobi(reg, vt, d, batch, rot, theta, stream);
+  if (rc != PC_OK) return rc;
+  fd_sort_kernel<<<batch, 512, 0, stream>>>(theta, d, order, sorted);
+  fd_gather_rows_kernel<<<dim3(d, batch), 256, 0, stream>>>(vt, order, d, d, d, vs);
+  // recovered = Vs reg Vs^T
+  FdGemm q{};
+  q.alpha = 1.f; q.a = vs; q.b = reg_copy; q.c = t1;
+  q.a_bs = q.b_bs = q.c_bs = (int64_t)nn;
+  q.a_si = d; q.a_sk = 1; q.b_sj = d; q.b_sk = 1; q.c_si = d;
+  q.m = q.n = q.k = d;
+  fd_gemm(q, batch, stream);
+  q.a = t1; q.b = vs; q.c = rec;
+  fd_gemm(q, batch, stream);
+  lr_error_kernel<<<dim3(g, batch), 256, 0, stream>>>(rec, sorted, pads, d, errbits);
+  lr_pack_kernel<<<batch, 256, 0, stream>>>(vs, sorted, ridge, ps, pads, errbits, d, rank_signed,
+                                           out, metrics);
+  count_launch(7);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
 }  // namespace pc
 
 extern "C" {
@@ -679,6 +862,29 @@ int pc_low_rank_to_dense(const float* packed, int batch, int d, int rank, float*
   PC_REQUIRE(packed && dense && workspace, "null pointer argument");
   return pc::run_low_rank_to_dense(packed, batch, d, rank, dense, workspace, workspace_bytes,
                                    (cudaStream_t)stream);
+}
+
+size_t pc_low_rank_root_workspace_bytes(int batch, int d) {
+  if (batch <= 0 || d <= 0) return 0;
+  return pc::low_rank_root_bytes(batch, d) + 512;
+}
+
+int pc_low_rank_root_batched(const float* xs, const int32_t* ps, const int32_t* padding_starts,
+                             int batch, int d, int compression_rank, float ridge_epsilon,
+                             float error_tolerance, int relative_matrix_epsilon, float* out,
+                             float* metrics, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  const int k = compression_rank < 0 ? -compression_rank : compression_rank;
+  PC_REQUIRE(batch >= 0 && d > 0 && k > 0, "bad low-rank root sizes");
+  if (batch == 0) return PC_OK;
+  PC_REQUIRE(xs && ps && out && workspace, "null pointer argument");
+  PC_REQUIRE(k + 2 < d, "low-rank root needs |rank| + 2 < d (DS:535-537), got rank=%d d=%d",
+             compression_rank, d);
+  PC_REQUIRE(d <= pc::kJacMaxN, "low-rank root supports d <= %d (one Jacobi solve), got %d",
+             pc::kJacMaxN, d);
+  return pc::run_low_rank_root(xs, ps, padding_starts, batch, d, compression_rank, ridge_epsilon,
+                               error_tolerance, relative_matrix_epsilon, out, metrics, workspace,
+                               workspace_bytes, (cudaStream_t)stream);
 }
 
 void pc_fd_options_default(pc_fd_options* opt) {

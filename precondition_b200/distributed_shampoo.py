@@ -699,7 +699,10 @@ class _Shampoo:
   def _compute_preconditioners(self, step=0):
     world, rank = self._world()
     if any(bk.compressed for bk in self.buckets.values()):
-      self._fd_update(step, world, rank)
+      if self.frequent_directions:
+        self._fd_update(step, world, rank)
+      else:
+        self._low_rank_update(world, rank)
     for s, bk in self.buckets.items():
       if bk.compressed:
         continue
@@ -769,6 +772,30 @@ class _Shampoo:
       o += bk.count
       ops.low_rank_to_dense(bk.packed, r, out=bk.precs)
       self.metrics[bk.size].zero_()  # DS:1263-1264: FD reports zero error
+
+  def _low_rank_update(self, world, rank):
+    """eigh-based low-rank roots (_low_rank_root, DS:1033-1120) of every compressed bucket,
+    with the failure fallback of DS:2936-2950 on the packed preconditioners.  Computed at the
+    bucket's own size: the zero eigenvalues the reference's pad-to-max adds are dropped by its
+    own roll / flip logic (DS:1088-1098), so the packed result is the same."""
+    r = self.compression_rank
+    for s, bk in sorted(self.buckets.items()):
+      if not bk.compressed:
+        continue
+      kw = dict(ridge_epsilon=self.matrix_epsilon,
+                relative_matrix_epsilon=self.relative_matrix_epsilon)
+      if world == 1:
+        new, metrics = ops.low_rank_root_batched(bk.stats, bk.exps, r, None, **kw)
+      else:
+        pads = torch.full((bk.count,), s, dtype=torch.int32, device=self.device)
+        new, metrics = sharded_inverse_pth_roots(
+            bk.stats, bk.exps, world, rank, self.process_group, pads=pads,
+            root_fn=lambda x, p, pd, **k2: ops.low_rank_root_batched(x, p, r, pd, **k2), **kw)
+      self.metrics[s].copy_(metrics)
+      err = metrics[:, 0]
+      bad = torch.isnan(err) | (err >= self.inverse_failure_threshold)
+      bk.packed.copy_(torch.where(bad[:, None, None], bk.packed, new))
+      ops.low_rank_to_dense(bk.packed, abs(r), out=bk.precs)
 
   def _roots_sharded(self, bk, world, rank):
     kw = dict(ridge_epsilon=self.matrix_epsilon,
@@ -856,7 +883,8 @@ def sharded_inverse_pth_roots(stats, exps, world, rank, group, root_fn=None, pad
     local_ps[:hi - lo] = exps[lo:hi]
     local_pad[:hi - lo] = s if pads is None else pads[lo:hi]
   roots, metrics = root_fn(local.contiguous(), local_ps, local_pad, **kw)
-  all_roots = torch.empty((world * b, s, s), dtype=roots.dtype, device=roots.device)
+  all_roots = torch.empty((world * b,) + tuple(roots.shape[1:]), dtype=roots.dtype,
+                          device=roots.device)  # [.., s, s] roots or [.., s, rank + 2] packed
   all_metrics = torch.empty((world * b, metrics.shape[1]), dtype=metrics.dtype,
                             device=metrics.device)
   dist.all_gather_into_tensor(all_roots, roots.contiguous(), group=group)
@@ -965,8 +993,6 @@ def distributed_shampoo(
                      f"({preconditioning_compute_steps})")
   for name, val in (("lobpcg_topk_precondition", lobpcg_topk_precondition), ("eigh", eigh),
                     ("shard_optimizer_states", shard_optimizer_states),
-                    ("compression_rank without frequent_directions (eigh-based "
-                     "_low_rank_root)", compression_rank and not frequent_directions),
                     ("decay_preconditioning_compute_steps",
                      decay_preconditioning_compute_steps and end_preconditioning_compute_steps)):
     if val:

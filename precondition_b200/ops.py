@@ -136,6 +136,35 @@ def fd_update_root_batched(
   return res, metrics
 
 
+def low_rank_root_batched(xs: torch.Tensor, ps, compression_rank: int, padding_starts=None,
+                          ridge_epsilon: float = 1e-6, error_tolerance: float = 1e-6,
+                          relative_matrix_epsilon: bool = True):
+  """Batched eigh-based low-rank root, ``_low_rank_root`` (DS:1033-1120); d <= 512.
+  Returns (packed [b, d, |rank| + 2], metrics [b, 5])."""
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(xs)
+  b, d = xs.shape[0], xs.shape[1]
+  dev = xs.device
+  k = abs(compression_rank)
+  ps_t = torch.as_tensor(ps, dtype=torch.int32).to(dev).contiguous()
+  pads_t = None
+  if padding_starts is not None:
+    pads_t = torch.as_tensor(padding_starts, dtype=torch.int32).to(dev).contiguous()
+  out = torch.empty((b, d, k + 2), dtype=torch.float32, device=dev)
+  metrics = torch.empty((b, _lib.PC_NUM_METRICS), dtype=torch.float32, device=dev)
+  if b == 0:
+    return out, metrics
+  ws = _workspace(lib.pc_low_rank_root_workspace_bytes(b, d), dev)
+  with torch.cuda.device(dev):
+    _lib.check(lib.pc_low_rank_root_batched(
+        _ptr(xs), _ptr(ps_t), _ptr(pads_t), b, d, compression_rank, ridge_epsilon,
+        error_tolerance, int(relative_matrix_epsilon), _ptr(out), _ptr(metrics), _ptr(ws),
+        ws.numel(), ctypes.c_void_p(_stream())))
+  gpu_launches += 1
+  return out, metrics
+
+
 def low_rank_to_dense(packed: torch.Tensor, rank: int,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
   """Dense operator of packed low-rank preconditioners [b, d, rank+2] -> [b, d, d]

@@ -186,3 +186,53 @@ def test_fd_all_padding_and_bad_arguments():
     ops.fd_update_root_batched(torch.zeros((1, 4, 4)).cuda(), torch.zeros((1, 4, 4)).cuda(), [4], 2)
   with pytest.raises(RuntimeError):  # CPU tensors: no fallback
     ops.fd_update_root_batched(torch.zeros((1, 8, 8)), torch.zeros((1, 8, 4)), [4], 2)
+
+
+def _lr_operator(packed, rank):
+  vecs, inv, const, skip = N.low_rank_unpack(packed.astype(np.float64), abs(rank))
+  d = packed.shape[0]
+  return const * (np.eye(d) - vecs @ vecs.T) + (vecs * inv) @ vecs.T
+
+
+def test_low_rank_root_matches_reference_golden(golden_fd):
+  """eigh-based _low_rank_root (DS:1033-1120) on the reference's own outputs: positive rank
+  keeps the largest eigenvalues, negative the smallest; with and without padding.
+  Eigenvectors are defined up to sign, so the packed operator and the scalar slots are
+  compared."""
+  from precondition_b200 import ops
+  g = golden_fd
+  a = torch.as_tensor(g["lowrank/a"]).cuda()[None].contiguous()
+  for cr in (3, -3):
+    for pad in (20, 15):
+      out, m = ops.low_rank_root_batched(a, [4], cr, [pad])
+      torch.cuda.synchronize()
+      got, want = out[0].cpu().numpy(), g[f"lowrank/{cr}/{pad}/root"]
+      k = abs(cr)
+      np.testing.assert_allclose(got[:, k:], want[:, k:], rtol=2e-4, atol=1e-6,
+                                 err_msg=f"slots rank {cr} pad {pad}")
+      og, ow = _lr_operator(got, cr), _lr_operator(want, cr)
+      assert np.abs(og - ow).max() <= 5e-4 * np.abs(ow).max(), (cr, pad)
+      assert np.abs(got[pad:, :k]).sum() == 0.0
+      err, werr = float(m[0, 0]), float(g[f"lowrank/{cr}/{pad}/err"])
+      assert err <= max(10 * werr, 1e-5), (err, werr)
+
+
+@pytest.mark.parametrize("d,rank", [(64, 8), (200, -16), (512, 32)])
+def test_low_rank_root_matches_oracle_batched(d, rank):
+  rng = np.random.default_rng(d)
+  from oracle.gen_golden import gen_symmetric_matrix
+  from precondition_b200 import ops
+  mats = np.stack([gen_symmetric_matrix(rng, d, 10.0**(2 + b)) * (b + 1) for b in range(3)])
+  mats = mats.astype(np.float32)
+  ps = [4, 2, 4]
+  out, m = ops.low_rank_root_batched(torch.as_tensor(mats).cuda(), ps, rank)
+  torch.cuda.synchronize()
+  for b in range(3):
+    want, wm = N.low_rank_root(mats[b], ps[b], rank)
+    got = out[b].cpu().numpy()
+    k = abs(rank)
+    np.testing.assert_allclose(got[:k, k], want[:k, k], rtol=2e-3)       # inverted eigenvalues
+    np.testing.assert_allclose(got[0, k + 1], want[0, k + 1], rtol=2e-3)  # const
+    og, ow = _lr_operator(got, rank), _lr_operator(want, rank)
+    assert np.abs(og - ow).max() <= 2e-3 * np.abs(ow).max(), (b, d, rank)
+    assert float(m[b, 0]) < 1e-3

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 SUPPORTED = ["default", "two_devices", "quantized_int16", "sqrt_n_input",
              "adagrad_norm_output_wd", "rmsprop_clip", "rmsprop_norm_ma", "adagrad_rank3",
              "abs_eps_beta2_1",  # "none_noshape" needs rank-4 blocks (not built yet)
-             "fd", "fd_avg_reset", "fd_every2"]  # Sketchy / frequent directions
+             "fd", "fd_avg_reset", "fd_every2",  # Sketchy / frequent directions
+             "lowrank_pos"]  # eigh-based low-rank roots (largest eigenvalues kept)
 
 
 def _kw(cfg):
@@ -178,6 +179,32 @@ def test_sketchy_full_rank_blocks_match_oracle(extra):
       np.testing.assert_allclose(a.cpu().numpy(), b @ b.T, rtol=1e-4, atol=1e-8)
 
 
+@pytest.mark.parametrize("rank", [3, -3])
+def test_low_rank_full_rank_blocks_match_oracle(rank):
+  """compression_rank != 0 without frequent_directions (DS:2706-2738 -> _low_rank_root) on
+  2-D parameters with full-rank 8 x 8 gradient blocks.  (The golden `lowrank_neg` config
+  keeps the SMALLEST eigenvalues of vector-parameter statistics, whose small eigenvalues form
+  an exactly degenerate cluster: which vectors LAPACK returns there is arbitrary.)"""
+  from precondition_b200 import distributed_shampoo as DS
+  rng = np.random.default_rng(5)
+  shapes = [(16, 16), (8, 24)]
+  params = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+  kw = dict(compression_rank=rank, merge_small_dims_block_size=8, start_preconditioning_step=2)
+  oracle = O.distributed_shampoo(0.1, 8, **kw)
+  ostate = oracle.init(params)
+  opt = DS.distributed_shampoo(0.1, 8, **kw)
+  tparams = [torch.as_tensor(p).cuda() for p in params]
+  state = opt.init(tparams)
+  for t in range(6):
+    grads = [(rng.standard_normal(s) * 0.1).astype(np.float32) for s in shapes]
+    want, ostate = oracle.update(grads, ostate, params)
+    got, state = opt.update([torch.as_tensor(x).cuda() for x in grads], state, tparams)
+    torch.cuda.synchronize()
+    for i, (u, w) in enumerate(zip(got, want)):
+      err = np.abs(u.cpu().numpy() - w).max() / max(np.abs(w).max(), 1e-12)
+      assert err <= 1e-3, (rank, t, i, err)
+
+
 def test_pytree_structure_and_errors():
   from precondition_b200 import distributed_shampoo as DS
   params = {"w": torch.randn(16, 8).cuda(), "b": (torch.randn(8).cuda(),)}
@@ -193,7 +220,7 @@ def test_pytree_structure_and_errors():
     DS.distributed_shampoo(0.1, 8, frequent_directions=True)
   with pytest.raises(ValueError):  # the sketch update needs the previous sketch (DS:1150)
     DS.distributed_shampoo(0.1, 8, frequent_directions=True, compression_rank=2)
-  with pytest.raises(NotImplementedError):  # eigh-based _low_rank_root: SURVEY 8(f)
-    DS.distributed_shampoo(0.1, 8, compression_rank=3)
+  with pytest.raises(NotImplementedError):  # LOBPCG deflation: SURVEY 8(f)
+    DS.distributed_shampoo(0.1, 8, lobpcg_topk_precondition=2)
   with pytest.raises(RuntimeError):
     DS.distributed_shampoo(0.1, 8).init([torch.zeros(4, 4)])  # CPU tensor: no fallback
