@@ -236,6 +236,16 @@ int pc_low_rank_root_batched(const float* xs, const int32_t* ps, const int32_t* 
                              float* metrics, void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* eigh-based full root, `eigh=True`: replaces matrix_inverse_pth_root_eigh (DS:943-1030).
+ * Same inputs as pc_inverse_pth_root_batched, workspace from pc_low_rank_root_workspace_bytes;
+ * roots [batch, d, d] = U diag(max(e, ridge)^(-1/p)) U^T, metrics error = max|U^T reg U - diag(e)|.
+ * d <= 512. */
+int pc_inverse_pth_root_eigh_batched(const float* xs, const int32_t* ps,
+                                     const int32_t* padding_starts, int batch, int d,
+                                     float ridge_epsilon, float error_tolerance,
+                                     int relative_matrix_epsilon, float* roots, float* metrics,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* Dense form of the operator a packed low-rank preconditioner applies in
  * _precondition_block (DS:1690-1705, _low_rank_unpack DS:540-545):
  *   dense[b] = c I + V diag(lambda^- - c) V^T   (identity if the has_zeros flag is set),

@@ -365,6 +365,30 @@ def run_shapes():
   return out
 
 
+def run_eigh_roots():
+  """matrix_inverse_pth_root_eigh (DS:943-1030) of the unmodified reference."""
+  from oracle.jax_shim import import_reference
+  DS, _ = import_reference()
+  import jax.numpy as jnp
+  rng = np.random.default_rng(99)
+  out = {}
+  cases = [("spec1e3_p4", gen_symmetric_matrix(rng, 24, 1e3), 4, None),
+           ("spec1e5_p2_pad", gen_symmetric_matrix(rng, 24, 1e5), 2, 17),
+           ("ema_p4", ema_statistics(rng, 32, 64), 4, None)]
+  # (padding_start = 0 cannot be generated here: the numpy-backed shim's eigh raises on the
+  #  NaN matrix that case produces before DS:1026-1030 zeroes the result)
+  for name, a, p, pad in cases:
+    a = a.astype(np.float32)
+    v, m = DS.matrix_inverse_pth_root_eigh(jnp.array(a), p, ridge_epsilon=1e-6,
+                                           padding_start=pad)
+    out[f"{name}/a"] = a
+    out[f"{name}/p"] = np.array(p)
+    out[f"{name}/pad"] = np.array(-1 if pad is None else pad)
+    out[f"{name}/root"] = np.asarray(v)
+    out[f"{name}/err"] = np.asarray(m.inverse_pth_root_errors)
+  return out
+
+
 def main():
   os.makedirs(OUT, exist_ok=True)
   sys.path.insert(0, ROOT)
@@ -372,11 +396,15 @@ def main():
       "roots.npz": lambda: run_roots(False),
       "roots_f64.npz": lambda: run_roots(True),
       "quant.npz": run_quant,
+      "roots_eigh.npz": run_eigh_roots,
       "fd.npz": run_fd,
       "optimizer.npz": run_optimizer,
       "shapes.npz": run_shapes,
   }
+  only = set(sys.argv[1:])  # optional: regenerate just the named files
   for fname, fn in jobs.items():
+    if only and fname not in only:
+      continue
     with np.errstate(all="ignore"):
       data = fn()
     np.savez_compressed(os.path.join(OUT, fname), **data)

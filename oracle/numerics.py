@@ -480,6 +480,51 @@ def low_rank_root(matrix, p, compression_rank, ridge_epsilon=1e-6,
 
 
 # --------------------------------------------------------------------------
+# eigh-based full root  (matrix_inverse_pth_root_eigh, DS:943-1030; `eigh=True`)
+# --------------------------------------------------------------------------
+def matrix_inverse_pth_root_eigh(matrix, p, ridge_epsilon=1e-6, error_tolerance=1e-6,
+                                 relative_matrix_epsilon=True, padding_start=None,
+                                 dtype=np.float32):
+  dtype = np.dtype(dtype)
+  f = dtype.type
+  d = matrix.shape[0]
+  orig_dtype = matrix.dtype
+  a = matrix.astype(dtype)
+  alpha = f(-1.0 / p)
+  identity = np.eye(d, dtype=dtype)
+  ix = None
+  if padding_start is not None:  # DS:992-997
+    ix = (np.arange(d, dtype=np.int32) < padding_start).astype(dtype)
+    a = a * ix[np.newaxis, :] * ix[:, np.newaxis]
+    identity = identity * ix
+  if relative_matrix_epsilon:  # DS:998-1004
+    _, max_ev = power_iteration(a, 100, error_tolerance, padding_start)
+  else:
+    max_ev = f(1.0)
+  ridge = f(ridge_epsilon) * np.maximum(max_ev, f(error_tolerance))  # DS:1008
+  reg = a + ridge * identity
+  if padding_start is not None and padding_start == 0:  # DS:1026-1030 (reg is NaN here)
+    return np.zeros_like(matrix), RootMetrics(inverse_pth_root_errors=0.0)
+  e, u = np.linalg.eigh(reg)
+  e, u = e.astype(dtype), u.astype(dtype)
+  if ix is not None:
+    e = e * np.flip(ix)  # DS:1012-1013
+  with np.errstate(divide="ignore"):
+    inv_e = np.where(e == 0.0, f(0), np.power(np.maximum(e, ridge), alpha))  # DS:1015-1016
+  root = u * np.sqrt(inv_e)
+  val = root @ root.T  # DS:1018-1019
+  eig_error = u.T @ (reg @ u) - np.diag(e)  # DS:1020-1021
+  if ix is not None:
+    eig_error = eig_error * np.flip(ix)
+  error = np.max(np.abs(eig_error))
+  metrics = RootMetrics(inverse_pth_root_errors=float(error))
+  if padding_start is not None and padding_start == 0:  # DS:1026-1030
+    val = np.zeros_like(val)
+    metrics.inverse_pth_root_errors = 0.0
+  return val.astype(orig_dtype), metrics
+
+
+# --------------------------------------------------------------------------
 # Sketchy / frequent-directions sketch update  (DS:1123-1290)
 # --------------------------------------------------------------------------
 def fd_update_root(new_grad, p, rank, ridge_epsilon=1e-6, error_tolerance=1e-6,

@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "pc_low_rank_to_dense_workspace_bytes", "pc_low_rank_to_dense",
     "pc_grouped_gemm_tc_workspace_bytes", "pc_grouped_gemm_tc",
     "pc_low_rank_root_workspace_bytes", "pc_low_rank_root_batched",
+    "pc_inverse_pth_root_eigh_batched",
 )
 
 
@@ -154,6 +155,9 @@ def load() -> ctypes.CDLL:
   lib.pc_low_rank_root_batched.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, i32, vp, vp, vp,
                                            sz, vp]
   lib.pc_low_rank_root_batched.restype = i32
+  lib.pc_inverse_pth_root_eigh_batched.argtypes = [vp, vp, vp, i32, i32, f32, f32, i32, vp, vp, vp,
+                                                   sz, vp]
+  lib.pc_inverse_pth_root_eigh_batched.restype = i32
   _lib = lib
   return lib
 

@@ -195,14 +195,16 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
   int crank = 0;
   if (csize > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   float* A = a_all + (size_t)b * n * n;
-  float* V = vt_all + (size_t)b * n * n;
+  float* V = vt_all ? vt_all + (size_t)b * n * n : nullptr;
   unsigned* cnt = rot_count + (size_t)b * kJacMaxSweeps;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarp = (kJacThreads / 32) * csize, gw = crank * (kJacThreads / 32) + warp;
-  // Vt <- I
-  for (size_t e = (size_t)crank * kJacThreads + threadIdx.x; e < (size_t)n * n;
-       e += (size_t)csize * kJacThreads)
-    __stcg(V + e, (e / n == e % n) ? 1.f : 0.f);
+  const bool with_v = vt_all != nullptr;  // without V: rows of A are a FACTOR (A = G, G^T G = T)
+  if (with_v) {                            // Vt <- I
+    for (size_t e = (size_t)crank * kJacThreads + threadIdx.x; e < (size_t)n * n;
+         e += (size_t)csize * kJacThreads)
+      __stcg(V + e, (e / n == e % n) ? 1.f : 0.f);
+  }
   jac_cluster_sync(csize);
   const int m2 = (n + 1) & ~1;  // players (one phantom if n is odd)
   const int rounds = m2 - 1, npairs = m2 / 2;
@@ -240,9 +242,11 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
           if (c < n) {
             __stcg(A + (size_t)i * n + c, cs * ai[q] - sn * aj[q]);
             __stcg(A + (size_t)j * n + c, sn * ai[q] + cs * aj[q]);
-            const float vi = __ldcg(V + (size_t)i * n + c), vj = __ldcg(V + (size_t)j * n + c);
-            __stcg(V + (size_t)i * n + c, cs * vi - sn * vj);
-            __stcg(V + (size_t)j * n + c, sn * vi + cs * vj);
+            if (with_v) {
+              const float vi = __ldcg(V + (size_t)i * n + c), vj = __ldcg(V + (size_t)j * n + c);
+              __stcg(V + (size_t)i * n + c, cs * vi - sn * vj);
+              __stcg(V + (size_t)j * n + c, sn * vi + cs * vj);
+            }
           }
         }
       }
@@ -256,8 +260,10 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
   float* theta = theta_all + (size_t)b * n;
   for (int i = gw; i < n; i += nwarp) {
     float dot = 0.f;
-    for (int c = lane; c < n; c += 32)
-      dot = fmaf(__ldcg(A + (size_t)i * n + c), __ldcg(V + (size_t)i * n + c), dot);
+    for (int c = lane; c < n; c += 32) {
+      const float a = __ldcg(A + (size_t)i * n + c);
+      dot = fmaf(a, with_v ? __ldcg(V + (size_t)i * n + c) : a, dot);  // <A_i, V_i> or |A_i|^2
+    }
     dot = warp_sum(dot);
     if (lane == 0) theta[i] = dot;
   }
@@ -709,6 +715,58 @@ __global__ void lr_damp_kernel(float* __restrict__ a, float* __restrict__ copy,
     copy[(size_t)b * nn + e] = v;
   }
 }
+// Inverse roots are dominated by the SMALL eigenvalues.  One-sided Jacobi on the matrix itself
+// leaves every row with absolute noise ~ eps * sqrt(#rotations) * theta_max, i.e. the rows of
+// small eigenvalues (norm theta_i) lose their direction (measured: 1 % error in the root at
+// cond 1e4).  Run it on the Cholesky factor instead: reg = L L^T, the rows of G = L^T become
+// sigma_i u_i^T with sigma_i = sqrt(theta_i), which squares the conditioning away.
+// One CTA per matrix, right-looking, in place on the leading pad x pad block; g <- L^T (upper
+// triangular, zero elsewhere).  A non-positive pivot (matrix not positive definite) poisons
+// the matrix with NaN, which surfaces as a NaN error metric -> failure fallback.
+__global__ void __launch_bounds__(1024)
+lr_cholesky_kernel(float* __restrict__ reg_all, const int32_t* __restrict__ pads, int d,
+                   float* __restrict__ g_all) {
+  __shared__ float piv_s;
+  const int b = blockIdx.x;
+  const int pad = pads ? min(max(pads[b], 0), d) : d;
+  float* A = reg_all + (size_t)b * d * d;
+  float* G = g_all + (size_t)b * d * d;
+  for (int k = 0; k < pad; ++k) {
+    if (threadIdx.x == 0) {
+      const float p = A[(size_t)k * d + k];
+      piv_s = p > 0.f ? sqrtf(p) : __int_as_float(0x7fc00000);
+      A[(size_t)k * d + k] = piv_s;
+    }
+    __syncthreads();
+    const float inv = 1.0f / piv_s;
+    for (int i = k + 1 + threadIdx.x; i < pad; i += blockDim.x) A[(size_t)i * d + k] *= inv;
+    __syncthreads();
+    const int m = pad - k - 1;  // trailing block: rows / cols k+1 .. pad-1, lower part
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+      const int i = k + 1 + e / m, j = k + 1 + e % m;
+      if (j <= i) A[(size_t)i * d + j] -= A[(size_t)i * d + k] * A[(size_t)j * d + k];
+    }
+    __syncthreads();
+  }
+  for (size_t e = threadIdx.x; e < (size_t)d * d; e += blockDim.x) {
+    const int i = (int)(e / d), j = (int)(e - (size_t)i * d);
+    G[e] = (i < pad && j < pad && j >= i) ? A[(size_t)j * d + i] : 0.f;  // G = L^T
+  }
+}
+// vs[b][t][:] = rows[b][order[t]][:] / |row|  (u_i = row_i / sigma_i; zero rows stay zero)
+__global__ void __launch_bounds__(256)
+lr_gather_normalize_kernel(const float* __restrict__ rows, const int* __restrict__ order, int d,
+                           float* __restrict__ vs) {
+  __shared__ float red[32];
+  const int b = blockIdx.y, t = blockIdx.x;
+  const float* src = rows + ((size_t)b * d + order[(size_t)b * d + t]) * d;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) ss = fmaf(src[i], src[i], ss);
+  const float nrm = sqrtf(block_sum(ss, red));
+  const float inv = nrm > 0.f ? 1.0f / nrm : 0.f;
+  for (int i = threadIdx.x; i < d; i += blockDim.x)
+    vs[((size_t)b * d + t) * d + i] = src[i] * inv;
+}
 // err[b] = max over rows i and real eigen-columns j (sorted rank < pad) of
 // |recovered[i][j] - delta_ij e_j|   (DS:1076-1081)
 __global__ void __launch_bounds__(256)
@@ -786,21 +844,50 @@ size_t low_rank_root_bytes(int batch, int d) {
          align_up((size_t)d * 4, 256) + align_up(2 * B * d * 4, 256) + 2048;
 }
 
+// `full_root`: instead of packing, form U diag(inv_e) U^T (matrix_inverse_pth_root_eigh,
+// DS:943-1030) into out [batch, d, d].
+__global__ void lr_scale_rows_kernel(const float* __restrict__ vs, const float* __restrict__ sorted,
+                                     const float* __restrict__ ridge_all,
+                                     const int32_t* __restrict__ ps,
+                                     const int32_t* __restrict__ pads, int d,
+                                     float* __restrict__ rt) {
+  const int b = blockIdx.y, idx = blockIdx.x;  // row idx = eigenvector of descending rank idx
+  const int pad = pads ? min(max(pads[b], 0), d) : d;
+  const float alpha = -1.0f / (float)ps[b];
+  const float inv_e = idx < pad ? powf(fmaxf(sorted[(size_t)b * d + idx], ridge_all[b]), alpha) : 0.f;
+  const float sc = sqrtf(inv_e);  // root = u * sqrt(inv_e), DS:1018
+  for (int i = threadIdx.x; i < d; i += blockDim.x)
+    rt[((size_t)b * d + idx) * d + i] = vs[((size_t)b * d + idx) * d + i] * sc;
+}
+__global__ void lr_root_metrics_kernel(const uint32_t* __restrict__ errbits,
+                                       const int32_t* __restrict__ pads, int d, int batch,
+                                       float* __restrict__ out, float* __restrict__ metrics) {
+  const int b = blockIdx.x;
+  const int pad = pads ? min(max(pads[b], 0), d) : d;
+  if (pad == 0)  // DS:1026-1030
+    for (size_t e = threadIdx.x; e < (size_t)d * d; e += blockDim.x) out[(size_t)b * d * d + e] = 0.f;
+  if (threadIdx.x == 0 && metrics) {
+    float* m = metrics + (size_t)b * PC_NUM_METRICS;
+    m[0] = pad == 0 ? 0.f : __uint_as_float(errbits[b]);
+    m[1] = 0.f; m[2] = 0.f; m[3] = 0.f; m[4] = 0.f;
+  }
+}
+
 int run_low_rank_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch, int d,
-                      int rank_signed, float ridge_epsilon, float error_tolerance, int relative,
-                      float* out, float* metrics, void* workspace, size_t workspace_bytes,
-                      cudaStream_t stream) {
+                      int rank_signed, bool full_root, float ridge_epsilon, float error_tolerance,
+                      int relative, float* out, float* metrics, void* workspace,
+                      size_t workspace_bytes, cudaStream_t stream) {
   if (workspace_bytes < low_rank_root_bytes(batch, d)) {
-    set_error("low-rank root workspace too small: %zu < %zu", workspace_bytes,
+    set_error("eigh root workspace too small: %zu < %zu", workspace_bytes,
               low_rank_root_bytes(batch, d));
     return PC_ERR_WORKSPACE;
   }
   const size_t B = (size_t)batch, nn = (size_t)d * d;
   char* w = reinterpret_cast<char*>(align_up((size_t)workspace, 256));
   auto take = [&](size_t bytes) { char* p = w; w += align_up(bytes, 256); return p; };
-  float* reg = (float*)take(B * nn * 4);       // destroyed by the Jacobi solve
+  float* reg = (float*)take(B * nn * 4);       // destroyed by the factorisation
   float* reg_copy = (float*)take(B * nn * 4);
-  float* vt = (float*)take(B * nn * 4);
+  float* vt = (float*)take(B * nn * 4);        // G = L^T, then sigma_i u_i^T as rows
   float* vs = (float*)take(B * nn * 4);        // eigenvectors as rows, sorted descending
   float* t1 = (float*)take(B * nn * 4);
   float* rec = (float*)take(B * nn * 4);
@@ -813,22 +900,23 @@ int run_low_rank_root(const float* xs, const int32_t* ps, const int32_t* pads, i
   float* ybuf = (float*)take(2 * B * d * 4);
   float* ridge = lambdas + batch;
   uint32_t* errbits = reinterpret_cast<uint32_t*>(lambdas + 2 * (size_t)batch);
-  PC_REQUIRE(d >= 3, "low-rank root needs d >= 3");
   const unsigned g = (unsigned)std::min<size_t>((nn + 255) / 256, 512);
   PC_CUDA_CHECK(cudaMemsetAsync(rot, 0, B * kJacMaxSweeps * 4, stream));
   PC_CUDA_CHECK(cudaMemsetAsync(lambdas, 0, B * d * 4, stream));
   lr_mask_kernel<<<dim3(g, batch), 256, 0, stream>>>(xs, pads, d, reg);
   if (relative) {
     int rc = run_power_iteration(reg, pads, batch, d, 100, error_tolerance, lambdas, nullptr,
-                                 nullptr, v0, ybuf, stream);  // DS:1061-1067
+                                 nullptr, v0, ybuf, stream);  // DS:1061-1067, DS:998-1004
     if (rc != PC_OK) return rc;
   }
   lr_damp_kernel<<<dim3(g, batch), 256, 0, stream>>>(reg, reg_copy, lambdas, pads, d,
                                                     ridge_epsilon, error_tolerance, relative, ridge);
-  int rc = fd_jacobi(reg, vt, d, batch, rot, theta, stream);
+  // factor, then one-sided Jacobi on the rows of G = L^T: rows -> sigma_i u_i^T, theta = sigma^2
+  lr_cholesky_kernel<<<batch, 1024, 0, stream>>>(reg, pads, d, vt);
+  int rc = fd_jacobi(vt, nullptr, d, batch, rot, theta, stream);
   if (rc != PC_OK) return rc;
   fd_sort_kernel<<<batch, 512, 0, stream>>>(theta, d, order, sorted);
-  fd_gather_rows_kernel<<<dim3(d, batch), 256, 0, stream>>>(vt, order, d, d, d, vs);
+  lr_gather_normalize_kernel<<<dim3(d, batch), 256, 0, stream>>>(vt, order, d, vs);
   // recovered = Vs reg Vs^T
   FdGemm q{};
   q.alpha = 1.f; q.a = vs; q.b = reg_copy; q.c = t1;
@@ -839,9 +927,21 @@ int run_low_rank_root(const float* xs, const int32_t* ps, const int32_t* pads, i
   q.a = t1; q.b = vs; q.c = rec;
   fd_gemm(q, batch, stream);
   lr_error_kernel<<<dim3(g, batch), 256, 0, stream>>>(rec, sorted, pads, d, errbits);
-  lr_pack_kernel<<<batch, 256, 0, stream>>>(vs, sorted, ridge, ps, pads, errbits, d, rank_signed,
-                                           out, metrics);
-  count_launch(7);
+  if (full_root) {
+    // val = root root^T with root = U sqrt(inv_e): out(i,j) = sum_k Rt(k,i) Rt(k,j)
+    lr_scale_rows_kernel<<<dim3(d, batch), 256, 0, stream>>>(vs, sorted, ridge, ps, pads, d, t1);
+    FdGemm r{};
+    r.alpha = 1.f; r.a = t1; r.b = t1; r.c = out;
+    r.a_bs = r.b_bs = r.c_bs = (int64_t)nn;
+    r.a_si = 1; r.a_sk = d; r.b_sj = 1; r.b_sk = d; r.c_si = d;
+    r.m = r.n = r.k = d;
+    fd_gemm(r, batch, stream);
+    lr_root_metrics_kernel<<<batch, 256, 0, stream>>>(errbits, pads, d, batch, out, metrics);
+  } else {
+    lr_pack_kernel<<<batch, 256, 0, stream>>>(vs, sorted, ridge, ps, pads, errbits, d, rank_signed,
+                                             out, metrics);
+  }
+  count_launch(8);
   PC_CUDA_CHECK(cudaGetLastError());
   return PC_OK;
 }
@@ -882,8 +982,23 @@ int pc_low_rank_root_batched(const float* xs, const int32_t* ps, const int32_t* 
              compression_rank, d);
   PC_REQUIRE(d <= pc::kJacMaxN, "low-rank root supports d <= %d (one Jacobi solve), got %d",
              pc::kJacMaxN, d);
-  return pc::run_low_rank_root(xs, ps, padding_starts, batch, d, compression_rank, ridge_epsilon,
-                               error_tolerance, relative_matrix_epsilon, out, metrics, workspace,
+  return pc::run_low_rank_root(xs, ps, padding_starts, batch, d, compression_rank, false,
+                               ridge_epsilon, error_tolerance, relative_matrix_epsilon, out,
+                               metrics, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int pc_inverse_pth_root_eigh_batched(const float* xs, const int32_t* ps,
+                                     const int32_t* padding_starts, int batch, int d,
+                                     float ridge_epsilon, float error_tolerance,
+                                     int relative_matrix_epsilon, float* roots, float* metrics,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(batch >= 0 && d > 0, "bad eigh root sizes");
+  if (batch == 0) return PC_OK;
+  PC_REQUIRE(xs && ps && roots && workspace, "null pointer argument");
+  PC_REQUIRE(d <= pc::kJacMaxN, "eigh root supports d <= %d (one Jacobi solve), got %d",
+             pc::kJacMaxN, d);
+  return pc::run_low_rank_root(xs, ps, padding_starts, batch, d, 0, true, ridge_epsilon,
+                               error_tolerance, relative_matrix_epsilon, roots, metrics, workspace,
                                workspace_bytes, (cudaStream_t)stream);
 }
 

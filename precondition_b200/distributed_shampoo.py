@@ -206,8 +206,15 @@ def matrix_inverse_pth_root(matrix, p, num_iters=100, ridge_epsilon=1e-6,
                             lobpcg_max_iter=0, padding_start=None, prev=None, eigh=False):
   """DS:702-940 on one matrix -> (root, metrics row [5])."""
   del precision, prev, lobpcg_max_iter
-  if eigh or lobpcg_topk_precondition:
-    raise NotImplementedError("eigh / LOBPCG branches are outside the B200 hot path")
+  if lobpcg_topk_precondition:
+    raise NotImplementedError("the LOBPCG deflation branch is not built (SURVEY 8(f))")
+  if eigh:  # matrix_inverse_pth_root_eigh, DS:943-1030
+    roots, metrics = ops.matrix_inverse_pth_root_eigh_batched(
+        matrix[None].contiguous(), [int(p)],
+        None if padding_start is None else [int(padding_start)],
+        ridge_epsilon=ridge_epsilon, error_tolerance=error_tolerance,
+        relative_matrix_epsilon=relative_matrix_epsilon)
+    return roots[0], metrics[0]
   roots, metrics = ops.matrix_inverse_pth_root_batched(
       matrix[None].contiguous(), [int(p)],
       None if padding_start is None else [int(padding_start)],
@@ -347,7 +354,7 @@ class _Shampoo:
                compression_rank, skip_preconditioning_rank_lt, decoupled_learning_rate,
                decoupled_weight_decay, generate_training_metrics, engine, process_group,
                frequent_directions=False, reuse_preconditioner=False, reset_frequency=None,
-               average_grad=False):
+               average_grad=False, eigh=False):
     self.__dict__.update({k: v for k, v in locals().items() if k != "self"})
     # DS:2051-2064: second-moment quantisation only with a batch axis
     self.quantize_second_moment = bool(best_effort_memory_usage_reduction and
@@ -800,6 +807,15 @@ class _Shampoo:
   def _roots_sharded(self, bk, world, rank):
     kw = dict(ridge_epsilon=self.matrix_epsilon,
               relative_matrix_epsilon=self.relative_matrix_epsilon, engine=self.engine)
+    if self.eigh:  # `eigh=True`: matrix_inverse_pth_root_eigh for every statistic (DS:2677-2684)
+      if bk.size > 512:
+        raise NotImplementedError(
+            f"eigh=True supports statistics up to 512 x 512 (one Jacobi solve), got {bk.size}")
+      if world == 1:
+        return ops.matrix_inverse_pth_root_eigh_batched(bk.stats, bk.exps, None,
+                                                        out=bk.roots_tmp, **kw)
+      return sharded_inverse_pth_roots(bk.stats, bk.exps, world, rank, self.process_group,
+                                       root_fn=ops.matrix_inverse_pth_root_eigh_batched, **kw)
     if bk.size == 1 and max(self.buckets) > 1:
       # The reference pads every statistic to the largest block (DS:2841-2843), so a
       # 1x1 statistic goes through the coupled iteration, not the scalar closed
@@ -991,7 +1007,7 @@ def distributed_shampoo(
                      f"statistics_compute_steps ({statistics_compute_steps}) "
                      "to equal != preconditioning_compute_steps "
                      f"({preconditioning_compute_steps})")
-  for name, val in (("lobpcg_topk_precondition", lobpcg_topk_precondition), ("eigh", eigh),
+  for name, val in (("lobpcg_topk_precondition", lobpcg_topk_precondition),
                     ("shard_optimizer_states", shard_optimizer_states),
                     ("decay_preconditioning_compute_steps",
                      decay_preconditioning_compute_steps and end_preconditioning_compute_steps)):
@@ -1013,5 +1029,6 @@ def distributed_shampoo(
                  merge_small_dims_block_size, PreconditionerType(precondtioner_type),
                  compression_rank, skip_preconditioning_rank_lt, decoupled_learning_rate,
                  decoupled_weight_decay, generate_training_metrics, engine, process_group,
-                 frequent_directions, reuse_preconditioner, reset_frequency, average_grad)
+                 frequent_directions, reuse_preconditioner, reset_frequency, average_grad,
+                 bool(eigh))
   return GradientTransformation(opt.init, opt.update)

@@ -165,6 +165,35 @@ def low_rank_root_batched(xs: torch.Tensor, ps, compression_rank: int, padding_s
   return out, metrics
 
 
+def matrix_inverse_pth_root_eigh_batched(xs: torch.Tensor, ps, padding_starts=None,
+                                         ridge_epsilon: float = 1e-6,
+                                         error_tolerance: float = 1e-6,
+                                         relative_matrix_epsilon: bool = True,
+                                         out: Optional[torch.Tensor] = None, **_unused):
+  """Batched ``matrix_inverse_pth_root_eigh`` (DS:943-1030, the ``eigh=True`` root); d <= 512."""
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(xs)
+  b, d = xs.shape[0], xs.shape[1]
+  dev = xs.device
+  ps_t = torch.as_tensor(ps, dtype=torch.int32).to(dev).contiguous()
+  pads_t = None
+  if padding_starts is not None:
+    pads_t = torch.as_tensor(padding_starts, dtype=torch.int32).to(dev).contiguous()
+  roots = out if out is not None else torch.empty_like(xs)
+  metrics = torch.empty((b, _lib.PC_NUM_METRICS), dtype=torch.float32, device=dev)
+  if b == 0:
+    return roots, metrics
+  ws = _workspace(lib.pc_low_rank_root_workspace_bytes(b, d), dev)
+  with torch.cuda.device(dev):
+    _lib.check(lib.pc_inverse_pth_root_eigh_batched(
+        _ptr(xs), _ptr(ps_t), _ptr(pads_t), b, d, ridge_epsilon, error_tolerance,
+        int(relative_matrix_epsilon), _ptr(roots), _ptr(metrics), _ptr(ws), ws.numel(),
+        ctypes.c_void_p(_stream())))
+  gpu_launches += 1
+  return roots, metrics
+
+
 def low_rank_to_dense(packed: torch.Tensor, rank: int,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
   """Dense operator of packed low-rank preconditioners [b, d, rank+2] -> [b, d, d]

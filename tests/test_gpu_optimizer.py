@@ -205,6 +205,29 @@ def test_low_rank_full_rank_blocks_match_oracle(rank):
       assert err <= 1e-3, (rank, t, i, err)
 
 
+def test_eigh_option_matches_oracle_roots():
+  """`eigh=True` selects matrix_inverse_pth_root_eigh for every statistic (DS:2677-2684)."""
+  from precondition_b200 import distributed_shampoo as DS
+  from oracle import numerics as N
+  rng = np.random.default_rng(9)
+  shapes = [(48, 32), (20,)]
+  params = [torch.as_tensor(rng.standard_normal(s).astype(np.float32)).cuda() for s in shapes]
+  opt = DS.distributed_shampoo(0.1, 32, eigh=True, start_preconditioning_step=1,
+                               merge_small_dims_block_size=32)  # (48, 32) stays 2-D: p = 4
+  state = opt.init(params)
+  for t in range(3):
+    grads = [torch.as_tensor((rng.standard_normal(s) * 0.1).astype(np.float32)).cuda()
+             for s in shapes]
+    upd, state = opt.update(grads, state, params)
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(u).all() for u in upd)
+  for st in state.stats:
+    for stat, pre in zip(st.statistics, st.preconditioners):
+      want, _ = N.matrix_inverse_pth_root_eigh(stat.cpu().numpy(), 4 if stat.shape[0] != 20 else 2)
+      rel = np.linalg.norm(pre.cpu().numpy() - want) / np.linalg.norm(want)
+      assert rel <= 1e-3, rel
+
+
 def test_pytree_structure_and_errors():
   from precondition_b200 import distributed_shampoo as DS
   params = {"w": torch.randn(16, 8).cuda(), "b": (torch.randn(8).cuda(),)}

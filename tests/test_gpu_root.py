@@ -231,3 +231,42 @@ def test_invalid_arguments_fail_loudly():
   x = torch.zeros((1, 4, 4))
   with pytest.raises(RuntimeError):
     ops.matrix_inverse_pth_root_batched(x, [4])  # CPU tensor: no fallback
+
+
+def test_eigh_root_matches_reference_golden_and_oracle():
+  """`eigh=True` root (pc_inverse_pth_root_eigh_batched, DS:943-1030) against the reference's
+  golden outputs and the oracle; also the all-padding and tiny cases."""
+  import os
+  from precondition_b200 import ops
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "roots_eigh.npz"))
+  for name in ("spec1e3_p4", "spec1e5_p2_pad", "ema_p4"):
+    pad = int(g[f"{name}/pad"])
+    a = torch.as_tensor(g[f"{name}/a"]).cuda()[None].contiguous()
+    r, m = ops.matrix_inverse_pth_root_eigh_batched(a, [int(g[f"{name}/p"])],
+                                                    None if pad < 0 else [pad])
+    torch.cuda.synchronize()
+    want = g[f"{name}/root"]
+    assert _rel_fro(r[0].cpu().numpy(), want) <= 1e-4, name
+    assert float(m[0, 0]) <= max(20 * float(g[f"{name}/err"]), 1e-5)
+  rng = np.random.default_rng(4)
+  xs = np.stack([gen_symmetric_matrix(rng, 300, 1e4), ema_statistics(rng, 300, 900),
+                 np.eye(300)]).astype(np.float32)
+  r, m = ops.matrix_inverse_pth_root_eigh_batched(torch.as_tensor(xs).cuda(), [4, 2, 4],
+                                                  [300, 280, 0])
+  torch.cuda.synchronize()
+  r, m = r.cpu().numpy(), m.cpu().numpy()
+  for b, (p, pad) in enumerate([(4, 300), (2, 280)]):
+    want, wm = N.matrix_inverse_pth_root_eigh(xs[b], p, padding_start=pad)
+    # two fp32 eigensolvers differ by ~cond * eps on the small eigenvalues that dominate the
+    # root: hold ours to the float64 truth as tightly as the reference's own LAPACK path
+    sub = xs[b][:pad, :pad].astype(np.float64)
+    lam = np.linalg.eigvalsh(sub)[-1]
+    truth = np.zeros((300, 300))
+    truth[:pad, :pad] = N.exact_inverse_pth_root(sub, p, 1e-6 * lam)
+    ours, ref = _rel_fro(r[b], truth), _rel_fro(want, truth)
+    assert ours <= max(4 * ref, 1e-3), (b, ours, ref)
+    assert np.abs(r[b][pad:]).sum() == 0 and np.abs(r[b][:, pad:]).sum() == 0
+  assert np.abs(r[2]).sum() == 0 and m[2, 0] == 0
+  tiny, _ = ops.matrix_inverse_pth_root_eigh_batched(
+      torch.tensor([[[4.0, 0.0], [0.0, 9.0]]]).cuda(), [2])
+  np.testing.assert_allclose(tiny[0].cpu().numpy(), np.diag([0.5, 1 / 3]), rtol=1e-4, atol=1e-6)

@@ -172,3 +172,18 @@ def test_reference_end_to_end_goldens(golden_optimizer, tag, expected):
     for i, u in enumerate(updates):
       assert np.all(np.isfinite(u))
       np.testing.assert_allclose(u, g[f"{tag}/update/{t}/{i}"], rtol=1e-6, atol=1e-7)
+
+
+def test_eigh_root_matches_reference_bitwise():
+  """matrix_inverse_pth_root_eigh (DS:943-1030): the oracle reproduces the unmodified
+  reference (tests/golden/roots_eigh.npz, oracle/gen_golden.py run_eigh_roots) bit for bit."""
+  import os
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "roots_eigh.npz"))
+  for name in ("spec1e3_p4", "spec1e5_p2_pad", "ema_p4"):
+    pad = int(g[f"{name}/pad"])
+    v, m = N.matrix_inverse_pth_root_eigh(g[f"{name}/a"], int(g[f"{name}/p"]),
+                                          padding_start=None if pad < 0 else pad)
+    np.testing.assert_array_equal(v, g[f"{name}/root"])
+    assert np.float32(m.inverse_pth_root_errors) == g[f"{name}/err"]
+  v, m = N.matrix_inverse_pth_root_eigh(np.eye(8, dtype=np.float32), 4, padding_start=0)
+  assert np.abs(v).sum() == 0 and m.inverse_pth_root_errors == 0  # DS:1026-1030
