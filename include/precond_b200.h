@@ -211,7 +211,7 @@ typedef struct {
   int relative_matrix_epsilon; /* DS:1155-1158                                    */
   float decay;                 /* beta2, DS:1180, DS:1201                         */
   int input_is_gram;
-  int subspace_iters;          /* block iterations of the large-d path (8)        */
+  int subspace_iters;          /* block iterations of the large-d path (6)        */
   int oversample;              /* extra basis vectors of the large-d path (32)    */
   int full_eigh_max_dim;       /* <= 512: d up to here is solved exactly (512)    */
 } pc_fd_options;

@@ -190,7 +190,8 @@ __device__ __forceinline__ void jac_cluster_sync(int csize) {
 
 __global__ void __launch_bounds__(kJacThreads)
 fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, float tol,
-                 unsigned* __restrict__ rot_count, float* __restrict__ theta_all, int csize) {
+                 unsigned* __restrict__ rot_count, float* __restrict__ theta_all, int csize,
+                 int max_sweeps) {
   const int b = blockIdx.x / csize;
   int crank = 0;
   if (csize > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
@@ -209,7 +210,7 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
   const int m2 = (n + 1) & ~1;  // players (one phantom if n is odd)
   const int rounds = m2 - 1, npairs = m2 / 2;
   constexpr int Q = kJacMaxN / 32;
-  for (int sweep = 0; sweep < kJacMaxSweeps; ++sweep) {
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     unsigned rotated = 0;
     for (int t = 0; t < rounds; ++t) {
       for (int p = gw; p < npairs; p += nwarp) {
@@ -474,7 +475,8 @@ static size_t fd_carve(FdWorkspace* w, char* base, int batch, int d, int m, int 
 }
 
 static int fd_jacobi(float* a, float* vt, int n, int batch, unsigned* rot, float* theta,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, float tol = 3e-6f, int max_sweeps = kJacMaxSweeps) {
+  max_sweeps = std::min(max_sweeps, kJacMaxSweeps);
   int csize = 1;
   while (csize < 8 && (kJacThreads / 32) * csize < (n + 1) / 2) csize <<= 1;
   cudaLaunchConfig_t cfg{};
@@ -489,7 +491,8 @@ static int fd_jacobi(float* a, float* vt, int n, int batch, unsigned* rot, float
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fd_jacobi_kernel, a, vt, n, 3e-6f, rot, theta, csize));
+  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fd_jacobi_kernel, a, vt, n, tol, rot, theta, csize,
+                                   max_sweeps));
   count_launch(1);
   return PC_OK;
 }
@@ -512,9 +515,13 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
   PC_CUDA_CHECK(cudaMemsetAsync(w.rot, 0, (size_t)batch * kJacMaxSweeps * 64 * sizeof(unsigned),
                                 stream));
   int jac_calls = 0;
-  auto jacobi = [&](float* a, float* vt, int n) -> int {
+  auto jacobi = [&](float* a, float* vt, int n, bool orth_only = false) -> int {
     unsigned* rot = w.rot + (size_t)(jac_calls++ % 64) * batch * kJacMaxSweeps;
-    return fd_jacobi(a, vt, n, batch, rot, w.theta, stream);
+    // orthonormalisation solves act on a Gram matrix of unit rows (nearly the identity once
+    // the basis has settled) and are followed by a Rayleigh-Ritz solve: a loose tolerance
+    // and a few sweeps suffice there
+    return orth_only ? fd_jacobi(a, vt, n, batch, rot, w.theta, stream, 3e-5f, 8)
+                     : fd_jacobi(a, vt, n, batch, rot, w.theta, stream);
   };
 
   fd_prepare_kernel<<<batch, 256, 0, stream>>>(prev, ps, pads, d, rank, opt->ridge_epsilon,
@@ -584,7 +591,7 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
       fd_row_normalize_kernel<<<dim3(k, batch), 256, 0, stream>>>(w.yt, k, d);
       count_launch(1);
       gemm_small_from_rows(w.yt, w.yt, w.small);
-      int rc = jacobi(w.small, w.vt, k);
+      int rc = jacobi(w.small, w.vt, k, true);
       if (rc != PC_OK) return rc;
       fd_orth_scale_kernel<<<batch, 256, 0, stream>>>(w.theta, k, w.rscale);
       count_launch(1);
@@ -1008,7 +1015,7 @@ void pc_fd_options_default(pc_fd_options* opt) {
   opt->relative_matrix_epsilon = 1;
   opt->decay = 1.0f;
   opt->input_is_gram = 0;
-  opt->subspace_iters = 8;
+  opt->subspace_iters = 6;
   opt->oversample = 32;
   opt->full_eigh_max_dim = 512;
 }
