@@ -100,6 +100,35 @@ class ClockSampler:
     self.gpu = gpu_index
 
   def start(self):
+    # NVML in a thread (one query ~0.1 ms, polled every 5 ms) so that even a 100 ms timed
+    # region is sampled tens of times; nvidia-smi (slow to start) is the fallback.
+    self.nvml_rows, self.stop_flag, self.thread = [], False, None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(pynvml))
+      reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+          pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+      bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20,
+              "hw_thermal_slowdown": 0x40}
+
+      def poll():
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        while not self.stop_flag:
+          try:
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            mask = int(reasons_fn(h))
+            self.nvml_rows.append((float(sm), float(mx), [k for k, b in bits.items() if mask & b]))
+          except pynvml.NVMLError:
+            pass
+          time.sleep(0.005)
+
+      self.thread = threading.Thread(target=poll, daemon=True)
+      self.thread.start()
+      self.proc = None
+      return
+    except Exception:  # pylint: disable=broad-except
+      self.thread = None
     try:
       self.proc = subprocess.Popen(
           ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -109,11 +138,28 @@ class ClockSampler:
     except OSError:
       self.proc = None
 
+  def _physical_index(self, pynvml):
+    """NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+      ids = [x.strip() for x in vis.split(",") if x.strip()]
+      if self.gpu < len(ids) and ids[self.gpu].isdigit():
+        return int(ids[self.gpu])
+    return self.gpu
+
   def _read(self):
     for line in self.proc.stdout:
       self.rows.append([x.strip() for x in line.split(",")])
 
   def stop(self):
+    if getattr(self, "nvml_rows", None) is not None and self.proc is None and self.thread is not None:
+      self.stop_flag = True
+      self.thread.join(timeout=1)
+      rows = self.nvml_rows
+      reasons = sorted({r for row in rows for r in row[2]})
+      return {"sm_mhz": statistics.median([r[0] for r in rows]) if rows else None,
+              "sm_max_mhz": max([r[1] for r in rows]) if rows else None, "reasons": reasons,
+              "samples": len(rows), "source": "nvml"}
     if self.proc is None:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
     self.proc.terminate()
