@@ -179,6 +179,32 @@ size_t pc_grouped_gemm_tc_workspace_bytes(const pc_gemm_desc* descs_host, int co
 int pc_grouped_gemm_tc(const pc_gemm_desc* descs_host, int count, void* workspace,
                        size_t workspace_bytes, int reuse_plan, void* stream);
 
+/* The same call with QuantizedValue (QU:49-113) fused in, for the statistics update of
+ * quantised second moments (DS:1588-1590 around gram_weighted_update): per descriptor (a
+ * symmetric product into a contiguous [n, n] matrix)
+ *   q_in != NULL      C_in is read as to_float(q_in, diag_in, bucket_in) = q * bucket[col] + diag
+ *                     on the diagonal -- the dequantised matrix is never materialised;
+ *   colmax_out != NULL  [n] uint32, zero on entry: receives the bit patterns of the per-column
+ *                     max |off-diagonal| of the RESULT (the reduction QU:86 needs), so that
+ *                     pc_quantize_from_colmax_batched requantises in a single pass.
+ * The fp32 result is still written to desc.c (scratch for the requantisation). */
+typedef struct {
+  const void* q_in;
+  const float* diag_in;
+  const float* bucket_in;
+  uint32_t* colmax_out;
+  int32_t qdtype; /* PC_QDTYPE_INT16 or PC_QDTYPE_INT8 */
+  int32_t reserved;
+} pc_gemm_quant;
+int pc_grouped_gemm_tc_quant(const pc_gemm_desc* descs_host, const pc_gemm_quant* quant_host,
+                             int count, void* workspace, size_t workspace_bytes, int reuse_plan,
+                             void* stream);
+/* from_float with extract_diagonal (QU:49-95) given the column maxima: x [batch, n, n] f32,
+ * colmax [batch, n] -> q, diag [batch, n], bucket [batch, n]; one pass over x. */
+int pc_quantize_from_colmax_batched(const float* x, const uint32_t* colmax, int batch, int n,
+                                    int qdtype, void* q, float* diag, float* bucket,
+                                    void* stream);
+
 /* Failure fallback of DS:2936-2950 without a host round trip: for every matrix b,
  * dst[b] <- src[b] unless metrics[b][PC_METRIC_ERROR] is NaN or >= threshold
  * (then dst keeps the previous preconditioner).  src rows are [src_rows, src_cols]

@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "pc_grouped_gemm_tc_workspace_bytes", "pc_grouped_gemm_tc",
     "pc_low_rank_root_workspace_bytes", "pc_low_rank_root_batched",
     "pc_inverse_pth_root_eigh_batched",
+    "pc_grouped_gemm_tc_quant", "pc_quantize_from_colmax_batched",
 )
 
 
@@ -64,6 +65,12 @@ class GemmDesc(ctypes.Structure):
               ("m", ctypes.c_int32), ("n", ctypes.c_int32), ("k", ctypes.c_int32),
               ("alpha", ctypes.c_float), ("beta", ctypes.c_float),
               ("reserved", ctypes.c_int32)]
+
+
+class GemmQuant(ctypes.Structure):
+  _fields_ = [("q_in", ctypes.c_void_p), ("diag_in", ctypes.c_void_p),
+              ("bucket_in", ctypes.c_void_p), ("colmax_out", ctypes.c_void_p),
+              ("qdtype", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class GraftOptions(ctypes.Structure):
@@ -158,6 +165,10 @@ def load() -> ctypes.CDLL:
   lib.pc_inverse_pth_root_eigh_batched.argtypes = [vp, vp, vp, i32, i32, f32, f32, i32, vp, vp, vp,
                                                    sz, vp]
   lib.pc_inverse_pth_root_eigh_batched.restype = i32
+  lib.pc_grouped_gemm_tc_quant.argtypes = [vp, vp, i32, vp, sz, i32, vp]
+  lib.pc_grouped_gemm_tc_quant.restype = i32
+  lib.pc_quantize_from_colmax_batched.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+  lib.pc_quantize_from_colmax_batched.restype = i32
   _lib = lib
   return lib
 

@@ -56,6 +56,30 @@ quantize_kernel(const float* __restrict__ x, int rows, int cols, float num_bucke
   }
 }
 
+// Requantisation when the column maxima are already known (they were reduced in the
+// epilogue of the kernel that produced x): one pass, same arithmetic as quantize_kernel.
+template <typename Q>
+__global__ void quantize_from_colmax_kernel(const float* __restrict__ x,
+                                            const uint32_t* __restrict__ colmax, int n,
+                                            float num_buckets, Q* __restrict__ q,
+                                            float* __restrict__ diag, float* __restrict__ bucket) {
+  const int b = blockIdx.y;
+  const size_t total = (size_t)n * n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / n), c = (int)(e - (size_t)r * n);
+    float v = x[(size_t)b * total + e];
+    const float bs = __uint_as_float(colmax[(size_t)b * n + c]) / num_buckets;  // QU:86-87
+    const float bs_nz = bs > 0.f ? bs : 1.f;                                    // QU:90-91
+    if (r == c) {
+      diag[(size_t)b * n + r] = v;  // QU:72-76
+      v = v - v;
+      bucket[(size_t)b * n + c] = bs;
+    }
+    q[(size_t)b * total + e] = to_q<Q>(rintf(v / bs_nz));                       // QU:92-95
+  }
+}
+
 template <typename Q>
 __global__ void dequantize_kernel(const Q* __restrict__ q, const float* __restrict__ diag,
                                   const float* __restrict__ bucket, int rows, int cols,
@@ -116,6 +140,26 @@ int pc_quantize_batched(const float* x, int batch, int rows, int cols, int qdtyp
     pc::quantize_kernel<int8_t><<<grid, block, 0, st>>>(x, rows, cols, 127.f,
                                                        extract_diagonal, (int8_t*)q, diag,
                                                        bucket);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+int pc_quantize_from_colmax_batched(const float* x, const uint32_t* colmax, int batch, int n,
+                                    int qdtype, void* q, float* diag, float* bucket,
+                                    void* stream) {
+  PC_REQUIRE(batch >= 0 && n >= 0, "bad sizes");
+  if (batch == 0 || n == 0) return PC_OK;
+  PC_REQUIRE(x && colmax && q && diag && bucket, "null pointer argument");
+  PC_REQUIRE(qdtype == PC_QDTYPE_INT16 || qdtype == PC_QDTYPE_INT8,
+             "Quantized dtype %d not supported.", qdtype);
+  const size_t per = (size_t)n * n;
+  dim3 grid((unsigned)((per + 255) / 256 < 2048 ? (per + 255) / 256 : 2048), batch);
+  if (qdtype == PC_QDTYPE_INT16)
+    pc::quantize_from_colmax_kernel<int16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x, colmax, n, 32767.f, (int16_t*)q, diag, bucket);
+  else
+    pc::quantize_from_colmax_kernel<int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x, colmax, n, 127.f, (int8_t*)q, diag, bucket);
   PC_CUDA_CHECK(cudaGetLastError());
   return PC_OK;
 }

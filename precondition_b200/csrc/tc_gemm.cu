@@ -1625,6 +1625,11 @@ struct TcGgItem {
   int a_tile0, b_tile0;  // first packed tile of each operand (b_tile0 == a_tile0 if symmetric)
   int symmetric;
   float alpha, beta;
+  // optional fused (de)quantisation of a square symmetric C (QuantizedValue, QU:49-113):
+  // C_in = q_in * bucket_in[col] + diag_in on the diagonal; colmax receives the bit
+  // patterns of max |off-diagonal| per column of the RESULT for the requantisation
+  const void* q_in; const float* diag_in; const float* bucket_in; uint32_t* colmax;
+  int qdtype;
 };
 struct TcGgWork { int z, tm, tn, pad; };
 struct TcGgOperand {  // one packed operand: view + where its tiles go
@@ -1885,17 +1890,69 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         const int col0 = wk.tn * TC_BN + c * 32;
         if (diag_tile && c > q) continue;  // strictly upper sub-block: written by its mirror
         float x[32];
-        const float* cin = it.c_in ? it.c_in + rowoff + col0 : nullptr;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (cin) old = *reinterpret_cast<const float4*>(cin + i);
-          x[i] = fmaf(it.beta, old.x, alpha * __uint_as_float(r[i]));
-          x[i + 1] = fmaf(it.beta, old.y, alpha * __uint_as_float(r[i + 1]));
-          x[i + 2] = fmaf(it.beta, old.z, alpha * __uint_as_float(r[i + 2]));
-          x[i + 3] = fmaf(it.beta, old.w, alpha * __uint_as_float(r[i + 3]));
-        }
         const bool diag_sub = diag_tile && c == q;
+        if (it.q_in) {
+          // to_float fused into the load (QU:97-113): q * bucket[col] (+ diag on the diagonal)
+          const size_t qoff = (size_t)row * it.n + col0;
+          float oldv[32];
+          if (it.qdtype == PC_QDTYPE_INT16) {
+            const int16_t* qp = reinterpret_cast<const int16_t*>(it.q_in) + qoff;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const uint4 w = *reinterpret_cast<const uint4*>(qp + i);
+              const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                oldv[i + 2 * h] = (float)(int16_t)(ws[h] & 0xffffu);
+                oldv[i + 2 * h + 1] = (float)(int16_t)(ws[h] >> 16);
+              }
+            }
+          } else {
+            const int8_t* qp = reinterpret_cast<const int8_t*>(it.q_in) + qoff;
+#pragma unroll
+            for (int i = 0; i < 32; i += 16) {
+              const uint4 w = *reinterpret_cast<const uint4*>(qp + i);
+              const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int h = 0; h < 4; ++h)
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb)
+                  oldv[i + 4 * h + bb] = (float)(int8_t)((ws[h] >> (8 * bb)) & 0xffu);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float o = oldv[i] * __ldg(it.bucket_in + col0 + i);
+            if (col0 + i == row) o += __ldg(it.diag_in + row);
+            x[i] = fmaf(it.beta, o, alpha * __uint_as_float(r[i]));
+          }
+        } else {
+          const float* cin = it.c_in ? it.c_in + rowoff + col0 : nullptr;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cin) old = *reinterpret_cast<const float4*>(cin + i);
+            x[i] = fmaf(it.beta, old.x, alpha * __uint_as_float(r[i]));
+            x[i + 1] = fmaf(it.beta, old.y, alpha * __uint_as_float(r[i + 1]));
+            x[i + 2] = fmaf(it.beta, old.z, alpha * __uint_as_float(r[i + 2]));
+            x[i + 3] = fmaf(it.beta, old.w, alpha * __uint_as_float(r[i + 3]));
+          }
+        }
+        if (it.colmax) {
+          // column max of |off-diagonal| for the requantisation (QU:86), fused into the
+          // epilogue: an element (row, col) of the lower triangle also stands for (col, row)
+          uint32_t rmax = 0, mine = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool owned = diag_sub ? i < lane : true;  // strictly lower part of a diagonal block
+            const uint32_t ab = (owned && col0 + i != row) ? absbits(x[i]) : 0u;
+            rmax = ab > rmax ? ab : rmax;
+            const uint32_t cm = __reduce_max_sync(0xffffffffu, ab);
+            if (lane == i) mine = cm;
+          }
+          if (rmax) atomicMax(it.colmax + row, rmax);
+          if (mine) atomicMax(it.colmax + col0 + lane, mine);
+        }
         float* crow = it.c + rowoff + col0;
         if (!diag_sub) {
 #pragma unroll
@@ -1943,10 +2000,15 @@ struct TcGgPlan {
   int total_tiles = 0;
 };
 
-static void tc_gg_plan(const pc_gemm_desc* descs, int count, TcGgPlan* pl) {
+static void tc_gg_plan(const pc_gemm_desc* descs, const pc_gemm_quant* quant, int count,
+                       TcGgPlan* pl) {
   for (int z = 0; z < count; ++z) {
     const pc_gemm_desc& d = descs[z];
     TcGgItem it{};
+    if (quant) {
+      it.q_in = quant[z].q_in; it.diag_in = quant[z].diag_in; it.bucket_in = quant[z].bucket_in;
+      it.colmax = quant[z].colmax_out; it.qdtype = quant[z].qdtype;
+    }
     it.a = d.a; it.b = d.b; it.c_in = d.c_in; it.c = d.c;
     it.c_sio = d.c_sio; it.c_sii = d.c_sii; it.c_iinner = d.c_iinner > 0 ? d.c_iinner : d.m;
     it.m = d.m; it.n = d.n; it.k = d.k; it.kblocks = (d.k + TC_BK - 1) / TC_BK;
@@ -1989,15 +2051,25 @@ static size_t tc_gg_bytes(const TcGgPlan& pl) {
 
 size_t tc_grouped_gemm_workspace_bytes(const pc_gemm_desc* descs, int count) {
   TcGgPlan pl;
-  tc_gg_plan(descs, count, &pl);
+  tc_gg_plan(descs, nullptr, count, &pl);
   return tc_gg_bytes(pl);
 }
 
-int tc_grouped_gemm(const pc_gemm_desc* descs, int count, void* workspace, size_t workspace_bytes,
-                    int reuse_plan, cudaStream_t stream) {
-  for (int z = 0; z < count; ++z)
+int tc_grouped_gemm(const pc_gemm_desc* descs, const pc_gemm_quant* quant, int count,
+                    void* workspace, size_t workspace_bytes, int reuse_plan, cudaStream_t stream) {
+  for (int z = 0; z < count; ++z) {
     PC_REQUIRE(tc_gg_supported(descs[z]),
                "descriptor %d is not eligible for the tcgen05 grouped GEMM (m, n %% 128, alignment)", z);
+    if (quant && (quant[z].q_in || quant[z].colmax_out)) {
+      PC_REQUIRE(tc_gg_symmetric(descs[z]) && descs[z].c_sii == descs[z].n && descs[z].c_sio == 0,
+                 "descriptor %d: fused (de)quantisation needs a symmetric product into a contiguous "
+                 "square matrix", z);
+      PC_REQUIRE(!quant[z].q_in || ((quant[z].qdtype == PC_QDTYPE_INT16 ||
+                                    quant[z].qdtype == PC_QDTYPE_INT8) &&
+                                   quant[z].diag_in && quant[z].bucket_in),
+                 "descriptor %d: quantised C_in needs int16 / int8 data, diagonal and buckets", z);
+    }
+  }
   if (!tc_engine_available()) {
     set_error("tcgen05 grouped GEMM requested but device is not sm_100");
     return PC_ERR_UNSUPPORTED;
@@ -2008,7 +2080,7 @@ int tc_grouped_gemm(const pc_gemm_desc* descs, int count, void* workspace, size_
     return PC_ERR_UNSUPPORTED;
   }
   TcGgPlan pl;
-  tc_gg_plan(descs, count, &pl);
+  tc_gg_plan(descs, quant, count, &pl);
   if (workspace_bytes < tc_gg_bytes(pl)) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, tc_gg_bytes(pl));
     return PC_ERR_WORKSPACE;
@@ -2091,6 +2163,17 @@ extern "C" int pc_grouped_gemm_tc(const pc_gemm_desc* descs_host, int count, voi
   PC_REQUIRE(count >= 0, "bad count");
   if (count == 0) return PC_OK;
   PC_REQUIRE(descs_host && workspace, "null pointer argument");
-  return pc::tc_grouped_gemm(descs_host, count, workspace, workspace_bytes, reuse_plan,
+  return pc::tc_grouped_gemm(descs_host, nullptr, count, workspace, workspace_bytes, reuse_plan,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int pc_grouped_gemm_tc_quant(const pc_gemm_desc* descs_host,
+                                        const pc_gemm_quant* quant_host, int count,
+                                        void* workspace, size_t workspace_bytes, int reuse_plan,
+                                        void* stream) {
+  PC_REQUIRE(count >= 0, "bad count");
+  if (count == 0) return PC_OK;
+  PC_REQUIRE(descs_host && quant_host && workspace, "null pointer argument");
+  return pc::tc_grouped_gemm(descs_host, quant_host, count, workspace, workspace_bytes, reuse_plan,
                              (cudaStream_t)stream);
 }

@@ -504,7 +504,7 @@ class _Shampoo:
     """Grouped-GEMM descriptors for the statistics update (DS:1582-1590) and the
     preconditioner application (DS:1676-1708), built once."""
     D = _lib.GemmDesc
-    stat_descs, apply_descs = [], [[], [], []]
+    stat_descs, stat_meta, apply_descs = [], [], [[], [], []]
     self._stat_max, self._apply_max = [1, 1], [[1, 1], [1, 1], [1, 1]]
     w1 = float(self.beta2)
     w2 = float(self.beta2 if self.beta2 == 1.0 else 1.0 - self.beta2)  # DS:2635-2636
@@ -555,6 +555,7 @@ class _Shampoo:
             # statistic slot holds x x^T itself (no QR on the device).
             d.c_in, d.alpha, d.beta = None, 1.0, 0.0
           stat_descs.append(d)
+          stat_meta.append((s, bi))
           self._stat_max = [max(self._stat_max[0], s), max(self._stat_max[1], s)]
         # ---- application: contract the leading axis and roll (DS:1678-1707) ----
         bnumel = int(np.prod(sizes))
@@ -621,6 +622,35 @@ class _Shampoo:
               (ops.upload_gemm_descs(simt, self.device), len(simt)) if simt else (None, 0), mx)
 
     self._stat_count = len(stat_descs)
+    self._stat_tc_fused = None
+    for bk in self.buckets.values():
+      bk.fused_quant = False
+    if self.quantize_second_moment and use_tc:
+      # Quantised second moments on the tcgen05 path: to_float is fused into the epilogue's
+      # C_in read and the column-max reduction of from_float into its write
+      # (pc_grouped_gemm_tc_quant); the requantisation is then a single pass.
+      fused, fused_ext, rest = [], [], []
+      for d, (sz, bi) in zip(stat_descs, stat_meta):
+        if not ops.tc_gemm_eligible(d):
+          rest.append(d)
+          continue
+        bk = self.buckets[sz]
+        if not bk.fused_quant:
+          bk.fused_quant = True
+          bk.colmax = torch.zeros((bk.count, sz), dtype=torch.int32, device=self.device)
+        q, dg, bs = bk.qstats
+        e = _lib.GemmQuant()
+        e.q_in = q[bi].data_ptr()
+        e.diag_in = dg[bi].data_ptr()
+        e.bucket_in = bs[bi].data_ptr()
+        e.colmax_out = bk.colmax[bi].data_ptr()
+        e.qdtype = ops._QDT[self.qdt_second]
+        d.c_in = None
+        fused.append(d)
+        fused_ext.append(e)
+      if fused:
+        self._stat_tc_fused = ops.TcGemmList(fused, self.device, quant=fused_ext)
+      stat_descs = rest
     self._stat_tc, self._stat_descs, self._stat_max = split(stat_descs)
     self._apply_tc, self._apply_descs, self._apply_max = [], [], []
     for lst in apply_descs:
@@ -687,6 +717,9 @@ class _Shampoo:
   def _update_statistics(self):
     if self.quantize_second_moment:  # to_float (DS:1588, QU:97-113)
       for bk in self.buckets.values():
+        if bk.fused_quant:
+          bk.colmax.zero_()
+          continue
         q, d, b = bk.qstats
         ops.dequantize(q, d, b, True, out=bk.stats)
     dev, count = self._stat_descs
@@ -694,9 +727,15 @@ class _Shampoo:
       ops.grouped_gemm(dev, count, self._stat_max[0], self._stat_max[1])
     if self._stat_tc is not None:
       self._stat_tc.run()
+    if self._stat_tc_fused is not None:
+      self._stat_tc_fused.run()
     if self.quantize_second_moment:  # from_float (DS:2654)
       for bk in self.buckets.values():
-        bk.qstats[0], bk.qstats[1], bk.qstats[2] = self._requant(bk.stats, bk.qstats)
+        if bk.fused_quant:
+          q, d, b = bk.qstats
+          ops.quantize_from_colmax(bk.stats, bk.colmax, self.qdt_second, q, d, b)
+        else:
+          bk.qstats[0], bk.qstats[1], bk.qstats[2] = self._requant(bk.stats, bk.qstats)
 
   def _requant(self, x, dst):
     q, d, b = ops.quantize(x, self.qdt_second, True)

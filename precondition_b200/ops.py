@@ -320,9 +320,12 @@ def tc_gemm_eligible(d: _lib.GemmDesc) -> bool:
 class TcGemmList:
   """Host-side descriptor array for ``pc_grouped_gemm_tc`` (kept alive by the caller)."""
 
-  def __init__(self, descs: Sequence[_lib.GemmDesc], device):
+  def __init__(self, descs: Sequence[_lib.GemmDesc], device,
+               quant: Optional[Sequence[_lib.GemmQuant]] = None):
     self.count = len(descs)
     self.arr = (_lib.GemmDesc * max(self.count, 1))(*descs)
+    # optional fused (de)quantisation extensions, one per descriptor (pc_gemm_quant)
+    self.quant = (_lib.GemmQuant * max(self.count, 1))(*quant) if quant else None
     self.device = device
     lib = _lib.load()
     self.nbytes = lib.pc_grouped_gemm_tc_workspace_bytes(
@@ -338,10 +341,30 @@ class TcGemmList:
     if self.ws is None:
       self.ws = torch.empty(self.nbytes + 4096, dtype=torch.uint8, device=self.device)
     with torch.cuda.device(self.device):
-      _lib.check(lib.pc_grouped_gemm_tc(ctypes.cast(self.arr, ctypes.c_void_p), self.count,
-                                        _ptr(self.ws), self.ws.numel(), int(reuse),
-                                        ctypes.c_void_p(_stream())))
+      if self.quant is not None:
+        _lib.check(lib.pc_grouped_gemm_tc_quant(
+            ctypes.cast(self.arr, ctypes.c_void_p), ctypes.cast(self.quant, ctypes.c_void_p),
+            self.count, _ptr(self.ws), self.ws.numel(), int(reuse), ctypes.c_void_p(_stream())))
+      else:
+        _lib.check(lib.pc_grouped_gemm_tc(ctypes.cast(self.arr, ctypes.c_void_p), self.count,
+                                          _ptr(self.ws), self.ws.numel(), int(reuse),
+                                          ctypes.c_void_p(_stream())))
     gpu_launches += 1
+
+
+def quantize_from_colmax(x: torch.Tensor, colmax: torch.Tensor, qdtype, q: torch.Tensor,
+                         diag: torch.Tensor, bucket: torch.Tensor):
+  """``from_float`` with extracted diagonal (QU:49-95) when the per-column maxima of
+  |off-diagonal| are already known (``colmax`` [b, n] int32 bit patterns): one pass over x."""
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(x, colmax, q, diag, bucket)
+  b, n = x.shape[0], x.shape[1]
+  with torch.cuda.device(x.device):
+    _lib.check(lib.pc_quantize_from_colmax_batched(
+        _ptr(x), _ptr(colmax), b, n, _QDT[qdtype], _ptr(q), _ptr(diag), _ptr(bucket),
+        ctypes.c_void_p(_stream())))
+  gpu_launches += 1
 
 
 def make_graft_options(**kw) -> _lib.GraftOptions:

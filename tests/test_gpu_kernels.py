@@ -230,3 +230,60 @@ def test_tc_grouped_gemm_gram_update_and_apply(scale):
   for got, w, sym in zip((s2, out), want[2:], (True, False)):
     ref = np.tril(w) + np.tril(w, -1).T if sym else w
     assert np.abs(got.cpu().numpy() - ref).max() / np.abs(ref).max() <= 2e-6
+
+
+@pytest.mark.parametrize("qdtype,levels", [(torch.int16, 32767.0), (torch.int8, 127.0)])
+def test_tc_statistics_update_with_fused_quantisation(qdtype, levels):
+  """pc_grouped_gemm_tc_quant + pc_quantize_from_colmax_batched: S <- w1 to_float(Q) + w2 G G^T
+  with the dequantisation fused into the C_in read and the column maxima of from_float
+  reduced in the epilogue, against the oracle's QuantizedValue (QU:49-113) in float64."""
+  if not _tc_ok():
+    pytest.skip("needs sm_100")
+  from precondition_b200 import _lib, ops
+  rng = np.random.default_rng(23)
+  n, k, batch = 256, 320, 2
+  w1, w2 = 0.95, 0.05
+  descs, exts, keep, want = [], [], [], []
+  colmax = torch.zeros((batch, n), dtype=torch.int32).cuda()
+  out = torch.zeros((batch, n, n), dtype=torch.float32).cuda()
+  for b in range(batch):
+    a = rng.standard_normal((n, 2 * n))
+    s_old = (a @ a.T / n).astype(np.float32)
+    qv = N.QuantizedValue.from_float_value(s_old, np.int16 if qdtype == torch.int16 else np.int8,
+                                           True)
+    g = torch.as_tensor((rng.standard_normal((n, k)) * 0.3).astype(np.float32)).cuda()
+    q = torch.as_tensor(qv.quantized).cuda()
+    dg = torch.as_tensor(qv.diagonal.astype(np.float32)).cuda()
+    bs = torch.as_tensor(qv.bucket_size.astype(np.float32)).cuda()
+    keep += [g, q, dg, bs]
+    d = _lib.GemmDesc()
+    d.a = d.b = g.data_ptr(); d.c = out[b].data_ptr(); d.c_in = None
+    d.a_si = d.b_sj = k; d.a_iinner, d.a_sio = n, 0
+    d.a_kinner = d.b_kinner = k; d.a_sko = d.b_sko = 0; d.a_ski = d.b_ski = 1
+    d.c_iinner, d.c_sio, d.c_sii = n, 0, n
+    d.m = d.n = n; d.k = k; d.alpha, d.beta = w2, w1
+    e = _lib.GemmQuant()
+    e.q_in, e.diag_in, e.bucket_in = q.data_ptr(), dg.data_ptr(), bs.data_ptr()
+    e.colmax_out = colmax[b].data_ptr()
+    e.qdtype = ops._QDT[qdtype]
+    descs.append(d); exts.append(e)
+    g64 = g.cpu().numpy().astype(np.float64)
+    want.append(w1 * qv.to_float().astype(np.float64) + w2 * g64 @ g64.T)
+  ops.TcGemmList(descs, out.device, quant=exts).run()
+  qn = torch.empty((batch, n, n), dtype=qdtype).cuda()
+  dn = torch.empty((batch, n), dtype=torch.float32).cuda()
+  bn = torch.empty((batch, n), dtype=torch.float32).cuda()
+  ops.quantize_from_colmax(out, colmax, qdtype, qn, dn, bn)
+  torch.cuda.synchronize()
+  for b in range(batch):
+    w = np.tril(want[b]) + np.tril(want[b], -1).T
+    got = out[b].cpu().numpy()
+    assert np.abs(got - w).max() / np.abs(w).max() <= 2e-6
+    ref = N.QuantizedValue.from_float_value(w.astype(np.float32),
+                                            np.int16 if qdtype == torch.int16 else np.int8, True)
+    np.testing.assert_allclose(dn[b].cpu().numpy(), ref.diagonal, rtol=1e-5)
+    np.testing.assert_allclose(bn[b].cpu().numpy(), ref.bucket_size, rtol=1e-5)
+    assert np.abs(qn[b].cpu().numpy().astype(np.int32) - ref.quantized.astype(np.int32)).max() <= 1
+    # exactly what the stand-alone quantiser makes of the same fp32 matrix
+    q2, d2, b2 = ops.quantize(out[b:b + 1].contiguous(), qdtype, True)
+    assert torch.equal(q2[0], qn[b]) and torch.equal(d2[0], dn[b]) and torch.equal(b2[0], bn[b])
