@@ -307,22 +307,38 @@ root_phase_simt_kernel(F32Store bufs, const RootCtl* __restrict__ ctl,
 // ---------------------------------------------------------------------------
 // per-iteration control (DS:836-848 bookkeeping, DS:876-885 retry logic)
 // ---------------------------------------------------------------------------
-__global__ void root_control_kernel(RootCtl* ctl, uint32_t* errbits, int batch,
-                                    RootParams prm, int* n_unfinished) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
-  RootCtl c = ctl[b];
-  if (c.active) {
-    const float new_err = __uint_as_float(errbits[b]);  // max|M' - I_m|, DS:847
-    errbits[b] = 0u;
-    c.ratio = new_err / c.err;                // DS:848
-    c.err = new_err;
-    c.iter += 1;
-    c.cur ^= 1;
-    root_after_error_update(c, prm);
-    ctl[b] = c;
+// One block walks the whole batch and publishes {unfinished, waiting for (re)initialisation}
+// straight into pinned host memory (UVA): no memset / copy launches around it.
+__global__ void __launch_bounds__(1024)
+root_control_kernel(RootCtl* ctl, uint32_t* errbits, int batch, RootParams prm,
+                    int* host_slot) {
+  __shared__ int counts[2];
+  if (threadIdx.x < 2) counts[threadIdx.x] = 0;
+  __syncthreads();
+  int unfinished = 0, waiting = 0;
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    RootCtl c = ctl[b];
+    if (c.active) {
+      const float new_err = __uint_as_float(errbits[b]);  // max|M' - I_m|, DS:847
+      errbits[b] = 0u;
+      c.ratio = new_err / c.err;                // DS:848
+      c.err = new_err;
+      c.iter += 1;
+      c.cur ^= 1;
+      root_after_error_update(c, prm);
+      ctl[b] = c;
+    }
+    unfinished += c.done ? 0 : 1;
+    waiting += c.need_init ? 1 : 0;
   }
-  if (!c.done) atomicAdd(n_unfinished, 1);
+  if (unfinished) atomicAdd(&counts[0], unfinished);
+  if (waiting) atomicAdd(&counts[1], waiting);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    host_slot[0] = counts[0];
+    host_slot[1] = counts[1];
+    __threadfence_system();
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -496,7 +512,7 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
   };
   static thread_local HostScratch hsx;
   if (!hsx.poll) {
-    PC_CUDA_CHECK(cudaMallocHost(&hsx.poll, sizeof(int) * kPollRing));
+    PC_CUDA_CHECK(cudaMallocHost(&hsx.poll, sizeof(int) * 2 * kPollRing));
     for (int i = 0; i < kPollRing; ++i)
       PC_CUDA_CHECK(cudaEventCreateWithFlags(&hsx.ev[i], cudaEventDisableTiming));
     PC_CUDA_CHECK(cudaEventCreateWithFlags(&hsx.ps_ev, cudaEventDisableTiming));
@@ -545,6 +561,9 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
   // (at most kPollLag) surplus iterations find no active matrix and return at once.
   const int tiles = (n + kSimtBM - 1) / kSimtBM;
   const int max_total = opt->num_iters * 6 + 8;
+  // (Re)initialisation is launched on the first iteration and afterwards only when a lagged
+  // poll reports matrices waiting for a retry (they idle until then; retries are rare).
+  bool init_pending = true;
   for (int it = 0; it < max_total + kPollLag; ++it) {
     if (it >= kPollLag) {
       const int slot = (it - kPollLag) % kPollRing;
@@ -553,9 +572,12 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
         set_error("root iteration failed: %s", cudaGetErrorString(e));
         return PC_ERR_CUDA;
       }
-      if (hsx.poll[slot] == 0) break;
+      if (hsx.poll[2 * slot] == 0) break;
+      if (hsx.poll[2 * slot + 1] > 0) init_pending = true;
     }
     if (it >= max_total) continue;
+    const bool do_init = init_pending;
+    init_pending = false;
     if (engine == PC_ENGINE_SIMT_FP32) {
       if (it == 0 && n >= 256) {  // first initialisation: whole-GPU strip kernels
         const int strips = (n + 31) / 32;
@@ -563,10 +585,13 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
                                                                        ws.ybuf, batch);
         root_init_strip_kernel<F32Store><<<dim3(strips, batch), 1024, 0, stream>>>(
             xs, ws.ctl, f32, batch, n, strips, prm, ws.ybuf);
+        count_launch(2);
       }
-      root_init_kernel<F32Store><<<batch, n >= 512 ? 1024 : 256, 0, stream>>>(
-          xs, ws.ctl, f32, batch, n, prm, roots);
-      count_launch(1);
+      if (do_init) {
+        root_init_kernel<F32Store><<<batch, n >= 512 ? 1024 : 256, 0, stream>>>(
+            xs, ws.ctl, f32, batch, n, prm, roots);
+        count_launch(1);
+      }
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (gemm_timing_enabled()) {
         cudaEventCreate(&ev0); cudaEventCreate(&ev1);
@@ -582,15 +607,13 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
       gemm_count(max_steps);
     } else {
       rc = tc_engine_iteration(&tc, xs, ws.ctl, ws.errbits, prm, roots, max_steps,
-                               it == 0 ? ws.ybuf : nullptr, stream);
+                               it == 0 ? ws.ybuf : nullptr, do_init, stream);
       if (rc != PC_OK) return rc;
     }
     count_launch(1);
-    cudaMemsetAsync(ws.unfinished, 0, sizeof(int), stream);
-    root_control_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(ws.ctl, ws.errbits, batch,
-                                                                prm, ws.unfinished);
     const int slot = it % kPollRing;
-    cudaMemcpyAsync(hsx.poll + slot, ws.unfinished, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    root_control_kernel<<<1, 1024, 0, stream>>>(ws.ctl, ws.errbits, batch, prm,
+                                                hsx.poll + 2 * slot);
     cudaEventRecord(hsx.ev[slot], stream);
   }
   dim3 fgrid((unsigned)std::min<size_t>(((size_t)n * n + 255) / 256, 64), batch);

@@ -21,7 +21,7 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt
 // strip kernels (scratch of batch * (n / 32 + 2) floats)
 int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* errbits,
                         RootParams prm, float* roots, int max_steps, float* first_init_scratch,
-                        cudaStream_t stream);
+                        bool do_init, cudaStream_t stream);
 int tc_engine_final(TcEngine* e, const RootCtl* ctl, float* roots, float* metrics,
                     cudaStream_t stream);
 

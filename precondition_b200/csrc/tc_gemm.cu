@@ -1465,7 +1465,7 @@ static int launch_phase(TcHostState* hs, int passes, int s, cudaStream_t stream)
 
 int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* errbits,
                         RootParams prm, float* roots, int max_steps, float* first_init_scratch,
-                        cudaStream_t stream) {
+                        bool do_init, cudaStream_t stream) {
   auto* hs = static_cast<TcHostState*>(e->host_state);
   hs->prm.ctl = ctl;
   hs->prm.errbits = errbits;
@@ -1482,9 +1482,11 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
         xs, ctl, ps, e->batch, e->n, strips, prm, first_init_scratch);
     count_launch(2);
   }
-  root_init_kernel<PlaneStore><<<e->batch, 1024, 0, stream>>>(xs, ctl, ps, e->batch, e->n, prm,
-                                                             roots);
-  count_launch(1);
+  if (do_init) {  // (re)initialise whoever needs it: first iteration, or a retry was reported
+    root_init_kernel<PlaneStore><<<e->batch, 1024, 0, stream>>>(xs, ctl, ps, e->batch, e->n, prm,
+                                                               roots);
+    count_launch(1);
+  }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (gemm_timing_enabled()) {
     cudaEventCreate(&ev0); cudaEventCreate(&ev1);
