@@ -230,6 +230,9 @@ struct TcParams {
   uint32_t* sync_ctr_next;  // the next launch's counters: zeroed by this launch
   int sync_group;           // items per group: per_mat, or per (matrix, op)
   int sync_arrivals;        // arrivals that release a group (= sync_group x CTAs per item)
+  // PC_TC_ABLATE (diagnostics only, results are garbage): bit 0 = the epilogue computes but
+  // neither stages nor stores; bit 1 = the accumulate warps skip the TMEM pull and the adds.
+  int ablate;
 };
 
 struct TcWork {
@@ -550,7 +553,8 @@ __device__ __forceinline__ void store_plane_block_tma(uint32_t bufD, uint32_t bu
                                                       const EpiAddr& ea, int lane,
                                                       uint32_t (&hp)[16], bool diag_sub,
                                                       bool do_mirror, const CUtensorMap* map,
-                                                      int row0, int col0, int mat) {
+                                                      int row0, int col0, int mat, int ablate) {
+  if (ablate & 1) return;
   if (lane == 0) tma_store_wait_read0();  // previous stores have consumed the buffers
   __syncwarp();
 #pragma unroll
@@ -620,7 +624,7 @@ __device__ __forceinline__ void store_block_3planes_tma(const TcParams& P, uint3
       }
     }
     store_plane_block_tma(stage, stage + TC_STAGE_BYTES_PER_WARP, ea, lane, hp, diag_sub,
-                          do_mirror, smaps[pl], row0, col0, mat);
+                          do_mirror, smaps[pl], row0, col0, mat, P.ablate);
   }
 }
 
@@ -839,13 +843,15 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
         mbar_wait(tfull_bar(acc), (chunk >> 1) & 1);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + lane_off + acc * TC_BN;
+        if (!(P.ablate & 2)) {
 #pragma unroll
-        for (int c = 0; c < TC_BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
+          for (int c = 0; c < TC_BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
+          }
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -1362,6 +1368,8 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt
     // plane formats (36 of 64 tiles instead of 40 of 64, hidden epilogue), so the CTA-pair
     // kernel is opt-in: PC_TC_PAIR256=1
     hs->use_pair256 = (n % 256 == 0) && (p256 && p256[0] == '1');
+    const char* ab = getenv("PC_TC_ABLATE");
+    hs->prm.ablate = ab ? atoi(ab) : 0;
     const char* ck = getenv("PC_TC_CHUNK");
     // measured on B200: 128-column chunks are not faster (the TMEM pull is not the limiter)
     // and cost accuracy, so 64 stays the default; PC_TC_CHUNK=2 selects 128

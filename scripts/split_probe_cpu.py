@@ -9,7 +9,7 @@ sys.path.insert(0, ".")
 from oracle import numerics as N
 from oracle.gen_golden import gen_symmetric_matrix, ema_statistics
 
-CH = 64
+CH = int(__import__("os").environ.get("PROBE_CHUNK", "64"))
 
 def bf16(x):
   x = np.asarray(x, np.float32)
