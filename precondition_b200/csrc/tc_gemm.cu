@@ -401,9 +401,10 @@ __device__ __forceinline__ void umma_any(uint32_t d, uint64_t a, uint64_t b, uin
 // scaled fp16 planes, cross terms of one k-block: D (+)= A0 B1 + A1 B0   (both x 2^11)
 template <bool k2sm>
 __device__ __forceinline__ void issue_fp16_cross(uint32_t d, uint32_t a0, uint32_t b0,
-                                                 uint32_t idesc, bool first) {
+                                                 uint32_t idesc, bool first,
+                                                 uint32_t b_plane = TC_TILE_BYTES) {
   const uint64_t a0d = make_kmajor_sw128_desc(a0), a1d = make_kmajor_sw128_desc(a0 + TC_TILE_BYTES);
-  const uint64_t b0d = make_kmajor_sw128_desc(b0), b1d = make_kmajor_sw128_desc(b0 + TC_TILE_BYTES);
+  const uint64_t b0d = make_kmajor_sw128_desc(b0), b1d = make_kmajor_sw128_desc(b0 + b_plane);
 #pragma unroll
   for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
     umma_any<k2sm>(d, a0d + 2u * k, b1d + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
@@ -905,6 +906,264 @@ tc_phase_kernel_ws(const __grid_constant__ CUtensorMap tmap0,
 }
 
 // ---------------------------------------------------------------------------
+// CTA-pair kernel with the 1-CTA kernel's role structure (scaled-fp16 planes only):
+// cta_group::2, M = 256, N = 128.  A cluster of two CTAs owns a 256 x 128 block of the
+// result; CTA r holds A rows [r*128, +128) and HALF of the B tile (rows [r*64, +64)), the
+// leader's elected thread issues the MMAs for both, and every CTA keeps the 1-CTA kernel's
+// private pipeline for ITS 128 x 128 accumulator: chunk-accumulation warpgroup -> two TMEM
+// output stages -> two epilogue warpgroups (so the epilogue stays hidden, unlike pair256).
+// Why: the ablation (profiles/r01s2_ncu_full_fp16x3.md) shows the 1-CTA kernel is paced by
+// shared-memory operand fetch (8 KB read + 5.3 KB TMA-written per 64-cycle MMA).  Here each
+// SM reads 6 KB and receives 4 KB per MMA: 4 stages of 48 KB.
+// Tiles: (tm2, tn) with tn <= 2 tm2 + 1; the strictly-upper half of a diagonal pair is
+// computed but not written (20 pair tiles = 40 of 64 tiles at n = 1024).
+// ---------------------------------------------------------------------------
+constexpr uint32_t kIdescF16M256N128 =
+    (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+// loads rows [row_off, row_off + 64) of storage tile (tile_row, tile_col): 8 KiB (box 64 x 64)
+__device__ __forceinline__ void tma_load_half_tile_2sm(uint32_t dst, const CUtensorMap* map,
+                                                       uint32_t bar, int tile_col, int tile_row,
+                                                       int row_off, int mat) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(0), "r"(row_off),
+      "r"(tile_col), "r"(tile_row), "r"(mat)
+      : "memory");
+}
+
+// pair-tile index t -> (tm2, tn), tn <= 2 tm2 + 1, t = tm2 (tm2 + 1) + tn
+__device__ __forceinline__ void pair_decode(int t, int& tm2, int& tn) {
+  int r = (int)((sqrtf(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while (r * (r + 1) > t) --r;
+  while ((r + 1) * (r + 2) <= t) ++r;
+  tm2 = r;
+  tn = t - r * (r + 1);
+}
+
+__device__ __forceinline__ bool tc_get_work_ws2(const TcParams& P, const Program* progs, int s,
+                                                int w, int cta_rank, TcWork& out) {
+  const int t2 = P.tiles / 2;
+  const int npair = t2 * (t2 + 1);
+  const int per_mat = tc_ops_per_matrix(s) * npair;
+  const int b = w / per_mat;
+  int r = w - b * per_mat;
+  const int op = r / npair;
+  r -= op * npair;
+  const RootCtl& c = P.ctl[b];
+  if (!c.active) return false;
+  out.op = op;
+  if (op == 1) {
+    out.st = Step{LB_HN, LB_H, LB_MI, 0};
+  } else {
+    const Program& pr = progs[c.p];
+    if (s >= pr.nsteps) return false;
+    out.st = pr.steps[s];
+  }
+  int tm2;
+  pair_decode(r, tm2, out.tn);
+  out.b = b;
+  out.tm = 2 * tm2 + cta_rank;
+  out.cur = c.cur;
+  out.p = c.p;
+  out.pad = c.pad;
+  out.kblocks = (c.pad + TC_BK - 1) / TC_BK;
+  return true;
+}
+
+template <int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_WS_THREADS, 1)
+tc_phase_kernel_ws2(const __grid_constant__ CUtensorMap tmap0,
+                    const __grid_constant__ CUtensorMap tmap1,
+                    const __grid_constant__ CUtensorMap hmap0,
+                    const __grid_constant__ CUtensorMap hmap1,
+                    const __grid_constant__ CUtensorMap smap0,
+                    const __grid_constant__ CUtensorMap smap1, const TcParams P,
+                    const Program* __restrict__ progs, int s, int total_work) {
+  constexpr int kATile = TC_TILE_BYTES;      // 128 rows x 64 k
+  constexpr int kBTile = TC_TILE_BYTES / 2;  // this CTA's 64 rows of the B tile
+  constexpr int kStageBytes = 2 * (kATile + kBTile);  // A0 A1 B0h B1h = 48 KiB
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };                         // leader's
+  auto empty_bar = [&](int i) { return bar_base + 8u * (kStages + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };   // leader's
+  auto ofull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 4 + i); };
+  auto oempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 6 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 8);
+  const uint32_t stage_base = bar_base + 1024;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full_bar(i), 2);   // one arrival per CTA of the pair (+ the tx bytes of both)
+      mbar_init(empty_bar(i), 1);  // tcgen05.commit, multicast to both CTAs
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);   // tcgen05.commit, multicast
+      mbar_init(tempty_bar(i), 8);  // 4 accumulate warps x 2 CTAs (leader's barrier)
+      mbar_init(ofull_bar(i), 4);
+      mbar_init(oempty_bar(i), 8);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && elect_one()) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+#pragma unroll 1
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        TcWork wk;
+        if (!tc_get_work_ws2(P, progs, s, w, (int)cta_rank, wk)) continue;
+        const int pa = physical_buf(wk.st.a, wk.cur), pb = physical_buf(wk.st.b, wk.cur);
+#pragma unroll 1
+        for (int kb = 0; kb < wk.kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t dst = smem_base + stage * kStageBytes;
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
+          else mbar_arrive_remote(full_bar(stage), 0);
+          tma_load_tile_2sm(dst, &tmap0, full_bar(stage), kb, wk.tm, pa * P.batch + wk.b);
+          tma_load_tile_2sm(dst + kATile, &tmap1, full_bar(stage), kb, wk.tm, pa * P.batch + wk.b);
+          tma_load_half_tile_2sm(dst + 2 * kATile, &hmap0, full_bar(stage), kb, wk.tn,
+                                 (int)cta_rank * 64, pb * P.batch + wk.b);
+          tma_load_half_tile_2sm(dst + 2 * kATile + kBTile, &hmap1, full_bar(stage), kb, wk.tn,
+                                 (int)cta_rank * 64, pb * P.batch + wk.b);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && leader && elect_one()) {
+      // ===================== MMA issuer (leader CTA) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      int chunk = 0;
+#pragma unroll 1
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        TcWork wk;
+        if (!tc_get_work_ws2(P, progs, s, w, 0, wk)) continue;
+#pragma unroll 1
+        for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+          const int acc = chunk & 1;
+          mbar_wait(tempty_bar(acc), ((chunk >> 1) & 1) ^ 1);
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * TC_BN;
+          const uint32_t a0 = smem_base + stage * kStageBytes;
+          const uint32_t b0 = a0 + 2 * kATile;
+          issue_fp16_cross<true>(tmem_d, a0, b0, kIdescF16M256N128, true, kBTile);
+          issue_fp16_main<true>(tmem_d, a0, b0, kIdescF16M256N128, true);
+          umma_commit_2sm(empty_bar(stage));  // frees the slot in both CTAs
+          umma_commit_2sm(tfull_bar(acc));    // chunk accumulator ready in both CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ============ warpgroup 1: chunk accumulation -> TMEM output stage (own 128 rows) ============
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int q = warp & 3;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    int chunk = 0, tile = 0;
+#pragma unroll 1
+    for (int w = cluster_id; w < total_work; w += num_clusters) {
+      TcWork wk;
+      if (!tc_get_work_ws2(P, progs, s, w, (int)cta_rank, wk)) continue;
+      float sum[TC_BN];
+#pragma unroll
+      for (int i = 0; i < TC_BN; ++i) sum[i] = 0.f;
+#pragma unroll 1
+      for (int kb = 0; kb < wk.kblocks; ++kb, ++chunk) {
+        const int acc = chunk & 1;
+        mbar_wait(tfull_bar(acc), (chunk >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + lane_off + acc * TC_BN;
+        if (!(P.ablate & 2)) {
+#pragma unroll
+          for (int c = 0; c < TC_BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(r[i]);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_remote(tempty_bar(acc), 0);
+        }
+      }
+      const int o = tile & 1;
+      mbar_wait(oempty_bar(o), ((tile >> 1) & 1) ^ 1);
+      tcgen05_fence_after();
+      const uint32_t oaddr = tmem_base + lane_off + 256 + o * TC_BN;
+#pragma unroll
+      for (int c = 0; c < TC_BN / 32; ++c) {
+        uint32_t r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(sum[c * 32 + i]);
+        tmem_st_32x32(oaddr + c * 32, r);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ofull_bar(o));
+      ++tile;
+    }
+  } else {
+    // ============ warpgroups 2, 3: epilogue of this CTA's 128 x 128 tile ============
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    const int q = warp & 3;
+    const int half = (warp >> 2) - 2;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    int tile = 0;
+#pragma unroll 1
+    for (int w = cluster_id; w < total_work; w += num_clusters) {
+      TcWork wk;
+      if (!tc_get_work_ws2(P, progs, s, w, (int)cta_rank, wk)) continue;
+      const int o = tile & 1;
+      mbar_wait(ofull_bar(o), (tile >> 1) & 1);
+      tcgen05_fence_after();
+      if (wk.tm < wk.tn) {
+        // strictly-upper tile of a diagonal pair: its mirror owns it; just recycle the stage
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(oempty_bar(o));
+      } else {
+        const CUtensorMap* const smaps[3] = {&smap0, &smap1, &smap1};
+        tc_epilogue_tile_tmem<TC_FMT_FP16S>(P, wk, wk.tm, row_in_tile, lane,
+                              stage_base + (warp - 8) * 2 * TC_STAGE_BYTES_PER_WARP,
+                              tmem_base + lane_off + 256 + o * TC_BN, oempty_bar(o), 2 * half,
+                              2 * half + 2, smaps);
+      }
+      ++tile;
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // no CTA may exit while its peer can still signal it
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
 // CTA-pair kernel, 256 x 256 output tile per cluster (cta_group::2, M = 256, N = 256).
 // This is the configuration that un-saturates shared memory: a 1-CTA M=128/N=128 MMA
 // reads 8 KB of operands per 64 cycles = the full 128 B/cycle smem bandwidth, so TMA
@@ -1271,6 +1530,8 @@ size_t tc_engine_bytes(int batch, int n, int planes) {
 struct TcHostState {
   CUtensorMap maps[3];     // operand loads: one 128 x 64 storage tile (16 KiB, contiguous)
   CUtensorMap maps_st[3];  // epilogue bulk stores: box {32, 32}, SWIZZLE_64B
+  CUtensorMap maps_half[2];  // B half tiles of the ws2 kernel: box {64, 64}, SWIZZLE_128B
+  bool use_ws2;            // cta_group::2 M=256/N=128 kernel with output stages (fp16 planes)
   bool use_pair256;        // cta_group::2, 256 x 256 cluster tiles (PC_TC_PAIR256=1)
   int fmt, planes;         // TC_FMT_*, stored planes per matrix
   int chunk_kb;            // 64-column k-blocks accumulated in TMEM before the fp32 register add
@@ -1346,6 +1607,11 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt
     CUresult r = enc(&hs->maps[pl], dt, 5, plane, dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint32_t box_h[5] = {64, 64, 1, 1, 1};
+    if (r == CUDA_SUCCESS && pl < 2)
+      r = enc(&hs->maps_half[pl], dt, 5, plane, dims, strides, box_h, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     cuuint32_t box_s[5] = {32, 32, 1, 1, 1};
     if (r == CUDA_SUCCESS)
       r = enc(&hs->maps_st[pl], dt, 5, plane, dims, strides, box_s,
@@ -1368,6 +1634,8 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt
     // plane formats (36 of 64 tiles instead of 40 of 64, hidden epilogue), so the CTA-pair
     // kernel is opt-in: PC_TC_PAIR256=1
     hs->use_pair256 = (n % 256 == 0) && (p256 && p256[0] == '1');
+    const char* w2 = getenv("PC_TC_WS2");
+    hs->use_ws2 = fmt == TC_FMT_FP16S && (n % 256 == 0) && (w2 && w2[0] == '1');
     const char* ab = getenv("PC_TC_ABLATE");
     hs->prm.ablate = ab ? atoi(ab) : 0;
     const char* ck = getenv("PC_TC_CHUNK");
@@ -1454,7 +1722,28 @@ static int launch_phase_pair256(TcHostState* hs, int s, cudaStream_t stream) {
   return PC_OK;
 }
 
+static int launch_phase_ws2(TcHostState* hs, int s, cudaStream_t stream) {
+  constexpr int kStages = 4;
+  constexpr size_t smem = (size_t)kStages * 3 * TC_TILE_BYTES + 1024 + 1024 +
+                          16 * TC_STAGE_BYTES_PER_WARP;
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_ws2<kStages>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int t2 = hs->prm.tiles / 2;
+  int clusters, total_work;
+  plan_launch(hs, s, t2 * (t2 + 1), hs->sms / 2, 2, &clusters, &total_work);
+  hs->prm.sync_group = 0;
+  tc_phase_kernel_ws2<kStages><<<2 * clusters, TC_WS_THREADS, smem, stream>>>(
+      hs->maps[0], hs->maps[1], hs->maps_half[0], hs->maps_half[1], hs->maps_st[0],
+      hs->maps_st[1], hs->prm, hs->progs_dev, s, total_work);
+  return PC_OK;
+}
+
 static int launch_phase(TcHostState* hs, int passes, int s, cudaStream_t stream) {
+  if (hs->fmt == TC_FMT_FP16S && hs->use_ws2) return launch_phase_ws2(hs, s, stream);
   if (hs->fmt == TC_FMT_FP16S) {
     // K-chunk of 128 columns (24 MMAs per TMEM accumulation, like bf16x6 at 64): the
     // chunk pull from TMEM (64 B/clk) then stays shorter than the chunk's MMAs
