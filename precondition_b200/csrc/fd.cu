@@ -177,6 +177,7 @@ fd_row_normalize_kernel(float* __restrict__ x, int rows, int len) {
 constexpr int kJacThreads = 512;
 constexpr int kJacMaxN = 512;
 constexpr int kJacMaxSweeps = 15;
+constexpr int kJacCnt = kJacMaxSweeps + 1;  // per-matrix counters: rotations per sweep + max row norm^2
 
 __device__ __forceinline__ void jac_cluster_sync(int csize) {
   if (csize > 1) {
@@ -197,7 +198,7 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
   if (csize > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   float* A = a_all + (size_t)b * n * n;
   float* V = vt_all ? vt_all + (size_t)b * n * n : nullptr;
-  unsigned* cnt = rot_count + (size_t)b * kJacMaxSweeps;
+  unsigned* cnt = rot_count + (size_t)b * kJacCnt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarp = (kJacThreads / 32) * csize, gw = crank * (kJacThreads / 32) + warp;
   const bool with_v = vt_all != nullptr;  // without V: rows of A are a FACTOR (A = G, G^T G = T)
@@ -210,8 +211,15 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
   const int m2 = (n + 1) & ~1;  // players (one phantom if n is odd)
   const int rounds = m2 - 1, npairs = m2 / 2;
   constexpr int Q = kJacMaxN / 32;
+  // Rows whose norm is below 1e-5 of the largest one are rounding noise (they belong to
+  // eigenvalues that are numerically zero): two such rows are never rotated against each
+  // other, otherwise their random mutual angles keep every sweep busy.  The largest squared
+  // row norm of the previous sweep is kept next to the rotation counters.
+  unsigned* amax_bits = cnt + kJacMaxSweeps;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     unsigned rotated = 0;
+    const float noise2 = 1e-10f * __uint_as_float(__ldcg(amax_bits));
+    float seen_max = 0.f;
     for (int t = 0; t < rounds; ++t) {
       for (int p = gw; p < npairs; p += nwarp) {
         int i, j;  // circle method: player m2-1 is fixed, the others rotate
@@ -231,8 +239,10 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
           ga = fmaf(ai[q], aj[q], ga);
         }
         al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+        seen_max = fmaxf(seen_max, fmaxf(al, be));
         const float lim = tol * sqrtf(al) * sqrtf(be);
         if (!(fabsf(ga) > lim) || lim == 0.f) continue;  // warp-uniform
+        if (fmaxf(al, be) < noise2) continue;            // both rows are noise
         ++rotated;
         const float zeta = (be - al) / (2.0f * ga);
         const float tt = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
@@ -254,6 +264,7 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
       jac_cluster_sync(csize);
     }
     if (lane == 0 && rotated) atomicAdd(cnt + sweep, rotated);
+    if (lane == 0 && seen_max > 0.f) atomicMax(amax_bits, __float_as_uint(seen_max));
     __threadfence();
     jac_cluster_sync(csize);
     if (__ldcg(cnt + sweep) == 0u) break;  // uniform across the cluster
@@ -451,7 +462,7 @@ static size_t fd_carve(FdWorkspace* w, char* base, int batch, int d, int m, int 
   const int k = pl.k;
   const int rot_slots = 64;  // Jacobi calls per update (each uses kJacMaxSweeps counters)
   w->scal = (FdScalars*)take(B * sizeof(FdScalars));
-  w->rot = (unsigned*)take(B * kJacMaxSweeps * rot_slots * sizeof(unsigned));
+  w->rot = (unsigned*)take(B * kJacCnt * rot_slots * sizeof(unsigned));
   w->bs = (float*)take(B * d * rank * 4);
   w->fm = gram ? nullptr : (float*)take(B * d * m * 4);
   w->cmat = (float*)take(B * d * d * 4);
@@ -512,11 +523,11 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
   fd_carve(&w, reinterpret_cast<char*>(align_up((size_t)workspace, 256)), batch, d, m, rank, pl,
            gram);
   const int k = pl.k;
-  PC_CUDA_CHECK(cudaMemsetAsync(w.rot, 0, (size_t)batch * kJacMaxSweeps * 64 * sizeof(unsigned),
+  PC_CUDA_CHECK(cudaMemsetAsync(w.rot, 0, (size_t)batch * kJacCnt * 64 * sizeof(unsigned),
                                 stream));
   int jac_calls = 0;
   auto jacobi = [&](float* a, float* vt, int n, bool orth_only = false) -> int {
-    unsigned* rot = w.rot + (size_t)(jac_calls++ % 64) * batch * kJacMaxSweeps;
+    unsigned* rot = w.rot + (size_t)(jac_calls++ % 64) * batch * kJacCnt;
     // orthonormalisation solves act on a Gram matrix of unit rows (nearly the identity once
     // the basis has settled) and are followed by a Rayleigh-Ritz solve: a loose tolerance
     // and a few sweeps suffice there
@@ -847,7 +858,7 @@ lr_pack_kernel(const float* __restrict__ vs, const float* __restrict__ sorted,
 
 size_t low_rank_root_bytes(int batch, int d) {
   const size_t B = (size_t)batch, nn = (size_t)d * d * 4;
-  return 6 * align_up(B * nn, 256) + 4 * align_up(B * d * 4, 256) + align_up(B * kJacMaxSweeps * 4, 256) +
+  return 6 * align_up(B * nn, 256) + 4 * align_up(B * d * 4, 256) + align_up(B * kJacCnt * 4, 256) +
          align_up((size_t)d * 4, 256) + align_up(2 * B * d * 4, 256) + 2048;
 }
 
@@ -902,13 +913,13 @@ int run_low_rank_root(const float* xs, const int32_t* ps, const int32_t* pads, i
   float* sorted = (float*)take(B * d * 4);
   int* order = (int*)take(B * d * 4);
   float* lambdas = (float*)take(B * d * 4);    // [batch] lambdas, [batch] ridge, [batch] err bits
-  unsigned* rot = (unsigned*)take(B * kJacMaxSweeps * 4);
+  unsigned* rot = (unsigned*)take(B * kJacCnt * 4);
   float* v0 = (float*)take((size_t)d * 4);
   float* ybuf = (float*)take(2 * B * d * 4);
   float* ridge = lambdas + batch;
   uint32_t* errbits = reinterpret_cast<uint32_t*>(lambdas + 2 * (size_t)batch);
   const unsigned g = (unsigned)std::min<size_t>((nn + 255) / 256, 512);
-  PC_CUDA_CHECK(cudaMemsetAsync(rot, 0, B * kJacMaxSweeps * 4, stream));
+  PC_CUDA_CHECK(cudaMemsetAsync(rot, 0, B * kJacCnt * 4, stream));
   PC_CUDA_CHECK(cudaMemsetAsync(lambdas, 0, B * d * 4, stream));
   lr_mask_kernel<<<dim3(g, batch), 256, 0, stream>>>(xs, pads, d, reg);
   if (relative) {
