@@ -227,13 +227,20 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
         else { i = (t + p) % rounds; j = (t - p + rounds) % rounds; }
         if (i > j) { const int tmp = i; i = j; j = tmp; }
         if (j >= n) continue;  // phantom
-        float ai[Q], aj[Q];
+        float ai[Q], aj[Q], vi[Q], vj[Q];
         float al = 0.f, be = 0.f, ga = 0.f;
+        // the V rows are fetched together with the A rows: one L2 round trip per pair instead
+        // of two on the critical path of the round (most pairs rotate in the early sweeps)
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           const int c = lane + 32 * q;
           ai[q] = c < n ? __ldcg(A + (size_t)i * n + c) : 0.f;
           aj[q] = c < n ? __ldcg(A + (size_t)j * n + c) : 0.f;
+          vi[q] = (with_v && c < n) ? __ldcg(V + (size_t)i * n + c) : 0.f;
+          vj[q] = (with_v && c < n) ? __ldcg(V + (size_t)j * n + c) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
           al = fmaf(ai[q], ai[q], al);
           be = fmaf(aj[q], aj[q], be);
           ga = fmaf(ai[q], aj[q], ga);
@@ -254,9 +261,8 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
             __stcg(A + (size_t)i * n + c, cs * ai[q] - sn * aj[q]);
             __stcg(A + (size_t)j * n + c, sn * ai[q] + cs * aj[q]);
             if (with_v) {
-              const float vi = __ldcg(V + (size_t)i * n + c), vj = __ldcg(V + (size_t)j * n + c);
-              __stcg(V + (size_t)i * n + c, cs * vi - sn * vj);
-              __stcg(V + (size_t)j * n + c, sn * vi + cs * vj);
+              __stcg(V + (size_t)i * n + c, cs * vi[q] - sn * vj[q]);
+              __stcg(V + (size_t)j * n + c, sn * vi[q] + cs * vj[q]);
             }
           }
         }
