@@ -174,7 +174,6 @@ fd_row_normalize_kernel(float* __restrict__ x, int rows, int len) {
 // cluster shares one matrix (rows live in L2, ld/st.cg) and a cluster barrier separates
 // rounds.  theta_i = <A_i, Vt_i> (Rayleigh quotient; A_i = theta_i v_i at convergence).
 // ---------------------------------------------------------------------------
-constexpr int kJacThreads = 512;
 constexpr int kJacMaxN = 512;
 constexpr int kJacMaxSweeps = 15;
 constexpr int kJacCnt = kJacMaxSweeps + 1;  // per-matrix counters: rotations per sweep + max row norm^2
@@ -189,6 +188,9 @@ __device__ __forceinline__ void jac_cluster_sync(int csize) {
   }
 }
 
+// Q = row elements per lane (n <= 32 Q), kJacThreads = CTA size: shorter rows leave registers for
+// more warps per CTA, so that one round needs a single pass over the pairs.
+template <int Q, int kJacThreads>
 __global__ void __launch_bounds__(kJacThreads)
 fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, float tol,
                  unsigned* __restrict__ rot_count, float* __restrict__ theta_all, int csize,
@@ -210,7 +212,6 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
   jac_cluster_sync(csize);
   const int m2 = (n + 1) & ~1;  // players (one phantom if n is odd)
   const int rounds = m2 - 1, npairs = m2 / 2;
-  constexpr int Q = kJacMaxN / 32;
   // Rows whose norm is below 1e-5 of the largest one are rounding noise (they belong to
   // eigenvalues that are numerically zero): two such rows are never rotated against each
   // other, otherwise their random mutual angles keep every sweep busy.  The largest squared
@@ -491,14 +492,14 @@ static size_t fd_carve(FdWorkspace* w, char* base, int batch, int d, int m, int 
   return off + 256;
 }
 
-static int fd_jacobi(float* a, float* vt, int n, int batch, unsigned* rot, float* theta,
-                     cudaStream_t stream, float tol = 3e-6f, int max_sweeps = kJacMaxSweeps) {
-  max_sweeps = std::min(max_sweeps, kJacMaxSweeps);
+template <int Q, int kThreads>
+static int fd_jacobi_launch(float* a, float* vt, int n, int batch, unsigned* rot, float* theta,
+                            cudaStream_t stream, float tol, int max_sweeps) {
   int csize = 1;
-  while (csize < 8 && (kJacThreads / 32) * csize < (n + 1) / 2) csize <<= 1;
+  while (csize < 8 && (kThreads / 32) * csize < (n + 1) / 2) csize <<= 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(batch * csize));
-  cfg.blockDim = dim3(kJacThreads);
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -508,10 +509,19 @@ static int fd_jacobi(float* a, float* vt, int n, int batch, unsigned* rot, float
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fd_jacobi_kernel, a, vt, n, tol, rot, theta, csize,
-                                   max_sweeps));
+  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fd_jacobi_kernel<Q, kThreads>, a, vt, n, tol, rot, theta,
+                                   csize, max_sweeps));
   count_launch(1);
   return PC_OK;
+}
+
+static int fd_jacobi(float* a, float* vt, int n, int batch, unsigned* rot, float* theta,
+                     cudaStream_t stream, float tol = 3e-6f, int max_sweeps = kJacMaxSweeps) {
+  max_sweeps = std::min(max_sweeps, kJacMaxSweeps);
+  if (n <= 128) return fd_jacobi_launch<4, 512>(a, vt, n, batch, rot, theta, stream, tol, max_sweeps);
+  if (n <= 256) return fd_jacobi_launch<8, 640>(a, vt, n, batch, rot, theta, stream, tol, max_sweeps);
+  if (n <= 384) return fd_jacobi_launch<12, 640>(a, vt, n, batch, rot, theta, stream, tol, max_sweeps);
+  return fd_jacobi_launch<16, 512>(a, vt, n, batch, rot, theta, stream, tol, max_sweeps);
 }
 
 int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
