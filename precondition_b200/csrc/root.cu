@@ -175,7 +175,8 @@ power_iteration_kernel(const float* __restrict__ xs, const int32_t* __restrict__
     const float norm = sqrtf(block_sum(ss, scratch));
     for (int i = threadIdx.x; i < n; i += blockDim.x) nv[i] = v[i] / norm;  // DS:634
     __syncthreads();
-    float* yout = ybuf + ((size_t)b * 2 + (it & 1)) * n;
+    // one CTA per matrix: the product stays in shared memory (no L2 round trip per step)
+    float* yout = csize > 1 ? ybuf + ((size_t)b * 2 + (it & 1)) * n : smem + 2 * n;
     for (int row = r_lo + warp; row < r_hi; row += nwarp) {
       float acc = 0.f;
       if (row < pad) {
@@ -205,7 +206,7 @@ power_iteration_kernel(const float* __restrict__ xs, const int32_t* __restrict__
     }
     float dot = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const float yi = __ldcg(yout + i);
+      const float yi = csize > 1 ? __ldcg(yout + i) : yout[i];
       v[i] = yi;
       dot += nv[i] * yi;
     }
@@ -443,7 +444,7 @@ int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n,
     }
   }
   PC_CUDA_CHECK(cudaMemcpyAsync(v0_dev, v0, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
-  const size_t smem = sizeof(float) * 2 * (size_t)n;
+  const size_t smem = sizeof(float) * 3 * (size_t)n;  // v, v / |v|, and A v when csize == 1
   if (smem > 48 * 1024) {
     PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
