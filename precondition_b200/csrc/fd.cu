@@ -20,10 +20,17 @@
 #include <math.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "simt_gemm.cuh"
 
 namespace pc {
+
+// tcgen05 grouped GEMM (tc_gemm.cu): used for the covariance build when d % 128 == 0
+bool tc_engine_available();
+size_t tc_grouped_gemm_workspace_bytes(const pc_gemm_desc* descs, int count);
+int tc_grouped_gemm(const pc_gemm_desc* descs, const pc_gemm_quant* quant, int count,
+                    void* workspace, size_t workspace_bytes, int reuse_plan, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
 // batched strided GEMM, descriptor by value:
@@ -455,7 +462,35 @@ struct FdWorkspace {
   FdScalars* scal; unsigned* rot; float* bs; float* fm; float* cmat; float* vt; float* theta;
   float* sorted; int* order; float* rscale; float* yt; float* qt; float* pt; float* small;
   float* zsel; float* vtop;
+  char* tcws; size_t tcws_bytes;  // tcgen05 grouped-GEMM workspace of the covariance build
 };
+
+// descriptors of the covariance build on the tcgen05 grouped GEMM (host side, per matrix)
+static void fd_cov_descs(const float* fm, const float* bs, float* cmat, int batch, int d, int m,
+                         int rank, bool gram, std::vector<pc_gemm_desc>* first,
+                         std::vector<pc_gemm_desc>* second) {
+  for (int b = 0; b < batch; ++b) {
+    pc_gemm_desc g{};
+    g.c = cmat + (size_t)b * d * d;
+    g.c_iinner = d; g.c_sio = 0; g.c_sii = d;
+    g.a_iinner = d; g.a_sio = 0; g.a_sko = g.b_sko = 0; g.a_ski = g.b_ski = 1;
+    g.m = g.n = d;
+    if (!gram) {  // C = F F^T
+      pc_gemm_desc f = g;
+      f.a = f.b = fm + (size_t)b * d * m;
+      f.a_si = f.b_sj = m; f.a_kinner = f.b_kinner = m; f.k = m;
+      f.c_in = nullptr; f.alpha = 1.f; f.beta = 0.f;
+      first->push_back(f);
+    }
+    pc_gemm_desc s2 = g;  // C += Bs Bs^T
+    s2.a = s2.b = bs + (size_t)b * d * rank;
+    s2.a_si = s2.b_sj = rank; s2.a_kinner = s2.b_kinner = rank; s2.k = rank;
+    s2.c_in = g.c; s2.alpha = 1.f; s2.beta = 1.f;
+    second->push_back(s2);
+  }
+}
+
+static bool fd_use_tc(int d) { return d % 128 == 0 && d >= 256 && tc_engine_available(); }
 
 static size_t fd_carve(FdWorkspace* w, char* base, int batch, int d, int m, int rank,
                        const FdPlan& pl, bool gram) {
@@ -488,6 +523,18 @@ static size_t fd_carve(FdWorkspace* w, char* base, int batch, int d, int m, int 
   } else {
     w->yt = w->qt = w->pt = w->small = w->zsel = nullptr;
     w->vtop = (float*)take(B * (rank + 1) * d * 4);
+  }
+  w->tcws = nullptr;
+  w->tcws_bytes = 0;
+  if (fd_use_tc(d)) {
+    std::vector<pc_gemm_desc> first, second;
+    fd_cov_descs(nullptr, nullptr, nullptr, batch, d, m, rank, gram, &first, &second);
+    // sized from dummy descriptors: only the extents matter for the plan
+    size_t need = tc_grouped_gemm_workspace_bytes(second.data(), (int)second.size());
+    if (!first.empty())
+      need = std::max(need, tc_grouped_gemm_workspace_bytes(first.data(), (int)first.size()));
+    w->tcws_bytes = need + 1024;
+    w->tcws = take(w->tcws_bytes);
   }
   return off + 256;
 }
@@ -558,28 +605,43 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
   count_launch(1);
   const unsigned mgrid = (unsigned)std::min<size_t>(((size_t)d * std::max(d, m) + 255) / 256, 1024);
   // ---- covariance C = Bs Bs^T + (masked) F F^T ----
-  FdGemm g{};
-  g.alpha = 1.f;
   if (gram) {
     fd_mask_kernel<<<dim3(mgrid, batch), 256, 0, stream>>>(new_grad, w.scal, d, d, 1, w.cmat);
-    count_launch(1);
   } else {
     fd_mask_kernel<<<dim3(mgrid, batch), 256, 0, stream>>>(new_grad, w.scal, d, m, m == d ? 1 : 0,
                                                           w.fm);
-    count_launch(1);
-    g.a = g.b = w.fm; g.cin = nullptr; g.c = w.cmat;
-    g.a_bs = g.b_bs = (int64_t)d * m; g.c_bs = (int64_t)d * d;
-    g.a_si = g.b_sj = m; g.a_sk = g.b_sk = 1; g.c_si = d;
-    g.m = g.n = d; g.k = m; g.beta = 0.f;
+  }
+  count_launch(1);
+  if (fd_use_tc(d)) {
+    // symmetric rank-k updates on the tensor cores (scaled-fp16 three-pass, 22-bit operands)
+    std::vector<pc_gemm_desc> first, second;
+    fd_cov_descs(w.fm, w.bs, w.cmat, batch, d, m, rank, gram, &first, &second);
+    if (!first.empty()) {
+      int rc = tc_grouped_gemm(first.data(), nullptr, (int)first.size(), w.tcws, w.tcws_bytes, 0,
+                               stream);
+      if (rc != PC_OK) return rc;
+    }
+    int rc = tc_grouped_gemm(second.data(), nullptr, (int)second.size(), w.tcws, w.tcws_bytes, 0,
+                             stream);
+    if (rc != PC_OK) return rc;
+  } else {
+    FdGemm g{};
+    g.alpha = 1.f;
+    if (!gram) {
+      g.a = g.b = w.fm; g.cin = nullptr; g.c = w.cmat;
+      g.a_bs = g.b_bs = (int64_t)d * m; g.c_bs = (int64_t)d * d;
+      g.a_si = g.b_sj = m; g.a_sk = g.b_sk = 1; g.c_si = d;
+      g.m = g.n = d; g.k = m; g.beta = 0.f;
+      fd_gemm(g, batch, stream);
+    }
+    g = FdGemm{};
+    g.alpha = 1.f; g.beta = 1.f;
+    g.a = g.b = w.bs; g.cin = w.cmat; g.c = w.cmat;
+    g.a_bs = g.b_bs = (int64_t)d * rank; g.c_bs = (int64_t)d * d;
+    g.a_si = g.b_sj = rank; g.a_sk = g.b_sk = 1; g.c_si = d;
+    g.m = g.n = d; g.k = rank;
     fd_gemm(g, batch, stream);
   }
-  g = FdGemm{};
-  g.alpha = 1.f; g.beta = 1.f;
-  g.a = g.b = w.bs; g.cin = w.cmat; g.c = w.cmat;
-  g.a_bs = g.b_bs = (int64_t)d * rank; g.c_bs = (int64_t)d * d;
-  g.a_si = g.b_sj = rank; g.a_sk = g.b_sk = 1; g.c_si = d;
-  g.m = g.n = d; g.k = rank;
-  fd_gemm(g, batch, stream);
 
   const float* vt_final = nullptr;
   int nv = 0;
