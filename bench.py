@@ -416,7 +416,13 @@ def run_ours(a):
   # ---- second half of the headline metric: full Shampoo step on BASELINE config 2
   #      (MLP 512->2048->512, block_size 128, SGD grafting, 1 GPU), through the
   #      optax-style API; steps >= 5 so the preconditioned path is active ----
-  shampoo_step, sketchy = None, None
+  shampoo_step, sketchy, resnet_step = None, None, None
+  if not a.no_step:
+    resnet_step = time_resnet50_step(dev, world)  # every rank takes part (sharded roots)
+    t = torch.tensor([resnet_step["ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    resnet_step["ms"] = float(t.item())
   if world == 1 and not a.no_step:
     shampoo_step = time_shampoo_step(dev)
     sketchy = time_sketchy_update(dev)
@@ -441,7 +447,7 @@ def run_ours(a):
                    "max_error": float(np.nanmax(m_host[:, 0]))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches // 1,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "shampoo_step": shampoo_step,
-        "sketchy_update": sketchy,
+        "sketchy_update": sketchy, "shampoo_step_resnet50": resnet_step,
     }
     print(json.dumps(line), flush=True)
   if world > 1:
@@ -474,6 +480,62 @@ def time_shampoo_step(dev, steps=10, warm=6):
   return {"ms": e0.elapsed_time(e1) / steps, "unit": "ms/step", "steps": steps,
           "config": "MLP 512->2048->512, block_size=128, SGD grafting, preconditioning_compute_steps=1",
           "statistics": int(tm.shape[0]), "newton_iters_mean": float(tm[:, 1].mean()),
+          "max_root_error": float(tm[:, 0].max()),
+          "update_finite": bool(all(torch.isfinite(u).all() for u in upd))}
+
+
+def resnet50_shapes():
+  """ResNet-50 v1.5 parameter shapes (HWIO conv kernels, BN scale / bias vectors, fc):
+  BASELINE config 3."""
+  shapes = [(7, 7, 3, 64), (64,), (64,)]
+  cin = 64
+  for width, blocks in ((64, 3), (128, 4), (256, 6), (512, 3)):
+    for blk in range(blocks):
+      cout = 4 * width
+      for k, ci, co in ((1, cin, width), (3, width, width), (1, width, cout)):
+        shapes += [(k, k, ci, co), (co,), (co,)]
+      if blk == 0:  # projection shortcut
+        shapes += [(1, 1, cin, cout), (cout,), (cout,)]
+      cin = cout
+  shapes += [(2048, 1000), (1000,)]
+  return shapes
+
+
+def time_resnet50_step(dev, world, steps=2, warm=2):
+  """ms per `update` of distributed_shampoo on ResNet-50 shapes, block_size=1024,
+  preconditioning_compute_steps=1 (BASELINE config 3); with more than one rank the
+  preconditioner blocks are partitioned over the ranks and all-gathered (batch_axis_name)."""
+  import torch
+  from precondition_b200 import distributed_shampoo as DS
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(3)  # same parameters / gradients on every rank (replicated state)
+  shapes = resnet50_shapes()
+  params = [torch.randn(s, generator=gen, device=dev) * 0.05 for s in shapes]
+  opt = DS.distributed_shampoo(0.1, 1024, preconditioning_compute_steps=1,
+                               batch_axis_name="batch" if world > 1 else None)
+  state = opt.init(params)
+  grads = [[torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes]
+           for _ in range(warm + steps)]
+  for t in range(warm):
+    _, state = opt.update(grads[t], state, params)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for t in range(warm, warm + steps):
+    upd, state = opt.update(grads[t], state, params)
+  e1.record()
+  torch.cuda.synchronize()
+  tm = torch.cat([st.training_metrics for st in state.stats if st.training_metrics is not None])
+  sizes = {}
+  for st in state.stats:
+    for x in st.statistics:
+      sizes[int(x.shape[0])] = sizes.get(int(x.shape[0]), 0) + 1
+  return {"ms": e0.elapsed_time(e1) / steps, "unit": "ms/step", "steps": steps, "n_gpus": world,
+          "config": "ResNet-50 shapes, block_size=1024, preconditioning_compute_steps=1, "
+                    "blocks sharded over the ranks" if world > 1 else
+                    "ResNet-50 shapes, block_size=1024, preconditioning_compute_steps=1",
+          "parameters": int(sum(p.numel() for p in params)), "statistics": int(tm.shape[0]),
+          "statistics_of_1024": sizes.get(1024, 0),
           "max_root_error": float(tm[:, 0].max()),
           "update_finite": bool(all(torch.isfinite(u).all() for u in upd))}
 

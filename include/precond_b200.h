@@ -165,6 +165,13 @@ typedef struct {
 int pc_grouped_gemm(const pc_gemm_desc* descs, int count, int max_m, int max_n,
                     void* stream);
 
+/* Split-K form of pc_grouped_gemm for descriptors with a small output and a very long
+ * contraction (e.g. the 9 x 9 statistic of a 3 x 3 x 512 x 512 kernel: k = 262144 in a single
+ * tile): `splits` CTAs per tile, partial products summed in a fixed order (deterministic). */
+size_t pc_grouped_gemm_splitk_workspace_bytes(int count, int max_m, int max_n, int splits);
+int pc_grouped_gemm_splitk(const pc_gemm_desc* descs, int count, int max_m, int max_n, int splits,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* tcgen05 path of the grouped GEMM for descriptors whose m and n are multiples of 128 (k is
  * arbitrary; c / c_in 16-byte aligned with c_sii, c_sio multiples of 4): every operand view is
  * packed once into scaled-fp16 plane tiles (22 mantissa bits, per-operand power-of-two scale)

@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "pc_low_rank_root_workspace_bytes", "pc_low_rank_root_batched",
     "pc_inverse_pth_root_eigh_batched",
     "pc_grouped_gemm_tc_quant", "pc_quantize_from_colmax_batched",
+    "pc_grouped_gemm_splitk_workspace_bytes", "pc_grouped_gemm_splitk",
 )
 
 
@@ -169,6 +170,10 @@ def load() -> ctypes.CDLL:
   lib.pc_grouped_gemm_tc_quant.restype = i32
   lib.pc_quantize_from_colmax_batched.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
   lib.pc_quantize_from_colmax_batched.restype = i32
+  lib.pc_grouped_gemm_splitk_workspace_bytes.argtypes = [i32, i32, i32, i32]
+  lib.pc_grouped_gemm_splitk_workspace_bytes.restype = sz
+  lib.pc_grouped_gemm_splitk.argtypes = [vp, i32, i32, i32, i32, vp, sz, vp]
+  lib.pc_grouped_gemm_splitk.restype = i32
   _lib = lib
   return lib
 

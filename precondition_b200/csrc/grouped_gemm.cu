@@ -30,6 +30,56 @@ grouped_gemm_simt_kernel(const pc_gemm_desc* __restrict__ descs) {
                  });
 }
 
+// Split-K variant for descriptors with a small output and a very long contraction (the
+// 9 x 9 statistic of a 3 x 3 x 512 x 512 kernel contracts 262144 elements in ONE tile):
+// blockIdx.z = descriptor * splits + split; every split writes alpha * (its partial product)
+// into part[z][split][m x n], then splitk_reduce_kernel adds the partials in a fixed order
+// (deterministic) and applies beta * C_in.
+__global__ void __launch_bounds__(kSimtThreads)
+grouped_gemm_splitk_kernel(const pc_gemm_desc* __restrict__ descs, int splits, int max_m,
+                           int max_n, float* __restrict__ part) {
+  __shared__ SimtSmem sm;
+  const int z = blockIdx.z / splits, sp = blockIdx.z - z * splits;
+  const pc_gemm_desc d = descs[z];
+  const int tile_m = blockIdx.y, tile_n = blockIdx.x;
+  if (tile_m * kSimtBM >= d.m || tile_n * kSimtBN >= d.n) return;
+  // K range of this split, in whole 32-wide slabs
+  const int slabs = (d.k + kSimtBK - 1) / kSimtBK;
+  const int per = (slabs + splits - 1) / splits;
+  const int k_lo = sp * per * kSimtBK, k_hi = min(d.k, (sp + 1) * per * kSimtBK);
+  float* out = part + ((size_t)z * splits + sp) * max_m * max_n;
+  const OperandView A{d.a, d.a_sio, d.a_si, d.a_sko, d.a_ski, d.a_iinner > 0 ? d.a_iinner : d.m,
+                      d.a_kinner, d.m, k_hi};
+  const OperandView B{d.b, 0, d.b_sj, d.b_sko, d.b_ski, d.n > 0 ? d.n : 1, d.b_kinner, d.n, k_hi};
+  struct Shift {  // views shifted to the split's first column
+    const OperandView& v; int k0;
+    __device__ __forceinline__ float operator()(int i, int kk) const { return v(i, kk + k0); }
+  };
+  const Shift As{A, k_lo}, Bs{B, k_lo};
+  simt_gemm_tile(k_hi > k_lo ? k_hi - k_lo : 0, tile_m, tile_n, As, Bs, A.k_fast(), B.k_fast(), sm,
+                 [&](int i, int j0, const float* acc) {
+                   if (i >= d.m) return;
+#pragma unroll
+                   for (int q = 0; q < 4; ++q)
+                     if (j0 + q < d.n) out[(size_t)i * max_n + j0 + q] = d.alpha * acc[q];
+                 });
+}
+
+__global__ void splitk_reduce_kernel(const pc_gemm_desc* __restrict__ descs, int splits, int max_m,
+                                     int max_n, const float* __restrict__ part) {
+  const pc_gemm_desc d = descs[blockIdx.y];
+  const float* p0 = part + (size_t)blockIdx.y * splits * max_m * max_n;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d.m * d.n; e += gridDim.x * blockDim.x) {
+    const int i = e / d.n, j = e - i * d.n;
+    float v = 0.f;
+    for (int sp = 0; sp < splits; ++sp) v += p0[((size_t)sp * max_m + i) * max_n + j];
+    const int io = i / d.c_iinner, ii = i - io * d.c_iinner;
+    const int64_t row = io * d.c_sio + ii * d.c_sii;
+    if (d.c_in) v = fmaf(d.beta, d.c_in[row + j], v);
+    d.c[row + j] = v;
+  }
+}
+
 }  // namespace pc
 
 namespace pc {
@@ -60,6 +110,34 @@ extern "C" int pc_select_preconditioners(const float* src, const float* metrics,
   pc::select_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       src, metrics, threshold, dst, src_cols, (size_t)src_rows * src_cols, rows, cols);
   pc::count_launch(1);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+extern "C" size_t pc_grouped_gemm_splitk_workspace_bytes(int count, int max_m, int max_n,
+                                                        int splits) {
+  if (count <= 0 || max_m <= 0 || max_n <= 0 || splits <= 0) return 0;
+  return (size_t)count * splits * max_m * max_n * sizeof(float) + 256;
+}
+
+extern "C" int pc_grouped_gemm_splitk(const pc_gemm_desc* descs, int count, int max_m, int max_n,
+                                      int splits, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  PC_REQUIRE(count >= 0 && max_m >= 0 && max_n >= 0 && splits >= 1, "bad split-K sizes");
+  if (count == 0 || max_m == 0 || max_n == 0) return PC_OK;
+  PC_REQUIRE(descs && workspace, "null pointer argument");
+  PC_REQUIRE((long long)count * splits <= 65535, "count * splits must be <= 65535");
+  PC_REQUIRE(workspace_bytes >= pc_grouped_gemm_splitk_workspace_bytes(count, max_m, max_n, splits),
+             "split-K workspace too small");
+  float* part = reinterpret_cast<float*>(pc::align_up((size_t)workspace, 256));
+  const int tm = (max_m + pc::kSimtBM - 1) / pc::kSimtBM, tn = (max_n + pc::kSimtBN - 1) / pc::kSimtBN;
+  dim3 grid(tn, tm, count * splits);
+  pc::grouped_gemm_splitk_kernel<<<grid, pc::kSimtThreads, 0, (cudaStream_t)stream>>>(
+      descs, splits, max_m, max_n, part);
+  const int rb = (max_m * max_n + 255) / 256;
+  pc::splitk_reduce_kernel<<<dim3(rb < 64 ? rb : 64, count), 256, 0, (cudaStream_t)stream>>>(
+      descs, splits, max_m, max_n, part);
+  pc::count_launch(2);
   PC_CUDA_CHECK(cudaGetLastError());
   return PC_OK;
 }

@@ -617,9 +617,8 @@ class _Shampoo:
     def split(descs):
       tc = [d for d in descs if use_tc and ops.tc_gemm_eligible(d)]
       simt = [d for d in descs if not (use_tc and ops.tc_gemm_eligible(d))]
-      mx = [max([d.m for d in simt], default=1), max([d.n for d in simt], default=1)]
       return (ops.TcGemmList(tc, self.device) if tc else None,
-              (ops.upload_gemm_descs(simt, self.device), len(simt)) if simt else (None, 0), mx)
+              ops.SimtGemmLists(simt, self.device) if simt else None)
 
     self._stat_count = len(stat_descs)
     self._stat_tc_fused = None
@@ -651,13 +650,12 @@ class _Shampoo:
       if fused:
         self._stat_tc_fused = ops.TcGemmList(fused, self.device, quant=fused_ext)
       stat_descs = rest
-    self._stat_tc, self._stat_descs, self._stat_max = split(stat_descs)
-    self._apply_tc, self._apply_descs, self._apply_max = [], [], []
+    self._stat_tc, self._stat_simt = split(stat_descs)
+    self._apply_tc, self._apply_simt = [], []
     for lst in apply_descs:
-      tc, simt, mx = split(lst)
+      tc, simt = split(lst)
       self._apply_tc.append(tc)
-      self._apply_descs.append(simt)
-      self._apply_max.append(mx)
+      self._apply_simt.append(simt)
 
   def _identity(self, n):
     cache = self.__dict__.setdefault("_eyes", {})
@@ -722,9 +720,8 @@ class _Shampoo:
           continue
         q, d, b = bk.qstats
         ops.dequantize(q, d, b, True, out=bk.stats)
-    dev, count = self._stat_descs
-    if count:
-      ops.grouped_gemm(dev, count, self._stat_max[0], self._stat_max[1])
+    if self._stat_simt is not None:
+      self._stat_simt.run()
     if self._stat_tc is not None:
       self._stat_tc.run()
     if self._stat_tc_fused is not None:
@@ -878,9 +875,9 @@ class _Shampoo:
       for bk in self.buckets.values():
         q, d, b = bk.qprecs
         ops.dequantize(q, d, b, True, out=bk.precs)
-    for j, (dev, count) in enumerate(self._apply_descs):
-      if count:
-        ops.grouped_gemm(dev, count, self._apply_max[j][0], self._apply_max[j][1])
+    for j, simt in enumerate(self._apply_simt):
+      if simt is not None:
+        simt.run()
       if self._apply_tc[j] is not None:
         self._apply_tc[j].run()
 

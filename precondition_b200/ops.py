@@ -310,6 +310,56 @@ def grouped_gemm(descs_dev: torch.Tensor, count: int, max_m: int, max_n: int):
   gpu_launches += 1
 
 
+class SimtGemmLists:
+  """CUDA-core grouped-GEMM launch lists for one phase.  Descriptors are grouped into size
+  classes (tile counts rounded up to powers of two) so that no launch's grid is sized by
+  another class's largest block, and descriptors with a small output but a very long
+  contraction go through the deterministic split-K kernel."""
+
+  SPLITK_MIN_K = 16384
+  SPLITK_MAX_TILES = 4
+
+  def __init__(self, descs: Sequence[_lib.GemmDesc], device):
+    self.device = device
+    self.groups = []   # (device descriptors, count, max_m, max_n)
+    self.splitk = []   # (device descriptors, count, max_m, max_n, splits, workspace)
+    classes, long_k = {}, []
+
+    def tiles(x):
+      t = (x + 63) // 64
+      return 1 << max(t - 1, 0).bit_length()
+
+    for d in descs:
+      if d.k >= self.SPLITK_MIN_K and tiles(d.m) * tiles(d.n) <= self.SPLITK_MAX_TILES:
+        long_k.append(d)
+      else:
+        classes.setdefault((tiles(d.m), tiles(d.n)), []).append(d)
+    for lst in classes.values():
+      self.groups.append((upload_gemm_descs(lst, device), len(lst),
+                          max(d.m for d in lst), max(d.n for d in lst)))
+    if long_k:
+      lib = _lib.load()
+      mm, mn = max(d.m for d in long_k), max(d.n for d in long_k)
+      splits = max(1, min(64, min(d.k for d in long_k) // 2048, 65535 // len(long_k)))
+      nbytes = lib.pc_grouped_gemm_splitk_workspace_bytes(len(long_k), mm, mn, splits)
+      ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+      self.splitk.append((upload_gemm_descs(long_k, device), len(long_k), mm, mn, splits, ws))
+
+  def __bool__(self):
+    return bool(self.groups or self.splitk)
+
+  def run(self):
+    global gpu_launches
+    lib = _lib.load()
+    for dev, count, mm, mn in self.groups:
+      grouped_gemm(dev, count, mm, mn)
+    for dev, count, mm, mn, splits, ws in self.splitk:
+      with torch.cuda.device(self.device):
+        _lib.check(lib.pc_grouped_gemm_splitk(_ptr(dev), count, mm, mn, splits, _ptr(ws),
+                                              ws.numel(), ctypes.c_void_p(_stream())))
+      gpu_launches += 1
+
+
 def tc_gemm_eligible(d: _lib.GemmDesc) -> bool:
   """Descriptor can run on the tcgen05 grouped GEMM (include/precond_b200.h)."""
   return (d.m > 0 and d.n > 0 and d.k > 0 and d.m % 128 == 0 and d.n % 128 == 0 and

