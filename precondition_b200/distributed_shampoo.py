@@ -505,7 +505,6 @@ class _Shampoo:
     preconditioner application (DS:1676-1708), built once."""
     D = _lib.GemmDesc
     stat_descs, stat_meta, apply_descs = [], [], [[], [], []]
-    self._stat_max, self._apply_max = [1, 1], [[1, 1], [1, 1], [1, 1]]
     w1 = float(self.beta2)
     w2 = float(self.beta2 if self.beta2 == 1.0 else 1.0 - self.beta2)  # DS:2635-2636
     f32 = 4
@@ -556,7 +555,6 @@ class _Shampoo:
             d.c_in, d.alpha, d.beta = None, 1.0, 0.0
           stat_descs.append(d)
           stat_meta.append((s, bi))
-          self._stat_max = [max(self._stat_max[0], s), max(self._stat_max[1], s)]
         # ---- application: contract the leading axis and roll (DS:1678-1707) ----
         bnumel = int(np.prod(sizes))
         cur_ptr, cur_strides, cur_sizes = gbase, list(strides), list(sizes)
@@ -604,8 +602,6 @@ class _Shampoo:
             d.c_iinner, d.c_sio, d.c_sii = max(rest, 1), 0, d0
             new_strides = [int(np.prod(new_sizes[i + 1:])) for i in range(rank)]
           apply_descs[j].append(d)
-          self._apply_max[j] = [max(self._apply_max[j][0], rest),
-                                max(self._apply_max[j][1], d0)]
           cur_ptr, cur_sizes, cur_strides = d.c, new_sizes, new_strides
         tmp_off += bnumel
     # Blocks whose GEMM output sizes are multiples of 128 go to the tcgen05 grouped GEMM

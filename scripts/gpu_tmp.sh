@@ -1,2 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_optimizer.py tests/test_gpu_baseline_configs.py -q -x 2>&1 | tail -2
-timeout 600 python scripts/resnet_step_probe.py 2>&1 | grep -v -i warn | grep -E "total|stats|apply|simt|tc_|splitk"
+timeout 600 python bench.py --no-cpu-baseline 2>gpurun_out/b.err | tail -1 | python -c "
+import sys,json
+l=json.loads(sys.stdin.readline()); print('value', round(l['value'],1)); print(l['shampoo_step_resnet50']['ms'], l['shampoo_step']['ms'], l['sketchy_update']['ms'])"
