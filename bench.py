@@ -501,7 +501,7 @@ def resnet50_shapes():
   return shapes
 
 
-def time_resnet50_step(dev, world, steps=2, warm=2):
+def time_resnet50_step(dev, world, steps=3, warm=3):
   """ms per `update` of distributed_shampoo on ResNet-50 shapes, block_size=1024,
   preconditioning_compute_steps=1 (BASELINE config 3); with more than one rank the
   preconditioner blocks are partitioned over the ranks and all-gathered (batch_axis_name)."""

@@ -862,6 +862,24 @@ class _Shampoo:
         r, m = sharded_inverse_pth_roots(padded, bk.exps, world, rank, self.process_group,
                                          pads=pads, **kw)
       return r[:, :1, :1].contiguous(), m
+    s = bk.size
+    if (s >= 256 and s % 128 != 0 and self.engine == _lib.PC_ENGINE_AUTO and
+        bool(_lib.load().pc_device_supports_tcgen05())):
+      # Sizes such as 1000 or 576 are embedded in the next multiple of 128 with
+      # padding_start = size -- exactly the reference's own pad-to-max convention
+      # (DS:2841-2843, masked by DS:777-783) -- so they run on the tcgen05 engine instead
+      # of the CUDA-core one.
+      sp = (s + 127) // 128 * 128
+      if getattr(bk, "padded", None) is None:
+        bk.padded = torch.zeros((bk.count, sp, sp), dtype=torch.float32, device=self.device)
+        bk.pads = torch.full((bk.count,), s, dtype=torch.int32, device=self.device)
+      bk.padded[:, :s, :s].copy_(bk.stats)
+      if world == 1:
+        r, m = ops.matrix_inverse_pth_root_batched(bk.padded, bk.exps, bk.pads, **kw)
+      else:
+        r, m = sharded_inverse_pth_roots(bk.padded, bk.exps, world, rank, self.process_group,
+                                         pads=bk.pads, **kw)
+      return r[:, :s, :s].contiguous(), m
     if world == 1:
       return ops.matrix_inverse_pth_root_batched(bk.stats, bk.exps, None, out=bk.roots_tmp, **kw)
     return sharded_inverse_pth_roots(bk.stats, bk.exps, world, rank, self.process_group, **kw)

@@ -247,3 +247,29 @@ def test_pytree_structure_and_errors():
     DS.distributed_shampoo(0.1, 8, lobpcg_topk_precondition=2)
   with pytest.raises(RuntimeError):
     DS.distributed_shampoo(0.1, 8).init([torch.zeros(4, 4)])  # CPU tensor: no fallback
+
+
+def test_odd_sized_statistics_run_padded_on_tensor_cores():
+  """A 300-wide dimension (not a multiple of 128) is embedded in 384 with padding_start = 300
+  (the reference's own pad-to-max convention, DS:2841-2843) so that it runs on the tcgen05
+  engine; the trajectory must still follow the oracle."""
+  from precondition_b200 import distributed_shampoo as DS
+  rng = np.random.default_rng(12)
+  shapes = [(300, 64)]
+  params = [rng.standard_normal(s).astype(np.float32) * 0.1 for s in shapes]
+  kw = dict(start_preconditioning_step=1, merge_small_dims_block_size=512)
+  oracle = O.distributed_shampoo(0.1, 512, **kw)
+  ostate = oracle.init(params)
+  opt = DS.distributed_shampoo(0.1, 512, **kw)
+  tparams = [torch.as_tensor(p).cuda() for p in params]
+  state = opt.init(tparams)
+  for t in range(4):
+    grads = [(rng.standard_normal(s) * 1e-2).astype(np.float32) for s in shapes]
+    want, ostate = oracle.update(grads, ostate, params)
+    got, state = opt.update([torch.as_tensor(g).cuda() for g in grads], state, tparams)
+    torch.cuda.synchronize()
+    err = np.abs(got[0].cpu().numpy() - want[0]).max() / np.abs(want[0]).max()
+    assert err <= 1e-3, (t, err)
+  for a, b in zip(state.stats[0].preconditioners, ostate.stats[0].preconditioners):
+    rel = np.linalg.norm(a.cpu().numpy() - b) / np.linalg.norm(b)
+    assert rel <= 2e-3, rel
