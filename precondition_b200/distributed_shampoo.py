@@ -667,8 +667,9 @@ class _Shampoo:
     s_leaves = self._flatten_stats(state.stats)
     p_leaves = _tree_flatten(params)[0] if params is not None else [None] * len(g_leaves)
     # (0) stage gradients into the flat buffer the static descriptors point at
-    for plan, g in zip(self.plans, g_leaves):
-      self.gbuf[plan.offset:plan.offset + plan.numel].copy_(g.reshape(-1))
+    if getattr(self, "_gviews", None) is None:
+      self._gviews = [self.gbuf[pl.offset:pl.offset + pl.numel] for pl in self.plans]
+    torch._foreach_copy_(self._gviews, [g.reshape(-1) for g in g_leaves])  # one fused staging pass
     if self.use_avg_grad:  # DS:2640-2645
       k = self.statistics_compute_steps
       if k == 1 or step % k == 1:
@@ -905,7 +906,10 @@ class _Shampoo:
       mom, dmom = st.momentum.to_float(), st.diagonal_momentum.to_float()
     diag = st.diagonal_statistics.quantized if self._graft_has_diag() else None
     update = torch.empty_like(grad, dtype=torch.float32)
-    opt = ops.make_graft_options(
+    key = (step >= self.start_preconditioning_step, lr)
+    if getattr(self, "_graft_opt_key", None) != key:  # the options are the same for every parameter
+      self._graft_opt_key = key
+      self._graft_opt = ops.make_graft_options(
         beta1=float(self.beta1), beta2=float(self.beta2), graft_type=int(self.graft_type),
         diagonal_epsilon=float(self.diagonal_epsilon), weight_decay=float(self.weight_decay),
         learning_rate=lr, nesterov=int(bool(self.nesterov)),
@@ -914,6 +918,7 @@ class _Shampoo:
         decoupled_weight_decay=int(bool(self.decoupled_weight_decay)),
         run_shampoo=int(step >= self.start_preconditioning_step),
         clip_by_scaled_gradient_norm=float(self.clip_by_scaled_gradient_norm or 0.0))
+    opt = self._graft_opt
     if self.weight_decay != 0 and param is None:
       raise ValueError("weight_decay needs params")
     ops.graft_momentum(gflat, None if param is None else param.contiguous().reshape(-1), pg,
