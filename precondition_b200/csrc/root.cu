@@ -561,7 +561,9 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
   // for the iteration it has just enqueued, so the device queue stays non-empty.  The
   // (at most kPollLag) surplus iterations find no active matrix and return at once.
   const int tiles = (n + kSimtBM - 1) / kSimtBM;
-  const int max_total = opt->num_iters * 6 + 8;
+  // 6 tries x num_iters iterations, plus the iterations a retry may idle before the lagged
+  // poll notices it and launches its (re)initialisation
+  const int max_total = opt->num_iters * 6 + 8 + 6 * (kPollLag + 1);
   // (Re)initialisation is launched on the first iteration and afterwards only when a lagged
   // poll reports matrices waiting for a retry (they idle until then; retries are rare).
   bool init_pending = true;
