@@ -85,25 +85,44 @@ __global__ void __launch_bounds__(kGraftThreads) graft_reduce_kernel(GraftArgs a
                      a.o.graft_type == PC_GRAFT_RMSPROP_NORMALIZED);
   if (STAGE == 2 && clip) cdenom = clip_denom_of(a, total_of(a.part_r, a.nblocks, scratch));
   float s0 = 0.f, s1 = 0.f;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.numel;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const float g = a.grad[e];
+  auto accumulate = [&](float g, float diag_e, float pg_e) {
     if (STAGE == 0) {
       s0 = fmaf(g, g, s0);
     } else {
       float nd;
-      float r = graft_raw(a, g, gdenom, a.diag ? a.diag[e] : 0.f, &nd);
+      float r = graft_raw(a, g, gdenom, diag_e, &nd);
       if (STAGE == 1) {
         s0 = fmaf(r, r, s0);
       } else {
         if (clip) r = r / cdenom;
         r = r * a.lr_mult;
         s0 = fmaf(r, r, s0);
-        const float pg = a.precond ? a.precond[e] : r;
+        const float pg = a.precond ? pg_e : r;
         s1 = fmaf(pg, pg, s1);
       }
     }
+  };
+  // 16-byte loads when every stream is aligned (the optimizer's flat buffers are): a reduction
+  // pass moves 8 B / element and has to stay on the HBM roofline
+  const bool vec = ((reinterpret_cast<uintptr_t>(a.grad) |
+                     reinterpret_cast<uintptr_t>(a.precond ? a.precond : a.grad) |
+                     reinterpret_cast<uintptr_t>(a.diag ? a.diag : a.grad)) & 15) == 0;
+  const int64_t n4 = vec ? a.numel >> 2 : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(a.grad)[i];
+    float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f), p4 = d4;
+    if (STAGE >= 1 && a.diag) d4 = reinterpret_cast<const float4*>(a.diag)[i];
+    if (STAGE == 2 && a.precond) p4 = reinterpret_cast<const float4*>(a.precond)[i];
+    accumulate(g4.x, d4.x, p4.x);
+    accumulate(g4.y, d4.y, p4.y);
+    accumulate(g4.z, d4.z, p4.z);
+    accumulate(g4.w, d4.w, p4.w);
   }
+  for (int64_t e = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.numel;
+       e += (int64_t)gridDim.x * blockDim.x)
+    accumulate(a.grad[e], (STAGE >= 1 && a.diag) ? a.diag[e] : 0.f,
+               (STAGE == 2 && a.precond) ? a.precond[e] : 0.f);
   s0 = block_sum(s0, scratch);
   if (STAGE == 2) s1 = block_sum(s1, scratch);
   if (threadIdx.x == 0) {
