@@ -467,17 +467,21 @@ def time_shampoo_step(dev, steps=10, warm=6):
   state = opt.init(params)
   grads = [[torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes]
            for _ in range(warm + steps)]
-  for t in range(warm):
-    _, state = opt.update(grads[t], state, params)
+  for t in range(warm):  # same name as in the timed loop: the caching allocator reaches its steady
+    upd, state = opt.update(grads[t], state, params)  # state (two update sets alive) before timing
   torch.cuda.synchronize()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  e0.record()
+  # one event pair per step: "ms" is the mean over the steps, the per-step list is kept so a
+  # one-off stall (allocator, host scheduling) is visible instead of silently folded in
+  evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+  evs[0].record()
   for t in range(warm, warm + steps):
     upd, state = opt.update(grads[t], state, params)
-  e1.record()
+    evs[t - warm + 1].record()
   torch.cuda.synchronize()
+  per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
   tm = torch.cat([st.training_metrics for st in state.stats if st.training_metrics is not None])
-  return {"ms": e0.elapsed_time(e1) / steps, "unit": "ms/step", "steps": steps,
+  return {"ms": sum(per_step) / steps, "ms_per_step_list": [round(x, 3) for x in per_step],
+          "unit": "ms/step", "steps": steps,
           "config": "MLP 512->2048->512, block_size=128, SGD grafting, preconditioning_compute_steps=1",
           "statistics": int(tm.shape[0]), "newton_iters_mean": float(tm[:, 1].mean()),
           "max_root_error": float(tm[:, 0].max()),
@@ -516,21 +520,25 @@ def time_resnet50_step(dev, world, steps=3, warm=3):
   state = opt.init(params)
   grads = [[torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes]
            for _ in range(warm + steps)]
-  for t in range(warm):
-    _, state = opt.update(grads[t], state, params)
+  for t in range(warm):  # same name as in the timed loop: the caching allocator reaches its steady
+    upd, state = opt.update(grads[t], state, params)  # state (two update sets alive) before timing
   torch.cuda.synchronize()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  e0.record()
+  # one event pair per step: "ms" is the mean over the steps, the per-step list is kept so a
+  # one-off stall (allocator, host scheduling) is visible instead of silently folded in
+  evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+  evs[0].record()
   for t in range(warm, warm + steps):
     upd, state = opt.update(grads[t], state, params)
-  e1.record()
+    evs[t - warm + 1].record()
   torch.cuda.synchronize()
+  per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
   tm = torch.cat([st.training_metrics for st in state.stats if st.training_metrics is not None])
   sizes = {}
   for st in state.stats:
     for x in st.statistics:
       sizes[int(x.shape[0])] = sizes.get(int(x.shape[0]), 0) + 1
-  return {"ms": e0.elapsed_time(e1) / steps, "unit": "ms/step", "steps": steps, "n_gpus": world,
+  return {"ms": sum(per_step) / steps, "ms_per_step_list": [round(x, 3) for x in per_step],
+          "unit": "ms/step", "steps": steps, "n_gpus": world,
           "config": "ResNet-50 shapes, block_size=1024, preconditioning_compute_steps=1, "
                     "blocks sharded over the ranks" if world > 1 else
                     "ResNet-50 shapes, block_size=1024, preconditioning_compute_steps=1",
