@@ -6,6 +6,8 @@
 // (+ one extra read of grad and precond_grad for the norm pass).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace pc {
 
 constexpr int kGraftThreads = 256;
@@ -74,23 +76,18 @@ __device__ __forceinline__ float clip_denom_of(const GraftArgs& a, float sum_raw
   return fmaxf(1.f, norm / a.o.clip_by_scaled_gradient_norm);
 }
 
-template <int STAGE>  // 0: sum grad^2; 1: sum raw^2; 2: sum graft^2 and precond^2
-__global__ void __launch_bounds__(kGraftThreads) graft_reduce_kernel(GraftArgs a) {
-  __shared__ float scratch[32];
-  float gdenom = 1.f, cdenom = 1.f;
-  if (STAGE >= 1 && is_normalized(a.o.graft_type))
-    gdenom = sqrtf(total_of(a.part_g, a.nblocks, scratch)) + 1e-25f;
-  const bool clip = a.o.clip_by_scaled_gradient_norm > 0.f &&
-                    (a.o.graft_type == PC_GRAFT_RMSPROP ||
-                     a.o.graft_type == PC_GRAFT_RMSPROP_NORMALIZED);
-  if (STAGE == 2 && clip) cdenom = clip_denom_of(a, total_of(a.part_r, a.nblocks, scratch));
-  float s0 = 0.f, s1 = 0.f;
+// Streaming part of a reduction pass.  IDENTITY = the graft is the gradient itself (SGD, NONE): the
+// graft-type dispatch stays out of the loop, which otherwise costs ~44 instructions per element and
+// makes the pass issue-bound (ncu: 62 % SM throughput at 4.0 TB/s).
+template <int STAGE, bool IDENTITY>
+__device__ __forceinline__ void graft_reduce_stream(const GraftArgs& a, float gdenom, float cdenom,
+                                                    bool clip, float& s0, float& s1) {
   auto accumulate = [&](float g, float diag_e, float pg_e) {
     if (STAGE == 0) {
       s0 = fmaf(g, g, s0);
     } else {
       float nd;
-      float r = graft_raw(a, g, gdenom, diag_e, &nd);
+      float r = IDENTITY ? g : graft_raw(a, g, gdenom, diag_e, &nd);
       if (STAGE == 1) {
         s0 = fmaf(r, r, s0);
       } else {
@@ -102,6 +99,8 @@ __global__ void __launch_bounds__(kGraftThreads) graft_reduce_kernel(GraftArgs a
       }
     }
   };
+  const bool diag = !IDENTITY && STAGE >= 1 && a.diag;
+  const bool prec = STAGE == 2 && a.precond;
   // 16-byte loads when every stream is aligned (the optimizer's flat buffers are): a reduction
   // pass moves 8 B / element and has to stay on the HBM roofline
   const bool vec = ((reinterpret_cast<uintptr_t>(a.grad) |
@@ -112,8 +111,8 @@ __global__ void __launch_bounds__(kGraftThreads) graft_reduce_kernel(GraftArgs a
        i += (int64_t)gridDim.x * blockDim.x) {
     const float4 g4 = reinterpret_cast<const float4*>(a.grad)[i];
     float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f), p4 = d4;
-    if (STAGE >= 1 && a.diag) d4 = reinterpret_cast<const float4*>(a.diag)[i];
-    if (STAGE == 2 && a.precond) p4 = reinterpret_cast<const float4*>(a.precond)[i];
+    if (diag) d4 = reinterpret_cast<const float4*>(a.diag)[i];
+    if (prec) p4 = reinterpret_cast<const float4*>(a.precond)[i];
     accumulate(g4.x, d4.x, p4.x);
     accumulate(g4.y, d4.y, p4.y);
     accumulate(g4.z, d4.z, p4.z);
@@ -121,8 +120,24 @@ __global__ void __launch_bounds__(kGraftThreads) graft_reduce_kernel(GraftArgs a
   }
   for (int64_t e = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.numel;
        e += (int64_t)gridDim.x * blockDim.x)
-    accumulate(a.grad[e], (STAGE >= 1 && a.diag) ? a.diag[e] : 0.f,
-               (STAGE == 2 && a.precond) ? a.precond[e] : 0.f);
+    accumulate(a.grad[e], diag ? a.diag[e] : 0.f, prec ? a.precond[e] : 0.f);
+}
+
+template <int STAGE>  // 0: sum grad^2; 1: sum raw^2; 2: sum graft^2 and precond^2
+__global__ void __launch_bounds__(kGraftThreads) graft_reduce_kernel(GraftArgs a) {
+  __shared__ float scratch[32];
+  float gdenom = 1.f, cdenom = 1.f;
+  if (STAGE >= 1 && is_normalized(a.o.graft_type))
+    gdenom = sqrtf(total_of(a.part_g, a.nblocks, scratch)) + 1e-25f;
+  const bool clip = a.o.clip_by_scaled_gradient_norm > 0.f &&
+                    (a.o.graft_type == PC_GRAFT_RMSPROP ||
+                     a.o.graft_type == PC_GRAFT_RMSPROP_NORMALIZED);
+  if (STAGE == 2 && clip) cdenom = clip_denom_of(a, total_of(a.part_r, a.nblocks, scratch));
+  float s0 = 0.f, s1 = 0.f;
+  if (a.o.graft_type == PC_GRAFT_SGD || a.o.graft_type == PC_GRAFT_NONE)
+    graft_reduce_stream<STAGE, true>(a, gdenom, cdenom, clip, s0, s1);
+  else
+    graft_reduce_stream<STAGE, false>(a, gdenom, cdenom, clip, s0, s1);
   s0 = block_sum(s0, scratch);
   if (STAGE == 2) s1 = block_sum(s1, scratch);
   if (threadIdx.x == 0) {
@@ -248,8 +263,21 @@ int pc_graft_momentum(const float* grad, const float* param, const float* precon
   float* w = reinterpret_cast<float*>(pc::align_up((size_t)workspace, 256));
   a.part_g = w; a.part_r = w + pc::kGraftMaxBlocks; a.part_gr = w + 2 * pc::kGraftMaxBlocks;
   a.part_p = w + 3 * pc::kGraftMaxBlocks;
+  // one full wave at most: the grid never exceeds what is resident at once (ncu: 42 registers ->
+  // 5 CTAs per SM; the former 8 per SM ran as 1.6 waves with a 60 %-filled tail)
+  static const int resident = [] {
+    int dev = 0, sms = 148, occ_r = 1, occ_a = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, pc::graft_reduce_kernel<2>,
+                                                  pc::kGraftThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, pc::graft_apply_kernel,
+                                                  pc::kGraftThreads, 0);
+    const int r = sms * std::max(1, std::min(occ_r, occ_a));
+    return r < pc::kGraftMaxBlocks ? r : pc::kGraftMaxBlocks;
+  }();
   int64_t want = (numel + pc::kGraftThreads * 4 - 1) / (pc::kGraftThreads * 4);
-  a.nblocks = (int)(want < 1 ? 1 : (want > pc::kGraftMaxBlocks ? pc::kGraftMaxBlocks : want));
+  a.nblocks = (int)(want < 1 ? 1 : (want > resident ? resident : want));
   cudaStream_t st = (cudaStream_t)stream;
   const bool normalized = opt->graft_type == PC_GRAFT_ADAGRAD_NORMALIZED ||
                           opt->graft_type == PC_GRAFT_RMSPROP_NORMALIZED;
