@@ -50,9 +50,9 @@ __device__ float total_of(const float* part, int n, float* scratch) {
 }
 
 // raw grafting update before clipping / lr multiplier (DS:3502-3543)
-__device__ __forceinline__ float graft_raw(const GraftArgs& a, float g, float gdenom,
+// t = the graft type; a compile-time constant at the call site folds the dispatch away
+__device__ __forceinline__ float graft_raw(const GraftArgs& a, const int t, float g, float gdenom,
                                            float diag_old, float* diag_new) {
-  const int t = a.o.graft_type;
   float sg = g;
   if (is_normalized(t)) sg = g / gdenom;
   if (t == PC_GRAFT_ADAGRAD || t == PC_GRAFT_ADAGRAD_NORMALIZED) {
@@ -76,10 +76,10 @@ __device__ __forceinline__ float clip_denom_of(const GraftArgs& a, float sum_raw
   return fmaxf(1.f, norm / a.o.clip_by_scaled_gradient_norm);
 }
 
-// Streaming part of a reduction pass.  IDENTITY = the graft is the gradient itself (SGD, NONE): the
-// graft-type dispatch stays out of the loop, which otherwise costs ~44 instructions per element and
-// makes the pass issue-bound (ncu: 62 % SM throughput at 4.0 TB/s).
-template <int STAGE, bool IDENTITY>
+// Streaming part of a reduction pass, one instance per graft type T: the graft-type dispatch stays
+// out of the loop, which otherwise costs ~44 instructions per element and makes the pass
+// issue-bound (ncu: 62 % SM throughput at 4.0 TB/s).
+template <int STAGE, int T>
 __device__ __forceinline__ void graft_reduce_stream(const GraftArgs& a, float gdenom, float cdenom,
                                                     bool clip, float& s0, float& s1) {
   auto accumulate = [&](float g, float diag_e, float pg_e) {
@@ -87,7 +87,7 @@ __device__ __forceinline__ void graft_reduce_stream(const GraftArgs& a, float gd
       s0 = fmaf(g, g, s0);
     } else {
       float nd;
-      float r = IDENTITY ? g : graft_raw(a, g, gdenom, diag_e, &nd);
+      float r = graft_raw(a, T, g, gdenom, diag_e, &nd);
       if (STAGE == 1) {
         s0 = fmaf(r, r, s0);
       } else {
@@ -99,7 +99,7 @@ __device__ __forceinline__ void graft_reduce_stream(const GraftArgs& a, float gd
       }
     }
   };
-  const bool diag = !IDENTITY && STAGE >= 1 && a.diag;
+  const bool diag = has_diag(T) && STAGE >= 1 && a.diag;
   const bool prec = STAGE == 2 && a.precond;
   // 16-byte loads when every stream is aligned (the optimizer's flat buffers are): a reduction
   // pass moves 8 B / element and has to stay on the HBM roofline
@@ -134,10 +134,18 @@ __global__ void __launch_bounds__(kGraftThreads) graft_reduce_kernel(GraftArgs a
                      a.o.graft_type == PC_GRAFT_RMSPROP_NORMALIZED);
   if (STAGE == 2 && clip) cdenom = clip_denom_of(a, total_of(a.part_r, a.nblocks, scratch));
   float s0 = 0.f, s1 = 0.f;
-  if (a.o.graft_type == PC_GRAFT_SGD || a.o.graft_type == PC_GRAFT_NONE)
-    graft_reduce_stream<STAGE, true>(a, gdenom, cdenom, clip, s0, s1);
-  else
-    graft_reduce_stream<STAGE, false>(a, gdenom, cdenom, clip, s0, s1);
+  switch (a.o.graft_type) {
+#define PC_GRAFT_CASE(T) \
+  case T: graft_reduce_stream<STAGE, T>(a, gdenom, cdenom, clip, s0, s1); break;
+    PC_GRAFT_CASE(PC_GRAFT_NONE)
+    PC_GRAFT_CASE(PC_GRAFT_SGD)
+    PC_GRAFT_CASE(PC_GRAFT_ADAGRAD)
+    PC_GRAFT_CASE(PC_GRAFT_RMSPROP)
+    PC_GRAFT_CASE(PC_GRAFT_RMSPROP_NORMALIZED)
+    PC_GRAFT_CASE(PC_GRAFT_SQRT_N)
+    PC_GRAFT_CASE(PC_GRAFT_ADAGRAD_NORMALIZED)
+#undef PC_GRAFT_CASE
+  }
   s0 = block_sum(s0, scratch);
   if (STAGE == 2) s1 = block_sum(s1, scratch);
   if (threadIdx.x == 0) {
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(kGraftThreads) graft_apply_kernel(GraftArgs a)
   // one element of the tail; state values come in by reference and leave updated
   auto element = [&](float g, float prm, float pg_e, float& diag_e, float& dmom_e, float& mom_e) {
     float nd;
-    float graft = graft_raw(a, g, gdenom, diag_e, &nd);
+    float graft = graft_raw(a, a.o.graft_type, g, gdenom, diag_e, &nd);
     if (clip) graft = graft / cdenom;
     graft = graft * a.lr_mult;
     const float pg = a.precond ? pg_e : graft;
