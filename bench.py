@@ -47,11 +47,31 @@ def parse_args():
                   help="matrices in the bounded CPU-baseline sample")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-step", action="store_true", help="skip the Shampoo-step measurement")
+  ap.add_argument("--no-big", action="store_true",
+                  help="skip the BERT-large (config 4) and Sketchy-step (config 5) measurements")
+  ap.add_argument("--split", type=int, default=0,
+                  help="sub-batches per step (0 = auto: 2 with several GPUs so that the all-gather of "
+                       "the first half overlaps the solve of the second, else 1)")
   return ap.parse_args()
 
 
 def workload_name(a):
   return f"ema_lowrank_statistics_{a.n}x{a.n}_p{a.p}_batch{a.batch}_per_gpu"
+
+
+def workload_config(a, world):
+  """`config` of the JSON line -- identical keys and values in both arms (`--impl ours` /
+  `--impl reference`); run-specific facts (engine, iteration counts, ...) go to `run_info`."""
+  return {"workload": workload_name(a), "n": a.n, "p": a.p, "batch_per_gpu": a.batch,
+          "statistics_class": "S0=1e-6 I; 20 EMA steps of rank n/32 Gram updates (cond ~1e6)",
+          "l2": "inputs_exceed_l2" if a.batch * a.n * a.n * 4 > 126e6 else "inputs_fit_l2",
+          "sharding": (f"blocks partitioned over {world} ranks + all_gather" if world > 1
+                       else "single gpu")}
+
+
+def newton_gemms(p):
+  """G(p), SURVEY 8(d)."""
+  return (int(p).bit_length() - 1) + bin(int(p)).count("1") - 1 + 2
 
 
 def make_statistics_torch(batch, n, seed, device):
@@ -194,22 +214,54 @@ def cpu_threads():
     return os.cpu_count() or 1
 
 
-def time_cpu_port(a, sample, reps=1):
+def time_cpu_port(a, sample, reps=1, xs=None):
   """Times the oracle's matrix_inverse_pth_root (reference algorithm incl. its
-  redundant mat_power products, DS:655-678) on `sample` matrices; roots/s."""
+  redundant mat_power products, DS:655-678) on `sample` matrices; roots/s.
+  `xs`: the matrices to use (default: the numpy generator of the same statistics class)."""
   from oracle import numerics as N
-  xs = make_statistics_numpy(sample, a.n, seed=1234)
+  if xs is None:
+    xs = make_statistics_numpy(sample, a.n, seed=1234)
   N.matrix_inverse_pth_root(xs[0][:64, :64].copy(), a.p)  # warm BLAS
   best = None
-  iters = []
+  iters, roots = [], []
   for _ in range(reps):
+    iters, roots = [], []
     t0 = time.perf_counter()
     for b in range(sample):
-      _, m = N.matrix_inverse_pth_root(xs[b], a.p, literal_mat_power=True)
+      r, m = N.matrix_inverse_pth_root(xs[b], a.p, literal_mat_power=True)
       iters.append(m.inverse_pth_root_iters)
+      roots.append((r, m))
     dt = time.perf_counter() - t0
     best = dt if best is None else min(best, dt)
+  time_cpu_port.last_roots = roots
   return sample / best, best, iters
+
+
+def parity_report(xs_dev, roots_dev, metrics_dev, oracle_roots, p):
+  """Achieved parity of sampled bench matrices against the oracle (fp32 restatement of the
+  reference): relative Frobenius distance of the roots, float64 residual max|X^p (A + eps I) - I|
+  of both (torch float64 on the device as the checker), iteration counts."""
+  import torch
+  out = []
+  for i, (want, wm) in enumerate(oracle_roots):
+    a = xs_dev[i].double()
+    n = a.shape[0]
+    eye = torch.eye(n, dtype=torch.float64, device=a.device)
+    d = a + 1e-6 * float(wm.max_eigen_value) * eye
+    res = []
+    for x in (roots_dev[i].double(), torch.as_tensor(want, device=a.device).double()):
+      res.append(float((torch.linalg.matrix_power(x, p) @ d - eye).abs().max()))
+    got = roots_dev[i].cpu().numpy()
+    out.append({"rel_frobenius_vs_oracle": float(np.linalg.norm(got - want) / np.linalg.norm(want)),
+                "residual_f64_ours": res[0], "residual_f64_oracle": res[1],
+                "iters_ours": float(metrics_dev[i, 1]), "iters_oracle": float(wm.inverse_pth_root_iters),
+                "error_ours": float(metrics_dev[i, 0]), "error_oracle": float(wm.inverse_pth_root_errors)})
+  return {"samples": out,
+          "max_rel_frobenius_vs_oracle": max(o["rel_frobenius_vs_oracle"] for o in out),
+          "residual_no_worse_than_oracle": all(
+              o["residual_f64_ours"] <= 2 * o["residual_f64_oracle"] + 1e-6 for o in out),
+          "tolerance": "kappa ~1e6 class (SURVEY 8(c)): two fp32 solvers differ by ~ their float64 "
+                       "residuals; tests assert rel <= 4 max(residuals) + 1e-3, iterations +-1"}
 
 
 def run_reference(a):
@@ -237,8 +289,9 @@ def run_reference(a):
       "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
       "data": "synthetic",
-      "config": {"workload": workload_name(a), "n": a.n, "p": a.p,
-                 "note": "reference algorithm on host cores; bounded sample per step"},
+      "config": workload_config(a, a.gpus),
+      "run_info": {"note": "reference algorithm on host cores; bounded sample of "
+                           f"{a.cpu_sample} statistics of the workload per step"},
       "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                        "sample": sample},
       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -272,14 +325,41 @@ def run_ours(a):
   n, B = a.n, a.batch
   xs = make_statistics_torch(B, n, seed=1000 + rank, device=dev)
   ps = torch.full((B,), a.p, dtype=torch.int32, device=dev)
+  ps_host = np.full((B,), a.p, dtype=np.int32)
   roots = torch.empty_like(xs)
-  gathered = torch.empty((world * B, n, n), dtype=torch.float32, device=dev) if world > 1 else None
+  metrics_buf = torch.empty((B, 5), dtype=torch.float32, device=dev)
+  # Sub-batches: with several ranks the all-gather of the first half (DS:2876) runs on its own
+  # stream underneath the solve of the second half; the solver call only enqueues.
+  nsplit = a.split if a.split > 0 else (2 if world > 1 else 1)
+  nsplit = max(1, min(nsplit, B))
+  bounds = [round(i * B / nsplit) for i in range(nsplit + 1)]
+  parts = [(bounds[i], bounds[i + 1]) for i in range(nsplit) if bounds[i + 1] > bounds[i]]
+  ws_parts = [torch.empty(ops.root_workspace_bytes(hi - lo, n, engine) + 256, dtype=torch.uint8,
+                          device=dev) for lo, hi in parts]
+  gathered = ([torch.empty((world * (hi - lo), n, n), dtype=torch.float32, device=dev)
+               for lo, hi in parts] if world > 1 else None)
+  comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+  gather_note = (f"{len(parts)} sub-batches; all-gather of sub-batch k on a side stream under the "
+                 f"solve of k+1" if world > 1 else "n/a (single gpu)")
+
+  def solve(x_in, out):
+    cur = torch.cuda.current_stream(dev)
+    for k, (lo, hi) in enumerate(parts):
+      ops.matrix_inverse_pth_root_batched(x_in[lo:hi], ps[lo:hi], None, engine=engine,
+                                          out=out[lo:hi], metrics_out=metrics_buf[lo:hi],
+                                          workspace=ws_parts[k], ps_host=ps_host[lo:hi])
+      if world > 1:
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(comm_stream):
+          comm_stream.wait_event(ev)
+          dist.all_gather_into_tensor(gathered[k], out[lo:hi])  # DS:2876
+    if world > 1:
+      cur.wait_stream(comm_stream)
+    return out, metrics_buf
 
   def step():
-    r, m = ops.matrix_inverse_pth_root_batched(xs, ps, None, engine=engine, out=roots)
-    if world > 1:
-      dist.all_gather_into_tensor(gathered, r)  # DS:2876
-    return m
+    return solve(xs, roots)[1]
 
   def barrier():
     if world > 1:
@@ -302,7 +382,12 @@ def run_ours(a):
   e1.record()
   barrier()
   lib.pc_stats_get(ctypes.byref(stats))
-  launches = int(stats.kernel_launches) + (a.steps if world > 1 else 0)
+  launches = int(stats.kernel_launches) + (a.steps * len(parts) if world > 1 else 0)
+  if lib.pc_root_mode():
+    # graph mode: the library counts the graph's kernel nodes once per launch; the WHILE body
+    # (re-init, G(p)-1 GEMM phases, control) repeats once per Newton iteration on the device
+    body = 2 + (newton_gemms(a.p) - 1)
+    launches += int(a.steps * len(parts) * body * max(float(metrics.cpu()[:, 1].max()) - 1, 0))
   ms = e0.elapsed_time(e1)
   t = torch.tensor([ms], dtype=torch.float64, device=dev)
   if world > 1:
@@ -347,10 +432,7 @@ def run_ours(a):
         upload(i + 1)
       cur.wait_event(ev_in[k])
       cur.wait_event(ev_out[k])  # the previous download of this output slot is done
-      r, m = ops.matrix_inverse_pth_root_batched(dev_ins[k], ps, None, engine=engine,
-                                                 out=dev_outs[k])
-      if world > 1:
-        dist.all_gather_into_tensor(gathered, r)
+      r, m = solve(dev_ins[k], dev_outs[k])
       ev_solved[k].record(cur)
       with torch.cuda.stream(s_d2h):
         s_d2h.wait_event(ev_solved[k])
@@ -402,6 +484,8 @@ def run_ours(a):
   resolved = {1: "simt_fp32", 2: "tcgen05_bf16x6", 3: "tcgen05_bf16x3", 4: "tcgen05_fp16x3"}[
       lib.pc_resolve_engine(n, engine)]
   passes = {"simt_fp32": 1, "tcgen05_bf16x6": 6, "tcgen05_bf16x3": 3, "tcgen05_fp16x3": 3}[resolved]
+  t_ = n // 128
+  tile_frac = (t_ * (t_ + 1) / 2) / (t_ * t_) if (resolved != "simt_fp32" and t_ > 0) else 1.0
   roofline = {
       "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
       "frac": achieved / peak if peak else None, "traffic": traffic,
@@ -410,44 +494,67 @@ def run_ours(a):
       "kernel": "newton_chain_gemm", "engine": resolved,
       "algorithmic_flops_per_step": stats.gemm_flops, "gemm_ms_per_step": stats.gemm_ms,
       "gemm_share_of_step": stats.gemm_ms / ms_per_step if ms_per_step else None,
-      "issued_passes": passes, "issued_tflops": achieved * passes, "peak_source": peak_src,
+      "issued_passes": passes,
+      # MMAs actually issued: `passes` products per k-step on the lower-triangular tiles only
+      "issued_tile_fraction": tile_frac, "issued_tflops": achieved * passes * tile_frac,
+      "peak_source": peak_src,
+      "peak_burst": float(peaks.get("bf16_tflops", 0.0)) or None,
+      "frac_of_burst": (achieved / float(peaks["bf16_tflops"])) if peaks.get("bf16_tflops") else None,
+      "ceiling_frac": (1.0 / (passes * tile_frac)) if passes else None,
   }
 
   # ---- second half of the headline metric: full Shampoo step on BASELINE config 2
   #      (MLP 512->2048->512, block_size 128, SGD grafting, 1 GPU), through the
   #      optax-style API; steps >= 5 so the preconditioned path is active ----
-  shampoo_step, sketchy, resnet_step = None, None, None
-  if not a.no_step:
-    resnet_step = time_resnet50_step(dev, world)  # every rank takes part (sharded roots)
-    t = torch.tensor([resnet_step["ms"]], dtype=torch.float64, device=dev)
+  shampoo_step, sketchy, resnet_step, bert_step, sketchy_step = None, None, None, None, None
+
+  def max_over_ranks(x):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
     if world > 1:
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    resnet_step["ms"] = float(t.item())
+    return float(t.item())
+
+  if not a.no_step:
+    resnet_step = time_resnet50_step(dev, world)  # every rank takes part (sharded roots)
+    resnet_step["ms"] = max_over_ranks(resnet_step["ms"])
+    if "sharded_vs_single_max_rel" in resnet_step:
+      resnet_step["sharded_vs_single_max_rel"] = max_over_ranks(
+          resnet_step["sharded_vs_single_max_rel"])
+    if not a.no_big:
+      bert_step = time_bert_large_step(dev, world)      # BASELINE config 4
+      bert_step["ms"] = max_over_ranks(bert_step["ms"])
+      sketchy_step = time_sketchy_step(dev, world)      # BASELINE config 5
+      sketchy_step["ms"] = max_over_ranks(sketchy_step["ms"])
   if world == 1 and not a.no_step:
     shampoo_step = time_shampoo_step(dev)
     sketchy = time_sketchy_update(dev)
 
   if rank == 0:
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if not a.no_cpu_baseline and world == 1:
-      rps, dt, iters = time_cpu_port(a, a.cpu_sample)
+      k = min(a.cpu_sample, B)
+      rps, dt, iters = time_cpu_port(a, k, xs=xs[:k].cpu().numpy())
       cpu_baseline = {"value": rps, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                      "sample": f"{a.cpu_sample} of the {B} statistics' class "
+                      "sample": f"the first {k} of this run's {B} statistics "
                                 f"({dt:.2f} s; numpy/BLAS oracle port, JAX unavailable)",
                       "iters": iters}
+      step()
+      torch.cuda.synchronize()
+      parity = parity_report(xs, roots, metrics_buf, time_cpu_port.last_roots, a.p)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "n": n, "p": a.p, "batch_per_gpu": B,
-                   "engine": resolved, "l2": "inputs_exceed_l2" if B * n * n * 4 > 126e6 else
-                   "inputs_fit_l2", "sharding": f"blocks partitioned over {world} ranks + all_gather"
-                   if world > 1 else "single gpu",
-                   "newton_iters_mean": float(m_host[:, 1].mean()),
-                   "max_error": float(np.nanmax(m_host[:, 0]))},
+        "config": workload_config(a, world),
+        "run_info": {"engine": resolved, "newton_iters_mean": float(m_host[:, 1].mean()),
+                     "max_error": float(np.nanmax(m_host[:, 0])),
+                     "root_mode": "cuda_graph_device_loop" if lib.pc_root_mode() else "host_polled",
+                     "gather_overlap": gather_note},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches // 1,
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "shampoo_step": shampoo_step,
-        "sketchy_update": sketchy, "shampoo_step_resnet50": resnet_step,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+        "shampoo_step": shampoo_step, "sketchy_update": sketchy,
+        "shampoo_step_resnet50": resnet_step, "shampoo_step_bert_large": bert_step,
+        "sketchy_step": sketchy_step,
     }
     print(json.dumps(line), flush=True)
   if world > 1:
@@ -505,10 +612,40 @@ def resnet50_shapes():
   return shapes
 
 
+def _timed_updates(opt, state, params, grads, warm, steps):
+  """Runs warm + steps updates; returns (per-step ms list, last updates, state)."""
+  import torch
+  upd = None
+  for t in range(warm):  # same statement as the timed loop: the caching allocator reaches its
+    upd, state = opt.update(grads[t], state, params)  # steady state before timing
+  torch.cuda.synchronize()
+  # one event pair per step: "ms" is the mean over the steps, the per-step list is kept so a
+  # one-off stall (allocator, host scheduling) is visible instead of silently folded in
+  evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+  evs[0].record()
+  for t in range(warm, warm + steps):
+    upd, state = opt.update(grads[t], state, params)
+    evs[t - warm + 1].record()
+  torch.cuda.synchronize()
+  return [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)], upd, state
+
+
+def _stat_sizes(state_stats):
+  sizes = {}
+  for st in state_stats:
+    for x in st.statistics:
+      k = int(x.shape[0])
+      sizes[k] = sizes.get(k, 0) + 1
+  return sizes
+
+
 def time_resnet50_step(dev, world, steps=3, warm=3):
   """ms per `update` of distributed_shampoo on ResNet-50 shapes, block_size=1024,
   preconditioning_compute_steps=1 (BASELINE config 3); with more than one rank the
-  preconditioner blocks are partitioned over the ranks and all-gathered (batch_axis_name)."""
+  preconditioner blocks are partitioned over the ranks and all-gathered (batch_axis_name),
+  and the same steps are repeated UNSHARDED on this rank to report
+  `sharded_vs_single_max_rel` (max over parameters of max|u_sharded - u_single| / max|u_single|
+  after the last step, and the same for every preconditioner)."""
   import torch
   from precondition_b200 import distributed_shampoo as DS
   gen = torch.Generator(device=dev)
@@ -520,31 +657,121 @@ def time_resnet50_step(dev, world, steps=3, warm=3):
   state = opt.init(params)
   grads = [[torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes]
            for _ in range(warm + steps)]
-  for t in range(warm):  # same name as in the timed loop: the caching allocator reaches its steady
-    upd, state = opt.update(grads[t], state, params)  # state (two update sets alive) before timing
-  torch.cuda.synchronize()
-  # one event pair per step: "ms" is the mean over the steps, the per-step list is kept so a
-  # one-off stall (allocator, host scheduling) is visible instead of silently folded in
-  evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-  evs[0].record()
-  for t in range(warm, warm + steps):
-    upd, state = opt.update(grads[t], state, params)
-    evs[t - warm + 1].record()
-  torch.cuda.synchronize()
-  per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+  per_step, upd, state = _timed_updates(opt, state, params, grads, warm, steps)
   tm = torch.cat([st.training_metrics for st in state.stats if st.training_metrics is not None])
-  sizes = {}
-  for st in state.stats:
-    for x in st.statistics:
-      sizes[int(x.shape[0])] = sizes.get(int(x.shape[0]), 0) + 1
+  sizes = _stat_sizes(state.stats)
+  out = {"ms": sum(per_step) / steps, "ms_per_step_list": [round(x, 3) for x in per_step],
+         "unit": "ms/step", "steps": steps, "n_gpus": world,
+         "config": "ResNet-50 shapes, block_size=1024, preconditioning_compute_steps=1, "
+                   "blocks sharded over the ranks" if world > 1 else
+                   "ResNet-50 shapes, block_size=1024, preconditioning_compute_steps=1",
+         "parameters": int(sum(p.numel() for p in params)), "statistics": int(tm.shape[0]),
+         "statistics_of_1024": sizes.get(1024, 0),
+         "max_root_error": float(tm[:, 0].max()),
+         "update_finite": bool(all(torch.isfinite(u).all() for u in upd))}
+  if world > 1:
+    single = DS.distributed_shampoo(0.1, 1024, preconditioning_compute_steps=1)
+    sstate = single.init(params)
+    _, supd, sstate = _timed_updates(single, sstate, params, grads, warm, steps)
+    rel = 0.0
+    for u, v in zip(upd, supd):
+      rel = max(rel, float((u - v).abs().max() / v.abs().max().clamp_min(1e-30)))
+    prel = 0.0
+    for a_, b_ in zip(state.stats, sstate.stats):
+      for x, y in zip(a_.preconditioners, b_.preconditioners):
+        prel = max(prel, float((x - y).abs().max() / y.abs().max().clamp_min(1e-30)))
+    out["sharded_vs_single_max_rel"] = max(rel, prel)
+    out["sharded_vs_single_updates_max_rel"] = rel
+    out["sharded_vs_single_preconditioners_max_rel"] = prel
+  return out
+
+
+def bert_large_shapes():
+  """BERT-large (340M) parameter shapes (BASELINE config 4): 24 layers of Q/K/V [1024,16,64],
+  attention output [16,64,1024], FFN 1024x4096 / 4096x1024, biases and LayerNorm vectors,
+  embeddings (the 30522 x 1024 table is skipped by DS:2627-2629), pooler."""
+  shapes = [(30522, 1024), (512, 1024), (2, 1024), (1024,), (1024,)]
+  for _ in range(24):
+    shapes += [(1024, 16, 64), (16, 64)] * 3
+    shapes += [(16, 64, 1024), (1024,), (1024,), (1024,)]
+    shapes += [(1024, 4096), (4096,), (4096, 1024), (1024,), (1024,), (1024,)]
+  shapes += [(1024, 1024), (1024,)]
+  return shapes
+
+
+def time_bert_large_step(dev, world, steps=2, warm=2):
+  """BASELINE config 4: BERT-large shapes, block_size=2048, best_effort_memory_usage_reduction
+  (int16 statistics / preconditioners with extracted diagonal, int8 momenta),
+  preconditioning_compute_steps=1; blocks sharded over the ranks when world > 1.  Also reports
+  the relative Frobenius distance of one sampled 1024^2 preconditioner from the oracle's root of
+  the same (dequantised) statistic -- the int16 storage quantum is part of it."""
+  import torch
+  from precondition_b200 import distributed_shampoo as DS
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(4)
+  shapes = bert_large_shapes()
+  params = [torch.randn(s, generator=gen, device=dev) * 0.02 for s in shapes]
+  opt = DS.distributed_shampoo(0.1, 2048, preconditioning_compute_steps=1,
+                               best_effort_memory_usage_reduction=True, batch_axis_name="batch")
+  state = opt.init(params)
+  # two gradient sets, reused alternately (the full list would hold 1.3 GB per step)
+  gsets = [[torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes] for _ in range(2)]
+  grads = [gsets[t % 2] for t in range(warm + steps)]
+  per_step, upd, state = _timed_updates(opt, state, params, grads, warm, steps)
+  leaves = state.stats
+  tm = torch.cat([st.training_metrics for st in leaves if st.training_metrics is not None])
+  sizes = _stat_sizes(leaves)
+  out = {"ms": sum(per_step) / steps, "ms_per_step_list": [round(x, 3) for x in per_step],
+         "unit": "ms/step", "steps": steps, "n_gpus": world,
+         "config": "BERT-large shapes, block_size=2048, best_effort_memory_usage_reduction "
+                   "(int16 statistics + preconditioners, int8 momenta), "
+                   "preconditioning_compute_steps=1",
+         "parameters": int(sum(p.numel() for p in params)), "statistics": int(tm.shape[0]),
+         "statistics_by_size": {str(k): v for k, v in sorted(sizes.items())},
+         "max_root_error": float(tm[:, 0].max()), "newton_iters_mean": float(tm[:, 1].mean()),
+         "update_finite": bool(all(torch.isfinite(u).all() for u in upd))}
+  if int(os.environ.get("RANK", "0")) == 0:
+    from oracle import numerics as N
+    st = next(s_ for s_ in leaves if s_.statistics and s_.statistics[0].shape[0] == 1024)
+    a_ = st.statistics[0].to_float().cpu().numpy()
+    got = st.preconditioners[0].to_float().cpu().numpy()
+    p_ = DS.Preconditioner(shapes[leaves.index(st)], 2048, 4096,
+                           True).exponent_for_preconditioner()
+    want, wm = N.matrix_inverse_pth_root(a_, p_)
+    out["sampled_root_rel_frobenius_vs_oracle"] = float(
+        np.linalg.norm(got - want) / np.linalg.norm(want))
+    out["sampled_root_iters_ours_oracle"] = [float(st.training_metrics[0, 1]),
+                                             float(wm.inverse_pth_root_iters)]
+  return out
+
+
+def time_sketchy_step(dev, world, steps=2, warm=2):
+  """BASELINE config 5: Sketchy / frequent-directions branch on 8 parameters of 4096 x 4096,
+  block_size=4096, rank 256 (16 statistics), sketch updates sharded over the ranks."""
+  import torch
+  from precondition_b200 import distributed_shampoo as DS
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(5)
+  shapes = [(4096, 4096)] * 8
+  params = [torch.randn(s, generator=gen, device=dev) * 0.02 for s in shapes]
+  opt = DS.distributed_shampoo(0.1, 4096, compression_rank=256, frequent_directions=True,
+                               reuse_preconditioner=True, statistics_compute_steps=1,
+                               preconditioning_compute_steps=1,
+                               batch_axis_name="batch" if world > 1 else None)
+  state = opt.init(params)
+  gsets = [[torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes] for _ in range(2)]
+  grads = [gsets[t % 2] for t in range(warm + steps)]
+  per_step, upd, state = _timed_updates(opt, state, params, grads, warm, steps)
+  pk = state.stats[0].preconditioners[0]
+  v = pk[:, :256]
   return {"ms": sum(per_step) / steps, "ms_per_step_list": [round(x, 3) for x in per_step],
           "unit": "ms/step", "steps": steps, "n_gpus": world,
-          "config": "ResNet-50 shapes, block_size=1024, preconditioning_compute_steps=1, "
-                    "blocks sharded over the ranks" if world > 1 else
-                    "ResNet-50 shapes, block_size=1024, preconditioning_compute_steps=1",
-          "parameters": int(sum(p.numel() for p in params)), "statistics": int(tm.shape[0]),
-          "statistics_of_1024": sizes.get(1024, 0),
-          "max_root_error": float(tm[:, 0].max()),
+          "config": "8 x (4096 x 4096), block_size=4096, compression_rank=256, "
+                    "frequent_directions, reuse_preconditioner, statistics_compute_steps="
+                    "preconditioning_compute_steps=1",
+          "statistics": 16, "statistics_per_gpu": (16 + world - 1) // world,
+          "eigvec_orthogonality_error": float(
+              (v.T @ v - torch.eye(256, device=dev)).abs().max()),
           "update_finite": bool(all(torch.isfinite(u).all() for u in upd))}
 
 

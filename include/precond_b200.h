@@ -19,9 +19,9 @@
  *   - the library owns no user memory: callers pass a workspace whose size comes
  *     from the matching *_workspace_bytes query;
  *   - matrices are row-major, contiguous, 16-byte aligned;
- *   - pc_inverse_pth_root_batched synchronises `stream` internally while it
- *     polls the device-side convergence flags (documented deviation from
- *     "enqueue only").
+ *   - every entry point enqueues on `stream` and returns; pc_inverse_pth_root_* do so through a
+ *     cached CUDA graph with a device-driven WHILE loop (PC_ROOT_MODE=poll restores the
+ *     host-polled loop, which waits on events while the device iterates).
  */
 #ifndef PRECOND_B200_H_
 #define PRECOND_B200_H_
@@ -97,7 +97,7 @@ void pc_stats_get(pc_stats* out);
  *           (DS:595-652), ridge damping (DS:830), coupled Newton (DS:836-885),
  *           retry loop (DS:858-885), padding mask (DS:777-783, DS:930-937).
  *   xs              [batch, n, n] f32   statistics (symmetric PSD)
- *   ps              [batch] i32         exponents p (any p >= 1)
+ *   ps              [batch] i32         exponents p in [1, 16] (larger p: zero root, NaN error)
  *   padding_starts  [batch] i32         rows/cols >= padding_start are padding
  *                                       (pass n for "no padding"; may be NULL)
  *   roots           [batch, n, n] f32   out: (A + eps I)^(-1/p), zeros in padding
@@ -123,6 +123,21 @@ int pc_inverse_pth_root_batched(const float* xs, const int32_t* ps,
                                 const pc_root_options* opt, float* roots,
                                 float* metrics, void* workspace,
                                 size_t workspace_bytes, void* stream);
+
+/* The same solver with the exponents also given as a HOST array (ps_host, may be NULL): the
+ * host then knows how many GEMM launches one Newton iteration needs without reading `ps`
+ * back, and exponents outside [1, 16] are rejected up front.  Both entry points ENQUEUE AND
+ * RETURN in the default "graph" mode: the call is one CUDA graph whose Newton loop is a
+ * conditional WHILE node driven by a device-side convergence check (no host polling; the
+ * executable graph is cached per argument set, so a training loop only re-launches it).
+ * PC_ROOT_MODE=poll selects the host-polled loop of round 1 (it waits on events while the
+ * device iterates); GEMM-timing runs (pc_stats_reset(1)) use it too. */
+int pc_inverse_pth_root_enqueue(const float* xs, const int32_t* ps, const int32_t* ps_host,
+                                const int32_t* padding_starts, int batch, int n,
+                                const pc_root_options* opt, float* roots, float* metrics,
+                                void* workspace, size_t workspace_bytes, void* stream);
+/* 1 if pc_inverse_pth_root_* currently run in graph mode (enqueue only), 0 if host-polled. */
+int pc_root_mode(void);
 
 /* Test hook for the tcgen05 engine: C[b] = A[b] * B[b]^T (fp32 in/out, computed as
  * split-bf16 products, `passes` = 6 or 3, or scaled-fp16 products, `passes` = -3), n % 128 == 0.  Workspace of at least
@@ -219,6 +234,18 @@ int pc_quantize_from_colmax_batched(const float* x, const uint32_t* colmax, int 
 int pc_select_preconditioners(const float* src, const float* metrics, float threshold,
                               float* dst, int batch, int src_rows, int src_cols, int rows,
                               int cols, void* stream);
+
+/* Scatter form for block-sharded roots after the all-gather (DS:2876-2879 + DS:2936-2950):
+ * row j of a gathered buffer goes to row dst_index[j] of the state (dst_index[j] < 0: filler
+ * row of the padded batch, DS:2844-2850, skipped) unless its metrics row -- at
+ * metrics_base + metrics_offset[j] -- reports NaN or an error >= threshold.  Rows are raw
+ * bytes at src + src_offset_bytes[j], so fp32 roots and the int16 / int8, diagonal and bucket
+ * parts of quantised preconditioners (DS:3116-3122) use the same call; metrics_dst (optional)
+ * receives the metrics rows in state order.  All index arrays are DEVICE arrays of `count`. */
+int pc_select_scatter(const void* src, const int64_t* src_offset_bytes,
+                      const float* metrics_base, const int64_t* metrics_offset,
+                      const int32_t* dst_index, float threshold, void* dst, int64_t row_bytes,
+                      float* metrics_dst, int count, void* stream);
 
 /* ------------------------------------------------------------------------
  * (3) Sketchy / frequent-directions sketch update
@@ -332,6 +359,35 @@ int pc_graft_momentum(const float* grad, const float* param,
                       float* diagonal_momentum, float* momentum, float* update,
                       int64_t numel, const pc_graft_options* opt, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* Grouped form of (4): the tail of _transform_grad for EVERY parameter of the model in a fixed
+ * number of launches (the reference maps _transform_grad over the parameter tree,
+ * DS:3650-3657).  All per-parameter arrays live in flat buffers with one segment per parameter
+ * at the same element offset in each of them (offsets multiples of 32 elements, so every
+ * segment is 16-byte aligned); precond_grad may be NULL, and a segment with has_precond == 0
+ * behaves like precond_grad == NULL in pc_graft_momentum (skipped parameter, DS:3557-3561).
+ * Work is cut into chunks of pc_graft_group_chunk_elems() elements:
+ *   segments       DEVICE [num_segments]; first_chunk = running sum of nchunks,
+ *                  nchunks = ceil(numel / chunk)
+ *   chunk_segment  DEVICE [total_chunks] i32: the segment each chunk belongs to
+ * Norms are reduced per segment with fixed-order two-level sums (deterministic). */
+typedef struct {
+  int64_t offset;      /* first element of the segment in every flat buffer */
+  int64_t numel;
+  int32_t first_chunk;
+  int32_t nchunks;
+  int32_t has_precond;
+  int32_t reserved;
+} pc_graft_segment;
+
+int64_t pc_graft_group_chunk_elems(void);
+size_t pc_graft_momentum_grouped_workspace_bytes(int num_segments, int64_t total_chunks);
+int pc_graft_momentum_grouped(const pc_graft_segment* segments, const int32_t* chunk_segment,
+                              int num_segments, int64_t total_chunks, const float* grad,
+                              const float* param, const float* precond_grad,
+                              float* diagonal_statistics, float* diagonal_momentum,
+                              float* momentum, float* update, const pc_graft_options* opt,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

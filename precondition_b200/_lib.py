@@ -33,6 +33,9 @@ EXPORTED_SYMBOLS = (
     "pc_inverse_pth_root_eigh_batched",
     "pc_grouped_gemm_tc_quant", "pc_quantize_from_colmax_batched",
     "pc_grouped_gemm_splitk_workspace_bytes", "pc_grouped_gemm_splitk",
+    "pc_graft_group_chunk_elems", "pc_graft_momentum_grouped_workspace_bytes",
+    "pc_graft_momentum_grouped", "pc_inverse_pth_root_enqueue", "pc_root_mode",
+    "pc_select_scatter",
 )
 
 
@@ -84,6 +87,12 @@ class GraftOptions(ctypes.Structure):
               ("clip_by_scaled_gradient_norm", ctypes.c_float)]
 
 
+class GraftSegment(ctypes.Structure):
+  _fields_ = [("offset", ctypes.c_int64), ("numel", ctypes.c_int64),
+              ("first_chunk", ctypes.c_int32), ("nchunks", ctypes.c_int32),
+              ("has_precond", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
 _lib = None
 
 
@@ -126,6 +135,10 @@ def load() -> ctypes.CDLL:
   lib.pc_inverse_pth_root_batched.argtypes = [vp, vp, vp, i32, i32,
                                               ctypes.POINTER(RootOptions), vp, vp, vp, sz, vp]
   lib.pc_inverse_pth_root_batched.restype = i32
+  lib.pc_inverse_pth_root_enqueue.argtypes = [vp, vp, vp, vp, i32, i32,
+                                              ctypes.POINTER(RootOptions), vp, vp, vp, sz, vp]
+  lib.pc_inverse_pth_root_enqueue.restype = i32
+  lib.pc_root_mode.restype = i32
   lib.pc_debug_tc_gemm.argtypes = [vp, vp, vp, i32, i32, i32, vp, sz, vp]
   lib.pc_debug_tc_gemm.restype = i32
   lib.pc_power_iteration_batched.argtypes = [vp, vp, i32, i32, i32, f32, vp, vp, vp]
@@ -134,6 +147,8 @@ def load() -> ctypes.CDLL:
   lib.pc_grouped_gemm.restype = i32
   lib.pc_select_preconditioners.argtypes = [vp, vp, f32, vp, i32, i32, i32, i32, i32, vp]
   lib.pc_select_preconditioners.restype = i32
+  lib.pc_select_scatter.argtypes = [vp, vp, vp, vp, vp, f32, vp, i64, vp, i32, vp]
+  lib.pc_select_scatter.restype = i32
   lib.pc_quantize_batched.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
   lib.pc_quantize_batched.restype = i32
   lib.pc_dequantize_batched.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
@@ -174,6 +189,13 @@ def load() -> ctypes.CDLL:
   lib.pc_grouped_gemm_splitk_workspace_bytes.restype = sz
   lib.pc_grouped_gemm_splitk.argtypes = [vp, i32, i32, i32, i32, vp, sz, vp]
   lib.pc_grouped_gemm_splitk.restype = i32
+  lib.pc_graft_group_chunk_elems.argtypes = []
+  lib.pc_graft_group_chunk_elems.restype = i64
+  lib.pc_graft_momentum_grouped_workspace_bytes.argtypes = [i32, i64]
+  lib.pc_graft_momentum_grouped_workspace_bytes.restype = sz
+  lib.pc_graft_momentum_grouped.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp,
+                                            ctypes.POINTER(GraftOptions), vp, sz, vp]
+  lib.pc_graft_momentum_grouped.restype = i32
   _lib = lib
   return lib
 

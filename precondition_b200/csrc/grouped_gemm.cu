@@ -1,6 +1,8 @@
 // Grouped GEMM over strided views (statistics update, preconditioner apply):
 //   C = alpha * A B^T-view + beta * C_in   -- see pc_gemm_desc in the header.
 // Replaces jnp.tensordot at DS:1468-1470 and DS:1707 (fp32, CUDA cores).
+#include <algorithm>
+
 #include "simt_gemm.cuh"
 
 namespace pc {
@@ -85,15 +87,16 @@ __global__ void splitk_reduce_kernel(const pc_gemm_desc* __restrict__ descs, int
 namespace pc {
 __global__ void select_copy_kernel(const float* __restrict__ src, const float* __restrict__ metrics,
                                    float threshold, float* __restrict__ dst, int src_cols,
-                                   size_t src_elems, int rows, int cols) {
-  const int b = blockIdx.y;
-  const float err = metrics[(size_t)b * PC_NUM_METRICS + PC_METRIC_ERROR];
-  if (isnan(err) || err >= threshold) return;  // keep the old preconditioner, DS:2936-2943
-  const size_t total = (size_t)rows * cols;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (size_t)gridDim.x * blockDim.x) {
-    const int r = (int)(e / cols), c = (int)(e - (size_t)r * cols);
-    dst[(size_t)b * total + e] = src[(size_t)b * src_elems + (size_t)r * src_cols + c];
+                                   size_t src_elems, int rows, int cols, int batch) {
+  for (int b = blockIdx.y; b < batch; b += gridDim.y) {
+    const float err = metrics[(size_t)b * PC_NUM_METRICS + PC_METRIC_ERROR];
+    if (isnan(err) || err >= threshold) continue;  // keep the old preconditioner, DS:2936-2943
+    const size_t total = (size_t)rows * cols;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (size_t)gridDim.x * blockDim.x) {
+      const int r = (int)(e / cols), c = (int)(e - (size_t)r * cols);
+      dst[(size_t)b * total + e] = src[(size_t)b * src_elems + (size_t)r * src_cols + c];
+    }
   }
 }
 }  // namespace pc
@@ -106,9 +109,64 @@ extern "C" int pc_select_preconditioners(const float* src, const float* metrics,
   if (batch == 0 || rows == 0 || cols == 0) return PC_OK;
   PC_REQUIRE(src && metrics && dst, "null pointer argument");
   const size_t total = (size_t)rows * cols;
-  dim3 grid((unsigned)((total + 255) / 256 < 256 ? (total + 255) / 256 : 256), batch);
+  dim3 grid((unsigned)((total + 255) / 256 < 256 ? (total + 255) / 256 : 256),
+            (unsigned)(batch < 65535 ? batch : 65535));
   pc::select_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      src, metrics, threshold, dst, src_cols, (size_t)src_rows * src_cols, rows, cols);
+      src, metrics, threshold, dst, src_cols, (size_t)src_rows * src_cols, rows, cols, batch);
+  pc::count_launch(1);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+namespace pc {
+// Row j of a gathered buffer -> row dst_idx[j] of the state, unless its metrics row reports a
+// failed root (DS:2936-2950).  Rows are raw bytes so that fp32 roots and the int16 / int8 +
+// diagonal + bucket triples of quantised preconditioners share the kernel.
+__global__ void select_scatter_kernel(const uint8_t* __restrict__ src,
+                                      const int64_t* __restrict__ src_off,
+                                      const float* __restrict__ metrics_base,
+                                      const int64_t* __restrict__ met_off,
+                                      const int32_t* __restrict__ dst_idx, float threshold,
+                                      uint8_t* __restrict__ dst, int64_t row_bytes,
+                                      float* __restrict__ metrics_dst, int count) {
+  for (int j = blockIdx.y; j < count; j += gridDim.y) {
+    const int di = dst_idx[j];
+    if (di < 0) continue;  // filler row (DS:2844-2850)
+    const float* m = metrics_base + met_off[j];
+    if (metrics_dst && blockIdx.x == 0 && threadIdx.x < PC_NUM_METRICS)
+      metrics_dst[(size_t)di * PC_NUM_METRICS + threadIdx.x] = m[threadIdx.x];
+    const float err = m[PC_METRIC_ERROR];
+    if (isnan(err) || err >= threshold) continue;  // keep the old preconditioner
+    const uint8_t* s = src + src_off[j];
+    uint8_t* d = dst + (size_t)di * row_bytes;
+    if ((row_bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+      const int64_t n16 = row_bytes >> 4;
+      for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n16;
+           e += (int64_t)gridDim.x * blockDim.x)
+        reinterpret_cast<uint4*>(d)[e] = reinterpret_cast<const uint4*>(s)[e];
+    } else {
+      for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < row_bytes;
+           e += (int64_t)gridDim.x * blockDim.x)
+        d[e] = s[e];
+    }
+  }
+}
+}  // namespace pc
+
+extern "C" int pc_select_scatter(const void* src, const int64_t* src_offset_bytes,
+                                 const float* metrics_base, const int64_t* metrics_offset,
+                                 const int32_t* dst_index, float threshold, void* dst,
+                                 int64_t row_bytes, float* metrics_dst, int count, void* stream) {
+  PC_REQUIRE(count >= 0 && row_bytes >= 0, "bad select sizes");
+  if (count == 0) return PC_OK;
+  PC_REQUIRE(src && src_offset_bytes && metrics_base && metrics_offset && dst_index && dst,
+             "null pointer argument");
+  const int64_t units = (row_bytes + 15) / 16;
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((units + 255) / 256, 64));
+  dim3 grid(gx, (unsigned)std::min(count, 65535));
+  pc::select_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const uint8_t*)src, src_offset_bytes, metrics_base, metrics_offset, dst_index, threshold,
+      (uint8_t*)dst, row_bytes, metrics_dst, count);
   pc::count_launch(1);
   PC_CUDA_CHECK(cudaGetLastError());
   return PC_OK;

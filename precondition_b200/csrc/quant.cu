@@ -6,6 +6,8 @@
 
 namespace pc {
 
+constexpr int kMaxGridY = 65535;
+
 template <typename Q>
 __device__ __forceinline__ Q to_q(float r);
 template <>
@@ -131,15 +133,20 @@ int pc_quantize_batched(const float* x, int batch, int rows, int cols, int qdtyp
   PC_REQUIRE(bucket != nullptr, "bucket output required");
   PC_REQUIRE(!extract_diagonal || (diag != nullptr && rows == cols),
              "extract_diagonal needs a square matrix and a diagonal output");
-  dim3 grid((cols + 31) / 32, batch), block(32, 8);
-  if (qdtype == PC_QDTYPE_INT16)
-    pc::quantize_kernel<int16_t><<<grid, block, 0, st>>>(x, rows, cols, 32767.f,
-                                                        extract_diagonal, (int16_t*)q, diag,
-                                                        bucket);
-  else
-    pc::quantize_kernel<int8_t><<<grid, block, 0, st>>>(x, rows, cols, 127.f,
-                                                       extract_diagonal, (int8_t*)q, diag,
-                                                       bucket);
+  const size_t per = (size_t)rows * cols;
+  for (int b0 = 0; b0 < batch; b0 += pc::kMaxGridY) {  // grid.y carries the batch
+    const int nb = batch - b0 < pc::kMaxGridY ? batch - b0 : pc::kMaxGridY;
+    dim3 grid((cols + 31) / 32, nb), block(32, 8);
+    float* dg = diag ? diag + (size_t)b0 * rows : nullptr;
+    if (qdtype == PC_QDTYPE_INT16)
+      pc::quantize_kernel<int16_t><<<grid, block, 0, st>>>(
+          x + b0 * per, rows, cols, 32767.f, extract_diagonal, (int16_t*)q + b0 * per, dg,
+          bucket + (size_t)b0 * cols);
+    else
+      pc::quantize_kernel<int8_t><<<grid, block, 0, st>>>(
+          x + b0 * per, rows, cols, 127.f, extract_diagonal, (int8_t*)q + b0 * per, dg,
+          bucket + (size_t)b0 * cols);
+  }
   PC_CUDA_CHECK(cudaGetLastError());
   return PC_OK;
 }
@@ -153,13 +160,17 @@ int pc_quantize_from_colmax_batched(const float* x, const uint32_t* colmax, int 
   PC_REQUIRE(qdtype == PC_QDTYPE_INT16 || qdtype == PC_QDTYPE_INT8,
              "Quantized dtype %d not supported.", qdtype);
   const size_t per = (size_t)n * n;
-  dim3 grid((unsigned)((per + 255) / 256 < 2048 ? (per + 255) / 256 : 2048), batch);
-  if (qdtype == PC_QDTYPE_INT16)
-    pc::quantize_from_colmax_kernel<int16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        x, colmax, n, 32767.f, (int16_t*)q, diag, bucket);
-  else
-    pc::quantize_from_colmax_kernel<int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        x, colmax, n, 127.f, (int8_t*)q, diag, bucket);
+  for (int b0 = 0; b0 < batch; b0 += pc::kMaxGridY) {
+    const int nb = batch - b0 < pc::kMaxGridY ? batch - b0 : pc::kMaxGridY;
+    dim3 grid((unsigned)((per + 255) / 256 < 2048 ? (per + 255) / 256 : 2048), nb);
+    const size_t v = (size_t)b0 * n;
+    if (qdtype == PC_QDTYPE_INT16)
+      pc::quantize_from_colmax_kernel<int16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          x + b0 * per, colmax + v, n, 32767.f, (int16_t*)q + b0 * per, diag + v, bucket + v);
+    else
+      pc::quantize_from_colmax_kernel<int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          x + b0 * per, colmax + v, n, 127.f, (int8_t*)q + b0 * per, diag + v, bucket + v);
+  }
   PC_CUDA_CHECK(cudaGetLastError());
   return PC_OK;
 }
@@ -184,13 +195,19 @@ int pc_dequantize_batched(const void* q, const float* diag, const float* bucket,
   PC_REQUIRE(!extract_diagonal || (diag != nullptr && rows == cols),
              "extract_diagonal needs a square matrix and a diagonal");
   const size_t per = (size_t)rows * cols;
-  dim3 grid((unsigned)((per + 255) / 256 < 1024 ? (per + 255) / 256 : 1024), batch);
-  if (qdtype == PC_QDTYPE_INT16)
-    pc::dequantize_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)q, diag, bucket, rows,
-                                                        cols, extract_diagonal, x);
-  else
-    pc::dequantize_kernel<int8_t><<<grid, 256, 0, st>>>((const int8_t*)q, diag, bucket, rows,
-                                                       cols, extract_diagonal, x);
+  for (int b0 = 0; b0 < batch; b0 += pc::kMaxGridY) {
+    const int nb = batch - b0 < pc::kMaxGridY ? batch - b0 : pc::kMaxGridY;
+    dim3 grid((unsigned)((per + 255) / 256 < 1024 ? (per + 255) / 256 : 1024), nb);
+    const float* dg = diag ? diag + (size_t)b0 * rows : nullptr;
+    if (qdtype == PC_QDTYPE_INT16)
+      pc::dequantize_kernel<int16_t><<<grid, 256, 0, st>>>(
+          (const int16_t*)q + b0 * per, dg, bucket + (size_t)b0 * cols, rows, cols,
+          extract_diagonal, x + b0 * per);
+    else
+      pc::dequantize_kernel<int8_t><<<grid, 256, 0, st>>>(
+          (const int8_t*)q + b0 * per, dg, bucket + (size_t)b0 * cols, rows, cols,
+          extract_diagonal, x + b0 * per);
+  }
   PC_CUDA_CHECK(cudaGetLastError());
   return PC_OK;
 }

@@ -3,8 +3,10 @@
 // GEMM chain engines: CUDA-core fp32 (this file) and tcgen05 split-bf16
 // (tc_gemm.cu), both behind the same per-matrix step programs.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -424,32 +426,37 @@ static int pick_cluster_size(int batch) {
   return c;
 }
 
+// numpy's start vector per size, in pinned memory that is never freed (so the upload needs no
+// host synchronisation), and the kernel attribute: everything that must not happen inside a
+// stream capture
+static std::mutex v0_mu;
+static std::map<int, float*> v0_cache;
+int prepare_power_iteration(int n) {
+  std::lock_guard<std::mutex> lock(v0_mu);
+  if (v0_cache.find(n) != v0_cache.end()) return PC_OK;
+  float* v0 = nullptr;
+  PC_CUDA_CHECK(cudaMallocHost(&v0, sizeof(float) * n));
+  mt19937_uniform(1729u, n, v0);
+  v0_cache[n] = v0;
+  const size_t smem = sizeof(float) * 3 * (size_t)n;
+  if (smem > 48 * 1024)
+    PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return PC_OK;
+}
+
 int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n,
                         int num_iters, float tol, float* lambdas, int32_t* iters,
                         RootCtl* ctl, float* v0_dev, float* ybuf, cudaStream_t stream) {
-  // the start vector lives in pinned memory that is never freed, so the upload needs
-  // no host synchronisation (one buffer per size, built once)
-  static std::mutex v0_mu;
-  static std::map<int, float*> v0_cache;
+  int rc = prepare_power_iteration(n);
+  if (rc != PC_OK) return rc;
   float* v0 = nullptr;
   {
     std::lock_guard<std::mutex> lock(v0_mu);
-    auto it = v0_cache.find(n);
-    if (it == v0_cache.end()) {
-      PC_CUDA_CHECK(cudaMallocHost(&v0, sizeof(float) * n));
-      mt19937_uniform(1729u, n, v0);
-      v0_cache[n] = v0;
-    } else {
-      v0 = it->second;
-    }
+    v0 = v0_cache[n];
   }
   PC_CUDA_CHECK(cudaMemcpyAsync(v0_dev, v0, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
   const size_t smem = sizeof(float) * 3 * (size_t)n;  // v, v / |v|, and A v when csize == 1
-  if (smem > 48 * 1024) {
-    PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-  }
   int csize = n >= 256 ? pick_cluster_size(batch) : 1;
   const int threads = n >= 512 ? 1024 : (n >= 128 ? 512 : 128);
   cudaLaunchConfig_t cfg{};
@@ -469,9 +476,274 @@ int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n,
   return PC_OK;
 }
 
-int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch, int n,
-             const pc_root_options* opt, float* roots, float* metrics, void* workspace,
-             size_t workspace_bytes, cudaStream_t stream) {
+// ---------------------------------------------------------------------------
+// One solver call = pre (setup, power iteration, first initialisation) -> Newton
+// iterations until every matrix is done -> final gather.  Two drivers share the pieces:
+//   * graph mode (default): the call is ONE CUDA graph whose middle is a conditional WHILE
+//     node; the control kernel sets the loop condition on the device
+//     (cudaGraphSetConditional), so the host enqueues and returns -- no event polling, no
+//     host round trip per iteration, and independent calls on different streams overlap.
+//     Executable graphs are cached per argument set (a training loop re-launches them).
+//   * host-polled mode (PC_ROOT_MODE=poll, GEMM timing runs, PC_TC_SYNC=1): the host launches
+//     iteration by iteration and reads the "unfinished" counter two iterations behind.
+// ---------------------------------------------------------------------------
+struct RootCall {
+  const float* xs; const int32_t* ps; const int32_t* pads;
+  int batch, n, engine, max_steps;
+  float* roots; float* metrics;
+  RootWorkspace ws;
+  RootParams prm;
+  F32Store f32;
+  TcEngine tc;
+};
+
+static int max_program_steps(const int32_t* ps_host, int batch) {
+  int max_steps = 1;
+  if (!ps_host) {
+    for (int p = 1; p <= kMaxP; ++p) max_steps = std::max(max_steps, h_programs[p].nsteps);
+    return max_steps;
+  }
+  for (int b = 0; b < batch; ++b)
+    if (ps_host[b] >= 1 && ps_host[b] <= kMaxP)
+      max_steps = std::max(max_steps, h_programs[ps_host[b]].nsteps);
+  return max_steps;
+}
+
+static int root_enqueue_pre(RootCall& c, cudaStream_t stream) {
+  root_setup_kernel<<<(c.batch + 127) / 128, 128, 0, stream>>>(c.ws.ctl, c.ps, c.pads, c.batch,
+                                                              c.n, c.ws.errbits);
+  PC_CUDA_CHECK(cudaGetLastError());
+  int launches = 1;
+  if (c.prm.relative_eps && c.n > 1) {
+    int rc = run_power_iteration(c.xs, nullptr, c.batch, c.n, 100, 1e-6f, nullptr, nullptr,
+                                 c.ws.ctl, c.ws.v0, c.ws.ybuf, stream);  // DS:820-825
+    if (rc != PC_OK) return rc;
+    ++launches;
+  }
+  if (c.engine == PC_ENGINE_SIMT_FP32) {
+    for (int k = 0; k < kNumBufs; ++k)
+      c.f32.base[k] = reinterpret_cast<float*>(c.ws.engine_mem) + (size_t)k * c.batch * c.n * c.n;
+    c.f32.mat_elems = (size_t)c.n * c.n;
+    if (c.n >= 256) {  // first initialisation: whole-GPU strip kernels
+      const int strips = (c.n + 31) / 32;
+      root_norm_strip_kernel<<<dim3(strips, c.batch), 256, 0, stream>>>(
+          c.xs, c.ws.ctl, c.n, strips, c.prm, c.ws.ybuf, c.batch);
+      root_init_strip_kernel<F32Store><<<dim3(strips, c.batch), 1024, 0, stream>>>(
+          c.xs, c.ws.ctl, c.f32, c.batch, c.n, strips, c.prm, c.ws.ybuf);
+      launches += 2;
+    }
+  } else {
+    int rc = tc_engine_init(&c.tc, c.ws.engine_mem, c.batch, c.n,
+                            c.engine == PC_ENGINE_TC_BF16X6 ? 6 : 3,
+                            c.engine == PC_ENGINE_TC_FP16X3 ? 1 : 0, stream);
+    if (rc != PC_OK) return rc;
+    // max_steps = 0: only the first (strip) initialisation
+    rc = tc_engine_iteration(&c.tc, c.xs, c.ws.ctl, c.ws.errbits, c.prm, c.roots, 0, c.ws.ybuf,
+                             false, stream);
+    if (rc != PC_OK) return rc;
+  }
+  count_launch(launches);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+// one Newton iteration of every active matrix (+ the (re)initialisation of whoever waits)
+static int root_enqueue_iteration(RootCall& c, bool do_init, cudaStream_t stream) {
+  if (c.engine == PC_ENGINE_SIMT_FP32) {
+    if (do_init) {
+      root_init_kernel<F32Store><<<c.batch, c.n >= 512 ? 1024 : 256, 0, stream>>>(
+          c.xs, c.ws.ctl, c.f32, c.batch, c.n, c.prm, c.roots);
+      count_launch(1);
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (gemm_timing_enabled()) {
+      cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+      cudaEventRecord(ev0, stream);
+    }
+    const int tiles = (c.n + kSimtBM - 1) / kSimtBM;
+    for (int s = 0; s < c.max_steps; ++s) {
+      dim3 grid(tiles * (tiles + 1) / 2, 1, c.batch * 2);
+      root_phase_simt_kernel<<<grid, kSimtThreads, 0, stream>>>(c.f32, c.ws.ctl, c.ws.errbits,
+                                                               c.n, s);
+    }
+    if (ev0) { cudaEventRecord(ev1, stream); gemm_timing_record(ev0, ev1); }
+    count_launch(c.max_steps);
+    gemm_count(c.max_steps);
+    PC_CUDA_CHECK(cudaGetLastError());
+    return PC_OK;
+  }
+  return tc_engine_iteration(&c.tc, c.xs, c.ws.ctl, c.ws.errbits, c.prm, c.roots, c.max_steps,
+                             nullptr, do_init, stream);
+}
+
+static int root_enqueue_final(RootCall& c, cudaStream_t stream) {
+  if (c.engine == PC_ENGINE_SIMT_FP32) {
+    dim3 fgrid((unsigned)std::min<size_t>(((size_t)c.n * c.n + 255) / 256, 64), c.batch);
+    root_final_kernel<F32Store><<<fgrid, 256, 0, stream>>>(c.ws.ctl, c.f32, c.n, c.roots,
+                                                          c.metrics);
+  } else {
+    int rc = tc_engine_final(&c.tc, c.ws.ctl, c.roots, c.metrics, stream);
+    if (rc != PC_OK) return rc;
+  }
+  count_launch(1);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+// ---- graph mode ------------------------------------------------------------
+struct RootGraphKey {
+  const void* xs; const void* ps; const void* pads; const void* roots; const void* metrics;
+  const void* workspace;
+  int batch, n, engine, max_steps, num_iters, relative_eps, device;
+  float ridge, tol;
+  bool operator<(const RootGraphKey& o) const { return memcmp(this, &o, sizeof(*this)) < 0; }
+};
+struct RootGraphEntry {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int nodes = 0;
+  uint64_t last_use = 0;
+};
+static std::mutex g_graph_mu;
+static std::map<RootGraphKey, RootGraphEntry> g_graph_cache;
+static uint64_t g_graph_clock = 0;
+constexpr size_t kGraphCacheMax = 64;
+
+static bool root_graph_mode_allowed() {
+  const char* m = getenv("PC_ROOT_MODE");
+  if (m && (m[0] == 'p' || m[0] == 'P')) return false;  // "poll"
+  const char* gs = getenv("PC_TC_SYNC");  // the group rendezvous alternates counters per launch
+  if (gs && gs[0] == '1') return false;
+  return !gemm_timing_enabled();
+}
+
+// Device-side convergence check of a captured iteration: same bookkeeping as
+// root_control_kernel, the loop condition goes to the graph's WHILE node.
+__global__ void __launch_bounds__(1024)
+root_control_graph_kernel(RootCtl* ctl, uint32_t* errbits, int batch, RootParams prm,
+                          cudaGraphConditionalHandle handle) {
+  __shared__ int unfinished_total;
+  if (threadIdx.x == 0) unfinished_total = 0;
+  __syncthreads();
+  int unfinished = 0;
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    RootCtl c = ctl[b];
+    if (c.active) {
+      const float new_err = __uint_as_float(errbits[b]);  // max|M' - I_m|, DS:847
+      errbits[b] = 0u;
+      c.ratio = new_err / c.err;                // DS:848
+      c.err = new_err;
+      c.iter += 1;
+      c.cur ^= 1;
+      root_after_error_update(c, prm);
+      ctl[b] = c;
+    }
+    unfinished += c.done ? 0 : 1;
+  }
+  if (unfinished) atomicAdd(&unfinished_total, unfinished);
+  __syncthreads();
+  if (threadIdx.x == 0) cudaGraphSetConditional(handle, unfinished_total > 0 ? 1u : 0u);
+}
+
+static int root_build_graph(RootCall& c, RootGraphEntry* out) {
+  // private capture stream of this host thread (per device)
+  static thread_local cudaStream_t capture_streams[64] = {nullptr};
+  int dev = 0;
+  PC_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaStream_t& cs = capture_streams[dev & 63];
+  if (!cs) PC_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaGraph_t g = nullptr;
+  PC_CUDA_CHECK(cudaGraphCreate(&g, 0));
+  auto fail = [&](int rc) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(cs, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+      cudaGraph_t dummy = nullptr;
+      cudaStreamEndCapture(cs, &dummy);
+    }
+    cudaGraphDestroy(g);
+    cudaGetLastError();
+    return rc;
+  };
+#define PC_G(expr)                                                                         \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return fail(PC_ERR_CUDA);                                                            \
+    }                                                                                      \
+  } while (0)
+  // (1) pre
+  PC_G(cudaStreamBeginCaptureToGraph(cs, g, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  int rc = root_enqueue_pre(c, cs);
+  if (rc != PC_OK) return fail(rc);
+  cudaStreamCaptureStatus status;
+  const cudaGraphNode_t* leaves = nullptr;
+  size_t nleaves = 0;
+  PC_G(cudaStreamGetCaptureInfo(cs, &status, nullptr, nullptr, &leaves, &nleaves));
+  std::vector<cudaGraphNode_t> deps(leaves, leaves + nleaves);
+  cudaGraph_t same = nullptr;
+  PC_G(cudaStreamEndCapture(cs, &same));
+  // (2) WHILE node: iterate while any matrix is unfinished
+  cudaGraphConditionalHandle handle;
+  PC_G(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
+  cudaGraphNodeParams cp = {};
+  cp.type = cudaGraphNodeTypeConditional;
+  cp.conditional.handle = handle;
+  cp.conditional.type = cudaGraphCondTypeWhile;
+  cp.conditional.size = 1;
+  cudaGraphNode_t while_node = nullptr;
+  PC_G(cudaGraphAddNode(&while_node, g, deps.data(), deps.size(), &cp));
+  cudaGraph_t body = cp.conditional.phGraph_out[0];
+  PC_G(cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  rc = root_enqueue_iteration(c, true, cs);
+  if (rc != PC_OK) return fail(rc);
+  root_control_graph_kernel<<<1, 1024, 0, cs>>>(c.ws.ctl, c.ws.errbits, c.batch, c.prm, handle);
+  PC_G(cudaGetLastError());
+  PC_G(cudaStreamEndCapture(cs, &same));
+  // (3) final gather
+  PC_G(cudaStreamBeginCaptureToGraph(cs, g, &while_node, nullptr, 1, cudaStreamCaptureModeRelaxed));
+  rc = root_enqueue_final(c, cs);
+  if (rc != PC_OK) return fail(rc);
+  PC_G(cudaStreamEndCapture(cs, &same));
+  cudaGraphExec_t exec = nullptr;
+  PC_G(cudaGraphInstantiate(&exec, g, 0));
+#undef PC_G
+  size_t nn = 0, nb = 0;
+  cudaGraphGetNodes(g, nullptr, &nn);
+  cudaGraphGetNodes(body, nullptr, &nb);
+  out->graph = g;
+  out->exec = exec;
+  out->nodes = (int)(nn + nb);
+  return PC_OK;
+}
+
+static int run_root_graph(RootCall& c, const RootGraphKey& key, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_graph_mu);  // graph construction / launch order per device
+  auto it = g_graph_cache.find(key);
+  if (it == g_graph_cache.end()) {
+    RootGraphEntry e;
+    int rc = root_build_graph(c, &e);
+    if (rc != PC_OK) return rc;
+    if (g_graph_cache.size() >= kGraphCacheMax) {  // evict the least recently used entry
+      auto victim = g_graph_cache.begin();
+      for (auto jt = g_graph_cache.begin(); jt != g_graph_cache.end(); ++jt)
+        if (jt->second.last_use < victim->second.last_use) victim = jt;
+      cudaGraphExecDestroy(victim->second.exec);
+      cudaGraphDestroy(victim->second.graph);
+      g_graph_cache.erase(victim);
+    }
+    it = g_graph_cache.emplace(key, e).first;
+  } else {
+    count_launch(it->second.nodes);  // (building counted its launches while capturing)
+  }
+  it->second.last_use = ++g_graph_clock;
+  PC_CUDA_CHECK(cudaGraphLaunch(it->second.exec, stream));
+  return PC_OK;
+}
+
+int run_root(const float* xs, const int32_t* ps, const int32_t* ps_host, const int32_t* pads,
+             int batch, int n, const pc_root_options* opt, float* roots, float* metrics,
+             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int engine = resolve_engine(opt->engine, n);
   PC_REQUIRE(engine == PC_ENGINE_SIMT_FP32 || engine == PC_ENGINE_TC_BF16X6 ||
                  engine == PC_ENGINE_TC_BF16X3 || engine == PC_ENGINE_TC_FP16X3,
@@ -490,17 +762,48 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
   }
   int rc = ensure_programs();
   if (rc != PC_OK) return rc;
+  if (ps_host)
+    for (int b = 0; b < batch; ++b)
+      PC_REQUIRE(ps_host[b] >= 1 && ps_host[b] <= kMaxP,
+                 "exponent p = %d of matrix %d is outside [1, %d]", ps_host[b], b, kMaxP);
 
+  RootCall c;
+  c.xs = xs; c.ps = ps; c.pads = pads; c.batch = batch; c.n = n; c.engine = engine;
+  c.roots = roots; c.metrics = metrics;
+  c.prm = RootParams{opt->ridge_epsilon, opt->error_tolerance, opt->num_iters,
+                     opt->relative_matrix_epsilon};
   // carve the workspace
   char* w = reinterpret_cast<char*>(align_up((size_t)workspace, 256));
-  RootWorkspace ws;
-  ws.ctl = reinterpret_cast<RootCtl*>(w); w += align_up(sizeof(RootCtl) * batch, 256);
-  ws.errbits = reinterpret_cast<uint32_t*>(w); w += align_up(sizeof(uint32_t) * batch, 256);
-  ws.unfinished = reinterpret_cast<int*>(w); w += 256;
-  ws.v0 = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * n, 256);
-  ws.ybuf = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * 2 * (size_t)batch * (n < 4 ? 4 : n), 256);
-  ws.engine_mem = w;
+  c.ws.ctl = reinterpret_cast<RootCtl*>(w); w += align_up(sizeof(RootCtl) * batch, 256);
+  c.ws.errbits = reinterpret_cast<uint32_t*>(w); w += align_up(sizeof(uint32_t) * batch, 256);
+  c.ws.unfinished = reinterpret_cast<int*>(w); w += 256;
+  c.ws.v0 = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * n, 256);
+  c.ws.ybuf = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * 2 * (size_t)batch * (n < 4 ? 4 : n), 256);
+  c.ws.engine_mem = w;
 
+  // everything that may not happen inside a stream capture: one-time allocations, symbol
+  // uploads, kernel attributes
+  rc = prepare_power_iteration(n);
+  if (rc != PC_OK) return rc;
+  if (engine != PC_ENGINE_SIMT_FP32) {
+    rc = tc_engine_prepare();
+    if (rc != PC_OK) return rc;
+  }
+
+  if (root_graph_mode_allowed()) {
+    c.max_steps = max_program_steps(ps_host, batch);
+    RootGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.xs = xs; key.ps = ps; key.pads = pads; key.roots = roots; key.metrics = metrics;
+    key.workspace = workspace;
+    key.batch = batch; key.n = n; key.engine = engine; key.max_steps = c.max_steps;
+    key.num_iters = opt->num_iters; key.relative_eps = opt->relative_matrix_epsilon;
+    key.ridge = opt->ridge_epsilon; key.tol = opt->error_tolerance;
+    cudaGetDevice(&key.device);
+    return run_root_graph(c, key, stream);
+  }
+
+  // ---- host-polled mode ----
   // Per-host-thread pinned scratch: exponents (decide how many GEMM launches one Newton
   // iteration needs) and a ring of poll slots for the device-side "unfinished" counter.
   constexpr int kPollRing = 4, kPollLag = 2;
@@ -526,41 +829,20 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
   int32_t* hps = hsx.ps;
   // the copy is queued BEFORE the power iteration and waited for after it has been
   // launched, so the host round trip hides behind that kernel
-  PC_CUDA_CHECK(cudaMemcpyAsync(hps, ps, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, stream));
-  PC_CUDA_CHECK(cudaEventRecord(hsx.ps_ev, stream));
-
-  RootParams prm{opt->ridge_epsilon, opt->error_tolerance, opt->num_iters,
-                 opt->relative_matrix_epsilon};
-  root_setup_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(ws.ctl, ps, pads, batch, n,
-                                                            ws.errbits);
-  PC_CUDA_CHECK(cudaGetLastError());
-  if (opt->relative_matrix_epsilon && n > 1) {
-    rc = run_power_iteration(xs, nullptr, batch, n, 100, 1e-6f, nullptr, nullptr, ws.ctl,
-                             ws.v0, ws.ybuf, stream);  // DS:820-825
-    if (rc != PC_OK) return rc;
-  }
-  PC_CUDA_CHECK(cudaEventSynchronize(hsx.ps_ev));
-  int max_steps = 1;
-  for (int b = 0; b < batch; ++b)
-    if (hps[b] >= 1 && hps[b] <= kMaxP)
-      max_steps = h_programs[hps[b]].nsteps > max_steps ? h_programs[hps[b]].nsteps : max_steps;
-
-  F32Store f32;
-  TcEngine tc;
-  if (engine == PC_ENGINE_SIMT_FP32) {
-    for (int k = 0; k < kNumBufs; ++k)
-      f32.base[k] = reinterpret_cast<float*>(ws.engine_mem) + (size_t)k * batch * n * n;
-    f32.mat_elems = (size_t)n * n;
+  if (ps_host) {
+    memcpy(hps, ps_host, sizeof(int32_t) * batch);
   } else {
-    rc = tc_engine_init(&tc, ws.engine_mem, batch, n, engine == PC_ENGINE_TC_BF16X6 ? 6 : 3,
-                        engine == PC_ENGINE_TC_FP16X3 ? 1 : 0, stream);
-    if (rc != PC_OK) return rc;
+    PC_CUDA_CHECK(cudaMemcpyAsync(hps, ps, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, stream));
+    PC_CUDA_CHECK(cudaEventRecord(hsx.ps_ev, stream));
   }
+  rc = root_enqueue_pre(c, stream);
+  if (rc != PC_OK) return rc;
+  if (!ps_host) PC_CUDA_CHECK(cudaEventSynchronize(hsx.ps_ev));
+  c.max_steps = max_program_steps(hps, batch);
 
   // Convergence is polled kPollLag iterations behind the launches: the host never waits
   // for the iteration it has just enqueued, so the device queue stays non-empty.  The
   // (at most kPollLag) surplus iterations find no active matrix and return at once.
-  const int tiles = (n + kSimtBM - 1) / kSimtBM;
   // 6 tries x num_iters iterations, plus the iterations a retry may idle before the lagged
   // poll notices it and launches its (re)initialisation
   const int max_total = opt->num_iters * 6 + 8 + 6 * (kPollLag + 1);
@@ -581,53 +863,16 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch,
     if (it >= max_total) continue;
     const bool do_init = init_pending;
     init_pending = false;
-    if (engine == PC_ENGINE_SIMT_FP32) {
-      if (it == 0 && n >= 256) {  // first initialisation: whole-GPU strip kernels
-        const int strips = (n + 31) / 32;
-        root_norm_strip_kernel<<<dim3(strips, batch), 256, 0, stream>>>(xs, ws.ctl, n, strips, prm,
-                                                                       ws.ybuf, batch);
-        root_init_strip_kernel<F32Store><<<dim3(strips, batch), 1024, 0, stream>>>(
-            xs, ws.ctl, f32, batch, n, strips, prm, ws.ybuf);
-        count_launch(2);
-      }
-      if (do_init) {
-        root_init_kernel<F32Store><<<batch, n >= 512 ? 1024 : 256, 0, stream>>>(
-            xs, ws.ctl, f32, batch, n, prm, roots);
-        count_launch(1);
-      }
-      cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-      if (gemm_timing_enabled()) {
-        cudaEventCreate(&ev0); cudaEventCreate(&ev1);
-        cudaEventRecord(ev0, stream);
-      }
-      for (int s = 0; s < max_steps; ++s) {
-        dim3 grid(tiles * (tiles + 1) / 2, 1, batch * 2);
-        root_phase_simt_kernel<<<grid, kSimtThreads, 0, stream>>>(f32, ws.ctl, ws.errbits,
-                                                                 n, s);
-      }
-      if (ev0) { cudaEventRecord(ev1, stream); gemm_timing_record(ev0, ev1); }
-      count_launch(max_steps);
-      gemm_count(max_steps);
-    } else {
-      rc = tc_engine_iteration(&tc, xs, ws.ctl, ws.errbits, prm, roots, max_steps,
-                               it == 0 ? ws.ybuf : nullptr, do_init, stream);
-      if (rc != PC_OK) return rc;
-    }
+    rc = root_enqueue_iteration(c, do_init, stream);
+    if (rc != PC_OK) return rc;
     count_launch(1);
     const int slot = it % kPollRing;
-    root_control_kernel<<<1, 1024, 0, stream>>>(ws.ctl, ws.errbits, batch, prm,
+    root_control_kernel<<<1, 1024, 0, stream>>>(c.ws.ctl, c.ws.errbits, batch, c.prm,
                                                 hsx.poll + 2 * slot);
     cudaEventRecord(hsx.ev[slot], stream);
   }
-  dim3 fgrid((unsigned)std::min<size_t>(((size_t)n * n + 255) / 256, 64), batch);
-  if (engine == PC_ENGINE_SIMT_FP32) {
-    root_final_kernel<F32Store><<<fgrid, 256, 0, stream>>>(ws.ctl, f32, n, roots, metrics);
-  } else {
-    rc = tc_engine_final(&tc, ws.ctl, roots, metrics, stream);
-    if (rc != PC_OK) return rc;
-  }
-  PC_CUDA_CHECK(cudaGetLastError());
-  count_launch(3);  // setup, power iteration, final
+  rc = root_enqueue_final(c, stream);
+  if (rc != PC_OK) return rc;
   // algorithmic GEMM flops actually needed: iterations x G(p) x 2 n^3
   if (gemm_timing_enabled()) {
     std::vector<float> hm((size_t)batch * PC_NUM_METRICS);
@@ -666,10 +911,36 @@ int pc_resolve_engine(int n, int engine) { return pc::resolve_engine(engine, n);
 
 size_t pc_inverse_pth_root_workspace_bytes(int batch, int n, int engine) {
   if (batch <= 0 || n <= 0) return 0;
-  return pc::root_workspace_bytes(batch, n, engine);
+  return pc::root_workspace_bytes(batch < 32767 ? batch : 32767, n, engine);
+}
+
+// grid.y / grid.z carry the batch in several kernels: larger batches run as consecutive chunks
+static int run_root_chunked(const float* xs, const int32_t* ps, const int32_t* ps_host,
+                            const int32_t* padding_starts, int batch, int n,
+                            const pc_root_options* opt, float* roots, float* metrics,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  constexpr int kMaxChunk = 32767;  // the SIMT engine launches 2 * batch blocks in grid.z
+  const size_t nn = (size_t)n * n;
+  for (int b0 = 0; b0 < batch; b0 += kMaxChunk) {
+    const int nb = batch - b0 < kMaxChunk ? batch - b0 : kMaxChunk;
+    int rc = pc::run_root(xs + (size_t)b0 * nn, ps + b0, ps_host ? ps_host + b0 : nullptr,
+                          padding_starts ? padding_starts + b0 : nullptr, nb, n, opt,
+                          roots + (size_t)b0 * nn, metrics + (size_t)b0 * PC_NUM_METRICS, workspace,
+                          workspace_bytes, stream);
+    if (rc != PC_OK) return rc;
+  }
+  return PC_OK;
 }
 
 int pc_inverse_pth_root_batched(const float* xs, const int32_t* ps,
+                                const int32_t* padding_starts, int batch, int n,
+                                const pc_root_options* opt, float* roots, float* metrics,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  return pc_inverse_pth_root_enqueue(xs, ps, nullptr, padding_starts, batch, n, opt, roots,
+                                     metrics, workspace, workspace_bytes, stream);
+}
+
+int pc_inverse_pth_root_enqueue(const float* xs, const int32_t* ps, const int32_t* ps_host,
                                 const int32_t* padding_starts, int batch, int n,
                                 const pc_root_options* opt, float* roots, float* metrics,
                                 void* workspace, size_t workspace_bytes, void* stream) {
@@ -677,9 +948,11 @@ int pc_inverse_pth_root_batched(const float* xs, const int32_t* ps,
   if (batch == 0) return PC_OK;
   PC_REQUIRE(xs && ps && roots && metrics && workspace && opt, "null pointer argument");
   PC_REQUIRE(opt->num_iters >= 0, "num_iters < 0");
-  return pc::run_root(xs, ps, padding_starts, batch, n, opt, roots, metrics, workspace,
-                      workspace_bytes, (cudaStream_t)stream);
+  return run_root_chunked(xs, ps, ps_host, padding_starts, batch, n, opt, roots, metrics,
+                          workspace, workspace_bytes, (cudaStream_t)stream);
 }
+
+int pc_root_mode(void) { return pc::root_graph_mode_allowed() ? 1 : 0; }
 
 int pc_power_iteration_batched(const float* xs, const int32_t* padding_starts, int batch,
                                int n, int num_iters, float error_tolerance, float* lambdas,

@@ -14,6 +14,8 @@ struct TcEngine {
 };
 
 bool tc_engine_available();
+// one-time per-device setup (kernel attributes, constants); call before any stream capture
+int tc_engine_prepare();
 size_t tc_engine_bytes(int batch, int n, int planes);
 int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt,
                    cudaStream_t stream);

@@ -28,6 +28,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "root_kernels.cuh"
@@ -1573,6 +1574,52 @@ static void plan_launch(TcHostState* hs, int s, int ntri, int units, int cpi, in
 
 static Program* g_progs_dev[64] = {nullptr};
 
+constexpr size_t kPhaseSmemBytes(int stages, int lp) {
+  return (size_t)stages * 2 * lp * TC_TILE_BYTES + 1024 + 1024 + 16 * TC_STAGE_BYTES_PER_WARP;
+}
+
+// One-time, per-device setup that must not run inside a stream capture: dynamic shared-memory
+// attributes of every kernel variant, the L2 policy constants, the device copy of the step
+// programs.
+int tc_engine_prepare() {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  PC_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 64 && done[dev]) return PC_OK;
+#define PC_TC_ATTR(kernel, bytes) \
+  PC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+  PC_TC_ATTR((tc_phase_kernel_ws<2, 3, TC_FMT_FP16S, 1>), kPhaseSmemBytes(3, 2));
+  PC_TC_ATTR((tc_phase_kernel_ws<2, 3, TC_FMT_FP16S, 2>), kPhaseSmemBytes(3, 2));
+  PC_TC_ATTR((tc_phase_kernel_ws<3, 2, TC_FMT_BF16, 1>), kPhaseSmemBytes(2, 3));
+  PC_TC_ATTR((tc_phase_kernel_ws<2, 3, TC_FMT_BF16, 1>), kPhaseSmemBytes(3, 2));
+  PC_TC_ATTR((tc_phase_kernel_pair256<2, 3, TC_FMT_FP16S, 1>), kPhaseSmemBytes(3, 2));
+  PC_TC_ATTR((tc_phase_kernel_pair256<2, 3, TC_FMT_FP16S, 2>), kPhaseSmemBytes(3, 2));
+  PC_TC_ATTR((tc_phase_kernel_pair256<3, 2, TC_FMT_BF16, 1>), kPhaseSmemBytes(2, 3));
+  PC_TC_ATTR((tc_phase_kernel_pair256<2, 3, TC_FMT_BF16, 1>), kPhaseSmemBytes(3, 2));
+  PC_TC_ATTR((tc_phase_kernel_ws2<4>),
+             (size_t)4 * 3 * TC_TILE_BYTES + 1024 + 1024 + 16 * TC_STAGE_BYTES_PER_WARP);
+#undef PC_TC_ATTR
+  {
+    const char* h = getenv("PC_TC_HINTS");
+    const int want = (h && h[0] == '1') ? 1 : 0;
+    const uint64_t lp = want ? kPolicyEvictLast : kPolicyEvictNormal;
+    const uint64_t sp = want ? kPolicyEvictFirst : kPolicyEvictNormal;
+    PC_CUDA_CHECK(cudaMemcpyToSymbol(g_load_policy, &lp, sizeof(lp)));
+    PC_CUDA_CHECK(cudaMemcpyToSymbol(g_store_policy, &sp, sizeof(sp)));
+  }
+  if (dev < 64 && !g_progs_dev[dev]) {
+    Program hp[kMaxP + 1];
+    memset(hp, 0, sizeof(hp));
+    for (int p = 1; p <= kMaxP; ++p) build_program(p, &hp[p]);
+    PC_CUDA_CHECK(cudaMalloc(&g_progs_dev[dev], sizeof(hp)));
+    PC_CUDA_CHECK(cudaMemcpy(g_progs_dev[dev], hp, sizeof(hp), cudaMemcpyHostToDevice));
+  }
+  if (dev < 64) done[dev] = true;
+  return PC_OK;
+}
+
 int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt,
                    cudaStream_t stream) {
   PC_REQUIRE(n % TC_BM == 0, "tcgen05 engine needs n %% 128 == 0");
@@ -1659,28 +1706,10 @@ int tc_engine_init(TcEngine* e, void* mem, int batch, int n, int passes, int fmt
   hs->prm.buf_stride = buf_stride;
   hs->prm.mat_stride = (size_t)n * n;
   hs->prm.n = n; hs->prm.batch = batch; hs->prm.tiles = n / TC_BM;
-  {
-    static int hints_set = -1;
-    const char* h = getenv("PC_TC_HINTS");
-    const int want = (h && h[0] == '1') ? 1 : 0;
-    if (hints_set != want) {
-      const uint64_t lp = want ? kPolicyEvictLast : kPolicyEvictNormal;
-      const uint64_t sp = want ? kPolicyEvictFirst : kPolicyEvictNormal;
-      cudaMemcpyToSymbol(g_load_policy, &lp, sizeof(lp));
-      cudaMemcpyToSymbol(g_store_policy, &sp, sizeof(sp));
-      hints_set = want;
-    }
-  }
-  // device copy of the step programs (the tc kernel reads them from global memory)
   int dev = 0;
   PC_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 64 && !g_progs_dev[dev]) {
-    Program hp[kMaxP + 1];
-    memset(hp, 0, sizeof(hp));
-    for (int p = 1; p <= kMaxP; ++p) build_program(p, &hp[p]);
-    PC_CUDA_CHECK(cudaMalloc(&g_progs_dev[dev], sizeof(hp)));
-    PC_CUDA_CHECK(cudaMemcpy(g_progs_dev[dev], hp, sizeof(hp), cudaMemcpyHostToDevice));
-  }
+  int rc_prep = tc_engine_prepare();  // no-op when already done (must precede any capture)
+  if (rc_prep != PC_OK) return rc_prep;
   hs->progs_dev = g_progs_dev[dev < 64 ? dev : 0];
   return PC_OK;
 }
@@ -1689,12 +1718,6 @@ template <int kLP, int kStages, int kFmt, int kChunkKB>
 static int launch_phase_ws(TcHostState* hs, int s, cudaStream_t stream) {
   constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 1024 +
                           16 * TC_STAGE_BYTES_PER_WARP;
-  static bool configured = false;
-  if (!configured) {
-    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_ws<kLP, kStages, kFmt, kChunkKB>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   int grid, total_work;
   plan_launch(hs, s, hs->prm.tiles * (hs->prm.tiles + 1) / 2, hs->sms, 1, &grid, &total_work);
   tc_phase_kernel_ws<kLP, kStages, kFmt, kChunkKB><<<grid, TC_WS_THREADS, smem, stream>>>(
@@ -1707,12 +1730,6 @@ template <int kLP, int kStages, int kFmt, int kChunkKB>
 static int launch_phase_pair256(TcHostState* hs, int s, cudaStream_t stream) {
   constexpr size_t smem = (size_t)kStages * 2 * kLP * TC_TILE_BYTES + 1024 + 1024 +
                           16 * TC_STAGE_BYTES_PER_WARP;
-  static bool configured = false;
-  if (!configured) {
-    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_pair256<kLP, kStages, kFmt, kChunkKB>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   const int t2 = hs->prm.tiles / 2;
   int clusters, total_work;
   plan_launch(hs, s, t2 * (t2 + 1) / 2, hs->sms / 2, 2, &clusters, &total_work);
@@ -1726,12 +1743,6 @@ static int launch_phase_ws2(TcHostState* hs, int s, cudaStream_t stream) {
   constexpr int kStages = 4;
   constexpr size_t smem = (size_t)kStages * 3 * TC_TILE_BYTES + 1024 + 1024 +
                           16 * TC_STAGE_BYTES_PER_WARP;
-  static bool configured = false;
-  if (!configured) {
-    PC_CUDA_CHECK(cudaFuncSetAttribute(tc_phase_kernel_ws2<kStages>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   const int t2 = hs->prm.tiles / 2;
   int clusters, total_work;
   plan_launch(hs, s, t2 * (t2 + 1), hs->sms / 2, 2, &clusters, &total_work);
@@ -1785,7 +1796,7 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
     count_launch(1);
   }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (gemm_timing_enabled()) {
+  if (gemm_timing_enabled() && max_steps > 0) {
     cudaEventCreate(&ev0); cudaEventCreate(&ev1);
     cudaEventRecord(ev0, stream);
   }

@@ -18,9 +18,8 @@ B200-first layout decisions:
     strided view handed to the grouped GEMM (DS:1412-1422 uses jnp.split copies);
   * the per-step work is a fixed list of launches built once in ``init``.
 
-Not built yet (raise on use): LOBPCG (DS:789-812), ``eigh=True`` (DS:943-1030),
-``shard_optimizer_states`` / pjit (DS:2162-2583), FD diagnostics, merged shapes of
-rank > 3.
+Not built yet (raise on use): LOBPCG (DS:789-812), ``shard_optimizer_states`` / pjit
+(DS:2162-2583), FD diagnostics, merged shapes of rank > 3.
 """
 from __future__ import annotations
 
@@ -303,30 +302,138 @@ def _tree_unflatten(treedef, leaves):
 
 
 # ---------------------------------------------------------------------------
+# preconditioning_compute_steps schedule (DS:44-76)
+# ---------------------------------------------------------------------------
+def preconditioning_compute_steps_schedule(lr_fn, start_preconditioning_compute_steps,
+                                           end_preconditioning_compute_steps, step):
+  """Grows preconditioning_compute_steps along the learning-rate schedule, from the start
+  value to start + end as the rate decays to 0, rounded down to a multiple of 10 (DS:44-76)."""
+  base_lr = float(lr_fn(0))
+  lr = float(lr_fn(step))
+  decay_factor = lr / base_lr
+  t = start_preconditioning_compute_steps + (1 - decay_factor) * end_preconditioning_compute_steps
+  return max((t // 10) * 10, 1)
+
+
+def newton_gemms_per_iteration(p: int) -> int:
+  """G(p) of SURVEY 8(d): necessary products per coupled-Newton iteration."""
+  p = int(p)
+  return (p.bit_length() - 1) + bin(p).count("1") - 1 + 2
+
+
+def partition_statistics(buckets, world):
+  """Cost-balanced partition of all statistics over ``world`` ranks.
+
+  ``buckets``: list of (key, [cost of statistic 0, 1, ...]).  Buckets are taken in order of
+  decreasing per-statistic cost; inside a bucket the statistics, sorted by decreasing cost, are
+  dealt round-robin over the ranks visited from the least loaded one upwards, so that per
+  bucket the counts differ by at most one (equal-size all-gather payloads, DS:2844-2850
+  fillers only for the remainder) while the total cost per rank stays balanced.  Every rank
+  computes the same table.  Returns {key: [sorted indices of rank 0, of rank 1, ...]}."""
+  load = [0.0] * world
+  out = {}
+  for key, costs in sorted(buckets, key=lambda kv: (-max(kv[1], default=0.0), str(kv[0]))):
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    rank_order = sorted(range(world), key=lambda r: (load[r], r))
+    ranks = [[] for _ in range(world)]
+    for k, i in enumerate(order):
+      r = rank_order[k % world]
+      ranks[r].append(i)
+      load[r] += costs[i]
+    out[key] = [sorted(r) for r in ranks]
+  return out
+
+
+def gather_layout(owned, cnt, sections):
+  """Byte layout of one bucket's packed all-gather and the index arrays of the scatter back
+  into state order (``pc_select_scatter``).
+
+  ``owned[r]``: sorted state indices rank r solves; ``cnt``: rows per rank (the shorter ranks
+  are padded with fillers, DS:2844-2850); ``sections``: [(name, row_bytes)] with "m" = the
+  metrics rows (5 floats).  Every rank sends ``lbytes`` bytes: the sections back to back, each
+  16-byte aligned.  Gathered row j = (rank j // cnt, local row j % cnt)."""
+  world = len(owned)
+  off, sec = 0, {}
+  for name, row in sections:
+    sec[name] = (off, row)
+    off += _align16(cnt * row)
+  dst = np.full(world * cnt, -1, dtype=np.int32)
+  for r, o in enumerate(owned):
+    dst[r * cnt:r * cnt + len(o)] = o
+  rr = np.repeat(np.arange(world, dtype=np.int64), cnt)
+  ll = np.tile(np.arange(cnt, dtype=np.int64), world)
+  src = {name: rr * off + o + ll * row for name, (o, row) in sec.items() if name != "m"}
+  return {"lbytes": off, "sections": sec, "dst_index": dst,
+          "metrics_offset": (rr * off + sec["m"][0]) // 4 + ll * 5, "src_offset": src}
+
+
+# ---------------------------------------------------------------------------
 # state
 # ---------------------------------------------------------------------------
 class ParameterStats:
-  """Per-parameter optimizer state, field-for-field DS:367-375."""
+  """Per-parameter optimizer state, field-for-field DS:367-375.  The tensors are VIEWS of
+  the optimizer's stacked / flat device buffers (see ``_Shampoo``): ``update`` advances them
+  in place.  ``export_state`` / ``import_state`` of the transformation copy them out / in."""
 
   def __init__(self, diagonal_statistics, statistics, preconditioners, diagonal_momentum,
-               momentum, avg_grad, metrics_ref):
+               momentum, avg_grad, metric_rows, device):
     self.diagonal_statistics = diagonal_statistics
     self.statistics = statistics
     self.preconditioners = preconditioners
     self.diagonal_momentum = diagonal_momentum
     self.momentum = momentum
     self.avg_grad = avg_grad
-    self._metrics_ref = metrics_ref  # (owner, [(bucket, index), ...]) or None
+    self._metric_rows = metric_rows  # [5] rows of the bucket metrics, or None
+    self._device = device
 
   @property
   def training_metrics(self):
     """[num_statistics, 5] rows of TrainingMetrics scalars (DS:338-351)."""
-    if self._metrics_ref is None:
+    if self._metric_rows is None:
       return None
-    owner, refs = self._metrics_ref
-    if not refs:
-      return torch.zeros((0, 5), dtype=torch.float32, device=owner.device)
-    return torch.stack([owner.metrics[s][i] for s, i in refs])
+    if not self._metric_rows:
+      return torch.zeros((0, 5), dtype=torch.float32, device=self._device)
+    return torch.stack(list(self._metric_rows))
+
+
+def _state_tensors(st: ParameterStats):
+  """Every tensor of a ParameterStats in a fixed order (export / import / aliasing checks)."""
+  out = []
+
+  def add(x):
+    if isinstance(x, QuantizedValue):
+      for t in (x.quantized, x.diagonal, x.bucket_size):
+        if isinstance(t, torch.Tensor):
+          out.append(t)
+    elif isinstance(x, torch.Tensor):
+      out.append(x)
+
+  add(st.diagonal_statistics)
+  for x in st.statistics:
+    add(x)
+  for x in st.preconditioners:
+    add(x)
+  add(st.diagonal_momentum)
+  add(st.momentum)
+  add(st.avg_grad)
+  if st._metric_rows:
+    out.extend(st._metric_rows)
+  return out
+
+
+def _clone_stats(st: ParameterStats) -> ParameterStats:
+  def cl(x):
+    if isinstance(x, QuantizedValue):
+      return QuantizedValue(cl(x.quantized), cl(x.diagonal), cl(x.bucket_size), x.quantized_dtype,
+                            x.extract_diagonal, list(x.shape))
+    if isinstance(x, torch.Tensor):
+      return x.detach().clone()
+    return x
+  return ParameterStats(cl(st.diagonal_statistics), [cl(x) for x in st.statistics],
+                        [cl(x) for x in st.preconditioners], cl(st.diagonal_momentum),
+                        cl(st.momentum), cl(st.avg_grad),
+                        None if st._metric_rows is None else [cl(x) for x in st._metric_rows],
+                        st._device)
 
 
 class _Bucket:
@@ -336,10 +443,20 @@ class _Bucket:
     self.size, self.pdim = size, pdim
     self.exponents: List[int] = []
     self.count = 0
+    self.job = None
 
 
 class _ParamPlan:
   pass
+
+
+class _RootJob:
+  """Static buffers of one bucket's (possibly sharded) root solve."""
+  pass
+
+
+def _align16(x):
+  return (x + 15) // 16 * 16
 
 
 class _Shampoo:
@@ -354,7 +471,8 @@ class _Shampoo:
                compression_rank, skip_preconditioning_rank_lt, decoupled_learning_rate,
                decoupled_weight_decay, generate_training_metrics, engine, process_group,
                frequent_directions=False, reuse_preconditioner=False, reset_frequency=None,
-               average_grad=False, eigh=False):
+               average_grad=False, eigh=False, decay_preconditioning_compute_steps=False,
+               end_preconditioning_compute_steps=None):
     self.__dict__.update({k: v for k, v in locals().items() if k != "self"})
     # DS:2051-2064: second-moment quantisation only with a batch axis
     self.quantize_second_moment = bool(best_effort_memory_usage_reduction and
@@ -395,21 +513,31 @@ class _Shampoo:
     self.device = leaves[0].device
     if self.device.type != "cuda":
       raise RuntimeError("precondition_b200 needs CUDA tensors: there is no CPU fallback")
+    for p in leaves:
+      if not p.is_floating_point():
+        raise TypeError(f"parameters must be floating point, got {p.dtype}")
+      if p.device != self.device:
+        raise RuntimeError("all parameters must live on one CUDA device")
     dev = self.device
-    # flat gradient / preconditioned-gradient / temp buffers
+    # Flat fp32 buffers, one 128-byte aligned segment per parameter at the same offset in each:
+    # gradient, preconditioned gradient, GEMM temporaries, momenta, diagonal statistics.  The
+    # optimizer state is float32 whatever the parameter dtype / memory layout is (the kernels
+    # read and write 4-byte elements of contiguous row-major segments).
     offsets, total = [], 0
     for p in leaves:
       offsets.append(total)
       total += (p.numel() + 31) // 32 * 32
-    self.gbuf = torch.zeros(total, dtype=torch.float32, device=dev)
-    self.pgbuf = torch.zeros(total, dtype=torch.float32, device=dev)
-    self.t1buf = torch.zeros(total, dtype=torch.float32, device=dev)
-    self.t2buf = torch.zeros(total, dtype=torch.float32, device=dev)
+    self.total = total
+    zeros = lambda: torch.zeros(total, dtype=torch.float32, device=dev)
+    self.gbuf, self.pgbuf, self.t1buf, self.t2buf = zeros(), zeros(), zeros(), zeros()
+    self.mbuf, self.dmbuf = zeros(), zeros()
+    self.dsbuf = zeros() if self._graft_has_diag() else None
+    self.pbuf = zeros() if self.weight_decay != 0 else None
     # Sketchy with average_grad (DS:2640-2645): statistics are taken from the running
     # gradient sum divided by statistics_compute_steps instead of the raw gradient
     self.use_avg_grad = bool(self.frequent_directions and self.average_grad)
-    self.agbuf = torch.zeros(total, dtype=torch.float32, device=dev) if self.use_avg_grad else None
-    self.sgbuf = torch.zeros(total, dtype=torch.float32, device=dev) if self.use_avg_grad else None
+    self.agbuf = zeros() if self.use_avg_grad else None
+    self.sgbuf = zeros() if self.use_avg_grad else None
 
     self.plans, self.buckets = [], {}
     for idx, p in enumerate(leaves):
@@ -423,12 +551,16 @@ class _Shampoo:
       plan.flags = plan.pre.should_precondition_dims()
       plan.exponent = (plan.pre.exponent_for_preconditioner()
                        if self.exponent_override == 0 else self.exponent_override)
+      plan.mdt = self._momentum_dtype(p)
       plan.stat_refs = []  # (bucket size, index in bucket) in reference order
       plan.blocks = []
       if not plan.skip:
         if len(plan.tshape) > 3:
           raise NotImplementedError(
               f"merged shape {plan.tshape} has rank > 3; not supported by the B200 path yet")
+        if any(plan.flags) and not 1 <= plan.exponent <= 16:
+          raise ValueError(f"inverse-root exponent {plan.exponent} outside [1, 16] "
+                           "(exponent_override or tensor rank too large for the Newton programs)")
         for offs, sizes in plan.pre._partitioner.block_offsets():
           refs = []
           for axis, flag in enumerate(plan.flags):
@@ -457,7 +589,7 @@ class _Shampoo:
       else:
         bk.precs = eye.repeat(bk.count, 1, 1).contiguous()
       bk.exps = torch.tensor(bk.exponents, dtype=torch.int32, device=dev)
-      bk.roots_tmp = torch.empty_like(bk.stats)
+      bk.exps_host = np.asarray(bk.exponents, dtype=np.int32)
       self.metrics[s] = torch.zeros((bk.count, 5), dtype=torch.float32, device=dev)
       if self.quantize_second_moment:
         q, d, b = ops.quantize(bk.stats, self.qdt_second, True)
@@ -465,21 +597,35 @@ class _Shampoo:
         q, d, b = ops.quantize(bk.precs, self.qdt_second, True)
         bk.qprecs = [q, d, b]
     self._build_launch_lists(leaves)
+    # the whole grafting / momentum tail runs as one grouped call over the flat buffers
+    self._graft_group = ops.GraftGroup(
+        [(pl.offset, pl.numel, not pl.skip) for pl in self.plans], dev)
+    self._gviews = [self.gbuf[pl.offset:pl.offset + pl.numel] for pl in self.plans]
+    self._pviews = ([self.pbuf[pl.offset:pl.offset + pl.numel] for pl in self.plans]
+                    if self.pbuf is not None else None)
 
     stats = []
     for plan, p in zip(self.plans, leaves):
-      diag = torch.zeros_like(p) if self._graft_has_diag() else []
-      mdt = self._momentum_dtype(p)
+      seg = slice(plan.offset, plan.offset + plan.numel)
+      diag = self.dsbuf[seg].view(p.shape) if self._graft_has_diag() else []
+      if plan.mdt == torch.float32:
+        mom = QuantizedValue.from_float_value(self.mbuf[seg].view(p.shape), torch.float32)
+        dmom = QuantizedValue.from_float_value(self.dmbuf[seg].view(p.shape), torch.float32)
+      else:  # int8 momenta (DS:2111-2114): the flat segments are the fp32 scratch of a step
+        z = torch.zeros(p.shape, dtype=torch.float32, device=dev)
+        mom = QuantizedValue.from_float_value(z, plan.mdt)
+        dmom = QuantizedValue.from_float_value(z, plan.mdt)
       st = ParameterStats(
           QuantizedValue.from_float_value(diag, torch.float32),
           [self._stat_view(r) for r in plan.stat_refs],
           [self._prec_view(r) for r in plan.stat_refs],
-          QuantizedValue.from_float_value(torch.zeros_like(p), mdt),
-          QuantizedValue.from_float_value(torch.zeros_like(p), mdt),
-          (self.agbuf[plan.offset:plan.offset + plan.numel].view(p.shape)
-           if self.use_avg_grad else None),
-          (self, plan.stat_refs) if self.generate_training_metrics else None)
+          dmom, mom,
+          (self.agbuf[seg].view(p.shape) if self.use_avg_grad else None),
+          ([self.metrics[s][i] for s, i in plan.stat_refs]
+           if self.generate_training_metrics else None), dev)
       stats.append(st)
+    self._own_leaves = stats
+    self._own_ptrs = [[t.data_ptr() for t in _state_tensors(st)] for st in stats]
     self._built = True
     return ShampooState(0, _tree_unflatten(treedef, stats))
 
@@ -498,6 +644,51 @@ class _Shampoo:
       q, d, b = bk.qprecs
       return QuantizedValue(q[i], d[i], b[i], self.qdt_second, True, [s, s])
     return bk.packed[i] if bk.compressed else bk.precs[i]
+
+  # ---- state export / import -------------------------------------------------
+  def export_state(self, state):
+    """Deep copy of ``state`` that no longer aliases the optimizer's buffers (checkpoint)."""
+    leaves = self._flatten_stats(state.stats)
+    return ShampooState(int(state.count),
+                        _tree_unflatten(self.treedef, [_clone_stats(st) for st in leaves]))
+
+  def import_state(self, state):
+    """Copies a foreign state (restored checkpoint, earlier export, deep copy) into the
+    optimizer's buffers and returns the equivalent state that aliases them."""
+    assert self._built, "call init(params) first"
+    leaves = self._flatten_stats(state.stats)
+    if len(leaves) != len(self._own_leaves):
+      raise ValueError("state does not match the parameters this optimizer was initialised with")
+    for own, other in zip(self._own_leaves, leaves):
+      if other is own:
+        continue
+      a, b = _state_tensors(own), _state_tensors(other)
+      if len(a) != len(b) or any(x.shape != y.shape or x.dtype != y.dtype for x, y in zip(a, b)):
+        raise ValueError("state layout does not match this optimizer's configuration")
+      for x, y in zip(a, b):
+        if x.data_ptr() != y.data_ptr():
+          x.copy_(y)
+    r = abs(self.compression_rank)
+    for bk in self.buckets.values():
+      if bk.compressed:  # the dense operator is derived from the packed sketch
+        ops.low_rank_to_dense(bk.packed, r, out=bk.precs)
+    return ShampooState(int(state.count), _tree_unflatten(self.treedef, self._own_leaves))
+
+  def _adopt(self, state):
+    """``update`` advances the buffers behind the state returned by ``init`` / ``update`` /
+    ``import_state``; any other state (checkpoint, copy, another init) is imported first."""
+    leaves = self._flatten_stats(state.stats)
+    if len(leaves) == len(self._own_leaves):
+      same = True
+      for own, ptrs, st in zip(self._own_leaves, self._own_ptrs, leaves):
+        if st is own:
+          continue
+        if [t.data_ptr() for t in _state_tensors(st)] != ptrs:
+          same = False
+          break
+      if same:
+        return
+    self.import_state(state)
 
   # ---- static launch lists ------------------------------------------------
   def _build_launch_lists(self, leaves):
@@ -653,6 +844,7 @@ class _Shampoo:
       self._apply_tc.append(tc)
       self._apply_simt.append(simt)
 
+
   def _identity(self, n):
     cache = self.__dict__.setdefault("_eyes", {})
     if n not in cache:
@@ -664,12 +856,22 @@ class _Shampoo:
     assert self._built, "call init(params) first"
     step = int(state.count)
     g_leaves, _ = _tree_flatten(grads)
-    s_leaves = self._flatten_stats(state.stats)
-    p_leaves = _tree_flatten(params)[0] if params is not None else [None] * len(g_leaves)
-    # (0) stage gradients into the flat buffer the static descriptors point at
-    if getattr(self, "_gviews", None) is None:
-      self._gviews = [self.gbuf[pl.offset:pl.offset + pl.numel] for pl in self.plans]
-    torch._foreach_copy_(self._gviews, [g.reshape(-1) for g in g_leaves])  # one fused staging pass
+    if len(g_leaves) != len(self.plans):
+      raise ValueError("gradient tree does not match the parameters given to init")
+    self._adopt(state)
+    for g, plan in zip(g_leaves, self.plans):
+      if tuple(g.shape) != plan.shape:
+        raise ValueError(f"gradient shape {tuple(g.shape)} != parameter shape {plan.shape}")
+      if not g.is_cuda or not g.is_floating_point():
+        raise TypeError("gradients must be floating-point CUDA tensors")
+    # (0) stage gradients (any float dtype, any memory layout) into the flat fp32 buffer the
+    #     static descriptors point at: one fused pass
+    torch._foreach_copy_(self._gviews, [g.reshape(-1) for g in g_leaves])
+    if self.weight_decay != 0:
+      if params is None:
+        raise ValueError("weight_decay needs params")
+      p_leaves = _tree_flatten(params)[0]
+      torch._foreach_copy_(self._pviews, [p.reshape(-1) for p in p_leaves])
     if self.use_avg_grad:  # DS:2640-2645
       k = self.statistics_compute_steps
       if k == 1 or step % k == 1:
@@ -681,17 +883,25 @@ class _Shampoo:
     if self._stat_count and (self.statistics_compute_steps <= 1 or
                                 step % self.statistics_compute_steps == 0):
       self._update_statistics()
-    # (2) preconditioners (DS:3648 -> DS:3442-3494)
-    if self.buckets and step % self.preconditioning_compute_steps == 0:
+    # (2) preconditioners (DS:3648 -> DS:3442-3494), optionally on the schedule of DS:2909-2934
+    pcs = self.preconditioning_compute_steps
+    if (self.decay_preconditioning_compute_steps and self.end_preconditioning_compute_steps and
+        callable(self.learning_rate)):
+      pcs = preconditioning_compute_steps_schedule(
+          self.learning_rate, self.preconditioning_compute_steps,
+          self.end_preconditioning_compute_steps, step)
+    if self.buckets and step % pcs == 0:
       self._compute_preconditioners(step)
     # (3) transform (DS:3650 -> DS:3496-3625)
     self._apply_preconditioners()
-    updates = []
     lr = self.learning_rate(step) if callable(self.learning_rate) else self.learning_rate
-    for plan, g, st, p in zip(self.plans, g_leaves, s_leaves, p_leaves):
-      updates.append(self._transform_grad(plan, g, st, p, step, float(lr)))
+    ubuf = self._transform_all(step, float(lr))
+    updates = []
+    for plan, g in zip(self.plans, g_leaves):
+      u = ubuf[plan.offset:plan.offset + plan.numel].view(plan.shape)
+      updates.append(u if g.dtype == torch.float32 else u.to(g.dtype))
     return (_tree_unflatten(self.treedef, updates),
-            ShampooState(step + 1, state.stats))
+            ShampooState(step + 1, _tree_unflatten(self.treedef, self._own_leaves)))
 
   def _flatten_stats(self, stats_tree):
     out = []
@@ -725,17 +935,13 @@ class _Shampoo:
       self._stat_tc_fused.run()
     if self.quantize_second_moment:  # from_float (DS:2654)
       for bk in self.buckets.values():
+        q, d, b = bk.qstats
         if bk.fused_quant:
-          q, d, b = bk.qstats
           ops.quantize_from_colmax(bk.stats, bk.colmax, self.qdt_second, q, d, b)
         else:
-          bk.qstats[0], bk.qstats[1], bk.qstats[2] = self._requant(bk.stats, bk.qstats)
+          ops.quantize(bk.stats, self.qdt_second, True, out=(q, d, b))
 
-  def _requant(self, x, dst):
-    q, d, b = ops.quantize(x, self.qdt_second, True)
-    dst[0].copy_(q); dst[1].copy_(d); dst[2].copy_(b)  # keep state views alive
-    return dst[0], dst[1], dst[2]
-
+  # ---- preconditioners -------------------------------------------------------
   def _compute_preconditioners(self, step=0):
     world, rank = self._world()
     if any(bk.compressed for bk in self.buckets.values()):
@@ -743,29 +949,201 @@ class _Shampoo:
         self._fd_update(step, world, rank)
       else:
         self._low_rank_update(world, rank)
-    for s, bk in self.buckets.items():
-      if bk.compressed:
-        continue
-      if self.quantize_second_moment:
-        q, d, b = bk.qstats
-        ops.dequantize(q, d, b, True, out=bk.stats)
-      roots, metrics = self._roots_sharded(bk, world, rank)
-      self.metrics[s].copy_(metrics)
-      if self.quantize_second_moment:
-        # DS:2746-2772 requantise the new root, DS:3183-3208 select per triple
-        q, d, b = ops.quantize(roots, self.qdt_second, True)
-        err = metrics[:, 0]
-        bad = torch.isnan(err) | (err >= self.inverse_failure_threshold)
-        oq, od, ob = bk.qprecs
-        oq.copy_(torch.where(bad[:, None, None], oq, q))
-        od.copy_(torch.where(bad[:, None], od, d))
-        ob.copy_(torch.where(bad[:, None], ob, b))
+    full = [bk for _, bk in sorted(self.buckets.items()) if not bk.compressed]
+    if not full:
+      return
+    if self.eigh:
+      for bk in full:
+        self._eigh_roots(bk, world, rank)
+      return
+    self._newton_roots(full, world, rank)
+
+  def _padded_size(self, s):
+    """Size of the problem a statistic of size ``s`` is solved in.  The reference pads every
+    statistic to the largest block (DS:2841-2843, masked by DS:777-783); here only where it
+    pays: 1 x 1 statistics take the iterative path like upstream (DS:850-855 only fires when
+    max_size == 1) as [[s, 0], [0, 0]] with padding_start = 1, and sizes such as 1000 or 576
+    are embedded in the next multiple of 128 so that they run on the tcgen05 engine."""
+    if s == 1 and max(self.buckets) > 1:
+      return 2
+    if (s >= 256 and s % 128 != 0 and self.engine == _lib.PC_ENGINE_AUTO and
+        bool(_lib.load().pc_device_supports_tcgen05())):
+      return (s + 127) // 128 * 128
+    return s
+
+  def _build_root_jobs(self, full, world, rank):
+    """Partition + static buffers of the Newton-root solves (built once per world size)."""
+    costs = [(bk.size, [float(self._padded_size(bk.size)) ** 3 * newton_gemms_per_iteration(p)
+                        for p in bk.exponents]) for bk in full]
+    table = partition_statistics(costs, world)
+    dev = self.device
+    for bk in full:
+      s, sp = bk.size, self._padded_size(bk.size)
+      job = _RootJob()
+      job.world, job.sp = world, sp
+      owned = table[s]
+      job.mine = owned[rank]
+      job.cnt = max(len(o) for o in owned)  # local batch (fillers pad the shorter ranks)
+      job.in_place = world == 1 and sp == s
+      exps = np.ones(job.cnt, dtype=np.int32)
+      pads = np.zeros(job.cnt, dtype=np.int32)
+      exps[:len(job.mine)] = bk.exps_host[job.mine]
+      pads[:len(job.mine)] = s
+      job.exps_host = exps
+      job.exps = torch.from_numpy(exps).to(dev)
+      job.pads = torch.from_numpy(pads).to(dev)
+      job.mine_idx = torch.tensor(job.mine, dtype=torch.int64, device=dev)
+      job.x = bk.stats if job.in_place else torch.zeros((job.cnt, sp, sp), dtype=torch.float32,
+                                                        device=dev)
+      job.ws = torch.empty(ops.root_workspace_bytes(job.cnt, sp, self.engine) + 256,
+                           dtype=torch.uint8, device=dev)
+      job.stream = torch.cuda.Stream(dev)
+      job.done = torch.cuda.Event()
+      qd = self.qdt_second
+      qbytes = {torch.int16: 2, torch.int8: 1}.get(qd, 4)
+      if world == 1:
+        job.roots = torch.empty((job.cnt, sp, sp), dtype=torch.float32, device=dev)
+        job.metrics = self.metrics[s] if not self.quantize_second_moment else torch.empty(
+            (job.cnt, 5), dtype=torch.float32, device=dev)
+        if self.quantize_second_moment:
+          job.q = torch.empty((job.cnt, s, s), dtype=qd, device=dev)
+          job.qd = torch.empty((job.cnt, s), dtype=torch.float32, device=dev)
+          job.qb = torch.empty((job.cnt, s), dtype=torch.float32, device=dev)
+          ar = torch.arange(job.cnt, device=dev)
+          job.sel = [(job.q, ar * (s * s * qbytes), s * s * qbytes, 0),
+                     (job.qd, ar * (s * 4), s * 4, 1), (job.qb, ar * (s * 4), s * 4, 2)]
+          job.met_off = ar * 5
+          job.dst_idx = ar.to(torch.int32)
       else:
-        lib = _lib.load()
-        _lib.check(lib.pc_select_preconditioners(
-            ctypes.c_void_p(roots.data_ptr()), ctypes.c_void_p(metrics.data_ptr()),
-            float(self.inverse_failure_threshold), ctypes.c_void_p(bk.precs.data_ptr()),
-            bk.count, s, s, s, s, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        # one packed payload per rank and bucket: [roots | metrics] in fp32, or
+        # [q | diagonal | bucket sizes | metrics] when the state is quantised (DS:3116-3122)
+        if self.quantize_second_moment:
+          sections = [("q", s * s * qbytes), ("d", s * 4), ("b", s * 4), ("m", 20)]
+        else:
+          sections = [("r", s * s * 4), ("m", 20)]
+        lay = gather_layout(owned, job.cnt, sections)
+        off, sec = lay["lbytes"], lay["sections"]
+        job.lbytes = off
+        job.send = torch.zeros(off, dtype=torch.uint8, device=dev)
+        job.recv = torch.empty((world, off), dtype=torch.uint8, device=dev)
+        job.recv_f32 = job.recv.view(-1).view(torch.float32)
+
+        def view(name, dtype, shape):
+          o, row = sec[name]
+          return job.send[o:o + job.cnt * row].view(dtype).view(shape)
+
+        job.metrics = view("m", torch.float32, (job.cnt, 5))
+        if self.quantize_second_moment:
+          job.roots = torch.empty((job.cnt, sp, sp), dtype=torch.float32, device=dev)
+          job.q = view("q", qd, (job.cnt, s, s))
+          job.qd = view("d", torch.float32, (job.cnt, s))
+          job.qb = view("b", torch.float32, (job.cnt, s))
+        elif sp == s:
+          job.roots = view("r", torch.float32, (job.cnt, s, s))
+        else:
+          job.roots = torch.empty((job.cnt, sp, sp), dtype=torch.float32, device=dev)
+          job.send_roots = view("r", torch.float32, (job.cnt, s, s))
+        job.dst_idx = torch.from_numpy(lay["dst_index"]).to(dev)
+        job.met_off = torch.from_numpy(lay["metrics_offset"]).to(dev)
+        job.sel = []
+        for k, name in enumerate(("q", "d", "b") if self.quantize_second_moment else ("r",)):
+          job.sel.append((job.recv, torch.from_numpy(lay["src_offset"][name]).to(dev),
+                          sec[name][1], k))
+      bk.job = job
+
+  def _newton_roots(self, full, world, rank):
+    """Coupled-Newton roots of every full statistic.  Each bucket (one statistic size) runs on
+    its own stream: the solver only enqueues (CUDA graph, device-side convergence), so the
+    buckets' power iterations / GEMM chains overlap on the GPU, and with more than one rank
+    each bucket's packed all-gather (DS:2876-2877) starts as soon as that bucket is done."""
+    if full[0].job is None or full[0].job.world != world:
+      self._build_root_jobs(full, world, rank)
+    import torch.distributed as dist
+    main = torch.cuda.current_stream(self.device)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    kw = dict(ridge_epsilon=self.matrix_epsilon,
+              relative_matrix_epsilon=self.relative_matrix_epsilon, engine=self.engine)
+    thr = float(self.inverse_failure_threshold)
+    # small buckets first: their all-gathers leave the NCCL queue before the big one arrives
+    for bk in sorted(full, key=lambda b: b.job.cnt * b.job.sp ** 3):
+      job, s = bk.job, bk.size
+      with torch.cuda.stream(job.stream):
+        job.stream.wait_event(fork)
+        if self.quantize_second_moment:
+          q, d, b = bk.qstats
+          ops.dequantize(q, d, b, True, out=bk.stats)
+        if not job.in_place and job.mine:
+          if job.sp == s:
+            torch.index_select(bk.stats, 0, job.mine_idx, out=job.x[:len(job.mine)])
+          else:
+            job.x[:len(job.mine), :s, :s].copy_(
+                bk.stats if world == 1 else bk.stats.index_select(0, job.mine_idx))
+        ops.matrix_inverse_pth_root_batched(
+            job.x, job.exps, None if job.in_place else job.pads, out=job.roots,
+            metrics_out=job.metrics, workspace=job.ws, ps_host=job.exps_host, **kw)
+        corner = job.roots if job.sp == s else job.roots[:, :s, :s]
+        if self.quantize_second_moment:
+          # DS:2746-2772: the new root is requantised by its owner; DS:3183-3208: select
+          ops.quantize(corner if job.sp == s else corner.contiguous(), self.qdt_second, True,
+                       out=(job.q, job.qd, job.qb))
+        elif world > 1 and job.sp != s:
+          job.send_roots.copy_(corner)
+        if world > 1:
+          dist.all_gather_into_tensor(job.recv.view(-1), job.send, group=self.process_group)
+        if world == 1 and not self.quantize_second_moment:
+          lib = _lib.load()
+          _lib.check(lib.pc_select_preconditioners(
+              ctypes.c_void_p(job.roots.data_ptr()), ctypes.c_void_p(job.metrics.data_ptr()), thr,
+              ctypes.c_void_p(bk.precs.data_ptr()), bk.count, job.sp, job.sp, s, s,
+              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        else:
+          mbase = job.recv_f32 if world > 1 else job.metrics.view(-1)
+          dsts = bk.qprecs if self.quantize_second_moment else [bk.precs]
+          for src, src_off, row, k in job.sel:
+            ops.select_scatter(src, src_off, mbase, job.met_off, job.dst_idx, thr, dsts[k], row,
+                               self.metrics[s] if k == 0 else None)
+        job.done.record(job.stream)
+    for bk in full:
+      main.wait_event(bk.job.done)
+
+  def _eigh_roots(self, bk, world, rank):
+    """`eigh=True`: matrix_inverse_pth_root_eigh for every statistic (DS:2677-2684)."""
+    s = bk.size
+    kw = dict(ridge_epsilon=self.matrix_epsilon,
+              relative_matrix_epsilon=self.relative_matrix_epsilon)
+    if s > ops.EIGH_MAX_DIM:
+      raise NotImplementedError(
+          f"eigh=True supports statistics up to {ops.EIGH_MAX_DIM} x {ops.EIGH_MAX_DIM}, got {s}")
+    if self.quantize_second_moment:
+      q, d, b = bk.qstats
+      ops.dequantize(q, d, b, True, out=bk.stats)
+    if world == 1:
+      roots, metrics = ops.matrix_inverse_pth_root_eigh_batched(bk.stats, bk.exps, None, **kw)
+    else:
+      roots, metrics = sharded_inverse_pth_roots(
+          bk.stats, bk.exps, world, rank, self.process_group,
+          root_fn=ops.matrix_inverse_pth_root_eigh_batched, **kw)
+    self.metrics[s].copy_(metrics)
+    self._select(bk, roots, metrics)
+
+  def _select(self, bk, roots, metrics):
+    """Failure fallback of DS:2936-2950 (quantised: DS:3183-3208) for a whole bucket."""
+    s = bk.size
+    if self.quantize_second_moment:
+      q, d, b = ops.quantize(roots, self.qdt_second, True)
+      err = metrics[:, 0]
+      bad = torch.isnan(err) | (err >= self.inverse_failure_threshold)
+      oq, od, ob = bk.qprecs
+      oq.copy_(torch.where(bad[:, None, None], oq, q))
+      od.copy_(torch.where(bad[:, None], od, d))
+      ob.copy_(torch.where(bad[:, None], ob, b))
+      return
+    lib = _lib.load()
+    _lib.check(lib.pc_select_preconditioners(
+        ctypes.c_void_p(roots.data_ptr()), ctypes.c_void_p(metrics.data_ptr()),
+        float(self.inverse_failure_threshold), ctypes.c_void_p(bk.precs.data_ptr()),
+        bk.count, s, s, s, s, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
   def _fd_update(self, step, world, rank):
     """Sketchy branch of new_mi_pth_root (DS:2706-2738) for every compressed statistic.
@@ -837,53 +1215,6 @@ class _Shampoo:
       bk.packed.copy_(torch.where(bad[:, None, None], bk.packed, new))
       ops.low_rank_to_dense(bk.packed, abs(r), out=bk.precs)
 
-  def _roots_sharded(self, bk, world, rank):
-    kw = dict(ridge_epsilon=self.matrix_epsilon,
-              relative_matrix_epsilon=self.relative_matrix_epsilon, engine=self.engine)
-    if self.eigh:  # `eigh=True`: matrix_inverse_pth_root_eigh for every statistic (DS:2677-2684)
-      if bk.size > 512:
-        raise NotImplementedError(
-            f"eigh=True supports statistics up to 512 x 512 (one Jacobi solve), got {bk.size}")
-      if world == 1:
-        return ops.matrix_inverse_pth_root_eigh_batched(bk.stats, bk.exps, None,
-                                                        out=bk.roots_tmp, **kw)
-      return sharded_inverse_pth_roots(bk.stats, bk.exps, world, rank, self.process_group,
-                                       root_fn=ops.matrix_inverse_pth_root_eigh_batched, **kw)
-    if bk.size == 1 and max(self.buckets) > 1:
-      # The reference pads every statistic to the largest block (DS:2841-2843), so a
-      # 1x1 statistic goes through the coupled iteration, not the scalar closed
-      # form (DS:850-855 only triggers when max_size == 1).  Mirror that with the
-      # smallest padded problem: [[s, 0], [0, 1]], padding_start = 1.
-      padded = torch.eye(2, dtype=torch.float32, device=self.device).repeat(bk.count, 1, 1)
-      padded[:, 0, 0] = bk.stats[:, 0, 0]
-      pads = torch.ones(bk.count, dtype=torch.int32, device=self.device)
-      if world == 1:
-        r, m = ops.matrix_inverse_pth_root_batched(padded, bk.exps, pads, **kw)
-      else:
-        r, m = sharded_inverse_pth_roots(padded, bk.exps, world, rank, self.process_group,
-                                         pads=pads, **kw)
-      return r[:, :1, :1].contiguous(), m
-    s = bk.size
-    if (s >= 256 and s % 128 != 0 and self.engine == _lib.PC_ENGINE_AUTO and
-        bool(_lib.load().pc_device_supports_tcgen05())):
-      # Sizes such as 1000 or 576 are embedded in the next multiple of 128 with
-      # padding_start = size -- exactly the reference's own pad-to-max convention
-      # (DS:2841-2843, masked by DS:777-783) -- so they run on the tcgen05 engine instead
-      # of the CUDA-core one.
-      sp = (s + 127) // 128 * 128
-      if getattr(bk, "padded", None) is None:
-        bk.padded = torch.zeros((bk.count, sp, sp), dtype=torch.float32, device=self.device)
-        bk.pads = torch.full((bk.count,), s, dtype=torch.int32, device=self.device)
-      bk.padded[:, :s, :s].copy_(bk.stats)
-      if world == 1:
-        r, m = ops.matrix_inverse_pth_root_batched(bk.padded, bk.exps, bk.pads, **kw)
-      else:
-        r, m = sharded_inverse_pth_roots(bk.padded, bk.exps, world, rank, self.process_group,
-                                         pads=bk.pads, **kw)
-      return r[:, :s, :s].contiguous(), m
-    if world == 1:
-      return ops.matrix_inverse_pth_root_batched(bk.stats, bk.exps, None, out=bk.roots_tmp, **kw)
-    return sharded_inverse_pth_roots(bk.stats, bk.exps, world, rank, self.process_group, **kw)
 
   def _apply_preconditioners(self):
     if self.quantize_second_moment:  # DS:3556 _maybe_dequantize_preconditioners
@@ -896,40 +1227,38 @@ class _Shampoo:
       if self._apply_tc[j] is not None:
         self._apply_tc[j].run()
 
-  def _transform_grad(self, plan, grad, st, param, step, lr):
-    gflat = self.gbuf[plan.offset:plan.offset + plan.numel]
-    pg = None if plan.skip else self.pgbuf[plan.offset:plan.offset + plan.numel]
-    mdt = st.momentum.quantized_dtype
-    if mdt == torch.float32:
-      mom, dmom = st.momentum.quantized, st.diagonal_momentum.quantized
-    else:  # int8 momenta: to_float, update, requantise (DS:3582-3586, DS:3620-3621)
-      mom, dmom = st.momentum.to_float(), st.diagonal_momentum.to_float()
-    diag = st.diagonal_statistics.quantized if self._graft_has_diag() else None
-    update = torch.empty_like(grad, dtype=torch.float32)
+  def _transform_all(self, step, lr):
+    """Grafting + momentum tail of every parameter (DS:3496-3625) as ONE grouped call over the
+    flat buffers; returns the flat update buffer (a fresh one per step: the returned updates
+    stay valid after the next ``update``)."""
     key = (step >= self.start_preconditioning_step, lr)
     if getattr(self, "_graft_opt_key", None) != key:  # the options are the same for every parameter
       self._graft_opt_key = key
       self._graft_opt = ops.make_graft_options(
-        beta1=float(self.beta1), beta2=float(self.beta2), graft_type=int(self.graft_type),
-        diagonal_epsilon=float(self.diagonal_epsilon), weight_decay=float(self.weight_decay),
-        learning_rate=lr, nesterov=int(bool(self.nesterov)),
-        moving_average_for_momentum=int(bool(self.moving_average_for_momentum)),
-        decoupled_learning_rate=int(bool(self.decoupled_learning_rate)),
-        decoupled_weight_decay=int(bool(self.decoupled_weight_decay)),
-        run_shampoo=int(step >= self.start_preconditioning_step),
-        clip_by_scaled_gradient_norm=float(self.clip_by_scaled_gradient_norm or 0.0))
-    opt = self._graft_opt
-    if self.weight_decay != 0 and param is None:
-      raise ValueError("weight_decay needs params")
-    ops.graft_momentum(gflat, None if param is None else param.contiguous().reshape(-1), pg,
-                       None if diag is None else diag.reshape(-1), dmom.reshape(-1),
-                       mom.reshape(-1), update.reshape(-1), opt)
-    if mdt != torch.float32:
-      for qv, val in ((st.momentum, mom), (st.diagonal_momentum, dmom)):
-        q, _, b = QuantizedValue.quantize(val, mdt)
+          beta1=float(self.beta1), beta2=float(self.beta2), graft_type=int(self.graft_type),
+          diagonal_epsilon=float(self.diagonal_epsilon), weight_decay=float(self.weight_decay),
+          learning_rate=lr, nesterov=int(bool(self.nesterov)),
+          moving_average_for_momentum=int(bool(self.moving_average_for_momentum)),
+          decoupled_learning_rate=int(bool(self.decoupled_learning_rate)),
+          decoupled_weight_decay=int(bool(self.decoupled_weight_decay)),
+          run_shampoo=int(step >= self.start_preconditioning_step),
+          clip_by_scaled_gradient_norm=float(self.clip_by_scaled_gradient_norm or 0.0))
+    quantised = [(pl, st) for pl, st in zip(self.plans, self._own_leaves)
+                 if pl.mdt != torch.float32]
+    for pl, st in quantised:  # int8 momenta: to_float into the flat scratch (DS:3582-3586)
+      seg = slice(pl.offset, pl.offset + pl.numel)
+      for qv, buf in ((st.momentum, self.mbuf), (st.diagonal_momentum, self.dmbuf)):
+        buf[seg].copy_(qv.to_float().reshape(-1))
+    ubuf = torch.empty(self.total, dtype=torch.float32, device=self.device)
+    self._graft_group.run(self.gbuf, self.pbuf, self.pgbuf, self.dsbuf, self.dmbuf, self.mbuf,
+                          ubuf, self._graft_opt)
+    for pl, st in quantised:  # requantise (DS:3620-3621)
+      seg = slice(pl.offset, pl.offset + pl.numel)
+      for qv, buf in ((st.momentum, self.mbuf), (st.diagonal_momentum, self.dmbuf)):
+        q, _, b = QuantizedValue.quantize(buf[seg].view(pl.shape), pl.mdt)
         qv.quantized.copy_(q)
         qv.bucket_size.copy_(b)
-    return update
+    return ubuf
 
 
 def sharded_inverse_pth_roots(stats, exps, world, rank, group, root_fn=None, pads=None, **kw):
@@ -987,6 +1316,15 @@ def sharded_fd_updates(grams, prevs, exps, pads, r, world, rank, group, fd_fn=No
   return gathered[:n_stats]
 
 
+
+
+class ShampooTransformation(GradientTransformation):
+  """``GradientTransformation(init, update)`` plus the state hand-over of this implementation:
+  ``export_state(state)`` (detached deep copy, e.g. for a checkpoint) and
+  ``import_state(state)`` (copy a foreign state into the optimizer's device buffers)."""
+  pass
+
+
 def distributed_shampoo(
     learning_rate,
     block_size,
@@ -1042,10 +1380,19 @@ def distributed_shampoo(
   are partitioned over the ranks of ``process_group`` (default world) of an
   initialised ``torch.distributed`` NCCL group and the roots are all-gathered.
   ``precision`` / ``tensordot_precision`` are accepted and ignored: GEMMs are fp32
-  (CUDA cores) or fp32-accurate split-bf16 (tcgen05).
+  (CUDA cores) or fp32-accurate split-fp16 / split-bf16 (tcgen05).
+
+  State semantics: ``init`` returns a ``ShampooState`` whose tensors are views of the
+  optimizer's device buffers and ``update`` advances them in place (the state it returns
+  aliases the same buffers).  Passing any OTHER state to ``update`` -- a restored checkpoint, an
+  ``export_state`` copy, a deep copy -- is supported: it is copied into the buffers first.
+  The returned object also carries ``export_state(state)`` and ``import_state(state)``.
   """
   del precision, tensordot_precision, lobpcg_max_iter, statistics_partition_spec
-  del preconditioner_partition_spec, num_devices_for_pjit, generate_fd_metrics
+  del preconditioner_partition_spec, num_devices_for_pjit
+  if generate_fd_metrics and frequent_directions:  # DS:2026: ignored without frequent_directions
+    raise NotImplementedError(
+        "generate_fd_metrics (FDDiagnostics, DS:197-335) is not built in the B200 hot path")
   if reset_preconditioner and not frequent_directions:  # DS:2019-2020
     raise ValueError("reset_preconditioner=True requries frequent_directions")
   reset_frequency = None
@@ -1062,10 +1409,11 @@ def distributed_shampoo(
                      f"statistics_compute_steps ({statistics_compute_steps}) "
                      "to equal != preconditioning_compute_steps "
                      f"({preconditioning_compute_steps})")
+  if exponent_override and not 1 <= int(exponent_override) <= 16:
+    raise ValueError(f"exponent_override={exponent_override} is outside [1, 16], the range of "
+                     "the Newton step programs (pc_inverse_pth_root_batched)")
   for name, val in (("lobpcg_topk_precondition", lobpcg_topk_precondition),
-                    ("shard_optimizer_states", shard_optimizer_states),
-                    ("decay_preconditioning_compute_steps",
-                     decay_preconditioning_compute_steps and end_preconditioning_compute_steps)):
+                    ("shard_optimizer_states", shard_optimizer_states)):
     if val:
       raise NotImplementedError(
           f"{name} is not built in the B200 hot path yet (see DESIGN.md, out of scope table)")
@@ -1085,5 +1433,8 @@ def distributed_shampoo(
                  compression_rank, skip_preconditioning_rank_lt, decoupled_learning_rate,
                  decoupled_weight_decay, generate_training_metrics, engine, process_group,
                  frequent_directions, reuse_preconditioner, reset_frequency, average_grad,
-                 bool(eigh))
-  return GradientTransformation(opt.init, opt.update)
+                 bool(eigh), bool(decay_preconditioning_compute_steps),
+                 end_preconditioning_compute_steps)
+  tx = ShampooTransformation(opt.init, opt.update)
+  tx.export_state, tx.import_state = opt.export_state, opt.import_state
+  return tx

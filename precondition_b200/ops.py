@@ -52,39 +52,89 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
   return ws
 
 
+def _as_i32_device(values, dev):
+  """(device tensor, host numpy copy or None) of an exponent / padding vector."""
+  if isinstance(values, torch.Tensor):
+    host = None if values.is_cuda else values.to(torch.int32).numpy()
+    return values.to(device=dev, dtype=torch.int32).contiguous(), host
+  host = np.ascontiguousarray(np.asarray(values, dtype=np.int32))
+  return torch.from_numpy(host).to(dev), host
+
+
 def matrix_inverse_pth_root_batched(
     xs: torch.Tensor, ps, padding_starts=None, ridge_epsilon: float = 1e-6,
     error_tolerance: float = 1e-6, num_iters: int = 100,
     relative_matrix_epsilon: bool = True, engine: int = _lib.PC_ENGINE_AUTO,
-    out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-  """Batched ``(A + eps I)^(-1/p)``; returns (roots [b,n,n], metrics [b,5])."""
+    out: Optional[torch.Tensor] = None, metrics_out: Optional[torch.Tensor] = None,
+    workspace: Optional[torch.Tensor] = None,
+    ps_host=None) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Batched ``(A + eps I)^(-1/p)``; returns (roots [b,n,n], metrics [b,5]).
+
+  The call only enqueues (CUDA graph with a device-driven Newton loop, see
+  ``pc_inverse_pth_root_enqueue``).  ``ps_host`` (or ``ps`` given as a list / CPU tensor) tells
+  the host the exponents without a device read-back.  ``workspace``: private scratch for calls
+  that run concurrently on different streams (default: one shared buffer per device, which
+  serialises through stream order only on ONE stream)."""
   global gpu_launches
   lib = _lib.load()
   _require_cuda(xs)
-  assert xs.dtype == torch.float32 and xs.dim() == 3 and xs.shape[1] == xs.shape[2]
+  if xs.dtype != torch.float32 or xs.dim() != 3 or xs.shape[1] != xs.shape[2]:
+    raise TypeError("statistics must be a float32 [batch, n, n] tensor")
   b, n = xs.shape[0], xs.shape[1]
   dev = xs.device
-  ps_t = torch.as_tensor(ps, dtype=torch.int32).to(dev).contiguous()
+  ps_t, host = _as_i32_device(ps, dev)
+  if ps_host is None:
+    ps_host = host
   pads_t = None
   if padding_starts is not None:
-    pads_t = torch.as_tensor(padding_starts, dtype=torch.int32).to(dev).contiguous()
+    pads_t, _ = _as_i32_device(padding_starts, dev)
   roots = out if out is not None else torch.empty_like(xs)
-  metrics = torch.empty((b, _lib.PC_NUM_METRICS), dtype=torch.float32, device=dev)
+  metrics = metrics_out if metrics_out is not None else torch.empty(
+      (b, _lib.PC_NUM_METRICS), dtype=torch.float32, device=dev)
   if b == 0:
     return roots, metrics
+  hp = None
+  if ps_host is not None:
+    ps_host = np.ascontiguousarray(np.asarray(ps_host, dtype=np.int32))
+    assert ps_host.shape == (b,)
+    hp = ctypes.c_void_p(ps_host.ctypes.data)
   opt = _lib.RootOptions()
   lib.pc_root_options_default(ctypes.byref(opt))
   opt.ridge_epsilon, opt.error_tolerance = ridge_epsilon, error_tolerance
   opt.num_iters, opt.relative_matrix_epsilon = num_iters, int(relative_matrix_epsilon)
   opt.engine = engine
   nbytes = lib.pc_inverse_pth_root_workspace_bytes(b, n, engine)
-  ws = _workspace(nbytes, dev)
+  ws = workspace if workspace is not None else _workspace(nbytes, dev)
+  if ws.numel() < nbytes:
+    raise ValueError(f"workspace too small: {ws.numel()} < {nbytes}")
   with torch.cuda.device(dev):
-    _lib.check(lib.pc_inverse_pth_root_batched(
-        _ptr(xs), _ptr(ps_t), _ptr(pads_t), b, n, ctypes.byref(opt), _ptr(roots),
+    _lib.check(lib.pc_inverse_pth_root_enqueue(
+        _ptr(xs), _ptr(ps_t), hp, _ptr(pads_t), b, n, ctypes.byref(opt), _ptr(roots),
         _ptr(metrics), _ptr(ws), ws.numel(), ctypes.c_void_p(_stream())))
   gpu_launches += 1
   return roots, metrics
+
+
+def root_workspace_bytes(batch: int, n: int, engine: int = _lib.PC_ENGINE_AUTO) -> int:
+  return int(_lib.load().pc_inverse_pth_root_workspace_bytes(batch, n, engine))
+
+
+def select_scatter(src: torch.Tensor, src_off: torch.Tensor, metrics_base: torch.Tensor,
+                   met_off: torch.Tensor, dst_idx: torch.Tensor, threshold: float,
+                   dst: torch.Tensor, row_bytes: int, metrics_dst: Optional[torch.Tensor]):
+  """``pc_select_scatter``: gathered rows -> state rows with the failure fallback of
+  DS:2936-2950 (index arrays are device tensors: int64 byte / element offsets, int32 rows)."""
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(src, src_off, metrics_base, met_off, dst_idx, dst, metrics_dst)
+  assert src_off.dtype == torch.int64 and met_off.dtype == torch.int64
+  assert dst_idx.dtype == torch.int32 and metrics_base.dtype == torch.float32
+  with torch.cuda.device(dst.device):
+    _lib.check(lib.pc_select_scatter(
+        _ptr(src), _ptr(src_off), _ptr(metrics_base), _ptr(met_off), _ptr(dst_idx),
+        float(threshold), _ptr(dst), int(row_bytes), _ptr(metrics_dst), int(dst_idx.numel()),
+        ctypes.c_void_p(_stream())))
+  gpu_launches += 1
 
 
 def fd_update_root_batched(
@@ -247,28 +297,39 @@ def power_iteration(xs: torch.Tensor, padding_starts=None, num_iters: int = 100,
   return lam, its
 
 
-def quantize(x: torch.Tensor, qdtype: torch.dtype, extract_diagonal: bool = False):
+EIGH_MAX_DIM = 512  # largest statistic of the Cholesky + Jacobi eigh pipeline (one cluster)
+
+
+def quantize(x: torch.Tensor, qdtype: torch.dtype, extract_diagonal: bool = False, out=None):
   """QU:49-95 on a [batch, rows, cols] (or [rows, cols]) tensor.
 
-  Returns (quantized, diagonal or None, bucket_size or None)."""
+  Returns (quantized, diagonal or None, bucket_size or None); ``out`` = (q, diag, bucket)
+  tensors to write into (int16 / int8 only)."""
   lib = _lib.load()
   _require_cuda(x)
+  if x.dtype != torch.float32:
+    raise TypeError(f"quantize expects float32, got {x.dtype}")
   squeeze = x.dim() == 2
   xb = x.unsqueeze(0) if squeeze else x
   b, rows, cols = xb.shape
   if qdtype == torch.float32:
     return x, None, None
-  q = torch.empty(xb.shape, dtype=qdtype, device=x.device)
   diag = bucket = None
-  if qdtype != torch.bfloat16:
-    bucket = torch.empty((b, cols), dtype=torch.float32, device=x.device)
-    if extract_diagonal:
-      diag = torch.empty((b, rows), dtype=torch.float32, device=x.device)
+  if out is not None:
+    q, diag, bucket = out
+    _require_cuda(q, diag, bucket)
+    assert q.dtype == qdtype and q.numel() == xb.numel()
+  else:
+    q = torch.empty(xb.shape, dtype=qdtype, device=x.device)
+    if qdtype != torch.bfloat16:
+      bucket = torch.empty((b, cols), dtype=torch.float32, device=x.device)
+      if extract_diagonal:
+        diag = torch.empty((b, rows), dtype=torch.float32, device=x.device)
   with torch.cuda.device(x.device):
     _lib.check(lib.pc_quantize_batched(_ptr(xb), b, rows, cols, _QDT[qdtype],
                                        int(extract_diagonal), _ptr(q), _ptr(diag),
                                        _ptr(bucket), ctypes.c_void_p(_stream())))
-  if squeeze:
+  if squeeze and out is None:
     q = q[0]
     diag = None if diag is None else diag[0]
     bucket = None if bucket is None else bucket[0]
@@ -431,6 +492,9 @@ def graft_momentum(grad, param, precond_grad, diagonal_statistics, diagonal_mome
   lib = _lib.load()
   _require_cuda(grad, param, precond_grad, diagonal_statistics, diagonal_momentum, momentum,
                 update)
+  for t in (grad, param, precond_grad, diagonal_statistics, diagonal_momentum, momentum, update):
+    if t is not None and t.dtype != torch.float32:
+      raise TypeError(f"pc_graft_momentum works on float32 tensors, got {t.dtype}")
   numel = grad.numel()
   nbytes = lib.pc_graft_momentum_workspace_bytes(numel)
   ws = _workspace(nbytes, grad.device)
@@ -440,3 +504,54 @@ def graft_momentum(grad, param, precond_grad, diagonal_statistics, diagonal_mome
         _ptr(diagonal_momentum), _ptr(momentum), _ptr(update), numel, ctypes.byref(opt),
         _ptr(ws), ws.numel(), ctypes.c_void_p(_stream())))
   gpu_launches += 1
+
+
+class GraftGroup:
+  """Static segment table for ``pc_graft_momentum_grouped``: the tail of ``_transform_grad``
+  (DS:3496-3625) for every parameter in a fixed number of launches.  ``segments`` is a list
+  of (offset, numel, has_precond) into the optimizer's flat buffers."""
+
+  def __init__(self, segments, device):
+    lib = _lib.load()
+    chunk = int(lib.pc_graft_group_chunk_elems())
+    segs, chunk_seg, first = [], [], 0
+    for i, (off, numel, has_precond) in enumerate(segments):
+      if numel <= 0:
+        continue
+      assert off % 4 == 0, "segments must be 16-byte aligned"
+      n = (numel + chunk - 1) // chunk
+      sg = _lib.GraftSegment()
+      sg.offset, sg.numel, sg.first_chunk, sg.nchunks = off, numel, first, n
+      sg.has_precond = int(bool(has_precond))
+      segs.append(sg)
+      chunk_seg.extend([len(segs) - 1] * n)
+      first += n
+    self.count, self.total_chunks = len(segs), first
+    self.device = device
+    if self.count:
+      arr = (_lib.GraftSegment * self.count)(*segs)
+      self.segs = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+      self.chunk_seg = torch.tensor(chunk_seg, dtype=torch.int32, device=device)
+      nbytes = lib.pc_graft_momentum_grouped_workspace_bytes(self.count, self.total_chunks)
+      self.ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+
+  def run(self, grad, param, precond_grad, diagonal_statistics, diagonal_momentum, momentum,
+          update, opt: _lib.GraftOptions):
+    """All arguments are the flat fp32 buffers (param / precond_grad / diagonal_statistics
+    may be None); momenta, diagonal statistics and update are written in place."""
+    global gpu_launches
+    if not self.count:
+      return
+    lib = _lib.load()
+    _require_cuda(grad, param, precond_grad, diagonal_statistics, diagonal_momentum, momentum,
+                  update)
+    for t in (grad, param, precond_grad, diagonal_statistics, diagonal_momentum, momentum, update):
+      if t is not None and t.dtype != torch.float32:
+        raise TypeError("pc_graft_momentum_grouped works on float32 buffers")
+    with torch.cuda.device(self.device):
+      _lib.check(lib.pc_graft_momentum_grouped(
+          _ptr(self.segs), _ptr(self.chunk_seg), self.count, self.total_chunks, _ptr(grad),
+          _ptr(param), _ptr(precond_grad), _ptr(diagonal_statistics), _ptr(diagonal_momentum),
+          _ptr(momentum), _ptr(update), ctypes.byref(opt), _ptr(self.ws), self.ws.numel(),
+          ctypes.c_void_p(_stream())))
+    gpu_launches += 1

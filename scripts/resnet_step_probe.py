@@ -20,17 +20,14 @@ def timed(f, n=3):
   for _ in range(n): f()
   torch.cuda.synchronize(); return (time.time() - t0) / n * 1e3
 def stage():
-  for plan, g in zip(sh.plans, grads):
-    sh.gbuf[plan.offset:plan.offset + plan.numel].copy_(g.reshape(-1))
+  torch._foreach_copy_(sh._gviews, [g.reshape(-1) for g in grads])
 def graft():
-  s_leaves = sh._flatten_stats(state.stats)
-  for plan, g, st, p in zip(sh.plans, grads, s_leaves, params):
-    sh._transform_grad(plan, g, st, p, 10, 0.1)
+  sh._transform_all(10, 0.1)
 print(f"total {timed(lambda: opt.update(grads, state, params)):.2f} ms | stage {timed(stage):.2f} stats {timed(sh._update_statistics):.2f} "
       f"roots {timed(lambda: sh._compute_preconditioners(10)):.2f} apply {timed(sh._apply_preconditioners):.2f} graft {timed(graft):.2f}")
 for s, bk in sorted(sh.buckets.items()):
-  t = timed(lambda: sh._roots_sharded(bk, 1, 0), 2)
-  print(f"   bucket {s:5d} x {bk.count:3d}: roots {t:7.2f} ms")
+  t = timed(lambda: sh._newton_roots([bk], 1, 0), 2)
+  print(f"   bucket {s:5d} x {bk.count:3d} (solved as {bk.job.sp}): roots alone {t:7.2f} ms")
 from torch.profiler import profile, ProfilerActivity
 for name, f in (("stats", sh._update_statistics), ("apply", sh._apply_preconditioners)):
   torch.cuda.synchronize()

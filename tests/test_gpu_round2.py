@@ -1,0 +1,315 @@
+"""GPU tests of the round-2 paths: graph-mode (enqueue-only) root solver against the host-polled
+loop, the grouped grafting kernel against the per-parameter one, pc_select_scatter, optimizer
+state hand-over (export / import), non-contiguous and half-precision parameters, and the
+block-sharded optimizer step against the unsharded one (two ranks over gloo on one GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import numerics as N
+from oracle.gen_golden import ema_statistics, gen_symmetric_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def _spd_batch(n, count, seed):
+  rng = np.random.default_rng(seed)
+  return np.stack([gen_symmetric_matrix(rng, n, 1e3) if i % 2 else ema_statistics(rng, n, 2 * n)
+                   for i in range(count)]).astype(np.float32)
+
+
+@pytest.mark.parametrize("n", [64, 128, 256])
+def test_root_graph_mode_equals_host_polled(n):
+  """The CUDA-graph driver (device-side WHILE loop) and the host-polled driver run the same
+  kernels on the same per-matrix state machine: bitwise identical roots and metrics."""
+  from precondition_b200 import _lib, ops
+  xs = torch.as_tensor(_spd_batch(n, 6, n)).cuda()
+  xs[5] = 0.0  # a singular statistic: exercises the retry path of DS:858-885
+  ps = [4, 2, 6, 8, 4, 4]
+  pads = [n, n, n - 3, n, 0, n]
+  assert _lib.load().pc_root_mode() == 1
+  r_graph, m_graph = ops.matrix_inverse_pth_root_batched(xs, ps, pads)
+  torch.cuda.synchronize()
+  os.environ["PC_ROOT_MODE"] = "poll"
+  try:
+    assert _lib.load().pc_root_mode() == 0
+    r_poll, m_poll = ops.matrix_inverse_pth_root_batched(xs, ps, pads)
+    torch.cuda.synchronize()
+  finally:
+    del os.environ["PC_ROOT_MODE"]
+  assert torch.equal(r_graph, r_poll)
+  assert torch.equal(m_graph.nan_to_num(-1.0), m_poll.nan_to_num(-1.0))
+  for b in (0, 1, 2):
+    want, wm = N.matrix_inverse_pth_root(xs[b].cpu().numpy(), ps[b], padding_start=pads[b])
+    rel = np.linalg.norm(r_graph[b].cpu().numpy() - want) / np.linalg.norm(want)
+    assert rel <= 1e-3 and float(m_graph[b, 1]) == wm.inverse_pth_root_iters
+
+
+def test_root_graph_is_cached_and_relaunchable():
+  """Same buffers -> the cached executable graph is re-launched and reads the NEW contents;
+  calls on different streams with private workspaces overlap and stay correct."""
+  from precondition_b200 import ops
+  n = 128
+  xs = torch.as_tensor(_spd_batch(n, 4, 1)).cuda()
+  ps = torch.tensor([4, 4, 2, 2], dtype=torch.int32, device="cuda")
+  out = torch.empty_like(xs)
+  met = torch.empty((4, 5), device="cuda")
+  r1 = ops.matrix_inverse_pth_root_batched(xs, ps, None, out=out, metrics_out=met,
+                                           ps_host=[4, 4, 2, 2])[0].clone()
+  xs.mul_(4.0)  # (4 A)^(-1/p) = 4^(-1/p) A^(-1/p)
+  r2 = ops.matrix_inverse_pth_root_batched(xs, ps, None, out=out, metrics_out=met,
+                                           ps_host=[4, 4, 2, 2])[0]
+  torch.cuda.synchronize()
+  scale = torch.tensor([4.0 ** -0.25] * 2 + [4.0 ** -0.5] * 2, device="cuda")[:, None, None]
+  err = ((r2 - r1 * scale).abs().amax((1, 2)) / r2.abs().amax((1, 2))).max()
+  assert float(err) <= 1e-4
+  # two independent calls on two streams, private workspaces
+  a, b = xs[:2].contiguous(), xs[2:].contiguous()
+  s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+  w1 = torch.empty(ops.root_workspace_bytes(2, n) + 256, dtype=torch.uint8, device="cuda")
+  w2 = torch.empty_like(w1)
+  torch.cuda.synchronize()
+  with torch.cuda.stream(s1):
+    ra, _ = ops.matrix_inverse_pth_root_batched(a, [4, 4], workspace=w1)
+  with torch.cuda.stream(s2):
+    rb, _ = ops.matrix_inverse_pth_root_batched(b, [2, 2], workspace=w2)
+  torch.cuda.synchronize()
+  assert torch.equal(ra, r2[:2]) and torch.equal(rb, r2[2:])
+
+
+def test_select_scatter_rows_and_failure_fallback():
+  from precondition_b200 import ops
+  dev = torch.device("cuda", 0)
+  rows, cnt, world = 5, 2, 3
+  owned = [[0, 3], [1, 4], [2]]
+  from precondition_b200.distributed_shampoo import gather_layout
+  lay = gather_layout(owned, cnt, [("r", 36), ("m", 20)])
+  recv = torch.zeros((world, lay["lbytes"]), dtype=torch.uint8, device=dev)
+  want = torch.arange(rows * 9, dtype=torch.float32, device=dev).reshape(rows, 9) + 1
+  ro, mo = lay["sections"]["r"][0], lay["sections"]["m"][0]
+  for r, o in enumerate(owned):
+    for l, i in enumerate(o):
+      recv[r, ro + l * 36:ro + (l + 1) * 36] = want[i].view(torch.uint8)
+      met = torch.tensor([0.5 if i == 3 else 1e-7, i, 1, 1, 1], dtype=torch.float32, device=dev)
+      recv[r, mo + l * 20:mo + (l + 1) * 20] = met.view(torch.uint8)
+  dst = torch.full((rows, 9), -7.0, device=dev)
+  mdst = torch.zeros((rows, 5), device=dev)
+  ops.select_scatter(recv, torch.from_numpy(lay["src_offset"]["r"]).to(dev),
+                     recv.view(-1).view(torch.float32),
+                     torch.from_numpy(lay["metrics_offset"]).to(dev),
+                     torch.from_numpy(lay["dst_index"]).to(dev), 0.1, dst, 36, mdst)
+  torch.cuda.synchronize()
+  keep = torch.tensor([True, True, True, False, True], device=dev)
+  assert torch.equal(dst[keep], want[keep])
+  assert float((dst[3] + 7.0).abs().max()) == 0.0  # failed root: old preconditioner kept
+  assert torch.equal(mdst[:, 1], torch.arange(rows, dtype=torch.float32, device=dev))
+
+
+@pytest.mark.parametrize("graft", [0, 1, 2, 3, 4, 5, 6])
+def test_grouped_graft_matches_per_parameter_kernel(graft):
+  from precondition_b200 import ops
+  dev = torch.device("cuda", 0)
+  gen = torch.Generator(device=dev).manual_seed(graft)
+  numels = [1, 37, 8192, 8193, 70001, 4]
+  skip = [False, True, False, False, False, True]
+  offs, total = [], 0
+  for n_ in numels:
+    offs.append(total)
+    total += (n_ + 31) // 32 * 32
+  mk = lambda scale=1.0: torch.randn(total, generator=gen, device=dev) * scale
+  grad, param, pg = mk(1e-2), mk(0.1), mk(3.0)
+  diag, dmom, mom = mk().abs(), mk(1e-2), mk(1e-2)
+  opt = ops.make_graft_options(
+      beta1=0.9, beta2=0.999, graft_type=graft, diagonal_epsilon=1e-10, weight_decay=1e-3,
+      learning_rate=0.1, nesterov=1, moving_average_for_momentum=int(graft % 2),
+      decoupled_learning_rate=int(graft % 3 != 0), decoupled_weight_decay=int(graft % 2 == 0),
+      run_shampoo=1, clip_by_scaled_gradient_norm=0.5 if graft in (3, 4) else 0.0)
+  want = [t.clone() for t in (diag, dmom, mom)]
+  want_u = torch.zeros(total, device=dev)
+  for o, n_, sk in zip(offs, numels, skip):
+    sl = slice(o, o + n_)
+    ops.graft_momentum(grad[sl], param[sl], None if sk else pg[sl], want[0][sl], want[1][sl],
+                       want[2][sl], want_u[sl], opt)
+  got = [t.clone() for t in (diag, dmom, mom)]
+  got_u = torch.zeros(total, device=dev)
+  group = ops.GraftGroup([(o, n_, not sk) for o, n_, sk in zip(offs, numels, skip)], dev)
+  group.run(grad, param, pg, got[0], got[1], got[2], got_u, opt)
+  torch.cuda.synchronize()
+  for o, n_ in zip(offs, numels):
+    sl = slice(o, o + n_)
+    for a, b in zip(got + [got_u], want + [want_u]):
+      assert torch.allclose(a[sl], b[sl], rtol=2e-5, atol=1e-12), (graft, n_)
+    pad = slice(o + n_, o + (n_ + 31) // 32 * 32)
+    assert float(got_u[pad].abs().sum()) == 0.0  # nothing written between segments
+
+
+def test_noncontiguous_and_half_precision_parameters():
+  """channels_last / transposed / bf16 leaves give the same updates as contiguous fp32 copies
+  (the optimizer state is float32 in flat row-major segments whatever the leaf layout is)."""
+  from precondition_b200 import distributed_shampoo as DS
+  dev = torch.device("cuda", 0)
+  gen = torch.Generator(device=dev).manual_seed(0)
+  conv = torch.randn(8, 4, 3, 3, generator=gen, device=dev).contiguous(
+      memory_format=torch.channels_last)
+  tied = torch.randn(24, 16, generator=gen, device=dev).t()  # transposed view
+  half = (torch.randn(16, 8, generator=gen, device=dev) * 0.1).to(torch.bfloat16)
+  assert not conv.is_contiguous() and not tied.is_contiguous()
+  params = [conv, tied, half]
+  ref_params = [p.float().contiguous() for p in params]
+  kw = dict(start_preconditioning_step=1, weight_decay=1e-2, graft_type=DS.GraftingType.RMSPROP)
+  opt, ref = DS.distributed_shampoo(0.1, 16, **kw), DS.distributed_shampoo(0.1, 16, **kw)
+  state, rstate = opt.init(params), ref.init(ref_params)
+  assert state.stats[2].momentum.quantized.dtype == torch.float32
+  for t in range(3):
+    grads = [torch.randn(p.shape, generator=gen, device=dev) * 1e-2 for p in params]
+    grads[0] = grads[0].contiguous(memory_format=torch.channels_last)
+    grads[2] = grads[2].to(torch.bfloat16)
+    upd, state = opt.update(grads, state, params)
+    rupd, rstate = ref.update([g.float().contiguous() for g in grads], rstate, ref_params)
+    torch.cuda.synchronize()
+    assert upd[2].dtype == torch.bfloat16 and upd[0].shape == conv.shape
+    for u, r in zip(upd[:2], rupd[:2]):
+      assert torch.equal(u, r), t
+    assert torch.equal(upd[2], rupd[2].to(torch.bfloat16))
+  for a, b in zip(state.stats, rstate.stats):
+    assert torch.equal(a.momentum.quantized.reshape(-1), b.momentum.quantized.reshape(-1))
+  with pytest.raises(TypeError):
+    DS.distributed_shampoo(0.1, 16).init([torch.zeros(4, 4, dtype=torch.int32, device=dev)])
+
+
+@pytest.mark.parametrize("variant", ["plain", "quantized", "sketchy"])
+def test_state_export_import_resume(variant):
+  """A state exported after step 3 and imported into a NEW optimizer continues exactly like
+  the original run; a foreign (exported) state passed straight to update() is adopted too."""
+  import copy
+  from precondition_b200 import distributed_shampoo as DS
+  dev = torch.device("cuda", 0)
+  shapes = [(32, 16), (16,), (3, 3, 8, 8)]
+  kw = dict(start_preconditioning_step=1, graft_type=DS.GraftingType.RMSPROP_NORMALIZED)
+  if variant == "quantized":
+    kw.update(best_effort_memory_usage_reduction=True, batch_axis_name="batch")
+  if variant == "sketchy":
+    kw.update(compression_rank=4, frequent_directions=True, reuse_preconditioner=True)
+  gen = torch.Generator(device=dev).manual_seed(7)
+  params = [torch.randn(s, generator=gen, device=dev) * 0.1 for s in shapes]
+  grads = [[torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes] for _ in range(6)]
+  opt = DS.distributed_shampoo(0.1, 16, **kw)
+  state = opt.init(params)
+  for t in range(3):
+    _, state = opt.update(grads[t], state, params)
+  saved = opt.export_state(state)
+  pickled = copy.deepcopy(saved)  # detached: survives deep copies / pickling
+  want = []
+  for t in range(3, 6):
+    u, state = opt.update(grads[t], state, params)
+    want.append([x.clone() for x in u])
+  # (a) a new optimizer resumes from the exported state
+  opt2 = DS.distributed_shampoo(0.1, 16, **kw)
+  opt2.init(params)
+  st2 = opt2.import_state(pickled)
+  assert int(st2.count) == 3
+  for t in range(3, 6):
+    u, st2 = opt2.update(grads[t], st2, params)
+    for a, b in zip(u, want[t - 3]):
+      assert torch.equal(a, b), (variant, t)
+  # (b) rollback on the SAME optimizer: the saved (foreign) state is adopted by update()
+  st = saved
+  for t in range(3, 6):
+    u, st = opt.update(grads[t], st, params)
+    for a, b in zip(u, want[t - 3]):
+      assert torch.equal(a, b), (variant, "rollback", t)
+  torch.cuda.synchronize()
+
+
+def test_preconditioning_schedule_skips_root_steps():
+  """decay_preconditioning_compute_steps (DS:2909-2934): with a decaying learning rate the
+  preconditioners are recomputed only on multiples of the scheduled period."""
+  from precondition_b200 import distributed_shampoo as DS
+  dev = torch.device("cuda", 0)
+  lr = lambda step: 0.1 * max(1.0 - step / 40.0, 0.0)
+  opt = DS.distributed_shampoo(lr, 16, start_preconditioning_step=1,
+                               preconditioning_compute_steps=1,
+                               decay_preconditioning_compute_steps=True,
+                               end_preconditioning_compute_steps=40)
+  gen = torch.Generator(device=dev).manual_seed(3)
+  params = [torch.randn(16, 16, generator=gen, device=dev)]
+  state = opt.init(params)
+  changed = []
+  for t in range(24):
+    before = state.stats[0].preconditioners[0].clone()
+    _, state = opt.update([torch.randn(16, 16, generator=gen, device=dev) * 1e-2], state, params)
+    changed.append(not torch.equal(before, state.stats[0].preconditioners[0]))
+  period = [DS.preconditioning_compute_steps_schedule(lr, 1, 40, t) for t in range(24)]
+  assert changed == [t % period[t] == 0 for t in range(24)], (changed, period)
+  assert period[0] == 1 and period[12] == 10 and period[23] == 20
+
+
+# ---------------------------------------------------------------------------
+# sharded optimizer step == unsharded step (two ranks over gloo, both on cuda:0)
+# ---------------------------------------------------------------------------
+def _free_port():
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    return s.getsockname()[1]
+
+
+def _sharded_worker(rank, world, port, variant, out):
+  import torch.distributed as dist
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from precondition_b200 import distributed_shampoo as DS
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    shapes = [(300, 64), (128, 128), (64,), (1, 7), (3, 3, 16, 16), (256, 128), (1,)]
+    kw = dict(start_preconditioning_step=1, merge_small_dims_block_size=512)
+    if variant == "quantized":
+      kw.update(best_effort_memory_usage_reduction=True)
+    gen = torch.Generator(device=dev).manual_seed(11)  # same data on both ranks
+    params = [torch.randn(s, generator=gen, device=dev) * 0.1 for s in shapes]
+    sharded = DS.distributed_shampoo(0.1, 512, batch_axis_name="batch", **kw)
+    single = DS.distributed_shampoo(0.1, 512, **kw)
+    solo = [dist.new_group([0]), dist.new_group([1])][rank]  # (collective on both ranks)
+    if variant == "quantized":  # quantisation needs a batch axis (DS:2051-2054): 1-rank group
+      single = DS.distributed_shampoo(0.1, 512, batch_axis_name="batch", process_group=solo,
+                                      **kw)
+    st_a, st_b = sharded.init(params), single.init(params)
+    worst = 0.0
+    for t in range(4):
+      grads = [torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes]
+      ua, st_a = sharded.update(grads, st_a, params)
+      ub, st_b = single.update(grads, st_b, params)
+      torch.cuda.synchronize()
+      for a, b in zip(ua, ub):
+        worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+    for a, b in zip(st_a.stats, st_b.stats):
+      for x, y in zip(a.preconditioners, b.preconditioners):
+        fx = x.to_float() if hasattr(x, "to_float") else x
+        fy = y.to_float() if hasattr(y, "to_float") else y
+        worst = max(worst, float((fx - fy).abs().max() / fy.abs().max().clamp_min(1e-30)))
+      if a.training_metrics is not None:
+        worst = max(worst, float((a.training_metrics - b.training_metrics).abs().max()))
+    out[rank] = worst
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("variant", ["plain", "quantized"])
+def test_sharded_step_equals_single_two_ranks(variant):
+  """Real solver, real exchange code (cost-balanced partition, packed all-gather, scatter with
+  failure fallback); gloo carries the bytes because two NCCL ranks cannot share one GPU."""
+  import torch.multiprocessing as mp
+  port = _free_port()
+  ctx = mp.get_context("spawn")
+  with ctx.Manager() as mgr:
+    out = mgr.dict()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, variant, out))
+             for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert all(out[r] == 0.0 for r in range(2)), dict(out)

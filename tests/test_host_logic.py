@@ -69,3 +69,79 @@ def test_unsupported_options_fail_loudly():
   for kw in (dict(lobpcg_topk_precondition=2), dict(shard_optimizer_states=True)):
     with pytest.raises(NotImplementedError):
       DS.distributed_shampoo(0.1, 32, **kw)
+
+
+def test_preconditioning_compute_steps_schedule_matches_reference_formula():
+  """DS:44-76: start + (1 - lr / lr0) * end, floored to a multiple of 10, at least 1."""
+  lr = lambda step: 0.1 * (1.0 - step / 1000.0)
+  f = DS.preconditioning_compute_steps_schedule
+  assert f(lr, 20, 200, 0) == 20
+  assert f(lr, 20, 200, 500) == 120      # 20 + 0.5 * 200
+  assert f(lr, 20, 200, 1000) == 220
+  assert f(lr, 1, 5, 100) == 1           # (1.5 // 10) * 10 = 0 -> max(., 1)
+  assert f(lr, 25, 0, 300) == 20         # rounded DOWN to a multiple of 10
+
+
+def test_partition_statistics_is_balanced_and_complete():
+  """Cost-balanced partition: every statistic owned once, per-bucket counts
+  differ by at most one, total cost per rank within one largest item of the mean."""
+  rng = np.random.default_rng(0)
+  buckets = [(1024, [4.0 * 1024**3] * 45 + [3.0 * 1024**3] * 34),
+             (512, [5.0 * 512**3] * 37), (64, list(rng.uniform(1, 2, 23) * 64**3)), (9, [3.0 * 729] * 16)]
+  for world in (1, 2, 3, 8):
+    table = DS.partition_statistics(buckets, world)
+    load = np.zeros(world)
+    for key, costs in buckets:
+      owned = table[key]
+      assert sorted(i for o in owned for i in o) == list(range(len(costs)))
+      counts = [len(o) for o in owned]
+      assert max(counts) - min(counts) <= 1
+      for r, o in enumerate(owned):
+        load[r] += sum(costs[i] for i in o)
+    assert load.max() - load.min() <= 4.0 * 1024**3 + 1e-6, (world, load)
+  assert DS.newton_gemms_per_iteration(4) == 4 and DS.newton_gemms_per_iteration(2) == 3
+  assert DS.newton_gemms_per_iteration(6) == 5 and DS.newton_gemms_per_iteration(8) == 5
+
+
+def test_gather_layout_round_trip():
+  """Packed all-gather layout + scatter indices (pc_select_scatter), emulated with numpy:
+  every rank packs its rows, the concatenation is scattered back into state order."""
+  owned = [[0, 3, 6], [1, 4], [2, 5]]
+  cnt, row = 3, 36  # 3 x 3 fp32 roots
+  lay = DS.gather_layout(owned, cnt, [("r", row), ("m", 20)])
+  assert lay["lbytes"] % 16 == 0
+  state = np.arange(7 * 9, dtype=np.float32).reshape(7, 9)
+  recv = np.zeros((3, lay["lbytes"]), np.uint8)
+  for r, o in enumerate(owned):
+    ro, _ = lay["sections"]["r"]
+    mo, _ = lay["sections"]["m"]
+    buf = np.zeros(lay["lbytes"], np.uint8)
+    rows = np.zeros((cnt, 9), np.float32)
+    rows[:len(o)] = state[o]
+    met = np.zeros((cnt, 5), np.float32)
+    met[:len(o), 1] = o
+    buf[ro:ro + cnt * row] = rows.view(np.uint8).reshape(-1)
+    buf[mo:mo + cnt * 20] = met.view(np.uint8).reshape(-1)
+    recv[r] = buf
+  flat = recv.reshape(-1)
+  out = np.full((7, 9), -1, np.float32)
+  mout = np.full((7, 5), -1, np.float32)
+  for j, d in enumerate(lay["dst_index"]):
+    if d < 0:
+      continue
+    so = lay["src_offset"]["r"][j]
+    out[d] = flat[so:so + row].view(np.float32)
+    mout[d] = flat.view(np.float32)[lay["metrics_offset"][j]:lay["metrics_offset"][j] + 5]
+  assert np.array_equal(out, state)
+  assert np.array_equal(mout[:, 1], np.arange(7))
+
+
+def test_option_validation():
+  with pytest.raises(ValueError):
+    DS.distributed_shampoo(0.1, 32, exponent_override=17)
+  with pytest.raises(NotImplementedError):
+    DS.distributed_shampoo(0.1, 32, frequent_directions=True, compression_rank=4,
+                           reuse_preconditioner=True, generate_fd_metrics=True)
+  DS.distributed_shampoo(0.1, 32, generate_fd_metrics=True)  # ignored without FD (DS:2026)
+  DS.distributed_shampoo(lambda s: 0.1, 32, decay_preconditioning_compute_steps=True,
+                         end_preconditioning_compute_steps=100)
