@@ -594,7 +594,7 @@ static int root_enqueue_final(RootCall& c, cudaStream_t stream) {
 struct RootGraphKey {
   const void* xs; const void* ps; const void* pads; const void* roots; const void* metrics;
   const void* workspace;
-  int batch, n, engine, max_steps, num_iters, relative_eps, device;
+  int batch, n, engine, max_steps, num_iters, relative_eps, device, variant;
   float ridge, tol;
   bool operator<(const RootGraphKey& o) const { return memcmp(this, &o, sizeof(*this)) < 0; }
 };
@@ -800,6 +800,7 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* ps_host, const i
     key.num_iters = opt->num_iters; key.relative_eps = opt->relative_matrix_epsilon;
     key.ridge = opt->ridge_epsilon; key.tol = opt->error_tolerance;
     cudaGetDevice(&key.device);
+    key.variant = engine == PC_ENGINE_SIMT_FP32 ? 0 : tc_engine_variant_mask();
     return run_root_graph(c, key, stream);
   }
 

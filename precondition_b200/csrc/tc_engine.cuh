@@ -14,6 +14,7 @@ struct TcEngine {
 };
 
 bool tc_engine_available();
+int tc_engine_variant_mask();
 // one-time per-device setup (kernel attributes, constants); call before any stream capture
 int tc_engine_prepare();
 size_t tc_engine_bytes(int batch, int n, int planes);

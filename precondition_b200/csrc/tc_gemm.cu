@@ -1513,6 +1513,17 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// kernel-variant knobs read from the environment at every call (part of the graph-cache key)
+int tc_engine_variant_mask() {
+  int m = 0;
+  const char* v;
+  if ((v = getenv("PC_TC_PAIR256")) && v[0] == '1') m |= 1;
+  if ((v = getenv("PC_TC_WS2")) && v[0] == '1') m |= 2;
+  if ((v = getenv("PC_TC_CHUNK")) && v[0] == '2') m |= 4;
+  if ((v = getenv("PC_TC_ABLATE"))) m |= atoi(v) << 4;
+  return m;
+}
+
 bool tc_engine_available() {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;

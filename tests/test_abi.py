@@ -66,3 +66,18 @@ def test_struct_layouts_match_header(tmp_path):
           ctypes.sizeof(_lib.FdOptions), _lib.FdOptions.full_eigh_max_dim.offset,
           ctypes.sizeof(_lib.GraftSegment), _lib.GraftSegment.has_precond.offset]
   assert got == want
+
+
+def test_ffi_adapter_type_checks():
+  """ffi/precond_ffi.cc (the jax.ffi handlers over this C ABI) compiles against the header --
+  with the real XLA FFI headers when JAX is present, else against the API stub."""
+  import subprocess
+  ffi_dir = os.path.join(ROOT, "ffi")
+  cmd = ["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-I",
+         "/usr/local/cuda/include"]
+  try:
+    import jax.ffi
+    cmd += ["-I", jax.ffi.include_dir()]
+  except Exception:  # pylint: disable=broad-except
+    cmd += ["-DPC_FFI_SYNTAX_CHECK", "-I", ffi_dir]
+  subprocess.run(cmd + [os.path.join(ffi_dir, "precond_ffi.cc")], check=True)

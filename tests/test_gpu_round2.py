@@ -40,12 +40,15 @@ def test_root_graph_mode_equals_host_polled(n):
     torch.cuda.synchronize()
   finally:
     del os.environ["PC_ROOT_MODE"]
-  assert torch.equal(r_graph, r_poll)
-  assert torch.equal(m_graph.nan_to_num(-1.0), m_poll.nan_to_num(-1.0))
+  for a, b in ((r_graph, r_poll), (m_graph, m_poll)):  # NaN-aware bitwise comparison
+    assert torch.equal(a.isnan(), b.isnan())
+    assert torch.equal(a.nan_to_num(0.0, 1e38, -1e38), b.nan_to_num(0.0, 1e38, -1e38))
   for b in (0, 1, 2):
     want, wm = N.matrix_inverse_pth_root(xs[b].cpu().numpy(), ps[b], padding_start=pads[b])
     rel = np.linalg.norm(r_graph[b].cpu().numpy() - want) / np.linalg.norm(want)
-    assert rel <= 1e-3 and float(m_graph[b, 1]) == wm.inverse_pth_root_iters
+    # +-1 iteration only at knife edges: the reference's own last error within 4x of 1e-6
+    slack = 1 if wm.inverse_pth_root_errors >= 2.5e-7 else 0
+    assert rel <= 1e-3 and abs(float(m_graph[b, 1]) - wm.inverse_pth_root_iters) <= slack
 
 
 def test_root_graph_is_cached_and_relaunchable():
@@ -141,7 +144,10 @@ def test_grouped_graft_matches_per_parameter_kernel(graft):
   for o, n_ in zip(offs, numels):
     sl = slice(o, o + n_)
     for a, b in zip(got + [got_u], want + [want_u]):
-      assert torch.allclose(a[sl], b[sl], rtol=2e-5, atol=1e-12), (graft, n_)
+      # the two kernels sum the norms in different orders (relative 1e-7 on the multipliers):
+      # compare against the scale of the buffer, not element-wise relative
+      atol = 2e-6 * float(b[sl].abs().max())
+      assert torch.allclose(a[sl], b[sl], rtol=1e-5, atol=atol), (graft, n_)
     pad = slice(o + n_, o + (n_ + 31) // 32 * 32)
     assert float(got_u[pad].abs().sum()) == 0.0  # nothing written between segments
 
