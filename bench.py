@@ -50,8 +50,9 @@ def parse_args():
   ap.add_argument("--no-big", action="store_true",
                   help="skip the BERT-large (config 4) and Sketchy-step (config 5) measurements")
   ap.add_argument("--split", type=int, default=0,
-                  help="sub-batches per step (0 = auto: 2 with several GPUs so that the all-gather of "
-                       "the first half overlaps the solve of the second, else 1)")
+                  help="sub-batches per step (default 1; with k > 1 the all-gather of sub-batch i "
+                       "overlaps the solve of i+1, measured slower: each sub-batch pays its own "
+                       "power iteration and launch ramps)")
   return ap.parse_args()
 
 
@@ -330,17 +331,20 @@ def run_ours(a):
   metrics_buf = torch.empty((B, 5), dtype=torch.float32, device=dev)
   # Sub-batches: with several ranks the all-gather of the first half (DS:2876) runs on its own
   # stream underneath the solve of the second half; the solver call only enqueues.
-  nsplit = a.split if a.split > 0 else (2 if world > 1 else 1)
+  nsplit = a.split if a.split > 0 else 1
   nsplit = max(1, min(nsplit, B))
   bounds = [round(i * B / nsplit) for i in range(nsplit + 1)]
   parts = [(bounds[i], bounds[i + 1]) for i in range(nsplit) if bounds[i + 1] > bounds[i]]
   ws_parts = [torch.empty(ops.root_workspace_bytes(hi - lo, n, engine) + 256, dtype=torch.uint8,
                           device=dev) for lo, hi in parts]
-  gathered = ([torch.empty((world * (hi - lo), n, n), dtype=torch.float32, device=dev)
-               for lo, hi in parts] if world > 1 else None)
+  # all-gather of the roots (DS:2876): copy-engine pushes over NVLink peer memory
+  # (precondition_b200/peer.py), NCCL as the fallback
+  from precondition_b200 import peer
+  gathered = ([peer.make_all_gather((hi - lo) * n * n * 4, None, dev) for lo, hi in parts]
+              if world > 1 else None)
   comm_stream = torch.cuda.Stream(dev) if world > 1 else None
-  gather_note = (f"{len(parts)} sub-batches; all-gather of sub-batch k on a side stream under the "
-                 f"solve of k+1" if world > 1 else "n/a (single gpu)")
+  gather_note = (f"{len(parts)} sub-batch(es); all-gather ({gathered[0].kind}) of sub-batch k on a "
+                 f"side stream under the solve of k+1" if world > 1 else "n/a (single gpu)")
 
   def solve(x_in, out):
     cur = torch.cuda.current_stream(dev)
@@ -353,7 +357,8 @@ def run_ours(a):
         ev.record(cur)
         with torch.cuda.stream(comm_stream):
           comm_stream.wait_event(ev)
-          dist.all_gather_into_tensor(gathered[k], out[lo:hi])  # DS:2876
+          gathered[k].all_gather(out[lo:hi])  # DS:2876
+          gathered[k].release()               # (nothing reads the gathered copy in this bench)
     if world > 1:
       cur.wait_stream(comm_stream)
     return out, metrics_buf

@@ -389,6 +389,46 @@ int pc_graft_momentum_grouped(const pc_graft_segment* segments, const int32_t* c
                               float* momentum, float* update, const pc_graft_options* opt,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * (5) all-gather of the block-sharded roots over NVLink peer memory
+ * replaces: jax.lax.all_gather of the preconditioners and metrics (DS:2876-2877; the four
+ *           gathers of the quantised path, DS:3116-3122) when every rank of the batch axis
+ *           is a process on the same NVSwitch box.
+ * Copy engines only -- no SM is used, so the exchange overlaps the persistent GEMM kernels of
+ * the next sub-batch / bucket (an NCCL kernel would compete with them for SMs).  One process
+ * per GPU: every rank allocates a receive buffer [world][slot_bytes] and a flag block of
+ * PC_PEER_FLAG_WORDS uint32 (zeroed), exports both with pc_ipc_export, exchanges the handles
+ * through its host-side launcher (torch.distributed in this repo), opens the peers' with
+ * pc_ipc_open and fills a pc_peer_group (its own pointers at index `rank`).
+ *   pc_peer_all_gather  stream-ordered: waits until every peer has released the previous
+ *                       epoch, pushes `bytes` of `send` into slot `rank` of every receive
+ *                       buffer (cudaMemcpyAsync peer-to-peer) followed by the epoch flag, then
+ *                       makes `stream` wait (cuStreamWaitValue32) until all peers' payloads of
+ *                       this epoch have landed here.  Epochs start at 1 and increase by 1.
+ *   pc_peer_release     enqueue after the last consumer of the receive buffer: tells the peers
+ *                       that this rank's buffer may be overwritten by epoch + 1.
+ * ------------------------------------------------------------------------ */
+#define PC_MAX_PEERS 16
+#define PC_PEER_FLAG_WORDS (2 * PC_MAX_PEERS + 16)
+typedef struct {
+  unsigned char handle[64]; /* cudaIpcMemHandle_t of the allocation that contains the pointer */
+  int64_t offset;           /* of the pointer inside that allocation */
+  int64_t size;
+  int32_t device;
+  int32_t reserved;
+} pc_ipc_handle;
+typedef struct {
+  int32_t world, rank;
+  int64_t slot_bytes;
+  void* recv[PC_MAX_PEERS];  /* receive buffers: own pointer at [rank], peers' mapped pointers */
+  void* flags[PC_MAX_PEERS]; /* flag blocks, same convention */
+} pc_peer_group;
+int pc_ipc_export(const void* dev_ptr, pc_ipc_handle* out);
+int pc_ipc_open(const pc_ipc_handle* handle, void** out_ptr);
+int pc_peer_all_gather(const pc_peer_group* group, const void* send, size_t bytes, uint32_t epoch,
+                       void* stream);
+int pc_peer_release(const pc_peer_group* group, uint32_t epoch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

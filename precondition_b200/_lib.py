@@ -17,6 +17,8 @@ PC_ENGINE_AUTO, PC_ENGINE_SIMT_FP32, PC_ENGINE_TC_BF16X6, PC_ENGINE_TC_BF16X3 = 
 PC_ENGINE_TC_FP16X3 = 4
 PC_QDTYPE_F32, PC_QDTYPE_INT16, PC_QDTYPE_INT8, PC_QDTYPE_BF16 = 0, 1, 2, 3
 PC_NUM_METRICS = 5
+PC_MAX_PEERS = 16
+PC_PEER_FLAG_WORDS = 2 * PC_MAX_PEERS + 16
 
 EXPORTED_SYMBOLS = (
     "pc_version", "pc_last_error", "pc_device_supports_tcgen05", "pc_stats_reset",
@@ -35,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "pc_grouped_gemm_splitk_workspace_bytes", "pc_grouped_gemm_splitk",
     "pc_graft_group_chunk_elems", "pc_graft_momentum_grouped_workspace_bytes",
     "pc_graft_momentum_grouped", "pc_inverse_pth_root_enqueue", "pc_root_mode",
-    "pc_select_scatter",
+    "pc_select_scatter", "pc_ipc_export", "pc_ipc_open", "pc_peer_all_gather", "pc_peer_release",
 )
 
 
@@ -91,6 +93,16 @@ class GraftSegment(ctypes.Structure):
   _fields_ = [("offset", ctypes.c_int64), ("numel", ctypes.c_int64),
               ("first_chunk", ctypes.c_int32), ("nchunks", ctypes.c_int32),
               ("has_precond", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class IpcHandle(ctypes.Structure):
+  _fields_ = [("handle", ctypes.c_ubyte * 64), ("offset", ctypes.c_int64),
+              ("size", ctypes.c_int64), ("device", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class PeerGroup(ctypes.Structure):
+  _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("slot_bytes", ctypes.c_int64),
+              ("recv", ctypes.c_void_p * PC_MAX_PEERS), ("flags", ctypes.c_void_p * PC_MAX_PEERS)]
 
 
 _lib = None
@@ -149,6 +161,14 @@ def load() -> ctypes.CDLL:
   lib.pc_select_preconditioners.restype = i32
   lib.pc_select_scatter.argtypes = [vp, vp, vp, vp, vp, f32, vp, i64, vp, i32, vp]
   lib.pc_select_scatter.restype = i32
+  lib.pc_ipc_export.argtypes = [vp, ctypes.POINTER(IpcHandle)]
+  lib.pc_ipc_export.restype = i32
+  lib.pc_ipc_open.argtypes = [ctypes.POINTER(IpcHandle), ctypes.POINTER(ctypes.c_void_p)]
+  lib.pc_ipc_open.restype = i32
+  lib.pc_peer_all_gather.argtypes = [ctypes.POINTER(PeerGroup), vp, sz, ctypes.c_uint32, vp]
+  lib.pc_peer_all_gather.restype = i32
+  lib.pc_peer_release.argtypes = [ctypes.POINTER(PeerGroup), ctypes.c_uint32, vp]
+  lib.pc_peer_release.restype = i32
   lib.pc_quantize_batched.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
   lib.pc_quantize_batched.restype = i32
   lib.pc_dequantize_batched.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]

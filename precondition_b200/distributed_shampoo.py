@@ -31,7 +31,7 @@ from typing import Any, Callable, List, NamedTuple, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from precondition_b200 import _lib, ops
+from precondition_b200 import _lib, ops, peer
 from precondition_b200.quantization_utils import QuantizedValue
 
 
@@ -1025,7 +1025,10 @@ class _Shampoo:
         off, sec = lay["lbytes"], lay["sections"]
         job.lbytes = off
         job.send = torch.zeros(off, dtype=torch.uint8, device=dev)
-        job.recv = torch.empty((world, off), dtype=torch.uint8, device=dev)
+        # copy-engine pushes over NVLink peer memory (no SM: overlaps the other buckets'
+        # persistent GEMM kernels); NCCL when peer mappings are unavailable
+        job.gather = peer.make_all_gather(off, self.process_group, dev)
+        job.recv = job.gather.recv
         job.recv_f32 = job.recv.view(-1).view(torch.float32)
 
         def view(name, dtype, shape):
@@ -1058,7 +1061,6 @@ class _Shampoo:
     each bucket's packed all-gather (DS:2876-2877) starts as soon as that bucket is done."""
     if full[0].job is None or full[0].job.world != world:
       self._build_root_jobs(full, world, rank)
-    import torch.distributed as dist
     main = torch.cuda.current_stream(self.device)
     fork = torch.cuda.Event()
     fork.record(main)
@@ -1090,7 +1092,7 @@ class _Shampoo:
         elif world > 1 and job.sp != s:
           job.send_roots.copy_(corner)
         if world > 1:
-          dist.all_gather_into_tensor(job.recv.view(-1), job.send, group=self.process_group)
+          job.gather.all_gather(job.send)
         if world == 1 and not self.quantize_second_moment:
           lib = _lib.load()
           _lib.check(lib.pc_select_preconditioners(
@@ -1103,6 +1105,8 @@ class _Shampoo:
           for src, src_off, row, k in job.sel:
             ops.select_scatter(src, src_off, mbase, job.met_off, job.dst_idx, thr, dsts[k], row,
                                self.metrics[s] if k == 0 else None)
+        if world > 1:
+          job.gather.release()
         job.done.record(job.stream)
     for bk in full:
       main.wait_event(bk.job.done)
