@@ -512,6 +512,7 @@ def run_ours(a):
   #      (MLP 512->2048->512, block_size 128, SGD grafting, 1 GPU), through the
   #      optax-style API; steps >= 5 so the preconditioned path is active ----
   shampoo_step, sketchy, resnet_step, bert_step, sketchy_step = None, None, None, None, None
+  small_block = None
 
   def max_over_ranks(x):
     t = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -533,6 +534,10 @@ def run_ours(a):
   if world == 1 and not a.no_step:
     shampoo_step = time_shampoo_step(dev)
     sketchy = time_sketchy_update(dev)
+    try:
+      small_block = time_small_block_batch(dev)
+    except RuntimeError as e:  # (not sm_100: the persistent solver needs tcgen05)
+      small_block = {"error": str(e)[:200]}
 
   if rank == 0:
     cpu_baseline, parity = None, None
@@ -559,11 +564,56 @@ def run_ours(a):
         "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
         "shampoo_step": shampoo_step, "sketchy_update": sketchy,
         "shampoo_step_resnet50": resnet_step, "shampoo_step_bert_large": bert_step,
-        "sketchy_step": sketchy_step,
+        "sketchy_step": sketchy_step, "small_block_roots": small_block,
     }
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()
+
+
+def time_small_block_batch(dev, batch=64, n=128, p=4, reps=20):
+  """BASELINE config 1: inverse 4th roots of a batch of 64 SPD 128 x 128 statistics (the
+  reference's default block size) -- ms per batch on the persistent small-block solver and on
+  the CUDA-core engine, iteration counts against the oracle for two of them."""
+  import torch
+  from oracle import numerics as N
+  from oracle.gen_golden import ema_statistics, gen_symmetric_matrix
+  from precondition_b200 import _lib, ops
+  rng = np.random.default_rng(0)
+  xs_h = np.stack([gen_symmetric_matrix(rng, n, 1e4) if i % 2 else ema_statistics(rng, n, 2 * n)
+                   for i in range(batch)]).astype(np.float32)
+  xs = torch.as_tensor(xs_h).to(dev)
+  ps = torch.full((batch,), p, dtype=torch.int32, device=dev)
+  ps_host = [p] * batch
+  out = {"batch": batch, "n": n, "p": p, "unit": "ms/batch"}
+  for name, engine in (("persistent_tcgen05", _lib.PC_ENGINE_TC_SMALL),
+                       ("cuda_core_fp32", _lib.PC_ENGINE_SIMT_FP32)):
+    roots, met = torch.empty_like(xs), torch.empty((batch, 5), device=dev)
+    ws = torch.empty(ops.root_workspace_bytes(batch, n, engine) + 256, dtype=torch.uint8, device=dev)
+    call = lambda: ops.matrix_inverse_pth_root_batched(xs, ps, None, engine=engine, out=roots,
+                                                       metrics_out=met, workspace=ws,
+                                                       ps_host=ps_host)
+    for _ in range(3):
+      call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+      call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out[name] = {"ms": ms, "roots_per_s": batch / ms * 1e3,
+                 "newton_iters_mean": float(met[:, 1].mean()), "max_error": float(met[:, 0].max())}
+    if name == "persistent_tcgen05":
+      rel, its = [], []
+      for b in (0, 1):
+        want, wm = N.matrix_inverse_pth_root(xs_h[b], p)
+        rel.append(float(np.linalg.norm(roots[b].cpu().numpy() - want) / np.linalg.norm(want)))
+        its.append([float(met[b, 1]), float(wm.inverse_pth_root_iters)])
+      out[name]["rel_frobenius_vs_oracle"] = rel
+      out[name]["iters_ours_oracle"] = its
+  return out
 
 
 def time_shampoo_step(dev, steps=10, warm=6):

@@ -54,6 +54,11 @@ extern "C" {
 #define PC_ENGINE_TC_BF16X3 3 /* tcgen05, bf16 2-way split, 3 products (~2^-16) */
 #define PC_ENGINE_TC_FP16X3 4 /* tcgen05, fp16 + 2^11-scaled fp16 residual, 3 products
                                  (22-bit operands, like 3xTF32 at the f16 MMA rate)  */
+#define PC_ENGINE_TC_SMALL 5  /* tcgen05, n <= 128: one persistent CTA per matrix runs the whole
+                                 solve (power iteration, Newton loop, retries) with the iterates
+                                 in shared / tensor memory; exact bf16x6 products; exponents 2^s
+                                 given on the host (pc_inverse_pth_root_enqueue).  PC_ENGINE_AUTO
+                                 picks it whenever it applies.                          */
 
 /* quantised storage of statistics / preconditioners, QU:49-113 */
 #define PC_QDTYPE_F32 0

@@ -15,6 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 PC_ENGINE_AUTO, PC_ENGINE_SIMT_FP32, PC_ENGINE_TC_BF16X6, PC_ENGINE_TC_BF16X3 = 0, 1, 2, 3
 PC_ENGINE_TC_FP16X3 = 4
+PC_ENGINE_TC_SMALL = 5
 PC_QDTYPE_F32, PC_QDTYPE_INT16, PC_QDTYPE_INT8, PC_QDTYPE_BF16 = 0, 1, 2, 3
 PC_NUM_METRICS = 5
 PC_MAX_PEERS = 16

@@ -18,6 +18,13 @@
 
 namespace pc {
 
+// persistent per-matrix solver for n <= 128 (small_root.cu)
+size_t small_root_workspace_bytes(int batch, int n);
+bool small_root_supported_exponents(const int32_t* ps_host, int batch);
+int run_small_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch, int n,
+                   const pc_root_options* opt, const float* v0_host_pinned, float* roots,
+                   float* metrics, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------
 // step programs
 // ---------------------------------------------------------------------------
@@ -411,10 +418,15 @@ static int resolve_engine(int engine, int n) {
 }
 
 size_t root_workspace_bytes(int batch, int n, int engine) {
+  if (engine == PC_ENGINE_TC_SMALL) return small_root_workspace_bytes(batch, n) + 1024;
+  const bool maybe_small = engine == PC_ENGINE_AUTO && n <= 128 && tc_engine_available();
   engine = resolve_engine(engine, n);
   size_t e = engine == PC_ENGINE_SIMT_FP32 ? engine_bytes_simt(batch, n)
                                            : tc_engine_bytes(batch, n, engine == PC_ENGINE_TC_FP16X3 ? 2 : 3);
-  return header_bytes(batch, n) + align_up(e, 256) + 1024;
+  size_t total = header_bytes(batch, n) + align_up(e, 256) + 1024;
+  // PC_ENGINE_AUTO may pick the persistent small-block solver (per-CTA H slots)
+  if (maybe_small) total = std::max(total, small_root_workspace_bytes(batch, n) + 1024);
+  return total;
 }
 
 static int pick_cluster_size(int batch) {
@@ -443,6 +455,12 @@ int prepare_power_iteration(int n) {
     PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return PC_OK;
+}
+
+static const float* power_iteration_v0_host(int n) {
+  std::lock_guard<std::mutex> lock(v0_mu);
+  auto it = v0_cache.find(n);
+  return it == v0_cache.end() ? nullptr : it->second;
 }
 
 int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n,
@@ -744,6 +762,29 @@ static int run_root_graph(RootCall& c, const RootGraphKey& key, cudaStream_t str
 int run_root(const float* xs, const int32_t* ps, const int32_t* ps_host, const int32_t* pads,
              int batch, int n, const pc_root_options* opt, float* roots, float* metrics,
              void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  // Small statistics (n <= 128, exponents 2^s known on the host): the whole solve of a matrix
+  // runs inside one persistent CTA on the tensor cores -- one launch, nothing to poll.
+  {
+    const char* sm = getenv("PC_SMALL_ROOT");
+    const bool allowed = !(sm && sm[0] == '0');
+    const bool eligible = n <= 128 && tc_engine_available() &&
+                          small_root_supported_exponents(ps_host, batch);
+    if (opt->engine == PC_ENGINE_TC_SMALL) {
+      PC_REQUIRE(eligible, "PC_ENGINE_TC_SMALL needs sm_100, n <= 128 and host exponents in "
+                           "{1, 2, 4, 8, 16} (pc_inverse_pth_root_enqueue with ps_host)");
+    }
+    if (opt->engine == PC_ENGINE_TC_SMALL || (opt->engine == PC_ENGINE_AUTO && eligible && allowed)) {
+      int rc0 = prepare_power_iteration(n);
+      if (rc0 != PC_OK) return rc0;
+      if (workspace_bytes < small_root_workspace_bytes(batch, n)) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes,
+                  small_root_workspace_bytes(batch, n));
+        return PC_ERR_WORKSPACE;
+      }
+      return run_small_root(xs, ps, pads, batch, n, opt, power_iteration_v0_host(n), roots,
+                            metrics, workspace, workspace_bytes, stream);
+    }
+  }
   const int engine = resolve_engine(opt->engine, n);
   PC_REQUIRE(engine == PC_ENGINE_SIMT_FP32 || engine == PC_ENGINE_TC_BF16X6 ||
                  engine == PC_ENGINE_TC_BF16X3 || engine == PC_ENGINE_TC_FP16X3,
