@@ -343,8 +343,16 @@ def run_ours(a):
   gathered = ([peer.make_all_gather((hi - lo) * n * n * 4, None, dev) for lo, hi in parts]
               if world > 1 else None)
   comm_stream = torch.cuda.Stream(dev) if world > 1 else None
-  gather_note = (f"{len(parts)} sub-batch(es); all-gather ({gathered[0].kind}) of sub-batch k on a "
-                 f"side stream under the solve of k+1" if world > 1 else "n/a (single gpu)")
+  gather_note = (f"all-gather ({gathered[0].kind}) of step k on a side stream under the solve of "
+                 f"step k+1 (double-buffered roots; {len(parts)} sub-batch(es) per step)"
+                 if world > 1 else "n/a (single gpu)")
+
+  # The all-gather of step k runs on the copy engines underneath the solve of step k + 1 (no
+  # SM is involved, precondition_b200/peer.py): two root buffers alternate, a buffer is reused
+  # only after its gather has completed.  Every gather is inside the timed region (the region
+  # ends with a synchronize, so the last one is fully exposed).
+  gather_done = [None, None]
+  step_no = [0]
 
   def solve(x_in, out):
     cur = torch.cuda.current_stream(dev)
@@ -359,12 +367,21 @@ def run_ours(a):
           comm_stream.wait_event(ev)
           gathered[k].all_gather(out[lo:hi])  # DS:2876
           gathered[k].release()               # (nothing reads the gathered copy in this bench)
-    if world > 1:
-      cur.wait_stream(comm_stream)
     return out, metrics_buf
 
+  roots_pp = [roots, torch.empty_like(roots)] if world > 1 else [roots, roots]
+
   def step():
-    return solve(xs, roots)[1]
+    i = step_no[0] % 2
+    step_no[0] += 1
+    cur = torch.cuda.current_stream(dev)
+    if world > 1 and gather_done[i] is not None:
+      cur.wait_event(gather_done[i])  # the gather that read this buffer two steps ago
+    m = solve(xs, roots_pp[i])[1]
+    if world > 1:
+      gather_done[i] = torch.cuda.Event()
+      gather_done[i].record(comm_stream)
+    return m
 
   def barrier():
     if world > 1:
@@ -438,6 +455,8 @@ def run_ours(a):
       cur.wait_event(ev_in[k])
       cur.wait_event(ev_out[k])  # the previous download of this output slot is done
       r, m = solve(dev_ins[k], dev_outs[k])
+      if world > 1:
+        cur.wait_stream(comm_stream)  # the gathered copy of this step is complete
       ev_solved[k].record(cur)
       with torch.cuda.stream(s_d2h):
         s_d2h.wait_event(ev_solved[k])

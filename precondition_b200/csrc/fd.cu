@@ -19,6 +19,8 @@
 // are contiguous.  All GEMMs run on the fp32 CUDA-core tile of simt_gemm.cuh.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(256)
 fd_prepare_kernel(const float* __restrict__ prev, const int32_t* __restrict__ ps,
                   const int32_t* __restrict__ pads, int d, int r, float ridge_epsilon,
                   float error_tolerance, int relative_eps, float decay, float* __restrict__ bs,
-                  FdScalars* __restrict__ scal, float* __restrict__ yt, int k) {
+                  FdScalars* __restrict__ scal, float* __restrict__ yt, int k, int k_ld) {
   __shared__ float scratch[32];
   const int b = blockIdx.x;
   const int pd = r + 2;
@@ -128,7 +130,7 @@ fd_prepare_kernel(const float* __restrict__ prev, const int32_t* __restrict__ ps
     B[e] = sdecay * w;
   }
   if (!yt) return;
-  float* Y = yt + (size_t)b * k * d;
+  float* Y = yt + (size_t)b * k_ld * d;  // k rows used of k_ld allocated
   for (int j = 0; j < k; ++j) {
     bool use_prev = false;
     if (j < r) {  // block-uniform decision: is the previous eigenvector slot populated?
@@ -164,9 +166,9 @@ __global__ void fd_mask_kernel(const float* __restrict__ src, const FdScalars* _
 
 // each row of X [rows, len] scaled to unit 2-norm (zero rows stay zero)
 __global__ void __launch_bounds__(256)
-fd_row_normalize_kernel(float* __restrict__ x, int rows, int len) {
+fd_row_normalize_kernel(float* __restrict__ x, int rows_ld, int len) {
   __shared__ float scratch[32];
-  float* row = x + ((size_t)blockIdx.y * rows + blockIdx.x) * len;
+  float* row = x + ((size_t)blockIdx.y * rows_ld + blockIdx.x) * len;
   float ss = 0.f;
   for (int i = threadIdx.x; i < len; i += blockDim.x) ss = fmaf(row[i], row[i], ss);
   const float nrm = sqrtf(block_sum(ss, scratch));
@@ -439,6 +441,186 @@ fd_finalize_kernel(const float* __restrict__ vt_all, int nv, const float* __rest
 }
 
 // ---------------------------------------------------------------------------
+// Cheap orthonormalisation of the intermediate subspace blocks (shifted Cholesky QR):
+//   G = Yt Yt^T + shift I = L L^T,   Qt = L^-1 Yt.
+// Only the SPAN of the block matters between iterations (the Rayleigh-Ritz rotation inside the
+// span is redundant there), so the k x k eigen-solves are kept for the last iteration only.
+// ---------------------------------------------------------------------------
+// in place on a [k, k] Gram matrix (lower triangle <- L); one CTA (32 x 32 threads) per matrix.
+// kSmem: the packed lower triangle (k (k + 1) / 2 floats) lives in shared memory for the whole
+// factorisation.  The scaled pivot column is staged in its own vector so that the trailing
+// update reads it without bank conflicts; threads tile the trailing block in 2-D (no div / mod).
+template <bool kSmem>
+__global__ void __launch_bounds__(1024)
+fd_cholesky_shift_kernel(float* __restrict__ a_all, int k, float shift) {
+  extern __shared__ float chol_smem[];
+  float* col = chol_smem;            // [k] scaled pivot column
+  float* packed = chol_smem + ((k + 31) & ~31);
+  __shared__ float piv_s;
+  float* A = a_all + (size_t)blockIdx.x * k * k;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  auto at = [&](int i, int j) -> float& {  // j <= i
+    return kSmem ? packed[(size_t)i * (i + 1) / 2 + j] : A[(size_t)i * k + j];
+  };
+  if (kSmem) {
+    for (int i = ty; i < k; i += 32)
+      for (int j = tx; j <= i; j += 32)
+        packed[(size_t)i * (i + 1) / 2 + j] = A[(size_t)i * k + j] + (i == j ? shift : 0.f);
+  } else {
+    for (int i = tid; i < k; i += blockDim.x) A[(size_t)i * k + i] += shift;
+  }
+  __syncthreads();
+  for (int c = 0; c < k; ++c) {
+    if (tid == 0) {
+      const float p = at(c, c);
+      piv_s = p > 0.f ? sqrtf(p) : __int_as_float(0x7fc00000);
+      at(c, c) = piv_s;
+    }
+    __syncthreads();
+    const float inv = 1.0f / piv_s;
+    for (int i = c + 1 + tid; i < k; i += blockDim.x) {
+      const float v = at(i, c) * inv;
+      at(i, c) = v;
+      col[i] = v;
+    }
+    __syncthreads();
+    for (int i = c + 1 + ty; i < k; i += 32) {
+      const float li = col[i];
+      for (int j = c + 1 + tx; j <= i; j += 32) at(i, j) -= li * col[j];
+    }
+    __syncthreads();
+  }
+  if (kSmem) {
+    for (int i = ty; i < k; i += 32)
+      for (int j = tx; j <= i; j += 32) A[(size_t)i * k + j] = packed[(size_t)i * (i + 1) / 2 + j];
+  }
+}
+// dst [k, k] <- top-left corner of src [ld, ld]
+__global__ void fd_compact_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst,
+                                  int k) {
+  const int b = blockIdx.y;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k * k; e += gridDim.x * blockDim.x) {
+    const int i = e / k, j = e - i * k;
+    dst[(size_t)b * k * k + e] = src[((size_t)b * ld + i) * ld + j];
+  }
+}
+constexpr size_t kCholSmemMax = 200 * 1024;
+static int fd_cholesky_shift(float* a, int k, int batch, float shift, cudaStream_t stream) {
+  const size_t colb = (size_t)((k + 31) & ~31) * sizeof(float);
+  const size_t bytes = colb + (size_t)k * (k + 1) / 2 * sizeof(float);
+  if (bytes <= kCholSmemMax) {
+    static bool configured = false;
+    if (!configured) {
+      PC_CUDA_CHECK(cudaFuncSetAttribute(fd_cholesky_shift_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kCholSmemMax));
+      configured = true;
+    }
+    fd_cholesky_shift_kernel<true><<<batch, 1024, bytes, stream>>>(a, k, shift);
+  } else {
+    fd_cholesky_shift_kernel<false><<<batch, 1024, colb, stream>>>(a, k, shift);
+  }
+  count_launch(1);
+  return PC_OK;
+}
+
+// Qt = L^-1 Yt by forward substitution, in place allowed; one thread per column of the [k, d]
+// block (the k^2 / 2 steps of a column are sequential, the d columns are independent).  The
+// finished part of a thread's column stays in shared memory ([k][128] floats) and the rows of L
+// are staged through shared memory eight at a time, so the inner loop is two LDS and one FMA.
+constexpr int kTrsmRows = 8;
+__global__ void __launch_bounds__(128)
+fd_trsm_rows_kernel(const float* __restrict__ l_all, const float* yt_all, float* qt_all, int k,
+                    int d, int k_ld) {
+  extern __shared__ float trsm_smem[];
+  const int kp = (k + 3) & ~3;
+  float* lrows = trsm_smem;                    // [kTrsmRows][kp]
+  float* cols = trsm_smem + kTrsmRows * kp;    // [k][128]
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = c < d;
+  const float* L = l_all + (size_t)b * k * k;
+  const float* Y = yt_all + (size_t)b * k_ld * d;
+  float* Q = qt_all + (size_t)b * k_ld * d;
+  for (int i0 = 0; i0 < k; i0 += kTrsmRows) {
+    const int nr = min(kTrsmRows, k - i0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * kp; e += blockDim.x) {
+      const int r = e / kp, j = e - r * kp;
+      lrows[e] = (j < k && j <= i0 + r) ? __ldg(L + (size_t)(i0 + r) * k + j) : 0.f;
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int r = 0; r < nr; ++r) {
+      const int i = i0 + r;
+      const float* li = lrows + r * kp;
+      float a0 = Y[(size_t)i * d + c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      float a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+      int j = 0;
+      for (; j + 8 <= i; j += 8) {
+        const float4 l0 = *reinterpret_cast<const float4*>(li + j);
+        const float4 l1 = *reinterpret_cast<const float4*>(li + j + 4);
+        a0 = fmaf(-l0.x, cols[j * 128 + threadIdx.x], a0);
+        a1 = fmaf(-l0.y, cols[(j + 1) * 128 + threadIdx.x], a1);
+        a2 = fmaf(-l0.z, cols[(j + 2) * 128 + threadIdx.x], a2);
+        a3 = fmaf(-l0.w, cols[(j + 3) * 128 + threadIdx.x], a3);
+        a4 = fmaf(-l1.x, cols[(j + 4) * 128 + threadIdx.x], a4);
+        a5 = fmaf(-l1.y, cols[(j + 5) * 128 + threadIdx.x], a5);
+        a6 = fmaf(-l1.z, cols[(j + 6) * 128 + threadIdx.x], a6);
+        a7 = fmaf(-l1.w, cols[(j + 7) * 128 + threadIdx.x], a7);
+      }
+      for (; j < i; ++j) a0 = fmaf(-li[j], cols[j * 128 + threadIdx.x], a0);
+      const float q = (((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7))) / li[i];
+      cols[i * 128 + threadIdx.x] = q;
+      Q[(size_t)i * d + c] = q;
+    }
+  }
+}
+// fallback for k too large for the shared-memory column block
+__global__ void __launch_bounds__(128)
+fd_trsm_rows_global_kernel(const float* __restrict__ l_all, const float* yt_all, float* qt_all,
+                           int k, int d, int k_ld) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const float* L = l_all + (size_t)b * k * k;
+  const float* Y = yt_all + (size_t)b * k_ld * d;
+  float* Q = qt_all + (size_t)b * k_ld * d;
+  for (int i = 0; i < k; ++i) {
+    const float* li = L + (size_t)i * k;
+    float a0 = Y[(size_t)i * d + c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = 0;
+    for (; j + 4 <= i; j += 4) {
+      a0 = fmaf(-__ldg(li + j), Q[(size_t)j * d + c], a0);
+      a1 = fmaf(-__ldg(li + j + 1), Q[(size_t)(j + 1) * d + c], a1);
+      a2 = fmaf(-__ldg(li + j + 2), Q[(size_t)(j + 2) * d + c], a2);
+      a3 = fmaf(-__ldg(li + j + 3), Q[(size_t)(j + 3) * d + c], a3);
+    }
+    for (; j < i; ++j) a0 = fmaf(-__ldg(li + j), Q[(size_t)j * d + c], a0);
+    Q[(size_t)i * d + c] = ((a0 + a1) + (a2 + a3)) / __ldg(li + i);
+  }
+}
+static int fd_trsm_rows(const float* l, const float* yt, float* qt, int k, int k_ld, int d,
+                        int batch, cudaStream_t stream) {
+  const size_t bytes = ((size_t)k * 128 + (size_t)kTrsmRows * ((k + 3) & ~3)) * sizeof(float);
+  dim3 grid((d + 127) / 128, batch);
+  if (bytes <= kCholSmemMax) {
+    static bool configured = false;
+    if (!configured) {
+      PC_CUDA_CHECK(cudaFuncSetAttribute(fd_trsm_rows_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kCholSmemMax));
+      configured = true;
+    }
+    fd_trsm_rows_kernel<<<grid, 128, bytes, stream>>>(l, yt, qt, k, d, k_ld);
+  } else {
+    fd_trsm_rows_global_kernel<<<grid, 128, 0, stream>>>(l, yt, qt, k, d, k_ld);
+  }
+  count_launch(1);
+  return PC_OK;
+}
+
+// ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
 struct FdPlan {
@@ -463,7 +645,42 @@ struct FdWorkspace {
   float* sorted; int* order; float* rscale; float* yt; float* qt; float* pt; float* small;
   float* zsel; float* vtop;
   char* tcws; size_t tcws_bytes;  // tcgen05 grouped-GEMM workspace of the covariance build
+  // subspace path on the tensor cores: the [k, d] blocks are allocated with k_ld = k rounded up
+  // to 128 rows (zero rows) so that the long-contraction products run on the grouped GEMM
+  int k_ld;
+  float* gram_pad;                 // [batch, k_ld, k_ld]
+  char* tcws_gram; size_t tcws_gram_bytes;  // Gram of Yt (plan reused across iterations)
+  char* tcws_c; size_t tcws_c_bytes;        // Qt C (plan reused across iterations)
+  char* tcws_misc; size_t tcws_misc_bytes;  // one-off plans (Gram of Qt, Ritz matrix)
 };
+
+// descriptors of the subspace products on the tcgen05 grouped GEMM
+static void fd_sub_descs(const float* x, const float* y, float* dst, int batch, int k_ld, int d,
+                         std::vector<pc_gemm_desc>* out) {  // dst [k_ld, k_ld] = X Y^T over d
+  for (int b = 0; b < batch; ++b) {
+    pc_gemm_desc g{};
+    g.a = x + (size_t)b * k_ld * d; g.b = y + (size_t)b * k_ld * d;
+    g.c = dst + (size_t)b * k_ld * k_ld; g.c_in = nullptr;
+    g.a_iinner = k_ld; g.a_sio = 0; g.a_si = d; g.a_kinner = g.b_kinner = d;
+    g.a_sko = g.b_sko = 0; g.a_ski = g.b_ski = 1; g.b_sj = d;
+    g.c_iinner = k_ld; g.c_sio = 0; g.c_sii = k_ld;
+    g.m = g.n = k_ld; g.k = d; g.alpha = 1.f; g.beta = 0.f;
+    out->push_back(g);
+  }
+}
+static void fd_timesc_descs(const float* x, const float* cmat, float* dst, int batch, int k_ld,
+                            int d, std::vector<pc_gemm_desc>* out) {  // dst [k_ld, d] = X C
+  for (int b = 0; b < batch; ++b) {
+    pc_gemm_desc g{};
+    g.a = x + (size_t)b * k_ld * d; g.b = cmat + (size_t)b * d * d;
+    g.c = dst + (size_t)b * k_ld * d; g.c_in = nullptr;
+    g.a_iinner = k_ld; g.a_sio = 0; g.a_si = d; g.a_kinner = g.b_kinner = d;
+    g.a_sko = g.b_sko = 0; g.a_ski = g.b_ski = 1; g.b_sj = d;  // C is symmetric: rows of C
+    g.c_iinner = k_ld; g.c_sio = 0; g.c_sii = d;
+    g.m = k_ld; g.n = d; g.k = d; g.alpha = 1.f; g.beta = 0.f;
+    out->push_back(g);
+  }
+}
 
 // descriptors of the covariance build on the tcgen05 grouped GEMM (host side, per matrix)
 static void fd_cov_descs(const float* fm, const float* bs, float* cmat, int batch, int d, int m,
@@ -513,13 +730,33 @@ static size_t fd_carve(FdWorkspace* w, char* base, int batch, int d, int m, int 
   w->sorted = (float*)take(B * k * 4);
   w->order = (int*)take(B * k * 4);
   w->rscale = (float*)take(B * k * 4);
+  w->k_ld = k;
+  w->gram_pad = nullptr;
+  w->tcws_gram = w->tcws_c = w->tcws_misc = nullptr;
+  w->tcws_gram_bytes = w->tcws_c_bytes = w->tcws_misc_bytes = 0;
   if (pl.subspace) {
-    w->yt = (float*)take(B * k * d * 4);
-    w->qt = (float*)take(B * k * d * 4);
-    w->pt = (float*)take(B * k * d * 4);
+    if (fd_use_tc(d)) w->k_ld = (k + 127) / 128 * 128;
+    const size_t kl = (size_t)w->k_ld;
+    w->yt = (float*)take(B * kl * d * 4);
+    w->qt = (float*)take(B * kl * d * 4);
+    w->pt = (float*)take(B * kl * d * 4);
     w->small = (float*)take(B * k * k * 4);
     w->zsel = (float*)take(B * (rank + 1) * k * 4);
     w->vtop = (float*)take(B * (rank + 1) * d * 4);
+    if (w->k_ld != k) {
+      w->gram_pad = (float*)take(B * kl * kl * 4);
+      std::vector<pc_gemm_desc> g1, g2;
+      fd_sub_descs(nullptr, nullptr, nullptr, batch, w->k_ld, d, &g1);
+      fd_timesc_descs(nullptr, nullptr, nullptr, batch, w->k_ld, d, &g2);
+      // (a symmetric plan packs one operand, a general one two: size for the general form)
+      for (auto& gd : g1) gd.b = reinterpret_cast<const float*>(1);
+      w->tcws_gram_bytes = tc_grouped_gemm_workspace_bytes(g1.data(), (int)g1.size()) + 1024;
+      w->tcws_misc_bytes = w->tcws_gram_bytes;
+      w->tcws_c_bytes = tc_grouped_gemm_workspace_bytes(g2.data(), (int)g2.size()) + 1024;
+      w->tcws_gram = take(w->tcws_gram_bytes);
+      w->tcws_misc = take(w->tcws_misc_bytes);
+      w->tcws_c = take(w->tcws_c_bytes);
+    }
   } else {
     w->yt = w->qt = w->pt = w->small = w->zsel = nullptr;
     w->vtop = (float*)take(B * (rank + 1) * d * 4);
@@ -601,7 +838,7 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
   fd_prepare_kernel<<<batch, 256, 0, stream>>>(prev, ps, pads, d, rank, opt->ridge_epsilon,
                                               opt->error_tolerance, opt->relative_matrix_epsilon,
                                               opt->decay, w.bs, w.scal, pl.subspace ? w.yt : nullptr,
-                                              k);
+                                              k, w.k_ld);
   count_launch(1);
   const unsigned mgrid = (unsigned)std::min<size_t>(((size_t)d * std::max(d, m) + 255) / 256, 1024);
   // ---- covariance C = Bs Bs^T + (masked) F F^T ----
@@ -658,46 +895,123 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
   } else {
     // ---- block subspace iteration with Rayleigh-Ritz ----
     const int iters = std::max(opt->subspace_iters, 1);
-    auto gemm_small_from_rows = [&](const float* x, const float* y, float* dst) {
-      FdGemm q{};  // dst [k,k] = X Y^T over the long dimension d
+    const int kl = w.k_ld;
+    const bool tc = kl != k;  // long-contraction products on the tcgen05 grouped GEMM
+    if (tc) {  // rows k .. k_ld - 1 of the blocks are zero and stay zero
+      const size_t blk = (size_t)batch * kl * d * sizeof(float);
+      PC_CUDA_CHECK(cudaMemsetAsync(w.qt, 0, blk, stream));
+      PC_CUDA_CHECK(cudaMemsetAsync(w.pt, 0, blk, stream));
+      // (yt: fd_prepare_kernel wrote rows < k; clear the padding rows)
+      for (int b = 0; b < batch; ++b)
+        PC_CUDA_CHECK(cudaMemsetAsync(w.yt + ((size_t)b * kl + k) * d, 0,
+                                      (size_t)(kl - k) * d * sizeof(float), stream));
+    }
+    std::vector<pc_gemm_desc> d_gram_y, d_gram_q, d_ritz, d_c;
+    bool plan_gram = false, plan_c = false;
+    if (tc) {
+      fd_sub_descs(w.yt, w.yt, w.gram_pad, batch, kl, d, &d_gram_y);
+      fd_sub_descs(w.qt, w.qt, w.gram_pad, batch, kl, d, &d_gram_q);
+      fd_sub_descs(w.qt, w.pt, w.gram_pad, batch, kl, d, &d_ritz);
+      fd_timesc_descs(w.qt, w.cmat, w.pt, batch, kl, d, &d_c);
+    }
+    auto compact = [&]() {
+      fd_compact_kernel<<<dim3(64, batch), 256, 0, stream>>>(w.gram_pad, kl, w.small, k);
+      count_launch(1);
+    };
+    auto gemm_small_from_rows = [&](const float* x, const float* y, float* dst) -> int {
+      if (tc) {  // dst [k,k] = X Y^T over the long dimension d (22-bit split products)
+        int rc;
+        if (x == w.yt) {
+          rc = tc_grouped_gemm(d_gram_y.data(), nullptr, batch, w.tcws_gram, w.tcws_gram_bytes,
+                               plan_gram ? 1 : 0, stream);
+          plan_gram = true;
+        } else {
+          std::vector<pc_gemm_desc>& dd = (y == w.pt) ? d_ritz : d_gram_q;
+          rc = tc_grouped_gemm(dd.data(), nullptr, batch, w.tcws_misc, w.tcws_misc_bytes, 0, stream);
+        }
+        if (rc != PC_OK) return rc;
+        compact();
+        return PC_OK;
+      }
+      FdGemm q{};
       q.alpha = 1.f; q.a = x; q.b = y; q.c = dst;
-      q.a_bs = q.b_bs = (int64_t)k * d; q.c_bs = (int64_t)k * k;
+      q.a_bs = q.b_bs = (int64_t)kl * d; q.c_bs = (int64_t)k * k;
       q.a_si = q.b_sj = d; q.a_sk = q.b_sk = 1; q.c_si = k;
       q.m = q.n = k; q.k = d;
       fd_gemm(q, batch, stream);
+      return PC_OK;
     };
     auto rotate_rows = [&](const float* coef, int rows, int64_t coef_bs, const float* rs,
                            const float* x, float* dst, int64_t dst_bs) {
       FdGemm q{};  // dst [rows, d] = diag(rs) coef [rows, k] X [k, d]
       q.alpha = 1.f; q.a = coef; q.b = x; q.c = dst; q.row_scale = rs;
-      q.a_bs = coef_bs; q.b_bs = (int64_t)k * d; q.c_bs = dst_bs; q.rs_bs = k;
+      q.a_bs = coef_bs; q.b_bs = (int64_t)kl * d; q.c_bs = dst_bs; q.rs_bs = k;
       q.a_si = k; q.a_sk = 1; q.b_sj = 1; q.b_sk = d; q.c_si = d;
       q.m = rows; q.n = d; q.k = k;
       fd_gemm(q, batch, stream);
     };
-    for (int it = 0; it < iters; ++it) {
-      // orthonormalise the rows of Yt: unit rows, Gram, eigh, Qt = S^-1/2 W^T Yt
-      fd_row_normalize_kernel<<<dim3(k, batch), 256, 0, stream>>>(w.yt, k, d);
-      count_launch(1);
-      gemm_small_from_rows(w.yt, w.yt, w.small);
-      int rc = jacobi(w.small, w.vt, k, true);
-      if (rc != PC_OK) return rc;
-      fd_orth_scale_kernel<<<batch, 256, 0, stream>>>(w.theta, k, w.rscale);
-      count_launch(1);
-      rotate_rows(w.vt, k, (int64_t)k * k, w.rscale, w.yt, w.qt, (int64_t)k * d);
-      // Pt = Qt C   (rows of Pt = C q_i)
+    // Pt = Qt C (rows of Pt = C q_i); always qt -> pt so that the tensor-core plan is reused
+    auto times_c = [&]() -> int {
+      if (tc) {
+        int rc = tc_grouped_gemm(d_c.data(), nullptr, batch, w.tcws_c, w.tcws_c_bytes,
+                                 plan_c ? 1 : 0, stream);
+        plan_c = true;
+        return rc;
+      }
       FdGemm q{};
       q.alpha = 1.f; q.a = w.qt; q.b = w.cmat; q.c = w.pt;
-      q.a_bs = (int64_t)k * d; q.b_bs = (int64_t)d * d; q.c_bs = (int64_t)k * d;
+      q.a_bs = (int64_t)kl * d; q.b_bs = (int64_t)d * d; q.c_bs = (int64_t)kl * d;
       q.a_si = d; q.a_sk = 1; q.b_sj = d; q.b_sk = 1; q.c_si = d;
       q.m = k; q.n = d; q.k = d;
       fd_gemm(q, batch, stream);
+      return PC_OK;
+    };
+    auto next_block_from_pt = [&]() -> int {  // Yt <- Pt
+      PC_CUDA_CHECK(cudaMemcpyAsync(w.yt, w.pt, (size_t)batch * kl * d * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, stream));
+      return PC_OK;
+    };
+    // PC_FD_RR_EVERY=1 restores a Rayleigh-Ritz eigen-solve in every iteration (round 1)
+    const char* rr_env = getenv("PC_FD_RR_EVERY");
+    const bool rr_every = rr_env && rr_env[0] == '1';
+    for (int it = 0; it < iters; ++it) {
+      const bool last = it + 1 == iters;
+      int rc;
+      fd_row_normalize_kernel<<<dim3(k, batch), 256, 0, stream>>>(w.yt, kl, d);
+      count_launch(1);
+      if ((rc = gemm_small_from_rows(w.yt, w.yt, w.small)) != PC_OK) return rc;
+      if (!rr_every) {
+        // Shifted Cholesky QR (unit rows: the shift is relative to a unit diagonal).  Between
+        // iterations only the SPAN of the block matters, one pass is enough; the last block is
+        // orthonormalised twice (Cholesky QR 2: orthogonality ~1e-6) before the Rayleigh-Ritz
+        // solve, which is the only k x k eigen-solve left.
+        rc = fd_cholesky_shift(w.small, k, batch, 1e-5f, stream);
+        if (rc == PC_OK) rc = fd_trsm_rows(w.small, w.yt, w.qt, k, kl, d, batch, stream);
+        if (rc != PC_OK) return rc;
+        if (!last) {
+          if ((rc = times_c()) != PC_OK) return rc;
+          if ((rc = next_block_from_pt()) != PC_OK) return rc;
+          continue;
+        }
+        if ((rc = gemm_small_from_rows(w.qt, w.qt, w.small)) != PC_OK) return rc;
+        rc = fd_cholesky_shift(w.small, k, batch, 0.f, stream);
+        if (rc == PC_OK) rc = fd_trsm_rows(w.small, w.qt, w.qt, k, kl, d, batch, stream);
+        if (rc != PC_OK) return rc;
+      } else {
+        // round-1 path: orthonormalise through an eigen-solve of the Gram matrix
+        rc = jacobi(w.small, w.vt, k, true);
+        if (rc != PC_OK) return rc;
+        fd_orth_scale_kernel<<<batch, 256, 0, stream>>>(w.theta, k, w.rscale);
+        count_launch(1);
+        rotate_rows(w.vt, k, (int64_t)k * k, w.rscale, w.yt, w.qt, (int64_t)kl * d);
+      }
+      if ((rc = times_c()) != PC_OK) return rc;
       // Rayleigh-Ritz: T = Qt Pt^T, eigh -> Zt (rows = Ritz coefficient vectors)
-      gemm_small_from_rows(w.qt, w.pt, w.small);
+      if ((rc = gemm_small_from_rows(w.qt, w.pt, w.small)) != PC_OK) return rc;
       rc = jacobi(w.small, w.vt, k);
       if (rc != PC_OK) return rc;
-      if (it + 1 < iters)  // next block: Yt = Zt Pt = (C Q Z)^T
-        rotate_rows(w.vt, k, (int64_t)k * k, nullptr, w.pt, w.yt, (int64_t)k * d);
+      if (!last)  // next block: Yt = Zt Pt = (C Q Z)^T
+        rotate_rows(w.vt, k, (int64_t)k * k, nullptr, w.pt, w.yt, (int64_t)kl * d);
     }
     fd_sort_kernel<<<batch, 512, 0, stream>>>(w.theta, k, w.order, w.sorted);
     fd_gather_rows_kernel<<<dim3(rank + 1, batch), 256, 0, stream>>>(w.vt, w.order, k, k, rank + 1,
