@@ -293,7 +293,8 @@ int pc_fd_update_batched(const float* new_grad, const float* prev, const int32_t
  *   xs [batch, d, d] f32 (lower triangle authoritative), ps [batch] i32, padding_starts [batch]
  *   i32 or NULL, compression_rank: > 0 keeps the largest eigenvalues, < 0 the smallest
  *   out [batch, d, |rank|+2] packed (eigvecs, inverted eigenvalues, const; DS:548-552),
- *   metrics [batch, 5]: error = max |U^T reg U - diag(e)| (DS:1076-1081).  d <= 512. */
+ *   metrics [batch, 5]: error = max |U^T reg U - diag(e)| (DS:1076-1081).  d <= 2048 (the
+ *   Jacobi solve runs in one thread-block cluster per matrix: fast up to 512, slow above). */
 size_t pc_low_rank_root_workspace_bytes(int batch, int d);
 int pc_low_rank_root_batched(const float* xs, const int32_t* ps, const int32_t* padding_starts,
                              int batch, int d, int compression_rank, float ridge_epsilon,
@@ -304,7 +305,7 @@ int pc_low_rank_root_batched(const float* xs, const int32_t* ps, const int32_t* 
 /* eigh-based full root, `eigh=True`: replaces matrix_inverse_pth_root_eigh (DS:943-1030).
  * Same inputs as pc_inverse_pth_root_batched, workspace from pc_low_rank_root_workspace_bytes;
  * roots [batch, d, d] = U diag(max(e, ridge)^(-1/p)) U^T, metrics error = max|U^T reg U - diag(e)|.
- * d <= 512. */
+ * d <= 2048. */
 int pc_inverse_pth_root_eigh_batched(const float* xs, const int32_t* ps,
                                      const int32_t* padding_starts, int batch, int d,
                                      float ridge_epsilon, float error_tolerance,

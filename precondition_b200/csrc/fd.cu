@@ -183,7 +183,8 @@ fd_row_normalize_kernel(float* __restrict__ x, int rows_ld, int len) {
 // cluster shares one matrix (rows live in L2, ld/st.cg) and a cluster barrier separates
 // rounds.  theta_i = <A_i, Vt_i> (Rayleigh quotient; A_i = theta_i v_i at convergence).
 // ---------------------------------------------------------------------------
-constexpr int kJacMaxN = 512;
+constexpr int kJacMaxN = 512;    // with accumulated eigenvectors (FD paths)
+constexpr int kEighMaxN = 2048;  // factor form (eigh-based roots)
 constexpr int kJacMaxSweeps = 15;
 constexpr int kJacCnt = kJacMaxSweeps + 1;  // per-matrix counters: rotations per sweep + max row norm^2
 
@@ -199,7 +200,7 @@ __device__ __forceinline__ void jac_cluster_sync(int csize) {
 
 // Q = row elements per lane (n <= 32 Q), kJacThreads = CTA size: shorter rows leave registers for
 // more warps per CTA, so that one round needs a single pass over the pairs.
-template <int Q, int kJacThreads>
+template <int Q, int kJacThreads, bool kWithV>
 __global__ void __launch_bounds__(kJacThreads)
 fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, float tol,
                  unsigned* __restrict__ rot_count, float* __restrict__ theta_all, int csize,
@@ -212,7 +213,7 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
   unsigned* cnt = rot_count + (size_t)b * kJacCnt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarp = (kJacThreads / 32) * csize, gw = crank * (kJacThreads / 32) + warp;
-  const bool with_v = vt_all != nullptr;  // without V: rows of A are a FACTOR (A = G, G^T G = T)
+  constexpr bool with_v = kWithV;  // without V: rows of A are a FACTOR (A = G, G^T G = T)
   if (with_v) {                            // Vt <- I
     for (size_t e = (size_t)crank * kJacThreads + threadIdx.x; e < (size_t)n * n;
          e += (size_t)csize * kJacThreads)
@@ -237,7 +238,7 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
         else { i = (t + p) % rounds; j = (t - p + rounds) % rounds; }
         if (i > j) { const int tmp = i; i = j; j = tmp; }
         if (j >= n) continue;  // phantom
-        float ai[Q], aj[Q], vi[Q], vj[Q];
+        float ai[Q], aj[Q], vi[kWithV ? Q : 1], vj[kWithV ? Q : 1];
         float al = 0.f, be = 0.f, ga = 0.f;
         // the V rows are fetched together with the A rows: one L2 round trip per pair instead
         // of two on the critical path of the round (most pairs rotate in the early sweeps)
@@ -246,8 +247,10 @@ fd_jacobi_kernel(float* __restrict__ a_all, float* __restrict__ vt_all, int n, f
           const int c = lane + 32 * q;
           ai[q] = c < n ? __ldcg(A + (size_t)i * n + c) : 0.f;
           aj[q] = c < n ? __ldcg(A + (size_t)j * n + c) : 0.f;
-          vi[q] = (with_v && c < n) ? __ldcg(V + (size_t)i * n + c) : 0.f;
-          vj[q] = (with_v && c < n) ? __ldcg(V + (size_t)j * n + c) : 0.f;
+          if (with_v) {
+            vi[q] = c < n ? __ldcg(V + (size_t)i * n + c) : 0.f;
+            vj[q] = c < n ? __ldcg(V + (size_t)j * n + c) : 0.f;
+          }
         }
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
@@ -776,9 +779,9 @@ static size_t fd_carve(FdWorkspace* w, char* base, int batch, int d, int m, int 
   return off + 256;
 }
 
-template <int Q, int kThreads>
-static int fd_jacobi_launch(float* a, float* vt, int n, int batch, unsigned* rot, float* theta,
-                            cudaStream_t stream, float tol, int max_sweeps) {
+template <int Q, int kThreads, bool kWithV>
+static int fd_jacobi_launch_v(float* a, float* vt, int n, int batch, unsigned* rot, float* theta,
+                              cudaStream_t stream, float tol, int max_sweeps) {
   int csize = 1;
   while (csize < 8 && (kThreads / 32) * csize < (n + 1) / 2) csize <<= 1;
   cudaLaunchConfig_t cfg{};
@@ -793,10 +796,18 @@ static int fd_jacobi_launch(float* a, float* vt, int n, int batch, unsigned* rot
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fd_jacobi_kernel<Q, kThreads>, a, vt, n, tol, rot, theta,
-                                   csize, max_sweeps));
+  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fd_jacobi_kernel<Q, kThreads, kWithV>, a, vt, n, tol, rot,
+                                   theta, csize, max_sweeps));
   count_launch(1);
   return PC_OK;
+}
+template <int Q, int kThreads>
+static int fd_jacobi_launch(float* a, float* vt, int n, int batch, unsigned* rot, float* theta,
+                            cudaStream_t stream, float tol, int max_sweeps) {
+  return vt ? fd_jacobi_launch_v<Q, kThreads, true>(a, vt, n, batch, rot, theta, stream, tol,
+                                                    max_sweeps)
+            : fd_jacobi_launch_v<Q, kThreads, false>(a, vt, n, batch, rot, theta, stream, tol,
+                                                     max_sweeps);
 }
 
 static int fd_jacobi(float* a, float* vt, int n, int batch, unsigned* rot, float* theta,
@@ -805,7 +816,17 @@ static int fd_jacobi(float* a, float* vt, int n, int batch, unsigned* rot, float
   if (n <= 128) return fd_jacobi_launch<4, 512>(a, vt, n, batch, rot, theta, stream, tol, max_sweeps);
   if (n <= 256) return fd_jacobi_launch<8, 640>(a, vt, n, batch, rot, theta, stream, tol, max_sweeps);
   if (n <= 384) return fd_jacobi_launch<12, 640>(a, vt, n, batch, rot, theta, stream, tol, max_sweeps);
-  return fd_jacobi_launch<16, 512>(a, vt, n, batch, rot, theta, stream, tol, max_sweeps);
+  if (n <= 512) return fd_jacobi_launch<16, 512>(a, vt, n, batch, rot, theta, stream, tol, max_sweeps);
+  // Larger factors (the eigh-based roots up to 2048 x 2048): rows of 32 / 64 elements per lane,
+  // factor form only (no accumulated V: the rotated rows ARE sigma_i u_i^T).  Correct but slow --
+  // one cluster of 8 CTAs per matrix, every rotation streams two rows through L2.
+  if (vt != nullptr || n > kEighMaxN) {
+    set_error("Jacobi eigen-solve with accumulated vectors supports n <= %d (n = %d)", kJacMaxN, n);
+    return PC_ERR_UNSUPPORTED;
+  }
+  if (n <= 1024)
+    return fd_jacobi_launch_v<32, 512, false>(a, nullptr, n, batch, rot, theta, stream, tol, max_sweeps);
+  return fd_jacobi_launch_v<64, 256, false>(a, nullptr, n, batch, rot, theta, stream, tol, max_sweeps);
 }
 
 int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
@@ -1390,8 +1411,8 @@ int pc_low_rank_root_batched(const float* xs, const int32_t* ps, const int32_t* 
   PC_REQUIRE(xs && ps && out && workspace, "null pointer argument");
   PC_REQUIRE(k + 2 < d, "low-rank root needs |rank| + 2 < d (DS:535-537), got rank=%d d=%d",
              compression_rank, d);
-  PC_REQUIRE(d <= pc::kJacMaxN, "low-rank root supports d <= %d (one Jacobi solve), got %d",
-             pc::kJacMaxN, d);
+  PC_REQUIRE(d <= pc::kEighMaxN, "low-rank root supports d <= %d (one Jacobi solve), got %d",
+             pc::kEighMaxN, d);
   return pc::run_low_rank_root(xs, ps, padding_starts, batch, d, compression_rank, false,
                                ridge_epsilon, error_tolerance, relative_matrix_epsilon, out,
                                metrics, workspace, workspace_bytes, (cudaStream_t)stream);
@@ -1405,8 +1426,8 @@ int pc_inverse_pth_root_eigh_batched(const float* xs, const int32_t* ps,
   PC_REQUIRE(batch >= 0 && d > 0, "bad eigh root sizes");
   if (batch == 0) return PC_OK;
   PC_REQUIRE(xs && ps && roots && workspace, "null pointer argument");
-  PC_REQUIRE(d <= pc::kJacMaxN, "eigh root supports d <= %d (one Jacobi solve), got %d",
-             pc::kJacMaxN, d);
+  PC_REQUIRE(d <= pc::kEighMaxN, "eigh root supports d <= %d (one Jacobi solve), got %d",
+             pc::kEighMaxN, d);
   return pc::run_low_rank_root(xs, ps, padding_starts, batch, d, 0, true, ridge_epsilon,
                                error_tolerance, relative_matrix_epsilon, roots, metrics, workspace,
                                workspace_bytes, (cudaStream_t)stream);

@@ -297,7 +297,7 @@ def power_iteration(xs: torch.Tensor, padding_starts=None, num_iters: int = 100,
   return lam, its
 
 
-EIGH_MAX_DIM = 512  # largest statistic of the Cholesky + Jacobi eigh pipeline (one cluster)
+EIGH_MAX_DIM = 2048  # largest statistic of the Cholesky + Jacobi eigh pipeline (one cluster)
 
 
 def quantize(x: torch.Tensor, qdtype: torch.dtype, extract_diagonal: bool = False, out=None):

@@ -407,3 +407,30 @@ def test_small_root_engine_retries_and_failures():
     assert (np.isnan(m1[b, 0]) or m1[b, 0] >= 0.1) == (np.isnan(m2[b, 0]) or m2[b, 0] >= 0.1)
     if not bad:
       assert m1[b, 1] == wm.inverse_pth_root_iters and m1[b, 4] == wm.total_retries
+
+
+@pytest.mark.parametrize("d", [640, 1024])
+def test_eigh_roots_above_512(d):
+  """`eigh=True` / `compression_rank != 0` roots at BASELINE block sizes (DS:943-1030,
+  DS:1033-1120): factor-form Jacobi in one cluster per matrix, checked against float64 eigh."""
+  from precondition_b200 import ops
+  rng = np.random.default_rng(d)
+  xs = np.stack([gen_symmetric_matrix(rng, d, 1e3), ema_statistics(rng, d, 2 * d)]).astype(np.float32)
+  ps = [4, 2]
+  roots, m = ops.matrix_inverse_pth_root_eigh_batched(torch.as_tensor(xs).cuda(), ps)
+  packed, m2 = ops.low_rank_root_batched(torch.as_tensor(xs).cuda(), ps, 16)
+  torch.cuda.synchronize()
+  for b in range(2):
+    a = xs[b].astype(np.float64)
+    e, u = np.linalg.eigh(a)
+    ridge = 1e-6 * max(e.max(), 1e-6)
+    want = (u * np.maximum(e + ridge, ridge) ** (-1.0 / ps[b])) @ u.T
+    rel = np.linalg.norm(roots[b].cpu().numpy() - want) / np.linalg.norm(want)
+    assert rel <= 2e-3, (d, b, rel)
+    assert float(m[b, 0]) <= 1e-3 * (e.max() + ridge), (d, b, m[b])
+    # packed low-rank form: the 16 largest eigenvalues inverted, eigenvectors orthonormal
+    pk = packed[b].cpu().numpy().astype(np.float64)
+    v, inv = pk[:, :16], pk[:16, 16]
+    top = np.sort(e)[::-1][:16] + ridge
+    assert np.abs(inv - top ** (-1.0 / ps[b])).max() <= 2e-3 * np.abs(inv).max(), (d, b)
+    assert np.abs(v.T @ v - np.eye(16)).max() <= 1e-3
