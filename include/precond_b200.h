@@ -396,6 +396,32 @@ int pc_graft_momentum_grouped(const pc_graft_segment* segments, const int32_t* c
                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * SM3 (precondition/sm3.py:40-168): the diagonal-accumulator optimizer that shares the int8
+ * momentum storage with distributed_shampoo.  One parameter tensor of rank 1..4 per call:
+ *   nu = beta2 * min_axis(acc_in[axis][index_axis]) + w2 * g^2        (rank 1: acc_in[0])
+ *   update = -lr * (m' + weight_decay * param),  m' = beta1 * to_float(m) + w1 * g / sqrt(nu + eps)
+ *   acc_out[axis][i] = max of nu over the other axes                  (rank 1: nu)
+ * w = 1 - beta (or 1 if beta == 1); normalize_grads: g <- g / (|g| + 1e-16).
+ * momentum_q / momentum_bucket: the int8 QuantizedValue of the momentum (bucket over
+ * shape[1:]; both may be NULL = zero momentum); momentum_f receives m' in fp32 -- requantise it
+ * with pc_quantize_batched(rows = dims[0], cols = numel / dims[0], PC_QDTYPE_INT8).
+ * acc_out must not alias acc_in.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  double beta1, beta2;
+  float diagonal_epsilon;
+  float weight_decay;
+  float learning_rate;
+  int normalize_grads;
+} pc_sm3_options;
+size_t pc_sm3_workspace_bytes(int64_t numel);
+int pc_sm3_update(const float* grad, const float* param, const float* const* acc_in,
+                  float* const* acc_out, const int8_t* momentum_q, const float* momentum_bucket,
+                  float* momentum_f, float* update, int rank, const int32_t* dims,
+                  const pc_sm3_options* opt, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* ------------------------------------------------------------------------
  * (5) all-gather of the block-sharded roots over NVLink peer memory
  * replaces: jax.lax.all_gather of the preconditioners and metrics (DS:2876-2877; the four
  *           gathers of the quantised path, DS:3116-3122) when every rank of the batch axis

@@ -15,6 +15,7 @@ Fixtures
   fd.npz         _fd_update_root, _low_rank_root, frequent_directions_update
   optimizer.npz  distributed_shampoo(...).update trajectories for 14 configs
   shapes.npz     merge_small_dims / BlockPartitioner / Preconditioner metadata
+  sm3.npz        precondition/sm3.py update trajectories (rank 1-4 parameters, 3 option sets)
 """
 from __future__ import annotations
 
@@ -389,6 +390,35 @@ def run_eigh_roots():
   return out
 
 
+def run_sm3():
+  """Trajectories of the unmodified precondition/sm3.py (SM3:40-168): 4 steps over parameters of
+  rank 1-4, three option sets; updates, final accumulators and int8 momenta."""
+  from oracle import jax_shim
+  _, _, ref = jax_shim.import_reference(extra=("sm3",))
+  shapes = [(6, 4), (5,), (2, 3, 4), (3, 1, 2, 5)]
+  out = {}
+  for tag, kw in (("default", dict()),
+                  ("wd_norm", dict(weight_decay=0.01, normalize_grads=True, beta1=0.8)),
+                  ("beta2_one", dict(beta2=1.0, diagonal_epsilon=1e-6))):
+    rng = np.random.default_rng(7)
+    params = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    opt = ref.sm3(0.1, **kw)
+    state = opt.init(params)
+    for i, p in enumerate(params):
+      out[f"{tag}/param{i}"] = p
+    for t in range(4):
+      g = [(rng.standard_normal(s) * 10**rng.uniform(-3, 0)).astype(np.float32) for s in shapes]
+      u, state = opt.update(g, state, params)
+      for i in range(len(shapes)):
+        out[f"{tag}/grad{t}_{i}"] = g[i]
+        out[f"{tag}/update{t}_{i}"] = np.asarray(u[i])
+    for i in range(len(shapes)):
+      for ax, acc in enumerate(state.stats[i].diagonal_statistics):
+        out[f"{tag}/acc{i}_{ax}"] = np.asarray(acc)
+      out[f"{tag}/momq{i}"] = np.asarray(state.stats[i].diagonal_momentum.quantized)
+  return out
+
+
 def main():
   os.makedirs(OUT, exist_ok=True)
   sys.path.insert(0, ROOT)
@@ -400,6 +430,7 @@ def main():
       "fd.npz": run_fd,
       "optimizer.npz": run_optimizer,
       "shapes.npz": run_shapes,
+      "sm3.npz": run_sm3,
   }
   only = set(sys.argv[1:])  # optional: regenerate just the named files
   for fname, fn in jobs.items():

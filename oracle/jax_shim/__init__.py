@@ -138,6 +138,8 @@ def _np_fn(fn, drop=("precision",)):
       kwargs.pop(k, None)
     if "dtype" in kwargs and kwargs["dtype"] is not None:
       kwargs["dtype"] = _canon_dtype(kwargs["dtype"])
+    if isinstance(kwargs.get("axis"), list):  # jnp accepts a list of axes, numpy wants a tuple
+      kwargs["axis"] = tuple(kwargs["axis"])
     args = tuple(np.asarray(a) if isinstance(a, Arr) else a for a in args)
     return _wrap_out(fn(*args, **kwargs))
 
@@ -534,7 +536,7 @@ def install(x64: bool = False):
   return jax
 
 
-def import_reference(root="/root/reference", x64=False):
+def import_reference(root="/root/reference", x64=False, extra=()):
   """Imports the unmodified reference ``distributed_shampoo`` over the shim."""
   install(x64=x64)
   # ``precondition/__init__.py`` is empty apart from __version__; import the two
@@ -544,11 +546,13 @@ def import_reference(root="/root/reference", x64=False):
   pkg.__path__ = [root + "/precondition"]
   sys.modules["precondition"] = pkg
   out = {}
-  for name in ("quantization_utils", "distributed_shampoo"):
+  for name in ("quantization_utils", "distributed_shampoo") + tuple(extra):
     spec = importlib.util.spec_from_file_location(
         f"precondition.{name}", f"{root}/precondition/{name}.py")
     mod = importlib.util.module_from_spec(spec)
     sys.modules[f"precondition.{name}"] = mod
     spec.loader.exec_module(mod)
     out[name] = mod
+  if extra:
+    return (out["distributed_shampoo"], out["quantization_utils"]) + tuple(out[e] for e in extra)
   return out["distributed_shampoo"], out["quantization_utils"]

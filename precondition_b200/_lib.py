@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = (
     "pc_graft_group_chunk_elems", "pc_graft_momentum_grouped_workspace_bytes",
     "pc_graft_momentum_grouped", "pc_inverse_pth_root_enqueue", "pc_root_mode",
     "pc_select_scatter", "pc_ipc_export", "pc_ipc_open", "pc_peer_all_gather", "pc_peer_release",
+    "pc_sm3_workspace_bytes", "pc_sm3_update",
 )
 
 
@@ -94,6 +95,12 @@ class GraftSegment(ctypes.Structure):
   _fields_ = [("offset", ctypes.c_int64), ("numel", ctypes.c_int64),
               ("first_chunk", ctypes.c_int32), ("nchunks", ctypes.c_int32),
               ("has_precond", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class Sm3Options(ctypes.Structure):
+  _fields_ = [("beta1", ctypes.c_double), ("beta2", ctypes.c_double),
+              ("diagonal_epsilon", ctypes.c_float), ("weight_decay", ctypes.c_float),
+              ("learning_rate", ctypes.c_float), ("normalize_grads", ctypes.c_int)]
 
 
 class IpcHandle(ctypes.Structure):
@@ -162,6 +169,11 @@ def load() -> ctypes.CDLL:
   lib.pc_select_preconditioners.restype = i32
   lib.pc_select_scatter.argtypes = [vp, vp, vp, vp, vp, f32, vp, i64, vp, i32, vp]
   lib.pc_select_scatter.restype = i32
+  lib.pc_sm3_workspace_bytes.argtypes = [i64]
+  lib.pc_sm3_workspace_bytes.restype = sz
+  lib.pc_sm3_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp,
+                                ctypes.POINTER(Sm3Options), vp, sz, vp]
+  lib.pc_sm3_update.restype = i32
   lib.pc_ipc_export.argtypes = [vp, ctypes.POINTER(IpcHandle)]
   lib.pc_ipc_export.restype = i32
   lib.pc_ipc_open.argtypes = [ctypes.POINTER(IpcHandle), ctypes.POINTER(ctypes.c_void_p)]

@@ -434,3 +434,38 @@ def test_eigh_roots_above_512(d):
     top = np.sort(e)[::-1][:16] + ridge
     assert np.abs(inv - top ** (-1.0 / ps[b])).max() <= 2e-3 * np.abs(inv).max(), (d, b)
     assert np.abs(v.T @ v - np.eye(16)).max() <= 1e-3
+
+
+@pytest.mark.parametrize("tag,kw", [("default", dict()),
+                                    ("wd_norm", dict(weight_decay=0.01, normalize_grads=True, beta1=0.8)),
+                                    ("beta2_one", dict(beta2=1.0, diagonal_epsilon=1e-6))])
+def test_sm3_matches_reference_golden(tag, kw):
+  """precondition_b200.sm3 (pc_sm3_update + int8 requantisation) against trajectories of the
+  unmodified precondition/sm3.py: updates of 4 steps, final accumulators, int8 momenta."""
+  from precondition_b200 import sm3 as S
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sm3.npz"))
+  shapes = [(6, 4), (5,), (2, 3, 4), (3, 1, 2, 5)]
+  params = [torch.as_tensor(g[f"{tag}/param{i}"]).cuda() for i in range(len(shapes))]
+  opt = S.sm3(0.1, **kw)
+  state = opt.init(params)
+  exact = not kw.get("normalize_grads")  # the gradient norm is summed in another order
+  for t in range(4):
+    grads = [torch.as_tensor(g[f"{tag}/grad{t}_{i}"]).cuda() for i in range(len(shapes))]
+    u, state = opt.update(grads, state, params)
+    torch.cuda.synchronize()
+    for i in range(len(shapes)):
+      got, want = u[i].cpu().numpy(), g[f"{tag}/update{t}_{i}"]
+      if exact:
+        assert np.array_equal(got, want), (tag, t, i, np.abs(got - want).max())
+      else:  # one int8 momentum quantum at most
+        assert np.abs(got - want).max() <= 0.1 * np.abs(want).max() / 100, (tag, t, i)
+  for i in range(len(shapes)):
+    for ax, acc in enumerate(state.stats[i].diagonal_statistics):
+      want = g[f"{tag}/acc{i}_{ax}"]
+      if exact:
+        assert np.array_equal(acc.cpu().numpy(), want)
+      else:
+        assert np.allclose(acc.cpu().numpy(), want, rtol=1e-5)
+    if exact:
+      assert np.array_equal(state.stats[i].diagonal_momentum.quantized.cpu().numpy(),
+                            g[f"{tag}/momq{i}"])

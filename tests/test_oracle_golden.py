@@ -1,6 +1,7 @@
 """Pins the CPU oracle to golden vectors recorded from the UNMODIFIED reference
 (run over ``oracle/jax_shim`` by ``oracle/gen_golden.py``).  CPU-only."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -187,3 +188,26 @@ def test_eigh_root_matches_reference_bitwise():
     assert np.float32(m.inverse_pth_root_errors) == g[f"{name}/err"]
   v, m = N.matrix_inverse_pth_root_eigh(np.eye(8, dtype=np.float32), 4, padding_start=0)
   assert np.abs(v).sum() == 0 and m.inverse_pth_root_errors == 0  # DS:1026-1030
+
+
+def test_sm3_oracle_matches_reference_golden():
+  """oracle/sm3.py == the unmodified precondition/sm3.py (recorded over the numpy shim), bit for
+  bit: updates of 4 steps, final accumulators and int8 momenta, three option sets."""
+  from oracle import sm3 as O
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sm3.npz"))
+  shapes = [(6, 4), (5,), (2, 3, 4), (3, 1, 2, 5)]
+  for tag, kw in (("default", dict()),
+                  ("wd_norm", dict(weight_decay=0.01, normalize_grads=True, beta1=0.8)),
+                  ("beta2_one", dict(beta2=1.0, diagonal_epsilon=1e-6))):
+    params = [g[f"{tag}/param{i}"] for i in range(len(shapes))]
+    opt = O.sm3(0.1, **kw)
+    state = opt.init(params)
+    for t in range(4):
+      grads = [g[f"{tag}/grad{t}_{i}"] for i in range(len(shapes))]
+      u, state = opt.update(grads, state, params)
+      for i in range(len(shapes)):
+        assert np.array_equal(u[i], g[f"{tag}/update{t}_{i}"]), (tag, t, i)
+    for i in range(len(shapes)):
+      for ax, acc in enumerate(state.stats[i].diagonal_statistics):
+        assert np.array_equal(acc, g[f"{tag}/acc{i}_{ax}"])
+      assert np.array_equal(state.stats[i].diagonal_momentum.quantized, g[f"{tag}/momq{i}"])
