@@ -396,6 +396,34 @@ int pc_graft_momentum_grouped(const pc_graft_segment* segments, const int32_t* c
                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Top-k deflation around the inverse p-th root: the `lobpcg_topk_precondition` branch of
+ * matrix_inverse_pth_root (DS:789-812, DS:889-928) and the diagnostics of DS:109-195.
+ * The top-k eigenpairs come from pc_fd_update_batched (the matrix passed as a Gram, an empty
+ * previous sketch, decay 1): `packed` below is that call's output [batch, n, k + 2].
+ *   pc_lobpcg_deflate_prep    eigvals [batch, k] out; scalars [batch, 4] = {max eigenvalue, min
+ *                             eigenvalue, absolute ridge = ridge_epsilon * max(max_ev, 1e-25),
+ *                             1 / max_ev}; s1 [batch, n, k] = V sqrt((l - l_min) / max_ev);
+ *                             a_scaled = A / max_ev.  The caller forms A' = a_scaled - s1 s1^T
+ *                             (grouped GEMM) and solves it with an ABSOLUTE epsilon ridge_epsilon.
+ *   pc_lobpcg_redeflate_prep  roots <- roots * max_ev^(-1/p); s2 = V sqrt(_pth_root_difference)
+ *                             (DS:681-699); the caller forms root - s2 s2^T (DS:896-900).
+ *   pc_root_diagnostics       InversePthRootDiagnostics (DS:109-142) of mat_m = B^p A:
+ *                             out [batch, 4] = {max, mean |diag - 1|, max, mean |offdiag|}.
+ *   pc_lobpcg_diagnostics     LOBPCGDiagnostics (DS:149-195) from av = A V [batch, n, k] and
+ *                             gram = V^T V [batch, k, k]: out [batch, 7] in field order.
+ * ------------------------------------------------------------------------ */
+int pc_lobpcg_deflate_prep(const float* packed, const float* a, int batch, int n, int k,
+                           float ridge_epsilon, int relative_matrix_epsilon, float* scalars,
+                           float* eigvals, float* s1, float* a_scaled, void* stream);
+int pc_lobpcg_redeflate_prep(const float* packed, const float* scalars, const float* eigvals,
+                             const int32_t* ps, int batch, int n, int k, float* roots, float* s2,
+                             void* stream);
+int pc_root_diagnostics(const float* mat_m, int batch, int n, float* out, void* stream);
+int pc_lobpcg_diagnostics(const float* packed, const float* av, const float* gram,
+                          const float* eigvals, int batch, int n, int k, float iters, float* out,
+                          void* stream);
+
+/* ------------------------------------------------------------------------
  * SM3 (precondition/sm3.py:40-168): the diagonal-accumulator optimizer that shares the int8
  * momentum storage with distributed_shampoo.  One parameter tensor of rank 1..4 per call:
  *   nu = beta2 * min_axis(acc_in[axis][index_axis]) + w2 * g^2        (rank 1: acc_in[0])

@@ -40,6 +40,8 @@ EXPORTED_SYMBOLS = (
     "pc_graft_momentum_grouped", "pc_inverse_pth_root_enqueue", "pc_root_mode",
     "pc_select_scatter", "pc_ipc_export", "pc_ipc_open", "pc_peer_all_gather", "pc_peer_release",
     "pc_sm3_workspace_bytes", "pc_sm3_update",
+    "pc_lobpcg_deflate_prep", "pc_lobpcg_redeflate_prep", "pc_root_diagnostics",
+    "pc_lobpcg_diagnostics",
 )
 
 
@@ -169,6 +171,14 @@ def load() -> ctypes.CDLL:
   lib.pc_select_preconditioners.restype = i32
   lib.pc_select_scatter.argtypes = [vp, vp, vp, vp, vp, f32, vp, i64, vp, i32, vp]
   lib.pc_select_scatter.restype = i32
+  lib.pc_lobpcg_deflate_prep.argtypes = [vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp]
+  lib.pc_lobpcg_deflate_prep.restype = i32
+  lib.pc_lobpcg_redeflate_prep.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+  lib.pc_lobpcg_redeflate_prep.restype = i32
+  lib.pc_root_diagnostics.argtypes = [vp, i32, i32, vp, vp]
+  lib.pc_root_diagnostics.restype = i32
+  lib.pc_lobpcg_diagnostics.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp]
+  lib.pc_lobpcg_diagnostics.restype = i32
   lib.pc_sm3_workspace_bytes.argtypes = [i64]
   lib.pc_sm3_workspace_bytes.restype = sz
   lib.pc_sm3_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp,

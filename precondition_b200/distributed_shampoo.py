@@ -18,8 +18,8 @@ B200-first layout decisions:
     strided view handed to the grouped GEMM (DS:1412-1422 uses jnp.split copies);
   * the per-step work is a fixed list of launches built once in ``init``.
 
-Not built yet (raise on use): LOBPCG (DS:789-812), ``shard_optimizer_states`` / pjit
-(DS:2162-2583), FD diagnostics, merged shapes of rank > 3.
+Not built yet (raise on use): ``shard_optimizer_states`` / pjit (DS:2162-2583), FD
+diagnostics (``generate_fd_metrics``), merged shapes of rank > 3.
 """
 from __future__ import annotations
 
@@ -204,9 +204,15 @@ def matrix_inverse_pth_root(matrix, p, num_iters=100, ridge_epsilon=1e-6,
                             relative_matrix_epsilon=True, lobpcg_topk_precondition=0,
                             lobpcg_max_iter=0, padding_start=None, prev=None, eigh=False):
   """DS:702-940 on one matrix -> (root, metrics row [5])."""
-  del precision, prev, lobpcg_max_iter
-  if lobpcg_topk_precondition:
-    raise NotImplementedError("the LOBPCG deflation branch is not built (SURVEY 8(f))")
+  del precision, prev
+  if lobpcg_topk_precondition:  # DS:789-812, DS:889-928
+    roots, metrics, _ = ops.matrix_inverse_pth_root_lobpcg_batched(
+        matrix[None].contiguous(), [int(p)], int(lobpcg_topk_precondition),
+        None if padding_start is None else [int(padding_start)], ridge_epsilon=ridge_epsilon,
+        error_tolerance=error_tolerance, num_iters=num_iters,
+        relative_matrix_epsilon=relative_matrix_epsilon, lobpcg_max_iter=lobpcg_max_iter,
+        diagnostics=False)
+    return roots[0], metrics[0]
   if eigh:  # matrix_inverse_pth_root_eigh, DS:943-1030
     roots, metrics = ops.matrix_inverse_pth_root_eigh_batched(
         matrix[None].contiguous(), [int(p)],
@@ -299,6 +305,32 @@ def _tree_unflatten(treedef, leaves):
   if kind == "namedtuple":
     return meta(*out)
   return meta(out)
+
+
+class InversePthRootDiagnostics(NamedTuple):
+  """DS:109-142: entrywise errors between B^p A and I for an inverse p-th root B."""
+  max_diag_error: Any = 0.0
+  avg_diag_error: Any = 0.0
+  max_off_diag_error: Any = 0.0
+  avg_off_diag_error: Any = 0.0
+  p: Any = 0.0
+
+  @classmethod
+  def create(cls, pth_inverse_root, matrix, p):
+    row = ops.root_diagnostics(pth_inverse_root[None].contiguous(), matrix[None].contiguous(),
+                               [int(p)])[0]
+    return cls(*[row[i] for i in range(5)])
+
+
+class LOBPCGDiagnostics(NamedTuple):
+  """DS:149-195: consistency |A v - l v| / (l + |A v|) and orthogonality of top-k eigenpairs."""
+  lobpcg_iters: Any = 0.0
+  max_consistency_error: Any = 0.0
+  avg_consistency_error: Any = 0.0
+  avg_orthogonality_error: Any = 0.0
+  max_eigenvalue: Any = 0.0
+  min_eigenvalue: Any = 0.0
+  num_topk_eigenvectors: Any = 0.0
 
 
 # ---------------------------------------------------------------------------
@@ -472,7 +504,8 @@ class _Shampoo:
                decoupled_weight_decay, generate_training_metrics, engine, process_group,
                frequent_directions=False, reuse_preconditioner=False, reset_frequency=None,
                average_grad=False, eigh=False, decay_preconditioning_compute_steps=False,
-               end_preconditioning_compute_steps=None):
+               end_preconditioning_compute_steps=None, lobpcg_topk_precondition=0,
+               lobpcg_max_iter=0):
     self.__dict__.update({k: v for k, v in locals().items() if k != "self"})
     # DS:2051-2064: second-moment quantisation only with a batch axis
     self.quantize_second_moment = bool(best_effort_memory_usage_reduction and
@@ -956,6 +989,16 @@ class _Shampoo:
       for bk in full:
         self._eigh_roots(bk, world, rank)
       return
+    if self.lobpcg_topk_precondition > 0:
+      # top-k deflation before the Newton iteration (DS:789-812); statistics too small for the
+      # requested k take the plain path
+      plain = [bk for bk in full if bk.size <= self.lobpcg_topk_precondition + 2]
+      for bk in full:
+        if bk not in plain:
+          self._lobpcg_roots(bk, world, rank)
+      if plain:
+        self._newton_roots(plain, world, rank)
+      return
     self._newton_roots(full, world, rank)
 
   def _padded_size(self, s):
@@ -1128,6 +1171,31 @@ class _Shampoo:
       roots, metrics = sharded_inverse_pth_roots(
           bk.stats, bk.exps, world, rank, self.process_group,
           root_fn=ops.matrix_inverse_pth_root_eigh_batched, **kw)
+    self.metrics[s].copy_(metrics)
+    self._select(bk, roots, metrics)
+
+  def _lobpcg_roots(self, bk, world, rank):
+    """`lobpcg_topk_precondition > 0`: deflated roots for a whole bucket (DS:789-812, DS:889-928);
+    the per-statistic diagnostics rows are kept in ``bk.diagnostics``."""
+    s = bk.size
+    kw = dict(ridge_epsilon=self.matrix_epsilon,
+              relative_matrix_epsilon=self.relative_matrix_epsilon, engine=self.engine,
+              lobpcg_max_iter=self.lobpcg_max_iter)
+    k = int(self.lobpcg_topk_precondition)
+    if self.quantize_second_moment:
+      q, d, b = bk.qstats
+      ops.dequantize(q, d, b, True, out=bk.stats)
+    if world == 1:
+      roots, metrics, diag = ops.matrix_inverse_pth_root_lobpcg_batched(
+          bk.stats, bk.exps_host, k, None, diagnostics=self.generate_training_metrics, **kw)
+      bk.diagnostics = diag
+    else:
+      def fn(x, p, pd, **k2):
+        r, m, _ = ops.matrix_inverse_pth_root_lobpcg_batched(x, p.cpu(), k, pd, diagnostics=False,
+                                                             **k2)
+        return r, m
+      roots, metrics = sharded_inverse_pth_roots(bk.stats, bk.exps, world, rank,
+                                                 self.process_group, root_fn=fn, **kw)
     self.metrics[s].copy_(metrics)
     self._select(bk, roots, metrics)
 
@@ -1392,7 +1460,7 @@ def distributed_shampoo(
   ``export_state`` copy, a deep copy -- is supported: it is copied into the buffers first.
   The returned object also carries ``export_state(state)`` and ``import_state(state)``.
   """
-  del precision, tensordot_precision, lobpcg_max_iter, statistics_partition_spec
+  del precision, tensordot_precision, statistics_partition_spec
   del preconditioner_partition_spec, num_devices_for_pjit
   if generate_fd_metrics and frequent_directions:  # DS:2026: ignored without frequent_directions
     raise NotImplementedError(
@@ -1416,8 +1484,7 @@ def distributed_shampoo(
   if exponent_override and not 1 <= int(exponent_override) <= 16:
     raise ValueError(f"exponent_override={exponent_override} is outside [1, 16], the range of "
                      "the Newton step programs (pc_inverse_pth_root_batched)")
-  for name, val in (("lobpcg_topk_precondition", lobpcg_topk_precondition),
-                    ("shard_optimizer_states", shard_optimizer_states)):
+  for name, val in (("shard_optimizer_states", shard_optimizer_states),):
     if val:
       raise NotImplementedError(
           f"{name} is not built in the B200 hot path yet (see DESIGN.md, out of scope table)")
@@ -1438,7 +1505,8 @@ def distributed_shampoo(
                  decoupled_weight_decay, generate_training_metrics, engine, process_group,
                  frequent_directions, reuse_preconditioner, reset_frequency, average_grad,
                  bool(eigh), bool(decay_preconditioning_compute_steps),
-                 end_preconditioning_compute_steps)
+                 end_preconditioning_compute_steps, int(lobpcg_topk_precondition),
+                 int(lobpcg_max_iter))
   tx = ShampooTransformation(opt.init, opt.update)
   tx.export_state, tx.import_state = opt.export_state, opt.import_state
   return tx

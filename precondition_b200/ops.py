@@ -555,3 +555,140 @@ class GraftGroup:
           _ptr(momentum), _ptr(update), ctypes.byref(opt), _ptr(self.ws), self.ws.numel(),
           ctypes.c_void_p(_stream())))
     gpu_launches += 1
+
+
+def batched_matmul(a: torch.Tensor, b: torch.Tensor, transpose_b: bool = False,
+                   alpha: float = 1.0, c_in: Optional[torch.Tensor] = None, beta: float = 0.0,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """C[z] = alpha * A[z] @ (B[z] or B[z]^T) + beta * C_in[z] through the grouped GEMM (tcgen05
+  when the output sizes are multiples of 128, fp32 CUDA cores otherwise).  a [bt, m, k];
+  b [bt, k, n] (or [bt, n, k] with transpose_b)."""
+  _require_cuda(a, b, c_in, out)
+  bt, m, k = a.shape
+  n = b.shape[1] if transpose_b else b.shape[2]
+  assert (b.shape[2] if transpose_b else b.shape[1]) == k and b.shape[0] == bt
+  c = out if out is not None else torch.empty((bt, m, n), dtype=torch.float32, device=a.device)
+  descs = []
+  for z in range(bt):
+    d = _lib.GemmDesc()
+    d.a = a[z].data_ptr()
+    d.b = b[z].data_ptr()
+    d.c = c[z].data_ptr()
+    d.c_in = None if c_in is None else c_in[z].data_ptr()
+    d.a_iinner, d.a_sio, d.a_si = m, 0, k
+    d.a_kinner, d.a_sko, d.a_ski = k, 0, 1
+    if transpose_b:   # B(j, kk) = b[j, kk]
+      d.b_sj, d.b_kinner, d.b_sko, d.b_ski = k, k, 0, 1
+    else:             # B(j, kk) = b[kk, j]
+      d.b_sj, d.b_kinner, d.b_sko, d.b_ski = 1, k, 0, n
+    d.c_iinner, d.c_sio, d.c_sii = m, 0, n
+    d.m, d.n, d.k, d.alpha, d.beta = m, n, k, alpha, beta
+    descs.append(d)
+  use_tc = bool(_lib.load().pc_device_supports_tcgen05()) and all(tc_gemm_eligible(d) for d in descs)
+  (TcGemmList(descs, a.device) if use_tc else SimtGemmLists(descs, a.device)).run()
+  return c
+
+
+def _lobpcg_call(fn, *args):
+  global gpu_launches
+  _lib.check(fn(*args, ctypes.c_void_p(_stream())))
+  gpu_launches += 1
+
+
+def root_diagnostics(root: torch.Tensor, matrix: torch.Tensor, ps) -> torch.Tensor:
+  """InversePthRootDiagnostics (DS:109-142) for a batch: rows {max_diag_error, avg_diag_error,
+  max_off_diag_error, avg_off_diag_error, p} of M = root^p @ matrix (mat_power order, DS:655-678)."""
+  lib = _lib.load()
+  bt, n = root.shape[0], root.shape[1]
+  ps_list = [int(x) for x in (ps.tolist() if isinstance(ps, torch.Tensor) else ps)]
+  out = torch.zeros((bt, 5), dtype=torch.float32, device=root.device)
+  mat_m = torch.empty_like(root)
+  for p in sorted(set(ps_list)):
+    idx = [z for z, q in enumerate(ps_list) if q == p]
+    sel = torch.tensor(idx, device=root.device)
+    r, mtx = root[sel].contiguous(), matrix[sel].contiguous()
+    power, mat, i = None, r, p
+    while i > 0:
+      if i % 2 == 1:
+        power = mat if power is None else batched_matmul(mat, power)
+      i //= 2
+      if i > 0:
+        mat = batched_matmul(mat, mat)
+    mat_m[sel] = batched_matmul(power, mtx)
+    out[sel, 4] = float(p)
+  out4 = torch.empty((bt, 4), dtype=torch.float32, device=root.device)
+  with torch.cuda.device(root.device):
+    _lobpcg_call(lib.pc_root_diagnostics, _ptr(mat_m), bt, n, _ptr(out4))
+  out[:, :4] = out4
+  return out
+
+
+def matrix_inverse_pth_root_lobpcg_batched(
+    xs: torch.Tensor, ps, topk: int, padding_starts=None, ridge_epsilon: float = 1e-6,
+    error_tolerance: float = 1e-6, num_iters: int = 100, relative_matrix_epsilon: bool = True,
+    engine: int = _lib.PC_ENGINE_AUTO, lobpcg_max_iter: int = 0, diagnostics: bool = True):
+  """matrix_inverse_pth_root with ``lobpcg_topk_precondition = topk`` (DS:789-812, DS:889-928):
+  the top-k eigenpairs are deflated out of every matrix before the coupled Newton iteration
+  (lower condition number -> fewer iterations) and put back into the root afterwards.
+
+  Returns (roots [b,n,n], metrics [b,5], diag) with diag = {"lobpcg": [b,7] LOBPCGDiagnostics
+  rows, "inverse_pth_root": [b,5], "conditioned_inverse_pth_root": [b,5]} (None without
+  ``diagnostics``).  As in the reference, ``metrics[:, 0]`` is then the entrywise error of the
+  UNCONDITIONED problem (DS:913-921) and ``metrics[:, 3]`` the largest deflated eigenvalue."""
+  lib = _lib.load()
+  _require_cuda(xs)
+  b, n = xs.shape[0], xs.shape[1]
+  k = int(topk)
+  if not 1 <= k < n - 2:
+    raise ValueError(f"lobpcg_topk_precondition = {k} needs 1 <= k < n - 2 (n = {n})")
+  dev = xs.device
+  ps_t, ps_host = _as_i32_device(ps, dev)
+  iters = lobpcg_max_iter if lobpcg_max_iter > 0 else max(8, min(k, 16))
+  prev = torch.zeros((b, n, k + 2), dtype=torch.float32, device=dev)
+  # top-k eigenpairs: block subspace iteration (exact Jacobi eigh for n <= 512) on the matrix
+  packed, _ = fd_update_root_batched(xs, prev, ps_t, k, padding_starts, ridge_epsilon=0.0,
+                                     relative_matrix_epsilon=False, decay=1.0,
+                                     input_is_gram=True, subspace_iters=iters)
+  scal = torch.empty((b, 4), dtype=torch.float32, device=dev)
+  eig = torch.empty((b, k), dtype=torch.float32, device=dev)
+  s1 = torch.empty((b, n, k), dtype=torch.float32, device=dev)
+  a_scaled = torch.empty_like(xs)
+  with torch.cuda.device(dev):
+    _lobpcg_call(lib.pc_lobpcg_deflate_prep, _ptr(packed), _ptr(xs), b, n, k, float(ridge_epsilon),
+                 int(relative_matrix_epsilon), _ptr(scal), _ptr(eig), _ptr(s1), _ptr(a_scaled))
+  # deflate: A' = A / m - S1 S1^T  (DS:805-812)
+  deflated = batched_matmul(s1, s1, transpose_b=True, alpha=-1.0, c_in=a_scaled, beta=1.0)
+  eps_abs = ridge_epsilon if relative_matrix_epsilon else None
+  roots, metrics = matrix_inverse_pth_root_batched(
+      deflated, ps_t, padding_starts, ridge_epsilon=ridge_epsilon, error_tolerance=error_tolerance,
+      num_iters=num_iters, relative_matrix_epsilon=False, engine=engine, ps_host=ps_host)
+  del eps_abs
+  diag = None
+  if diagnostics:
+    # conditioned problem (scaled units: root^p (A' + eps 10^t I) is scale invariant), DS:903-906
+    tries = metrics[:, 4].clamp_min(1.0) - 1.0
+    damped = deflated.clone()
+    damped.diagonal(dim1=1, dim2=2).add_((ridge_epsilon * 10.0 ** tries)[:, None])
+    cond = root_diagnostics(roots, damped, ps_host if ps_host is not None else ps_t)
+  s2 = torch.empty_like(s1)
+  with torch.cuda.device(dev):
+    _lobpcg_call(lib.pc_lobpcg_redeflate_prep, _ptr(packed), _ptr(scal), _ptr(eig), _ptr(ps_t), b, n,
+                 k, _ptr(roots), _ptr(s2))
+  final = batched_matmul(s2, s2, transpose_b=True, alpha=-1.0, c_in=roots, beta=1.0)  # DS:896-900
+  metrics = metrics.clone()
+  metrics[:, 3] = scal[:, 0]  # max_eigen_value: from the deflated eigenvalues (DS:815-816)
+  if diagnostics:
+    undamped = xs.clone()
+    undamped.diagonal(dim1=1, dim2=2).add_(scal[:, 2][:, None])  # original + ridge I, DS:907
+    uncond = root_diagnostics(final, undamped, ps_host if ps_host is not None else ps_t)
+    vecs = packed[:, :, :k].contiguous()
+    av = batched_matmul(xs, vecs)
+    gram = batched_matmul(vecs.transpose(1, 2).contiguous(), vecs)
+    lob = torch.empty((b, 7), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+      _lobpcg_call(lib.pc_lobpcg_diagnostics, _ptr(packed), _ptr(av), _ptr(gram), _ptr(eig), b, n, k,
+                   float(iters), _ptr(lob))
+    # DS:913-921: report the error of the unconditioned problem
+    metrics[:, 0] = torch.maximum(uncond[:, 0], uncond[:, 2])
+    diag = {"lobpcg": lob, "inverse_pth_root": uncond, "conditioned_inverse_pth_root": cond}
+  return final, metrics, diag

@@ -469,3 +469,53 @@ def test_sm3_matches_reference_golden(tag, kw):
     if exact:
       assert np.array_equal(state.stats[i].diagonal_momentum.quantized.cpu().numpy(),
                             g[f"{tag}/momq{i}"])
+
+
+@pytest.mark.parametrize("n,k", [(128, 8), (640, 16)])
+def test_lobpcg_deflated_root_matches_float64(n, k):
+  """`lobpcg_topk_precondition`: deflating the top-k eigenpairs before the Newton iteration and
+  re-inserting them afterwards (DS:789-812, DS:889-928) gives the same root as the exact
+  float64 inverse root, with fewer iterations on a spectrum with a few dominant directions."""
+  from precondition_b200 import ops
+  rng = np.random.default_rng(n + k)
+  u = np.linalg.qr(rng.standard_normal((n, n)))[0]
+  spec = np.concatenate([np.logspace(3, 1.5, k), np.linspace(1.0, 0.2, n - k)])
+  xs = np.stack([(u * spec) @ u.T, (u * spec[::-1].copy()) @ u.T * 3.0]).astype(np.float32)
+  ps = [4, 2]
+  a = torch.as_tensor(xs).cuda()
+  roots, m, diag = ops.matrix_inverse_pth_root_lobpcg_batched(a, ps, k)
+  plain, m0 = ops.matrix_inverse_pth_root_batched(a, ps)
+  torch.cuda.synchronize()
+  for b in range(2):
+    e, v = np.linalg.eigh(xs[b].astype(np.float64))
+    ridge = 1e-6 * e.max()
+    want = (v * (e + ridge) ** (-1.0 / ps[b])) @ v.T
+    rel = np.linalg.norm(roots[b].cpu().numpy() - want) / np.linalg.norm(want)
+    assert rel <= 1e-3, (n, b, rel)
+    assert float(m[b, 1]) < float(m0[b, 1]), (m[b], m0[b])        # deflation saves iterations
+    assert abs(float(m[b, 3]) - e.max()) <= 1e-3 * e.max()         # max_eigen_value from top-k
+    assert float(m[b, 0]) <= 2e-2  # unconditioned entrywise error of B^p (A + eps I) in fp32 (kappa ~5e3)
+    lob = diag["lobpcg"][b].cpu().numpy()
+    assert lob[6] == k and lob[1] <= 1e-3 and abs(lob[3]) <= 1e-4   # consistent, orthonormal
+    assert abs(lob[4] - e.max()) <= 1e-3 * e.max()
+    assert float(diag["inverse_pth_root"][b, 4]) == ps[b]
+    assert float(diag["conditioned_inverse_pth_root"][b, 2]) <= 1e-3
+
+
+def test_lobpcg_option_in_optimizer_matches_plain_roots():
+  from precondition_b200 import distributed_shampoo as DS
+  dev = torch.device("cuda", 0)
+  gen = torch.Generator(device=dev).manual_seed(5)
+  params = [torch.randn(96, 64, generator=gen, device=dev) * 0.1]
+  a = DS.distributed_shampoo(0.1, 128, start_preconditioning_step=1, lobpcg_topk_precondition=4)
+  b = DS.distributed_shampoo(0.1, 128, start_preconditioning_step=1)
+  sa, sb = a.init(params), b.init(params)
+  for t in range(4):
+    g = [torch.randn(96, 64, generator=gen, device=dev) * 1e-2]
+    ua, sa = a.update(g, sa, params)
+    ub, sb = b.update(g, sb, params)
+    torch.cuda.synchronize()
+    assert float((ua[0] - ub[0]).abs().max() / ub[0].abs().max()) <= 2e-3, t
+  r = DS.matrix_inverse_pth_root(sa.stats[0].statistics[0], 4, lobpcg_topk_precondition=4)[0]
+  want = sb.stats[0].preconditioners[0]
+  assert float((r - want).norm() / want.norm()) <= 1e-3

@@ -66,7 +66,7 @@ def test_statistic_inventory_of_baseline_configs():
 
 
 def test_unsupported_options_fail_loudly():
-  for kw in (dict(lobpcg_topk_precondition=2), dict(shard_optimizer_states=True)):
+  for kw in (dict(shard_optimizer_states=True),):
     with pytest.raises(NotImplementedError):
       DS.distributed_shampoo(0.1, 32, **kw)
 
