@@ -18,8 +18,11 @@ B200-first layout decisions:
     strided view handed to the grouped GEMM (DS:1412-1422 uses jnp.split copies);
   * the per-step work is a fixed list of launches built once in ``init``.
 
-Not built yet (raise on use): ``shard_optimizer_states`` / pjit (DS:2162-2583), FD
-diagnostics (``generate_fd_metrics``), merged shapes of rank > 3.
+``shard_optimizer_states=True`` (the pjit path, DS:2162-2583) is the stacked layout: one
+padded-to-max array of statistics whose leading axis is sharded over the ranks (each rank
+stores and updates only its rows), roots computed where the rows live, preconditioners
+all-gathered.  Not built (raise on use): FD diagnostics (``generate_fd_metrics``), merged
+shapes of rank > 3.
 """
 from __future__ import annotations
 
@@ -292,6 +295,17 @@ def _tree_flatten(tree):
   raise TypeError(f"unsupported pytree node {type(tree)}")
 
 
+def _tree_flatten_any(tree, leaf_type):
+  """Leaves of `tree` that are instances of `leaf_type` (dict / list / tuple containers)."""
+  if isinstance(tree, leaf_type):
+    return [tree]
+  if isinstance(tree, dict):
+    return [x for k in sorted(tree.keys()) for x in _tree_flatten_any(tree[k], leaf_type)]
+  if isinstance(tree, (list, tuple)):
+    return [x for v in tree for x in _tree_flatten_any(v, leaf_type)]
+  return []
+
+
 def _tree_unflatten(treedef, leaves):
   if treedef is None:
     return leaves[0]
@@ -305,6 +319,37 @@ def _tree_unflatten(treedef, leaves):
   if kind == "namedtuple":
     return meta(*out)
   return meta(out)
+
+
+class GlobalShardedParameterStats(NamedTuple):  # DS:382-386
+  """Sharded mode: one stacked, padded-to-max array per kind; the leading axis is sharded over
+  the devices.  In this implementation ``statistics`` holds THIS rank's rows
+  ``[N / D, max, max]`` (row ``i`` is global row ``rank * N / D + i``), ``preconditioners`` all
+  ``[N, max, max]`` rows (every rank applies all of them), ``exponents`` all ``[N]``."""
+  statistics: Any
+  preconditioners: Any
+  exponents: Any
+
+
+class LocalShardedParameterStats(NamedTuple):  # DS:391-402
+  diagonal_statistics: Any
+  diagonal_momentum: Any
+  momentum: Any
+  avg_grad: Any
+  training_metrics: Any
+  index_start: int  # first row of this parameter in the global arrays
+  sizes: Any        # true sizes of its statistics
+
+
+class ShardedShampooStats(NamedTuple):  # DS:482-485
+  global_stats: Any
+  local_stats: Any
+
+
+class InitFnState(NamedTuple):  # DS:493-496
+  init_fn: Any
+  pspec_fn: Any
+  shape_and_dtype_fn: Any
 
 
 class InversePthRootDiagnostics(NamedTuple):
@@ -474,6 +519,7 @@ class _Bucket:
   def __init__(self, size, pdim):
     self.size, self.pdim = size, pdim
     self.exponents: List[int] = []
+    self.true_sizes: List[int] = []  # == size except in the stacked (sharded-state) layout
     self.count = 0
     self.job = None
 
@@ -505,7 +551,7 @@ class _Shampoo:
                frequent_directions=False, reuse_preconditioner=False, reset_frequency=None,
                average_grad=False, eigh=False, decay_preconditioning_compute_steps=False,
                end_preconditioning_compute_steps=None, lobpcg_topk_precondition=0,
-               lobpcg_max_iter=0):
+               lobpcg_max_iter=0, stacked=False, num_devices_for_pjit=None):
     self.__dict__.update({k: v for k, v in locals().items() if k != "self"})
     # DS:2051-2064: second-moment quantisation only with a batch axis
     self.quantize_second_moment = bool(best_effort_memory_usage_reduction and
@@ -573,6 +619,16 @@ class _Shampoo:
     self.sgbuf = zeros() if self.use_avg_grad else None
 
     self.plans, self.buckets = [], {}
+    max_size = 0
+    if self.stacked:  # DS:2169-2176
+      if self.compression_rank or self.best_effort_memory_usage_reduction:
+        raise NotImplementedError("shard_optimizer_states: quantised / compressed states are not "
+                                  "built in the B200 path")
+      for p in leaves:
+        if not self._skip_preconditioning(p.shape):
+          pre = Preconditioner(p.shape, self.block_size, self.merge_small_dims_block_size,
+                               self.best_effort_shape_interpretation, self.precondtioner_type, 0)
+          max_size = max([max_size] + [sh[0] for sh in pre.shapes_for_preconditioners()])
     for idx, p in enumerate(leaves):
       plan = _ParamPlan()
       plan.index, plan.offset, plan.shape, plan.numel = idx, offsets[idx], tuple(p.shape), p.numel()
@@ -586,6 +642,7 @@ class _Shampoo:
                        if self.exponent_override == 0 else self.exponent_override)
       plan.mdt = self._momentum_dtype(p)
       plan.stat_refs = []  # (bucket size, index in bucket) in reference order
+      plan.stat_sizes = []
       plan.blocks = []
       if not plan.skip:
         if len(plan.tshape) > 3:
@@ -601,18 +658,37 @@ class _Shampoo:
               refs.append(None)
               continue
             s = sizes[axis]
-            bk = self.buckets.setdefault(s, _Bucket(s, _precond_dim(self.compression_rank, s)))
-            refs.append((s, bk.count))
-            plan.stat_refs.append((s, bk.count))
+            # sharded-state mode (DS:2162-2240): ONE stacked array, every statistic padded to
+            # the largest one; otherwise one bucket per true size
+            key = max_size if self.stacked else s
+            bk = self.buckets.setdefault(key, _Bucket(key, _precond_dim(self.compression_rank, key)))
+            refs.append((key, bk.count))
+            plan.stat_refs.append((key, bk.count))
+            plan.stat_sizes.append(s)
             bk.exponents.append(plan.exponent)
+            bk.true_sizes.append(s)
             bk.count += 1
           plan.blocks.append((offs, sizes, refs))
       self.plans.append(plan)
 
     # bucket storage: statistics = matrix_epsilon * I, preconditioners = I (DS:2594-2602)
+    world, rank = self._world()
     for s, bk in self.buckets.items():
       eye = torch.eye(s, dtype=torch.float32, device=dev)
-      bk.stats = (self.matrix_epsilon * eye).repeat(bk.count, 1, 1).contiguous()
+      bk.lo, bk.n_local = 0, bk.count
+      if self.stacked:
+        # DS:2229-2256: pad the stack to a multiple of the device count with (I, exponent 1)
+        # fillers; rank r keeps the statistics rows [r N / D, (r + 1) N / D)
+        ndev = int(self.num_devices_for_pjit or world)
+        if world > 1 and ndev != world:
+          raise ValueError(f"num_devices_for_pjit={ndev} != world size {world}")
+        fill = -bk.count % ndev
+        bk.exponents += [1] * fill
+        bk.true_sizes += [0] * fill  # padding_start 0: zero root (DS:930-937)
+        bk.count += fill
+        bk.n_local = bk.count // world
+        bk.lo = rank * bk.n_local
+      bk.stats = (self.matrix_epsilon * eye).repeat(bk.n_local, 1, 1).contiguous()
       bk.compressed = bk.pdim != s  # DS:535-537: low-rank [s, rank + 2] preconditioners
       if bk.compressed:
         # packed sketches start at zero (DS:2598-2602); `precs` holds the dense operator the
@@ -660,11 +736,36 @@ class _Shampoo:
     self._own_leaves = stats
     self._own_ptrs = [[t.data_ptr() for t in _state_tensors(st)] for st in stats]
     self._built = True
-    return ShampooState(0, _tree_unflatten(treedef, stats))
+    return ShampooState(0, self._wrap_stats(stats))
+
+  def _wrap_stats(self, stats):
+    """State tree handed to the caller: per-parameter ParameterStats, or in sharded-state mode
+    ShardedShampooStats(global stacked arrays, per-parameter local stats with index_start /
+    sizes) -- DS:2243-2256.  The local entries are the same ParameterStats views (``update``
+    finds them under ``.local_stats``)."""
+    tree = _tree_unflatten(self.treedef, stats)
+    if not self.stacked:
+      return tree
+    if not self.buckets:
+      return ShardedShampooStats(GlobalShardedParameterStats(None, None, None), tree)
+    (bk,) = self.buckets.values()
+    local, start = [], 0
+    for plan, st in zip(self.plans, stats):
+      local.append(LocalShardedParameterStats(
+          st.diagonal_statistics, st.diagonal_momentum, st.momentum, st.avg_grad,
+          st.training_metrics, start, list(plan.stat_sizes)))
+      start += len(plan.stat_sizes)
+    self._sharded_local = local
+    return ShardedShampooStats(
+        GlobalShardedParameterStats(bk.stats, bk.precs, bk.exps),
+        _tree_unflatten(self.treedef, local))
 
   def _stat_view(self, ref):
     s, i = ref
     bk = self.buckets[s]
+    if self.stacked:  # padded row of the stacked array, if this rank holds it
+      j = i - bk.lo
+      return bk.stats[j] if 0 <= j < bk.n_local else None
     if self.quantize_second_moment:
       q, d, b = bk.qstats
       return QuantizedValue(q[i], d[i], b[i], self.qdt_second, True, [s, s])
@@ -749,9 +850,12 @@ class _Shampoo:
         for axis in range(rank):
           if refs[axis] is None:
             continue
-          s, bi = refs[axis]
-          bk = self.buckets[s]
-          cptr = bk.stats.data_ptr() + f32 * bi * s * s
+          S, bi = refs[axis]  # S = row stride of the bucket (== s unless stacked)
+          s = sizes[axis]
+          bk = self.buckets[S]
+          if self.stacked and not bk.lo <= bi < bk.lo + bk.n_local:
+            continue  # sharded statistics: another rank owns (and updates) this row
+          cptr = bk.stats.data_ptr() + f32 * (bi - bk.lo) * S * S
           others = [a for a in range(rank) if a != axis]
           k = int(np.prod([sizes[a] for a in others])) if others else 1
           d = D()
@@ -768,7 +872,7 @@ class _Shampoo:
           d.a_kinner = d.b_kinner = kin
           d.a_sko = d.b_sko = sko
           d.a_ski = d.b_ski = ski
-          d.c_iinner, d.c_sio, d.c_sii = s, 0, s
+          d.c_iinner, d.c_sio, d.c_sii = s, 0, S
           d.m = d.n = s
           d.k = k
           d.alpha, d.beta = w2, w1
@@ -778,7 +882,7 @@ class _Shampoo:
             # statistic slot holds x x^T itself (no QR on the device).
             d.c_in, d.alpha, d.beta = None, 1.0, 0.0
           stat_descs.append(d)
-          stat_meta.append((s, bi))
+          stat_meta.append((S, bi))
         # ---- application: contract the leading axis and roll (DS:1678-1707) ----
         bnumel = int(np.prod(sizes))
         cur_ptr, cur_strides, cur_sizes = gbase, list(strides), list(sizes)
@@ -800,13 +904,13 @@ class _Shampoo:
             d.a_iinner, d.a_sio, d.a_si = rest_sizes[1], rest_strides[0], rest_strides[1]
           # B(j = output column, k) = P[k, j]
           if refs[j] is not None:
-            s, bi = refs[j]
-            pptr = self.buckets[s].precs.data_ptr() + f32 * bi * s * s
+            S, bi = refs[j]  # row stride of the stored preconditioner
+            pptr = self.buckets[S].precs.data_ptr() + f32 * bi * S * S
           else:  # not preconditioned: pure roll (DS:1684-1686) -> multiply by I
-            s = d0
+            S = d0
             pptr = self._identity(d0).data_ptr()
           d.b = pptr
-          d.b_sj, d.b_kinner, d.b_sko, d.b_ski = 1, d0, 0, s
+          d.b_sj, d.b_kinner, d.b_sko, d.b_ski = 1, d0, 0, S
           d.m, d.n, d.k = rest, d0, d0
           d.alpha, d.beta = 1.0, 0.0
           d.c_in = None
@@ -934,12 +1038,19 @@ class _Shampoo:
       u = ubuf[plan.offset:plan.offset + plan.numel].view(plan.shape)
       updates.append(u if g.dtype == torch.float32 else u.to(g.dtype))
     return (_tree_unflatten(self.treedef, updates),
-            ShampooState(step + 1, _tree_unflatten(self.treedef, self._own_leaves)))
+            ShampooState(step + 1, self._wrap_stats(self._own_leaves)))
 
   def _flatten_stats(self, stats_tree):
     out = []
 
     def rec(t):
+      if isinstance(t, ShardedShampooStats):
+        # the local entries mirror the optimizer's own ParameterStats one to one
+        n = len(_tree_flatten_any(t.local_stats, LocalShardedParameterStats))
+        if getattr(self, "_own_leaves", None) is not None and n == len(self._own_leaves):
+          out.extend(self._own_leaves)
+          return
+        raise ValueError("sharded state does not match this optimizer")
       if isinstance(t, ParameterStats):
         out.append(t)
       elif isinstance(t, dict):
@@ -1024,14 +1135,17 @@ class _Shampoo:
       s, sp = bk.size, self._padded_size(bk.size)
       job = _RootJob()
       job.world, job.sp = world, sp
-      owned = table[s]
+      if self.stacked:  # sharded-state layout: rank r owns the contiguous rows it stores
+        owned = [list(range(r * bk.n_local, (r + 1) * bk.n_local)) for r in range(world)]
+      else:
+        owned = table[s]
       job.mine = owned[rank]
       job.cnt = max(len(o) for o in owned)  # local batch (fillers pad the shorter ranks)
-      job.in_place = world == 1 and sp == s
+      job.in_place = (world == 1 and sp == s) or self.stacked
       exps = np.ones(job.cnt, dtype=np.int32)
       pads = np.zeros(job.cnt, dtype=np.int32)
       exps[:len(job.mine)] = bk.exps_host[job.mine]
-      pads[:len(job.mine)] = s
+      pads[:len(job.mine)] = np.asarray(bk.true_sizes, dtype=np.int32)[job.mine]
       job.exps_host = exps
       job.exps = torch.from_numpy(exps).to(dev)
       job.pads = torch.from_numpy(pads).to(dev)
@@ -1125,7 +1239,8 @@ class _Shampoo:
             job.x[:len(job.mine), :s, :s].copy_(
                 bk.stats if world == 1 else bk.stats.index_select(0, job.mine_idx))
         ops.matrix_inverse_pth_root_batched(
-            job.x, job.exps, None if job.in_place else job.pads, out=job.roots,
+            job.x, job.exps, None if (job.in_place and not self.stacked) else job.pads,
+            out=job.roots,
             metrics_out=job.metrics, workspace=job.ws, ps_host=job.exps_host, **kw)
         corner = job.roots if job.sp == s else job.roots[:, :s, :s]
         if self.quantize_second_moment:
@@ -1460,8 +1575,7 @@ def distributed_shampoo(
   ``export_state`` copy, a deep copy -- is supported: it is copied into the buffers first.
   The returned object also carries ``export_state(state)`` and ``import_state(state)``.
   """
-  del precision, tensordot_precision, statistics_partition_spec
-  del preconditioner_partition_spec, num_devices_for_pjit
+  del precision, tensordot_precision
   if generate_fd_metrics and frequent_directions:  # DS:2026: ignored without frequent_directions
     raise NotImplementedError(
         "generate_fd_metrics (FDDiagnostics, DS:197-335) is not built in the B200 hot path")
@@ -1484,10 +1598,6 @@ def distributed_shampoo(
   if exponent_override and not 1 <= int(exponent_override) <= 16:
     raise ValueError(f"exponent_override={exponent_override} is outside [1, 16], the range of "
                      "the Newton step programs (pc_inverse_pth_root_batched)")
-  for name, val in (("shard_optimizer_states", shard_optimizer_states),):
-    if val:
-      raise NotImplementedError(
-          f"{name} is not built in the B200 hot path yet (see DESIGN.md, out of scope table)")
   if frequent_directions and not reuse_preconditioner:
     # _fd_update_root asserts that the previous sketch is passed in (DS:1150)
     raise ValueError("frequent_directions=True needs reuse_preconditioner=True")
@@ -1506,7 +1616,45 @@ def distributed_shampoo(
                  frequent_directions, reuse_preconditioner, reset_frequency, average_grad,
                  bool(eigh), bool(decay_preconditioning_compute_steps),
                  end_preconditioning_compute_steps, int(lobpcg_topk_precondition),
-                 int(lobpcg_max_iter))
-  tx = ShampooTransformation(opt.init, opt.update)
+                 int(lobpcg_max_iter), bool(shard_optimizer_states), num_devices_for_pjit)
+  if shard_optimizer_states:
+    # DS:3660-3673: `init` hands back the init / partition-spec / shape functions of the sharded
+    # state; `opt.init(params).init_fn(params)` builds ShampooState(count,
+    # ShardedShampooStats(global_stats, local_stats)) and `update` is sharded_update_fn.
+    if not batch_axis_name:
+      opt.batch_axis_name = "pjit"  # the device axis of the sharded state
+
+    def pspec_fn(params, params_partition_spec=None, partition_spec_for_statistics=None):
+      """Partition specs of the state (DS:2277-2330): leading axis of the global arrays sharded
+      (`statistics_partition_spec`), local statistics like their parameters."""
+      del params, params_partition_spec
+      stat = partition_spec_for_statistics or statistics_partition_spec
+      return ShampooState(count=(), stats=ShardedShampooStats(
+          GlobalShardedParameterStats(stat, preconditioner_partition_spec or stat, ()), None))
+
+    def shape_and_dtype_fn(params):
+      """Shapes / dtypes of the global arrays without allocating them (DS:2332-2416)."""
+      leaves, _ = _tree_flatten(params)
+      n, mx = 0, 0
+      for p in leaves:
+        if not opt._skip_preconditioning(p.shape):
+          pre = Preconditioner(p.shape, block_size, merge_small_dims_block_size,
+                               best_effort_shape_interpretation,
+                               PreconditionerType(precondtioner_type), 0)
+          sizes = [sh[0] for sh in pre.shapes_for_preconditioners()]
+          n, mx = n + len(sizes), max([mx] + sizes)
+      ndev = int(num_devices_for_pjit or 1)
+      n += -n % ndev
+      return ShampooState(count=((), torch.int32), stats=ShardedShampooStats(
+          GlobalShardedParameterStats(((n, mx, mx), torch.float32), ((n, mx, mx), torch.float32),
+                                      ((n,), torch.int32)), None))
+
+    def _init_fns(unused_params):
+      return InitFnState(init_fn=opt.init, pspec_fn=pspec_fn,
+                         shape_and_dtype_fn=shape_and_dtype_fn)
+
+    tx = ShampooTransformation(_init_fns, opt.update)
+  else:
+    tx = ShampooTransformation(opt.init, opt.update)
   tx.export_state, tx.import_state = opt.export_state, opt.import_state
   return tx

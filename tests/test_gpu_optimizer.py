@@ -243,8 +243,6 @@ def test_pytree_structure_and_errors():
     DS.distributed_shampoo(0.1, 8, frequent_directions=True)
   with pytest.raises(ValueError):  # the sketch update needs the previous sketch (DS:1150)
     DS.distributed_shampoo(0.1, 8, frequent_directions=True, compression_rank=2)
-  with pytest.raises(NotImplementedError):  # pjit / sharded optimizer states: SURVEY 8(f)
-    DS.distributed_shampoo(0.1, 8, shard_optimizer_states=True)
   with pytest.raises(RuntimeError):
     DS.distributed_shampoo(0.1, 8).init([torch.zeros(4, 4)])  # CPU tensor: no fallback
 

@@ -519,3 +519,68 @@ def test_lobpcg_option_in_optimizer_matches_plain_roots():
   r = DS.matrix_inverse_pth_root(sa.stats[0].statistics[0], 4, lobpcg_topk_precondition=4)[0]
   want = sb.stats[0].preconditioners[0]
   assert float((r - want).norm() / want.norm()) <= 1e-3
+
+
+def _pjit_worker(rank, world, port, out):
+  import torch.distributed as dist
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from precondition_b200 import distributed_shampoo as DS
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    shapes = [(96, 64), (128, 128), (64,), (3, 3, 16, 16)]
+    kw = dict(start_preconditioning_step=1, merge_small_dims_block_size=512)
+    gen = torch.Generator(device=dev).manual_seed(21)
+    params = [torch.randn(s, generator=gen, device=dev) * 0.1 for s in shapes]
+    sharded = DS.distributed_shampoo(0.1, 128, shard_optimizer_states=True,
+                                     num_devices_for_pjit=world, **kw)
+    plain = DS.distributed_shampoo(0.1, 128, **kw)
+    st_a = sharded.init(params).init_fn(params)
+    st_b = plain.init(params)
+    g = st_a.stats.global_stats
+    n_stats = sum(len(st.statistics) for st in st_b.stats)
+    n_pad = n_stats + (-n_stats % world)
+    ok = tuple(g.statistics.shape) == (n_pad // world, 128, 128)
+    ok = ok and tuple(g.preconditioners.shape) == (n_pad, 128, 128)
+    loc = st_a.stats.local_stats
+    ok = ok and loc[0].index_start == 0 and loc[0].sizes == [96, 64] and loc[1].index_start == 2
+    worst = 0.0
+    for t in range(4):
+      grads = [torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes]
+      ua, st_a = sharded.update(grads, st_a, params)
+      ub, st_b = plain.update(grads, st_b, params)
+      torch.cuda.synchronize()
+      for a, b in zip(ua, ub):
+        worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+    # the global preconditioner stack holds every root in its top-left corner, zeros elsewhere
+    row = 0
+    for st in st_b.stats:
+      for pre in st.preconditioners:
+        s = pre.shape[0]
+        got = st_a.stats.global_stats.preconditioners[row]
+        worst = max(worst, float((got[:s, :s] - pre).abs().max() / pre.abs().max()))
+        worst = max(worst, float(got[s:].abs().max()) if s < 128 else 0.0)
+        row += 1
+    out[rank] = (bool(ok), worst)
+  finally:
+    dist.destroy_process_group()
+
+
+def test_shard_optimizer_states_two_ranks_matches_plain():
+  """`shard_optimizer_states=True` (the pjit path, DS:2162-2583): stacked padded-to-max state,
+  statistics rows owned by one rank each, roots computed where the rows live, preconditioners
+  all-gathered -- same updates as the replicated optimizer."""
+  import torch.multiprocessing as mp
+  port = _free_port()
+  ctx = mp.get_context("spawn")
+  with ctx.Manager() as mgr:
+    out = mgr.dict()
+    procs = [ctx.Process(target=_pjit_worker, args=(r, 2, port, out)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    for r in range(2):
+      ok, worst = out[r]
+      assert ok and worst <= 2e-3, dict(out)  # (padded 128 problems run on another engine)

@@ -66,9 +66,16 @@ def test_statistic_inventory_of_baseline_configs():
 
 
 def test_unsupported_options_fail_loudly():
-  for kw in (dict(shard_optimizer_states=True),):
-    with pytest.raises(NotImplementedError):
-      DS.distributed_shampoo(0.1, 32, **kw)
+  with pytest.raises(NotImplementedError):  # FD diagnostics
+    DS.distributed_shampoo(0.1, 32, frequent_directions=True, compression_rank=4,
+                           reuse_preconditioner=True, generate_fd_metrics=True)
+  tx = DS.distributed_shampoo(0.1, 32, shard_optimizer_states=True, num_devices_for_pjit=2)
+  fns = tx.init(None)  # DS:3660-3673: init hands back the sharded init / pspec / shape functions
+  assert isinstance(fns, DS.InitFnState) and callable(fns.init_fn)
+  shapes = [(40, 24), (8,), (3, 5)]
+  n = sum(len(DS.Preconditioner(sh, 32, 4096, True).shapes_for_preconditioners()) for sh in shapes)
+  shp = fns.shape_and_dtype_fn([torch.zeros(sh) for sh in shapes])
+  assert shp.stats.global_stats.statistics[0] == (n + n % 2, 32, 32)  # padded to the device count
 
 
 def test_preconditioning_compute_steps_schedule_matches_reference_formula():
