@@ -97,6 +97,57 @@ __global__ void dequantize_kernel(const Q* __restrict__ q, const float* __restri
   }
 }
 
+// Two-pass form for tall matrices (momenta of shape [d0, rest], large statistics): the column
+// kernel above walks a whole column per thread, i.e. cols / 32 CTAs of 1024+ dependent loads.
+// Pass 1 reduces max |x| per column over row chunks (atomicMax on the float bits, all values >= 0),
+// pass 2 quantises element-wise over the whole grid.  Same arithmetic, bit-identical output.
+constexpr int kQRowChunk = 128;
+__global__ void __launch_bounds__(256)
+quant_colmax_kernel(const float* __restrict__ x, int rows, int cols, int extract_diagonal,
+                    uint32_t* __restrict__ colmax) {
+  __shared__ uint32_t smax[8][32];
+  const int b = blockIdx.z;
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * kQRowChunk, r1 = min(rows, r0 + kQRowChunk);
+  const float* xb = x + (size_t)b * rows * cols;
+  uint32_t m = 0;
+  if (col < cols) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float v = xb[(size_t)r * cols + col];
+      if (extract_diagonal && r == col) v = v - v;  // NaN / inf stay non-finite, QU:72-76
+      const uint32_t ab = absbits(v);
+      m = ab > m ? ab : m;
+    }
+  }
+  smax[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < cols) {
+    for (int k = 1; k < 8; ++k) m = smax[k][threadIdx.x] > m ? smax[k][threadIdx.x] : m;
+    if (m) atomicMax(colmax + (size_t)b * cols + col, m);
+  }
+}
+template <typename Q>
+__global__ void __launch_bounds__(256)
+quant_apply_kernel(const float* __restrict__ x, const uint32_t* __restrict__ colmax, int rows,
+                   int cols, float num_buckets, int extract_diagonal, Q* __restrict__ q,
+                   float* __restrict__ diag, float* __restrict__ bucket) {
+  const int b = blockIdx.y;
+  const size_t total = (size_t)rows * cols;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / cols), c = (int)(e - (size_t)r * cols);
+    float v = x[(size_t)b * total + e];
+    const float bs = __uint_as_float(colmax[(size_t)b * cols + c]) / num_buckets;  // QU:86-87
+    const float bs_nz = bs > 0.f ? bs : 1.f;                                       // QU:90-91
+    if (r == 0) bucket[(size_t)b * cols + c] = bs;
+    if (extract_diagonal && r == c) {
+      diag[(size_t)b * rows + r] = v;  // QU:72-76
+      v = v - v;
+    }
+    q[(size_t)b * total + e] = to_q<Q>(rintf(v / bs_nz));                          // QU:92-95
+  }
+}
+
 __global__ void to_bf16_kernel(const float* __restrict__ x, size_t total,
                                __nv_bfloat16* __restrict__ q) {
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -134,6 +185,24 @@ int pc_quantize_batched(const float* x, int batch, int rows, int cols, int qdtyp
   PC_REQUIRE(!extract_diagonal || (diag != nullptr && rows == cols),
              "extract_diagonal needs a square matrix and a diagonal output");
   const size_t per = (size_t)rows * cols;
+  if (rows >= 256 && batch <= 65535) {
+    // tall matrices: two fully parallel passes (column maxima, then element-wise)
+    uint32_t* colmax = nullptr;
+    PC_CUDA_CHECK(cudaMallocAsync(&colmax, sizeof(uint32_t) * (size_t)batch * cols, st));
+    PC_CUDA_CHECK(cudaMemsetAsync(colmax, 0, sizeof(uint32_t) * (size_t)batch * cols, st));
+    dim3 g1((cols + 31) / 32, (rows + pc::kQRowChunk - 1) / pc::kQRowChunk, batch), b1(32, 8);
+    pc::quant_colmax_kernel<<<g1, b1, 0, st>>>(x, rows, cols, extract_diagonal, colmax);
+    dim3 g2((unsigned)((per + 255) / 256 < 2048 ? (per + 255) / 256 : 2048), batch);
+    if (qdtype == PC_QDTYPE_INT16)
+      pc::quant_apply_kernel<int16_t><<<g2, 256, 0, st>>>(x, colmax, rows, cols, 32767.f,
+                                                         extract_diagonal, (int16_t*)q, diag, bucket);
+    else
+      pc::quant_apply_kernel<int8_t><<<g2, 256, 0, st>>>(x, colmax, rows, cols, 127.f,
+                                                        extract_diagonal, (int8_t*)q, diag, bucket);
+    PC_CUDA_CHECK(cudaFreeAsync(colmax, st));
+    PC_CUDA_CHECK(cudaGetLastError());
+    return PC_OK;
+  }
   for (int b0 = 0; b0 < batch; b0 += pc::kMaxGridY) {  // grid.y carries the batch
     const int nb = batch - b0 < pc::kMaxGridY ? batch - b0 : pc::kMaxGridY;
     dim3 grid((cols + 31) / 32, nb), block(32, 8);

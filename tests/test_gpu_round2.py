@@ -584,3 +584,26 @@ def test_shard_optimizer_states_two_ranks_matches_plain():
     for r in range(2):
       ok, worst = out[r]
       assert ok and worst <= 2e-3, dict(out)  # (padded 128 problems run on another engine)
+
+
+def test_quantize_two_pass_tall_matrices_bit_exact():
+  """Tall matrices (momenta [d0, rest], rows >= 256) take the two-pass quantiser (column maxima,
+  then element-wise): bit-identical to the oracle's QuantizedValue.quantize (QU:49-95)."""
+  from precondition_b200 import ops
+  rng = np.random.default_rng(1)
+  for shape, dt, ext in (((1024, 48), np.int8, False), ((300, 300), np.int8, True),
+                         ((2, 512, 129), np.int16, False)):
+    x = (rng.standard_normal(shape) * 10 ** rng.uniform(-4, 2, size=shape[-1])).astype(np.float32)
+    if not ext:
+      x[..., 3] = 0.0  # a zero column: bucket 0 -> divide by 1
+    tdt = torch.int8 if dt == np.int8 else torch.int16
+    q, d, b = ops.quantize(torch.as_tensor(x).cuda(), tdt, ext)
+    xs = x if x.ndim == 3 else x[None]
+    qs = q if x.ndim == 3 else q[None]
+    bs = b if x.ndim == 3 else b[None]
+    for i in range(xs.shape[0]):
+      wq, wd, wb = N.quantize(xs[i], dt, ext)
+      np.testing.assert_array_equal(qs[i].cpu().numpy(), wq)
+      np.testing.assert_array_equal(bs[i].cpu().numpy(), wb)
+      if ext:
+        np.testing.assert_array_equal(d.cpu().numpy(), wd)
