@@ -236,3 +236,33 @@ def test_low_rank_root_matches_oracle_batched(d, rank):
     og, ow = _lr_operator(got, rank), _lr_operator(want, rank)
     assert np.abs(og - ow).max() <= 2e-3 * np.abs(ow).max(), (b, d, rank)
     assert float(m[b, 0]) < 1e-3
+
+
+def test_fd_1024_against_the_oracle_svd():
+  """d = 1024, rank 64 (subspace path, tcgen05 products): the sketch eigenvalues, tail and
+  vectors against the ORACLE's SVD-based _fd_update_root (numpy gesdd of [1024, 1088]) over three
+  chained updates -- eigenvalues to 1e-4 of the largest, tail to 1e-3, subspace to 1e-3."""
+  from precondition_b200 import ops
+  rng = np.random.default_rng(21)
+  d, rank = 1024, 64
+  u, _ = np.linalg.qr(rng.standard_normal((d, d)))
+  spec = np.concatenate([np.logspace(0, -1.2, rank + 32), np.full(d - rank - 32, 0.03)])
+  prev_o = np.zeros((d, rank + 2), np.float32)
+  prev_g = torch.zeros((1, d, rank + 2), device="cuda")
+  for step in range(3):
+    fac = ((u * spec) @ rng.standard_normal((d, d)) / np.sqrt(d)).astype(np.float32)
+    want, _ = N.fd_update_root(fac, 4, rank, decay=0.999, padding_start=d, prev=prev_o)
+    got, _ = ops.fd_update_root_batched(torch.as_tensor(fac[None]).cuda(), prev_g, [4], rank,
+                                        decay=0.999)
+    torch.cuda.synchronize()
+    g = got[0].cpu().numpy().astype(np.float64)
+    w = want.astype(np.float64)
+    top = w[-rank:, -1].max() + w[1, -1]
+    assert np.abs(g[-rank:, -1] - w[-rank:, -1]).max() <= 1e-4 * top, step      # deflated eigenvalues
+    assert abs(g[1, -1] - w[1, -1]) <= 1e-3 * w[1, -1], step                     # tail
+    assert abs(g[0, -1] - w[0, -1]) <= 1e-3 * abs(w[0, -1]), step                # const = tail^(-1/p)
+    assert g[-1, -2] == w[-1, -2] == 0.0                                         # has_zeros
+    # same subspace: projector difference of the leading 48 vectors (well separated eigenvalues)
+    pg, pw = g[:, :48] @ g[:, :48].T, w[:, :48] @ w[:, :48].T
+    assert np.abs(pg - pw).max() <= 1e-3, step
+    prev_o, prev_g = want, got
