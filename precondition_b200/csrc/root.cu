@@ -233,6 +233,265 @@ power_iteration_kernel(const float* __restrict__ xs, const int32_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------
+// Power iteration over the LOWER TRIANGLE only (solver path: the statistics are symmetric and
+// everything after this reads them that way).  Each a(r,c), c < r, is loaded once per step and
+// used twice -- y_r += a v_c (warp reduction per row) and y_c += a v_r (per-lane column
+// accumulators, reduced across warps through shared memory in a fixed order, so the result
+// is reproducible) -- which halves the bytes of the HBM-bound sweep.  Rows are paired
+// (t, pad-1-t) so every warp task has pad+1 elements; the sweep direction alternates between
+// steps so the tail of one sweep is the head of the next and is still in L2.
+// n <= 128 * NJ, n % 4 == 0.  ybuf: [batch, 2, csize, n].
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pi_prefetch_l2(const float* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+__device__ __forceinline__ uint32_t pi_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void pi_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "PI_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra PI_DONE;\n\t"
+      "bra PI_WAIT;\n\t"
+      "PI_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void pi_bulk_load(uint32_t dst, const float* src, uint32_t bytes,
+                                             uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// row r of the lower triangle staged in shared memory at `a`; NC column chunks of 128.
+// Chunks left of the one holding the diagonal need no masks (a warp-uniform test).
+template <int NC, int NJ>
+__device__ __forceinline__ float pi_sym_fma(const float* a, int r, int lane, const float* nv,
+                                            float (&cacc)[NJ * 4]) {
+  const float vr = nv[r];
+  const int jd = r >> 7;  // chunk of the diagonal element
+  const float4* a4 = reinterpret_cast<const float4*>(a) + lane;
+  const float4* x4 = reinterpret_cast<const float4*>(nv) + lane;
+  float racc = 0.f;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    if (j < jd) {
+      // every element feeds its row and its column
+      const float4 e = a4[32 * j];
+      const float4 x = x4[32 * j];
+      racc = fmaf(e.x, x.x, racc);
+      racc = fmaf(e.y, x.y, racc);
+      racc = fmaf(e.z, x.z, racc);
+      racc = fmaf(e.w, x.w, racc);
+      cacc[j * 4 + 0] = fmaf(e.x, vr, cacc[j * 4 + 0]);
+      cacc[j * 4 + 1] = fmaf(e.y, vr, cacc[j * 4 + 1]);
+      cacc[j * 4 + 2] = fmaf(e.z, vr, cacc[j * 4 + 2]);
+      cacc[j * 4 + 3] = fmaf(e.w, vr, cacc[j * 4 + 3]);
+    } else if (j == jd) {
+      // elements right of the diagonal belong to the mirrored half; the diagonal counts once
+      const int c = lane * 4 + 128 * j;
+      if (c <= r) {
+        const float4 e = a4[32 * j];
+        const float4 x = x4[32 * j];
+        const float a0 = e.x, a1 = c + 1 <= r ? e.y : 0.f, a2 = c + 2 <= r ? e.z : 0.f,
+                    a3 = c + 3 <= r ? e.w : 0.f;
+        racc = fmaf(a0, x.x, racc);
+        racc = fmaf(a1, x.y, racc);
+        racc = fmaf(a2, x.z, racc);
+        racc = fmaf(a3, x.w, racc);
+        cacc[j * 4 + 0] = fmaf(c + 0 < r ? a0 : 0.f, vr, cacc[j * 4 + 0]);
+        cacc[j * 4 + 1] = fmaf(c + 1 < r ? a1 : 0.f, vr, cacc[j * 4 + 1]);
+        cacc[j * 4 + 2] = fmaf(c + 2 < r ? a2 : 0.f, vr, cacc[j * 4 + 2]);
+        cacc[j * 4 + 3] = fmaf(c + 3 < r ? a3 : 0.f, vr, cacc[j * 4 + 3]);
+      }
+    }
+  }
+  return racc;
+}
+
+// two block-wide sums at once, every thread gets both (fixed order).  `scratch` >= 64 floats;
+// the caller keeps a __syncthreads between two uses.
+__device__ __forceinline__ float2 pi_block_sum2(float a, float b, float* scratch, int nwarp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    scratch[warp] = a;
+    scratch[32 + warp] = b;
+  }
+  __syncthreads();
+  a = lane < nwarp ? scratch[lane] : 0.f;
+  b = lane < nwarp ? scratch[32 + lane] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  return make_float2(a, b);
+}
+
+// Every warp streams its own tasks through a private S-stage shared-memory ring filled by
+// 1-D bulk copies (one elected lane issues them, an mbarrier per stage counts the bytes), so
+// the bytes in flight per SM are set by the ring depth, not by registers.  The task stream
+// runs on across the steps (the matrix does not change), so the copies also cover the
+// reductions and the cluster exchange between two sweeps.
+template <int NJ, int T, int S>
+__global__ void __launch_bounds__(T)
+power_iteration_sym_kernel(const float* __restrict__ xs, const float* __restrict__ v0, int n,
+                           int num_iters, float tol, RootCtl* ctl, float* __restrict__ ybuf,
+                           int csize) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int kWarps = T / 32;
+  float* v = smem;               // current iterate
+  float* nv = smem + n;          // normalised iterate
+  float* rowy = smem + 2 * n;    // row parts of this CTA's tasks
+  float* colred = smem + 3 * n;  // [kWarps][n] column parts per warp
+  const int stage_floats = n + 8;
+  float* ring = colred + (size_t)kWarps * n;  // [kWarps][S][n + 8]
+  __shared__ float scratch[64];
+  __shared__ __align__(8) uint64_t bars[kWarps * S];
+  const int b = blockIdx.x / csize;
+  const int crank = csize > 1 ? (int)pi_cluster_rank() : 0;
+  if (ctl[b].done != 0) return;  // uniform across the cluster
+  const int pad = ctl[b].pad;
+  const float* A = xs + (size_t)b * n * n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < S; ++q)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pi_smem_u32(&bars[warp * S + q])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < n; i += T) v[i] = i < pad ? v0[i] : 0.f;
+  __syncthreads();
+  const int ntask = (pad + 1) / 2;
+  // tasks of this warp: t = crank + csize * (warp + kWarps * k), k = 0 .. nk-1; rows (t, pad-1-t)
+  const int first = crank + csize * warp, stride = csize * kWarps;
+  const int nk = first < ntask ? (ntask - 1 - first) / stride + 1 : 0;
+  float* my_ring = ring + (size_t)warp * S * stage_floats;
+  const uint32_t my_bars = pi_smem_u32(&bars[warp * S]);
+  // producer cursor (lane 0): sweep `p_it`, position `p_kk` in it, ring slot `p_slot`
+  int p_it = 0, p_kk = 0, p_slot = 0;
+  auto issue = [&]() {
+    if (nk == 0 || p_it >= num_iters) return;
+    const int k = (p_it & 1) ? nk - 1 - p_kk : p_kk;
+    const int t = first + stride * k, r2 = pad - 1 - t;
+    const uint32_t len2 = (uint32_t)(r2 + 4) & ~3u, len1 = r2 != t ? (uint32_t)(t + 4) & ~3u : 0u;
+    const uint32_t bar = my_bars + 8u * p_slot;
+    const uint32_t dst = pi_smem_u32(my_ring + (size_t)p_slot * stage_floats);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                 "r"((len1 + len2) * 4u)
+                 : "memory");
+    pi_bulk_load(dst, A + (size_t)r2 * n, len2 * 4u, bar);
+    if (len1) pi_bulk_load(dst + len2 * 4u, A + (size_t)t * n, len1 * 4u, bar);
+    if (++p_kk == nk) { p_kk = 0; ++p_it; }
+    p_slot = p_slot + 1 == S ? 0 : p_slot + 1;
+  };
+  if (lane == 0)
+    for (int q = 0; q < S; ++q) issue();
+  int c_slot = 0;
+  uint32_t c_phase = 0;
+  float s = 0.f;
+  int it = 0;
+  bool run = true;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += T) ss += v[i] * v[i];
+  ss = pi_block_sum2(ss, 0.f, scratch, kWarps).x;
+  while (it < num_iters && run) {
+    const float norm = sqrtf(ss);
+    for (int i = threadIdx.x; i < n; i += T) {
+      nv[i] = v[i] / norm;  // DS:634
+      rowy[i] = 0.f;
+    }
+    __syncthreads();
+    float cacc[NJ * 4];
+#pragma unroll
+    for (int q = 0; q < NJ * 4; ++q) cacc[q] = 0.f;
+    for (int kk = 0; kk < nk; ++kk) {
+      const int k = (it & 1) ? nk - 1 - kk : kk;
+      const int t = first + stride * k;
+      const int r2 = pad - 1 - t;
+      const float* st = my_ring + (size_t)c_slot * stage_floats;
+      pi_mbar_wait(my_bars + 8u * c_slot, c_phase);
+      // the short row t <= (pad-1)/2 spans at most half of the column chunks
+      float q2 = pi_sym_fma<NJ, NJ>(st, r2, lane, nv, cacc);
+      float q1 = r2 != t ? pi_sym_fma<(NJ + 1) / 2, NJ>(st + ((r2 + 4) & ~3), t, lane, nv, cacc)
+                         : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+        q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+      }
+      // the shuffles also order every lane's reads of the slot before it is refilled
+      if (lane == 0) {
+        rowy[r2] = q2;
+        if (r2 != t) rowy[t] = q1;
+        issue();
+      }
+      if (++c_slot == S) { c_slot = 0; c_phase ^= 1u; }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = lane * 4 + 128 * j;
+      if (c < n)
+        *reinterpret_cast<float4*>(colred + (size_t)warp * n + c) =
+            make_float4(cacc[j * 4], cacc[j * 4 + 1], cacc[j * 4 + 2], cacc[j * 4 + 3]);
+    }
+    __syncthreads();
+    float* slot = ybuf + (((size_t)b * 2 + (it & 1)) * csize) * n;
+    for (int i = threadIdx.x; i < n; i += T) {
+      float y = rowy[i];
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) y += colred[(size_t)w * n + i];
+      if (csize > 1) slot[(size_t)crank * n + i] = y;
+      else v[i] = y;
+    }
+    if (csize > 1) pi_cluster_sync();
+    else __syncthreads();
+    float dot = 0.f, yy = 0.f;
+    for (int i = threadIdx.x; i < n; i += T) {
+      float yi;
+      if (csize > 1) {
+        yi = 0.f;
+        for (int r = 0; r < csize; ++r) yi += __ldcg(slot + (size_t)r * n + i);
+        v[i] = yi;  // DS:636
+      } else {
+        yi = v[i];
+      }
+      dot += nv[i] * yi;
+      yy += yi * yi;
+    }
+    // v.y for this step and |y|^2 for the next normalisation in one reduction
+    const float2 red = pi_block_sum2(dot, yy, scratch, kWarps);
+    const float s_new = red.x;     // DS:637
+    ss = red.y;
+    run = fabsf(s_new - s) > tol;  // DS:639 (NaN -> stop)
+    s = s_new;
+    ++it;
+  }
+  // copies issued for sweeps that will not run must land before the CTA gives up its memory
+  {
+    const int issued = __shfl_sync(0xffffffffu, p_it * nk + p_kk, 0);
+    for (int g = it * nk; g < issued; ++g) {
+      pi_mbar_wait(my_bars + 8u * c_slot, c_phase);
+      if (++c_slot == S) { c_slot = 0; c_phase ^= 1u; }
+    }
+  }
+  if (threadIdx.x == 0 && crank == 0) ctl[b].max_ev = s;
+}
+
+// ---------------------------------------------------------------------------
 // SIMT engine: one launch executes step `s` of every active matrix's program
 // (+ the H update alongside step 0).
 // ---------------------------------------------------------------------------
@@ -397,13 +656,31 @@ static size_t engine_bytes_simt(int batch, int n) {
   return (size_t)kNumBufs * batch * n * n * sizeof(float);
 }
 
+static int pick_cluster_size(int batch) {
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();  // workspace queries also run without a device
+    sms = 148;
+  }
+  int c = 8;
+  while (c > 1 && (long long)batch * c > sms) c >>= 1;
+  return c;
+}
+
+// power-iteration exchange vectors: [batch, 2, cluster size, n] (the strip kernels of the
+// first initialisation reuse the space)
+static size_t pi_exchange_bytes(int batch, int n) {
+  return sizeof(float) * 2 * (size_t)batch * pick_cluster_size(batch) * (n < 4 ? 4 : n);
+}
+
 static size_t header_bytes(int batch, int n) {
   size_t s = 0;
   s += align_up(sizeof(RootCtl) * batch, 256);
   s += align_up(sizeof(uint32_t) * batch, 256);
   s += 256;
   s += align_up(sizeof(float) * n, 256);
-  s += align_up(sizeof(float) * 2 * (size_t)batch * (n < 4 ? 4 : n), 256);
+  s += align_up(pi_exchange_bytes(batch, n), 256);
   return s;
 }
 
@@ -429,20 +706,17 @@ size_t root_workspace_bytes(int batch, int n, int engine) {
   return total;
 }
 
-static int pick_cluster_size(int batch) {
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int c = 8;
-  while (c > 1 && (long long)batch * c > sms) c >>= 1;
-  return c;
-}
 
 // numpy's start vector per size, in pinned memory that is never freed (so the upload needs no
 // host synchronisation), and the kernel attribute: everything that must not happen inside a
 // stream capture
 static std::mutex v0_mu;
 static std::map<int, float*> v0_cache;
+// v, v/|v|, row parts, column parts per warp, and the per-warp rings of (n + 8)-float slots
+static size_t pi_sym_smem_bytes(int n, int warps, int stages) {
+  return sizeof(float) * ((size_t)n * (3 + warps) + (size_t)warps * stages * (n + 8));
+}
+
 int prepare_power_iteration(int n) {
   std::lock_guard<std::mutex> lock(v0_mu);
   if (v0_cache.find(n) != v0_cache.end()) return PC_OK;
@@ -454,6 +728,19 @@ int prepare_power_iteration(int n) {
   if (smem > 48 * 1024)
     PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool sym_configured = false;
+  if (!sym_configured) {
+    const cudaFuncAttribute kMax = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_sym_kernel<2, 512, 4>, kMax,
+                                       (int)pi_sym_smem_bytes(256, 16, 4)));
+    PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_sym_kernel<4, 512, 4>, kMax,
+                                       (int)pi_sym_smem_bytes(512, 16, 4)));
+    PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_sym_kernel<8, 512, 2>, kMax,
+                                       (int)pi_sym_smem_bytes(1024, 16, 2)));
+    PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_sym_kernel<16, 256, 2>, kMax,
+                                       (int)pi_sym_smem_bytes(2048, 8, 2)));
+    sym_configured = true;
+  }
   return PC_OK;
 }
 
@@ -492,6 +779,49 @@ int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n,
   PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, power_iteration_kernel, xs, pads, (const float*)v0_dev,
                                    n, num_iters, tol, lambdas, iters, ctl, ybuf, csize));
   return PC_OK;
+}
+
+// symmetric-half sweep (solver path); false when the shape is outside its range
+static bool pi_sym_supported(int n) {
+  static const bool off = [] {
+    const char* e = getenv("PC_PI_SYM");
+    return e && e[0] == '0';
+  }();
+  return !off && n >= 256 && n <= 2048 && n % 4 == 0;
+}
+
+template <int NJ, int T, int S>
+static int launch_pi_sym(const float* xs, int batch, int n, RootCtl* ctl, const float* v0_dev,
+                         float* ybuf, int csize, cudaStream_t stream) {
+  const size_t smem = pi_sym_smem_bytes(n, T / 32, S);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(batch * csize));
+  cfg.blockDim = dim3((unsigned)T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, power_iteration_sym_kernel<NJ, T, S>, xs, v0_dev, n,
+                                   100, 1e-6f, ctl, ybuf, csize));  // DS:820-825
+  return PC_OK;
+}
+
+static int run_power_iteration_sym(const float* xs, int batch, int n, RootCtl* ctl, float* v0_dev,
+                                   float* ybuf, cudaStream_t stream) {
+  int rc = prepare_power_iteration(n);
+  if (rc != PC_OK) return rc;
+  const float* v0 = power_iteration_v0_host(n);
+  PC_CUDA_CHECK(cudaMemcpyAsync(v0_dev, v0, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+  const int csize = pick_cluster_size(batch);
+  if (n <= 256) return launch_pi_sym<2, 512, 4>(xs, batch, n, ctl, v0_dev, ybuf, csize, stream);
+  if (n <= 512) return launch_pi_sym<4, 512, 4>(xs, batch, n, ctl, v0_dev, ybuf, csize, stream);
+  if (n <= 1024) return launch_pi_sym<8, 512, 2>(xs, batch, n, ctl, v0_dev, ybuf, csize, stream);
+  return launch_pi_sym<16, 256, 2>(xs, batch, n, ctl, v0_dev, ybuf, csize, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -533,8 +863,10 @@ static int root_enqueue_pre(RootCall& c, cudaStream_t stream) {
   PC_CUDA_CHECK(cudaGetLastError());
   int launches = 1;
   if (c.prm.relative_eps && c.n > 1) {
-    int rc = run_power_iteration(c.xs, nullptr, c.batch, c.n, 100, 1e-6f, nullptr, nullptr,
-                                 c.ws.ctl, c.ws.v0, c.ws.ybuf, stream);  // DS:820-825
+    int rc = pi_sym_supported(c.n)
+                 ? run_power_iteration_sym(c.xs, c.batch, c.n, c.ws.ctl, c.ws.v0, c.ws.ybuf, stream)
+                 : run_power_iteration(c.xs, nullptr, c.batch, c.n, 100, 1e-6f, nullptr, nullptr,
+                                       c.ws.ctl, c.ws.v0, c.ws.ybuf, stream);  // DS:820-825
     if (rc != PC_OK) return rc;
     ++launches;
   }
@@ -819,7 +1151,7 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* ps_host, const i
   c.ws.errbits = reinterpret_cast<uint32_t*>(w); w += align_up(sizeof(uint32_t) * batch, 256);
   c.ws.unfinished = reinterpret_cast<int*>(w); w += 256;
   c.ws.v0 = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * n, 256);
-  c.ws.ybuf = reinterpret_cast<float*>(w); w += align_up(sizeof(float) * 2 * (size_t)batch * (n < 4 ? 4 : n), 256);
+  c.ws.ybuf = reinterpret_cast<float*>(w); w += align_up(pi_exchange_bytes(batch, n), 256);
   c.ws.engine_mem = w;
 
   // everything that may not happen inside a stream capture: one-time allocations, symbol
