@@ -312,6 +312,16 @@ int pc_inverse_pth_root_eigh_batched(const float* xs, const int32_t* ps,
                                      int relative_matrix_epsilon, float* roots, float* metrics,
                                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Pseudo-inverse p-th root by eigendecomposition, as tearfree's blocked Shampoo computes its
+ * preconditioners: replaces _pth_inv_root (TF/shampoo.py:440-448).
+ *   roots[b] = V diag(w_i^(-1/p), or 0 where w_i <= rel_cutoff * max(w)) V^T,  (w, V) = eigh(xs[b])
+ * No ridge is added (rank-deficient statistics are expected); rel_cutoff = 1e-6 in the reference.
+ * xs [batch, d, d] f32 symmetric, ps [batch] i32 DEVICE, workspace from
+ * pc_low_rank_root_workspace_bytes(batch, d).  d <= 2048. */
+int pc_pinv_pth_root_eigh_batched(const float* xs, const int32_t* ps, int batch, int d,
+                                  float rel_cutoff, float* roots, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* Dense form of the operator a packed low-rank preconditioner applies in
  * _precondition_block (DS:1690-1705, _low_rank_unpack DS:540-545):
  *   dense[b] = c I + V diag(lambda^- - c) V^T   (identity if the has_zeros flag is set),
@@ -448,6 +458,58 @@ int pc_sm3_update(const float* grad, const float* param, const float* const* acc
                   float* momentum_f, float* update, int rank, const int32_t* dims,
                   const pc_sm3_options* opt, void* workspace, size_t workspace_bytes,
                   void* stream);
+
+/* ------------------------------------------------------------------------
+ * tearfree (precondition/tearfree): everything after the second-order direction, for every
+ * parameter of the model in three launches.  Per parameter (segment), in the reference's order:
+ *   grafting.graft   (TF/grafting.py:224-300)  u = graft update of g: g itself (SGD) or
+ *                    g * rsqrt(acc' + eps) with acc' = decay * acc + (1 - decay) * g^2
+ *                    (acc + g^2 if decay == 1) (RMSPROP, TF/grafting.py:190-222);
+ *                    x = precond * (|u| / |precond|, 0 if |precond| == 0) once use_precond is set
+ *                    (count >= start_preconditioning_step), u before; parameters without a
+ *                    direction (precond == NULL: masked by skip_preconditioning_*) always take u;
+ *                    graft_type PC_TF_GRAFT_NONE passes precond (or g if NULL) through.
+ *   momentum.apply   (TF/momentum.py:81-139)   x *= 1 - decay if ema; v' = x + decay * v;
+ *                    x = x + decay * v' (nesterov) or v'; skipped if decay == 0; weight decay
+ *                    x += weight_decay * param before or after it.
+ *   learning rate    (TF/optimizer.py:91-99)   update = scale * x, scale = -learning_rate.
+ * Norms are two-level sums in a fixed order.  Arrays are addressed per segment (no flat copy
+ * of the model is needed); pointers 16-byte aligned.  acc / velocity are updated in place and
+ * may be NULL when their stage is off; update may alias grad.
+ *   segments       DEVICE [num_segments]; first_chunk = running sum of nchunks, nchunks =
+ *                  ceil(numel / pc_graft_group_chunk_elems())
+ *   chunk_segment  DEVICE [total_chunks] i32: the segment each chunk belongs to
+ * ------------------------------------------------------------------------ */
+#define PC_TF_GRAFT_NONE 0
+#define PC_TF_GRAFT_SGD 1
+#define PC_TF_GRAFT_RMSPROP 2
+typedef struct {
+  const float* grad;
+  const float* param;   /* NULL allowed when weight_decay == 0 */
+  const float* precond; /* NULL: parameter without a second-order direction */
+  float* acc;
+  float* velocity;
+  float* update;
+  int64_t numel;
+  int32_t first_chunk;
+  int32_t nchunks;
+} pc_tearfree_segment;
+typedef struct {
+  int graft_type;
+  float graft_decay;
+  float graft_epsilon;
+  int use_precond;
+  int ema;
+  int nesterov;
+  float momentum_decay;
+  float weight_decay;
+  int weight_decay_after_momentum;
+  float scale;
+} pc_tearfree_options;
+size_t pc_tearfree_transform_workspace_bytes(int num_segments, int64_t total_chunks);
+int pc_tearfree_transform(const pc_tearfree_segment* segments, const int32_t* chunk_segment,
+                          int num_segments, int64_t total_chunks, const pc_tearfree_options* opt,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * (5) all-gather of the block-sharded roots over NVLink peer memory

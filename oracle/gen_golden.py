@@ -419,6 +419,94 @@ def run_sm3():
   return out
 
 
+TEARFREE_CASES = {
+    # tag: (shapes, steps, kwargs of oracle.tearfree.Tearfree == fields of the reference's options)
+    "rmsprop": ([(6, 4), (5,), (8, 3, 2)], 4,
+                dict(learning_rate=0.1, graft="rmsprop", start_preconditioning_step=1,
+                     merge_dims=4, block_size=4, second_moment_decay=0.9)),
+    "sgd_ema": ([(8, 8), (3, 5)], 5,
+                dict(learning_rate="schedule", graft="sgd", merge_dims=8, block_size=4,
+                     update_preconditioners_freq=2, second_moment_decay=0.8, ema=True,
+                     nesterov=False, momentum_decay=0.5, weight_decay=0.01,
+                     weight_decay_after_momentum=False, skip_preconditioning_any_dim_gt=6)),
+    "none_sum": ([(4, 6), (7,)], 3,
+                 dict(learning_rate=0.05, graft="none", merge_dims=8, block_size=4,
+                      second_moment_decay=1.0, momentum_decay=0.0, weight_decay=0.1)),
+    "tc_blocks": ([(256, 128)], 3,
+                  dict(learning_rate=0.01, graft="rmsprop", graft_decay=1.0, merge_dims=128,
+                       block_size=128, second_moment_decay=0.9, update_statistics_freq=1)),
+}
+
+
+def tearfree_schedule(step):
+  return 0.1 / (1.0 + float(step))
+
+
+def tearfree_inputs(tag):
+  shapes, steps, kw = TEARFREE_CASES[tag]
+  rng = np.random.default_rng(sum(map(ord, tag)))
+  params = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+  grads = [[(rng.standard_normal(s) * 10**rng.uniform(-2, 0)).astype(np.float32) for s in shapes]
+           for _ in range(steps)]
+  return params, grads, kw
+
+
+def run_tearfree():
+  """Trajectories of the unmodified precondition/tearfree/optimizer.py:tearfree (blocked Shampoo
+  direction, grafting, momentum, weight decay, learning rate) over the numpy shim: the updates of
+  every step and the final Shampoo statistics."""
+  import importlib
+  from oracle import jax_shim
+  jax_shim.import_reference()
+  opt = importlib.import_module("precondition.tearfree.optimizer")
+  graft = importlib.import_module("precondition.tearfree.grafting")
+  so = importlib.import_module("precondition.tearfree.second_order")
+  sh = importlib.import_module("precondition.tearfree.shampoo")
+  mom = importlib.import_module("precondition.tearfree.momentum")
+  gtype = {"none": graft.GraftingType.NONE, "sgd": graft.GraftingType.SGD,
+           "rmsprop": graft.GraftingType.RMSPROP}
+  out = {}
+  import contextlib, io
+  for tag in TEARFREE_CASES:
+    params, grads, kw = tearfree_inputs(tag)
+    g = lambda k, d: kw.get(k, d)
+    options = opt.TearfreeOptions(
+        grafting_options=graft.Options(
+            grafting_type=gtype[g("graft", "rmsprop")],
+            second_moment_decay=g("graft_decay", 0.999), epsilon=g("graft_epsilon", 1e-23),
+            start_preconditioning_step=g("start_preconditioning_step", 0),
+            skip_preconditioning_any_dim_gt=g("skip_preconditioning_any_dim_gt", 4096),
+            skip_preconditioning_rank1=g("skip_preconditioning_rank1", True)),
+        second_order_options=so.Options(
+            merge_dims=g("merge_dims", 1024),
+            shampoo_options=sh.Options(
+                block_size=g("block_size", 1024),
+                update_preconditioners_freq=g("update_preconditioners_freq", 1),
+                update_statistics_freq=g("update_statistics_freq", 1),
+                second_moment_decay=g("second_moment_decay", 0.999))),
+        momentum_options=mom.Options(
+            ema=g("ema", False), nesterov=g("nesterov", True),
+            momentum_decay=g("momentum_decay", 0.9), weight_decay=g("weight_decay", 0.0),
+            weight_decay_after_momentum=g("weight_decay_after_momentum", True)))
+    lr = tearfree_schedule if kw["learning_rate"] == "schedule" else kw["learning_rate"]
+    tx = opt.tearfree(lr, options)
+    state = tx.init(params)
+    for t, gr in enumerate(grads):
+      with contextlib.redirect_stdout(io.StringIO()):  # the reference prints its einsum formula
+        u, state = tx.update(gr, state, params)
+      for i, ui in enumerate(u):
+        out[f"{tag}/update{t}_{i}"] = np.asarray(ui)
+    graft_state = state[0]
+    direction = graft_state if kw.get("graft") == "none" else graft_state.direction
+    blocks = direction[1].blocks
+    for i, b in enumerate(blocks):
+      if hasattr(b, "stats"):
+        for a, (st, rt) in enumerate(zip(b.stats, b.roots)):
+          out[f"{tag}/stats{i}_{a}"] = np.asarray(st)
+          out[f"{tag}/roots{i}_{a}"] = np.asarray(rt)
+  return out
+
+
 def main():
   os.makedirs(OUT, exist_ok=True)
   sys.path.insert(0, ROOT)
@@ -431,6 +519,7 @@ def main():
       "optimizer.npz": run_optimizer,
       "shapes.npz": run_shapes,
       "sm3.npz": run_sm3,
+      "tearfree.npz": run_tearfree,
   }
   only = set(sys.argv[1:])  # optional: regenerate just the named files
   for fname, fn in jobs.items():

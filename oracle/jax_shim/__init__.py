@@ -265,6 +265,48 @@ def tree_leaves(tree, is_leaf=None):
   return tree_flatten(tree, is_leaf)[0]
 
 
+class _Key:
+  """Path entry of tree_map_with_path: `.key` for dict / attribute nodes, `.idx` for sequences."""
+
+  def __init__(self, key=None, idx=None):
+    if key is not None:
+      self.key = key
+    if idx is not None:
+      self.idx = idx
+
+  def __repr__(self):
+    return f"[{self.key!r}]" if hasattr(self, "key") else f"[{self.idx}]"
+
+
+def _paths(x, prefix, out, is_leaf=None):
+  if is_leaf is not None and is_leaf(x):
+    out.append(prefix)
+    return
+  node = _node_children(x)
+  if node is None:
+    out.append(prefix)
+    return
+  kind, meta, children = node
+  if kind == "dict":
+    keys = [_Key(key=k) for k in meta]
+  elif kind == "namedtuple":
+    keys = [_Key(key=k) for k in meta._fields]
+  elif kind == "struct":
+    keys = [_Key(key=k) for k in meta[1]]
+  else:
+    keys = [_Key(idx=i) for i in range(len(children))]
+  for k, c in zip(keys, children):
+    _paths(c, prefix + (k,), out, is_leaf)
+
+
+def tree_map_with_path(f, tree, *rest, is_leaf=None):
+  leaves, td = tree_flatten(tree, is_leaf)
+  paths = []
+  _paths(tree, (), paths, is_leaf)
+  others = [td.flatten_up_to(r) for r in rest]
+  return td.unflatten([f(p, *xs) for p, xs in zip(paths, zip(leaves, *others))])
+
+
 def tree_all(tree):
   return all(bool(x) for x in tree_leaves(tree))
 
@@ -385,6 +427,8 @@ def vmap(fn, in_axes=0, out_axes=0):
     return _wrap_out(v)
 
   def run(*args, **kwargs):
+    if isinstance(in_axes, int) and in_axes != 0:  # one mapped axis for every positional array
+      args = tuple(_wrap_out(np.moveaxis(np.asarray(a), in_axes, 0)) for a in args)
     sized = [a for a in list(args) + list(kwargs.values()) if a is not None]
     b = len(sized[0])
     outs = []
@@ -458,6 +502,72 @@ def _make_jnp():
   return jnp
 
 
+def _install_optax(optax, masked_node):
+  """The handful of optax transformations precondition/tearfree composes (optax 0.2 semantics:
+  `trace` = g + decay * t, Nesterov = g + decay * new_trace; `add_decayed_weights` = g + wd * p;
+  `scale_by_schedule` multiplies by schedule(count) and counts up)."""
+  GT = optax.GradientTransformation
+  EmptyState = collections.namedtuple("EmptyState", [])
+  TraceState = collections.namedtuple("TraceState", ["trace"])
+  MaskedState = collections.namedtuple("MaskedState", ["inner_state"])
+  ScaleByScheduleState = collections.namedtuple("ScaleByScheduleState", ["count"])
+  optax.EmptyState, optax.TraceState, optax.MaskedState = EmptyState, TraceState, MaskedState
+  optax.ScaleByScheduleState = ScaleByScheduleState
+  for alias in ("Updates", "Params", "OptState", "TransformInitFn", "TransformUpdateFn",
+                "Schedule"):
+    setattr(optax, alias, object)
+
+  def identity():
+    return GT(lambda params: EmptyState(), lambda u, s, p=None: (u, s))
+
+  def scale(step_size):
+    return GT(lambda params: EmptyState(),
+              lambda u, s, p=None: (tree_map(lambda g: step_size * g, u), s))
+
+  def scale_by_schedule(step_size_fn):
+    def update(u, s, p=None):
+      step = step_size_fn(s.count)
+      return tree_map(lambda g: _wrap_out(np.asarray(step, np.float32) * g), u), (
+          ScaleByScheduleState(count=s.count + 1))
+    return GT(lambda params: ScaleByScheduleState(count=_wrap_out(np.zeros([], np.int32))),
+              update)
+
+  def add_decayed_weights(weight_decay=0.0, mask=None):
+    assert mask is None
+    return GT(lambda params: EmptyState(),
+              lambda u, s, p=None: (tree_map(lambda g, w: g + weight_decay * w, u, p), s))
+
+  def trace(decay, nesterov=False, accumulator_dtype=None):
+    def init(params):
+      return TraceState(trace=tree_map(lambda x: _wrap_out(np.zeros_like(np.asarray(x))), params))
+
+    def update(u, s, p=None):
+      f = lambda g, t: g + decay * t
+      new_trace = tree_map(f, u, s.trace)
+      out = tree_map(f, u, new_trace) if nesterov else new_trace
+      return out, TraceState(trace=new_trace)
+    return GT(init, update)
+
+  def chain(*txs):
+    def init(params):
+      return tuple(t.init(params) for t in txs)
+
+    def update(u, state, p=None):
+      new = []
+      for t, st in zip(txs, state):
+        u, st = t.update(u, st, p)
+        new.append(st)
+      return u, tuple(new)
+    return GT(init, update)
+
+  def adafactor(*a, **k):
+    raise NotImplementedError("optax.adafactor is not part of the shim")
+
+  optax.identity, optax.scale, optax.scale_by_schedule = identity, scale, scale_by_schedule
+  optax.add_decayed_weights, optax.trace, optax.chain = add_decayed_weights, trace, chain
+  optax.adafactor = adafactor
+
+
 def install(x64: bool = False):
   """Registers the fake modules.  Call before importing the reference."""
   global _X64
@@ -473,8 +583,11 @@ def install(x64: bool = False):
   lax.while_loop, lax.cond = while_loop, cond
   lax.psum, lax.axis_index, lax.all_gather = psum, axis_index, all_gather
   lax.with_sharding_constraint = with_sharding_constraint
+  lax.rsqrt = lambda x: _wrap_out(1.0 / np.sqrt(np.asarray(x)))
   jax.numpy, jax.lax = jnp, lax
   jax.vmap, jax.pmap = vmap, pmap
+  import contextlib
+  jax.named_scope = lambda name: contextlib.nullcontext()
   jax.jit = lambda f, **k: f
   jax.Array = np.ndarray
   tree = types.ModuleType("jax.tree")
@@ -484,6 +597,7 @@ def install(x64: bool = False):
   tu = types.ModuleType("jax.tree_util")
   tu.tree_all, tu.tree_map, tu.tree_flatten = tree_all, tree_map, tree_flatten
   tu.tree_unflatten, tu.tree_leaves = tree_unflatten, tree_leaves
+  tu.tree_map_with_path = tree_map_with_path
   jax.tree_util = tu
   sharding = types.ModuleType("jax.sharding")
   sharding.PartitionSpec = lambda *a: tuple(a)
@@ -510,6 +624,7 @@ def install(x64: bool = False):
   chex = types.ModuleType("chex")
   chex.Array = np.ndarray
   chex.Numeric = float
+  chex.ArrayTree = object
 
   optax = types.ModuleType("optax")
   optax.GradientTransformation = collections.namedtuple(
@@ -524,6 +639,7 @@ def install(x64: bool = False):
       return tuple.__new__(cls)
 
   optax.MaskedNode = MaskedNode
+  _install_optax(optax, MaskedNode)
 
   mods = {
       "jax": jax, "jax.numpy": jnp, "jax.lax": lax, "jax.tree": tree,

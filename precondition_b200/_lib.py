@@ -16,6 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 PC_ENGINE_AUTO, PC_ENGINE_SIMT_FP32, PC_ENGINE_TC_BF16X6, PC_ENGINE_TC_BF16X3 = 0, 1, 2, 3
 PC_ENGINE_TC_FP16X3 = 4
 PC_ENGINE_TC_SMALL = 5
+PC_TF_GRAFT_NONE, PC_TF_GRAFT_SGD, PC_TF_GRAFT_RMSPROP = 0, 1, 2
 PC_QDTYPE_F32, PC_QDTYPE_INT16, PC_QDTYPE_INT8, PC_QDTYPE_BF16 = 0, 1, 2, 3
 PC_NUM_METRICS = 5
 PC_MAX_PEERS = 16
@@ -42,6 +43,8 @@ EXPORTED_SYMBOLS = (
     "pc_sm3_workspace_bytes", "pc_sm3_update",
     "pc_lobpcg_deflate_prep", "pc_lobpcg_redeflate_prep", "pc_root_diagnostics",
     "pc_lobpcg_diagnostics",
+    "pc_pinv_pth_root_eigh_batched", "pc_tearfree_transform_workspace_bytes",
+    "pc_tearfree_transform",
 )
 
 
@@ -97,6 +100,21 @@ class GraftSegment(ctypes.Structure):
   _fields_ = [("offset", ctypes.c_int64), ("numel", ctypes.c_int64),
               ("first_chunk", ctypes.c_int32), ("nchunks", ctypes.c_int32),
               ("has_precond", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class TearfreeSegment(ctypes.Structure):
+  _fields_ = [("grad", ctypes.c_void_p), ("param", ctypes.c_void_p), ("precond", ctypes.c_void_p),
+              ("acc", ctypes.c_void_p), ("velocity", ctypes.c_void_p), ("update", ctypes.c_void_p),
+              ("numel", ctypes.c_int64), ("first_chunk", ctypes.c_int32),
+              ("nchunks", ctypes.c_int32)]
+
+
+class TearfreeOptions(ctypes.Structure):
+  _fields_ = [("graft_type", ctypes.c_int), ("graft_decay", ctypes.c_float),
+              ("graft_epsilon", ctypes.c_float), ("use_precond", ctypes.c_int),
+              ("ema", ctypes.c_int), ("nesterov", ctypes.c_int),
+              ("momentum_decay", ctypes.c_float), ("weight_decay", ctypes.c_float),
+              ("weight_decay_after_momentum", ctypes.c_int), ("scale", ctypes.c_float)]
 
 
 class Sm3Options(ctypes.Structure):
@@ -239,6 +257,13 @@ def load() -> ctypes.CDLL:
   lib.pc_graft_momentum_grouped.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp,
                                             ctypes.POINTER(GraftOptions), vp, sz, vp]
   lib.pc_graft_momentum_grouped.restype = i32
+  lib.pc_pinv_pth_root_eigh_batched.argtypes = [vp, vp, i32, i32, f32, vp, vp, sz, vp]
+  lib.pc_pinv_pth_root_eigh_batched.restype = i32
+  lib.pc_tearfree_transform_workspace_bytes.argtypes = [i32, i64]
+  lib.pc_tearfree_transform_workspace_bytes.restype = sz
+  lib.pc_tearfree_transform.argtypes = [vp, vp, i32, i64, ctypes.POINTER(TearfreeOptions), vp, sz,
+                                        vp]
+  lib.pc_tearfree_transform.restype = i32
   _lib = lib
   return lib
 

@@ -1281,11 +1281,20 @@ __global__ void lr_scale_rows_kernel(const float* __restrict__ vs, const float* 
                                      const float* __restrict__ ridge_all,
                                      const int32_t* __restrict__ ps,
                                      const int32_t* __restrict__ pads, int d,
-                                     float* __restrict__ rt) {
+                                     float pinv_cutoff, float* __restrict__ rt) {
   const int b = blockIdx.y, idx = blockIdx.x;  // row idx = eigenvector of descending rank idx
   const int pad = pads ? min(max(pads[b], 0), d) : d;
   const float alpha = -1.0f / (float)ps[b];
-  const float inv_e = idx < pad ? powf(fmaxf(sorted[(size_t)b * d + idx], ridge_all[b]), alpha) : 0.f;
+  float inv_e;
+  if (pinv_cutoff > 0.f) {
+    // pseudo-inverse root (TF/shampoo.py:440-448): the shift that made the factorisation
+    // possible comes off again; eigenvalues <= cutoff * max are dropped, not clamped
+    const float ridge = ridge_all[b];
+    const float w = sorted[(size_t)b * d + idx] - ridge, wmax = sorted[(size_t)b * d] - ridge;
+    inv_e = (w <= pinv_cutoff * wmax) ? 0.f : powf(w, alpha);
+  } else {
+    inv_e = idx < pad ? powf(fmaxf(sorted[(size_t)b * d + idx], ridge_all[b]), alpha) : 0.f;
+  }
   const float sc = sqrtf(inv_e);  // root = u * sqrt(inv_e), DS:1018
   for (int i = threadIdx.x; i < d; i += blockDim.x)
     rt[((size_t)b * d + idx) * d + i] = vs[((size_t)b * d + idx) * d + i] * sc;
@@ -1307,7 +1316,7 @@ __global__ void lr_root_metrics_kernel(const uint32_t* __restrict__ errbits,
 int run_low_rank_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch, int d,
                       int rank_signed, bool full_root, float ridge_epsilon, float error_tolerance,
                       int relative, float* out, float* metrics, void* workspace,
-                      size_t workspace_bytes, cudaStream_t stream) {
+                      size_t workspace_bytes, cudaStream_t stream, float pinv_cutoff = 0.f) {
   if (workspace_bytes < low_rank_root_bytes(batch, d)) {
     set_error("eigh root workspace too small: %zu < %zu", workspace_bytes,
               low_rank_root_bytes(batch, d));
@@ -1348,19 +1357,22 @@ int run_low_rank_root(const float* xs, const int32_t* ps, const int32_t* pads, i
   if (rc != PC_OK) return rc;
   fd_sort_kernel<<<batch, 512, 0, stream>>>(theta, d, order, sorted);
   lr_gather_normalize_kernel<<<dim3(d, batch), 256, 0, stream>>>(vt, order, d, vs);
-  // recovered = Vs reg Vs^T
-  FdGemm q{};
-  q.alpha = 1.f; q.a = vs; q.b = reg_copy; q.c = t1;
-  q.a_bs = q.b_bs = q.c_bs = (int64_t)nn;
-  q.a_si = d; q.a_sk = 1; q.b_sj = d; q.b_sk = 1; q.c_si = d;
-  q.m = q.n = q.k = d;
-  fd_gemm(q, batch, stream);
-  q.a = t1; q.b = vs; q.c = rec;
-  fd_gemm(q, batch, stream);
-  lr_error_kernel<<<dim3(g, batch), 256, 0, stream>>>(rec, sorted, pads, d, errbits);
+  if (pinv_cutoff <= 0.f) {
+    // recovered = Vs reg Vs^T
+    FdGemm q{};
+    q.alpha = 1.f; q.a = vs; q.b = reg_copy; q.c = t1;
+    q.a_bs = q.b_bs = q.c_bs = (int64_t)nn;
+    q.a_si = d; q.a_sk = 1; q.b_sj = d; q.b_sk = 1; q.c_si = d;
+    q.m = q.n = q.k = d;
+    fd_gemm(q, batch, stream);
+    q.a = t1; q.b = vs; q.c = rec;
+    fd_gemm(q, batch, stream);
+    lr_error_kernel<<<dim3(g, batch), 256, 0, stream>>>(rec, sorted, pads, d, errbits);
+  }
   if (full_root) {
     // val = root root^T with root = U sqrt(inv_e): out(i,j) = sum_k Rt(k,i) Rt(k,j)
-    lr_scale_rows_kernel<<<dim3(d, batch), 256, 0, stream>>>(vs, sorted, ridge, ps, pads, d, t1);
+    lr_scale_rows_kernel<<<dim3(d, batch), 256, 0, stream>>>(vs, sorted, ridge, ps, pads, d,
+                                                            pinv_cutoff, t1);
     FdGemm r{};
     r.alpha = 1.f; r.a = t1; r.b = t1; r.c = out;
     r.a_bs = r.b_bs = r.c_bs = (int64_t)nn;
@@ -1431,6 +1443,23 @@ int pc_inverse_pth_root_eigh_batched(const float* xs, const int32_t* ps,
   return pc::run_low_rank_root(xs, ps, padding_starts, batch, d, 0, true, ridge_epsilon,
                                error_tolerance, relative_matrix_epsilon, roots, metrics, workspace,
                                workspace_bytes, (cudaStream_t)stream);
+}
+
+int pc_pinv_pth_root_eigh_batched(const float* xs, const int32_t* ps, int batch, int d,
+                                  float rel_cutoff, float* roots, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  PC_REQUIRE(batch >= 0 && d > 0 && rel_cutoff > 0.f, "bad pseudo-inverse root arguments");
+  if (batch == 0) return PC_OK;
+  PC_REQUIRE(xs && ps && roots && workspace, "null pointer argument");
+  PC_REQUIRE(d <= pc::kEighMaxN, "eigh root supports d <= %d (one Jacobi solve), got %d",
+             pc::kEighMaxN, d);
+  // the eigensolver factors the matrix first, which a rank-deficient statistic (the usual
+  // state of the first steps) does not survive in fp32: shift by a few d * eps * lambda_max,
+  // take the shift off the eigenvalues again before the cutoff
+  const float shift = fmaxf(1e-6f, 4.0f * (float)d * 5.96e-8f);
+  return pc::run_low_rank_root(xs, ps, nullptr, batch, d, 0, true, shift, 1e-30f, 1, roots,
+                               nullptr, workspace, workspace_bytes, (cudaStream_t)stream,
+                               rel_cutoff);
 }
 
 void pc_fd_options_default(pc_fd_options* opt) {

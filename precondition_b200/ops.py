@@ -244,6 +244,90 @@ def matrix_inverse_pth_root_eigh_batched(xs: torch.Tensor, ps, padding_starts=No
   return roots, metrics
 
 
+def pinv_pth_root_eigh_batched(xs: torch.Tensor, ps, rel_cutoff: float = 1e-6,
+                               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """Batched pseudo-inverse p-th root by eigendecomposition, tearfree's ``_pth_inv_root``
+  (TF/shampoo.py:440-448): eigenvalues <= rel_cutoff * max are dropped.  xs [b, d, d]; d <= 2048."""
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(xs, out)
+  b, d = xs.shape[0], xs.shape[1]
+  dev = xs.device
+  ps_t = ps if isinstance(ps, torch.Tensor) else torch.as_tensor(ps, dtype=torch.int32).to(dev)
+  roots = out if out is not None else torch.empty_like(xs)
+  if b == 0:
+    return roots
+  ws = _workspace(lib.pc_low_rank_root_workspace_bytes(b, d), dev)
+  with torch.cuda.device(dev):
+    _lib.check(lib.pc_pinv_pth_root_eigh_batched(
+        _ptr(xs), _ptr(ps_t), b, d, rel_cutoff, _ptr(roots), _ptr(ws), ws.numel(),
+        ctypes.c_void_p(_stream())))
+  gpu_launches += 1
+  return roots
+
+
+class TearfreeTail:
+  """Launch list of ``pc_tearfree_transform`` for a fixed set of parameters: grafting, momentum,
+  weight decay and the learning rate for all of them in three launches.  The state tensors
+  (``acc``, ``velocity``) are fixed at construction; gradients, directions and outputs are
+  bound per call (their addresses change from step to step)."""
+
+  def __init__(self, numels: Sequence[int], device):
+    lib = _lib.load()
+    self.device = device
+    self.n = len(numels)
+    chunk = int(lib.pc_graft_group_chunk_elems())
+    self.segs = (_lib.TearfreeSegment * max(self.n, 1))()
+    chunk_seg, first = [], 0
+    for i, ne in enumerate(numels):
+      nch = max(1, -(-int(ne) // chunk))
+      self.segs[i].numel, self.segs[i].first_chunk, self.segs[i].nchunks = int(ne), first, nch
+      chunk_seg += [i] * nch
+      first += nch
+    self.total_chunks = first
+    self.chunk_seg = torch.tensor(chunk_seg, dtype=torch.int32).to(device)
+    nbytes = lib.pc_tearfree_transform_workspace_bytes(self.n, self.total_chunks)
+    self.ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+    self.segs_dev = torch.empty(ctypes.sizeof(self.segs), dtype=torch.uint8, device=device)
+    # two pinned staging copies: the upload of step k may still be queued when step k+1 is built
+    self.segs_host = [torch.empty(ctypes.sizeof(self.segs), dtype=torch.uint8).pin_memory()
+                      for _ in range(2)]
+    self.uploaded = [None, None]
+    self.turn = 0
+
+  def run(self, grads, params, preconds, accs, velocities, updates, opt: "_lib.TearfreeOptions"):
+    """Each argument: list of tensors (fp32, contiguous) or None entries where the stage is off."""
+    global gpu_launches
+    if not self.n:
+      return
+    lib = _lib.load()
+    for i in range(self.n):
+      sg = self.segs[i]
+      for name, lst in (("grad", grads), ("param", params), ("precond", preconds),
+                        ("acc", accs), ("velocity", velocities), ("update", updates)):
+        t = lst[i] if lst is not None else None
+        if t is not None:
+          _require_cuda(t)
+          assert t.numel() == sg.numel, (name, i, t.shape, sg.numel)
+          if t.data_ptr() % 16:
+            raise ValueError(f"tearfree: {name}[{i}] is not 16-byte aligned")
+        setattr(sg, name, None if t is None else t.data_ptr())
+    t = self.turn
+    self.turn ^= 1
+    if self.uploaded[t] is not None:
+      self.uploaded[t].synchronize()
+    ctypes.memmove(self.segs_host[t].data_ptr(), ctypes.addressof(self.segs),
+                   ctypes.sizeof(self.segs))
+    self.segs_dev.copy_(self.segs_host[t], non_blocking=True)
+    self.uploaded[t] = torch.cuda.Event()
+    self.uploaded[t].record()
+    with torch.cuda.device(self.device):
+      _lib.check(lib.pc_tearfree_transform(_ptr(self.segs_dev), _ptr(self.chunk_seg), self.n,
+                                           self.total_chunks, ctypes.byref(opt), _ptr(self.ws),
+                                           self.ws.numel(), ctypes.c_void_p(_stream())))
+    gpu_launches += 3 if opt.graft_type != _lib.PC_TF_GRAFT_NONE else 1
+
+
 def low_rank_to_dense(packed: torch.Tensor, rank: int,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
   """Dense operator of packed low-rank preconditioners [b, d, rank+2] -> [b, d, d]

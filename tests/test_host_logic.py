@@ -152,3 +152,58 @@ def test_option_validation():
   DS.distributed_shampoo(0.1, 32, generate_fd_metrics=True)  # ignored without FD (DS:2026)
   DS.distributed_shampoo(lambda s: 0.1, 32, decay_preconditioning_compute_steps=True,
                          end_preconditioning_compute_steps=100)
+
+
+def test_tearfree_blocking_and_reshaper_layout():
+  """Host-side layout logic of the tearfree front-end on CPU tensors: block n of the blocked
+  layout is the n-th block in the reference's order (left blocked axis major, TF/shampoo.py:302-
+  362), blockify / deblockify round-trip, and merge / unmerge follow TF/reshaper.py:52-133."""
+  import torch
+  from oracle import tearfree as T
+  from precondition_b200.tearfree import reshaper, shampoo
+  opts = shampoo.Options(block_size=4)
+  rng = np.random.default_rng(0)
+  for shape in [(3, 8, 12, 2), (8, 3), (3, 2), (4,), (12, 8)]:
+    x = rng.standard_normal(shape).astype(np.float32)
+    meta = shampoo._blocks_metadata(opts, list(shape), "p")
+    xb = shampoo._blockify(torch.as_tensor(x), meta)
+    assert list(xb.shape) == [meta.num_blocks] + meta.block_sizes
+    for n, sl in enumerate(T.blocks_of(x, 4)):
+      np.testing.assert_array_equal(xb[n].numpy(), x[sl])
+    np.testing.assert_array_equal(shampoo._deblockify(xb.contiguous(), meta).numpy(), x)
+  ro = reshaper.Options(merge_dims=6, block_size=4)
+  merge_tx, unmerge_tx = reshaper.merge(ro), reshaper.unmerge(ro)
+  params = {"a": torch.as_tensor(rng.standard_normal((3, 2, 5)).astype(np.float32)),
+            "b": [torch.as_tensor(rng.standard_normal((7,)).astype(np.float32))]}
+  merged, _ = merge_tx.update(params, merge_tx.init(params), params)
+  assert list(merged["a"].shape) == [8, 8] and list(merged["b"][0].shape) == [8]
+  np.testing.assert_array_equal(merged["a"].numpy(),
+                                T.merge(params["a"].numpy(), 6, 4))
+  back, _ = unmerge_tx.update(merged, None, params)
+  for got, want in ((back["a"], params["a"]), (back["b"][0], params["b"][0])):
+    np.testing.assert_array_equal(got.numpy(), want.numpy())
+
+
+def test_tearfree_chain_and_partition_specs():
+  """sharded_chain threads updates and states like TF/praxis_shim.py:45-90 and the optimizer's
+  init_partition_spec mirrors the nesting of its state."""
+  import torch
+  from precondition_b200.tearfree import optimizer, praxis_shim
+  double = praxis_shim.ShardedGradientTransformation(
+      lambda p: praxis_shim.EmptyState(), lambda u, s, p=None: ([2 * x for x in u], s),
+      lambda p: "spec")
+  chain = praxis_shim.sharded_chain(double, double)
+  st = chain.init([torch.ones(2)])
+  out, st2 = chain.update([torch.ones(2)], st)
+  assert out[0].tolist() == [4.0, 4.0] and len(st2) == 2
+  assert chain.init_partition_spec(None).inner_state == ("spec", "spec")
+  with pytest.raises(ValueError, match="number of updates and states"):
+    chain.update([torch.ones(2)], st[:1])
+  tx = optimizer.tearfree(0.1, optimizer.TearfreeOptions())
+  spec = tx.init_partition_spec({"w": praxis_shim.WeightHParams([2048, 512], None, torch.float32,
+                                                              None, [-1, -1])})
+  graft_spec, mom_spec, _ = spec.inner_state
+  blocks = graft_spec["direction"].inner_state[1]["blocks"]["w"]
+  assert [tuple(s.shape) for s in blocks["stats"]] == [(2, 1024, 1024), (2, 512, 512)]
+  assert tuple(graft_spec["norm"].acc["w"].shape) == (2048, 512)
+  assert tuple(mom_spec.inner_state[0].trace["w"].shape) == (2048, 512)

@@ -211,3 +211,32 @@ def test_sm3_oracle_matches_reference_golden():
       for ax, acc in enumerate(state.stats[i].diagonal_statistics):
         assert np.array_equal(acc, g[f"{tag}/acc{i}_{ax}"])
       assert np.array_equal(state.stats[i].diagonal_momentum.quantized, g[f"{tag}/momq{i}"])
+
+
+def test_tearfree_oracle_matches_reference_golden():
+  """oracle/tearfree.py == the unmodified precondition/tearfree (recorded over the numpy shim):
+  updates of every step and the final blocked statistics / roots, for the four option sets of
+  oracle.gen_golden.TEARFREE_CASES.  The eigendecompositions are the same LAPACK calls, so the
+  trajectories agree to rounding of the products around them."""
+  from oracle import gen_golden as G
+  from oracle import tearfree as T
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tearfree.npz"))
+  for tag in G.TEARFREE_CASES:
+    params, grads, kw = G.tearfree_inputs(tag)
+    kw = dict(kw)
+    if kw["learning_rate"] == "schedule":
+      kw["learning_rate"] = G.tearfree_schedule
+    opt = T.Tearfree(params, **kw)
+    for t, gr in enumerate(grads):
+      outs = opt.update(gr, params)
+      for i, u in enumerate(outs):
+        want = g[f"{tag}/update{t}_{i}"]
+        scale = np.abs(want).max() + 1e-30
+        assert np.abs(u - want).max() <= 2e-4 * scale, (tag, t, i, np.abs(u - want).max() / scale)
+    for i, leaf in enumerate(opt.leaves):
+      if leaf is None:
+        continue
+      for a in range(len(leaf.shape)):
+        want = g[f"{tag}/stats{i}_{a}"]  # [N, B, B]
+        got = np.stack([leaf.stats[n][a] for n in range(len(leaf.slices))])
+        assert np.abs(got - want).max() <= 1e-5 * (np.abs(want).max() + 1e-30), (tag, i, a)
