@@ -300,6 +300,40 @@ def run_reference(a):
   print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+  """Pins this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host
+  buffers of the end-to-end loop (first touch) live in the memory next to the GPU's PCIe root.
+  Returns a short description for the JSON line; failures leave the affinity alone."""
+  if os.environ.get("PC_BENCH_NUMA", "1") == "0":
+    return "off"
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+    bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+    bus = bus.decode() if isinstance(bus, bytes) else bus
+    node = None
+    for cand in (bus.lower(), bus.lower()[4:] if len(bus) > 12 else bus.lower()):
+      path = f"/sys/bus/pci/devices/{cand}/numa_node"
+      if os.path.exists(path):
+        node = int(open(path).read().strip())
+        break
+    if node is None or node < 0:
+      return f"unknown node for {bus}"
+    cpus = set()
+    for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+      lo, _, hi = part.partition("-")
+      cpus.update(range(int(lo), int(hi or lo) + 1))
+    cpus &= os.sched_getaffinity(0)
+    if not cpus:
+      return f"node {node}: no allowed cpus"
+    os.sched_setaffinity(0, cpus)
+    return f"node {node} ({len(cpus)} cpus)"
+  except Exception as e:  # pylint: disable=broad-except
+    return f"unavailable ({type(e).__name__})"
+
+
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
@@ -314,6 +348,7 @@ def run_ours(a):
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   if not torch.cuda.is_available():
     raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+  numa = bind_to_gpu_numa_node(local_rank)
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   if world > 1:
@@ -575,7 +610,8 @@ def run_ours(a):
         "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, world),
-        "run_info": {"engine": resolved, "newton_iters_mean": float(m_host[:, 1].mean()),
+        "run_info": {"engine": resolved, "host_numa_binding": numa,
+                     "newton_iters_mean": float(m_host[:, 1].mean()),
                      "max_error": float(np.nanmax(m_host[:, 0])),
                      "root_mode": "cuda_graph_device_loop" if lib.pc_root_mode() else "host_polled",
                      "gather_overlap": gather_note},

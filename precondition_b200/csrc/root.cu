@@ -22,7 +22,7 @@ namespace pc {
 size_t small_root_workspace_bytes(int batch, int n);
 bool small_root_supported_exponents(const int32_t* ps_host, int batch);
 int run_small_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch, int n,
-                   const pc_root_options* opt, const float* v0_host_pinned, float* roots,
+                   const pc_root_options* opt, const float* v0_device, float* roots,
                    float* metrics, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
@@ -707,11 +707,13 @@ size_t root_workspace_bytes(int batch, int n, int engine) {
 }
 
 
-// numpy's start vector per size, in pinned memory that is never freed (so the upload needs no
-// host synchronisation), and the kernel attribute: everything that must not happen inside a
-// stream capture
+// numpy's start vector per (device, size), uploaded ONCE into device memory that is never
+// freed, and the kernel attributes: everything that must not happen inside a stream capture.
+// (A per-call upload, however small, queues on the host-to-device copy engine behind whatever
+// the application is uploading on other streams -- a 310 MB input copy of the next step held
+// every solve back by its full 5.6 ms.)
 static std::mutex v0_mu;
-static std::map<int, float*> v0_cache;
+static std::map<std::pair<int, int>, float*> v0_cache;
 // v, v/|v|, row parts, column parts per warp, and the per-warp rings of (n + 8)-float slots
 static size_t pi_sym_smem_bytes(int n, int warps, int stages) {
   return sizeof(float) * ((size_t)n * (3 + warps) + (size_t)warps * stages * (n + 8));
@@ -719,11 +721,15 @@ static size_t pi_sym_smem_bytes(int n, int warps, int stages) {
 
 int prepare_power_iteration(int n) {
   std::lock_guard<std::mutex> lock(v0_mu);
-  if (v0_cache.find(n) != v0_cache.end()) return PC_OK;
+  int dev = 0;
+  PC_CUDA_CHECK(cudaGetDevice(&dev));
+  if (v0_cache.find({dev, n}) != v0_cache.end()) return PC_OK;
+  std::vector<float> host((size_t)n);
+  mt19937_uniform(1729u, n, host.data());
   float* v0 = nullptr;
-  PC_CUDA_CHECK(cudaMallocHost(&v0, sizeof(float) * n));
-  mt19937_uniform(1729u, n, v0);
-  v0_cache[n] = v0;
+  PC_CUDA_CHECK(cudaMalloc(&v0, sizeof(float) * n));
+  PC_CUDA_CHECK(cudaMemcpy(v0, host.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+  v0_cache[{dev, n}] = v0;
   const size_t smem = sizeof(float) * 3 * (size_t)n;
   if (smem > 48 * 1024)
     PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_kernel,
@@ -744,9 +750,12 @@ int prepare_power_iteration(int n) {
   return PC_OK;
 }
 
-static const float* power_iteration_v0_host(int n) {
+// device pointer of the start vector on the current device (after prepare_power_iteration)
+static const float* power_iteration_v0_device(int n) {
   std::lock_guard<std::mutex> lock(v0_mu);
-  auto it = v0_cache.find(n);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto it = v0_cache.find({dev, n});
   return it == v0_cache.end() ? nullptr : it->second;
 }
 
@@ -755,12 +764,8 @@ int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n,
                         RootCtl* ctl, float* v0_dev, float* ybuf, cudaStream_t stream) {
   int rc = prepare_power_iteration(n);
   if (rc != PC_OK) return rc;
-  float* v0 = nullptr;
-  {
-    std::lock_guard<std::mutex> lock(v0_mu);
-    v0 = v0_cache[n];
-  }
-  PC_CUDA_CHECK(cudaMemcpyAsync(v0_dev, v0, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+  (void)v0_dev;  // the start vector is resident on the device
+  const float* v0 = power_iteration_v0_device(n);
   const size_t smem = sizeof(float) * 3 * (size_t)n;  // v, v / |v|, and A v when csize == 1
   int csize = n >= 256 ? pick_cluster_size(batch) : 1;
   const int threads = n >= 512 ? 1024 : (n >= 128 ? 512 : 128);
@@ -776,7 +781,7 @@ int run_power_iteration(const float* xs, const int32_t* pads, int batch, int n,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, power_iteration_kernel, xs, pads, (const float*)v0_dev,
+  PC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, power_iteration_kernel, xs, pads, v0,
                                    n, num_iters, tol, lambdas, iters, ctl, ybuf, csize));
   return PC_OK;
 }
@@ -815,13 +820,13 @@ static int run_power_iteration_sym(const float* xs, int batch, int n, RootCtl* c
                                    float* ybuf, cudaStream_t stream) {
   int rc = prepare_power_iteration(n);
   if (rc != PC_OK) return rc;
-  const float* v0 = power_iteration_v0_host(n);
-  PC_CUDA_CHECK(cudaMemcpyAsync(v0_dev, v0, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+  (void)v0_dev;
+  const float* v0 = power_iteration_v0_device(n);
   const int csize = pick_cluster_size(batch);
-  if (n <= 256) return launch_pi_sym<2, 512, 4>(xs, batch, n, ctl, v0_dev, ybuf, csize, stream);
-  if (n <= 512) return launch_pi_sym<4, 512, 4>(xs, batch, n, ctl, v0_dev, ybuf, csize, stream);
-  if (n <= 1024) return launch_pi_sym<8, 512, 2>(xs, batch, n, ctl, v0_dev, ybuf, csize, stream);
-  return launch_pi_sym<16, 256, 2>(xs, batch, n, ctl, v0_dev, ybuf, csize, stream);
+  if (n <= 256) return launch_pi_sym<2, 512, 4>(xs, batch, n, ctl, v0, ybuf, csize, stream);
+  if (n <= 512) return launch_pi_sym<4, 512, 4>(xs, batch, n, ctl, v0, ybuf, csize, stream);
+  if (n <= 1024) return launch_pi_sym<8, 512, 2>(xs, batch, n, ctl, v0, ybuf, csize, stream);
+  return launch_pi_sym<16, 256, 2>(xs, batch, n, ctl, v0, ybuf, csize, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -1113,7 +1118,7 @@ int run_root(const float* xs, const int32_t* ps, const int32_t* ps_host, const i
                   small_root_workspace_bytes(batch, n));
         return PC_ERR_WORKSPACE;
       }
-      return run_small_root(xs, ps, pads, batch, n, opt, power_iteration_v0_host(n), roots,
+      return run_small_root(xs, ps, pads, batch, n, opt, power_iteration_v0_device(n), roots,
                             metrics, workspace, workspace_bytes, stream);
     }
   }

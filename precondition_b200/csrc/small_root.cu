@@ -693,15 +693,13 @@ bool small_root_supported_exponents(const int32_t* ps_host, int batch) {
 }
 
 int run_small_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch, int n,
-                   const pc_root_options* opt, const float* v0_host_pinned, float* roots,
+                   const pc_root_options* opt, const float* v0_device, float* roots,
                    float* metrics, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   PC_REQUIRE(n >= 1 && n <= kN, "persistent small-block solver needs n <= 128 (n=%d)", n);
   PC_REQUIRE(workspace_bytes >= small_root_workspace_bytes(batch, n), "workspace too small");
   char* w = reinterpret_cast<char*>(align_up((size_t)workspace, 256));
-  float* v0 = reinterpret_cast<float*>(w);
+  const float* v0 = v0_device;  // resident start vector (prepare_power_iteration)
   float* hslot = reinterpret_cast<float*>(w + 512);
-  PC_CUDA_CHECK(cudaMemcpyAsync(v0, v0_host_pinned, sizeof(float) * n, cudaMemcpyHostToDevice,
-                                stream));
   constexpr size_t smem = 2 * (size_t)kMatBytes + sizeof(SmallShared) + 1024;
   static bool configured[64] = {false};
   int dev = 0, sms = 148;
