@@ -645,9 +645,6 @@ class _Shampoo:
       plan.stat_sizes = []
       plan.blocks = []
       if not plan.skip:
-        if len(plan.tshape) > 3:
-          raise NotImplementedError(
-              f"merged shape {plan.tshape} has rank > 3; not supported by the B200 path yet")
         if any(plan.flags) and not 1 <= plan.exponent <= 16:
           raise ValueError(f"inverse-root exponent {plan.exponent} outside [1, 16] "
                            "(exponent_override or tensor rank too large for the Newton programs)")
@@ -829,7 +826,11 @@ class _Shampoo:
     """Grouped-GEMM descriptors for the statistics update (DS:1582-1590) and the
     preconditioner application (DS:1676-1708), built once."""
     D = _lib.GemmDesc
-    stat_descs, stat_meta, apply_descs = [], [], [[], [], []]
+    stat_descs, stat_meta, apply_descs = [], [], []
+    # blocks of merged rank > 3: their mode unfoldings are no two-level strided views of the flat
+    # gradient buffer, so each block is staged through contiguous copies (in: before the
+    # statistics, out: after the last mode product); DS:1676-1708 loops over any rank
+    self._staged = []
     w1 = float(self.beta2)
     w2 = float(self.beta2 if self.beta2 == 1.0 else 1.0 - self.beta2)  # DS:2635-2636
     f32 = 4
@@ -846,6 +847,14 @@ class _Shampoo:
       for offs, sizes, refs in plan.blocks:
         base_elem = plan.offset + sum(o * st for o, st in zip(offs, strides))
         gbase = g0 + f32 * base_elem
+        staged = rank > 3
+        if staged:
+          st_in = torch.empty(sizes, dtype=torch.float32, device=self.device)
+          st_stat = torch.empty_like(st_in) if self.use_avg_grad else st_in
+          st_out = torch.empty_like(st_in)
+          box = tuple(slice(o, o + z) for o, z in zip(offs, sizes))
+          self._staged.append((plan, box, st_in, st_stat, st_out))
+          blk_strides = [int(np.prod(sizes[i + 1:])) for i in range(rank)]
         # ---- statistics: one Gram product per preconditioned axis ----
         for axis in range(rank):
           if refs[axis] is None:
@@ -863,7 +872,13 @@ class _Shampoo:
           d.c = d.c_in = cptr
           d.a_si = d.b_sj = strides[axis]
           d.a_iinner, d.a_sio = sizes[axis], 0
-          if len(others) == 0:
+          if staged:
+            # contiguous block: k = (axes before `axis`, flattened) x (axes after it, flattened)
+            d.a = d.b = st_stat.data_ptr()
+            d.a_si = d.b_sj = blk_strides[axis]
+            suf = blk_strides[axis]
+            kin, sko, ski = suf, sizes[axis] * suf, 1
+          elif len(others) == 0:
             kin, sko, ski = 1, 0, 0
           elif len(others) == 1:
             kin, sko, ski = sizes[others[0]], 0, strides[others[0]]
@@ -886,7 +901,11 @@ class _Shampoo:
         # ---- application: contract the leading axis and roll (DS:1678-1707) ----
         bnumel = int(np.prod(sizes))
         cur_ptr, cur_strides, cur_sizes = gbase, list(strides), list(sizes)
+        if staged:
+          cur_ptr, cur_strides = st_in.data_ptr(), list(blk_strides)
         t_ptrs = [t10 + f32 * (plan.offset + tmp_off), t20 + f32 * (plan.offset + tmp_off)]
+        while len(apply_descs) < rank:
+          apply_descs.append([])
         for j in range(rank):
           d0 = cur_sizes[0]
           rest_sizes, rest_strides = cur_sizes[1:], cur_strides[1:]
@@ -900,6 +919,8 @@ class _Shampoo:
             d.a_iinner, d.a_sio, d.a_si = 1, 0, 0
           elif len(rest_sizes) == 1:
             d.a_iinner, d.a_sio, d.a_si = rest_sizes[0], 0, rest_strides[0]
+          elif staged:  # every intermediate of a staged block is contiguous
+            d.a_iinner, d.a_sio, d.a_si = rest, 0, 1
           else:
             d.a_iinner, d.a_sio, d.a_si = rest_sizes[1], rest_strides[0], rest_strides[1]
           # B(j = output column, k) = P[k, j]
@@ -915,7 +936,11 @@ class _Shampoo:
           d.alpha, d.beta = 1.0, 0.0
           d.c_in = None
           new_sizes = rest_sizes + [d0]
-          if last:
+          if last and staged:
+            d.c = st_out.data_ptr()
+            d.c_iinner, d.c_sio, d.c_sii = rest, 0, d0
+            new_strides = None
+          elif last:
             # final layout == original axis order: write into the param-shaped buffer
             d.c = pg0 + f32 * base_elem
             if rank == 1:
@@ -1016,6 +1041,8 @@ class _Shampoo:
       else:
         self.agbuf.add_(self.gbuf)
       torch.div(self.agbuf, float(k), out=self.sgbuf)
+    if self._staged:
+      self._stage_in()
     # (1) statistics (DS:3644 -> DS:2631-2675)
     if self._stat_count and (self.statistics_compute_steps <= 1 or
                                 step % self.statistics_compute_steps == 0):
@@ -1062,6 +1089,18 @@ class _Shampoo:
 
     rec(stats_tree)
     return out
+
+  def _stage_in(self):
+    """Contiguous copies of the blocks of rank > 3 tensors (see _build_launch_lists)."""
+    for plan, box, st_in, st_stat, _ in self._staged:
+      flat = slice(plan.offset, plan.offset + plan.numel)
+      st_in.copy_(self.gbuf[flat].view(plan.tshape)[box])
+      if st_stat is not st_in:
+        st_stat.copy_(self.sgbuf[flat].view(plan.tshape)[box])
+
+  def _stage_out(self):
+    for plan, box, _, _, st_out in self._staged:
+      self.pgbuf[plan.offset:plan.offset + plan.numel].view(plan.tshape)[box].copy_(st_out)
 
   def _update_statistics(self):
     if self.quantize_second_moment:  # to_float (DS:1588, QU:97-113)
@@ -1413,6 +1452,8 @@ class _Shampoo:
         simt.run()
       if self._apply_tc[j] is not None:
         self._apply_tc[j].run()
+    if self._staged:
+      self._stage_out()
 
   def _transform_all(self, step, lr):
     """Grafting + momentum tail of every parameter (DS:3496-3625) as ONE grouped call over the

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 SUPPORTED = ["default", "two_devices", "quantized_int16", "sqrt_n_input",
              "adagrad_norm_output_wd", "rmsprop_clip", "rmsprop_norm_ma", "adagrad_rank3",
-             "abs_eps_beta2_1",  # "none_noshape" needs rank-4 blocks (not built yet)
+             "abs_eps_beta2_1", "none_noshape",  # rank-4 blocks (staged contiguous copies), p = 8
              "fd", "fd_avg_reset", "fd_every2",  # Sketchy / frequent directions
              "lowrank_pos"]  # eigh-based low-rank roots (largest eigenvalues kept)
 
