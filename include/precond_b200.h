@@ -279,6 +279,14 @@ typedef struct {
   int subspace_iters;          /* block iterations of the large-d path (6)        */
   int oversample;              /* extra basis vectors of the large-d path (32)    */
   int full_eigh_max_dim;       /* <= 512: d up to here is solved exactly (512)    */
+  /* tearfree's Sketchy (TF/sketchy.py:380-470) on the same eigen-solver: the eigenvalue slots
+   * of prev / out hold SINGULAR values, the tail decays by sqrt(decay), no ridge enters the
+   * sketch (ridge_epsilon is ignored), the inverted values are (undeflated + eps)^(-1/p) with
+   * eps = tearfree_epsilon (* the largest undeflated eigenvalue if relative), the const slot
+   * is (tail + eps)^(-1/p), and the has_zeros skip flag is never set. */
+  int tearfree;
+  float tearfree_epsilon;
+  int tearfree_relative_epsilon;
 } pc_fd_options;
 
 void pc_fd_options_default(pc_fd_options* opt);

@@ -432,6 +432,13 @@ TEARFREE_CASES = {
     "none_sum": ([(4, 6), (7,)], 3,
                  dict(learning_rate=0.05, graft="none", merge_dims=8, block_size=4,
                       second_moment_decay=1.0, momentum_decay=0.0, weight_decay=0.1)),
+    "sketchy": ([(12, 9), (5,), (6, 3, 4)], 4,
+                dict(learning_rate=0.1, graft="rmsprop", merge_dims=4, second_order="sketchy",
+                     sketchy_rank=4, sketchy_decay=0.9)),
+    "sketchy_abs": ([(40, 24)], 5,
+                    dict(learning_rate=0.1, graft="sgd", merge_dims=64, second_order="sketchy",
+                         sketchy_rank=6, sketchy_epsilon=1e-5, sketchy_relative_epsilon=False,
+                         sketchy_decay=1.0, sketchy_update_freq=2, momentum_decay=0.0)),
     "tc_blocks": ([(256, 128)], 3,
                   dict(learning_rate=0.01, graft="rmsprop", graft_decay=1.0, merge_dims=128,
                        block_size=128, second_moment_decay=0.9, update_statistics_freq=1)),
@@ -462,6 +469,9 @@ def run_tearfree():
   graft = importlib.import_module("precondition.tearfree.grafting")
   so = importlib.import_module("precondition.tearfree.second_order")
   sh = importlib.import_module("precondition.tearfree.shampoo")
+  sk = importlib.import_module("precondition.tearfree.sketchy")
+  import logging
+  logging.getLogger("absl").setLevel(logging.ERROR)
   mom = importlib.import_module("precondition.tearfree.momentum")
   gtype = {"none": graft.GraftingType.NONE, "sgd": graft.GraftingType.SGD,
            "rmsprop": graft.GraftingType.RMSPROP}
@@ -479,6 +489,13 @@ def run_tearfree():
             skip_preconditioning_rank1=g("skip_preconditioning_rank1", True)),
         second_order_options=so.Options(
             merge_dims=g("merge_dims", 1024),
+            second_order_type=(so.SecondOrderType.SKETCHY if g("second_order", "") == "sketchy"
+                               else so.SecondOrderType.SHAMPOO),
+            sketchy_options=sk.Options(
+                epsilon=g("sketchy_epsilon", 1e-7), rank=g("sketchy_rank", 128),
+                relative_epsilon=g("sketchy_relative_epsilon", True),
+                second_moment_decay=g("sketchy_decay", 0.999),
+                update_freq=g("sketchy_update_freq", 1)),
             shampoo_options=sh.Options(
                 block_size=g("block_size", 1024),
                 update_preconditioners_freq=g("update_preconditioners_freq", 1),
@@ -498,6 +515,14 @@ def run_tearfree():
         out[f"{tag}/update{t}_{i}"] = np.asarray(ui)
     graft_state = state[0]
     direction = graft_state if kw.get("graft") == "none" else graft_state.direction
+    if kw.get("second_order") == "sketchy":
+      for i, t in enumerate(direction[1].sketches):
+        for a, ax in enumerate(getattr(t, "axes", [])):
+          for name in ("eigvals", "inv_eigvals", "tail", "inv_tail"):
+            out[f"{tag}/{name}{i}_{a}"] = np.asarray(getattr(ax, name))
+          v = np.asarray(ax.eigvecs)
+          out[f"{tag}/projector{i}_{a}"] = v @ v.T
+      continue
     blocks = direction[1].blocks
     for i, b in enumerate(blocks):
       if hasattr(b, "stats"):

@@ -99,6 +99,63 @@ class ShampooLeaf:
     return out
 
 
+# --- sketchy (TF/sketchy.py) ---------------------------------------------------------------------
+class SketchyLeaf:
+  """Per axis: eigvecs [d, k], eigvals [k] (singular values), inv_eigvals [k], tail, inv_tail."""
+
+  def __init__(self, shape, rank):
+    if any(d == 1 for d in shape):
+      raise ValueError("unit dimensions")
+    self.shape = list(shape)
+    self.axes = []
+    for d in shape:
+      k = min(d, rank)
+      self.axes.append(dict(eigvecs=np.zeros((d, k), f32), eigvals=np.zeros(k, f32),
+                            inv_eigvals=np.zeros(k, f32), tail=f32(0), inv_tail=f32(0)))
+
+  def update_axis(self, g, dim, st, smd, epsilon, relative):  # TF/sketchy.py:380-470
+    d, k = st["eigvecs"].shape
+    sketch = st["eigvecs"] * st["eigvals"][None, :]
+    rest = [i for i in range(g.ndim) if i != dim]
+    g_dm = g.transpose([dim] + rest).reshape(d, -1)
+    decay = np.sqrt(f32(smd))
+    updated = np.concatenate([sketch * decay, g_dm], axis=1).astype(f32)
+    updated = np.linalg.qr(updated.T, mode="r").T
+    if np.isfinite(updated).all():
+      u, s, _ = np.linalg.svd(updated, full_matrices=False)
+    else:
+      m = min(updated.shape)
+      u, s = np.full((d, m), np.nan, f32), np.full((m,), np.nan, f32)
+    cutoff = max(s[k], 0.0) if k < len(s) else f32(0.0)
+    top = np.maximum(s[:k], 0.0)
+    deflated = np.sqrt(np.maximum(0.0, top - cutoff)) * np.sqrt(top + cutoff)
+    tail = st["tail"] * decay + cutoff**2
+    undeflated = np.square(np.maximum(top, 0.0)) + st["tail"] * decay
+    mask = deflated > 0
+    alpha = f32(-1.0 / (2 * g.ndim))
+    eps = np.max(undeflated) * epsilon if (relative and epsilon > 0) else epsilon
+    st["eigvecs"] = (u[:, :k] * mask).astype(f32)
+    st["inv_eigvals"] = np.where(mask, (undeflated + eps) ** alpha, 0.0).astype(f32)
+    st["eigvals"] = (deflated * mask).astype(f32)
+    st["inv_tail"] = f32((tail + eps) ** alpha if tail > 0 else 0.0)
+    st["tail"] = f32(tail)
+
+  def update(self, g, count, smd, epsilon, relative, update_freq):
+    if count % update_freq == 0:
+      for dim, st in enumerate(self.axes):
+        self.update_axis(g, dim, st, smd, epsilon, relative)
+    roll = tuple(range(1, g.ndim)) + (0,)
+    for st in self.axes:  # TF/sketchy.py:322-361
+      v = st["eigvecs"]
+      basis = np.tensordot(g, v, axes=[[0], [0]])
+      low = np.tensordot(basis, v, axes=[[g.ndim - 1], [1]])
+      g = np.transpose(g, roll)
+      complement = g - low
+      scaled = np.tensordot(basis * st["inv_eigvals"], v, axes=[[g.ndim - 1], [1]])
+      g = (scaled + st["inv_tail"] * complement).astype(f32)
+    return g
+
+
 # --- the optimizer (TF/optimizer.py:61-99) ---------------------------------------------------------
 class Tearfree:
   """lists of arrays in, lists of arrays out.  graft in {'none', 'sgd', 'rmsprop'}."""
@@ -108,7 +165,9 @@ class Tearfree:
                skip_preconditioning_any_dim_gt=4096, skip_preconditioning_rank1=True,
                merge_dims=1024, block_size=1024, update_preconditioners_freq=1,
                update_statistics_freq=1, second_moment_decay=0.999, ema=False, nesterov=True,
-               momentum_decay=0.9, weight_decay=0.0, weight_decay_after_momentum=True):
+               momentum_decay=0.9, weight_decay=0.0, weight_decay_after_momentum=True,
+               second_order="shampoo", sketchy_rank=128, sketchy_epsilon=1e-7,
+               sketchy_relative_epsilon=True, sketchy_decay=0.999, sketchy_update_freq=1):
     self.__dict__.update(locals())
     self.count = 0
     self.masked = []
@@ -116,16 +175,26 @@ class Tearfree:
       skip = graft != "none" and ((skip_preconditioning_rank1 and p.ndim <= 1) or
                                   any(s > skip_preconditioning_any_dim_gt for s in p.shape))
       self.masked.append(skip)
-    self.leaves = [None if m else
-                   ShampooLeaf(derive_shapes(p.shape, merge_dims, block_size)[1], block_size)
-                   for p, m in zip(params, self.masked)]
+    if second_order == "sketchy":  # TF/second_order.py:84-85: no padding
+      self.block_size = 0
+      self.leaves = [None if m else SketchyLeaf(derive_shapes(p.shape, merge_dims, 0)[1],
+                                                sketchy_rank)
+                     for p, m in zip(params, self.masked)]
+    else:
+      self.leaves = [None if m else
+                     ShampooLeaf(derive_shapes(p.shape, merge_dims, block_size)[1], block_size)
+                     for p, m in zip(params, self.masked)]
     self.acc = [np.zeros_like(p, dtype=f32) for p in params]
     self.trace = [np.zeros_like(p, dtype=f32) for p in params]
 
   def direction(self, g, leaf):
     merged = merge(g, self.merge_dims, self.block_size)
-    y = leaf.update(merged, self.count, self.second_moment_decay, self.update_statistics_freq,
-                    self.update_preconditioners_freq)
+    if self.second_order == "sketchy":
+      y = leaf.update(merged, self.count, self.sketchy_decay, self.sketchy_epsilon,
+                      self.sketchy_relative_epsilon, self.sketchy_update_freq)
+    else:
+      y = leaf.update(merged, self.count, self.second_moment_decay, self.update_statistics_freq,
+                      self.update_preconditioners_freq)
     return unmerge(y, g.shape, self.merge_dims, self.block_size)
 
   def update(self, grads, params):

@@ -58,7 +58,9 @@ class FdOptions(ctypes.Structure):
   _fields_ = [("ridge_epsilon", ctypes.c_float), ("error_tolerance", ctypes.c_float),
               ("relative_matrix_epsilon", ctypes.c_int), ("decay", ctypes.c_float),
               ("input_is_gram", ctypes.c_int), ("subspace_iters", ctypes.c_int),
-              ("oversample", ctypes.c_int), ("full_eigh_max_dim", ctypes.c_int)]
+              ("oversample", ctypes.c_int), ("full_eigh_max_dim", ctypes.c_int),
+              ("tearfree", ctypes.c_int), ("tearfree_epsilon", ctypes.c_float),
+              ("tearfree_relative_epsilon", ctypes.c_int)]
 
 
 class Stats(ctypes.Structure):

@@ -90,6 +90,15 @@ struct FdScalars {
   int p;
 };
 
+// tearfree's Sketchy (TF/sketchy.py:380-470) keeps SINGULAR values where distributed_shampoo
+// keeps eigenvalues, decays its tail by sqrt(decay), adds no ridge to the sketch and instead
+// regularises at the inversion: (undeflated + eps)^(-1/p), eps = epsilon (* max undeflated).
+struct FdTearfree {
+  int on;
+  float epsilon;
+  int relative;
+};
+
 __device__ __forceinline__ float fd_hash_uniform(uint32_t b, uint32_t j, uint32_t i) {
   uint32_t x = b * 0x9E3779B1u ^ (j + 0x7F4A7C15u) * 0x85EBCA77u ^ (i + 0x165667B1u) * 0xC2B2AE3Du;
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
@@ -104,17 +113,19 @@ __global__ void __launch_bounds__(256)
 fd_prepare_kernel(const float* __restrict__ prev, const int32_t* __restrict__ ps,
                   const int32_t* __restrict__ pads, int d, int r, float ridge_epsilon,
                   float error_tolerance, int relative_eps, float decay, float* __restrict__ bs,
-                  FdScalars* __restrict__ scal, float* __restrict__ yt, int k, int k_ld) {
+                  FdScalars* __restrict__ scal, float* __restrict__ yt, int k, int k_ld,
+                  FdTearfree tf) {
   __shared__ float scratch[32];
   const int b = blockIdx.x;
   const int pd = r + 2;
   const float* P = prev + (size_t)b * d * pd;
   const int pad = pads ? min(max(pads[b], 0), d) : d;
   const float max_ev = relative_eps ? P[(size_t)(d - r) * pd + r + 1] : 1.0f;   // DS:1155-1158
-  const float ridge = ridge_epsilon * fmaxf(max_ev, error_tolerance);           // DS:1159
+  const float ridge = tf.on ? 0.f : ridge_epsilon * fmaxf(max_ev, error_tolerance);  // DS:1159
   if (threadIdx.x == 0) {
     FdScalars s;
-    s.tail_decayed = P[(size_t)1 * pd + r + 1] * decay;  // DS:1201
+    // DS:1201; TF/sketchy.py:390,425: the tail decays by sqrt(second_moment_decay)
+    s.tail_decayed = P[(size_t)1 * pd + r + 1] * (tf.on ? sqrtf(decay) : decay);
     s.ridge = ridge;
     s.pad = pad;
     s.p = ps[b];
@@ -125,8 +136,10 @@ fd_prepare_kernel(const float* __restrict__ prev, const int32_t* __restrict__ ps
   for (size_t e = threadIdx.x; e < (size_t)d * r; e += blockDim.x) {
     const int i = (int)(e / r), j = (int)(e - (size_t)i * r);
     const bool on = i < pad && j < pad;                                  // DS:1167-1168
-    const float ev = (P[(size_t)(d - r + j) * pd + r + 1] + ridge) * (j < pad ? 1.f : 0.f);
-    const float w = (on ? P[(size_t)i * pd + j] : 0.f) * sqrtf(ev);      // DS:1171
+    const float stored = P[(size_t)(d - r + j) * pd + r + 1];
+    // sqrt(eigenvalue + ridge) -- or the stored singular value itself (TF/sketchy.py:387)
+    const float sv = tf.on ? stored : sqrtf(stored + ridge);
+    const float w = (on ? P[(size_t)i * pd + j] : 0.f) * sv * (j < pad ? 1.f : 0.f);  // DS:1171
     B[e] = sdecay * w;
   }
   if (!yt) return;
@@ -356,7 +369,7 @@ __global__ void fd_gather_rows_kernel(const float* __restrict__ src, const int* 
 __global__ void __launch_bounds__(256)
 fd_finalize_kernel(const float* __restrict__ vt_all, int nv, const float* __restrict__ theta_all,
                    int ld_theta, const FdScalars* __restrict__ scal, int d, int r,
-                   float* __restrict__ out_all, float* __restrict__ metrics) {
+                   float* __restrict__ out_all, float* __restrict__ metrics, FdTearfree tf) {
   extern __shared__ float sh[];
   float* deflated = sh;        // [r]
   float* inverted = sh + r;    // [r]
@@ -382,7 +395,12 @@ fd_finalize_kernel(const float* __restrict__ vt_all, int nv, const float* __rest
   const float cutoff = sqrtf(ev(r));  // s[rank], DS:1195
   const float rho = cutoff * cutoff;
   float new_tail = s.tail_decayed + rho;             // DS:1202
-  const float new_const = new_tail <= 0.f ? 0.f : powf(new_tail, alpha);  // DS:1205
+  // tearfree: eps = epsilon * max(undeflated) with undeflated_0 = theta_0 + decayed tail the
+  // largest (TF/sketchy.py:444-449); distributed_shampoo regularised the sketch instead
+  float inv_eps = 0.f;
+  if (tf.on) inv_eps = tf.relative && tf.epsilon > 0.f ? (ev(0) + s.tail_decayed) * tf.epsilon
+                                                        : tf.epsilon;
+  const float new_const = new_tail <= 0.f ? 0.f : powf(new_tail + inv_eps, alpha);  // DS:1205
   new_tail = new_tail <= 0.f ? 0.f : new_tail;
   // one warp per direction: deflation, norm / padding safety (DS:1199-1246)
   for (int j = warp; j < r; j += nwarp) {
@@ -407,9 +425,9 @@ fd_finalize_kernel(const float* __restrict__ vt_all, int nv, const float* __rest
     defl = defl * (safe ? 1.f : 0.f) * (haspad ? 0.f : 1.f);
     float up = (top * top + s.tail_decayed) * (defl > 0.f ? 1.f : 0.f);  // DS:1247-1248
     up = up <= 0.f ? 0.f : up;
-    const float invd = up <= 0.f ? 0.f : powf(up, alpha);
+    const float invd = up <= 0.f ? 0.f : powf(up + inv_eps, alpha);
     if (lane == 0) {
-      deflated[j] = defl;
+      deflated[j] = tf.on ? sqrtf(defl) : defl;  // TF/sketchy.py:404-406: singular values
       inverted[j] = invd;
       keep[j] = kp;
       scale[j] = inv;
@@ -417,7 +435,8 @@ fd_finalize_kernel(const float* __restrict__ vt_all, int nv, const float* __rest
     }
   }
   __syncthreads();
-  const bool has_zeros = has_zero_flag != 0 || new_tail <= 0.f;
+  // tearfree has no skip rule: dropped directions and an empty tail simply contribute nothing
+  const bool has_zeros = !tf.on && (has_zero_flag != 0 || new_tail <= 0.f);
   const bool zero_all = s.pad == 0;  // DS:1265-1268
   for (size_t e = threadIdx.x; e < (size_t)d * pd; e += blockDim.x) {
     const int i = (int)(e / pd), j = (int)(e - (size_t)i * pd);
@@ -834,6 +853,7 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
                   const pc_fd_options* opt, float* out, float* metrics, void* workspace,
                   size_t workspace_bytes, cudaStream_t stream) {
   const bool gram = opt->input_is_gram != 0;
+  const FdTearfree tf{opt->tearfree, opt->tearfree_epsilon, opt->tearfree_relative_epsilon};
   const FdPlan pl = fd_plan(d, rank, opt);
   FdWorkspace w;
   const size_t need = fd_carve(&w, nullptr, batch, d, m, rank, pl, gram);
@@ -859,7 +879,7 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
   fd_prepare_kernel<<<batch, 256, 0, stream>>>(prev, ps, pads, d, rank, opt->ridge_epsilon,
                                               opt->error_tolerance, opt->relative_matrix_epsilon,
                                               opt->decay, w.bs, w.scal, pl.subspace ? w.yt : nullptr,
-                                              k, w.k_ld);
+                                              k, w.k_ld, tf);
   count_launch(1);
   const unsigned mgrid = (unsigned)std::min<size_t>(((size_t)d * std::max(d, m) + 255) / 256, 1024);
   // ---- covariance C = Bs Bs^T + (masked) F F^T ----
@@ -1044,7 +1064,7 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
     nv = rank + 1;
   }
   fd_finalize_kernel<<<batch, 256, sizeof(float) * 4 * rank, stream>>>(
-      vt_final, nv, w.sorted, k, w.scal, d, rank, out, metrics);
+      vt_final, nv, w.sorted, k, w.scal, d, rank, out, metrics, tf);
   count_launch(1);
   PC_CUDA_CHECK(cudaGetLastError());
   return PC_OK;
@@ -1471,6 +1491,9 @@ void pc_fd_options_default(pc_fd_options* opt) {
   opt->subspace_iters = 6;
   opt->oversample = 32;
   opt->full_eigh_max_dim = 512;
+  opt->tearfree = 0;
+  opt->tearfree_epsilon = 0.f;
+  opt->tearfree_relative_epsilon = 0;
 }
 
 size_t pc_fd_update_workspace_bytes(int batch, int d, int m, int rank, const pc_fd_options* opt) {

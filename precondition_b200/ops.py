@@ -143,8 +143,12 @@ def fd_update_root_batched(
     relative_matrix_epsilon: bool = True, decay: float = 1.0, input_is_gram: bool = False,
     subspace_iters: Optional[int] = None, oversample: Optional[int] = None,
     full_eigh_max_dim: Optional[int] = None,
-    out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    out: Optional[torch.Tensor] = None,
+    tearfree_epsilon: Optional[float] = None,
+    tearfree_relative_epsilon: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
   """Batched Sketchy / frequent-directions step, ``_fd_update_root`` (DS:1123-1290).
+  ``tearfree_epsilon`` (not None) selects tearfree's variant of the update (TF/sketchy.py:380-470,
+  see ``pc_fd_options.tearfree``).
 
   new_grad [b, d, m]: a factor F with F F^T = x x^T (the reference's QR factor has m = d),
   or with ``input_is_gram`` the covariance x x^T [b, d, d].  prev / result: packed sketches
@@ -157,16 +161,22 @@ def fd_update_root_batched(
   b, d, m = new_grad.shape
   assert prev.shape[0] == b and prev.shape[1] == d
   dev = new_grad.device
-  ps_t = torch.as_tensor(ps, dtype=torch.int32).to(dev).contiguous()
+  ps_t = ps if isinstance(ps, torch.Tensor) and ps.is_cuda else \
+      torch.as_tensor(ps, dtype=torch.int32).to(dev).contiguous()
   pads_t = None
   if padding_starts is not None:
-    pads_t = torch.as_tensor(padding_starts, dtype=torch.int32).to(dev).contiguous()
+    pads_t = padding_starts if isinstance(padding_starts, torch.Tensor) and \
+        padding_starts.is_cuda else \
+        torch.as_tensor(padding_starts, dtype=torch.int32).to(dev).contiguous()
   res = out if out is not None else torch.empty_like(prev)
   metrics = torch.empty((b, _lib.PC_NUM_METRICS), dtype=torch.float32, device=dev)
   if b == 0:
     return res, metrics
   opt = _lib.FdOptions()
   lib.pc_fd_options_default(ctypes.byref(opt))
+  if tearfree_epsilon is not None:
+    opt.tearfree, opt.tearfree_epsilon = 1, tearfree_epsilon
+    opt.tearfree_relative_epsilon = int(tearfree_relative_epsilon)
   opt.ridge_epsilon, opt.error_tolerance = ridge_epsilon, error_tolerance
   opt.relative_matrix_epsilon, opt.decay = int(relative_matrix_epsilon), decay
   opt.input_is_gram = int(input_is_gram)

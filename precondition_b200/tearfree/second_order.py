@@ -7,6 +7,7 @@ from typing import Any, Optional
 from precondition_b200.tearfree import praxis_shim
 from precondition_b200.tearfree import reshaper
 from precondition_b200.tearfree import shampoo
+from precondition_b200.tearfree import sketchy
 
 
 @enum.unique
@@ -23,7 +24,7 @@ class Options:
   second_order_type: SecondOrderType = SecondOrderType.SHAMPOO
   shampoo_options: Optional[shampoo.Options] = dataclasses.field(
       default_factory=shampoo.Options)
-  sketchy_options: Optional[Any] = None
+  sketchy_options: Optional[sketchy.Options] = None
 
 
 def _reshaper_options(options: Options) -> reshaper.Options:  # TF/second_order.py:78-89
@@ -40,9 +41,8 @@ def _update_stats_and_precondition(options: Options, _alias_outputs=False):  # T
     assert options.shampoo_options
     return shampoo.apply(options.shampoo_options, _alias_outputs)
   if options.second_order_type == SecondOrderType.SKETCHY:
-    raise NotImplementedError(
-        'tearfree SKETCHY (TF/sketchy.py) is not built; the frequent-directions kernels are '
-        'reachable through distributed_shampoo(frequent_directions=True)')
+    assert options.sketchy_options
+    return sketchy.apply(options.sketchy_options, _alias_outputs)
   raise ValueError('unknown second order type {}'.format(options.second_order_type))
 
 

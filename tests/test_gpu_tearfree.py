@@ -18,6 +18,7 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "tearfree.npz")
 
 def _options(kw):
   from precondition_b200.tearfree import grafting, momentum, optimizer, second_order, shampoo
+  from precondition_b200.tearfree import sketchy
   g = lambda k, d: kw.get(k, d)
   gtype = {"none": grafting.GraftingType.NONE, "sgd": grafting.GraftingType.SGD,
            "rmsprop": grafting.GraftingType.RMSPROP}
@@ -30,6 +31,14 @@ def _options(kw):
           skip_preconditioning_rank1=g("skip_preconditioning_rank1", True)),
       second_order_options=second_order.Options(
           merge_dims=g("merge_dims", 1024),
+          second_order_type=(second_order.SecondOrderType.SKETCHY
+                             if g("second_order", "") == "sketchy"
+                             else second_order.SecondOrderType.SHAMPOO),
+          sketchy_options=sketchy.Options(
+              epsilon=g("sketchy_epsilon", 1e-7), rank=g("sketchy_rank", 128),
+              relative_epsilon=g("sketchy_relative_epsilon", True),
+              second_moment_decay=g("sketchy_decay", 0.999),
+              update_freq=g("sketchy_update_freq", 1)),
           shampoo_options=shampoo.Options(
               block_size=g("block_size", 1024),
               update_preconditioners_freq=g("update_preconditioners_freq", 1),
@@ -68,6 +77,17 @@ def test_tearfree_matches_reference_golden(tag):
   assert ops.gpu_launches > before
   graft_state = state[0]
   direction = graft_state if kw.get("graft") == "none" else graft_state.direction
+  if kw.get("second_order") == "sketchy":
+    for i, t in enumerate(direction[1].sketches):
+      for a, ax in enumerate(getattr(t, "axes", [])):
+        for name in ("eigvals", "inv_eigvals", "tail", "inv_tail"):
+          want = g[f"{tag}/{name}{i}_{a}"]
+          got = getattr(ax, name).cpu().numpy()
+          assert got.shape == want.shape, (name, got.shape, want.shape)
+          assert np.abs(got - want).max() <= 1e-3 * (np.abs(want).max() + 1e-30), (tag, i, a, name)
+        v = ax.eigvecs.cpu().numpy()
+        assert np.abs(v @ v.T - g[f"{tag}/projector{i}_{a}"]).max() <= 2e-3, (tag, i, a)
+    return
   blocks = direction[1].blocks
   for i, b in enumerate(blocks):
     if not hasattr(b, "stats"):
@@ -222,6 +242,32 @@ def test_tearfree_validation_errors():
     tx.init([torch.zeros(4, 4, 4, device="cuda")])
   with pytest.raises(RuntimeError, match="CUDA"):
     tx.init([torch.zeros(4, 3)])
+  from precondition_b200.tearfree import sketchy
+  with pytest.raises(ValueError, match="rank"):
+    sketchy.apply(sketchy.Options(rank=0))
   with pytest.raises(NotImplementedError):
-    second_order.apply(second_order.Options(
-        second_order_type=second_order.SecondOrderType.SKETCHY))
+    sketchy.apply(sketchy.Options(ekfac_svd=True))
+
+
+def test_tearfree_sketchy_large_axis_against_the_oracle():
+  """Sketchy on a 1024 x 768 matrix with rank 32 (the subspace-iteration path of the
+  eigen-solver, tcgen05 Gram and mode products): 4 steps against the oracle's QR + SVD."""
+  from precondition_b200.tearfree import optimizer
+  rng = np.random.default_rng(9)
+  shapes = [(1024, 768)]
+  kw = dict(learning_rate=0.05, graft="rmsprop", merge_dims=1024, second_order="sketchy",
+            sketchy_rank=32, sketchy_decay=0.95, momentum_decay=0.5)
+  params = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+  ref = T.Tearfree(params, **kw)
+  tx = optimizer.tearfree(kw["learning_rate"], _options(kw))
+  dparams = [torch.as_tensor(p).cuda() for p in params]
+  state = tx.init(dparams)
+  low = rng.standard_normal((1024, 40)).astype(np.float32)
+  for t in range(4):
+    # gradients with a decaying spectrum so that the sketch has something to find
+    gr = [(low * np.logspace(0, -2, 40, dtype=np.float32)) @
+          rng.standard_normal((40, 768)).astype(np.float32) +
+          0.01 * rng.standard_normal(shapes[0]).astype(np.float32)]
+    want = ref.update(gr, params)
+    got, state = tx.update([torch.as_tensor(x).cuda() for x in gr], state, dparams)
+    assert _rel(got[0].cpu().numpy(), want[0]) <= 5e-3, (t, _rel(got[0].cpu().numpy(), want[0]))
