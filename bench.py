@@ -793,6 +793,20 @@ def time_resnet50_step(dev, world, steps=3, warm=3):
     out["sharded_vs_single_max_rel"] = max(rel, prel)
     out["sharded_vs_single_updates_max_rel"] = rel
     out["sharded_vs_single_preconditioners_max_rel"] = prel
+    del single, sstate, supd
+    try:  # the pjit layout (DS:2162-2583): statistics stored / updated / solved by their owner only
+      zero = DS.distributed_shampoo(0.1, 1024, preconditioning_compute_steps=1,
+                                    shard_optimizer_states=True, num_devices_for_pjit=world)
+      zstate = zero.init(params).init_fn(params)  # DS:2585-2625: init returns an InitFnState
+      zper, zupd, zstate = _timed_updates(zero, zstate, params, grads, warm, steps)
+      zrel = 0.0
+      for u, v in zip(upd, zupd):
+        zrel = max(zrel, float((u - v).abs().max() / u.abs().max().clamp_min(1e-30)))
+      out["shard_optimizer_states"] = {"ms": sum(zper) / steps,
+                                       "ms_per_step_list": [round(x, 3) for x in zper],
+                                       "updates_vs_replicated_max_rel": zrel}
+    except Exception as e:  # pylint: disable=broad-except
+      out["shard_optimizer_states"] = {"error": f"{type(e).__name__}: {e}"[:200]}
   return out
 
 
