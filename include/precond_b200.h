@@ -199,9 +199,11 @@ int pc_grouped_gemm_splitk(const pc_gemm_desc* descs, int count, int max_m, int 
  * with identical A and B views (the Gram update of DS:1468-1470) is computed as a symmetric
  * rank-k update: lower tiles only, mirrored, so the result is bitwise symmetric.
  * descs_host: HOST array (the host plans the tile list and uploads it into `workspace`, which
- * costs one synchronisation of `stream`).  reuse_plan != 0: the caller guarantees that
+ * costs one synchronisation of `stream`).  reuse_plan bit 0: the caller guarantees that
  * `workspace` still holds the plan of the previous call with identical descriptors (a
- * training loop's static launch list) -- nothing is uploaded and the call only enqueues. */
+ * training loop's static launch list) -- nothing is uploaded and the call only enqueues.
+ * reuse_plan == 3: additionally the B views are unchanged since that call, their packed planes
+ * are reused (a fixed matrix applied to changing blocks). */
 size_t pc_grouped_gemm_tc_workspace_bytes(const pc_gemm_desc* descs_host, int count);
 int pc_grouped_gemm_tc(const pc_gemm_desc* descs_host, int count, void* workspace,
                        size_t workspace_bytes, int reuse_plan, void* stream);

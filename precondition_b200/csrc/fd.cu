@@ -122,7 +122,7 @@ fd_prepare_kernel(const float* __restrict__ prev, const int32_t* __restrict__ ps
   const int pad = pads ? min(max(pads[b], 0), d) : d;
   const float max_ev = relative_eps ? P[(size_t)(d - r) * pd + r + 1] : 1.0f;   // DS:1155-1158
   const float ridge = tf.on ? 0.f : ridge_epsilon * fmaxf(max_ev, error_tolerance);  // DS:1159
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && blockIdx.y == 0) {
     FdScalars s;
     // DS:1201; TF/sketchy.py:390,425: the tail decays by sqrt(second_moment_decay)
     s.tail_decayed = P[(size_t)1 * pd + r + 1] * (tf.on ? sqrtf(decay) : decay);
@@ -133,7 +133,8 @@ fd_prepare_kernel(const float* __restrict__ prev, const int32_t* __restrict__ ps
   }
   const float sdecay = sqrtf(decay);
   float* B = bs + (size_t)b * d * r;
-  for (size_t e = threadIdx.x; e < (size_t)d * r; e += blockDim.x) {
+  for (size_t e = (size_t)blockIdx.y * blockDim.x + threadIdx.x; e < (size_t)d * r;
+       e += (size_t)gridDim.y * blockDim.x) {
     const int i = (int)(e / r), j = (int)(e - (size_t)i * r);
     const bool on = i < pad && j < pad;                                  // DS:1167-1168
     const float stored = P[(size_t)(d - r + j) * pd + r + 1];
@@ -144,7 +145,7 @@ fd_prepare_kernel(const float* __restrict__ prev, const int32_t* __restrict__ ps
   }
   if (!yt) return;
   float* Y = yt + (size_t)b * k_ld * d;  // k rows used of k_ld allocated
-  for (int j = 0; j < k; ++j) {
+  for (int j = blockIdx.y; j < k; j += gridDim.y) {  // whole rows per CTA (block-uniform test)
     bool use_prev = false;
     if (j < r) {  // block-uniform decision: is the previous eigenvector slot populated?
       float ss = 0.f;
@@ -361,6 +362,16 @@ __global__ void fd_gather_rows_kernel(const float* __restrict__ src, const int* 
   for (int i = threadIdx.x; i < len; i += blockDim.x) o[i] = s[i];
 }
 
+// the same with `rows_ld` rows allocated per matrix in dst (rows >= gridDim.x stay as they are)
+__global__ void fd_gather_rows_pad_kernel(const float* __restrict__ src,
+                                          const int* __restrict__ order, int n_rows, int len,
+                                          int rows_ld, float* __restrict__ dst) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  const float* s = src + ((size_t)b * n_rows + order[(size_t)b * n_rows + t]) * len;
+  float* o = dst + ((size_t)b * rows_ld + t) * len;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) o[i] = s[i];
+}
+
 // ---------------------------------------------------------------------------
 // deflation, tail, inversion, safety masks and packing: DS:1195-1262, DS:572-592
 //   vt      [batch, nv, d]  candidate eigenvectors as rows, sorted by eigenvalue (>= r rows)
@@ -546,6 +557,69 @@ static int fd_cholesky_shift(float* a, int k, int batch, float shift, cudaStream
   return PC_OK;
 }
 
+// L^-1 of the [k, k] Cholesky factor into the top-left corner of a zero [k_ld, k_ld] matrix: with
+// it, Qt = L^-1 Yt is ONE tensor-core GEMM instead of k dependent substitution steps over d
+// columns (21 of 76 ms of the Sketchy step at 16 x 4096^2).  One CTA per matrix, the packed
+// triangle in shared memory, one warp per column of the inverse (x_jj = 1 / l_jj,
+// x_ij = -(sum_{j <= m < i} l_im x_mj) / l_ii, the sum split over the lanes in a fixed order).
+__global__ void __launch_bounds__(1024)
+fd_tri_inverse_kernel(const float* __restrict__ l_all, float* __restrict__ inv_all, int k,
+                      int k_ld) {
+  extern __shared__ float tri_smem[];
+  float* packed = tri_smem;                               // k (k + 1) / 2
+  float* xcol = tri_smem + (size_t)k * (k + 1) / 2;       // [32 warps][k]
+  const float* L = l_all + (size_t)blockIdx.x * k * k;
+  float* X = inv_all + (size_t)blockIdx.x * k_ld * k_ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = warp; i < k; i += 32)
+    for (int j = lane; j <= i; j += 32) packed[(size_t)i * (i + 1) / 2 + j] = L[(size_t)i * k + j];
+  __syncthreads();
+  float* x = xcol + (size_t)warp * k;
+  // gridDim.y CTAs share one matrix: the columns are dealt round-robin over all their warps (the
+  // early columns are the long ones), so with k <= 32 gridDim.y every warp solves one column
+  for (int j = blockIdx.y * 32 + warp; j < k; j += gridDim.y * 32) {
+    const float xjj = 1.0f / packed[(size_t)j * (j + 1) / 2 + j];
+    if (lane == 0) {
+      x[j] = xjj;
+      X[(size_t)j * k_ld + j] = xjj;
+    }
+    __syncwarp();
+    for (int i = j + 1; i < k; ++i) {
+      const float* li = packed + (size_t)i * (i + 1) / 2;
+      float acc = 0.f;
+      for (int m = j + lane; m < i; m += 32) acc = fmaf(li[m], x[m], acc);
+      acc = warp_sum(acc);
+      const float xij = -acc / li[i];
+      if (lane == 0) {
+        x[i] = xij;
+        X[(size_t)i * k_ld + j] = xij;
+      }
+      __syncwarp();
+    }
+  }
+}
+static bool fd_tri_inverse_fits(int k) {
+  return ((size_t)k * (k + 1) / 2 + 32 * (size_t)k) * sizeof(float) <= kCholSmemMax;
+}
+static int fd_tri_inverse(const float* l, float* inv, int k, int k_ld, int batch,
+                          cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    PC_CUDA_CHECK(cudaFuncSetAttribute(fd_tri_inverse_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kCholSmemMax));
+    configured = true;
+  }
+  const size_t bytes = ((size_t)k * (k + 1) / 2 + 32 * (size_t)k) * sizeof(float);
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int share = std::max(1, std::min((k + 31) / 32, sms / std::max(batch, 1)));
+  fd_tri_inverse_kernel<<<dim3(batch, share), 1024, bytes, stream>>>(l, inv, k, k_ld);
+  count_launch(1);
+  return PC_OK;
+}
+
 // Qt = L^-1 Yt by forward substitution, in place allowed; one thread per column of the [k, d]
 // block (the k^2 / 2 steps of a column are sequential, the d columns are independent).  The
 // finished part of a thread's column stays in shared memory ([k][128] floats) and the rows of L
@@ -674,6 +748,9 @@ struct FdWorkspace {
   char* tcws_gram; size_t tcws_gram_bytes;  // Gram of Yt (plan reused across iterations)
   char* tcws_c; size_t tcws_c_bytes;        // Qt C (plan reused across iterations)
   char* tcws_misc; size_t tcws_misc_bytes;  // one-off plans (Gram of Qt, Ritz matrix)
+  float* linv;                     // [batch, k_ld, k_ld] inverse Cholesky factor (zero padded)
+  char* tcws_x; size_t tcws_x_bytes;        // L^-1 Yt (plan reused across iterations)
+  char* tcws_x2; size_t tcws_x2_bytes;      // one-off [k_ld, d] products (second pass, final rotation)
 };
 
 // descriptors of the subspace products on the tcgen05 grouped GEMM
@@ -700,6 +777,22 @@ static void fd_timesc_descs(const float* x, const float* cmat, float* dst, int b
     g.a_sko = g.b_sko = 0; g.a_ski = g.b_ski = 1; g.b_sj = d;  // C is symmetric: rows of C
     g.c_iinner = k_ld; g.c_sio = 0; g.c_sii = d;
     g.m = k_ld; g.n = d; g.k = d; g.alpha = 1.f; g.beta = 0.f;
+    out->push_back(g);
+  }
+}
+
+// dst [m_ld, d] = coef [m_ld, kk] (row stride coef_ld) times X [kk rows of a k_ld-row block, d]
+static void fd_left_descs(const float* coef, int coef_ld, int64_t coef_bs, const float* x,
+                          float* dst, int batch, int m_ld, int kk, int k_ld, int d,
+                          std::vector<pc_gemm_desc>* out) {
+  for (int b = 0; b < batch; ++b) {
+    pc_gemm_desc g{};
+    g.a = coef + (size_t)b * coef_bs; g.b = x + (size_t)b * k_ld * d;
+    g.c = dst + (size_t)b * m_ld * d; g.c_in = nullptr;
+    g.a_iinner = m_ld; g.a_sio = 0; g.a_si = coef_ld; g.a_kinner = kk; g.a_sko = 0; g.a_ski = 1;
+    g.b_sj = 1; g.b_kinner = kk; g.b_sko = 0; g.b_ski = d;  // B(j, k) = X[k, j]
+    g.c_iinner = m_ld; g.c_sio = 0; g.c_sii = d;
+    g.m = m_ld; g.n = d; g.k = kk; g.alpha = 1.f; g.beta = 0.f;
     out->push_back(g);
   }
 }
@@ -763,9 +856,25 @@ static size_t fd_carve(FdWorkspace* w, char* base, int batch, int d, int m, int 
     w->qt = (float*)take(B * kl * d * 4);
     w->pt = (float*)take(B * kl * d * 4);
     w->small = (float*)take(B * k * k * 4);
-    w->zsel = (float*)take(B * (rank + 1) * k * 4);
-    w->vtop = (float*)take(B * (rank + 1) * d * 4);
+    // tensor-core path: the selected Ritz vectors and the rotated block are padded to k_ld rows
+    const size_t zrows = (w->k_ld != k) ? kl : (size_t)(rank + 1);
+    w->zsel = (float*)take(B * zrows * k * 4);
+    w->vtop = (float*)take(B * zrows * d * 4);
+    w->linv = nullptr;
+    w->tcws_x = w->tcws_x2 = nullptr;
+    w->tcws_x_bytes = w->tcws_x2_bytes = 0;
     if (w->k_ld != k) {
+      w->linv = (float*)take(B * kl * kl * 4);
+      {
+        std::vector<pc_gemm_desc> gx;
+        fd_left_descs(nullptr, w->k_ld, 0, nullptr, nullptr, batch, w->k_ld, w->k_ld, w->k_ld, d,
+                      &gx);
+        for (auto& gd : gx) gd.b = reinterpret_cast<const float*>(1);
+        w->tcws_x_bytes = tc_grouped_gemm_workspace_bytes(gx.data(), (int)gx.size()) + 1024;
+        w->tcws_x2_bytes = w->tcws_x_bytes;
+        w->tcws_x = take(w->tcws_x_bytes);
+        w->tcws_x2 = take(w->tcws_x2_bytes);
+      }
       w->gram_pad = (float*)take(B * kl * kl * 4);
       std::vector<pc_gemm_desc> g1, g2;
       fd_sub_descs(nullptr, nullptr, nullptr, batch, w->k_ld, d, &g1);
@@ -781,6 +890,9 @@ static size_t fd_carve(FdWorkspace* w, char* base, int batch, int d, int m, int 
     }
   } else {
     w->yt = w->qt = w->pt = w->small = w->zsel = nullptr;
+    w->linv = nullptr;
+    w->tcws_x = w->tcws_x2 = nullptr;
+    w->tcws_x_bytes = w->tcws_x2_bytes = 0;
     w->vtop = (float*)take(B * (rank + 1) * d * 4);
   }
   w->tcws = nullptr;
@@ -876,7 +988,8 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
                      : fd_jacobi(a, vt, n, batch, rot, w.theta, stream);
   };
 
-  fd_prepare_kernel<<<batch, 256, 0, stream>>>(prev, ps, pads, d, rank, opt->ridge_epsilon,
+  // grid.y CTAs share one matrix (the kernel used to run one CTA per matrix: 5 ms at d = 4096)
+  fd_prepare_kernel<<<dim3(batch, 64), 256, 0, stream>>>(prev, ps, pads, d, rank, opt->ridge_epsilon,
                                               opt->error_tolerance, opt->relative_matrix_epsilon,
                                               opt->decay, w.bs, w.scal, pl.subspace ? w.yt : nullptr,
                                               k, w.k_ld, tf);
@@ -947,8 +1060,35 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
         PC_CUDA_CHECK(cudaMemsetAsync(w.yt + ((size_t)b * kl + k) * d, 0,
                                       (size_t)(kl - k) * d * sizeof(float), stream));
     }
-    std::vector<pc_gemm_desc> d_gram_y, d_gram_q, d_ritz, d_c;
-    bool plan_gram = false, plan_c = false;
+    std::vector<pc_gemm_desc> d_gram_y, d_gram_q, d_ritz, d_c, d_x, d_x2, d_rot;
+    bool plan_gram = false, plan_c = false, plan_x = false;
+    // L^-1 as a matrix + one GEMM instead of the forward substitution (PC_FD_TRSM=1: old path)
+    const char* trsm_env = getenv("PC_FD_TRSM");
+    const bool inv_gemm = tc && fd_tri_inverse_fits(k) && !(trsm_env && trsm_env[0] == '1');
+    if (inv_gemm) {
+      PC_CUDA_CHECK(cudaMemsetAsync(w.linv, 0, (size_t)batch * kl * kl * sizeof(float), stream));
+      PC_CUDA_CHECK(cudaMemsetAsync(w.zsel, 0, (size_t)batch * kl * k * sizeof(float), stream));
+      fd_left_descs(w.linv, kl, (int64_t)kl * kl, w.yt, w.qt, batch, kl, kl, kl, d, &d_x);
+      fd_left_descs(w.linv, kl, (int64_t)kl * kl, w.qt, w.pt, batch, kl, kl, kl, d, &d_x2);
+      fd_left_descs(w.zsel, k, (int64_t)kl * k, w.qt, w.vtop, batch, kl, k, kl, d, &d_rot);
+    }
+    // Qt <- L^-1 X for X = Yt (plan reused) or X = Qt (through Pt, which is free at that point)
+    auto solve_rows = [&](const float* x) -> int {
+      if (!inv_gemm) return fd_trsm_rows(w.small, x, w.qt, k, kl, d, batch, stream);
+      int rc = fd_tri_inverse(w.small, w.linv, k, kl, batch, stream);
+      if (rc != PC_OK) return rc;
+      if (x == w.yt) {
+        rc = tc_grouped_gemm(d_x.data(), nullptr, batch, w.tcws_x, w.tcws_x_bytes, plan_x ? 1 : 0,
+                             stream);
+        plan_x = true;
+        return rc;
+      }
+      rc = tc_grouped_gemm(d_x2.data(), nullptr, batch, w.tcws_x2, w.tcws_x2_bytes, 0, stream);
+      if (rc != PC_OK) return rc;
+      PC_CUDA_CHECK(cudaMemcpyAsync(w.qt, w.pt, (size_t)batch * kl * d * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, stream));
+      return PC_OK;
+    };
     if (tc) {
       fd_sub_descs(w.yt, w.yt, w.gram_pad, batch, kl, d, &d_gram_y);
       fd_sub_descs(w.qt, w.qt, w.gram_pad, batch, kl, d, &d_gram_q);
@@ -994,8 +1134,9 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
     // Pt = Qt C (rows of Pt = C q_i); always qt -> pt so that the tensor-core plan is reused
     auto times_c = [&]() -> int {
       if (tc) {
+        // C does not change during the call: after the first product its packed planes stay
         int rc = tc_grouped_gemm(d_c.data(), nullptr, batch, w.tcws_c, w.tcws_c_bytes,
-                                 plan_c ? 1 : 0, stream);
+                                 plan_c ? 3 : 0, stream);
         plan_c = true;
         return rc;
       }
@@ -1027,7 +1168,7 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
         // orthonormalised twice (Cholesky QR 2: orthogonality ~1e-6) before the Rayleigh-Ritz
         // solve, which is the only k x k eigen-solve left.
         rc = fd_cholesky_shift(w.small, k, batch, 1e-5f, stream);
-        if (rc == PC_OK) rc = fd_trsm_rows(w.small, w.yt, w.qt, k, kl, d, batch, stream);
+        if (rc == PC_OK) rc = solve_rows(w.yt);
         if (rc != PC_OK) return rc;
         if (!last) {
           if ((rc = times_c()) != PC_OK) return rc;
@@ -1036,7 +1177,7 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
         }
         if ((rc = gemm_small_from_rows(w.qt, w.qt, w.small)) != PC_OK) return rc;
         rc = fd_cholesky_shift(w.small, k, batch, 0.f, stream);
-        if (rc == PC_OK) rc = fd_trsm_rows(w.small, w.qt, w.qt, k, kl, d, batch, stream);
+        if (rc == PC_OK) rc = solve_rows(w.qt);
         if (rc != PC_OK) return rc;
       } else {
         // round-1 path: orthonormalise through an eigen-solve of the Gram matrix
@@ -1055,13 +1196,25 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
         rotate_rows(w.vt, k, (int64_t)k * k, nullptr, w.pt, w.yt, (int64_t)kl * d);
     }
     fd_sort_kernel<<<batch, 512, 0, stream>>>(w.theta, k, w.order, w.sorted);
-    fd_gather_rows_kernel<<<dim3(rank + 1, batch), 256, 0, stream>>>(w.vt, w.order, k, k, rank + 1,
-                                                                    w.zsel);
-    count_launch(2);
-    rotate_rows(w.zsel, rank + 1, (int64_t)(rank + 1) * k, nullptr, w.qt, w.vtop,
-                (int64_t)(rank + 1) * d);
-    vt_final = w.vtop;
-    nv = rank + 1;
+    if (inv_gemm) {
+      // selected Ritz vectors into the first rank + 1 rows of the zero [k_ld, k] block, then
+      // Vtop = Zsel Qt on the tensor cores (rows >= rank + 1 of the result are zero)
+      fd_gather_rows_pad_kernel<<<dim3(rank + 1, batch), 256, 0, stream>>>(w.vt, w.order, k, k, kl,
+                                                                          w.zsel);
+      count_launch(2);
+      int rc = tc_grouped_gemm(d_rot.data(), nullptr, batch, w.tcws_x2, w.tcws_x2_bytes, 0, stream);
+      if (rc != PC_OK) return rc;
+      vt_final = w.vtop;
+      nv = kl;  // only the batch stride of the rows is taken from nv
+    } else {
+      fd_gather_rows_kernel<<<dim3(rank + 1, batch), 256, 0, stream>>>(w.vt, w.order, k, k, rank + 1,
+                                                                      w.zsel);
+      count_launch(2);
+      rotate_rows(w.zsel, rank + 1, (int64_t)(rank + 1) * k, nullptr, w.qt, w.vtop,
+                  (int64_t)(rank + 1) * d);
+      vt_final = w.vtop;
+      nv = rank + 1;
+    }
   }
   fd_finalize_kernel<<<batch, 256, sizeof(float) * 4 * rank, stream>>>(
       vt_final, nv, w.sorted, k, w.scal, d, rank, out, metrics, tf);
@@ -1097,9 +1250,34 @@ __global__ void fd_add_diag_kernel(const float* __restrict__ packed, int d, int 
     dense[((size_t)b * d + i) * d + i] += c;
 }
 
+// dense = (V diag(lambda^- - c)) V^T: descriptors of the tcgen05 grouped GEMM (d % 128 == 0)
+static void fd_dense_descs(const float* scaled, const float* packed, float* dense, int batch,
+                           int d, int rank, std::vector<pc_gemm_desc>* out) {
+  for (int b = 0; b < batch; ++b) {
+    pc_gemm_desc g{};
+    g.a = scaled + (size_t)b * d * rank; g.b = packed + (size_t)b * d * (rank + 2);
+    g.c = dense + (size_t)b * d * d; g.c_in = nullptr;
+    g.a_iinner = d; g.a_sio = 0; g.a_si = rank; g.a_kinner = g.b_kinner = rank;
+    g.a_sko = g.b_sko = 0; g.a_ski = g.b_ski = 1; g.b_sj = rank + 2;
+    g.c_iinner = d; g.c_sio = 0; g.c_sii = d;
+    g.m = g.n = d; g.k = rank; g.alpha = 1.f; g.beta = 0.f;
+    out->push_back(g);
+  }
+}
+
+size_t low_rank_to_dense_bytes(int batch, int d, int rank) {
+  size_t need = align_up((size_t)batch * d * rank * sizeof(float), 256) + 512;
+  if (fd_use_tc(d)) {
+    std::vector<pc_gemm_desc> g;
+    fd_dense_descs(nullptr, reinterpret_cast<const float*>(1), nullptr, batch, d, rank, &g);
+    need += tc_grouped_gemm_workspace_bytes(g.data(), (int)g.size()) + 1024;
+  }
+  return need;
+}
+
 int run_low_rank_to_dense(const float* packed, int batch, int d, int rank, float* dense,
                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  const size_t need = (size_t)batch * d * rank * sizeof(float) + 256;
+  const size_t need = low_rank_to_dense_bytes(batch, d, rank);
   if (workspace_bytes < need) {
     set_error("low-rank workspace too small: %zu < %zu", workspace_bytes, need);
     return PC_ERR_WORKSPACE;
@@ -1107,6 +1285,18 @@ int run_low_rank_to_dense(const float* packed, int batch, int d, int rank, float
   float* ws = reinterpret_cast<float*>(align_up((size_t)workspace, 256));
   const unsigned grid = (unsigned)std::min<size_t>(((size_t)d * rank + 255) / 256, 512);
   fd_lowrank_scale_kernel<<<dim3(grid, batch), 256, 0, stream>>>(packed, d, rank, ws);
+  if (fd_use_tc(d)) {
+    std::vector<pc_gemm_desc> descs;
+    fd_dense_descs(ws, packed, dense, batch, d, rank, &descs);
+    char* tcws = reinterpret_cast<char*>(ws) + align_up((size_t)batch * d * rank * sizeof(float), 256);
+    const size_t tcb = workspace_bytes - (size_t)(tcws - reinterpret_cast<char*>(workspace));
+    int rc = tc_grouped_gemm(descs.data(), nullptr, batch, tcws, tcb, 0, stream);
+    if (rc != PC_OK) return rc;
+    fd_add_diag_kernel<<<dim3((d + 255) / 256, batch), 256, 0, stream>>>(packed, d, rank, dense);
+    count_launch(2);
+    PC_CUDA_CHECK(cudaGetLastError());
+    return PC_OK;
+  }
   FdGemm g{};
   g.alpha = 1.f;
   g.a = ws; g.b = packed; g.c = dense;
@@ -1415,7 +1605,7 @@ extern "C" {
 
 size_t pc_low_rank_to_dense_workspace_bytes(int batch, int d, int rank) {
   if (batch <= 0 || d <= 0 || rank <= 0) return 0;
-  return (size_t)batch * d * rank * sizeof(float) + 512;
+  return pc::low_rank_to_dense_bytes(batch, d, rank) + 512;
 }
 
 int pc_low_rank_to_dense(const float* packed, int batch, int d, int rank, float* dense,

@@ -1957,6 +1957,7 @@ struct TcGgOperand {  // one packed operand: view + where its tiles go
   const float* base;
   int64_t s_io, s_i, s_ko, s_ki;
   int i_inner, k_inner, rows, k, kblocks, tile0;
+  int is_b, reserved;  // second operand of a general product (its pack can be skipped, see below)
 };
 
 __device__ __forceinline__ float tc_gg_view(const TcGgOperand& o, int i, int kk) {
@@ -1983,10 +1984,11 @@ __device__ __forceinline__ float tc_gg_scale(uint32_t maxbits) {
 // point; the GEMM multiplies each K-chunk by 1 / (sA sB) when it adds it in fp32).
 __global__ void __launch_bounds__(256)
 tc_pack_kernel(const TcGgOperand* __restrict__ ops, float* __restrict__ inv_scale,
-               uint16_t* __restrict__ plane0, uint16_t* __restrict__ plane1) {
+               uint16_t* __restrict__ plane0, uint16_t* __restrict__ plane1, int skip_b) {
   __shared__ float tile[64][129];
   __shared__ uint32_t red[32];
   const TcGgOperand o = ops[blockIdx.y];
+  if (skip_b && o.is_b) return;  // its planes from the previous call are still valid
   const int tiles = (o.rows / 128) * o.kblocks;
   const bool kfast = o.s_ki == 1;
   const bool simple = o.i_inner >= o.rows && o.k_inner >= o.k;  // one-level addressing
@@ -2349,6 +2351,7 @@ static void tc_gg_plan(const pc_gemm_desc* descs, const pc_gemm_quant* quant, in
       ob.base = d.b; ob.s_io = 0; ob.s_i = d.b_sj; ob.s_ko = d.b_sko; ob.s_ki = d.b_ski;
       ob.i_inner = d.n; ob.k_inner = d.b_kinner > 0 ? d.b_kinner : d.k;
       ob.rows = d.n; ob.k = d.k; ob.kblocks = it.kblocks; ob.tile0 = pl->total_tiles;
+      ob.is_b = 1;
       it.b_tile0 = ob.tile0;
       pl->total_tiles += (d.n / 128) * it.kblocks;
       pl->ops.push_back(ob);
@@ -2413,7 +2416,9 @@ int tc_grouped_gemm(const pc_gemm_desc* descs, const pc_gemm_quant* quant, int c
   float* d_inv = reinterpret_cast<float*>(w); w += align_up((size_t)pl.total_tiles * sizeof(float), 256);
   uint16_t* plane0 = reinterpret_cast<uint16_t*>(align_up((size_t)w, 1024));
   uint16_t* plane1 = plane0 + align_up((size_t)pl.total_tiles * TC_TILE_BYTES, 1024) / 2;
-  if (!reuse_plan) {
+  // reuse_plan bit 0: the uploaded plan is still in the workspace; bit 1 (with bit 0): so are the
+  // packed planes of every B operand (the caller guarantees the B views did not change)
+  if (!(reuse_plan & 1)) {
     // the plan lives in heap vectors: wait for the copies before they go out of scope
     PC_CUDA_CHECK(cudaMemcpyAsync(d_items, pl.items.data(), pl.items.size() * sizeof(TcGgItem),
                                   cudaMemcpyHostToDevice, stream));
@@ -2442,7 +2447,7 @@ int tc_grouped_gemm(const pc_gemm_desc* descs, const pc_gemm_quant* quant, int c
   for (const TcGgOperand& o : pl.ops)
     max_tiles = std::max(max_tiles, (o.rows / 128) * o.kblocks);
   tc_pack_kernel<<<dim3((unsigned)std::min(max_tiles, 1024), nops), 256, 0, stream>>>(
-      d_ops, d_inv, plane0, plane1);
+      d_ops, d_inv, plane0, plane1, (reuse_plan & 3) == 3 ? 1 : 0);
   constexpr size_t smem = (size_t)TC_GG_STAGES * 4 * TC_TILE_BYTES + 1024 + 1024;
   static bool configured = false;
   if (!configured) {
