@@ -357,6 +357,32 @@ int pc_dequantize_batched(const void* q, const float* diag, const float* bucket,
                           int batch, int rows, int cols, int qdtype,
                           int extract_diagonal, float* x, void* stream);
 
+/* Grouped form for the int8 momenta of a whole model (the reference maps to_float /
+ * from_float over the parameter tree around _transform_grad, DS:3582-3586, DS:3620-3621): one
+ * segment per momentum, work cut into chunks of pc_quant_group_chunk_elems() elements.
+ *   segments       DEVICE [num_segments]: int8 data q [rows, cols], bucket [cols], the fp32 view
+ *                  x (e.g. a slice of a flat buffer), colmax [cols] uint32 scratch of the
+ *                  quantiser; first_chunk = running sum of nchunks = ceil(rows*cols / chunk)
+ *   chunk_segment  DEVICE [total_chunks] i32
+ *   pc_dequantize_grouped  x = q * bucket[col]                                   (QU:97-113)
+ *   pc_quantize_grouped    bucket = max_rows |x| / 127, q = round(x / bucket)    (QU:49-95);
+ *                          colmax_all / colmax_bytes: the scratch all segments' colmax point into
+ *                          (zeroed here). */
+typedef struct {
+  void* q;
+  float* bucket;
+  float* x;
+  uint32_t* colmax;
+  int32_t rows, cols;
+  int32_t first_chunk, nchunks;
+} pc_quant_segment;
+int64_t pc_quant_group_chunk_elems(void);
+int pc_dequantize_grouped(const pc_quant_segment* segments, const int32_t* chunk_segment,
+                          int num_segments, int64_t total_chunks, void* stream);
+int pc_quantize_grouped(const pc_quant_segment* segments, const int32_t* chunk_segment,
+                        int num_segments, int64_t total_chunks, uint32_t* colmax_all,
+                        size_t colmax_bytes, void* stream);
+
 /* ------------------------------------------------------------------------
  * (4) grafting + momentum tail of _transform_grad (DS:3496-3625) for one
  *     parameter tensor of `numel` elements.  precond_grad is the output of the

@@ -2,6 +2,7 @@
 // to int16 / int8 with optional diagonal extraction, and bf16 casts.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include "common.cuh"
 
 namespace pc {
@@ -161,9 +162,126 @@ __global__ void from_bf16_kernel(const __nv_bfloat16* __restrict__ q, size_t tot
     x[e] = __bfloat162float(q[e]);
 }
 
+// ---------------------------------------------------------------------------
+// Grouped (de)quantisation of the int8 momenta of a whole model (DS:3582-3586, DS:3620-3621):
+// the reference maps to_float / from_float over the parameter tree; here every momentum is a
+// segment {int8 data, bucket sizes [cols], fp32 view in a flat buffer, rows, cols} and three
+// launches serve all of them.  Work items = chunks of kQgChunk consecutive elements.
+// ---------------------------------------------------------------------------
+constexpr int kQgThreads = 256;
+constexpr int kQgChunk = kQgThreads * 32;
+
+__global__ void __launch_bounds__(kQgThreads)
+qgroup_dequantize_kernel(const pc_quant_segment* __restrict__ segs,
+                         const int32_t* __restrict__ chunk_seg, int total_chunks) {
+  for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+    const pc_quant_segment sg = segs[chunk_seg[c]];
+    const int64_t numel = (int64_t)sg.rows * sg.cols;
+    const int64_t begin = (int64_t)(c - sg.first_chunk) * kQgChunk;
+    const int64_t end = begin + kQgChunk < numel ? begin + kQgChunk : numel;
+    const int8_t* q = reinterpret_cast<const int8_t*>(sg.q);
+    for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads)
+      sg.x[e] = (float)q[e] * sg.bucket[e % sg.cols];  // QU:107-108
+  }
+}
+
+// per-column max |x| (bit patterns, atomicMax) into sg.colmax (zero on entry)
+__global__ void __launch_bounds__(kQgThreads)
+qgroup_colmax_kernel(const pc_quant_segment* __restrict__ segs,
+                     const int32_t* __restrict__ chunk_seg, int total_chunks) {
+  __shared__ uint32_t red[32];
+  for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+    const pc_quant_segment sg = segs[chunk_seg[c]];
+    const int64_t numel = (int64_t)sg.rows * sg.cols;
+    const int64_t begin = (int64_t)(c - sg.first_chunk) * kQgChunk;
+    const int64_t end = begin + kQgChunk < numel ? begin + kQgChunk : numel;
+    if (sg.cols == 1) {  // vectors: one bucket for everything -> block reduction, one atomic
+      uint32_t mx = 0;
+      for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads) {
+        const uint32_t ab = absbits(sg.x[e]);
+        mx = ab > mx ? ab : mx;
+      }
+      mx = block_max_u32(mx, red);
+      if (threadIdx.x == 0 && mx) atomicMax(sg.colmax, mx);
+      __syncthreads();
+    } else if (sg.cols <= kQgThreads && kQgThreads % sg.cols == 0) {
+      // a thread always meets the same column: running maximum in a register
+      uint32_t mx = 0;
+      for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads) {
+        const uint32_t ab = absbits(sg.x[e]);
+        mx = ab > mx ? ab : mx;
+      }
+      if (mx) atomicMax(sg.colmax + (begin + threadIdx.x) % sg.cols, mx);
+    } else {
+      for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads) {
+        const uint32_t ab = absbits(sg.x[e]);
+        if (ab) atomicMax(sg.colmax + e % sg.cols, ab);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kQgThreads)
+qgroup_quantize_kernel(const pc_quant_segment* __restrict__ segs,
+                       const int32_t* __restrict__ chunk_seg, int total_chunks) {
+  for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+    const pc_quant_segment sg = segs[chunk_seg[c]];
+    const int64_t numel = (int64_t)sg.rows * sg.cols;
+    const int64_t begin = (int64_t)(c - sg.first_chunk) * kQgChunk;
+    const int64_t end = begin + kQgChunk < numel ? begin + kQgChunk : numel;
+    int8_t* q = reinterpret_cast<int8_t*>(sg.q);
+    for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads) {
+      const int col = (int)(e % sg.cols);
+      const float bs = __uint_as_float(sg.colmax[col]) / 127.0f;  // QU:86-87
+      const float bs_nz = bs > 0.f ? bs : 1.f;                     // QU:90-91
+      if (e < sg.cols) sg.bucket[col] = bs;                        // row 0 publishes the buckets
+      q[e] = to_q<int8_t>(rintf(sg.x[e] / bs_nz));                 // QU:92-95
+    }
+  }
+}
+
 }  // namespace pc
 
 extern "C" {
+
+int64_t pc_quant_group_chunk_elems(void) { return pc::kQgChunk; }
+
+int pc_dequantize_grouped(const pc_quant_segment* segments, const int32_t* chunk_segment,
+                          int num_segments, int64_t total_chunks, void* stream) {
+  PC_REQUIRE(num_segments >= 0 && total_chunks >= 0 && total_chunks < (1ll << 31), "bad counts");
+  if (num_segments == 0 || total_chunks == 0) return PC_OK;
+  PC_REQUIRE(segments && chunk_segment, "null pointer argument");
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)std::min<int64_t>(total_chunks, (int64_t)sms * 8);
+  pc::qgroup_dequantize_kernel<<<grid, pc::kQgThreads, 0, (cudaStream_t)stream>>>(
+      segments, chunk_segment, (int)total_chunks);
+  pc::count_launch(1);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
+
+int pc_quantize_grouped(const pc_quant_segment* segments, const int32_t* chunk_segment,
+                        int num_segments, int64_t total_chunks, uint32_t* colmax_all,
+                        size_t colmax_bytes, void* stream) {
+  PC_REQUIRE(num_segments >= 0 && total_chunks >= 0 && total_chunks < (1ll << 31), "bad counts");
+  if (num_segments == 0 || total_chunks == 0) return PC_OK;
+  PC_REQUIRE(segments && chunk_segment && colmax_all, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PC_CUDA_CHECK(cudaMemsetAsync(colmax_all, 0, colmax_bytes, st));
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)std::min<int64_t>(total_chunks, (int64_t)sms * 8);
+  pc::qgroup_colmax_kernel<<<grid, pc::kQgThreads, 0, st>>>(segments, chunk_segment,
+                                                           (int)total_chunks);
+  pc::qgroup_quantize_kernel<<<grid, pc::kQgThreads, 0, st>>>(segments, chunk_segment,
+                                                             (int)total_chunks);
+  pc::count_launch(2);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
+}
 
 int pc_quantize_batched(const float* x, int batch, int rows, int cols, int qdtype,
                         int extract_diagonal, void* q, float* diag, float* bucket,

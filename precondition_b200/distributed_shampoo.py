@@ -1473,14 +1473,32 @@ class _Shampoo:
           clip_by_scaled_gradient_norm=float(self.clip_by_scaled_gradient_norm or 0.0))
     quantised = [(pl, st) for pl, st in zip(self.plans, self._own_leaves)
                  if pl.mdt != torch.float32]
-    for pl, st in quantised:  # int8 momenta: to_float into the flat scratch (DS:3582-3586)
+    int8 = [(pl, st) for pl, st in quantised if pl.mdt == torch.int8]
+    other = [(pl, st) for pl, st in quantised if pl.mdt != torch.int8]
+    # int8 momenta (the usual best_effort_memory_usage_reduction case): every to_float /
+    # from_float of the model in one grouped call each; the segment table is static
+    ptrs = tuple(qv.quantized.data_ptr() for _, st in int8
+                 for qv in (st.momentum, st.diagonal_momentum))
+    if getattr(self, "_qgroup_key", None) != ptrs:
+      self._qgroup_key = ptrs
+      items = []
+      for pl, st in int8:
+        seg = slice(pl.offset, pl.offset + pl.numel)
+        for qv, buf in ((st.momentum, self.mbuf), (st.diagonal_momentum, self.dmbuf)):
+          items.append((qv.quantized, qv.bucket_size, buf[seg]))
+      self._qgroup = ops.QuantGroup(items, self.device) if items else None
+    if self._qgroup is not None:
+      self._qgroup.dequantize()  # to_float into the flat scratch (DS:3582-3586)
+    for pl, st in other:
       seg = slice(pl.offset, pl.offset + pl.numel)
       for qv, buf in ((st.momentum, self.mbuf), (st.diagonal_momentum, self.dmbuf)):
         buf[seg].copy_(qv.to_float().reshape(-1))
     ubuf = torch.empty(self.total, dtype=torch.float32, device=self.device)
     self._graft_group.run(self.gbuf, self.pbuf, self.pgbuf, self.dsbuf, self.dmbuf, self.mbuf,
                           ubuf, self._graft_opt)
-    for pl, st in quantised:  # requantise (DS:3620-3621)
+    if self._qgroup is not None:
+      self._qgroup.quantize()  # requantise (DS:3620-3621)
+    for pl, st in other:
       seg = slice(pl.offset, pl.offset + pl.numel)
       for qv, buf in ((st.momentum, self.mbuf), (st.diagonal_momentum, self.dmbuf)):
         q, _, b = QuantizedValue.quantize(buf[seg].view(pl.shape), pl.mdt)

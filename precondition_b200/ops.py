@@ -448,6 +448,59 @@ def dequantize(q: torch.Tensor, diag, bucket, extract_diagonal: bool = False,
   return x[0] if (squeeze and out is None) else x
 
 
+class QuantGroup:
+  """Static launch list of ``pc_dequantize_grouped`` / ``pc_quantize_grouped``: the int8 momenta
+  of a whole model in one / two launches.  ``items``: (q int8 tensor, bucket fp32 tensor, x fp32
+  view) with q.numel() == x.numel(); the per-column layout is [q.shape[0], rest] (QU:86)."""
+
+  def __init__(self, items, device):
+    lib = _lib.load()
+    self.device = device
+    self.n = len(items)
+    self.keep = items  # the tensors the table points at
+    chunk = int(lib.pc_quant_group_chunk_elems())
+    total_cols = sum(int(b.numel()) for _, b, _ in items)
+    self.colmax = torch.zeros(max(total_cols, 1), dtype=torch.int32, device=device)
+    segs = (_lib.QuantSegment * max(self.n, 1))()
+    chunk_seg, first, coff = [], 0, 0
+    for i, (q, bucket, x) in enumerate(items):
+      _require_cuda(q, bucket, x)
+      assert q.dtype == torch.int8 and bucket.dtype == torch.float32 and x.dtype == torch.float32
+      rows = int(q.shape[0]) if q.dim() > 0 else 1
+      cols = int(q.numel()) // max(rows, 1)
+      assert bucket.numel() == cols and x.numel() == q.numel(), (q.shape, bucket.shape, x.shape)
+      nch = max(1, -(-int(q.numel()) // chunk))
+      sg = segs[i]
+      sg.q, sg.bucket, sg.x = q.data_ptr(), bucket.data_ptr(), x.data_ptr()
+      sg.colmax = self.colmax.data_ptr() + 4 * coff
+      sg.rows, sg.cols, sg.first_chunk, sg.nchunks = rows, cols, first, nch
+      chunk_seg += [i] * nch
+      first += nch
+      coff += cols
+    self.total_chunks = first
+    self.segs = torch.frombuffer(bytearray(bytes(segs)), dtype=torch.uint8).to(device)
+    self.chunk_seg = torch.tensor(chunk_seg, dtype=torch.int32).to(device)
+
+  def dequantize(self):
+    global gpu_launches
+    if not self.n:
+      return
+    with torch.cuda.device(self.device):
+      _lib.check(_lib.load().pc_dequantize_grouped(_ptr(self.segs), _ptr(self.chunk_seg), self.n,
+                                                   self.total_chunks, ctypes.c_void_p(_stream())))
+    gpu_launches += 1
+
+  def quantize(self):
+    global gpu_launches
+    if not self.n:
+      return
+    with torch.cuda.device(self.device):
+      _lib.check(_lib.load().pc_quantize_grouped(
+          _ptr(self.segs), _ptr(self.chunk_seg), self.n, self.total_chunks, _ptr(self.colmax),
+          self.colmax.numel() * 4, ctypes.c_void_p(_stream())))
+    gpu_launches += 2
+
+
 def upload_gemm_descs(descs: Sequence[_lib.GemmDesc], device) -> torch.Tensor:
   """Packs descriptors into a device byte tensor (kept alive by the caller)."""
   arr = (_lib.GemmDesc * len(descs))(*descs)
