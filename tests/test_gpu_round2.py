@@ -607,3 +607,37 @@ def test_quantize_two_pass_tall_matrices_bit_exact():
       np.testing.assert_array_equal(bs[i].cpu().numpy(), wb)
       if ext:
         np.testing.assert_array_equal(d.cpu().numpy(), wd)
+
+
+def test_grouped_int8_momentum_quantisation_is_bit_exact():
+  """pc_quantize_grouped / pc_dequantize_grouped (all int8 momenta of a model in three launches)
+  against the per-tensor kernels, which are bit-exact against the reference goldens (QU:49-113):
+  vectors (one bucket), columns that divide the block size, odd column counts, wide matrices, a
+  zero column and a tensor longer than one work chunk."""
+  from precondition_b200 import ops
+  gen = torch.Generator(device="cuda").manual_seed(12)
+  shapes = [(37,), (8192 * 3 + 5,), (64, 64), (300, 3), (5, 300), (16, 4096), (1024, 16, 64), (2, 2)]
+  xs = [torch.randn(s, generator=gen, device="cuda") * 10 ** float(i % 4 - 2)
+        for i, s in enumerate(shapes)]
+  xs[2][:, 5] = 0.0  # QU:90-91: zero bucket -> divide by one
+  flat = torch.cat([x.reshape(-1) for x in xs]).contiguous()
+  items, off = [], 0
+  for x in xs:
+    q = torch.empty(x.shape, dtype=torch.int8, device="cuda")
+    b = torch.empty(x.shape[1:], dtype=torch.float32, device="cuda")
+    items.append((q, b, flat[off:off + x.numel()]))
+    off += x.numel()
+  grp = ops.QuantGroup(items, torch.device("cuda", 0))
+  grp.quantize()
+  for x, (q, b, _) in zip(xs, items):
+    mat = x.reshape(x.shape[0], -1).contiguous()
+    q_ref, _, b_ref = ops.quantize(mat, torch.int8)
+    assert torch.equal(q.reshape(mat.shape), q_ref) and torch.equal(b.reshape(-1), b_ref)
+  flat.zero_()
+  grp.dequantize()
+  off = 0
+  for x, (q, b, _) in zip(xs, items):
+    mat_q = q.reshape(x.shape[0], -1).contiguous()
+    want = ops.dequantize(mat_q, None, b.reshape(-1).contiguous())
+    assert torch.equal(flat[off:off + x.numel()], want.reshape(-1))
+    off += x.numel()
