@@ -363,7 +363,10 @@ int pc_dequantize_batched(const void* q, const float* diag, const float* bucket,
  *   segments       DEVICE [num_segments]: int8 data q [rows, cols], bucket [cols], the fp32 view
  *                  x (e.g. a slice of a flat buffer), colmax [cols] uint32 scratch of the
  *                  quantiser; first_chunk = running sum of nchunks = ceil(rows*cols / chunk)
- *   chunk_segment  DEVICE [total_chunks] i32
+ *                  the column maxima are reduced over tiles of pc_quant_group_tile_rows() rows x
+ *                  128 columns: col_tiles = ceil(cols / 128), first_tile = running sum of
+ *                  ceil(rows / tile_rows) * col_tiles
+ *   chunk_segment  DEVICE [total_chunks] i32;  tile_segment  DEVICE [total_tiles] i32
  *   pc_dequantize_grouped  x = q * bucket[col]                                   (QU:97-113)
  *   pc_quantize_grouped    bucket = max_rows |x| / 127, q = round(x / bucket)    (QU:49-95);
  *                          colmax_all / colmax_bytes: the scratch all segments' colmax point into
@@ -375,13 +378,16 @@ typedef struct {
   uint32_t* colmax;
   int32_t rows, cols;
   int32_t first_chunk, nchunks;
+  int32_t first_tile, col_tiles;
 } pc_quant_segment;
 int64_t pc_quant_group_chunk_elems(void);
+int pc_quant_group_tile_rows(void);
 int pc_dequantize_grouped(const pc_quant_segment* segments, const int32_t* chunk_segment,
                           int num_segments, int64_t total_chunks, void* stream);
 int pc_quantize_grouped(const pc_quant_segment* segments, const int32_t* chunk_segment,
-                        int num_segments, int64_t total_chunks, uint32_t* colmax_all,
-                        size_t colmax_bytes, void* stream);
+                        int num_segments, int64_t total_chunks, const int32_t* tile_segment,
+                        int64_t total_tiles, uint32_t* colmax_all, size_t colmax_bytes,
+                        void* stream);
 
 /* ------------------------------------------------------------------------
  * (4) grafting + momentum tail of _transform_grad (DS:3496-3625) for one

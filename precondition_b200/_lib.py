@@ -45,7 +45,8 @@ EXPORTED_SYMBOLS = (
     "pc_lobpcg_diagnostics",
     "pc_pinv_pth_root_eigh_batched", "pc_tearfree_transform_workspace_bytes",
     "pc_tearfree_transform",
-    "pc_quant_group_chunk_elems", "pc_dequantize_grouped", "pc_quantize_grouped",
+    "pc_quant_group_chunk_elems", "pc_quant_group_tile_rows", "pc_dequantize_grouped",
+    "pc_quantize_grouped",
 )
 
 
@@ -108,7 +109,8 @@ class GraftSegment(ctypes.Structure):
 class QuantSegment(ctypes.Structure):
   _fields_ = [("q", ctypes.c_void_p), ("bucket", ctypes.c_void_p), ("x", ctypes.c_void_p),
               ("colmax", ctypes.c_void_p), ("rows", ctypes.c_int32), ("cols", ctypes.c_int32),
-              ("first_chunk", ctypes.c_int32), ("nchunks", ctypes.c_int32)]
+              ("first_chunk", ctypes.c_int32), ("nchunks", ctypes.c_int32),
+              ("first_tile", ctypes.c_int32), ("col_tiles", ctypes.c_int32)]
 
 
 class TearfreeSegment(ctypes.Structure):
@@ -270,7 +272,9 @@ def load() -> ctypes.CDLL:
   lib.pc_quant_group_chunk_elems.restype = i64
   lib.pc_dequantize_grouped.argtypes = [vp, vp, i32, i64, vp]
   lib.pc_dequantize_grouped.restype = i32
-  lib.pc_quantize_grouped.argtypes = [vp, vp, i32, i64, vp, sz, vp]
+  lib.pc_quant_group_tile_rows.argtypes = []
+  lib.pc_quant_group_tile_rows.restype = i32
+  lib.pc_quantize_grouped.argtypes = [vp, vp, i32, i64, vp, i64, vp, sz, vp]
   lib.pc_quantize_grouped.restype = i32
   lib.pc_pinv_pth_root_eigh_batched.argtypes = [vp, vp, i32, i32, f32, vp, vp, sz, vp]
   lib.pc_pinv_pth_root_eigh_batched.restype = i32

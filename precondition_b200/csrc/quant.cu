@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <stdint.h>
 #include "common.cuh"
 
 namespace pc {
@@ -98,6 +99,96 @@ __global__ void dequantize_kernel(const Q* __restrict__ q, const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------
+// Vectorised forms (cols % 4 == 0, 16-byte aligned fp32, 4-element aligned integers): one
+// thread = four consecutive columns of one row, rows of all matrices of the batch strided over
+// grid.y -- no 64-bit index division per element, 16-byte fp32 and 8 / 4-byte integer accesses.
+// Same arithmetic as the scalar kernels (bit-identical output).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void q_load4(const int16_t* p, float (&v)[4]) {
+  const short4 s = *reinterpret_cast<const short4*>(p);
+  v[0] = (float)s.x; v[1] = (float)s.y; v[2] = (float)s.z; v[3] = (float)s.w;
+}
+__device__ __forceinline__ void q_load4(const int8_t* p, float (&v)[4]) {
+  const char4 s = *reinterpret_cast<const char4*>(p);
+  v[0] = (float)s.x; v[1] = (float)s.y; v[2] = (float)s.z; v[3] = (float)s.w;
+}
+__device__ __forceinline__ void q_store4(int16_t* p, const float (&r)[4]) {
+  *reinterpret_cast<short4*>(p) = make_short4((short)r[0], (short)r[1], (short)r[2], (short)r[3]);
+}
+__device__ __forceinline__ void q_store4(int8_t* p, const float (&r)[4]) {
+  *reinterpret_cast<char4*>(p) = make_char4((signed char)r[0], (signed char)r[1],
+                                            (signed char)r[2], (signed char)r[3]);
+}
+
+template <typename Q>
+__global__ void __launch_bounds__(256)
+dequantize_vec_kernel(const Q* __restrict__ q, const float* __restrict__ diag,
+                      const float* __restrict__ bucket, int batch, int rows, int cols,
+                      int extract_diagonal, float* __restrict__ x) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const int total_rows = batch * rows;
+  for (int R = blockIdx.y; R < total_rows; R += gridDim.y) {
+    const int b = R / rows, r = R - b * rows;
+    const size_t off = (size_t)R * cols + c;
+    float v[4];
+    q_load4(q + off, v);
+    const float4 bs = *reinterpret_cast<const float4*>(bucket + (size_t)b * cols + c);
+    float4 o = make_float4(v[0] * bs.x, v[1] * bs.y, v[2] * bs.z, v[3] * bs.w);  // QU:110
+    if (extract_diagonal && r >= c && r < c + 4) {                               // QU:111-112
+      const float dg = diag[(size_t)b * rows + r];
+      if (r == c) o.x += dg; else if (r == c + 1) o.y += dg;
+      else if (r == c + 2) o.z += dg; else o.w += dg;
+    }
+    *reinterpret_cast<float4*>(x + off) = o;
+  }
+}
+
+// kDiagBucket: the diagonal element's thread publishes the bucket (quantize_from_colmax, square
+// matrices with an extracted diagonal); otherwise row 0 does (quant_apply)
+template <typename Q, bool kDiagBucket>
+__global__ void __launch_bounds__(256)
+quantize_vec_kernel(const float* __restrict__ x, const uint32_t* __restrict__ colmax, int batch,
+                    int rows, int cols, float num_buckets, int extract_diagonal,
+                    Q* __restrict__ q, float* __restrict__ diag, float* __restrict__ bucket) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const int total_rows = batch * rows;
+  for (int R = blockIdx.y; R < total_rows; R += gridDim.y) {
+    const int b = R / rows, r = R - b * rows;
+    const size_t off = (size_t)R * cols + c;
+    const float4 xv = *reinterpret_cast<const float4*>(x + off);
+    const uint4 cm = *reinterpret_cast<const uint4*>(colmax + (size_t)b * cols + c);
+    float v[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float bs[4] = {__uint_as_float(cm.x) / num_buckets, __uint_as_float(cm.y) / num_buckets,
+                         __uint_as_float(cm.z) / num_buckets, __uint_as_float(cm.w) / num_buckets};
+    float out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool on_diag = extract_diagonal && r == c + k;
+      if (on_diag) {
+        diag[(size_t)b * rows + r] = v[k];  // QU:72-76
+        v[k] = v[k] - v[k];
+      }
+      if (kDiagBucket ? (r == c + k) : (r == 0)) bucket[(size_t)b * cols + c + k] = bs[k];
+      const float bs_nz = bs[k] > 0.f ? bs[k] : 1.f;  // QU:90-91
+      out[k] = rintf(v[k] / bs_nz);                   // QU:92-95
+    }
+    q_store4(q + off, out);
+  }
+}
+
+static bool quant_vec_ok(const void* x, const void* q, const void* aux, int cols, int elem_q,
+                         long long total_rows) {
+  return cols % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)q & (4 * elem_q - 1)) == 0 &&
+         ((uintptr_t)aux & 15) == 0 && total_rows < (1ll << 31);
+}
+static dim3 quant_vec_grid(int cols, long long total_rows) {
+  return dim3((unsigned)((cols / 4 + 255) / 256),
+              (unsigned)std::min<long long>(total_rows, 8192));
+}
+
 // Two-pass form for tall matrices (momenta of shape [d0, rest], large statistics): the column
 // kernel above walks a whole column per thread, i.e. cols / 32 CTAs of 1024+ dependent loads.
 // Pass 1 reduces max |x| per column over row chunks (atomicMax on the float bits, all values >= 0),
@@ -180,43 +271,67 @@ qgroup_dequantize_kernel(const pc_quant_segment* __restrict__ segs,
     const int64_t begin = (int64_t)(c - sg.first_chunk) * kQgChunk;
     const int64_t end = begin + kQgChunk < numel ? begin + kQgChunk : numel;
     const int8_t* q = reinterpret_cast<const int8_t*>(sg.q);
-    for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads)
-      sg.x[e] = (float)q[e] * sg.bucket[e % sg.cols];  // QU:107-108
+    const bool vec = sg.cols % 4 == 0 && (((uintptr_t)sg.x | (uintptr_t)sg.bucket) & 15) == 0 &&
+                     ((uintptr_t)sg.q & 3) == 0;
+    if (vec) {  // four consecutive elements share a row: 32-bit column arithmetic per group
+      const int col0 = (int)(begin % sg.cols), n4 = (int)((end - begin) >> 2);
+      for (int g = threadIdx.x; g < n4; g += kQgThreads) {
+        const int col = (col0 + 4 * g) % sg.cols;
+        const char4 qv = *reinterpret_cast<const char4*>(q + begin + 4 * g);
+        const float4 bs = *reinterpret_cast<const float4*>(sg.bucket + col);
+        *reinterpret_cast<float4*>(sg.x + begin + 4 * g) =
+            make_float4((float)qv.x * bs.x, (float)qv.y * bs.y, (float)qv.z * bs.z,
+                        (float)qv.w * bs.w);  // QU:107-108
+      }
+    } else {
+      for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads)
+        sg.x[e] = (float)q[e] * sg.bucket[e % sg.cols];
+    }
   }
 }
 
-// per-column max |x| (bit patterns, atomicMax) into sg.colmax (zero on entry)
+// per-column max |x| (bit patterns, atomicMax) into sg.colmax (zero on entry).  Work items are
+// tiles of kQgTileRows rows x 128 columns: a lane owns four consecutive columns, a warp strides
+// over the rows, the eight warps meet in shared memory, one atomic per column and tile.
+constexpr int kQgTileRows = 128;
 __global__ void __launch_bounds__(kQgThreads)
 qgroup_colmax_kernel(const pc_quant_segment* __restrict__ segs,
-                     const int32_t* __restrict__ chunk_seg, int total_chunks) {
-  __shared__ uint32_t red[32];
-  for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
-    const pc_quant_segment sg = segs[chunk_seg[c]];
-    const int64_t numel = (int64_t)sg.rows * sg.cols;
-    const int64_t begin = (int64_t)(c - sg.first_chunk) * kQgChunk;
-    const int64_t end = begin + kQgChunk < numel ? begin + kQgChunk : numel;
-    if (sg.cols == 1) {  // vectors: one bucket for everything -> block reduction, one atomic
-      uint32_t mx = 0;
-      for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads) {
-        const uint32_t ab = absbits(sg.x[e]);
-        mx = ab > mx ? ab : mx;
+                     const int32_t* __restrict__ tile_seg, int total_tiles) {
+  __shared__ uint32_t smax[8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const pc_quant_segment sg = segs[tile_seg[t]];
+    const int local = t - sg.first_tile;
+    const int tr = local / sg.col_tiles, tc = local - tr * sg.col_tiles;
+    const int r0 = tr * kQgTileRows, r1 = min(sg.rows, r0 + kQgTileRows);
+    const int c = tc * 128 + lane * 4;
+    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    const bool vec = sg.cols % 4 == 0 && ((uintptr_t)sg.x & 15) == 0;
+    if (c < sg.cols) {
+      for (int r = r0 + warp; r < r1; r += 8) {
+        const float* row = sg.x + (size_t)r * sg.cols + c;
+        if (vec) {
+          const float4 v = *reinterpret_cast<const float4*>(row);
+          m0 = max(m0, absbits(v.x)); m1 = max(m1, absbits(v.y));
+          m2 = max(m2, absbits(v.z)); m3 = max(m3, absbits(v.w));
+        } else {
+          m0 = max(m0, absbits(row[0]));
+          if (c + 1 < sg.cols) m1 = max(m1, absbits(row[1]));
+          if (c + 2 < sg.cols) m2 = max(m2, absbits(row[2]));
+          if (c + 3 < sg.cols) m3 = max(m3, absbits(row[3]));
+        }
       }
-      mx = block_max_u32(mx, red);
-      if (threadIdx.x == 0 && mx) atomicMax(sg.colmax, mx);
-      __syncthreads();
-    } else if (sg.cols <= kQgThreads && kQgThreads % sg.cols == 0) {
-      // a thread always meets the same column: running maximum in a register
-      uint32_t mx = 0;
-      for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads) {
-        const uint32_t ab = absbits(sg.x[e]);
-        mx = ab > mx ? ab : mx;
-      }
-      if (mx) atomicMax(sg.colmax + (begin + threadIdx.x) % sg.cols, mx);
-    } else {
-      for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads) {
-        const uint32_t ab = absbits(sg.x[e]);
-        if (ab) atomicMax(sg.colmax + e % sg.cols, ab);
-      }
+    }
+    __syncthreads();
+    smax[warp][lane * 4] = m0; smax[warp][lane * 4 + 1] = m1;
+    smax[warp][lane * 4 + 2] = m2; smax[warp][lane * 4 + 3] = m3;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      uint32_t m = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) m = max(m, smax[w][threadIdx.x]);
+      const int col = tc * 128 + threadIdx.x;
+      if (col < sg.cols && m) atomicMax(sg.colmax + col, m);
     }
   }
 }
@@ -230,12 +345,34 @@ qgroup_quantize_kernel(const pc_quant_segment* __restrict__ segs,
     const int64_t begin = (int64_t)(c - sg.first_chunk) * kQgChunk;
     const int64_t end = begin + kQgChunk < numel ? begin + kQgChunk : numel;
     int8_t* q = reinterpret_cast<int8_t*>(sg.q);
-    for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads) {
-      const int col = (int)(e % sg.cols);
-      const float bs = __uint_as_float(sg.colmax[col]) / 127.0f;  // QU:86-87
-      const float bs_nz = bs > 0.f ? bs : 1.f;                     // QU:90-91
-      if (e < sg.cols) sg.bucket[col] = bs;                        // row 0 publishes the buckets
-      q[e] = to_q<int8_t>(rintf(sg.x[e] / bs_nz));                 // QU:92-95
+    const bool vec = sg.cols % 4 == 0 && (((uintptr_t)sg.x | (uintptr_t)sg.colmax) & 15) == 0 &&
+                     ((uintptr_t)sg.q & 3) == 0;
+    if (vec) {
+      const int col0 = (int)(begin % sg.cols), n4 = (int)((end - begin) >> 2);
+      for (int g = threadIdx.x; g < n4; g += kQgThreads) {
+        const int col = (col0 + 4 * g) % sg.cols;
+        const float4 xv = *reinterpret_cast<const float4*>(sg.x + begin + 4 * g);
+        const uint4 cm = *reinterpret_cast<const uint4*>(sg.colmax + col);
+        const float b0 = __uint_as_float(cm.x) / 127.0f, b1 = __uint_as_float(cm.y) / 127.0f,
+                    b2 = __uint_as_float(cm.z) / 127.0f, b3 = __uint_as_float(cm.w) / 127.0f;
+        if (begin + 4 * g < sg.cols) {  // row 0 publishes the buckets
+          sg.bucket[col] = b0; sg.bucket[col + 1] = b1;
+          sg.bucket[col + 2] = b2; sg.bucket[col + 3] = b3;
+        }
+        *reinterpret_cast<char4*>(q + begin + 4 * g) = make_char4(
+            (signed char)rintf(xv.x / (b0 > 0.f ? b0 : 1.f)),
+            (signed char)rintf(xv.y / (b1 > 0.f ? b1 : 1.f)),
+            (signed char)rintf(xv.z / (b2 > 0.f ? b2 : 1.f)),
+            (signed char)rintf(xv.w / (b3 > 0.f ? b3 : 1.f)));  // QU:86-95
+      }
+    } else {
+      for (int64_t e = begin + threadIdx.x; e < end; e += kQgThreads) {
+        const int col = (int)(e % sg.cols);
+        const float bs = __uint_as_float(sg.colmax[col]) / 127.0f;  // QU:86-87
+        const float bs_nz = bs > 0.f ? bs : 1.f;                     // QU:90-91
+        if (e < sg.cols) sg.bucket[col] = bs;                        // row 0 publishes the buckets
+        q[e] = to_q<int8_t>(rintf(sg.x[e] / bs_nz));                 // QU:92-95
+      }
     }
   }
 }
@@ -245,6 +382,7 @@ qgroup_quantize_kernel(const pc_quant_segment* __restrict__ segs,
 extern "C" {
 
 int64_t pc_quant_group_chunk_elems(void) { return pc::kQgChunk; }
+int pc_quant_group_tile_rows(void) { return pc::kQgTileRows; }
 
 int pc_dequantize_grouped(const pc_quant_segment* segments, const int32_t* chunk_segment,
                           int num_segments, int64_t total_chunks, void* stream) {
@@ -263,19 +401,22 @@ int pc_dequantize_grouped(const pc_quant_segment* segments, const int32_t* chunk
 }
 
 int pc_quantize_grouped(const pc_quant_segment* segments, const int32_t* chunk_segment,
-                        int num_segments, int64_t total_chunks, uint32_t* colmax_all,
-                        size_t colmax_bytes, void* stream) {
-  PC_REQUIRE(num_segments >= 0 && total_chunks >= 0 && total_chunks < (1ll << 31), "bad counts");
+                        int num_segments, int64_t total_chunks, const int32_t* tile_segment,
+                        int64_t total_tiles, uint32_t* colmax_all, size_t colmax_bytes,
+                        void* stream) {
+  PC_REQUIRE(num_segments >= 0 && total_chunks >= 0 && total_chunks < (1ll << 31) &&
+             total_tiles >= 0 && total_tiles < (1ll << 31), "bad counts");
   if (num_segments == 0 || total_chunks == 0) return PC_OK;
-  PC_REQUIRE(segments && chunk_segment && colmax_all, "null pointer argument");
+  PC_REQUIRE(segments && chunk_segment && tile_segment && colmax_all, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
   PC_CUDA_CHECK(cudaMemsetAsync(colmax_all, 0, colmax_bytes, st));
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)std::min<int64_t>(total_chunks, (int64_t)sms * 8);
-  pc::qgroup_colmax_kernel<<<grid, pc::kQgThreads, 0, st>>>(segments, chunk_segment,
-                                                           (int)total_chunks);
+  const unsigned tgrid = (unsigned)std::min<int64_t>(total_tiles, (int64_t)sms * 8);
+  pc::qgroup_colmax_kernel<<<tgrid, pc::kQgThreads, 0, st>>>(segments, tile_segment,
+                                                            (int)total_tiles);
   pc::qgroup_quantize_kernel<<<grid, pc::kQgThreads, 0, st>>>(segments, chunk_segment,
                                                              (int)total_chunks);
   pc::count_launch(2);
@@ -311,7 +452,15 @@ int pc_quantize_batched(const float* x, int batch, int rows, int cols, int qdtyp
     dim3 g1((cols + 31) / 32, (rows + pc::kQRowChunk - 1) / pc::kQRowChunk, batch), b1(32, 8);
     pc::quant_colmax_kernel<<<g1, b1, 0, st>>>(x, rows, cols, extract_diagonal, colmax);
     dim3 g2((unsigned)((per + 255) / 256 < 2048 ? (per + 255) / 256 : 2048), batch);
-    if (qdtype == PC_QDTYPE_INT16)
+    const long long trows = (long long)batch * rows;
+    const bool vec = pc::quant_vec_ok(x, q, bucket, cols, qdtype == PC_QDTYPE_INT16 ? 2 : 1, trows);
+    if (vec && qdtype == PC_QDTYPE_INT16)
+      pc::quantize_vec_kernel<int16_t, false><<<pc::quant_vec_grid(cols, trows), 256, 0, st>>>(
+          x, colmax, batch, rows, cols, 32767.f, extract_diagonal, (int16_t*)q, diag, bucket);
+    else if (vec)
+      pc::quantize_vec_kernel<int8_t, false><<<pc::quant_vec_grid(cols, trows), 256, 0, st>>>(
+          x, colmax, batch, rows, cols, 127.f, extract_diagonal, (int8_t*)q, diag, bucket);
+    else if (qdtype == PC_QDTYPE_INT16)
       pc::quant_apply_kernel<int16_t><<<g2, 256, 0, st>>>(x, colmax, rows, cols, 32767.f,
                                                          extract_diagonal, (int16_t*)q, diag, bucket);
     else
@@ -347,6 +496,21 @@ int pc_quantize_from_colmax_batched(const float* x, const uint32_t* colmax, int 
   PC_REQUIRE(qdtype == PC_QDTYPE_INT16 || qdtype == PC_QDTYPE_INT8,
              "Quantized dtype %d not supported.", qdtype);
   const size_t per = (size_t)n * n;
+  {
+    const long long trows = (long long)batch * n;
+    if (pc::quant_vec_ok(x, q, colmax, n, qdtype == PC_QDTYPE_INT16 ? 2 : 1, trows) &&
+        ((uintptr_t)bucket & 3) == 0) {
+      cudaStream_t st = (cudaStream_t)stream;
+      if (qdtype == PC_QDTYPE_INT16)
+        pc::quantize_vec_kernel<int16_t, true><<<pc::quant_vec_grid(n, trows), 256, 0, st>>>(
+            x, colmax, batch, n, n, 32767.f, 1, (int16_t*)q, diag, bucket);
+      else
+        pc::quantize_vec_kernel<int8_t, true><<<pc::quant_vec_grid(n, trows), 256, 0, st>>>(
+            x, colmax, batch, n, n, 127.f, 1, (int8_t*)q, diag, bucket);
+      PC_CUDA_CHECK(cudaGetLastError());
+      return PC_OK;
+    }
+  }
   for (int b0 = 0; b0 < batch; b0 += pc::kMaxGridY) {
     const int nb = batch - b0 < pc::kMaxGridY ? batch - b0 : pc::kMaxGridY;
     dim3 grid((unsigned)((per + 255) / 256 < 2048 ? (per + 255) / 256 : 2048), nb);
@@ -382,6 +546,19 @@ int pc_dequantize_batched(const void* q, const float* diag, const float* bucket,
   PC_REQUIRE(!extract_diagonal || (diag != nullptr && rows == cols),
              "extract_diagonal needs a square matrix and a diagonal");
   const size_t per = (size_t)rows * cols;
+  {
+    const long long trows = (long long)batch * rows;
+    if (pc::quant_vec_ok(x, q, bucket, cols, qdtype == PC_QDTYPE_INT16 ? 2 : 1, trows)) {
+      if (qdtype == PC_QDTYPE_INT16)
+        pc::dequantize_vec_kernel<int16_t><<<pc::quant_vec_grid(cols, trows), 256, 0, st>>>(
+            (const int16_t*)q, diag, bucket, batch, rows, cols, extract_diagonal, x);
+      else
+        pc::dequantize_vec_kernel<int8_t><<<pc::quant_vec_grid(cols, trows), 256, 0, st>>>(
+            (const int8_t*)q, diag, bucket, batch, rows, cols, extract_diagonal, x);
+      PC_CUDA_CHECK(cudaGetLastError());
+      return PC_OK;
+    }
+  }
   for (int b0 = 0; b0 < batch; b0 += pc::kMaxGridY) {
     const int nb = batch - b0 < pc::kMaxGridY ? batch - b0 : pc::kMaxGridY;
     dim3 grid((unsigned)((per + 255) / 256 < 1024 ? (per + 255) / 256 : 1024), nb);

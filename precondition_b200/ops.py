@@ -459,10 +459,13 @@ class QuantGroup:
     self.n = len(items)
     self.keep = items  # the tensors the table points at
     chunk = int(lib.pc_quant_group_chunk_elems())
-    total_cols = sum(int(b.numel()) for _, b, _ in items)
-    self.colmax = torch.zeros(max(total_cols, 1), dtype=torch.int32, device=device)
+    tile_rows = int(lib.pc_quant_group_tile_rows())
+    # every segment's column maxima start 16-byte aligned in the shared scratch
+    total_cols = sum(-(-int(b.numel()) // 4) * 4 for _, b, _ in items)
+    self.colmax = torch.zeros(max(total_cols, 4), dtype=torch.int32, device=device)
     segs = (_lib.QuantSegment * max(self.n, 1))()
     chunk_seg, first, coff = [], 0, 0
+    tile_seg, first_tile = [], 0
     for i, (q, bucket, x) in enumerate(items):
       _require_cuda(q, bucket, x)
       assert q.dtype == torch.int8 and bucket.dtype == torch.float32 and x.dtype == torch.float32
@@ -474,10 +477,16 @@ class QuantGroup:
       sg.q, sg.bucket, sg.x = q.data_ptr(), bucket.data_ptr(), x.data_ptr()
       sg.colmax = self.colmax.data_ptr() + 4 * coff
       sg.rows, sg.cols, sg.first_chunk, sg.nchunks = rows, cols, first, nch
+      sg.first_tile, sg.col_tiles = first_tile, -(-cols // 128)
+      ntiles = -(-rows // tile_rows) * sg.col_tiles
       chunk_seg += [i] * nch
+      tile_seg += [i] * ntiles
       first += nch
-      coff += cols
+      first_tile += ntiles
+      coff += -(-cols // 4) * 4
     self.total_chunks = first
+    self.total_tiles = first_tile
+    self.tile_seg = torch.tensor(tile_seg, dtype=torch.int32).to(device)
     self.segs = torch.frombuffer(bytearray(bytes(segs)), dtype=torch.uint8).to(device)
     self.chunk_seg = torch.tensor(chunk_seg, dtype=torch.int32).to(device)
 
@@ -496,8 +505,9 @@ class QuantGroup:
       return
     with torch.cuda.device(self.device):
       _lib.check(_lib.load().pc_quantize_grouped(
-          _ptr(self.segs), _ptr(self.chunk_seg), self.n, self.total_chunks, _ptr(self.colmax),
-          self.colmax.numel() * 4, ctypes.c_void_p(_stream())))
+          _ptr(self.segs), _ptr(self.chunk_seg), self.n, self.total_chunks, _ptr(self.tile_seg),
+          self.total_tiles, _ptr(self.colmax), self.colmax.numel() * 4,
+          ctypes.c_void_p(_stream())))
     gpu_launches += 2
 
 
