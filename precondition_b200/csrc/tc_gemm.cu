@@ -1494,6 +1494,141 @@ struct PlaneStore {
 };
 
 // ---------------------------------------------------------------------------
+// First initialisation of M0 / M_i0 / H0 (DS:871-874) straight into the plane tiles of the
+// scaled-fp16 engine: one CTA per 128 x 64 plane tile, a thread owns 32 consecutive columns of
+// one row, so every plane row leaves as four 16-byte stores (the strip kernel stores 2 bytes
+// at a time).  The lower triangle of the input is authoritative: tiles above the diagonal read
+// the mirrored tile coalesced and transpose it through shared memory; the two tiles per row
+// block that straddle the diagonal take element-wise max / min indexing.  The last CTA of a
+// matrix publishes err0 and runs the loop-predicate bookkeeping, like root_init_strip_kernel.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void split_fp16s(float v, uint16_t* hi, uint16_t* lo) {
+  const float c = fabsf(v) > 65504.0f ? copysignf(65504.0f, v) : v;  // NaN stays NaN
+  const __half h0 = __float2half_rn(c);
+  *hi = __half_as_ushort(h0);
+  *lo = __half_as_ushort(__float2half_rn((c - __half2float(h0)) * TC_FP16_SCALE));
+}
+
+__global__ void __launch_bounds__(256)
+root_init_tile_kernel(const float* __restrict__ xs, RootCtl* ctl, PlaneStore bufs, int batch, int n,
+                      int strips, RootParams prm, float* __restrict__ scratch) {
+  __shared__ float tr[64][129];
+  __shared__ uint32_t ured[32];
+  __shared__ int is_last;
+  const int b = blockIdx.z, ti = blockIdx.y, tj = blockIdx.x;
+  RootCtl c = ctl[b];
+  if (!c.need_init) return;
+  const int pad = c.pad, p = c.p;
+  const float eps = root_try_eps(c, prm);
+  const int t = threadIdx.x, r = t >> 1, half = t & 1;
+  // |A + eps I|_F^2 from the strip partials: one warp, the same tree in every CTA (a serial
+  // loop over the partials cost 5 us of dependent loads per CTA, 32 waves of CTAs per call)
+  __shared__ float ssum_s;
+  if (t < 32) {
+    float v = 0.f;
+    for (int q = t; q < strips; q += 32) v += scratch[(size_t)b * strips + q];
+    v = warp_sum(v);
+    if (t == 0) ssum_s = v;
+  }
+  __syncthreads();
+  const float norm = sqrtf(ssum_s);
+  const float alpha = -1.0f / (float)p, one_minus_alpha = 1.0f - alpha;
+  const float z = (float)(1 + p) / (2.0f * norm);
+  const float h0 = powf(z, (float)(1.0 / (double)p));  // DS:873
+  float hmul = 1.0f;
+  const float hdiag = bufs.h_init_scale(h0, powf(fmaxf(z * eps, 1e-37f), alpha), &hmul);
+  const float* A = xs + (size_t)b * n * n;
+  const int i = ti * 128 + r, j0 = tj * 64 + half * 32;
+  float a[32];
+  if (tj * 64 + 63 <= ti * 128) {  // whole tile on or below the diagonal: rows as stored
+    const float4* src = reinterpret_cast<const float4*>(A + (size_t)i * n + j0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = __ldg(src + q);
+      a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+    }
+  } else if (tj * 64 >= ti * 128 + 128) {  // whole tile above: the mirrored tile, transposed
+    const int mr = t >> 2, mc = (t & 3) * 32;  // row of the mirrored tile (a column here)
+    const float4* src = reinterpret_cast<const float4*>(A + (size_t)(tj * 64 + mr) * n + ti * 128 + mc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = __ldg(src + q);
+      tr[mr][mc + 4 * q] = v.x; tr[mr][mc + 4 * q + 1] = v.y;
+      tr[mr][mc + 4 * q + 2] = v.z; tr[mr][mc + 4 * q + 3] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a[k] = tr[half * 32 + k][r];
+  } else {  // straddles the diagonal
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int j = j0 + k;
+      a[k] = __ldg(A + (size_t)max(i, j) * n + min(i, j));
+    }
+  }
+  uint32_t emax = 0;
+  uint32_t m_hi[16], m_lo[16], mi_hi[16], mi_lo[16], h_hi[16], h_lo[16];
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) {
+    uint16_t w[2][6];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + k + u;
+      float m0 = 0.f, mi0 = 0.f, h = 0.f;
+      if (i < pad && j < pad) {
+        float av = a[k + u];
+        if (i == j) av += eps;
+        m0 = av * z;  // DS:871
+        const uint32_t ab = absbits(m0 - (i == j ? 1.f : 0.f));
+        emax = ab > emax ? ab : emax;
+        mi0 = mi_from_m(m0, i == j, alpha, one_minus_alpha);
+        h = (i == j) ? hdiag : 0.f;
+      }
+      split_fp16s(m0, &w[u][0], &w[u][1]);
+      split_fp16s(mi0, &w[u][2], &w[u][3]);
+      split_fp16s(h, &w[u][4], &w[u][5]);
+    }
+    const int q = k >> 1;
+    m_hi[q] = w[0][0] | ((uint32_t)w[1][0] << 16);  m_lo[q] = w[0][1] | ((uint32_t)w[1][1] << 16);
+    mi_hi[q] = w[0][2] | ((uint32_t)w[1][2] << 16); mi_lo[q] = w[0][3] | ((uint32_t)w[1][3] << 16);
+    h_hi[q] = w[0][4] | ((uint32_t)w[1][4] << 16);  h_lo[q] = w[0][5] | ((uint32_t)w[1][5] << 16);
+  }
+  auto put = [&](int phys, int plane, const uint32_t (&v)[16]) {
+    uint4* dst = reinterpret_cast<uint4*>(bufs.plane[plane] + bufs.elem(phys, b, i, j0, n));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  };
+  put(0, 0, m_hi); put(0, 1, m_lo);
+  put(2, 0, mi_hi); put(2, 1, mi_lo);
+  put(4, 0, h_hi); put(4, 1, h_lo);
+  emax = block_max_u32(emax, ured);
+  uint32_t* slots = reinterpret_cast<uint32_t*>(scratch + (size_t)batch * strips);
+  if (threadIdx.x == 0) {
+    atomicMax(slots + b, emax);
+    __threadfence();
+    is_last = atomicAdd(slots + batch + b, 1u) == (uint32_t)(gridDim.x * gridDim.y - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t e = atomicMax(slots + b, 0u);  // atomic read of the final maximum
+    if (c.tries == 0) {
+      const float ev = prm.relative_eps ? c.max_ev : 1.0f;
+      c.max_ev = ev;
+      c.ridge = prm.ridge_epsilon * fmaxf(ev, 1e-25f);
+    }
+    c.need_init = 0;
+    c.iter = 0;
+    c.cur = 0;
+    c.err = __uint_as_float(e);  // DS:872
+    c.ratio = 1.0f;
+    c.hmul = hmul;
+    root_after_error_update(c, prm);
+    ctl[b] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1797,8 +1932,17 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
     const int strips = (e->n + 31) / 32;
     root_norm_strip_kernel<<<dim3(strips, e->batch), 256, 0, stream>>>(
         xs, ctl, e->n, strips, prm, first_init_scratch, e->batch);
-    root_init_strip_kernel<PlaneStore><<<dim3(strips, e->batch), 1024, 0, stream>>>(
-        xs, ctl, ps, e->batch, e->n, strips, prm, first_init_scratch);
+    static const bool strip_only = [] {
+      const char* v = getenv("PC_INIT_STRIP");
+      return v && v[0] == '1';
+    }();
+    if (hs->fmt == TC_FMT_FP16S && e->n % 128 == 0 && ((uintptr_t)xs & 15) == 0 &&
+        e->batch <= 65535 && !strip_only)
+      root_init_tile_kernel<<<dim3(e->n / 64, e->n / 128, e->batch), 256, 0, stream>>>(
+          xs, ctl, ps, e->batch, e->n, strips, prm, first_init_scratch);
+    else
+      root_init_strip_kernel<PlaneStore><<<dim3(strips, e->batch), 1024, 0, stream>>>(
+          xs, ctl, ps, e->batch, e->n, strips, prm, first_init_scratch);
     count_launch(2);
   }
   if (do_init) {  // (re)initialise whoever needs it: first iteration, or a retry was reported
