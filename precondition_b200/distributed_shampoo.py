@@ -1353,17 +1353,31 @@ class _Shampoo:
     self.metrics[s].copy_(metrics)
     self._select(bk, roots, metrics)
 
+  def _select_rows(self, new, old, metrics):
+    """old[i] <- new[i] unless metrics row i reports a failed root (DS:2936-2950), for rows of
+    any dtype (fp32 roots, int16 / int8 data, diagonals, bucket sizes): ``pc_select_scatter`` with
+    the identity index."""
+    n = int(new.shape[0])
+    if n == 0:
+      return
+    row_bytes = new[0].numel() * new.element_size()
+    key = (n, row_bytes)
+    cache = self.__dict__.setdefault("_select_idx", {})
+    if key not in cache:
+      ar = torch.arange(n, device=self.device)
+      cache[key] = ((ar * row_bytes).to(torch.int64), (ar * metrics.shape[1]).to(torch.int64),
+                    ar.to(torch.int32))
+    src_off, met_off, dst_idx = cache[key]
+    ops.select_scatter(new.contiguous(), src_off, metrics.contiguous(), met_off, dst_idx,
+                       self.inverse_failure_threshold, old, row_bytes, None)
+
   def _select(self, bk, roots, metrics):
     """Failure fallback of DS:2936-2950 (quantised: DS:3183-3208) for a whole bucket."""
     s = bk.size
     if self.quantize_second_moment:
       q, d, b = ops.quantize(roots, self.qdt_second, True)
-      err = metrics[:, 0]
-      bad = torch.isnan(err) | (err >= self.inverse_failure_threshold)
-      oq, od, ob = bk.qprecs
-      oq.copy_(torch.where(bad[:, None, None], oq, q))
-      od.copy_(torch.where(bad[:, None], od, d))
-      ob.copy_(torch.where(bad[:, None], ob, b))
+      for new, old in zip((q, d, b), bk.qprecs):
+        self._select_rows(new, old, metrics)
       return
     lib = _lib.load()
     _lib.check(lib.pc_select_preconditioners(
@@ -1436,9 +1450,7 @@ class _Shampoo:
             bk.stats, bk.exps, world, rank, self.process_group, pads=pads,
             root_fn=lambda x, p, pd, **k2: ops.low_rank_root_batched(x, p, r, pd, **k2), **kw)
       self.metrics[s].copy_(metrics)
-      err = metrics[:, 0]
-      bad = torch.isnan(err) | (err >= self.inverse_failure_threshold)
-      bk.packed.copy_(torch.where(bad[:, None, None], bk.packed, new))
+      self._select_rows(new, bk.packed, metrics)
       ops.low_rank_to_dense(bk.packed, abs(r), out=bk.precs)
 
 
