@@ -179,6 +179,8 @@ typedef struct {
   int32_t m, n, k;
   float alpha, beta;
   int32_t reserved;
+  const float* beta_dev; /* optional DEVICE scalar: if not NULL it replaces `beta` (a weight that
+                          * only exists on the device, e.g. the `const` of a packed sketch) */
 } pc_gemm_desc;
 
 /* descs: DEVICE array of `count` descriptors; max_m/max_n bound the tile grid. */
@@ -339,6 +341,11 @@ int pc_pinv_pth_root_eigh_batched(const float* xs, const int32_t* ps, int batch,
  * low-rank blocks go through the same grouped GEMM as the full ones.
  *   packed [batch, d, rank+2] f32 -> dense [batch, d, d] f32 */
 size_t pc_low_rank_to_dense_workspace_bytes(int batch, int d, int rank);
+/* The same operator in factored form, for applying it as  g -> c g + (g V) W^T  (two thin
+ * products, DS:1690-1705 as written) instead of through its d x d matrix:
+ *   w [batch, d, rank] = V diag(lambda^- - c)  (zero if has_zeros),  c [batch] (1 if has_zeros). */
+int pc_low_rank_factors(const float* packed, int batch, int d, int rank, float* w, float* c,
+                        void* stream);
 int pc_low_rank_to_dense(const float* packed, int batch, int d, int rank, float* dense,
                          void* workspace, size_t workspace_bytes, void* stream);
 

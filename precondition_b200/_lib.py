@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = (
     "pc_quantize_batched", "pc_dequantize_batched",
     "pc_graft_momentum_workspace_bytes", "pc_graft_momentum",
     "pc_fd_options_default", "pc_fd_update_workspace_bytes", "pc_fd_update_batched",
-    "pc_low_rank_to_dense_workspace_bytes", "pc_low_rank_to_dense",
+    "pc_low_rank_to_dense_workspace_bytes", "pc_low_rank_to_dense", "pc_low_rank_factors",
     "pc_grouped_gemm_tc_workspace_bytes", "pc_grouped_gemm_tc",
     "pc_low_rank_root_workspace_bytes", "pc_low_rank_root_batched",
     "pc_inverse_pth_root_eigh_batched",
@@ -81,7 +81,7 @@ class GemmDesc(ctypes.Structure):
               ("b_kinner", ctypes.c_int32), ("c_iinner", ctypes.c_int32),
               ("m", ctypes.c_int32), ("n", ctypes.c_int32), ("k", ctypes.c_int32),
               ("alpha", ctypes.c_float), ("beta", ctypes.c_float),
-              ("reserved", ctypes.c_int32)]
+              ("reserved", ctypes.c_int32), ("beta_dev", ctypes.c_void_p)]
 
 
 class GemmQuant(ctypes.Structure):
@@ -241,6 +241,8 @@ def load() -> ctypes.CDLL:
   lib.pc_low_rank_to_dense_workspace_bytes.restype = sz
   lib.pc_low_rank_to_dense.argtypes = [vp, i32, i32, i32, vp, vp, sz, vp]
   lib.pc_low_rank_to_dense.restype = i32
+  lib.pc_low_rank_factors.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+  lib.pc_low_rank_factors.restype = i32
   lib.pc_grouped_gemm_tc_workspace_bytes.argtypes = [vp, i32]
   lib.pc_grouped_gemm_tc_workspace_bytes.restype = sz
   lib.pc_grouped_gemm_tc.argtypes = [vp, i32, vp, sz, i32, vp]

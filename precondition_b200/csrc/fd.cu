@@ -1229,11 +1229,12 @@ int run_fd_update(const float* new_grad, const float* prev, const int32_t* ps,
 // identity when has_zeros is set (the reference bypasses the block then).
 // ---------------------------------------------------------------------------
 __global__ void fd_lowrank_scale_kernel(const float* __restrict__ packed, int d, int r,
-                                        float* __restrict__ ws) {
+                                        float* __restrict__ ws, float* __restrict__ c_out) {
   const int b = blockIdx.y, pd = r + 2;
   const float* P = packed + (size_t)b * d * pd;
   const float c = P[r + 1];
   const bool skip = P[(size_t)(d - 1) * pd + r] != 0.f;
+  if (c_out && blockIdx.x == 0 && threadIdx.x == 0) c_out[b] = skip ? 1.0f : c;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)d * r;
        e += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(e / r), j = (int)(e - (size_t)i * r);
@@ -1284,7 +1285,7 @@ int run_low_rank_to_dense(const float* packed, int batch, int d, int rank, float
   }
   float* ws = reinterpret_cast<float*>(align_up((size_t)workspace, 256));
   const unsigned grid = (unsigned)std::min<size_t>(((size_t)d * rank + 255) / 256, 512);
-  fd_lowrank_scale_kernel<<<dim3(grid, batch), 256, 0, stream>>>(packed, d, rank, ws);
+  fd_lowrank_scale_kernel<<<dim3(grid, batch), 256, 0, stream>>>(packed, d, rank, ws, nullptr);
   if (fd_use_tc(d)) {
     std::vector<pc_gemm_desc> descs;
     fd_dense_descs(ws, packed, dense, batch, d, rank, &descs);
@@ -1606,6 +1607,19 @@ extern "C" {
 size_t pc_low_rank_to_dense_workspace_bytes(int batch, int d, int rank) {
   if (batch <= 0 || d <= 0 || rank <= 0) return 0;
   return pc::low_rank_to_dense_bytes(batch, d, rank) + 512;
+}
+
+int pc_low_rank_factors(const float* packed, int batch, int d, int rank, float* w, float* c,
+                        void* stream) {
+  PC_REQUIRE(batch >= 0 && d > 0 && rank > 0 && rank + 2 < d, "bad low-rank sizes");
+  if (batch == 0) return PC_OK;
+  PC_REQUIRE(packed && w && c, "null pointer argument");
+  const unsigned grid = (unsigned)std::min<size_t>(((size_t)d * rank + 255) / 256, 512);
+  pc::fd_lowrank_scale_kernel<<<dim3(grid, batch), 256, 0, (cudaStream_t)stream>>>(packed, d, rank,
+                                                                                  w, c);
+  pc::count_launch(1);
+  PC_CUDA_CHECK(cudaGetLastError());
+  return PC_OK;
 }
 
 int pc_low_rank_to_dense(const float* packed, int batch, int d, int rank, float* dense,

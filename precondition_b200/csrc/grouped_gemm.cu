@@ -16,6 +16,7 @@ grouped_gemm_simt_kernel(const pc_gemm_desc* __restrict__ descs) {
   const OperandView A{d.a, d.a_sio, d.a_si, d.a_sko, d.a_ski, d.a_iinner > 0 ? d.a_iinner : d.m,
                       d.a_kinner, d.m, d.k};
   const OperandView B{d.b, 0, d.b_sj, d.b_sko, d.b_ski, d.n > 0 ? d.n : 1, d.b_kinner, d.n, d.k};
+  const float beta = d.beta_dev ? __ldg(d.beta_dev) : d.beta;
   simt_gemm_tile(d.k, tile_m, tile_n, A, B, A.k_fast(), B.k_fast(), sm,
                  [&](int i, int j0, const float* acc) {
                    if (i >= d.m) return;
@@ -26,7 +27,7 @@ grouped_gemm_simt_kernel(const pc_gemm_desc* __restrict__ descs) {
                      const int j = j0 + q;
                      if (j >= d.n) continue;
                      float v = d.alpha * acc[q];
-                     if (d.c_in) v = fmaf(d.beta, d.c_in[row + j], v);
+                     if (d.c_in) v = fmaf(beta, d.c_in[row + j], v);
                      d.c[row + j] = v;
                    }
                  });
@@ -71,13 +72,14 @@ __global__ void splitk_reduce_kernel(const pc_gemm_desc* __restrict__ descs, int
                                      int max_n, const float* __restrict__ part) {
   const pc_gemm_desc d = descs[blockIdx.y];
   const float* p0 = part + (size_t)blockIdx.y * splits * max_m * max_n;
+  const float beta = d.beta_dev ? __ldg(d.beta_dev) : d.beta;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d.m * d.n; e += gridDim.x * blockDim.x) {
     const int i = e / d.n, j = e - i * d.n;
     float v = 0.f;
     for (int sp = 0; sp < splits; ++sp) v += p0[((size_t)sp * max_m + i) * max_n + j];
     const int io = i / d.c_iinner, ii = i - io * d.c_iinner;
     const int64_t row = io * d.c_sio + ii * d.c_sii;
-    if (d.c_in) v = fmaf(d.beta, d.c_in[row + j], v);
+    if (d.c_in) v = fmaf(beta, d.c_in[row + j], v);
     d.c[row + j] = v;
   }
 }

@@ -2090,6 +2090,7 @@ struct TcGgItem {
   int a_tile0, b_tile0;  // first packed tile of each operand (b_tile0 == a_tile0 if symmetric)
   int symmetric;
   float alpha, beta;
+  const float* beta_dev;  // device scalar replacing beta (pc_gemm_desc.beta_dev)
   // optional fused (de)quantisation of a square symmetric C (QuantizedValue, QU:49-113):
   // C_in = q_in * bucket_in[col] + diag_in on the diagonal; colmax receives the bit
   // patterns of max |off-diagonal| per column of the RESULT for the requantisation
@@ -2340,6 +2341,7 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       mbar_wait(ofull_bar(o), (tile >> 1) & 1);
       tcgen05_fence_after();
       const float alpha = it.alpha;
+      const float beta = it.beta_dev ? __ldg(it.beta_dev) : it.beta;
       const int row = wk.tm * TC_BM + q * 32 + lane;
       const int io = row / it.c_iinner, ii = row - io * it.c_iinner;
       const int64_t rowoff = io * it.c_sio + ii * it.c_sii;
@@ -2391,7 +2393,7 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           for (int i = 0; i < 32; ++i) {
             float o = oldv[i] * __ldg(it.bucket_in + col0 + i);
             if (col0 + i == row) o += __ldg(it.diag_in + row);
-            x[i] = fmaf(it.beta, o, alpha * __uint_as_float(r[i]));
+            x[i] = fmaf(beta, o, alpha * __uint_as_float(r[i]));
           }
         } else {
           const float* cin = it.c_in ? it.c_in + rowoff + col0 : nullptr;
@@ -2399,10 +2401,10 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           for (int i = 0; i < 32; i += 4) {
             float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
             if (cin) old = *reinterpret_cast<const float4*>(cin + i);
-            x[i] = fmaf(it.beta, old.x, alpha * __uint_as_float(r[i]));
-            x[i + 1] = fmaf(it.beta, old.y, alpha * __uint_as_float(r[i + 1]));
-            x[i + 2] = fmaf(it.beta, old.z, alpha * __uint_as_float(r[i + 2]));
-            x[i + 3] = fmaf(it.beta, old.w, alpha * __uint_as_float(r[i + 3]));
+            x[i] = fmaf(beta, old.x, alpha * __uint_as_float(r[i]));
+            x[i + 1] = fmaf(beta, old.y, alpha * __uint_as_float(r[i + 1]));
+            x[i + 2] = fmaf(beta, old.z, alpha * __uint_as_float(r[i + 2]));
+            x[i + 3] = fmaf(beta, old.w, alpha * __uint_as_float(r[i + 3]));
           }
         }
         if (it.colmax) {
@@ -2479,7 +2481,7 @@ static void tc_gg_plan(const pc_gemm_desc* descs, const pc_gemm_quant* quant, in
     it.a = d.a; it.b = d.b; it.c_in = d.c_in; it.c = d.c;
     it.c_sio = d.c_sio; it.c_sii = d.c_sii; it.c_iinner = d.c_iinner > 0 ? d.c_iinner : d.m;
     it.m = d.m; it.n = d.n; it.k = d.k; it.kblocks = (d.k + TC_BK - 1) / TC_BK;
-    it.alpha = d.alpha; it.beta = d.beta;
+    it.alpha = d.alpha; it.beta = d.beta; it.beta_dev = d.beta_dev;
     it.symmetric = tc_gg_symmetric(d) ? 1 : 0;
     TcGgOperand oa{};
     oa.base = d.a; oa.s_io = d.a_sio; oa.s_i = d.a_si; oa.s_ko = d.a_sko; oa.s_ki = d.a_ski;

@@ -28,6 +28,7 @@ from __future__ import annotations
 
 import ctypes
 import enum
+import os
 import itertools
 from typing import Any, Callable, List, NamedTuple, Optional, Sequence, Tuple
 
@@ -692,6 +693,10 @@ class _Shampoo:
         # packed form applies (pc_low_rank_to_dense) and is what the apply GEMMs read
         bk.packed = torch.zeros((bk.count, s, bk.pdim), dtype=torch.float32, device=dev)
         bk.precs = torch.zeros((bk.count, s, s), dtype=torch.float32, device=dev)
+        # the same operator in factored form, c g + (g V) W^T (rank-2 blocks apply it that way)
+        bk.loww = torch.zeros((bk.count, s, bk.pdim - 2), dtype=torch.float32, device=dev)
+        bk.lowc = torch.zeros((bk.count,), dtype=torch.float32, device=dev)
+        bk.needs_dense = False
       else:
         bk.precs = eye.repeat(bk.count, 1, 1).contiguous()
       bk.exps = torch.tensor(bk.exponents, dtype=torch.int32, device=dev)
@@ -801,8 +806,8 @@ class _Shampoo:
           x.copy_(y)
     r = abs(self.compression_rank)
     for bk in self.buckets.values():
-      if bk.compressed:  # the dense operator is derived from the packed sketch
-        ops.low_rank_to_dense(bk.packed, r, out=bk.precs)
+      if bk.compressed:  # the applied operator is derived from the packed sketch
+        self._refresh_low_rank(bk)
     return ShampooState(int(state.count), _tree_unflatten(self.treedef, self._own_leaves))
 
   def _adopt(self, state):
@@ -831,6 +836,11 @@ class _Shampoo:
     # gradient buffer, so each block is staged through contiguous copies (in: before the
     # statistics, out: after the last mode product); DS:1676-1708 loops over any rank
     self._staged = []
+    self._lowrank_tmp = []  # intermediates of the factored low-rank application (kept alive)
+    self._lowrank_apply = os.environ.get("PC_LOWRANK_APPLY", "1") != "0"
+    for bk in self.buckets.values():
+      if getattr(bk, "compressed", False):
+        bk.needs_dense = False
     w1 = float(self.beta2)
     w2 = float(self.beta2 if self.beta2 == 1.0 else 1.0 - self.beta2)  # DS:2635-2636
     f32 = 4
@@ -906,6 +916,16 @@ class _Shampoo:
         t_ptrs = [t10 + f32 * (plan.offset + tmp_off), t20 + f32 * (plan.offset + tmp_off)]
         while len(apply_descs) < rank:
           apply_descs.append([])
+        comp_axes = [refs[a] is not None and self.buckets[refs[a][0]].compressed
+                     for a in range(rank)]
+        if rank == 2 and any(comp_axes) and self._lowrank_apply:
+          self._lowrank_descs(apply_descs, sizes, refs, comp_axes, gbase, pg0 + f32 * base_elem,
+                              strides[0])
+          tmp_off += int(np.prod(sizes))
+          continue
+        for a in range(rank):
+          if comp_axes[a]:
+            self.buckets[refs[a][0]].needs_dense = True
         for j in range(rank):
           d0 = cur_sizes[0]
           rest_sizes, rest_strides = cur_sizes[1:], cur_strides[1:]
@@ -1006,6 +1026,95 @@ class _Shampoo:
       self._apply_tc.append(tc)
       self._apply_simt.append(simt)
 
+
+  def _lowrank_descs(self, apply_descs, sizes, refs, comp_axes, x_ptr, z_ptr, ld):
+    """Application descriptors of one rank-2 block [d0, d1] (row stride `ld` in the gradient and
+    in the output buffer) with at least one packed low-rank preconditioner (DS:1690-1705):
+      axis 0:  Y = P0 X = c0 X + W0 (V0^T X)        axis 1:  Z = Y P1 = c1 Y + (Y V1) W1^T
+    two thin products per compressed axis (the `c` term rides on the second one as C_in with a
+    device-scalar weight), one dense product per full axis, no roll.  Steps 0-3 of the launch
+    lists; Y keeps the gradient's row stride so that C_in and C are addressed alike."""
+    D = _lib.GemmDesc
+    f32 = 4
+    d0, d1 = sizes
+    dev = self.device
+    while len(apply_descs) < 4:
+      apply_descs.append([])
+    y = torch.empty((d0 - 1) * ld + d1, dtype=torch.float32, device=dev)
+    self._lowrank_tmp.append(y)
+    y_ptr = y.data_ptr()
+
+    def prec(a):
+      if refs[a] is None:
+        n = sizes[a]
+        return self._identity(n).data_ptr(), n
+      S, bi = refs[a]
+      return self.buckets[S].precs.data_ptr() + f32 * bi * S * S, S
+
+    def factors(a):
+      S, bi = refs[a]
+      bk = self.buckets[S]
+      pd = bk.pdim
+      return (bk.packed.data_ptr() + f32 * bi * S * pd, pd,
+              bk.loww.data_ptr() + f32 * bi * S * (pd - 2), pd - 2,
+              bk.lowc.data_ptr() + f32 * bi)
+
+    # ---- axis 0: Y = P0 X ----
+    if comp_axes[0]:
+      v, pd, w, r, c = factors(0)
+      t = torch.empty(r * d1, dtype=torch.float32, device=dev)
+      self._lowrank_tmp.append(t)
+      g = D()  # T0[q, j] = sum_k V[k, q] X[k, j]
+      g.a, g.b, g.c, g.c_in = v, x_ptr, t.data_ptr(), None
+      g.a_iinner, g.a_sio, g.a_si, g.a_kinner, g.a_sko, g.a_ski = r, 0, 1, d0, 0, pd
+      g.b_sj, g.b_kinner, g.b_sko, g.b_ski = 1, d0, 0, ld
+      g.c_iinner, g.c_sio, g.c_sii = r, 0, d1
+      g.m, g.n, g.k, g.alpha, g.beta = r, d1, d0, 1.0, 0.0
+      apply_descs[0].append(g)
+      g = D()  # Y = W T0 + c X
+      g.a, g.b, g.c, g.c_in, g.beta_dev = w, t.data_ptr(), y_ptr, x_ptr, c
+      g.a_iinner, g.a_sio, g.a_si, g.a_kinner, g.a_sko, g.a_ski = d0, 0, r, r, 0, 1
+      g.b_sj, g.b_kinner, g.b_sko, g.b_ski = 1, r, 0, d1
+      g.c_iinner, g.c_sio, g.c_sii = d0, 0, ld
+      g.m, g.n, g.k, g.alpha, g.beta = d0, d1, r, 1.0, 1.0
+      apply_descs[1].append(g)
+    else:
+      p, S = prec(0)
+      g = D()  # Y[i, j] = sum_k P0[i, k] X[k, j]
+      g.a, g.b, g.c, g.c_in = p, x_ptr, y_ptr, None
+      g.a_iinner, g.a_sio, g.a_si, g.a_kinner, g.a_sko, g.a_ski = d0, 0, S, d0, 0, 1
+      g.b_sj, g.b_kinner, g.b_sko, g.b_ski = 1, d0, 0, ld
+      g.c_iinner, g.c_sio, g.c_sii = d0, 0, ld
+      g.m, g.n, g.k, g.alpha, g.beta = d0, d1, d0, 1.0, 0.0
+      apply_descs[1].append(g)
+    # ---- axis 1: Z = Y P1 ----
+    if comp_axes[1]:
+      v, pd, w, r, c = factors(1)
+      t = torch.empty(d0 * r, dtype=torch.float32, device=dev)
+      self._lowrank_tmp.append(t)
+      g = D()  # T1[i, q] = sum_k Y[i, k] V[k, q]
+      g.a, g.b, g.c, g.c_in = y_ptr, v, t.data_ptr(), None
+      g.a_iinner, g.a_sio, g.a_si, g.a_kinner, g.a_sko, g.a_ski = d0, 0, ld, d1, 0, 1
+      g.b_sj, g.b_kinner, g.b_sko, g.b_ski = 1, d1, 0, pd
+      g.c_iinner, g.c_sio, g.c_sii = d0, 0, r
+      g.m, g.n, g.k, g.alpha, g.beta = d0, r, d1, 1.0, 0.0
+      apply_descs[2].append(g)
+      g = D()  # Z = T1 W^T + c Y
+      g.a, g.b, g.c, g.c_in, g.beta_dev = t.data_ptr(), w, z_ptr, y_ptr, c
+      g.a_iinner, g.a_sio, g.a_si, g.a_kinner, g.a_sko, g.a_ski = d0, 0, r, r, 0, 1
+      g.b_sj, g.b_kinner, g.b_sko, g.b_ski = r, r, 0, 1
+      g.c_iinner, g.c_sio, g.c_sii = d0, 0, ld
+      g.m, g.n, g.k, g.alpha, g.beta = d0, d1, r, 1.0, 1.0
+      apply_descs[3].append(g)
+    else:
+      p, S = prec(1)
+      g = D()  # Z[i, j] = sum_k Y[i, k] P1[j, k]  (P1 symmetric)
+      g.a, g.b, g.c, g.c_in = y_ptr, p, z_ptr, None
+      g.a_iinner, g.a_sio, g.a_si, g.a_kinner, g.a_sko, g.a_ski = d0, 0, ld, d1, 0, 1
+      g.b_sj, g.b_kinner, g.b_sko, g.b_ski = S, d1, 0, 1
+      g.c_iinner, g.c_sio, g.c_sii = d0, 0, ld
+      g.m, g.n, g.k, g.alpha, g.beta = d0, d1, d1, 1.0, 0.0
+      apply_descs[3].append(g)
 
   def _identity(self, n):
     cache = self.__dict__.setdefault("_eyes", {})
@@ -1353,6 +1462,15 @@ class _Shampoo:
     self.metrics[s].copy_(metrics)
     self._select(bk, roots, metrics)
 
+  def _refresh_low_rank(self, bk):
+    """Operator of a packed low-rank preconditioner (DS:1690-1705) after the sketch changed: its
+    factors (c, W = V diag(lambda^- - c)) for the two-thin-products application, and the dense
+    d x d form only where a block still applies it that way (rank != 2)."""
+    r = abs(self.compression_rank)
+    ops.low_rank_factors(bk.packed, r, bk.loww, bk.lowc)
+    if bk.needs_dense:
+      ops.low_rank_to_dense(bk.packed, r, out=bk.precs)
+
   def _select_rows(self, new, old, metrics):
     """old[i] <- new[i] unless metrics row i reports a failed root (DS:2936-2950), for rows of
     any dtype (fp32 roots, int16 / int8 data, diagonals, bucket sizes): ``pc_select_scatter`` with
@@ -1428,7 +1546,7 @@ class _Shampoo:
     for bk in comp:
       bk.packed.copy_(new[o:o + bk.count, :bk.size])
       o += bk.count
-      ops.low_rank_to_dense(bk.packed, r, out=bk.precs)
+      self._refresh_low_rank(bk)
       self.metrics[bk.size].zero_()  # DS:1263-1264: FD reports zero error
 
   def _low_rank_update(self, world, rank):
@@ -1451,7 +1569,7 @@ class _Shampoo:
             root_fn=lambda x, p, pd, **k2: ops.low_rank_root_batched(x, p, r, pd, **k2), **kw)
       self.metrics[s].copy_(metrics)
       self._select_rows(new, bk.packed, metrics)
-      ops.low_rank_to_dense(bk.packed, abs(r), out=bk.precs)
+      self._refresh_low_rank(bk)
 
 
   def _apply_preconditioners(self):

@@ -338,6 +338,21 @@ class TearfreeTail:
     gpu_launches += 3 if opt.graft_type != _lib.PC_TF_GRAFT_NONE else 1
 
 
+def low_rank_factors(packed: torch.Tensor, rank: int, w: torch.Tensor, c: torch.Tensor):
+  """Factors of the operator of packed low-rank preconditioners [b, d, rank + 2] for the
+  application g -> c g + (g V) W^T (DS:1690-1705): w [b, d, rank] = V diag(lambda^- - c),
+  c [b] (identity -- w = 0, c = 1 -- when has_zeros)."""
+  global gpu_launches
+  lib = _lib.load()
+  _require_cuda(packed, w, c)
+  b, d = packed.shape[0], packed.shape[1]
+  assert packed.shape[2] == rank + 2 and tuple(w.shape) == (b, d, rank) and c.numel() == b
+  with torch.cuda.device(packed.device):
+    _lib.check(lib.pc_low_rank_factors(_ptr(packed), b, d, rank, _ptr(w), _ptr(c),
+                                       ctypes.c_void_p(_stream())))
+  gpu_launches += 1
+
+
 def low_rank_to_dense(packed: torch.Tensor, rank: int,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
   """Dense operator of packed low-rank preconditioners [b, d, rank+2] -> [b, d, d]

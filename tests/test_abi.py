@@ -50,14 +50,16 @@ def test_struct_layouts_match_header(tmp_path):
   src = tmp_path / "sz.c"
   src.write_text(
       '#include <stdio.h>\n#include <stddef.h>\n#include "precond_b200.h"\n'
-      'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pc_root_options),'
+      'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pc_root_options),'
       'sizeof(pc_gemm_desc), sizeof(pc_graft_options), offsetof(pc_gemm_desc, m),'
       'offsetof(pc_gemm_desc, alpha), offsetof(pc_graft_options, run_shampoo),'
       'sizeof(pc_fd_options), offsetof(pc_fd_options, full_eigh_max_dim),'
       'sizeof(pc_graft_segment), offsetof(pc_graft_segment, has_precond),'
       'sizeof(pc_ipc_handle), sizeof(pc_peer_group), offsetof(pc_peer_group, flags),'
       'sizeof(pc_tearfree_segment), offsetof(pc_tearfree_segment, first_chunk),'
-      'sizeof(pc_tearfree_options), offsetof(pc_tearfree_options, scale));return 0;}\n')
+      'sizeof(pc_tearfree_options), offsetof(pc_tearfree_options, scale),'
+      'offsetof(pc_gemm_desc, beta_dev), sizeof(pc_quant_segment),'
+      'offsetof(pc_quant_segment, first_tile));return 0;}\n')
   exe = tmp_path / "sz"
   subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
                  check=True)
@@ -70,7 +72,9 @@ def test_struct_layouts_match_header(tmp_path):
           ctypes.sizeof(_lib.GraftSegment), _lib.GraftSegment.has_precond.offset,
           ctypes.sizeof(_lib.IpcHandle), ctypes.sizeof(_lib.PeerGroup), _lib.PeerGroup.flags.offset,
           ctypes.sizeof(_lib.TearfreeSegment), _lib.TearfreeSegment.first_chunk.offset,
-          ctypes.sizeof(_lib.TearfreeOptions), _lib.TearfreeOptions.scale.offset]
+          ctypes.sizeof(_lib.TearfreeOptions), _lib.TearfreeOptions.scale.offset,
+          _lib.GemmDesc.beta_dev.offset, ctypes.sizeof(_lib.QuantSegment),
+          _lib.QuantSegment.first_tile.offset]
   assert got == want
 
 
