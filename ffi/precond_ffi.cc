@@ -126,6 +126,22 @@ ffi::Error LowRankToDenseImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> packed,
                                      workspace->typed_data(), workspace->element_count(), stream));
 }
 
+// ---- the same operator in factored form (c, W = V diag(lambda^- - c)) -----------------------
+ffi::Error LowRankFactorsImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> packed,
+                              ffi::ResultBuffer<ffi::F32> w, ffi::ResultBuffer<ffi::F32> c) {
+  return Status(pc_low_rank_factors(packed.typed_data(), Dim(packed, 0), Dim(packed, 1),
+                                    Dim(packed, 2) - 2, w->typed_data(), c->typed_data(), stream));
+}
+
+// ---- tearfree _pth_inv_root (TF/shampoo.py:440-448) -----------------------------------------
+ffi::Error PinvRootEighImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> xs, ffi::Buffer<ffi::S32> ps,
+                            float rel_cutoff, ffi::ResultBuffer<ffi::F32> roots,
+                            ffi::ResultBuffer<ffi::U8> workspace) {
+  return Status(pc_pinv_pth_root_eigh_batched(
+      xs.typed_data(), ps.typed_data(), Dim(xs, 0), Dim(xs, 1), rel_cutoff, roots->typed_data(),
+      workspace->typed_data(), workspace->element_count(), stream));
+}
+
 // ---- _select_preconditioner (DS:2936-2950) ---------------------------------------------------
 // `old` is aliased to the result by the caller (input_output_aliases={2: 0}); rows whose root
 // failed keep it.
@@ -262,6 +278,10 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(PcFdUpdate, FdUpdateImpl,
         .Attr<int32_t>("input_is_gram").Ret<F32>().Ret<F32>().Ret<U8>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(PcLowRankToDense, LowRankToDenseImpl,
     PC_STREAM.Arg<F32>().Ret<F32>().Ret<U8>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(PcLowRankFactors, LowRankFactorsImpl,
+    PC_STREAM.Arg<F32>().Ret<F32>().Ret<F32>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(PcPinvRootEigh, PinvRootEighImpl,
+    PC_STREAM.Arg<F32>().Arg<S32>().Attr<float>("rel_cutoff").Ret<F32>().Ret<U8>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(PcSelectPreconditioners, SelectImpl,
     PC_STREAM.Arg<F32>().Arg<F32>().Arg<F32>().Attr<float>("threshold").Ret<F32>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(PcQuantizeInt16, (QuantizeImpl<S16, PC_QDTYPE_INT16>),

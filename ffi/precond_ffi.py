@@ -22,6 +22,8 @@ _core.pc_inverse_pth_root_workspace_bytes.argtypes = [ctypes.c_int] * 3
 for _name, _sym in (("pc_inverse_root", "PcInverseRoot"), ("pc_inverse_root_eigh", "PcInverseRootEigh"),
                     ("pc_low_rank_root", "PcLowRankRoot"), ("pc_power_iteration", "PcPowerIteration"),
                     ("pc_fd_update", "PcFdUpdate"), ("pc_low_rank_to_dense", "PcLowRankToDense"),
+                    ("pc_low_rank_factors", "PcLowRankFactors"),
+                    ("pc_pinv_pth_root_eigh", "PcPinvRootEigh"),
                     ("pc_select_preconditioners", "PcSelectPreconditioners"),
                     ("pc_quantize_int16", "PcQuantizeInt16"), ("pc_quantize_int8", "PcQuantizeInt8"),
                     ("pc_dequantize_int16", "PcDequantizeInt16"),
