@@ -13,8 +13,10 @@ from precondition_b200 import ops
 def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
   if not isinstance(t, torch.Tensor) or not t.is_cuda:
     raise RuntimeError(f"tearfree: {what} must be CUDA tensors (no CPU fallback)")
-  if t.dtype != torch.float32:
-    raise TypeError(f"tearfree: {what} must be float32, got {t.dtype}")
+  if not t.is_floating_point():
+    raise TypeError(f"tearfree: {what} must be floating point, got {t.dtype}")
+  if t.dtype != torch.float32:  # half-precision leaves are widened for the kernel
+    t = t.to(torch.float32)
   return t if t.is_contiguous() else t.contiguous()
 
 
@@ -34,6 +36,7 @@ class Tail:
     updated in place."""
     if not grads:
       return []
+    dtypes = [g.dtype for g in grads]
     grads = [_f32c(g, "updates") for g in grads]
     if weight_decay > 0.0:
       if params is None or any(p is None for p in params):
@@ -62,4 +65,4 @@ class Tail:
     opt.scale = scale
     lst.run(grads, params, preconds, accs if graft_type == _lib.PC_TF_GRAFT_RMSPROP else None,
             velocities if momentum_decay != 0.0 else None, outs, opt)
-    return outs
+    return [o if dt == torch.float32 else o.to(dt) for o, dt in zip(outs, dtypes)]

@@ -22,6 +22,11 @@ class GraftingType(enum.Enum):
   ADAFACTOR = 'adafactor'
 
 
+def _zeros_f32(p: torch.Tensor) -> torch.Tensor:
+  """State is fp32 and contiguous whatever the parameter's dtype / memory format."""
+  return torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+
+
 @dataclasses.dataclass
 class Options:
   """Grafting configuration (TF/grafting.py:41-86); same fields and defaults."""
@@ -97,7 +102,7 @@ def _masked(node) -> bool:
 def norm_init(options: Options, params):
   """State of the first-order optimizer whose norm is grafted."""
   if options.grafting_type == GraftingType.RMSPROP:
-    return RMSPropAccumulator(acc=_tree.tree_map(torch.zeros_like, params))
+    return RMSPropAccumulator(acc=_tree.tree_map(_zeros_f32, params))
   return praxis_shim.EmptyState()
 
 

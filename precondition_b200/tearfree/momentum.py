@@ -11,6 +11,11 @@ from precondition_b200.tearfree import _tree
 from precondition_b200.tearfree import praxis_shim
 
 
+def _zeros_f32(p: torch.Tensor) -> torch.Tensor:
+  """State is fp32 and contiguous whatever the parameter's dtype / memory format."""
+  return torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+
+
 @dataclasses.dataclass
 class Options:
   """Momentum (and weight decay) options, TF/momentum.py:26-77:
@@ -48,7 +53,7 @@ def init_state(options: Options, params):
   out = []
   for kind in state_layout(options):
     if kind == "trace":
-      out.append(praxis_shim.TraceState(trace=_tree.tree_map(torch.zeros_like, params)))
+      out.append(praxis_shim.TraceState(trace=_tree.tree_map(_zeros_f32, params)))
     else:
       out.append(praxis_shim.EmptyState())
   return tuple(out)

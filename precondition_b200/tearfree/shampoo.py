@@ -280,8 +280,8 @@ class _Engine:
     def load(leaf, u):
       if not isinstance(u, torch.Tensor) or not u.is_cuda:
         raise RuntimeError("tearfree shampoo needs CUDA tensors: there is no CPU fallback")
-      if u.dtype != torch.float32:
-        raise TypeError(f"tearfree shampoo: updates must be float32, got {u.dtype}")
+      if not u.is_floating_point():
+        raise TypeError(f"tearfree shampoo: updates must be floating point, got {u.dtype}")
       assert list(u.shape) == leaf.meta.param_shape, (u.shape, leaf.meta.param_shape)
       shape, perm = _split_shape(leaf.meta)
       leaf.xb.view([shape[p] for p in perm]).copy_(u.reshape(shape).permute(perm))

@@ -222,8 +222,8 @@ class _Engine:
     def load(leaf, u):
       if not isinstance(u, torch.Tensor) or not u.is_cuda:
         raise RuntimeError("tearfree sketchy needs CUDA tensors: there is no CPU fallback")
-      if u.dtype != torch.float32:
-        raise TypeError(f"tearfree sketchy: updates must be float32, got {u.dtype}")
+      if not u.is_floating_point():
+        raise TypeError(f"tearfree sketchy: updates must be floating point, got {u.dtype}")
       leaf.xb.copy_(u)
       return leaf
 

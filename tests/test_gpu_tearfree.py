@@ -271,3 +271,31 @@ def test_tearfree_sketchy_large_axis_against_the_oracle():
     want = ref.update(gr, params)
     got, state = tx.update([torch.as_tensor(x).cuda() for x in gr], state, dparams)
     assert _rel(got[0].cpu().numpy(), want[0]) <= 5e-3, (t, _rel(got[0].cpu().numpy(), want[0]))
+
+
+def test_tearfree_half_precision_and_strided_leaves():
+  """bf16 parameters / gradients and a transposed (non-contiguous) gradient: the state is fp32 and
+  contiguous whatever the leaves look like, updates come back in the gradient's dtype and equal
+  the fp32 run on the same (bf16-rounded) values."""
+  from precondition_b200.tearfree import optimizer
+  kw = dict(graft="rmsprop", merge_dims=16, block_size=8, second_moment_decay=0.9,
+            momentum_decay=0.5, weight_decay=0.01)
+  rng = np.random.default_rng(2)
+  shapes = [(16, 8), (24,), (8, 16)]
+  p32 = [torch.as_tensor(rng.standard_normal(s).astype(np.float32)).cuda().bfloat16().float()
+         for s in shapes]
+  tx_a, tx_b = optimizer.tearfree(0.1, _options(kw)), optimizer.tearfree(0.1, _options(kw))
+  p16 = [p.bfloat16() for p in p32]
+  sa, sb = tx_a.init(p32), tx_b.init(p16)
+  for t in range(3):
+    g32 = [torch.as_tensor(rng.standard_normal(s).astype(np.float32)).cuda().bfloat16().float()
+           for s in shapes]
+    g16 = [g.bfloat16() for g in g32]
+    g16[2] = g16[2].t().contiguous().t()  # same values, column-major storage
+    assert not g16[2].is_contiguous()
+    ua, sa = tx_a.update(g32, sa, p32)
+    ub, sb = tx_b.update(g16, sb, p16)
+    for a, b in zip(ua, ub):
+      assert b.dtype == torch.bfloat16
+      torch.testing.assert_close(a.bfloat16(), b, rtol=2e-2, atol=1e-3)
+  assert sb[1][0].trace[0].dtype == torch.float32 and sb[1][0].trace[2].is_contiguous()
