@@ -641,3 +641,30 @@ def test_grouped_int8_momentum_quantisation_is_bit_exact():
     want = ops.dequantize(mat_q, None, b.reshape(-1).contiguous())
     assert torch.equal(flat[off:off + x.numel()], want.reshape(-1))
     off += x.numel()
+
+
+@pytest.mark.parametrize("n,count,pad", [(576, 3, 576), (1000, 5, 990), (1024, 80, 1024),
+                                         (2048, 2, 2048), (256, 150, 250)])
+def test_solver_power_iteration_sizes_and_cluster_shapes(n, count, pad):
+  """The lower-triangle power iteration of the solver (DS:595-652 on DS:777-783's masked matrix)
+  at sizes that are no multiple of 128, at 2048 (16 column chunks per lane), with and without
+  padding, and at batch sizes that pick clusters of 8 / 1 CTAs per matrix: the Rayleigh
+  quotient it hands to the Newton loop (metrics column 3) equals the oracle's to 1e-5 -- the
+  stopping rule |s - s_prev| <= 1e-6 makes the two stop within a step of each other."""
+  from precondition_b200 import ops
+  rng = np.random.default_rng(n + count)
+  base = [ema_statistics(rng, n, 2 * n).astype(np.float32) for _ in range(min(count, 3))]
+  xs = np.stack([base[i % len(base)] * np.float32(1 + 0.01 * (i // len(base)))
+                 for i in range(count)])
+  pads = [pad] * count
+  roots, metrics = ops.matrix_inverse_pth_root_batched(torch.as_tensor(xs).cuda(), [4] * count, pads)
+  got = metrics[:, 3].cpu().numpy()
+  # the first matrices and the last ones of the batch (other CTAs / clusters of the grid)
+  for i in sorted(set(list(range(min(count, 3))) + [count - 2, count - 1])):
+    m = xs[i].copy()
+    m[pad:, :] = 0
+    m[:, pad:] = 0
+    _, want = N.power_iteration(m, padding_start=pad)
+    # the stopping rule is absolute (1e-6): allow that much on top of the relative bound
+    assert abs(got[i] - want) <= 1e-5 * abs(want) + 2e-6, (n, i, got[i], want)
+  assert np.isfinite(roots.cpu().numpy()).all()
