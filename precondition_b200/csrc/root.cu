@@ -347,7 +347,7 @@ __device__ __forceinline__ float2 pi_block_sum2(float a, float b, float* scratch
 // runs on across the steps (the matrix does not change), so the copies also cover the
 // reductions and the cluster exchange between two sweeps.
 template <int NJ, int T, int S>
-__global__ void __launch_bounds__(T)
+__global__ void __launch_bounds__(T, (T <= 256 && NJ <= 8) ? 2 : 1)
 power_iteration_sym_kernel(const float* __restrict__ xs, const float* __restrict__ v0, int n,
                            int num_iters, float tol, RootCtl* ctl, float* __restrict__ ybuf,
                            int csize) {
@@ -671,7 +671,15 @@ static int pick_cluster_size(int batch) {
 // power-iteration exchange vectors: [batch, 2, cluster size, n] (the strip kernels of the
 // first initialisation reuse the space)
 static size_t pi_exchange_bytes(int batch, int n) {
-  return sizeof(float) * 2 * (size_t)batch * pick_cluster_size(batch) * (n < 4 ? 4 : n);
+  // (the symmetric kernel picks any cluster size up to 8 with batch * csize <= 2 * SMs)
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  const int cmax = std::max(pick_cluster_size(batch), std::max(1, std::min(8, 2 * sms / std::max(batch, 1))));
+  return sizeof(float) * 2 * (size_t)batch * cmax * (n < 4 ? 4 : n);
 }
 
 static size_t header_bytes(int batch, int n) {
@@ -745,6 +753,12 @@ int prepare_power_iteration(int n) {
                                        (int)pi_sym_smem_bytes(1024, 16, 2)));
     PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_sym_kernel<16, 256, 2>, kMax,
                                        (int)pi_sym_smem_bytes(2048, 8, 2)));
+    PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_sym_kernel<2, 256, 2>, kMax,
+                                       (int)pi_sym_smem_bytes(256, 8, 2)));
+    PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_sym_kernel<4, 256, 2>, kMax,
+                                       (int)pi_sym_smem_bytes(512, 8, 2)));
+    PC_CUDA_CHECK(cudaFuncSetAttribute(power_iteration_sym_kernel<8, 256, 2>, kMax,
+                                       (int)pi_sym_smem_bytes(1024, 8, 2)));
     sym_configured = true;
   }
   return PC_OK;
@@ -822,7 +836,27 @@ static int run_power_iteration_sym(const float* xs, int batch, int n, RootCtl* c
   if (rc != PC_OK) return rc;
   (void)v0_dev;
   const float* v0 = power_iteration_v0_device(n);
-  const int csize = pick_cluster_size(batch);
+  // Two shapes of the same kernel: (A) 16 warps, one CTA per SM; (B) 8 warps and half the
+  // ring, two CTAs per SM.  Clusters of any size up to 8 share a matrix; the shape whose grid
+  // puts more warps on the machine wins (A on a tie: fewer partial vectors to exchange).  E.g.
+  // 74 statistics: A with clusters of 2 (148 CTAs); 79: B with clusters of 3 (237 CTAs on 296
+  // slots) instead of 79 CTAs on 148 SMs; 40: B with clusters of 7.
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static const bool only_a = [] {
+    const char* e = getenv("PC_PI_SHAPE");
+    return e && e[0] == 'A';
+  }();
+  const int ca = std::max(1, std::min(8, sms / std::max(batch, 1)));
+  const int cb = std::max(1, std::min(8, 2 * sms / std::max(batch, 1)));
+  const bool shape_b = !only_a && n <= 1024 && (long long)batch * cb * 8 > (long long)batch * ca * 16;
+  if (shape_b) {
+    if (n <= 256) return launch_pi_sym<2, 256, 2>(xs, batch, n, ctl, v0, ybuf, cb, stream);
+    if (n <= 512) return launch_pi_sym<4, 256, 2>(xs, batch, n, ctl, v0, ybuf, cb, stream);
+    return launch_pi_sym<8, 256, 2>(xs, batch, n, ctl, v0, ybuf, cb, stream);
+  }
+  const int csize = only_a ? pick_cluster_size(batch) : ca;
   if (n <= 256) return launch_pi_sym<2, 512, 4>(xs, batch, n, ctl, v0, ybuf, csize, stream);
   if (n <= 512) return launch_pi_sym<4, 512, 4>(xs, batch, n, ctl, v0, ybuf, csize, stream);
   if (n <= 1024) return launch_pi_sym<8, 512, 2>(xs, batch, n, ctl, v0, ybuf, csize, stream);
