@@ -590,9 +590,14 @@ def run_ours(a):
       bert_step["ms"] = max_over_ranks(bert_step["ms"])
       sketchy_step = time_sketchy_step(dev, world)      # BASELINE config 5
       sketchy_step["ms"] = max_over_ranks(sketchy_step["ms"])
+  tearfree_step = None
   if world == 1 and not a.no_step:
     shampoo_step = time_shampoo_step(dev)
     sketchy = time_sketchy_update(dev)
+    try:
+      tearfree_step = time_tearfree_step(dev)
+    except Exception as e:  # pylint: disable=broad-except
+      tearfree_step = {"error": f"{type(e).__name__}: {e}"[:200]}
     try:
       small_block = time_small_block_batch(dev)
     except RuntimeError as e:  # (not sm_100: the persistent solver needs tcgen05)
@@ -625,6 +630,7 @@ def run_ours(a):
         "shampoo_step": shampoo_step, "sketchy_update": sketchy,
         "shampoo_step_resnet50": resnet_step, "shampoo_step_bert_large": bert_step,
         "sketchy_step": sketchy_step, "small_block_roots": small_block,
+        "tearfree_step": tearfree_step,
     }
     print(json.dumps(line), flush=True)
   if world > 1:
@@ -871,6 +877,36 @@ def time_bert_large_step(dev, world, steps=2, warm=2):
         np.linalg.norm(got - want) / np.linalg.norm(want))
     out["sampled_root_iters_ours_oracle"] = [float(st.training_metrics[0, 1]),
                                              float(wm.inverse_pth_root_iters)]
+  return out
+
+
+def time_tearfree_step(dev, steps=3, warm=3):
+  """ms per `update` of the tearfree front-end (precondition_b200.tearfree.optimizer.tearfree) on
+  a transformer-block-shaped parameter set (hidden 1024, FFN 4096), two configurations of
+  TF/second_order.py: blocked Shampoo at block_size 256 (eigh-based pseudo-inverse roots every
+  step) and Sketchy at rank 128; RMSProp grafting, Nesterov momentum (the defaults)."""
+  import torch
+  from precondition_b200.tearfree import grafting, momentum, optimizer, second_order, shampoo
+  from precondition_b200.tearfree import sketchy
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(6)
+  shapes = [(1024, 1024)] * 4 + [(1024, 4096), (4096, 1024), (1024,), (4096,), (1024,)]
+  params = [torch.randn(s, generator=gen, device=dev) * 0.05 for s in shapes]
+  grads = [[torch.randn(s, generator=gen, device=dev) * 1e-2 for s in shapes]
+           for _ in range(warm + steps)]
+  out = {"unit": "ms/step", "steps": steps, "parameters": int(sum(p.numel() for p in params)),
+         "config": "4 x 1024^2 + 1024x4096 + 4096x1024 + 3 vectors; RMSProp grafting, Nesterov 0.9"}
+  for name, so in (
+      ("shampoo_block256", second_order.Options(
+          merge_dims=1024, shampoo_options=shampoo.Options(block_size=256))),
+      ("sketchy_rank128", second_order.Options(
+          merge_dims=1024, second_order_type=second_order.SecondOrderType.SKETCHY,
+          sketchy_options=sketchy.Options(rank=128)))):
+    tx = optimizer.tearfree(0.1, optimizer.TearfreeOptions(second_order_options=so))
+    state = tx.init(params)
+    per_step, upd, state = _timed_updates(tx, state, params, grads, warm, steps)
+    out[name] = {"ms": sum(per_step) / steps, "ms_per_step_list": [round(x, 3) for x in per_step],
+                 "update_finite": bool(all(torch.isfinite(u).all() for u in upd))}
   return out
 
 

@@ -915,6 +915,22 @@ static int fd_jacobi_launch_v(float* a, float* vt, int n, int batch, unsigned* r
                               cudaStream_t stream, float tol, int max_sweeps) {
   int csize = 1;
   while (csize < 8 && (kThreads / 32) * csize < (n + 1) / 2) csize <<= 1;
+  // Large batches (tearfree's blocked Shampoo: hundreds of 256 x 256 statistics): a cluster per
+  // matrix only pays while there are SMs to spare; beyond that fewer CTAs per matrix (more pairs
+  // per warp and round, block barriers instead of cluster barriers) give the same rotations --
+  // bitwise, the pairs of a round are disjoint -- at a multiple of the throughput.
+  {
+    static int occ = 0;  // resident CTAs per SM of this instantiation
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (occ == 0) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fd_jacobi_kernel<Q, kThreads, kWithV>,
+                                                    kThreads, 0);
+      if (occ < 1) occ = 1;
+    }
+    while (csize > 1 && (long long)batch * csize > (long long)sms * occ) csize >>= 1;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(batch * csize));
   cfg.blockDim = dim3(kThreads);
