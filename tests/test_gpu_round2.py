@@ -644,11 +644,13 @@ def test_grouped_int8_momentum_quantisation_is_bit_exact():
 
 
 @pytest.mark.parametrize("n,count,pad", [(576, 3, 576), (1000, 5, 990), (1024, 80, 1024),
-                                         (2048, 2, 2048), (256, 150, 250)])
+                                         (2048, 2, 2048), (256, 150, 250), (1024, 50, 1024),
+                                         (512, 20, 500), (256, 40, 256)])
 def test_solver_power_iteration_sizes_and_cluster_shapes(n, count, pad):
   """The lower-triangle power iteration of the solver (DS:595-652 on DS:777-783's masked matrix)
   at sizes that are no multiple of 128, at 2048 (16 column chunks per lane), with and without
-  padding, and at batch sizes that pick clusters of 8 / 1 CTAs per matrix: the Rayleigh
+  padding, and at batch sizes that pick clusters of 8 / 7 / 5 / 3 / 1 CTAs per matrix in either
+  shape of the kernel (16 warps and one CTA per SM, 8 warps and two): the Rayleigh
   quotient it hands to the Newton loop (metrics column 3) equals the oracle's to 1e-5 -- the
   stopping rule |s - s_prev| <= 1e-6 makes the two stop within a step of each other."""
   from precondition_b200 import ops
