@@ -333,6 +333,14 @@ int pc_inverse_pth_root_eigh_batched(const float* xs, const int32_t* ps,
 int pc_pinv_pth_root_eigh_batched(const float* xs, const int32_t* ps, int batch, int d,
                                   float rel_cutoff, float* roots, void* workspace,
                                   size_t workspace_bytes, void* stream);
+/* The same with a warm start: eigvecs [batch, d, d] (rows = eigenvectors, descending) receives
+ * this call's eigenvectors and, when eigvecs_valid != 0, holds those of the previous call for
+ * the same statistics -- the eigen-solve then runs in that basis and needs a fraction of the
+ * Jacobi sweeps while the statistics drift slowly (every step of a training run). */
+int pc_pinv_pth_root_eigh_warm_batched(const float* xs, const int32_t* ps, int batch, int d,
+                                       float rel_cutoff, float* roots, float* eigvecs,
+                                       int eigvecs_valid, void* workspace,
+                                       size_t workspace_bytes, void* stream);
 
 /* Dense form of the operator a packed low-rank preconditioner applies in
  * _precondition_block (DS:1690-1705, _low_rank_unpack DS:540-545):

@@ -43,7 +43,8 @@ EXPORTED_SYMBOLS = (
     "pc_sm3_workspace_bytes", "pc_sm3_update",
     "pc_lobpcg_deflate_prep", "pc_lobpcg_redeflate_prep", "pc_root_diagnostics",
     "pc_lobpcg_diagnostics",
-    "pc_pinv_pth_root_eigh_batched", "pc_tearfree_transform_workspace_bytes",
+    "pc_pinv_pth_root_eigh_batched", "pc_pinv_pth_root_eigh_warm_batched",
+    "pc_tearfree_transform_workspace_bytes",
     "pc_tearfree_transform",
     "pc_quant_group_chunk_elems", "pc_quant_group_tile_rows", "pc_dequantize_grouped",
     "pc_quantize_grouped",
@@ -280,6 +281,8 @@ def load() -> ctypes.CDLL:
   lib.pc_quantize_grouped.restype = i32
   lib.pc_pinv_pth_root_eigh_batched.argtypes = [vp, vp, i32, i32, f32, vp, vp, sz, vp]
   lib.pc_pinv_pth_root_eigh_batched.restype = i32
+  lib.pc_pinv_pth_root_eigh_warm_batched.argtypes = [vp, vp, i32, i32, f32, vp, vp, i32, vp, sz, vp]
+  lib.pc_pinv_pth_root_eigh_warm_batched.restype = i32
   lib.pc_tearfree_transform_workspace_bytes.argtypes = [i32, i64]
   lib.pc_tearfree_transform_workspace_bytes.restype = sz
   lib.pc_tearfree_transform.argtypes = [vp, vp, i32, i64, ctypes.POINTER(TearfreeOptions), vp, sz,

@@ -1543,7 +1543,13 @@ __global__ void lr_root_metrics_kernel(const uint32_t* __restrict__ errbits,
 int run_low_rank_root(const float* xs, const int32_t* ps, const int32_t* pads, int batch, int d,
                       int rank_signed, bool full_root, float ridge_epsilon, float error_tolerance,
                       int relative, float* out, float* metrics, void* workspace,
-                      size_t workspace_bytes, cudaStream_t stream, float pinv_cutoff = 0.f) {
+                      size_t workspace_bytes, cudaStream_t stream, float pinv_cutoff = 0.f,
+                      float* warm = nullptr, int warm_valid = 0) {
+  // `warm` [batch, d, d] (rows = eigenvectors of the previous call's matrix, in / out): the
+  // solve then runs on M = W reg W^T, which is nearly diagonal when the matrix moved little
+  // since -- its Cholesky factor has nearly orthogonal rows and the Jacobi sweeps drop from
+  // ~8 to 2-3 (quadratic convergence); eigenvectors of reg = (eigenvectors of M) W.
+  const bool use_warm = warm != nullptr && warm_valid != 0 && pads == nullptr;
   if (workspace_bytes < low_rank_root_bytes(batch, d)) {
     set_error("eigh root workspace too small: %zu < %zu", workspace_bytes,
               low_rank_root_bytes(batch, d));
@@ -1578,12 +1584,33 @@ int run_low_rank_root(const float* xs, const int32_t* ps, const int32_t* pads, i
   }
   lr_damp_kernel<<<dim3(g, batch), 256, 0, stream>>>(reg, reg_copy, lambdas, pads, d,
                                                     ridge_epsilon, error_tolerance, relative, ridge);
+  if (use_warm) {  // reg <- W reg W^T (reg_copy keeps the matrix itself)
+    FdGemm q{};
+    q.alpha = 1.f; q.a = warm; q.b = reg_copy; q.c = t1;  // t1 = W reg (reg symmetric)
+    q.a_bs = q.b_bs = q.c_bs = (int64_t)nn;
+    q.a_si = d; q.a_sk = 1; q.b_sj = d; q.b_sk = 1; q.c_si = d;
+    q.m = q.n = q.k = d;
+    fd_gemm(q, batch, stream);
+    q.a = t1; q.b = warm; q.c = reg;                       // reg = t1 W^T
+    fd_gemm(q, batch, stream);
+  }
   // factor, then one-sided Jacobi on the rows of G = L^T: rows -> sigma_i u_i^T, theta = sigma^2
   lr_cholesky_kernel<<<batch, 1024, 0, stream>>>(reg, pads, d, vt);
   int rc = fd_jacobi(vt, nullptr, d, batch, rot, theta, stream);
   if (rc != PC_OK) return rc;
   fd_sort_kernel<<<batch, 512, 0, stream>>>(theta, d, order, sorted);
   lr_gather_normalize_kernel<<<dim3(d, batch), 256, 0, stream>>>(vt, order, d, vs);
+  if (use_warm) {  // back to the original basis: Vs <- Vs W
+    FdGemm q{};
+    q.alpha = 1.f; q.a = vs; q.b = warm; q.c = t1;
+    q.a_bs = q.b_bs = q.c_bs = (int64_t)nn;
+    q.a_si = d; q.a_sk = 1; q.b_sj = 1; q.b_sk = d; q.c_si = d;
+    q.m = q.n = q.k = d;
+    fd_gemm(q, batch, stream);
+    PC_CUDA_CHECK(cudaMemcpyAsync(vs, t1, B * nn * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (warm != nullptr && pads == nullptr)
+    PC_CUDA_CHECK(cudaMemcpyAsync(warm, vs, B * nn * 4, cudaMemcpyDeviceToDevice, stream));
   if (pinv_cutoff <= 0.f) {
     // recovered = Vs reg Vs^T
     FdGemm q{};
@@ -1688,6 +1715,14 @@ int pc_inverse_pth_root_eigh_batched(const float* xs, const int32_t* ps,
 int pc_pinv_pth_root_eigh_batched(const float* xs, const int32_t* ps, int batch, int d,
                                   float rel_cutoff, float* roots, void* workspace,
                                   size_t workspace_bytes, void* stream) {
+  return pc_pinv_pth_root_eigh_warm_batched(xs, ps, batch, d, rel_cutoff, roots, nullptr, 0,
+                                            workspace, workspace_bytes, stream);
+}
+
+int pc_pinv_pth_root_eigh_warm_batched(const float* xs, const int32_t* ps, int batch, int d,
+                                       float rel_cutoff, float* roots, float* eigvecs,
+                                       int eigvecs_valid, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
   PC_REQUIRE(batch >= 0 && d > 0 && rel_cutoff > 0.f, "bad pseudo-inverse root arguments");
   if (batch == 0) return PC_OK;
   PC_REQUIRE(xs && ps && roots && workspace, "null pointer argument");
@@ -1699,7 +1734,7 @@ int pc_pinv_pth_root_eigh_batched(const float* xs, const int32_t* ps, int batch,
   const float shift = fmaxf(1e-6f, 4.0f * (float)d * 5.96e-8f);
   return pc::run_low_rank_root(xs, ps, nullptr, batch, d, 0, true, shift, 1e-30f, 1, roots,
                                nullptr, workspace, workspace_bytes, (cudaStream_t)stream,
-                               rel_cutoff);
+                               rel_cutoff, eigvecs, eigvecs_valid);
 }
 
 void pc_fd_options_default(pc_fd_options* opt) {

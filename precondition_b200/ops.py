@@ -255,7 +255,9 @@ def matrix_inverse_pth_root_eigh_batched(xs: torch.Tensor, ps, padding_starts=No
 
 
 def pinv_pth_root_eigh_batched(xs: torch.Tensor, ps, rel_cutoff: float = 1e-6,
-                               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                               out: Optional[torch.Tensor] = None,
+                               eigvecs: Optional[torch.Tensor] = None,
+                               eigvecs_valid: bool = False) -> torch.Tensor:
   """Batched pseudo-inverse p-th root by eigendecomposition, tearfree's ``_pth_inv_root``
   (TF/shampoo.py:440-448): eigenvalues <= rel_cutoff * max are dropped.  xs [b, d, d]; d <= 2048."""
   global gpu_launches
@@ -269,8 +271,11 @@ def pinv_pth_root_eigh_batched(xs: torch.Tensor, ps, rel_cutoff: float = 1e-6,
     return roots
   ws = _workspace(lib.pc_low_rank_root_workspace_bytes(b, d), dev)
   with torch.cuda.device(dev):
-    _lib.check(lib.pc_pinv_pth_root_eigh_batched(
-        _ptr(xs), _ptr(ps_t), b, d, rel_cutoff, _ptr(roots), _ptr(ws), ws.numel(),
+    # eigvecs [b, d, d] (optional, in / out): warm start of the eigen-solve, see the header
+    _require_cuda(eigvecs)
+    _lib.check(lib.pc_pinv_pth_root_eigh_warm_batched(
+        _ptr(xs), _ptr(ps_t), b, d, rel_cutoff, _ptr(roots), _ptr(eigvecs),
+        int(bool(eigvecs_valid and eigvecs is not None)), _ptr(ws), ws.numel(),
         ctypes.c_void_p(_stream())))
   gpu_launches += 1
   return roots

@@ -14,6 +14,7 @@ Statistics and roots of equal size live in one buffer per size so the root solve
 import dataclasses
 import functools
 import math
+import os
 from typing import Any, NamedTuple, Optional, Sequence
 
 import torch
@@ -24,6 +25,7 @@ from precondition_b200.tearfree import _tree
 from precondition_b200.tearfree import praxis_shim
 
 EIGH_CUTOFF = 1e-6  # `eps` of _pth_inv_root, TF/shampoo.py:442
+WARM_START = os.environ.get("PC_TF_EIGH_WARM", "1") != "0"  # previous eigenvectors as the basis
 
 
 @dataclasses.dataclass
@@ -164,11 +166,15 @@ class _Engine:
 
     self.plan_tree = _tree.tree_map_with_path(plan, params)
     dev = self.device
-    self.stats, self.roots, self.ps = {}, {}, {}
+    self.stats, self.roots, self.ps, self.eigvecs, self.eig_valid = {}, {}, {}, {}, {}
     for d, cnt in counts.items():
       self.stats[d] = torch.zeros((cnt, d, d), dtype=torch.float32, device=dev)
       self.roots[d] = torch.eye(d, dtype=torch.float32, device=dev).repeat(cnt, 1, 1)
       self.ps[d] = torch.zeros(cnt, dtype=torch.int32)
+      # eigenvectors of the last solve, the warm start of the next one (not part of the state:
+      # after a restore the first solve simply starts cold)
+      self.eigvecs[d] = torch.zeros((cnt, d, d), dtype=torch.float32, device=dev)
+      self.eig_valid[d] = False
     for leaf in self.leaves:
       m = leaf.meta
       for d, first in leaf.slots:
@@ -201,6 +207,7 @@ class _Engine:
     for m, t in zip(mine, theirs):
       for a, b in zip(m.stats + m.roots, t.stats + t.roots):
         a.copy_(b.to(device=a.device, dtype=torch.float32))
+    self.eig_valid = {d: False for d in self.eig_valid}
 
   def _build_lists(self):
     decay = self.options.second_moment_decay
@@ -294,7 +301,9 @@ class _Engine:
         lst.run()
     if count % o.update_preconditioners_freq == 0:  # TF/shampoo.py:291-296
       for d in self.stats:
-        ops.pinv_pth_root_eigh_batched(self.stats[d], self.ps[d], EIGH_CUTOFF, out=self.roots[d])
+        ops.pinv_pth_root_eigh_batched(self.stats[d], self.ps[d], EIGH_CUTOFF, out=self.roots[d],
+                                       eigvecs=self.eigvecs[d], eigvecs_valid=self.eig_valid[d])
+        self.eig_valid[d] = WARM_START
     for group in self.apply_lists:
       for lst in group:
         lst.run()
