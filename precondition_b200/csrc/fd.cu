@@ -1411,6 +1411,17 @@ lr_cholesky_kernel(float* __restrict__ reg_all, const int32_t* __restrict__ pads
     G[e] = (i < pad && j < pad && j >= i) ? A[(size_t)j * d + i] : 0.f;  // G = L^T
   }
 }
+// G = L^T from the lower triangle of an in-place factorisation (no padding)
+__global__ void lr_upper_from_lower_kernel(const float* __restrict__ l_all, int d,
+                                           float* __restrict__ g_all) {
+  const int b = blockIdx.y;
+  const size_t nn = (size_t)d * d;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nn;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / d), j = (int)(e - (size_t)i * d);
+    g_all[(size_t)b * nn + e] = j >= i ? l_all[(size_t)b * nn + (size_t)j * d + i] : 0.f;
+  }
+}
 // vs[b][t][:] = rows[b][order[t]][:] / |row|  (u_i = row_i / sigma_i; zero rows stay zero)
 __global__ void __launch_bounds__(256)
 lr_gather_normalize_kernel(const float* __restrict__ rows, const int* __restrict__ order, int d,
@@ -1595,7 +1606,15 @@ int run_low_rank_root(const float* xs, const int32_t* ps, const int32_t* pads, i
     fd_gemm(q, batch, stream);
   }
   // factor, then one-sided Jacobi on the rows of G = L^T: rows -> sigma_i u_i^T, theta = sigma^2
-  lr_cholesky_kernel<<<batch, 1024, 0, stream>>>(reg, pads, d, vt);
+  const size_t chol_smem = ((size_t)((d + 31) & ~31) + (size_t)d * (d + 1) / 2) * sizeof(float);
+  if (pads == nullptr && chol_smem <= kCholSmemMax) {
+    // the packed triangle fits in shared memory: the tiled factorisation of the sketch path
+    int rcc = fd_cholesky_shift(reg, d, batch, 0.f, stream);
+    if (rcc != PC_OK) return rcc;
+    lr_upper_from_lower_kernel<<<dim3(g, batch), 256, 0, stream>>>(reg, d, vt);
+  } else {
+    lr_cholesky_kernel<<<batch, 1024, 0, stream>>>(reg, pads, d, vt);
+  }
   int rc = fd_jacobi(vt, nullptr, d, batch, rot, theta, stream);
   if (rc != PC_OK) return rc;
   fd_sort_kernel<<<batch, 512, 0, stream>>>(theta, d, order, sorted);
