@@ -226,6 +226,16 @@ typedef struct {
   uint32_t* colmax_out;
   int32_t qdtype; /* PC_QDTYPE_INT16 or PC_QDTYPE_INT8 */
   int32_t reserved;
+  /* b_q != NULL: the B operand is a QuantizedValue with extracted diagonal -- a square
+   * [b_ld, b_ld] matrix q (b_qdtype), diag [b_ld], bucket [b_ld] -- read through desc.b's
+   * strides with desc.b ignored: to_float(q)[r][c] = q[r][c] * bucket[c] + diag[r] (r == c) is
+   * formed while the operand is packed, the dequantised preconditioner is never materialised
+   * (DS:3556 _maybe_dequantize_preconditioners + DS:1707).  One-level B addressing only. */
+  const void* b_q;
+  const float* b_diag;
+  const float* b_bucket;
+  int32_t b_ld;
+  int32_t b_qdtype;
 } pc_gemm_quant;
 int pc_grouped_gemm_tc_quant(const pc_gemm_desc* descs_host, const pc_gemm_quant* quant_host,
                              int count, void* workspace, size_t workspace_bytes, int reuse_plan,

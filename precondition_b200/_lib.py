@@ -88,7 +88,9 @@ class GemmDesc(ctypes.Structure):
 class GemmQuant(ctypes.Structure):
   _fields_ = [("q_in", ctypes.c_void_p), ("diag_in", ctypes.c_void_p),
               ("bucket_in", ctypes.c_void_p), ("colmax_out", ctypes.c_void_p),
-              ("qdtype", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+              ("qdtype", ctypes.c_int32), ("reserved", ctypes.c_int32),
+              ("b_q", ctypes.c_void_p), ("b_diag", ctypes.c_void_p), ("b_bucket", ctypes.c_void_p),
+              ("b_ld", ctypes.c_int32), ("b_qdtype", ctypes.c_int32)]
 
 
 class GraftOptions(ctypes.Structure):

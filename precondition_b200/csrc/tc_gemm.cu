@@ -2103,6 +2103,9 @@ struct TcGgOperand {  // one packed operand: view + where its tiles go
   int64_t s_io, s_i, s_ko, s_ki;
   int i_inner, k_inner, rows, k, kblocks, tile0;
   int is_b, reserved;  // second operand of a general product (its pack can be skipped, see below)
+  // quantised source (pc_gemm_quant.b_q): element offset `off` of the view addresses q, the
+  // value is q[off] * bucket[off % ld] (+ diag[off / ld] on the diagonal)
+  const void* q; const float* q_diag; const float* q_bucket; int q_ld, q_dtype;
 };
 
 __device__ __forceinline__ float tc_gg_view(const TcGgOperand& o, int i, int kk) {
@@ -2145,8 +2148,23 @@ tc_pack_kernel(const TcGgOperand* __restrict__ ops, float* __restrict__ inv_scal
       const int r = kfast ? e >> 6 : e & 127, c = kfast ? e & 63 : e >> 7;
       const int i = tr * 128 + r, kk = kb * 64 + c;
       float v;
-      if (simple) v = kk < o.k ? __ldg(o.base + (int64_t)i * o.s_i + (int64_t)kk * o.s_ki) : 0.f;
-      else v = tc_gg_view(o, i, kk);
+      if (o.q) {  // to_float of a quantised square matrix on the fly (QU:97-113)
+        v = 0.f;
+        if (kk < o.k) {
+          // (a square matrix of up to 46340 rows: the offset fits 32 bits)
+          const uint32_t off = (uint32_t)((int64_t)i * o.s_i + (int64_t)kk * o.s_ki);
+          const uint32_t qr = off / (uint32_t)o.q_ld, qc = off - qr * (uint32_t)o.q_ld;
+          const float qv = o.q_dtype == PC_QDTYPE_INT16
+                               ? (float)reinterpret_cast<const int16_t*>(o.q)[off]
+                               : (float)reinterpret_cast<const int8_t*>(o.q)[off];
+          v = qv * __ldg(o.q_bucket + qc);
+          if (qr == qc) v += __ldg(o.q_diag + qr);
+        }
+      } else if (simple) {
+        v = kk < o.k ? __ldg(o.base + (int64_t)i * o.s_i + (int64_t)kk * o.s_ki) : 0.f;
+      } else {
+        v = tc_gg_view(o, i, kk);
+      }
       tile[c][r] = v;
       const uint32_t ab = absbits(v);
       mx = ab > mx ? ab : mx;
@@ -2498,6 +2516,10 @@ static void tc_gg_plan(const pc_gemm_desc* descs, const pc_gemm_quant* quant, in
       ob.i_inner = d.n; ob.k_inner = d.b_kinner > 0 ? d.b_kinner : d.k;
       ob.rows = d.n; ob.k = d.k; ob.kblocks = it.kblocks; ob.tile0 = pl->total_tiles;
       ob.is_b = 1;
+      if (quant && quant[z].b_q) {
+        ob.q = quant[z].b_q; ob.q_diag = quant[z].b_diag; ob.q_bucket = quant[z].b_bucket;
+        ob.q_ld = quant[z].b_ld; ob.q_dtype = quant[z].b_qdtype;
+      }
       it.b_tile0 = ob.tile0;
       pl->total_tiles += (d.n / 128) * it.kblocks;
       pl->ops.push_back(ob);
@@ -2539,6 +2561,15 @@ int tc_grouped_gemm(const pc_gemm_desc* descs, const pc_gemm_quant* quant, int c
                                    quant[z].diag_in && quant[z].bucket_in),
                  "descriptor %d: quantised C_in needs int16 / int8 data, diagonal and buckets", z);
     }
+  }
+  for (int z = 0; z < count && quant; ++z) {
+    if (!quant[z].b_q) continue;
+    const pc_gemm_desc& d = descs[z];
+    PC_REQUIRE(!tc_gg_symmetric(d) && quant[z].b_diag && quant[z].b_bucket && quant[z].b_ld > 0 &&
+                   (quant[z].b_qdtype == PC_QDTYPE_INT16 || quant[z].b_qdtype == PC_QDTYPE_INT8) &&
+                   (d.b_kinner <= 0 || d.b_kinner >= d.k),
+               "descriptor %d: a quantised B operand needs diagonal, buckets, its row stride and "
+               "one-level addressing", z);
   }
   if (!tc_engine_available()) {
     set_error("tcgen05 grouped GEMM requested but device is not sm_100");

@@ -832,6 +832,7 @@ class _Shampoo:
     preconditioner application (DS:1676-1708), built once."""
     D = _lib.GemmDesc
     stat_descs, stat_meta, apply_descs = [], [], []
+    apply_qsrc = {}  # id(descriptor) -> (bucket, index) of the quantised preconditioner it applies
     # blocks of merged rank > 3: their mode unfoldings are no two-level strided views of the flat
     # gradient buffer, so each block is staged through contiguous copies (in: before the
     # statistics, out: after the last mode product); DS:1676-1708 loops over any rank
@@ -947,6 +948,8 @@ class _Shampoo:
           if refs[j] is not None:
             S, bi = refs[j]  # row stride of the stored preconditioner
             pptr = self.buckets[S].precs.data_ptr() + f32 * bi * S * S
+            if self.quantize_second_moment and not self.buckets[S].compressed:
+              apply_qsrc[id(d)] = (S, bi)  # its QuantizedValue can feed the GEMM directly
           else:  # not preconditioned: pure roll (DS:1684-1686) -> multiply by I
             S = d0
             pptr = self._identity(d0).data_ptr()
@@ -1021,10 +1024,30 @@ class _Shampoo:
       stat_descs = rest
     self._stat_tc, self._stat_simt = split(stat_descs)
     self._apply_tc, self._apply_simt = [], []
+    # quantised preconditioners (DS:3556): products on the tcgen05 path read the int16 / int8
+    # QuantizedValue while packing the operand (pc_gemm_quant.b_q); only buckets with a consumer
+    # on the CUDA-core path are still dequantised into `precs` before the application
+    for bk in self.buckets.values():
+      bk.dequant_for_apply = False
     for lst in apply_descs:
-      tc, simt = split(lst)
-      self._apply_tc.append(tc)
-      self._apply_simt.append(simt)
+      tc = [d for d in lst if use_tc and ops.tc_gemm_eligible(d)]
+      simt = [d for d in lst if not (use_tc and ops.tc_gemm_eligible(d))]
+      for d in simt:
+        if id(d) in apply_qsrc:
+          self.buckets[apply_qsrc[id(d)][0]].dequant_for_apply = True
+      ext = None
+      if tc and any(id(d) in apply_qsrc for d in tc):
+        ext = []
+        for d in tc:
+          e = _lib.GemmQuant()
+          if id(d) in apply_qsrc:
+            S, bi = apply_qsrc[id(d)]
+            q, dg, bs = self.buckets[S].qprecs
+            e.b_q, e.b_diag, e.b_bucket = q[bi].data_ptr(), dg[bi].data_ptr(), bs[bi].data_ptr()
+            e.b_ld, e.b_qdtype = S, ops._QDT[self.qdt_second]
+          ext.append(e)
+      self._apply_tc.append(ops.TcGemmList(tc, self.device, quant=ext) if tc else None)
+      self._apply_simt.append(ops.SimtGemmLists(simt, self.device) if simt else None)
 
 
   def _lowrank_descs(self, apply_descs, sizes, refs, comp_axes, x_ptr, z_ptr, ld):
@@ -1575,8 +1598,9 @@ class _Shampoo:
   def _apply_preconditioners(self):
     if self.quantize_second_moment:  # DS:3556 _maybe_dequantize_preconditioners
       for bk in self.buckets.values():
-        q, d, b = bk.qprecs
-        ops.dequantize(q, d, b, True, out=bk.precs)
+        if getattr(bk, "dequant_for_apply", True):  # (tcgen05 consumers read the quantised form)
+          q, d, b = bk.qprecs
+          ops.dequantize(q, d, b, True, out=bk.precs)
     for j, simt in enumerate(self._apply_simt):
       if simt is not None:
         simt.run()

@@ -289,6 +289,61 @@ def test_tc_statistics_update_with_fused_quantisation(qdtype, levels):
     assert torch.equal(q2[0], qn[b]) and torch.equal(d2[0], dn[b]) and torch.equal(b2[0], bn[b])
 
 
+@pytest.mark.parametrize("qdtype", [torch.int16, torch.int8])
+def test_tc_apply_reads_quantised_preconditioner(qdtype):
+  """pc_gemm_quant.b_q: out = G to_float(Q) and out = G to_float(Q)^T with the QuantizedValue
+  (QU:97-113, per-column buckets + extracted diagonal) dequantised while the operand is packed,
+  against the same products over the separately dequantised matrix (DS:3556 then DS:1707) and
+  against the oracle's to_float in float64.  Q is not symmetric as a float matrix (buckets are
+  per column), so both orientations of the B view are checked."""
+  if not _tc_ok():
+    pytest.skip("needs sm_100")
+  from precondition_b200 import _lib, ops
+  rng = np.random.default_rng(41)
+  m, s = 256, 384
+  npq = np.int16 if qdtype == torch.int16 else np.int8
+  a = rng.standard_normal((s, 2 * s))
+  pmat = ((a @ a.T / s) * np.exp(rng.standard_normal(s))[None, :]).astype(np.float32)
+  qv = N.QuantizedValue.from_float_value(pmat, npq, True)
+  q = torch.as_tensor(qv.quantized).cuda()
+  dg = torch.as_tensor(qv.diagonal.astype(np.float32)).cuda()
+  bs = torch.as_tensor(qv.bucket_size.astype(np.float32)).cuda()
+  deq = ops.dequantize(q[None], dg[None], bs[None], True)[0].contiguous()
+  g = torch.as_tensor(rng.standard_normal((m, s)).astype(np.float32)).cuda()
+  outs = [torch.zeros((m, s), dtype=torch.float32).cuda() for _ in range(4)]
+
+  def desc(out, b_ptr, transposed):
+    d = _lib.GemmDesc()
+    d.a = g.data_ptr(); d.b = b_ptr; d.c = out.data_ptr(); d.c_in = None
+    d.a_si = s; d.a_iinner, d.a_sio = m, 0; d.a_kinner, d.a_sko, d.a_ski = s, 0, 1
+    # B(j, k) = P[k, j] (G P) or P[j, k] (G P^T)
+    d.b_sj, d.b_ski = (s, 1) if transposed else (1, s)
+    d.b_kinner, d.b_sko = s, 0
+    d.c_iinner, d.c_sio, d.c_sii = m, 0, s
+    d.m, d.n, d.k = m, s, s; d.alpha, d.beta = 1.0, 0.0
+    return d
+
+  def ext():
+    e = _lib.GemmQuant()
+    e.b_q, e.b_diag, e.b_bucket = q.data_ptr(), dg.data_ptr(), bs.data_ptr()
+    e.b_ld, e.b_qdtype = s, ops._QDT[qdtype]
+    return e
+
+  # the first descriptor of the fused list is a plain fp32 one: extensions are per descriptor
+  fused = [desc(outs[0], None, False), desc(outs[1], None, True)]
+  plain = [desc(outs[2], deq.data_ptr(), False), desc(outs[3], deq.data_ptr(), True)]
+  ops.TcGemmList(fused, g.device, quant=[ext(), ext()]).run()
+  ops.TcGemmList(plain, g.device).run()
+  torch.cuda.synchronize()
+  f64 = qv.to_float().astype(np.float64)
+  g64 = g.cpu().numpy().astype(np.float64)
+  for got, ref, w in ((outs[0], outs[2], g64 @ f64), (outs[1], outs[3], g64 @ f64.T)):
+    got, ref = got.cpu().numpy(), ref.cpu().numpy()
+    assert np.abs(got - w).max() / np.abs(w).max() <= 2e-6
+    # same operand values up to the fused multiply-add of the diagonal term
+    assert np.abs(got - ref).max() / np.abs(w).max() <= 1e-6
+
+
 def test_simt_lists_split_k_and_size_classes():
   """ops.SimtGemmLists: a 9 x 9 Gram over k = 40000 (split-K kernel, deterministic) next to a
   larger block and a tiny one (separate size classes) against float64."""
