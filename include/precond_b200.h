@@ -194,8 +194,10 @@ size_t pc_grouped_gemm_splitk_workspace_bytes(int count, int max_m, int max_n, i
 int pc_grouped_gemm_splitk(const pc_gemm_desc* descs, int count, int max_m, int max_n, int splits,
                            void* workspace, size_t workspace_bytes, void* stream);
 
-/* tcgen05 path of the grouped GEMM for descriptors whose m and n are multiples of 128 (k is
- * arbitrary; c / c_in 16-byte aligned with c_sii, c_sio multiples of 4): every operand view is
+/* tcgen05 path of the grouped GEMM (any m and k, n a multiple of 4; c / c_in 16-byte aligned with
+ * c_sii, c_sio multiples of 4; edge tiles of sizes that are no multiples of 128 -- the 1000 x 1000
+ * statistic of a classifier, 576-row convolution kernels -- are zero-filled when the operand is
+ * packed and masked when the result is stored): every operand view is
  * packed once into scaled-fp16 plane tiles (22 mantissa bits, per-operand power-of-two scale)
  * and the products run as three kind::f16 MMAs per k-step with fp32 accumulation.  A descriptor
  * with identical A and B views (the Gram update of DS:1468-1470) is computed as a symmetric
@@ -212,7 +214,7 @@ int pc_grouped_gemm_tc(const pc_gemm_desc* descs_host, int count, void* workspac
 
 /* The same call with QuantizedValue (QU:49-113) fused in, for the statistics update of
  * quantised second moments (DS:1588-1590 around gram_weighted_update): per descriptor (a
- * symmetric product into a contiguous [n, n] matrix)
+ * symmetric product into a contiguous [n, n] matrix, n a multiple of 128)
  *   q_in != NULL      C_in is read as to_float(q_in, diag_in, bucket_in) = q * bucket[col] + diag
  *                     on the diagonal -- the dequantised matrix is never materialised;
  *   colmax_out != NULL  [n] uint32, zero on entry: receives the bit patterns of the per-column

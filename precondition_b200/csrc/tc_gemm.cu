@@ -2137,7 +2137,7 @@ tc_pack_kernel(const TcGgOperand* __restrict__ ops, float* __restrict__ inv_scal
   __shared__ uint32_t red[32];
   const TcGgOperand o = ops[blockIdx.y];
   if (skip_b && o.is_b) return;  // its planes from the previous call are still valid
-  const int tiles = (o.rows / 128) * o.kblocks;
+  const int tiles = ((o.rows + 127) / 128) * o.kblocks;  // rows past the view are zero-filled
   const bool kfast = o.s_ki == 1;
   const bool simple = o.i_inner >= o.rows && o.k_inner >= o.k;  // one-level addressing
   for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -2150,7 +2150,7 @@ tc_pack_kernel(const TcGgOperand* __restrict__ ops, float* __restrict__ inv_scal
       float v;
       if (o.q) {  // to_float of a quantised square matrix on the fly (QU:97-113)
         v = 0.f;
-        if (kk < o.k) {
+        if (kk < o.k && i < o.rows) {
           // (a square matrix of up to 46340 rows: the offset fits 32 bits)
           const uint32_t off = (uint32_t)((int64_t)i * o.s_i + (int64_t)kk * o.s_ki);
           const uint32_t qr = off / (uint32_t)o.q_ld, qc = off - qr * (uint32_t)o.q_ld;
@@ -2161,7 +2161,8 @@ tc_pack_kernel(const TcGgOperand* __restrict__ ops, float* __restrict__ inv_scal
           if (qr == qc) v += __ldg(o.q_diag + qr);
         }
       } else if (simple) {
-        v = kk < o.k ? __ldg(o.base + (int64_t)i * o.s_i + (int64_t)kk * o.s_ki) : 0.f;
+        v = (kk < o.k && i < o.rows)
+                ? __ldg(o.base + (int64_t)i * o.s_i + (int64_t)kk * o.s_ki) : 0.f;
       } else {
         v = tc_gg_view(o, i, kk);
       }
@@ -2361,6 +2362,7 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       const float alpha = it.alpha;
       const float beta = it.beta_dev ? __ldg(it.beta_dev) : it.beta;
       const int row = wk.tm * TC_BM + q * 32 + lane;
+      const bool row_ok = row < it.m;  // ragged edge tiles: rows / columns past the block are masked
       const int io = row / it.c_iinner, ii = row - io * it.c_iinner;
       const int64_t rowoff = io * it.c_sio + ii * it.c_sii;
       const bool diag_tile = it.symmetric && wk.tm == wk.tn;
@@ -2376,6 +2378,7 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         }
         const int col0 = wk.tn * TC_BN + c * 32;
         if (diag_tile && c > q) continue;  // strictly upper sub-block: written by its mirror
+        if (col0 >= it.n) continue;        // sub-block past the last column (warp-uniform)
         float x[32];
         const bool diag_sub = diag_tile && c == q;
         if (it.q_in) {
@@ -2414,11 +2417,11 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             x[i] = fmaf(beta, o, alpha * __uint_as_float(r[i]));
           }
         } else {
-          const float* cin = it.c_in ? it.c_in + rowoff + col0 : nullptr;
+          const float* cin = (it.c_in && row_ok) ? it.c_in + rowoff + col0 : nullptr;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cin) old = *reinterpret_cast<const float4*>(cin + i);
+            if (cin && col0 + i < it.n) old = *reinterpret_cast<const float4*>(cin + i);
             x[i] = fmaf(beta, old.x, alpha * __uint_as_float(r[i]));
             x[i + 1] = fmaf(beta, old.y, alpha * __uint_as_float(r[i + 1]));
             x[i + 2] = fmaf(beta, old.z, alpha * __uint_as_float(r[i + 2]));
@@ -2444,11 +2447,12 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         if (!diag_sub) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(crow + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+            if (row_ok && col0 + i < it.n)  // (n % 4 == 0: a group of four is in or out as a whole)
+              *reinterpret_cast<float4*>(crow + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
         } else {  // lower triangle of the diagonal sub-block only (its mirror fills the rest)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i <= lane) crow[i] = x[i];
+            if (i <= lane && row_ok) crow[i] = x[i];
         }
         if (it.symmetric) {
           // mirror: element (row, col0 + i) -> (col0 + i, row); lanes write consecutive floats
@@ -2456,6 +2460,7 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           for (int i = 0; i < 32; ++i) {
             const int mr = col0 + i;
             if (diag_sub && i >= lane) continue;  // strictly lower elements only
+            if (!row_ok || mr >= it.m) continue;
             const int mio = mr / it.c_iinner, mii = mr - mio * it.c_iinner;
             it.c[mio * it.c_sio + mii * it.c_sii + row] = x[i];
           }
@@ -2471,7 +2476,9 @@ tc_ggemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
 
 // ---- host ----
 static bool tc_gg_supported(const pc_gemm_desc& d) {
-  return d.m > 0 && d.n > 0 && d.k > 0 && d.m % 128 == 0 && d.n % 128 == 0 &&
+  // (any m; n % 4 == 0: the epilogue moves groups of four columns; edge tiles are zero-filled
+  // by the pack and masked by the epilogue)
+  return d.m > 0 && d.n > 0 && d.k > 0 && d.n % 4 == 0 &&
          (reinterpret_cast<uintptr_t>(d.c) % 16 == 0) && d.c_sii % 4 == 0 && d.c_sio % 4 == 0 &&
          (!d.c_in || (reinterpret_cast<uintptr_t>(d.c_in) % 16 == 0));
 }
@@ -2506,7 +2513,7 @@ static void tc_gg_plan(const pc_gemm_desc* descs, const pc_gemm_quant* quant, in
     oa.i_inner = d.a_iinner > 0 ? d.a_iinner : d.m; oa.k_inner = d.a_kinner > 0 ? d.a_kinner : d.k;
     oa.rows = d.m; oa.k = d.k; oa.kblocks = it.kblocks; oa.tile0 = pl->total_tiles;
     it.a_tile0 = oa.tile0;
-    pl->total_tiles += (d.m / 128) * it.kblocks;
+    pl->total_tiles += ((d.m + 127) / 128) * it.kblocks;
     pl->ops.push_back(oa);
     if (it.symmetric) {
       it.b_tile0 = it.a_tile0;
@@ -2521,12 +2528,12 @@ static void tc_gg_plan(const pc_gemm_desc* descs, const pc_gemm_quant* quant, in
         ob.q_ld = quant[z].b_ld; ob.q_dtype = quant[z].b_qdtype;
       }
       it.b_tile0 = ob.tile0;
-      pl->total_tiles += (d.n / 128) * it.kblocks;
+      pl->total_tiles += ((d.n + 127) / 128) * it.kblocks;
       pl->ops.push_back(ob);
     }
     pl->items.push_back(it);
-    for (int tm = 0; tm < d.m / 128; ++tm)
-      for (int tn = 0; tn < d.n / 128; ++tn)
+    for (int tm = 0; tm < (d.m + 127) / 128; ++tm)
+      for (int tn = 0; tn < (d.n + 127) / 128; ++tn)
         if (!it.symmetric || tn <= tm) pl->work.push_back(TcGgWork{z, tm, tn, 0});
   }
 }
@@ -2551,11 +2558,12 @@ int tc_grouped_gemm(const pc_gemm_desc* descs, const pc_gemm_quant* quant, int c
                     void* workspace, size_t workspace_bytes, int reuse_plan, cudaStream_t stream) {
   for (int z = 0; z < count; ++z) {
     PC_REQUIRE(tc_gg_supported(descs[z]),
-               "descriptor %d is not eligible for the tcgen05 grouped GEMM (m, n %% 128, alignment)", z);
+               "descriptor %d is not eligible for the tcgen05 grouped GEMM (n %% 4, alignment)", z);
     if (quant && (quant[z].q_in || quant[z].colmax_out)) {
-      PC_REQUIRE(tc_gg_symmetric(descs[z]) && descs[z].c_sii == descs[z].n && descs[z].c_sio == 0,
+      PC_REQUIRE(tc_gg_symmetric(descs[z]) && descs[z].c_sii == descs[z].n && descs[z].c_sio == 0 &&
+                     descs[z].m % 128 == 0,
                  "descriptor %d: fused (de)quantisation needs a symmetric product into a contiguous "
-                 "square matrix", z);
+                 "square matrix whose size is a multiple of 128", z);
       PC_REQUIRE(!quant[z].q_in || ((quant[z].qdtype == PC_QDTYPE_INT16 ||
                                     quant[z].qdtype == PC_QDTYPE_INT8) &&
                                    quant[z].diag_in && quant[z].bucket_in),
@@ -2622,7 +2630,7 @@ int tc_grouped_gemm(const pc_gemm_desc* descs, const pc_gemm_quant* quant, int c
   const int nops = (int)pl.ops.size();
   int max_tiles = 1;
   for (const TcGgOperand& o : pl.ops)
-    max_tiles = std::max(max_tiles, (o.rows / 128) * o.kblocks);
+    max_tiles = std::max(max_tiles, ((o.rows + 127) / 128) * o.kblocks);
   tc_pack_kernel<<<dim3((unsigned)std::min(max_tiles, 1024), nops), 256, 0, stream>>>(
       d_ops, d_inv, plane0, plane1, (reuse_plan & 3) == 3 ? 1 : 0);
   constexpr size_t smem = (size_t)TC_GG_STAGES * 4 * TC_TILE_BYTES + 1024 + 1024;

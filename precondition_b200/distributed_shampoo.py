@@ -1002,7 +1002,7 @@ class _Shampoo:
       # (pc_grouped_gemm_tc_quant); the requantisation is then a single pass.
       fused, fused_ext, rest = [], [], []
       for d, (sz, bi) in zip(stat_descs, stat_meta):
-        if not ops.tc_gemm_eligible(d):
+        if not ops.tc_gemm_fused_quant_eligible(d):
           rest.append(d)
           continue
         bk = self.buckets[sz]

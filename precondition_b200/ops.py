@@ -561,6 +561,7 @@ class SimtGemmLists:
     self.device = device
     self.groups = []   # (device descriptors, count, max_m, max_n)
     self.splitk = []   # (device descriptors, count, max_m, max_n, splits, workspace)
+    self.group_descs, self.splitk_descs = [], []  # host descriptors of each launch (diagnostics)
     classes, long_k = {}, []
 
     def tiles(x):
@@ -575,6 +576,7 @@ class SimtGemmLists:
     for lst in classes.values():
       self.groups.append((upload_gemm_descs(lst, device), len(lst),
                           max(d.m for d in lst), max(d.n for d in lst)))
+      self.group_descs.append(lst)
     if long_k:
       lib = _lib.load()
       mm, mn = max(d.m for d in long_k), max(d.n for d in long_k)
@@ -582,6 +584,7 @@ class SimtGemmLists:
       nbytes = lib.pc_grouped_gemm_splitk_workspace_bytes(len(long_k), mm, mn, splits)
       ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
       self.splitk.append((upload_gemm_descs(long_k, device), len(long_k), mm, mn, splits, ws))
+      self.splitk_descs.append(long_k)
 
   def __bool__(self):
     return bool(self.groups or self.splitk)
@@ -598,11 +601,28 @@ class SimtGemmLists:
       gpu_launches += 1
 
 
+# smallest ragged product (multiply-adds) that is sent to the tensor cores: below, zero-padding
+# the edge tiles to 128 costs more than the CUDA-core tile
+TC_RAGGED_MIN_MACS = 1 << 21
+
+
 def tc_gemm_eligible(d: _lib.GemmDesc) -> bool:
-  """Descriptor can run on the tcgen05 grouped GEMM (include/precond_b200.h)."""
-  return (d.m > 0 and d.n > 0 and d.k > 0 and d.m % 128 == 0 and d.n % 128 == 0 and
-          (d.c or 0) % 16 == 0 and d.c_sii % 4 == 0 and d.c_sio % 4 == 0 and
-          (d.c_in or 0) % 16 == 0)
+  """Descriptor can run on the tcgen05 grouped GEMM (include/precond_b200.h).  Output sizes that
+  are multiples of 128 always do; ragged blocks (1000 x 1000 statistics, 576-row kernels: edge
+  tiles zero-filled by the pack, masked by the epilogue) when they are large enough to pay."""
+  if not (d.m > 0 and d.n > 0 and d.k > 0 and (d.c or 0) % 16 == 0 and d.c_sii % 4 == 0 and
+          d.c_sio % 4 == 0 and (d.c_in or 0) % 16 == 0):
+    return False
+  if d.m % 128 == 0 and d.n % 128 == 0:
+    return True
+  return (d.n % 4 == 0 and d.m >= 64 and d.n >= 64 and
+          d.m * d.n * d.k >= TC_RAGGED_MIN_MACS)
+
+
+def tc_gemm_fused_quant_eligible(d: _lib.GemmDesc) -> bool:
+  """... and its (de)quantisation can be fused into the epilogue (pc_grouped_gemm_tc_quant):
+  whole 128 x 128 tiles only (16-byte reads of the quantised rows)."""
+  return tc_gemm_eligible(d) and d.m % 128 == 0 and d.n % 128 == 0
 
 
 class TcGemmList:

@@ -289,6 +289,104 @@ def test_tc_statistics_update_with_fused_quantisation(qdtype, levels):
     assert torch.equal(q2[0], qn[b]) and torch.equal(d2[0], dn[b]) and torch.equal(b2[0], bn[b])
 
 
+def test_tc_grouped_gemm_ragged_blocks():
+  """Output sizes that are no multiples of 128 on the tcgen05 grouped GEMM (edge tiles
+  zero-filled by the pack, masked by the epilogue) against float64: the 1000 x 1000 statistic
+  and both applications of a [1000, 1024] classifier block, a [576, 64] convolution block, and
+  a two-level (rank-3 unfolding) view with 200 rows.  Outputs sit inside sentinel-filled
+  buffers with a padded row stride: nothing outside the block may be written."""
+  if not _tc_ok():
+    pytest.skip("needs sm_100")
+  from precondition_b200 import _lib, ops
+  rng = np.random.default_rng(29)
+  D = _lib.GemmDesc
+  SENT = 7.25
+  keep, descs, checks = [], [], []
+
+  def dev(x):
+    t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+    keep.append(t)
+    return t
+
+  def out_buf(m, n, init=None):
+    ld = n + 8
+    buf = torch.full((m + 3, ld), SENT, dtype=torch.float32).cuda()
+    if init is not None:
+      buf[:m, :n] = torch.as_tensor(init.astype(np.float32)).cuda()
+    keep.append(buf)
+    return buf, ld
+
+  def gram(gt, rows, k, s_i, s_k, w1, w2, old):
+    buf, ld = out_buf(rows, rows, old)
+    d = D()
+    d.a = d.b = gt.data_ptr(); d.c = d.c_in = buf.data_ptr()
+    d.a_si = d.b_sj = s_i; d.a_iinner, d.a_sio = rows, 0
+    d.a_kinner = d.b_kinner = k; d.a_sko = d.b_sko = 0; d.a_ski = d.b_ski = s_k
+    d.c_iinner, d.c_sio, d.c_sii = rows, 0, ld
+    d.m = d.n = rows; d.k = k; d.alpha, d.beta = w2, w1
+    return d, buf
+
+  g = rng.standard_normal((1000, 1024)) * 0.3
+  gt = dev(g)
+  a = rng.standard_normal((1000, 1200)); old_l = a @ a.T / 1200
+  d, buf = gram(gt, 1000, 1024, 1024, 1, 0.9, 0.1, old_l)          # L = w1 L + w2 G G^T
+  descs.append(d); checks.append((buf, 1000, 1000, 0.9 * old_l + 0.1 * g @ g.T, True))
+  p_r = rng.standard_normal((1024, 1024)); p_rt = dev(p_r)
+  buf, ld = out_buf(1000, 1024)                                      # G P_R  (m = 1000)
+  d = D()
+  d.a = gt.data_ptr(); d.b = p_rt.data_ptr(); d.c = buf.data_ptr(); d.c_in = None
+  d.a_si = 1024; d.a_iinner, d.a_sio = 1000, 0; d.a_kinner, d.a_sko, d.a_ski = 1024, 0, 1
+  d.b_sj, d.b_kinner, d.b_sko, d.b_ski = 1, 1024, 0, 1024
+  d.c_iinner, d.c_sio, d.c_sii = 1000, 0, ld
+  d.m, d.n, d.k = 1000, 1024, 1024; d.alpha, d.beta = 1.0, 0.0
+  descs.append(d); checks.append((buf, 1000, 1024, g @ p_r, False))
+  p_l = rng.standard_normal((1000, 1000)); p_lt = dev(p_l)
+  buf, ld = out_buf(1024, 1000)                                      # G^T P_L  (n = k = 1000)
+  d = D()
+  d.a = gt.data_ptr(); d.b = p_lt.data_ptr(); d.c = buf.data_ptr(); d.c_in = None
+  d.a_si = 1; d.a_iinner, d.a_sio = 1024, 0; d.a_kinner, d.a_sko, d.a_ski = 1000, 0, 1024
+  d.b_sj, d.b_kinner, d.b_sko, d.b_ski = 1, 1000, 0, 1000
+  d.c_iinner, d.c_sio, d.c_sii = 1024, 0, ld
+  d.m, d.n, d.k = 1024, 1000, 1000; d.alpha, d.beta = 0.5, 0.0
+  descs.append(d); checks.append((buf, 1024, 1000, 0.5 * g.T @ p_l, False))
+  c = rng.standard_normal((576, 64)) * 1e-3
+  ct = dev(c)
+  d, buf = gram(ct, 576, 64, 64, 1, 0.0, 1.0, np.zeros((576, 576)))  # 576 = 4.5 tiles, k = 64
+  descs.append(d); checks.append((buf, 576, 576, c @ c.T, True))
+  p_c = rng.standard_normal((576, 576)); p_ct = dev(p_c)
+  buf, ld = out_buf(64, 576)                                         # C^T P  (m = 64)
+  d = D()
+  d.a = ct.data_ptr(); d.b = p_ct.data_ptr(); d.c = buf.data_ptr(); d.c_in = None
+  d.a_si = 1; d.a_iinner, d.a_sio = 64, 0; d.a_kinner, d.a_sko, d.a_ski = 576, 0, 64
+  d.b_sj, d.b_kinner, d.b_sko, d.b_ski = 1, 576, 0, 576
+  d.c_iinner, d.c_sio, d.c_sii = 64, 0, ld
+  d.m, d.n, d.k = 64, 576, 576; d.alpha, d.beta = 1.0, 0.0
+  descs.append(d); checks.append((buf, 64, 576, c.T @ p_c, False))
+  t3 = rng.standard_normal((3, 200, 136))
+  t3t = dev(t3)
+  buf, ld = out_buf(200, 200)     # Gram of the mode-1 unfolding: k = (slice, column), two-level
+  d = D()
+  d.a = d.b = t3t.data_ptr(); d.c = buf.data_ptr(); d.c_in = None
+  d.a_si = d.b_sj = 136; d.a_iinner, d.a_sio = 200, 0
+  d.a_kinner = d.b_kinner = 136; d.a_sko = d.b_sko = 200 * 136; d.a_ski = d.b_ski = 1
+  d.c_iinner, d.c_sio, d.c_sii = 200, 0, ld
+  d.m = d.n = 200; d.k = 3 * 136; d.alpha, d.beta = 1.0, 0.0
+  u = np.moveaxis(t3, 1, 0).reshape(200, -1)
+  descs.append(d); checks.append((buf, 200, 200, u @ u.T, True))
+  assert all(ops.tc_gemm_eligible(x) for x in descs)
+  lst = ops.TcGemmList(descs, gt.device)
+  lst.run()
+  torch.cuda.synchronize()
+  for buf, m, n, w, sym in checks:
+    got = buf.cpu().numpy()
+    ref = np.tril(w) + np.tril(w, -1).T if sym else w
+    err = np.abs(got[:m, :n] - ref).max() / np.abs(ref).max()
+    assert err <= 2e-6, (m, n, err)
+    if sym:
+      np.testing.assert_array_equal(got[:m, :n], got[:m, :n].T)
+    assert np.all(got[m:] == SENT) and np.all(got[:, n:] == SENT), (m, n)
+
+
 @pytest.mark.parametrize("qdtype", [torch.int16, torch.int8])
 def test_tc_apply_reads_quantised_preconditioner(qdtype):
   """pc_gemm_quant.b_q: out = G to_float(Q) and out = G to_float(Q)^T with the QuantizedValue
