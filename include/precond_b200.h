@@ -194,6 +194,20 @@ size_t pc_grouped_gemm_splitk_workspace_bytes(int count, int max_m, int max_n, i
 int pc_grouped_gemm_splitk(const pc_gemm_desc* descs, int count, int max_m, int max_n, int splits,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Thin products on CUDA cores, HBM-bound streaming kernels for the shapes a 64 x 64 tile wastes
+ * (same descriptors, DEVICE array, as pc_grouped_gemm; any sizes are computed correctly, the
+ * kinds say what each kernel is built for):
+ *   PC_THIN_GEMV    m <= 4: a rank-1 parameter times its preconditioner (DS:1707 on a [1, n]
+ *                   block) -- one CTA per 32 columns, the matrix is read once;
+ *   PC_THIN_ROWMAP  n <= 16 and k <= 16 over very many rows: the mode product of a [9, c, c]
+ *                   convolution kernel with its 9 x 9 preconditioner -- one thread per row.
+ * pc_grouped_gemm_splitk picks its thin form by itself when max_m, max_n <= 16 (the 9 x 9
+ * statistic of the same kernel, DS:1468-1470). */
+#define PC_THIN_GEMV 0
+#define PC_THIN_ROWMAP 1
+int pc_grouped_gemm_thin(const pc_gemm_desc* descs, int count, int max_m, int max_n, int kind,
+                         void* stream);
+
 /* tcgen05 path of the grouped GEMM (any m and k, n a multiple of 4; c / c_in 16-byte aligned with
  * c_sii, c_sio multiples of 4; edge tiles of sizes that are no multiples of 128 -- the 1000 x 1000
  * statistic of a classifier, 576-row convolution kernels -- are zero-filled when the operand is

@@ -19,6 +19,7 @@ PC_ENGINE_TC_SMALL = 5
 PC_TF_GRAFT_NONE, PC_TF_GRAFT_SGD, PC_TF_GRAFT_RMSPROP = 0, 1, 2
 PC_QDTYPE_F32, PC_QDTYPE_INT16, PC_QDTYPE_INT8, PC_QDTYPE_BF16 = 0, 1, 2, 3
 PC_NUM_METRICS = 5
+PC_THIN_GEMV, PC_THIN_ROWMAP = 0, 1
 PC_MAX_PEERS = 16
 PC_PEER_FLAG_WORDS = 2 * PC_MAX_PEERS + 16
 
@@ -36,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "pc_low_rank_root_workspace_bytes", "pc_low_rank_root_batched",
     "pc_inverse_pth_root_eigh_batched",
     "pc_grouped_gemm_tc_quant", "pc_quantize_from_colmax_batched",
-    "pc_grouped_gemm_splitk_workspace_bytes", "pc_grouped_gemm_splitk",
+    "pc_grouped_gemm_splitk_workspace_bytes", "pc_grouped_gemm_splitk", "pc_grouped_gemm_thin",
     "pc_graft_group_chunk_elems", "pc_graft_momentum_grouped_workspace_bytes",
     "pc_graft_momentum_grouped", "pc_inverse_pth_root_enqueue", "pc_root_mode",
     "pc_select_scatter", "pc_ipc_export", "pc_ipc_open", "pc_peer_all_gather", "pc_peer_release",
@@ -266,6 +267,8 @@ def load() -> ctypes.CDLL:
   lib.pc_grouped_gemm_splitk_workspace_bytes.restype = sz
   lib.pc_grouped_gemm_splitk.argtypes = [vp, i32, i32, i32, i32, vp, sz, vp]
   lib.pc_grouped_gemm_splitk.restype = i32
+  lib.pc_grouped_gemm_thin.argtypes = [vp, i32, i32, i32, i32, vp]
+  lib.pc_grouped_gemm_thin.restype = i32
   lib.pc_graft_group_chunk_elems.argtypes = []
   lib.pc_graft_group_chunk_elems.restype = i64
   lib.pc_graft_momentum_grouped_workspace_bytes.argtypes = [i32, i64]

@@ -34,6 +34,12 @@ struct OperandView {
     return __ldg(base + io * s_io + ii * s_i + ko * s_ko + ki * s_ki);
   }
   __device__ __forceinline__ bool k_fast() const { return s_ki == 1; }
+  // Two-level addressing whose outer stride continues the inner one (an unpartitioned
+  // contiguous tensor described axis by axis) is one-level addressing: drop the div / mod.
+  __device__ __forceinline__ void collapse() {
+    if (k_inner < k && s_ko == (int64_t)k_inner * s_ki) k_inner = 0x7fffffff;
+    if (i_inner < rows && s_io == (int64_t)i_inner * s_i) i_inner = 0x7fffffff;
+  }
 };
 
 // Masked square view used by the Newton chain: rows/cols >= limit read as 0.

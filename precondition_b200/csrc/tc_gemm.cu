@@ -2494,6 +2494,14 @@ struct TcGgPlan {
   int total_tiles = 0;
 };
 
+// Two-level addressing whose outer stride continues the inner one (an unpartitioned contiguous
+// tensor described axis by axis) is one-level addressing: the pack then takes its div / mod-free
+// path.
+static void tc_gg_collapse(TcGgOperand* o) {
+  if (o->k_inner < o->k && o->s_ko == (int64_t)o->k_inner * o->s_ki) o->k_inner = 0x7fffffff;
+  if (o->i_inner < o->rows && o->s_io == (int64_t)o->i_inner * o->s_i) o->i_inner = 0x7fffffff;
+}
+
 static void tc_gg_plan(const pc_gemm_desc* descs, const pc_gemm_quant* quant, int count,
                        TcGgPlan* pl) {
   for (int z = 0; z < count; ++z) {
@@ -2512,6 +2520,7 @@ static void tc_gg_plan(const pc_gemm_desc* descs, const pc_gemm_quant* quant, in
     oa.base = d.a; oa.s_io = d.a_sio; oa.s_i = d.a_si; oa.s_ko = d.a_sko; oa.s_ki = d.a_ski;
     oa.i_inner = d.a_iinner > 0 ? d.a_iinner : d.m; oa.k_inner = d.a_kinner > 0 ? d.a_kinner : d.k;
     oa.rows = d.m; oa.k = d.k; oa.kblocks = it.kblocks; oa.tile0 = pl->total_tiles;
+    tc_gg_collapse(&oa);
     it.a_tile0 = oa.tile0;
     pl->total_tiles += ((d.m + 127) / 128) * it.kblocks;
     pl->ops.push_back(oa);
@@ -2523,6 +2532,7 @@ static void tc_gg_plan(const pc_gemm_desc* descs, const pc_gemm_quant* quant, in
       ob.i_inner = d.n; ob.k_inner = d.b_kinner > 0 ? d.b_kinner : d.k;
       ob.rows = d.n; ob.k = d.k; ob.kblocks = it.kblocks; ob.tile0 = pl->total_tiles;
       ob.is_b = 1;
+      tc_gg_collapse(&ob);
       if (quant && quant[z].b_q) {
         ob.q = quant[z].b_q; ob.q_diag = quant[z].b_diag; ob.q_bucket = quant[z].b_bucket;
         ob.q_ld = quant[z].b_ld; ob.q_dtype = quant[z].b_qdtype;

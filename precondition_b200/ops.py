@@ -561,8 +561,10 @@ class SimtGemmLists:
     self.device = device
     self.groups = []   # (device descriptors, count, max_m, max_n)
     self.splitk = []   # (device descriptors, count, max_m, max_n, splits, workspace)
+    self.thin = []     # (device descriptors, count, max_m, max_n, kind): pc_grouped_gemm_thin
     self.group_descs, self.splitk_descs = [], []  # host descriptors of each launch (diagnostics)
-    classes, long_k = {}, []
+    self.thin_descs = []
+    classes, long_k, thin = {}, [], {}
 
     def tiles(x):
       t = (x + 63) // 64
@@ -571,29 +573,53 @@ class SimtGemmLists:
     for d in descs:
       if d.k >= self.SPLITK_MIN_K and tiles(d.m) * tiles(d.n) <= self.SPLITK_MAX_TILES:
         long_k.append(d)
+      elif d.m <= 4:  # a vector (rank-1 parameter) times a matrix: streaming kernel
+        thin.setdefault(_lib.PC_THIN_GEMV, []).append(d)
+      elif d.n <= 16 and d.k <= 16 and d.m >= 1024:  # mode product with a tiny preconditioner
+        thin.setdefault(_lib.PC_THIN_ROWMAP, []).append(d)
       else:
         classes.setdefault((tiles(d.m), tiles(d.n)), []).append(d)
     for lst in classes.values():
       self.groups.append((upload_gemm_descs(lst, device), len(lst),
                           max(d.m for d in lst), max(d.n for d in lst)))
       self.group_descs.append(lst)
+    for kind, lst in thin.items():
+      self.thin.append((upload_gemm_descs(lst, device), len(lst), max(d.m for d in lst),
+                        max(d.n for d in lst), kind))
+      self.thin_descs.append(lst)
+    # outputs of at most 16 x 16 (the 9 x 9 statistic of a 3 x 3 kernel) take the thin split-K
+    # kernel, which wants many short splits; the others go through the 64 x 64 tile kernel
+    for lk in ([d for d in long_k if d.m <= 16 and d.n <= 16],
+               [d for d in long_k if not (d.m <= 16 and d.n <= 16)]):
+      if lk:
+        self._add_splitk(lk, device)
+
+  def _add_splitk(self, long_k, device):
     if long_k:
       lib = _lib.load()
       mm, mn = max(d.m for d in long_k), max(d.n for d in long_k)
-      splits = max(1, min(64, min(d.k for d in long_k) // 2048, 65535 // len(long_k)))
+      if mm <= 16 and mn <= 16:
+        splits = max(1, min(256, min(d.k for d in long_k) // 1024, 65535 // len(long_k)))
+      else:
+        splits = max(1, min(64, min(d.k for d in long_k) // 2048, 65535 // len(long_k)))
       nbytes = lib.pc_grouped_gemm_splitk_workspace_bytes(len(long_k), mm, mn, splits)
       ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
       self.splitk.append((upload_gemm_descs(long_k, device), len(long_k), mm, mn, splits, ws))
       self.splitk_descs.append(long_k)
 
   def __bool__(self):
-    return bool(self.groups or self.splitk)
+    return bool(self.groups or self.splitk or self.thin)
 
   def run(self):
     global gpu_launches
     lib = _lib.load()
     for dev, count, mm, mn in self.groups:
       grouped_gemm(dev, count, mm, mn)
+    for dev, count, mm, mn, kind in self.thin:
+      with torch.cuda.device(self.device):
+        _lib.check(lib.pc_grouped_gemm_thin(_ptr(dev), count, mm, mn, kind,
+                                            ctypes.c_void_p(_stream())))
+      gpu_launches += 1
     for dev, count, mm, mn, splits, ws in self.splitk:
       with torch.cuda.device(self.device):
         _lib.check(lib.pc_grouped_gemm_splitk(_ptr(dev), count, mm, mn, splits, _ptr(ws),

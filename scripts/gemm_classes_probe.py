@@ -55,6 +55,12 @@ def show(tag, lists_tc, lists_simt):
       fl, by, top = describe(descs)
       print(f"{tag} simt      {count:4d} descs {t*1e3:8.1f} us  {fl/t/1e9:8.2f} TF/s "
             f"{by/t/1e6:8.1f} GB/s  {top}")
+    for (devd, count, mm, mn, kind), descs in zip(lists_simt.thin, lists_simt.thin_descs):
+      t = timed(lambda: ops._lib.load().pc_grouped_gemm_thin(
+          ops._ptr(devd), count, mm, mn, kind, __import__("ctypes").c_void_p(ops._stream())))
+      fl, by, top = describe(descs)
+      print(f"{tag} thin {kind}    {count:4d} descs {t*1e3:8.1f} us  {fl/t/1e9:8.2f} TF/s "
+            f"{by/t/1e6:8.1f} GB/s  {top}")
     for (devd, count, mm, mn, splits, ws), descs in zip(lists_simt.splitk, lists_simt.splitk_descs):
       t = timed(lambda: (ops._lib.load().pc_grouped_gemm_splitk(
           ops._ptr(devd), count, mm, mn, splits, ops._ptr(ws), ws.numel(),
@@ -67,3 +73,17 @@ def show(tag, lists_tc, lists_simt):
 show("stats  ", sh._stat_tc, sh._stat_simt)
 for j, (tc, simt) in enumerate(zip(sh._apply_tc, sh._apply_simt)):
   show(f"apply {j}", tc, simt)
+
+# kernel-level view of the CUDA-core lists (torch.profiler)
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+  for lst in [sh._stat_simt] + list(sh._apply_simt):
+    if lst is not None:
+      lst.run()
+  torch.cuda.synchronize()
+agg = {}
+for e in prof.events():
+  if e.device_type == torch.autograd.DeviceType.CUDA:
+    a = agg.setdefault(e.name[:60], [0, 0.0]); a[0] += 1; a[1] += e.time_range.end - e.time_range.start
+for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
+  print(f"  {k:60s} {v[0]:4d} {v[1]:9.1f} us")

@@ -442,6 +442,83 @@ def test_tc_apply_reads_quantised_preconditioner(qdtype):
     assert np.abs(got - ref).max() / np.abs(w).max() <= 1e-6
 
 
+def test_thin_products_gemv_rowmap_splitk():
+  """The streaming kernels behind ops.SimtGemmLists for shapes a 64 x 64 tile wastes, against
+  float64: vector x matrix (a rank-1 parameter times its preconditioner) with the matrix stored
+  j-fast and k-fast, up to 3 rows, odd sizes, beta * C_in; the [rows, 9] x [9, 9] mode product
+  of a 3 x 3 convolution kernel with packed and with padded output rows; thin split-K Grams
+  (9 x 9 and 16 x 16 over a long contraction, and a non-symmetric 9 x 7 product)."""
+  from precondition_b200 import _lib, ops
+  rng = np.random.default_rng(37)
+  D = _lib.GemmDesc
+  keep, descs, checks = [], [], []
+
+  def dev(x):
+    t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+    keep.append(t)
+    return t
+
+  def product(a, b, b_kfast, alpha=1.0, beta=0.0, c_ld=None, a_transposed=False):
+    """C[m, n] = alpha a[m, k] @ b[k, n] + beta C_in; b handed over as [k, n] (j-fast) or as
+    its transpose [n, k] (k-fast); a as [m, k] or stored transposed [k, m]."""
+    m, k = a.shape
+    n = b.shape[1]
+    at = dev(a.T if a_transposed else a)
+    bt = dev(b.T if b_kfast else b)
+    ld = c_ld or n
+    c0 = rng.standard_normal((m, ld))
+    ct = dev(c0)
+    d = D()
+    d.a = at.data_ptr(); d.b = bt.data_ptr(); d.c = ct.data_ptr()
+    d.c_in = ct.data_ptr() if beta != 0.0 else None
+    d.a_iinner, d.a_sio = m, 0
+    d.a_si, d.a_ski = (1, m) if a_transposed else (k, 1)
+    d.a_kinner, d.a_sko = k, 0
+    d.b_sj, d.b_ski = (k, 1) if b_kfast else (1, n)
+    d.b_kinner, d.b_sko = k, 0
+    d.c_iinner, d.c_sio, d.c_sii = m, 0, ld
+    d.m, d.n, d.k = m, n, k; d.alpha, d.beta = alpha, beta
+    want = c0.astype(np.float32).astype(np.float64).copy()
+    a64, b64 = a.astype(np.float32).astype(np.float64), b.astype(np.float32).astype(np.float64)
+    want[:, :n] = alpha * a64 @ b64 + beta * want[:, :n]
+    descs.append(d); checks.append((ct, want))
+
+  product(rng.standard_normal((1, 1024)), rng.standard_normal((1024, 1024)), False)
+  product(rng.standard_normal((1, 1000)), rng.standard_normal((1000, 1000)), True)
+  product(rng.standard_normal((3, 70)), rng.standard_normal((70, 100)), False, 0.5, 0.25)
+  product(rng.standard_normal((2, 333)), rng.standard_normal((333, 45)), True, 2.0, -1.0, c_ld=48)
+  product(rng.standard_normal((1, 64)), rng.standard_normal((64, 64)), False)
+  product(rng.standard_normal((5000, 9)), rng.standard_normal((9, 9)), False, a_transposed=True)
+  product(rng.standard_normal((3000, 9)), rng.standard_normal((9, 9)), True, 1.5, 0.5,
+          a_transposed=True)
+  product(rng.standard_normal((2049, 7)), rng.standard_normal((7, 12)), False, c_ld=16,
+          a_transposed=True)
+  product(rng.standard_normal((9, 70000)), rng.standard_normal((70000, 9)), True, 0.1, 0.9)
+  product(rng.standard_normal((16, 20000)), rng.standard_normal((20000, 16)), True)
+  product(rng.standard_normal((9, 33000)), rng.standard_normal((33000, 7)), False, c_ld=8)
+  lists = ops.SimtGemmLists(descs, keep[0].device)
+  kinds = sorted(t[4] for t in lists.thin)
+  assert kinds == [_lib.PC_THIN_GEMV, _lib.PC_THIN_ROWMAP] and not lists.groups
+  assert sum(t[1] for t in lists.thin) == 8 and sum(t[1] for t in lists.splitk) == 3
+  lists.run()
+  torch.cuda.synchronize()
+  first = [ct.clone() for ct, _ in checks]
+  for z, (ct, want) in enumerate(checks):
+    got = ct.cpu().numpy()
+    assert np.abs(got - want).max() / np.abs(want).max() <= 2e-5, z
+  # deterministic: the same inputs give the same bits (fixed-order sums, no atomics)
+  for (ct, want), d in zip(checks, descs):
+    if d.beta == 0.0:
+      ct.zero_()
+  lists2 = ops.SimtGemmLists([d for d in descs if d.beta == 0.0], keep[0].device)
+  lists2.run()
+  torch.cuda.synchronize()
+  for (ct, _), f, d in zip(checks, first, descs):
+    if d.beta == 0.0:
+      n = d.n
+      assert torch.equal(ct[:, :n], f[:, :n])
+
+
 def test_simt_lists_split_k_and_size_classes():
   """ops.SimtGemmLists: a 9 x 9 Gram over k = 40000 (split-K kernel, deterministic) next to a
   larger block and a tiny one (separate size classes) against float64."""
