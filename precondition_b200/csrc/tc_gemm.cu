@@ -2127,10 +2127,138 @@ __device__ __forceinline__ float tc_gg_scale(uint32_t maxbits) {
   return ldexpf(1.0f, sh);
 }
 
+// Element (i, kk) of an operand view, any addressing mode (zero outside the view); the
+// quantised form is to_float of a square QuantizedValue on the fly (QU:97-113).
+__device__ __forceinline__ float tc_pack_elem(const TcGgOperand& o, bool simple, int i, int kk) {
+  if (i >= o.rows || kk >= o.k) return 0.f;
+  if (o.q) {
+    // (a square matrix of up to 46340 rows: the offset fits 32 bits)
+    const uint32_t off = (uint32_t)((int64_t)i * o.s_i + (int64_t)kk * o.s_ki);
+    const uint32_t qr = off / (uint32_t)o.q_ld, qc = off - qr * (uint32_t)o.q_ld;
+    const float qv = o.q_dtype == PC_QDTYPE_INT16
+                         ? (float)reinterpret_cast<const int16_t*>(o.q)[off]
+                         : (float)reinterpret_cast<const int8_t*>(o.q)[off];
+    float v = qv * __ldg(o.q_bucket + qc);
+    if (qr == qc) v += __ldg(o.q_diag + qr);
+    return v;
+  }
+  if (simple) return __ldg(o.base + (int64_t)i * o.s_i + (int64_t)kk * o.s_ki);
+  return tc_gg_view(o, i, kk);
+}
+
+// Four consecutive elements along the view's fast axis at element offset `off` of the source
+// as one 16 / 8 / 4-byte load (fp32 / int16 / int8).  Quantised sources: the four are columns
+// col .. col+3 of one row of q; diag_at = position of the diagonal element among them or -1.
+// kSrc: 0 fp32, 1 int16, 2 int8 (a template parameter: no branch between the loads of a loop).
+template <int kSrc>
+__device__ __forceinline__ float4 tc_pack_load4(const TcGgOperand& o, int64_t off, bool ok,
+                                                int col, int diag_at, int diag_idx) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kSrc == 0) {
+    const float4* p = reinterpret_cast<const float4*>(o.base + off);
+    if (ok) v = __ldg(p);
+    return v;
+  }
+  if (kSrc == 1) {
+    const uint2* p = reinterpret_cast<const uint2*>(reinterpret_cast<const int16_t*>(o.q) + off);
+    uint2 w = make_uint2(0u, 0u);
+    if (ok) w = __ldg(p);
+    v = make_float4((float)(int16_t)(w.x & 0xffffu), (float)(int16_t)(w.x >> 16),
+                    (float)(int16_t)(w.y & 0xffffu), (float)(int16_t)(w.y >> 16));
+  } else {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(reinterpret_cast<const int8_t*>(o.q) + off);
+    uint32_t w = 0u;
+    if (ok) w = __ldg(p);
+    v = make_float4((float)(int8_t)(w & 0xffu), (float)(int8_t)((w >> 8) & 0xffu),
+                    (float)(int8_t)((w >> 16) & 0xffu), (float)(int8_t)(w >> 24));
+  }
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) b = __ldg(reinterpret_cast<const float4*>(o.q_bucket + col));
+  v.x *= b.x; v.y *= b.y; v.z *= b.z; v.w *= b.w;
+  if (ok && diag_at >= 0) {
+    const float dg = __ldg(o.q_diag + diag_idx);
+    if (diag_at == 0) v.x += dg;
+    else if (diag_at == 1) v.y += dg;
+    else if (diag_at == 2) v.z += dg;
+    else v.w += dg;
+  }
+  return v;
+}
+
+// two fp32 values -> the fp16 pair of plane 0 and the 2^11-scaled fp16 residual pair of plane 1
+__device__ __forceinline__ void tc_pack_split2(float v0, float v1, uint32_t& w0, uint32_t& w1) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w0) : "f"(v1), "f"(v0));
+  const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w1)
+      : "f"((v1 - f2.y) * TC_FP16_SCALE), "f"((v0 - f2.x) * TC_FP16_SCALE));
+}
+
+// Vector staging of one tile (modes 1 / 2 of tc_pack_kernel; the mode is a template parameter so
+// that the four loads of a half sit in one basic block and are all in flight together).
+template <int kMode, int kSrc>
+__device__ __forceinline__ uint32_t tc_pack_stage_vec(const TcGgOperand& o, bool simple, int tr,
+                                                      int kb, float (&tile)[64][129], int lane,
+                                                      int warp) {
+  uint32_t mx = 0;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float4 v[4];
+    bool ok[4];
+    int ri[4], ci[4];  // tile coordinates of element 0 of each group of four
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int s8 = half * 4 + s4;
+      if (kMode == 1) {
+        // four consecutive k per load; a warp instruction covers 4 rows x 32 k (128 B runs)
+        ri[s4] = 16 * warp + 4 * (s8 >> 1) + (lane >> 3);
+        ci[s4] = 4 * (lane & 7) + 32 * (s8 & 1);
+        const int i = tr * 128 + ri[s4], kk = kb * 64 + ci[s4];
+        ok[s4] = i < o.rows && kk + 3 < o.k;
+        // q row = i, columns kk .. kk+3; the diagonal is element i - kk of the four
+        const int da = (kSrc != 0 && i >= kk && i < kk + 4) ? i - kk : -1;
+        v[s4] = tc_pack_load4<kSrc>(o, (int64_t)i * o.s_i + kk, ok[s4], kk, da, i);
+      } else {
+        // four consecutive rows per load; a warp owns 8 k-columns, a warp instruction covers
+        // 8 k x (4 groups of 4 rows, 32 B apart)
+        ci[s4] = (lane & 7) + 8 * warp;
+        ri[s4] = 4 * (2 * (lane >> 3) + (s8 & 1) + 8 * (s8 >> 1));
+        const int i = tr * 128 + ri[s4], kk = kb * 64 + ci[s4];
+        ok[s4] = i + 3 < o.rows && kk < o.k;
+        // q row = kk, columns i .. i+3; the diagonal is element kk - i of the four
+        const int da = (kSrc != 0 && kk >= i && kk < i + 4) ? kk - i : -1;
+        v[s4] = tc_pack_load4<kSrc>(o, (int64_t)kk * o.s_ki + i, ok[s4], i, da, kk);
+      }
+    }
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int i = tr * 128 + ri[s4], kk = kb * 64 + ci[s4];
+      float x[4] = {v[s4].x, v[s4].y, v[s4].z, v[s4].w};
+      if (!ok[s4] && i < o.rows && kk < o.k) {  // the view's last, partial group of four
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          x[q4] = kMode == 1 ? tc_pack_elem(o, simple, i, kk + q4)
+                             : tc_pack_elem(o, simple, i + q4, kk);
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        if (kMode == 1) tile[ci[s4] + q4][ri[s4]] = x[q4];
+        else tile[ci[s4]][ri[s4] + q4] = x[q4];
+        const uint32_t ab = absbits(x[q4]);
+        mx = ab > mx ? ab : mx;
+      }
+    }
+  }
+  return mx;
+}
+
 // One CTA per 128 x 64 tile of an operand view: stage the tile in shared memory, reduce its
 // max |x|, then write the two fp16 planes scaled by the TILE's power of two (block floating
 // point; the GEMM multiplies each K-chunk by 1 / (sA sB) when it adds it in fp32).
-__global__ void __launch_bounds__(256)
+// One-level views whose fast axis is k (mode 1) or i (mode 2) with 16-byte aligned rows are read
+// with one vector load per four elements through lane mappings whose transposing shared-memory
+// stores are bank-conflict free; everything else (two-level views, unaligned sources) goes
+// element by element (mode 0).  The planes leave as 16-byte stores (8 k of one row per thread).
+__global__ void __launch_bounds__(256, 4)
 tc_pack_kernel(const TcGgOperand* __restrict__ ops, float* __restrict__ inv_scale,
                uint16_t* __restrict__ plane0, uint16_t* __restrict__ plane1, int skip_b) {
   __shared__ float tile[64][129];
@@ -2140,50 +2268,61 @@ tc_pack_kernel(const TcGgOperand* __restrict__ ops, float* __restrict__ inv_scal
   const int tiles = ((o.rows + 127) / 128) * o.kblocks;  // rows past the view are zero-filled
   const bool kfast = o.s_ki == 1;
   const bool simple = o.i_inner >= o.rows && o.k_inner >= o.k;  // one-level addressing
+  int mode = 0;
+  if (simple) {
+    const int64_t slow = kfast ? o.s_i : o.s_ki;
+    bool aligned;
+    if (!o.q) {
+      aligned = (slow & 3) == 0 && (reinterpret_cast<uintptr_t>(o.base) & 15) == 0;
+    } else {
+      // off = i * s_i + kk * s_ki addresses q: the slow stride must be q's row stride
+      const int es = o.q_dtype == PC_QDTYPE_INT16 ? 2 : 1;
+      aligned = slow == o.q_ld && (o.q_ld & 3) == 0 &&
+                (reinterpret_cast<uintptr_t>(o.q) & (4 * es - 1)) == 0 &&
+                (reinterpret_cast<uintptr_t>(o.q_bucket) & 15) == 0;
+    }
+    if (aligned && kfast && o.s_i != 1) mode = 1;
+    else if (aligned && o.s_i == 1 && !kfast) mode = 2;
+  }
+  const int src = !o.q ? 0 : (o.q_dtype == PC_QDTYPE_INT16 ? 1 : 2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int tr = t / o.kblocks, kb = t - tr * o.kblocks;
     uint32_t mx = 0;
     __syncthreads();
-    for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {  // coalesced along the fast axis
-      const int r = kfast ? e >> 6 : e & 127, c = kfast ? e & 63 : e >> 7;
-      const int i = tr * 128 + r, kk = kb * 64 + c;
-      float v;
-      if (o.q) {  // to_float of a quantised square matrix on the fly (QU:97-113)
-        v = 0.f;
-        if (kk < o.k && i < o.rows) {
-          // (a square matrix of up to 46340 rows: the offset fits 32 bits)
-          const uint32_t off = (uint32_t)((int64_t)i * o.s_i + (int64_t)kk * o.s_ki);
-          const uint32_t qr = off / (uint32_t)o.q_ld, qc = off - qr * (uint32_t)o.q_ld;
-          const float qv = o.q_dtype == PC_QDTYPE_INT16
-                               ? (float)reinterpret_cast<const int16_t*>(o.q)[off]
-                               : (float)reinterpret_cast<const int8_t*>(o.q)[off];
-          v = qv * __ldg(o.q_bucket + qc);
-          if (qr == qc) v += __ldg(o.q_diag + qr);
-        }
-      } else if (simple) {
-        v = (kk < o.k && i < o.rows)
-                ? __ldg(o.base + (int64_t)i * o.s_i + (int64_t)kk * o.s_ki) : 0.f;
-      } else {
-        v = tc_gg_view(o, i, kk);
+    if (mode == 1) {
+      mx = src == 0 ? tc_pack_stage_vec<1, 0>(o, simple, tr, kb, tile, lane, warp)
+         : src == 1 ? tc_pack_stage_vec<1, 1>(o, simple, tr, kb, tile, lane, warp)
+                    : tc_pack_stage_vec<1, 2>(o, simple, tr, kb, tile, lane, warp);
+    } else if (mode == 2) {
+      mx = src == 0 ? tc_pack_stage_vec<2, 0>(o, simple, tr, kb, tile, lane, warp)
+         : src == 1 ? tc_pack_stage_vec<2, 1>(o, simple, tr, kb, tile, lane, warp)
+                    : tc_pack_stage_vec<2, 2>(o, simple, tr, kb, tile, lane, warp);
+    } else {
+      for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {  // coalesced along the fast axis
+        const int r = kfast ? e >> 6 : e & 127, c = kfast ? e & 63 : e >> 7;
+        const float v = tc_pack_elem(o, simple, tr * 128 + r, kb * 64 + c);
+        tile[c][r] = v;
+        const uint32_t ab = absbits(v);
+        mx = ab > mx ? ab : mx;
       }
-      tile[c][r] = v;
-      const uint32_t ab = absbits(v);
-      mx = ab > mx ? ab : mx;
     }
     mx = block_max_u32(mx, red);  // (contains the barrier that publishes the tile)
     const float sc = tc_gg_scale(mx);
     if (threadIdx.x == 0) inv_scale[o.tile0 + t] = 1.0f / sc;
     const size_t base = (size_t)(o.tile0 + t) * 8192;
-    for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {  // two columns per thread
-      const int r = e >> 5, c = (e & 31) * 2;
-      const float v0 = tile[c][r] * sc, v1 = tile[c + 1][r] * sc;
-      uint32_t w0, w1;
-      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w0) : "f"(v1), "f"(v0));
-      const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
-      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w1)
-          : "f"((v1 - f2.y) * TC_FP16_SCALE), "f"((v0 - f2.x) * TC_FP16_SCALE));
-      reinterpret_cast<uint32_t*>(plane0 + base)[e] = w0;
-      reinterpret_cast<uint32_t*>(plane1 + base)[e] = w1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // eight k of one row per thread: one 16-byte store per plane
+      const int e = threadIdx.x + 256 * u;
+      const int r = e >> 3, c8 = (e & 7) * 8;
+      uint32_t w0[4], w1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        tc_pack_split2(tile[c8 + 2 * q][r] * sc, tile[c8 + 2 * q + 1][r] * sc, w0[q], w1[q]);
+      *reinterpret_cast<uint4*>(plane0 + base + (size_t)r * 64 + c8) =
+          make_uint4(w0[0], w0[1], w0[2], w0[3]);
+      *reinterpret_cast<uint4*>(plane1 + base + (size_t)r * 64 + c8) =
+          make_uint4(w1[0], w1[1], w1[2], w1[3]);
     }
   }
 }
