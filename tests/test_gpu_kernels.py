@@ -496,27 +496,53 @@ def test_thin_products_gemv_rowmap_splitk():
   product(rng.standard_normal((9, 70000)), rng.standard_normal((70000, 9)), True, 0.1, 0.9)
   product(rng.standard_normal((16, 20000)), rng.standard_normal((20000, 16)), True)
   product(rng.standard_normal((9, 33000)), rng.standard_normal((33000, 7)), False, c_ld=8)
+  # a [9, 150, 128] block inside a [9, 160, 140] tensor: genuinely two-level views (the generic
+  # addressing path of the thin kernels) -- the 9 x 9 statistic over k = (150, 128) and the mode
+  # product [19200, 9] x [9, 9] written back into a [160, 140, 9] tensor (two-level C rows)
+  big = rng.standard_normal((9, 160, 140))
+  bigt = dev(big)
+  blk = big[:, :150, :128].astype(np.float32).astype(np.float64)
+  st0 = rng.standard_normal((9, 9)); stt = dev(st0)
+  d = D()
+  d.a = d.b = bigt.data_ptr(); d.c = d.c_in = stt.data_ptr()
+  d.a_si = d.b_sj = 160 * 140; d.a_iinner, d.a_sio = 9, 0
+  d.a_kinner = d.b_kinner = 128; d.a_sko = d.b_sko = 140; d.a_ski = d.b_ski = 1
+  d.c_iinner, d.c_sio, d.c_sii = 9, 0, 9
+  d.m = d.n = 9; d.k = 150 * 128; d.alpha, d.beta = 0.25, 0.5
+  u = blk.reshape(9, -1)
+  descs.append(d)
+  checks.append((stt, 0.5 * st0.astype(np.float32).astype(np.float64) + 0.25 * u @ u.T))
+  p9 = rng.standard_normal((9, 9)); p9t = dev(p9)
+  out0 = rng.standard_normal((160, 140, 9)); outt = dev(out0)
+  d = D()
+  d.a = bigt.data_ptr(); d.b = p9t.data_ptr(); d.c = outt.data_ptr(); d.c_in = None
+  d.a_si, d.a_iinner, d.a_sio = 1, 128, 140       # row i = (r, c) of the block
+  d.a_kinner, d.a_sko, d.a_ski = 9, 0, 160 * 140  # k = slice
+  d.b_sj, d.b_kinner, d.b_sko, d.b_ski = 1, 9, 0, 9
+  d.c_iinner, d.c_sio, d.c_sii = 128, 140 * 9, 9
+  d.m, d.n, d.k = 150 * 128, 9, 9; d.alpha, d.beta = 1.0, 0.0
+  want = out0.astype(np.float32).astype(np.float64).copy()
+  want[:150, :128, :] = np.einsum("krc,kj->rcj", blk, p9.astype(np.float32).astype(np.float64))
+  descs.append(d); checks.append((outt, want))
   lists = ops.SimtGemmLists(descs, keep[0].device)
   kinds = sorted(t[4] for t in lists.thin)
   assert kinds == [_lib.PC_THIN_GEMV, _lib.PC_THIN_ROWMAP] and not lists.groups
-  assert sum(t[1] for t in lists.thin) == 8 and sum(t[1] for t in lists.splitk) == 3
+  assert sum(t[1] for t in lists.thin) == 9 and sum(t[1] for t in lists.splitk) == 4
+  start = [ct.clone() for ct, _ in checks]
   lists.run()
   torch.cuda.synchronize()
   first = [ct.clone() for ct, _ in checks]
   for z, (ct, want) in enumerate(checks):
     got = ct.cpu().numpy()
     assert np.abs(got - want).max() / np.abs(want).max() <= 2e-5, z
-  # deterministic: the same inputs give the same bits (fixed-order sums, no atomics)
-  for (ct, want), d in zip(checks, descs):
-    if d.beta == 0.0:
-      ct.zero_()
-  lists2 = ops.SimtGemmLists([d for d in descs if d.beta == 0.0], keep[0].device)
-  lists2.run()
+  # deterministic: the same launch list on the same inputs gives the same bits (fixed-order
+  # sums, no atomics)
+  for (ct, _), c0 in zip(checks, start):
+    ct.copy_(c0)
+  lists.run()
   torch.cuda.synchronize()
-  for (ct, _), f, d in zip(checks, first, descs):
-    if d.beta == 0.0:
-      n = d.n
-      assert torch.equal(ct[:, :n], f[:, :n])
+  for (ct, _), f in zip(checks, first):
+    assert torch.equal(ct, f)
 
 
 def test_simt_lists_split_k_and_size_classes():
