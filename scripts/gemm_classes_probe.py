@@ -87,3 +87,13 @@ for e in prof.events():
     a = agg.setdefault(e.name[:60], [0, 0.0]); a[0] += 1; a[1] += e.time_range.end - e.time_range.start
 for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
   print(f"  {k:60s} {v[0]:4d} {v[1]:9.1f} us")
+
+# rank-1 statistics updates (k = 1) vs the rest of the tcgen05 statistics list
+if sh._stat_tc is not None:
+  arr = list(sh._stat_tc.arr)[:sh._stat_tc.count]
+  for tag, sub in (("k == 1", [d for d in arr if d.k == 1]), ("k > 1", [d for d in arr if d.k > 1])):
+    if sub:
+      lst = ops.TcGemmList(sub, dev)
+      t = timed(lst.run)
+      fl, by, top = describe(sub)
+      print(f"stats tcgen05 {tag}: {len(sub)} descs {t*1e3:8.1f} us  {top}")
