@@ -201,10 +201,14 @@ int pc_grouped_gemm_splitk(const pc_gemm_desc* descs, int count, int max_m, int 
  *                   block) -- one CTA per 32 columns, the matrix is read once;
  *   PC_THIN_ROWMAP  n <= 16 and k <= 16 over very many rows: the mode product of a [9, c, c]
  *                   convolution kernel with its 9 x 9 preconditioner -- one thread per row.
+ *   PC_THIN_OUTER   k <= 4: the statistic of a rank-1
+ *                   parameter, S <- w1 S + w2 g g^T (DS:1468-1470 on a [n] block) -- a streaming
+ *                   pass over the output, bitwise symmetric for A == B and a symmetric C_in.
  * pc_grouped_gemm_splitk picks its thin form by itself when max_m, max_n <= 16 (the 9 x 9
  * statistic of the same kernel, DS:1468-1470). */
 #define PC_THIN_GEMV 0
 #define PC_THIN_ROWMAP 1
+#define PC_THIN_OUTER 2
 int pc_grouped_gemm_thin(const pc_gemm_desc* descs, int count, int max_m, int max_n, int kind,
                          void* stream);
 

@@ -19,7 +19,7 @@ PC_ENGINE_TC_SMALL = 5
 PC_TF_GRAFT_NONE, PC_TF_GRAFT_SGD, PC_TF_GRAFT_RMSPROP = 0, 1, 2
 PC_QDTYPE_F32, PC_QDTYPE_INT16, PC_QDTYPE_INT8, PC_QDTYPE_BF16 = 0, 1, 2, 3
 PC_NUM_METRICS = 5
-PC_THIN_GEMV, PC_THIN_ROWMAP = 0, 1
+PC_THIN_GEMV, PC_THIN_ROWMAP, PC_THIN_OUTER = 0, 1, 2
 PC_MAX_PEERS = 16
 PC_PEER_FLAG_WORDS = 2 * PC_MAX_PEERS + 16
 

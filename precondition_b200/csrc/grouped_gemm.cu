@@ -273,6 +273,104 @@ grouped_gemv_kernel(const pc_gemm_desc* __restrict__ descs) {
   }
 }
 
+// Products with a contraction of at most 4 (the statistic of a rank-1 parameter, DS:1468-1470 on
+// a [n] block: S <- w1 S + w2 g g^T): out(i, j) = alpha sum_k A(i, k) B(j, k) + beta C_in is a
+// streaming pass over the output.  One CTA per 16 rows; a thread owns 4 consecutive columns
+// (16-byte C_in loads / C stores when rows are aligned), B(j, :) stays in registers over the rows.
+// With A == B and a bitwise symmetric C_in the result is bitwise symmetric (a * b == b * a).
+template <bool kVec>
+__device__ __forceinline__ void outer_rows(const pc_gemm_desc& d, const OperandView& A,
+                                           const OperandView& B, int r0, float beta,
+                                           float (&as)[16][4]) {
+  const int c_iinner = d.c_iinner > 0 ? d.c_iinner : d.m;
+  // (a contraction longer than 4 is walked in chunks that accumulate into C: correct, not what
+  // the kernel is for)
+  for (int kc = 0; kc < d.k; kc += 4) {
+    __syncthreads();
+    if (threadIdx.x < 64)  // A(r0 .. r0+15, kc .. kc+3) of this CTA's rows (0 outside the view)
+      as[threadIdx.x >> 2][threadIdx.x & 3] = A(r0 + (threadIdx.x >> 2), kc + (threadIdx.x & 3));
+    __syncthreads();
+    for (int j = 4 * threadIdx.x; j < d.n; j += 4 * blockDim.x) {
+      float b[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) b[q][kk] = B(j + q, kc + kk);  // (0 outside the view)
+      const float* cin = kc == 0 ? d.c_in : d.c;
+      const float bw = kc == 0 ? beta : 1.0f;
+      const int rend = min(r0 + 16, d.m);
+      for (int i0 = r0; i0 < rend; i0 += 4) {  // four rows at a time: their C_in loads in flight
+        float4 o[4];
+        int64_t row[4];
+        bool ok[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int i = i0 + r;
+          ok[r] = i < rend;
+          const int io = i / c_iinner, ii = i - io * c_iinner;
+          row[r] = io * d.c_sio + ii * d.c_sii;
+          o[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kVec) {
+            const float4* p = reinterpret_cast<const float4*>(cin + row[r] + j);
+            if (cin && ok[r]) o[r] = *p;
+          } else if (cin && ok[r]) {
+            o[r].x = cin[row[r] + j];
+            if (j + 1 < d.n) o[r].y = cin[row[r] + j + 1];
+            if (j + 2 < d.n) o[r].z = cin[row[r] + j + 2];
+            if (j + 3 < d.n) o[r].w = cin[row[r] + j + 3];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float a[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) a[kk] = as[(i0 + r - r0) & 15][kk];
+          float v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float acc = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) acc = fmaf(a[kk], b[q][kk], acc);
+            v[q] = d.alpha * acc;
+          }
+          if (cin) {
+            v[0] = fmaf(bw, o[r].x, v[0]); v[1] = fmaf(bw, o[r].y, v[1]);
+            v[2] = fmaf(bw, o[r].z, v[2]); v[3] = fmaf(bw, o[r].w, v[3]);
+          }
+          if (!ok[r]) continue;
+          if (kVec) {
+            *reinterpret_cast<float4*>(d.c + row[r] + j) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (j + q < d.n) d.c[row[r] + j + q] = v[q];
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 3)
+grouped_outer_kernel(const pc_gemm_desc* __restrict__ descs) {
+  __shared__ float as[16][4];
+  const pc_gemm_desc d = descs[blockIdx.y];
+  const int r0 = blockIdx.x * 16;
+  if (r0 >= d.m) return;
+  OperandView A{d.a, d.a_sio, d.a_si, d.a_sko, d.a_ski, d.a_iinner > 0 ? d.a_iinner : d.m,
+                d.a_kinner > 0 ? d.a_kinner : d.k, d.m, d.k};
+  OperandView B{d.b, 0, d.b_sj, d.b_sko, d.b_ski, d.n > 0 ? d.n : 1,
+                d.b_kinner > 0 ? d.b_kinner : d.k, d.n, d.k};
+  A.collapse();
+  B.collapse();
+  const float beta = d.beta_dev ? __ldg(d.beta_dev) : d.beta;
+  const bool vec = (d.n & 3) == 0 && (d.c_sii & 3) == 0 && (d.c_sio & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d.c) & 15) == 0 &&
+                   (!d.c_in || (reinterpret_cast<uintptr_t>(d.c_in) & 15) == 0);
+  if (vec) outer_rows<true>(d, A, B, r0, beta, as);
+  else outer_rows<false>(d, A, B, r0, beta, as);
+}
+
 // Products with a tiny contraction AND a tiny output width (n, k <= 16) over very many rows:
 // the mode product of a [9, 512, 512] convolution kernel with its 9 x 9 preconditioner is a
 // [262144, 9] x [9, 9] product -- a streaming pass, one thread per row.  Larger n / k are
@@ -498,13 +596,17 @@ extern "C" int pc_grouped_gemm_splitk(const pc_gemm_desc* descs, int count, int 
 extern "C" int pc_grouped_gemm_thin(const pc_gemm_desc* descs, int count, int max_m, int max_n,
                                     int kind, void* stream) {
   PC_REQUIRE(count >= 0 && max_m >= 0 && max_n >= 0, "bad grouped gemm sizes");
-  PC_REQUIRE(kind == PC_THIN_GEMV || kind == PC_THIN_ROWMAP, "unknown thin product kind %d", kind);
+  PC_REQUIRE(kind == PC_THIN_GEMV || kind == PC_THIN_ROWMAP || kind == PC_THIN_OUTER,
+             "unknown thin product kind %d", kind);
   if (count == 0 || max_m == 0 || max_n == 0) return PC_OK;
   PC_REQUIRE(descs != nullptr, "null descriptor array");
   for (int z0 = 0; z0 < count; z0 += 65535) {
     const int nz = count - z0 < 65535 ? count - z0 : 65535;
     if (kind == PC_THIN_GEMV) {
       pc::grouped_gemv_kernel<<<dim3((max_n + 127) / 128, nz), 256, 0, (cudaStream_t)stream>>>(
+          descs + z0);
+    } else if (kind == PC_THIN_OUTER) {
+      pc::grouped_outer_kernel<<<dim3((max_m + 15) / 16, nz), 256, 0, (cudaStream_t)stream>>>(
           descs + z0);
     } else {
       const int bx = std::max(1, std::min((max_m + 255) / 256, 2048));

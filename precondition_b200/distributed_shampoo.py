@@ -987,8 +987,10 @@ class _Shampoo:
               bool(_lib.load().pc_device_supports_tcgen05()))
 
     def split(descs):
-      tc = [d for d in descs if use_tc and ops.tc_gemm_eligible(d)]
-      simt = [d for d in descs if not (use_tc and ops.tc_gemm_eligible(d))]
+      # (outer-product updates of rank-1 parameters stream through a CUDA-core kernel)
+      on_tc = lambda d: use_tc and ops.tc_gemm_eligible(d) and not ops.thin_outer_eligible(d)
+      tc = [d for d in descs if on_tc(d)]
+      simt = [d for d in descs if not on_tc(d)]
       return (ops.TcGemmList(tc, self.device) if tc else None,
               ops.SimtGemmLists(simt, self.device) if simt else None)
 

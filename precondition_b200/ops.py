@@ -573,6 +573,8 @@ class SimtGemmLists:
     for d in descs:
       if d.k >= self.SPLITK_MIN_K and tiles(d.m) * tiles(d.n) <= self.SPLITK_MAX_TILES:
         long_k.append(d)
+      elif thin_outer_eligible(d):  # statistic of a rank-1 parameter: streaming outer product
+        thin.setdefault(_lib.PC_THIN_OUTER, []).append(d)
       elif d.m <= 4:  # a vector (rank-1 parameter) times a matrix: streaming kernel
         thin.setdefault(_lib.PC_THIN_GEMV, []).append(d)
       elif d.n <= 16 and d.k <= 16 and d.m >= 1024:  # mode product with a tiny preconditioner
@@ -643,6 +645,12 @@ def tc_gemm_eligible(d: _lib.GemmDesc) -> bool:
     return True
   return (d.n % 4 == 0 and d.m >= 64 and d.n >= 64 and
           d.m * d.n * d.k >= TC_RAGGED_MIN_MACS)
+
+
+def thin_outer_eligible(d: _lib.GemmDesc) -> bool:
+  """Contraction of at most 4 into a large output (the statistic of a rank-1 parameter): a
+  streaming pass over the output (``PC_THIN_OUTER``) beats any tile kernel."""
+  return d.k <= 4 and d.m >= 64 and d.n >= 64
 
 
 def tc_gemm_fused_quant_eligible(d: _lib.GemmDesc) -> bool:

@@ -496,6 +496,25 @@ def test_thin_products_gemv_rowmap_splitk():
   product(rng.standard_normal((9, 70000)), rng.standard_normal((70000, 9)), True, 0.1, 0.9)
   product(rng.standard_normal((16, 20000)), rng.standard_normal((20000, 16)), True)
   product(rng.standard_normal((9, 33000)), rng.standard_normal((33000, 7)), False, c_ld=8)
+  # outer-product updates (k <= 4): the statistic of a 1024-vector (symmetric, beta * C_in),
+  # a non-symmetric k = 3 product with an odd width (scalar stores) and a padded row stride
+  gvec = rng.standard_normal((1024, 1)) * 0.1
+  gv = dev(gvec)
+  a0 = rng.standard_normal((1024, 1200)); s_old = a0 @ a0.T / 1200
+  s_old = (s_old + s_old.T) / 2  # bitwise symmetric, like a statistic of the optimizer
+  sv = dev(s_old)
+  d = D()
+  d.a = d.b = gv.data_ptr(); d.c = d.c_in = sv.data_ptr()
+  d.a_si = d.b_sj = 1; d.a_iinner, d.a_sio = 1024, 0
+  d.a_kinner = d.b_kinner = 1; d.a_sko = d.b_sko = 0; d.a_ski = d.b_ski = 1
+  d.c_iinner, d.c_sio, d.c_sii = 1024, 0, 1024
+  d.m = d.n = 1024; d.k = 1; d.alpha, d.beta = 0.05, 0.95
+  g64 = gvec.astype(np.float32).astype(np.float64)
+  descs.append(d)
+  checks.append((sv, 0.95 * s_old.astype(np.float32).astype(np.float64) + 0.05 * g64 @ g64.T))
+  sym_index = len(checks) - 1
+  product(rng.standard_normal((70, 3)), rng.standard_normal((3, 99)), False, 1.5, 0.5, c_ld=104)
+  product(rng.standard_normal((128, 4)), rng.standard_normal((4, 256)), True)
   # a [9, 150, 128] block inside a [9, 160, 140] tensor: genuinely two-level views (the generic
   # addressing path of the thin kernels) -- the 9 x 9 statistic over k = (150, 128) and the mode
   # product [19200, 9] x [9, 9] written back into a [160, 140, 9] tensor (two-level C rows)
@@ -526,8 +545,8 @@ def test_thin_products_gemv_rowmap_splitk():
   descs.append(d); checks.append((outt, want))
   lists = ops.SimtGemmLists(descs, keep[0].device)
   kinds = sorted(t[4] for t in lists.thin)
-  assert kinds == [_lib.PC_THIN_GEMV, _lib.PC_THIN_ROWMAP] and not lists.groups
-  assert sum(t[1] for t in lists.thin) == 9 and sum(t[1] for t in lists.splitk) == 4
+  assert kinds == [_lib.PC_THIN_GEMV, _lib.PC_THIN_ROWMAP, _lib.PC_THIN_OUTER] and not lists.groups
+  assert sum(t[1] for t in lists.thin) == 12 and sum(t[1] for t in lists.splitk) == 4
   start = [ct.clone() for ct, _ in checks]
   lists.run()
   torch.cuda.synchronize()
@@ -543,6 +562,8 @@ def test_thin_products_gemv_rowmap_splitk():
   torch.cuda.synchronize()
   for (ct, _), f in zip(checks, first):
     assert torch.equal(ct, f)
+  # the outer-product update of a symmetric statistic is bitwise symmetric
+  assert torch.equal(checks[sym_index][0], checks[sym_index][0].T)
 
 
 def test_simt_lists_split_k_and_size_classes():
