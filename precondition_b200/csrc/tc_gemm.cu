@@ -1967,6 +1967,59 @@ int tc_engine_iteration(TcEngine* e, const float* xs, RootCtl* ctl, uint32_t* er
   return PC_OK;
 }
 
+// Final gather of the scaled-fp16 engine (root_final_kernel's arithmetic, by plane tile): a
+// thread turns 8 consecutive elements of a tile row -- one 16-byte load per plane -- into two
+// 16-byte stores of the fp32 root (the generic kernel moves 2 + 2 + 4 bytes per thread and step
+// and divides a 64-bit index per element).
+__global__ void __launch_bounds__(256)
+root_final_tile_kernel(const RootCtl* __restrict__ ctl, PlaneStore ps, int n,
+                       float* __restrict__ roots, float* __restrict__ metrics) {
+  const int b = blockIdx.y;
+  const RootCtl& c = ctl[b];
+  float* out = roots + (size_t)b * n * n;
+  if (c.result_h != -1) {  // -1: already written by the n == 1 closed form
+    const bool zero = (c.result_h == -2) || (c.pad == 0) || !c.done;  // DS:930-937
+    const int tiles_j = n >> 6, tiles = (n >> 7) * tiles_j;
+    const float hmul = c.hmul;
+    const size_t mat = zero ? 0 : (size_t)(4 + c.result_h) * ps.buf_stride + (size_t)b * ps.mat_elems;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int ti = t / tiles_j, tj = t - ti * tiles_j;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = threadIdx.x + 256 * u;
+        const int r = e >> 3, g = (e & 7) * 8;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = 0.f;
+        if (!zero) {
+          const size_t off = mat + (size_t)t * 8192 + (size_t)r * 64 + g;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(ps.plane[0] + off);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(ps.plane[1] + off);
+          const uint32_t a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&a0[q]));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&a1[q]));
+            v[2 * q] = fmaf(x1.x, 1.0f / TC_FP16_SCALE, x0.x) * hmul;
+            v[2 * q + 1] = fmaf(x1.y, 1.0f / TC_FP16_SCALE, x0.y) * hmul;
+          }
+        }
+        float* o = out + (size_t)(ti * 128 + r) * n + tj * 64 + g;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float* m = metrics + (size_t)b * PC_NUM_METRICS;
+    m[PC_METRIC_ERROR] = c.pad == 0 ? 0.f : c.m_err;
+    m[PC_METRIC_ITERS] = c.m_iters;
+    m[PC_METRIC_ERROR_RATIO] = c.m_ratio;
+    m[PC_METRIC_MAX_EV] = c.max_ev;
+    m[PC_METRIC_RETRIES] = c.m_retries;
+  }
+}
+
 int tc_engine_final(TcEngine* e, const RootCtl* ctl, float* roots, float* metrics,
                     cudaStream_t stream) {
   auto* hs = static_cast<TcHostState*>(e->host_state);
@@ -1975,8 +2028,15 @@ int tc_engine_final(TcEngine* e, const RootCtl* ctl, float* roots, float* metric
   ps.fmt = hs->fmt;
   ps.buf_stride = hs->prm.buf_stride;
   ps.mat_elems = hs->prm.mat_stride;
-  dim3 fgrid((unsigned)std::min<size_t>(((size_t)e->n * e->n + 255) / 256, 64), e->batch);
-  root_final_kernel<PlaneStore><<<fgrid, 256, 0, stream>>>(ctl, ps, e->n, roots, metrics);
+  if (hs->fmt == TC_FMT_FP16S && e->n % 128 == 0 && ((uintptr_t)roots & 15) == 0 &&
+      e->batch <= 65535) {
+    const int tiles = (e->n / 128) * (e->n / 64);
+    root_final_tile_kernel<<<dim3((unsigned)std::min(tiles, 256), e->batch), 256, 0, stream>>>(
+        ctl, ps, e->n, roots, metrics);
+  } else {
+    dim3 fgrid((unsigned)std::min<size_t>(((size_t)e->n * e->n + 255) / 256, 64), e->batch);
+    root_final_kernel<PlaneStore><<<fgrid, 256, 0, stream>>>(ctl, ps, e->n, roots, metrics);
+  }
   PC_CUDA_CHECK(cudaGetLastError());
   delete hs;
   e->host_state = nullptr;
