@@ -207,3 +207,35 @@ def test_tearfree_chain_and_partition_specs():
   assert [tuple(s.shape) for s in blocks["stats"]] == [(2, 1024, 1024), (2, 512, 512)]
   assert tuple(graft_spec["norm"].acc["w"].shape) == (2048, 512)
   assert tuple(mom_spec.inner_state[0].trace["w"].shape) == (2048, 512)
+
+
+def test_grouped_gemm_routing_rules():
+  """Which kernel family a product descriptor is sent to (host-side rules, no GPU): multiples
+  of 128 and large ragged blocks with n % 4 == 0 -> tcgen05; fused (de)quantisation only for
+  whole 128 x 128 tiles; k <= 4 into a large output -> streaming outer product."""
+  from precondition_b200 import _lib, ops
+
+  def desc(m, n, k, c=0x1000, c_sii=None, c_sio=0, c_in=0):
+    d = _lib.GemmDesc()
+    d.m, d.n, d.k = m, n, k
+    d.c, d.c_in = c, c_in or None
+    d.c_sii, d.c_sio = (n if c_sii is None else c_sii), c_sio
+    return d
+
+  assert ops.tc_gemm_eligible(desc(1024, 1024, 256))
+  assert ops.tc_gemm_eligible(desc(128, 128, 1))              # multiples of 128: always
+  assert ops.tc_gemm_eligible(desc(1000, 1000, 1024))         # ragged, large, n % 4 == 0
+  assert ops.tc_gemm_eligible(desc(64, 576, 576))
+  assert ops.tc_gemm_eligible(desc(576, 576, 64))
+  assert not ops.tc_gemm_eligible(desc(147, 147, 64))         # n % 4 != 0
+  assert not ops.tc_gemm_eligible(desc(64, 64, 256))          # ragged and too small to pay
+  assert not ops.tc_gemm_eligible(desc(1000, 1000, 1))
+  assert not ops.tc_gemm_eligible(desc(1, 1024, 1024))        # a vector: the streaming kernel
+  assert not ops.tc_gemm_eligible(desc(1024, 1024, 256, c=0x1004))        # C not 16-byte aligned
+  assert not ops.tc_gemm_eligible(desc(1024, 1024, 256, c_sii=1026))      # row stride % 4 != 0
+  assert ops.tc_gemm_fused_quant_eligible(desc(2048, 2048, 1024))
+  assert not ops.tc_gemm_fused_quant_eligible(desc(1000, 1000, 1024))
+  assert ops.thin_outer_eligible(desc(1024, 1024, 1))
+  assert ops.thin_outer_eligible(desc(64, 64, 4))
+  assert not ops.thin_outer_eligible(desc(1024, 1024, 5))
+  assert not ops.thin_outer_eligible(desc(8, 8, 1))           # tiny blocks stay on the tile kernel
