@@ -1509,7 +1509,7 @@ __device__ __forceinline__ void split_fp16s(float v, uint16_t* hi, uint16_t* lo)
   *lo = __half_as_ushort(__float2half_rn((c - __half2float(h0)) * TC_FP16_SCALE));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 root_init_tile_kernel(const float* __restrict__ xs, RootCtl* ctl, PlaneStore bufs, int batch, int n,
                       int strips, RootParams prm, float* __restrict__ scratch) {
   __shared__ float tr[64][129];
@@ -1567,40 +1567,44 @@ root_init_tile_kernel(const float* __restrict__ xs, RootCtl* ctl, PlaneStore buf
     }
   }
   uint32_t emax = 0;
-  uint32_t m_hi[16], m_lo[16], mi_hi[16], mi_lo[16], h_hi[16], h_lo[16];
+  // eight columns at a time: split, then the six 16-byte stores of the chunk (keeps the packed
+  // words of only one chunk live: 3 CTAs per SM instead of 2)
 #pragma unroll
-  for (int k = 0; k < 32; k += 2) {
-    uint16_t w[2][6];
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t m_hi[4], m_lo[4], mi_hi[4], mi_lo[4], h_hi[4], h_lo[4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j = j0 + k + u;
-      float m0 = 0.f, mi0 = 0.f, h = 0.f;
-      if (i < pad && j < pad) {
-        float av = a[k + u];
-        if (i == j) av += eps;
-        m0 = av * z;  // DS:871
-        const uint32_t ab = absbits(m0 - (i == j ? 1.f : 0.f));
-        emax = ab > emax ? ab : emax;
-        mi0 = mi_from_m(m0, i == j, alpha, one_minus_alpha);
-        h = (i == j) ? hdiag : 0.f;
+    for (int kq = 0; kq < 4; ++kq) {
+      const int k = ch * 8 + 2 * kq;
+      uint16_t w[2][6];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = j0 + k + u;
+        float m0 = 0.f, mi0 = 0.f, h = 0.f;
+        if (i < pad && j < pad) {
+          float av = a[k + u];
+          if (i == j) av += eps;
+          m0 = av * z;  // DS:871
+          const uint32_t ab = absbits(m0 - (i == j ? 1.f : 0.f));
+          emax = ab > emax ? ab : emax;
+          mi0 = mi_from_m(m0, i == j, alpha, one_minus_alpha);
+          h = (i == j) ? hdiag : 0.f;
+        }
+        split_fp16s(m0, &w[u][0], &w[u][1]);
+        split_fp16s(mi0, &w[u][2], &w[u][3]);
+        split_fp16s(h, &w[u][4], &w[u][5]);
       }
-      split_fp16s(m0, &w[u][0], &w[u][1]);
-      split_fp16s(mi0, &w[u][2], &w[u][3]);
-      split_fp16s(h, &w[u][4], &w[u][5]);
+      m_hi[kq] = w[0][0] | ((uint32_t)w[1][0] << 16);  m_lo[kq] = w[0][1] | ((uint32_t)w[1][1] << 16);
+      mi_hi[kq] = w[0][2] | ((uint32_t)w[1][2] << 16); mi_lo[kq] = w[0][3] | ((uint32_t)w[1][3] << 16);
+      h_hi[kq] = w[0][4] | ((uint32_t)w[1][4] << 16);  h_lo[kq] = w[0][5] | ((uint32_t)w[1][5] << 16);
     }
-    const int q = k >> 1;
-    m_hi[q] = w[0][0] | ((uint32_t)w[1][0] << 16);  m_lo[q] = w[0][1] | ((uint32_t)w[1][1] << 16);
-    mi_hi[q] = w[0][2] | ((uint32_t)w[1][2] << 16); mi_lo[q] = w[0][3] | ((uint32_t)w[1][3] << 16);
-    h_hi[q] = w[0][4] | ((uint32_t)w[1][4] << 16);  h_lo[q] = w[0][5] | ((uint32_t)w[1][5] << 16);
+    auto put = [&](int phys, int plane, const uint32_t (&v)[4]) {
+      uint4* dst = reinterpret_cast<uint4*>(bufs.plane[plane] + bufs.elem(phys, b, i, j0, n));
+      dst[ch] = make_uint4(v[0], v[1], v[2], v[3]);
+    };
+    put(0, 0, m_hi); put(0, 1, m_lo);
+    put(2, 0, mi_hi); put(2, 1, mi_lo);
+    put(4, 0, h_hi); put(4, 1, h_lo);
   }
-  auto put = [&](int phys, int plane, const uint32_t (&v)[16]) {
-    uint4* dst = reinterpret_cast<uint4*>(bufs.plane[plane] + bufs.elem(phys, b, i, j0, n));
-#pragma unroll
-    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-  };
-  put(0, 0, m_hi); put(0, 1, m_lo);
-  put(2, 0, mi_hi); put(2, 1, mi_lo);
-  put(4, 0, h_hi); put(4, 1, h_lo);
   emax = block_max_u32(emax, ured);
   uint32_t* slots = reinterpret_cast<uint32_t*>(scratch + (size_t)batch * strips);
   if (threadIdx.x == 0) {
